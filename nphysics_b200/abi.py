@@ -1,0 +1,140 @@
+"""numpy / ctypes mirror of include/nphysics_b200.h (the C-ABI structs).
+
+Records travel as numpy structured arrays whose layout is checked against
+``nb2_sizeof`` when the library is loaded.  Field names are the header's.
+"""
+import ctypes
+
+import numpy as np
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+# nb2_error
+OK = 0
+ERR_INVALID_ARGUMENT = -1
+ERR_NO_DEVICE = -2
+ERR_CUDA = -3
+ERR_OUT_OF_MEMORY = -4
+ERR_BAD_INDEX = -5
+ERR_UNSUPPORTED = -6
+ERR_TOO_MANY_COLOURS = -7
+ERR_NOT_READY = -8
+ERR_NON_FINITE = -9
+
+# nb2_body_status
+BODY_DISABLED, BODY_STATIC, BODY_DYNAMIC, BODY_KINEMATIC = 0, 1, 2, 3
+BODY_FLAG_GRAVITY = 1
+
+# nb2_kinematic_geom
+GEOM_POINT, GEOM_LINE, GEOM_PLANE = 0, 1, 2
+
+# nb2_joint_type
+(JOINT_BALL, JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_UNIVERSAL, JOINT_PLANAR, JOINT_RECTANGULAR,
+ JOINT_PIN_SLOT, JOINT_CYLINDRICAL, JOINT_FIXED, JOINT_CARTESIAN) = range(10)
+JOINT_FLAG_MIN_OFFSET, JOINT_FLAG_MAX_OFFSET = 1, 2
+
+# nb2_step_mode
+MODE_REFERENCE_ORDER, MODE_COLOURED = 0, 1
+
+f4, u4, i4, u8, u1 = np.float32, np.uint32, np.int32, np.uint64, np.uint8
+
+params_dtype = np.dtype([
+    ("dt", f4), ("erp", f4), ("warmstart_coeff", f4), ("restitution_velocity_threshold", f4),
+    ("allowed_linear_error", f4), ("allowed_angular_error", f4), ("max_linear_correction", f4),
+    ("max_angular_correction", f4), ("max_stabilization_multiplier", f4),
+    ("max_velocity_iterations", u4), ("max_position_iterations", u4),
+    ("max_ccd_position_iterations", u4), ("max_ccd_substeps", u4), ("gravity", f4, 3)], align=True)
+
+body_dtype = np.dtype([
+    ("position", f4, 7), ("velocity", f4, 6), ("local_com", f4, 3), ("mass", f4),
+    ("local_inertia", f4, 9), ("external_forces", f4, 6), ("linear_damping", f4),
+    ("angular_damping", f4), ("max_linear_velocity", f4), ("max_angular_velocity", f4),
+    ("jacobian_mask", f4, 6), ("status", u4), ("flags", u4)], align=True)
+
+body_state_dtype = np.dtype([("position", f4, 7), ("velocity", f4, 6)], align=True)
+
+manifold_dtype = np.dtype([
+    ("body1", i4), ("body2", i4), ("first_contact", u4), ("num_contacts", u4), ("margin1", f4),
+    ("margin2", f4), ("friction", f4), ("restitution", f4), ("surface_velocity", f4, 3),
+    ("coll1_wrt_body", f4, 7), ("coll2_wrt_body", f4, 7)], align=True)
+
+contact_dtype = np.dtype([
+    ("world1", f4, 3), ("world2", f4, 3), ("normal", f4, 3), ("depth", f4), ("key", u8),
+    ("local1", f4, 3), ("local2", f4, 3), ("dir1", f4, 3), ("dir2", f4, 3), ("dilation1", f4),
+    ("dilation2", f4), ("geom1", u1), ("geom2", u1), ("pad_", u1, 6)], align=True)
+
+joint_dtype = np.dtype([
+    ("type", u4), ("body1", i4), ("body2", i4), ("flags", u4), ("anchor1", f4, 3), ("anchor2", f4, 3),
+    ("axis1", f4, 3), ("axis2", f4, 3), ("axis3", f4, 3), ("ref_frame1", f4, 4), ("ref_frame2", f4, 4),
+    ("angle", f4), ("min_offset", f4), ("max_offset", f4), ("break_force_squared", f4),
+    ("break_torque_squared", f4), ("impulses", f4, 7), ("broken", u4)], align=True)
+
+stats_dtype = np.dtype([
+    ("n_bodies", u4), ("n_dynamic_bodies", u4), ("n_manifolds", u4), ("n_contacts", u4), ("n_joints", u4),
+    ("n_rows_two_body", u4), ("n_rows_ground", u4), ("n_phases_velocity", u4), ("n_phases_position", u4),
+    ("n_broken_joints", u4), ("non_finite", u4), ("pad_", u4), ("residual_max", f4), ("residual_rms", f4),
+    ("max_penetration", f4), ("kinetic_energy", f4), ("t_assembly_ms", f4),
+    ("t_velocity_resolution_ms", f4), ("t_velocity_update_ms", f4), ("t_position_resolution_ms", f4),
+    ("t_step_ms", f4), ("pad2_", f4)], align=True)
+
+# index used by nb2_sizeof(which)
+SIZEOF_ORDER = [params_dtype, body_dtype, body_state_dtype, manifold_dtype, contact_dtype, joint_dtype,
+                stats_dtype]
+EXPECTED_SIZES = [64, 176, 52, 100, 112, 160, 88]
+
+for _d, _s in zip(SIZEOF_ORDER, EXPECTED_SIZES):
+    assert _d.itemsize == _s, (_d, _d.itemsize, _s)
+
+
+def ptr(arr):
+    """void* to a C-contiguous numpy array (or None)."""
+    if arr is None:
+        return None
+    assert arr.flags["C_CONTIGUOUS"]
+    return arr.ctypes.data_as(ctypes.c_void_p)
+
+
+def default_params():
+    """IntegrationParameters::default() (integration_parameters.rs:169-189) + gravity of the
+    examples (examples3d/pyramid3.rs:21)."""
+    p = np.zeros((), dtype=params_dtype)
+    p["dt"] = 1.0 / 60.0
+    p["erp"] = 0.2
+    p["warmstart_coeff"] = 1.0
+    p["restitution_velocity_threshold"] = 1.0
+    p["allowed_linear_error"] = 0.001
+    p["allowed_angular_error"] = 0.001
+    p["max_linear_correction"] = 0.2
+    p["max_angular_correction"] = 0.2
+    p["max_stabilization_multiplier"] = 0.2
+    p["max_velocity_iterations"] = 8
+    p["max_position_iterations"] = 3
+    p["max_ccd_position_iterations"] = 10
+    p["max_ccd_substeps"] = 1
+    p["gravity"] = (0.0, -9.81, 0.0)
+    return p
+
+
+def new_bodies(n):
+    """n zeroed body records with the RigidBody::new defaults (rigid_body.rs:55-85)."""
+    b = np.zeros(n, dtype=body_dtype)
+    b["position"][:, 6] = 1.0
+    b["max_linear_velocity"] = FLT_MAX
+    b["max_angular_velocity"] = FLT_MAX
+    b["jacobian_mask"] = 1.0
+    b["status"] = BODY_DYNAMIC
+    b["flags"] = BODY_FLAG_GRAVITY
+    return b
+
+
+def new_joints(n, jtype=JOINT_BALL):
+    j = np.zeros(n, dtype=joint_dtype)
+    j["type"] = jtype
+    j["ref_frame1"][:, 3] = 1.0
+    j["ref_frame2"][:, 3] = 1.0
+    j["axis1"][:, 0] = 1.0
+    j["axis2"][:, 0] = 1.0
+    j["axis3"][:, 0] = 1.0
+    j["break_force_squared"] = FLT_MAX
+    j["break_torque_squared"] = FLT_MAX
+    return j

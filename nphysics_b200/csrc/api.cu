@@ -1,0 +1,505 @@
+// The extern "C" boundary (include/nphysics_b200.h) and the step orchestration.
+//
+// nb2_step replaces MoreauJeanSolver::step (src/solver/moreau_jean_solver.rs:47-90) together with
+// the per-body work MechanicalWorld::step does around it (update_dynamics / update_acceleration
+// before, kinematic integration after: src/world/mechanical_world.rs:230-243, 328-346).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+
+#include "solver.cuh"
+
+namespace nb2 {
+
+static thread_local char g_thread_error[512] = "";
+
+int set_error(Context* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        strncpy(ctx->last_error, buf, sizeof(ctx->last_error) - 1);
+        ctx->last_error[sizeof(ctx->last_error) - 1] = 0;
+    }
+    strncpy(g_thread_error, buf, sizeof(g_thread_error) - 1);
+    g_thread_error[sizeof(g_thread_error) - 1] = 0;
+    return code;
+}
+
+static void release_all(Context* c) {
+    c->raw.release(); c->pos_t.release(); c->pos_q.release(); c->vel.release(); c->com_im.release();
+    c->inv_i.release(); c->ext.release(); c->lam.release(); c->b_status.release(); c->joints.release();
+    c->manifolds.release(); c->contacts.release(); c->c_manifold.release(); c->chunk_base.release();
+    c->chunk_manifold.release();
+    for (int k = 0; k < 2; ++k) {
+        c->imp[k].release();
+        c->ht_keys[k].release();
+        c->ht_vals[k].release();
+    }
+    c->vs.release(); c->ps.release(); c->deg.release(); c->adj_off.release(); c->cursor.release();
+    c->adj.release(); c->pred_a.release(); c->pred_b.release(); c->level.release(); c->adj_off_p.release();
+    c->adj_p.release(); c->cmask.release(); c->best.release(); c->scan_tmp.release(); c->barrier.release();
+    c->r_jac.release(); c->r_hdr.release(); c->r_meta.release(); c->r_imp.release(); c->p_row.release();
+    c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
+}
+
+static int check_flags(Context* ctx) {
+    // input-validation bits + schedule overflow, read after a synchronisation point
+    unsigned int f = 0;
+    if (ctx->flags.p) {
+        NB2_CUDA(ctx, cudaMemcpyAsync(&f, ctx->flags.p, sizeof(f), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SchedHeader hv, hp;
+    memset(&hv, 0, sizeof(hv));
+    memset(&hp, 0, sizeof(hp));
+    if (ctx->stepped && ctx->vs.hdr.p)
+        NB2_CUDA(ctx, cudaMemcpyAsync(&hv, ctx->vs.hdr.p, sizeof(hv), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->stepped && ctx->last_mode == NB2_MODE_REFERENCE_ORDER && ctx->ps.hdr.p)
+        NB2_CUDA(ctx, cudaMemcpyAsync(&hp, ctx->ps.hdr.p, sizeof(hp), cudaMemcpyDeviceToHost, ctx->stream));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->last_stats.n_phases_velocity = hv.n_phases;
+    ctx->last_stats.n_phases_position = ctx->last_mode == NB2_MODE_REFERENCE_ORDER ? hp.n_phases : hv.n_phases;
+    if (f & 1u) return set_error(ctx, NB2_ERR_BAD_INDEX, "a manifold/joint record referenced a body or contact out of range");
+    if (f & 2u) return set_error(ctx, NB2_ERR_UNSUPPORTED, "a manifold/joint connects a body to itself (unsupported)");
+    if ((hv.overflow | hp.overflow) & 1u)
+        return set_error(ctx, NB2_ERR_TOO_MANY_COLOURS, "colouring needs more than %d colours", NB2_MAX_COLOURS);
+    if ((hv.overflow | hp.overflow) & 2u) return set_error(ctx, NB2_ERR_CUDA, "internal: phase index overflow");
+    return NB2_OK;
+}
+
+static int do_step(Context* ctx, int mode) {
+    const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
+    ctx->cur = 1 - ctx->cur;
+    const bool tm = ctx->timers;
+    if (tm && !ctx->ev.created) {
+        for (int k = 0; k < 6; ++k) NB2_CUDA(ctx, cudaEventCreate(&ctx->ev.e[k]));
+        ctx->ev.created = true;
+    }
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[0], ctx->stream));
+    // ---- dynamics refresh + assembly (Counters: "assembly")
+    NB2_TRY(launch_refresh_dynamics(ctx));
+    ctx->max_chunks = (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
+    NB2_TRY(launch_build_items(ctx, mode));
+    NB2_TRY(launch_schedule(ctx, &ctx->vs, mode));
+    if (ref) NB2_TRY(launch_schedule(ctx, &ctx->ps, mode));
+    NB2_TRY(launch_assemble(ctx, mode));
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[1], ctx->stream));
+    // ---- velocity resolution + impulse caching (Counters: "velocity resolution")
+    NB2_TRY(launch_velocity_solve(ctx, mode));
+    NB2_TRY(launch_cache_impulses(ctx, mode));
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[2], ctx->stream));
+    // ---- velocity update + integration (Counters: "velocity update")
+    NB2_TRY(launch_integrate(ctx, false));
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[3], ctx->stream));
+    // ---- position resolution
+    NB2_TRY(launch_position_solve(ctx, mode));
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[4], ctx->stream));
+    // ---- kinematic bodies (mechanical_world.rs:328-332)
+    NB2_TRY(launch_integrate(ctx, true));
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[5], ctx->stream));
+    ctx->ev_valid = tm;
+    ctx->last_mode = mode;
+    ctx->stepped = true;
+    return NB2_OK;
+}
+
+}  // namespace nb2
+
+using namespace nb2;
+
+#define NB2_CHECK_CTX(ctx)                                   \
+    do {                                                     \
+        if (!(ctx)) return set_error(nullptr, NB2_ERR_INVALID_ARGUMENT, "null context"); \
+    } while (0)
+
+struct nb2_context {
+    Context c;
+};
+
+extern "C" {
+
+int nb2_abi_version(void) { return NB2_ABI_VERSION; }
+
+const char* nb2_error_string(int err) {
+    switch (err) {
+        case NB2_OK: return "ok";
+        case NB2_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case NB2_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+        case NB2_ERR_CUDA: return "CUDA error";
+        case NB2_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case NB2_ERR_BAD_INDEX: return "record index out of range";
+        case NB2_ERR_UNSUPPORTED: return "unsupported input";
+        case NB2_ERR_TOO_MANY_COLOURS: return "too many colours";
+        case NB2_ERR_NOT_READY: return "bodies/params not uploaded";
+        case NB2_ERR_NON_FINITE: return "non-finite body state";
+        default: return "unknown error";
+    }
+}
+
+int nb2_default_params(nb2_params* p) {
+    if (!p) return NB2_ERR_INVALID_ARGUMENT;
+    memset(p, 0, sizeof(*p));
+    p->dt = 1.0f / 60.0f;
+    p->erp = 0.2f;
+    p->warmstart_coeff = 1.0f;
+    p->restitution_velocity_threshold = 1.0f;
+    p->allowed_linear_error = 0.001f;
+    p->allowed_angular_error = 0.001f;
+    p->max_linear_correction = 0.2f;
+    p->max_angular_correction = 0.2f;
+    p->max_stabilization_multiplier = 0.2f;
+    p->max_velocity_iterations = 8;
+    p->max_position_iterations = 3;
+    p->max_ccd_position_iterations = 10;
+    p->max_ccd_substeps = 1;
+    p->gravity[0] = 0.f;
+    p->gravity[1] = -9.81f;
+    p->gravity[2] = 0.f;
+    return NB2_OK;
+}
+
+int nb2_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(nb2_params);
+        case 1: return (int)sizeof(nb2_body);
+        case 2: return (int)sizeof(nb2_body_state);
+        case 3: return (int)sizeof(nb2_manifold);
+        case 4: return (int)sizeof(nb2_contact);
+        case 5: return (int)sizeof(nb2_joint);
+        case 6: return (int)sizeof(nb2_stats);
+        default: return NB2_ERR_INVALID_ARGUMENT;
+    }
+}
+
+// MaterialCombineMode::combine (src/material/material.rs:72-86): precedence Max > Multiply > Min > Average.
+static float combine_coeff(float a, int ma, float b, int mb) {
+    if (ma == 3 || mb == 3) return a > b ? a : b;
+    if (ma == 2 || mb == 2) return a * b;
+    if (ma == 1 || mb == 1) return a < b ? a : b;
+    return (a + b) * 0.5f;
+}
+int nb2_combine_materials(float friction1, int friction_mode1, float restitution1, int restitution_mode1,
+                          const float* sv1, float friction2, int friction_mode2, float restitution2,
+                          int restitution_mode2, const float* sv2, float* out_friction, float* out_restitution,
+                          float* out_sv) {
+    if (!out_friction || !out_restitution || !out_sv) return NB2_ERR_INVALID_ARGUMENT;
+    *out_restitution = combine_coeff(restitution1, restitution_mode1, restitution2, restitution_mode2);
+    *out_friction = combine_coeff(friction1, friction_mode1, friction2, friction_mode2);
+    for (int k = 0; k < 3; ++k) out_sv[k] = (sv1 ? sv1[k] : 0.f) - (sv2 ? sv2[k] : 0.f);  // material.rs:174
+    return NB2_OK;
+}
+
+const char* nb2_last_error(const nb2_context* ctx) { return ctx ? ctx->c.last_error : g_thread_error; }
+
+int nb2_create(int device, void* stream, nb2_context** out) {
+    if (!out) return set_error(nullptr, NB2_ERR_INVALID_ARGUMENT, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_error(nullptr, NB2_ERR_NO_DEVICE, "no CUDA device: %s (this library has no CPU fallback)",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return set_error(nullptr, NB2_ERR_INVALID_ARGUMENT, "bad device ordinal %d", device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return set_error(nullptr, NB2_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return set_error(nullptr, NB2_ERR_NO_DEVICE, "device %d is sm_%d%d; this build carries sm_100a code only", device,
+                         prop.major, prop.minor);
+    if (!prop.cooperativeLaunch) return set_error(nullptr, NB2_ERR_NO_DEVICE, "device lacks cooperative launch");
+    nb2_context* h = new (std::nothrow) nb2_context();
+    if (!h) return set_error(nullptr, NB2_ERR_OUT_OF_MEMORY, "host allocation failed");
+    Context* ctx = &h->c;
+    ctx->last_error[0] = 0;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    memset(&ctx->last_stats, 0, sizeof(ctx->last_stats));
+    nb2_default_params(&ctx->params);
+    ctx->inv_dt = 1.0f / ctx->params.dt;
+    ctx->have_params = true;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete h;
+        return set_error(nullptr, NB2_ERR_CUDA, "cudaSetDevice failed");
+    }
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+        ctx->own_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete h;
+            return set_error(nullptr, NB2_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        ctx->own_stream = true;
+    }
+    int rc = ctx->flags.reserve(ctx, 4);
+    if (rc == NB2_OK) rc = ctx->barrier.reserve(ctx, 8);
+    if (rc == NB2_OK && cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(unsigned int), ctx->stream) != cudaSuccess)
+        rc = NB2_ERR_CUDA;
+    if (rc != NB2_OK) {
+        release_all(ctx);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return NB2_OK;
+}
+
+int nb2_destroy(nb2_context* h) {
+    if (!h) return NB2_OK;
+    Context* ctx = &h->c;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    release_all(ctx);
+    if (ctx->ev.created)
+        for (int k = 0; k < 6; ++k) cudaEventDestroy(ctx->ev.e[k]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete h;
+    return NB2_OK;
+}
+
+int nb2_set_params(nb2_context* h, const nb2_params* p) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!p) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null params");
+    if (!(p->dt >= 0.f)) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "The time-stepping length cannot be negative.");
+    ctx->params = *p;
+    ctx->inv_dt = p->dt == 0.f ? 0.f : 1.0f / p->dt;  // integration_parameters.rs:141-153
+    ctx->have_params = true;
+    return NB2_OK;
+}
+
+int nb2_get_params(const nb2_context* h, nb2_params* out) {
+    if (!h || !out) return NB2_ERR_INVALID_ARGUMENT;
+    *out = h->c.params;
+    return NB2_OK;
+}
+
+int nb2_enable_timers(nb2_context* h, int enabled) {
+    NB2_CHECK_CTX(h);
+    h->c.timers = enabled != 0;
+    return NB2_OK;
+}
+
+int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!bodies || n == 0) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "empty body set");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // buffers may be reallocated
+    NB2_TRY(ctx->raw.reserve(ctx, n));
+    NB2_TRY(ctx->pos_t.reserve(ctx, n));
+    NB2_TRY(ctx->pos_q.reserve(ctx, n));
+    NB2_TRY(ctx->vel.reserve(ctx, 2 * (size_t)n));
+    NB2_TRY(ctx->com_im.reserve(ctx, n));
+    NB2_TRY(ctx->inv_i.reserve(ctx, 3 * (size_t)n));
+    NB2_TRY(ctx->ext.reserve(ctx, 2 * (size_t)n));
+    NB2_TRY(ctx->lam.reserve(ctx, 2 * (size_t)n));
+    NB2_TRY(ctx->b_status.reserve(ctx, n));
+    ctx->n_bodies = n;
+    uint32_t nd = 0;
+    for (uint32_t i = 0; i < n; ++i) nd += bodies[i].status == NB2_BODY_DYNAMIC ? 1u : 0u;
+    ctx->n_dynamic = nd;
+    NB2_CUDA(ctx, cudaMemcpyAsync(ctx->raw.p, bodies, (size_t)n * sizeof(nb2_body), cudaMemcpyHostToDevice, ctx->stream));
+    NB2_TRY(launch_unpack_bodies(ctx));
+    // joints / manifolds referring to the old set are dropped
+    ctx->n_manifolds = ctx->n_contacts = 0;
+    ctx->n_joints = 0;
+    ctx->stepped = false;
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may free `bodies` on return
+    return NB2_OK;
+}
+
+int nb2_upload_body_states(nb2_context* h, const nb2_body_state* states, uint32_t first, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!states && n) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null states");
+    if ((uint64_t)first + n > ctx->n_bodies) return set_error(ctx, NB2_ERR_BAD_INDEX, "body range out of bounds");
+    if (!n) return NB2_OK;
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NB2_TRY(ctx->stage_states.reserve(ctx, n));
+    NB2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_states.p, states, (size_t)n * sizeof(nb2_body_state),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    NB2_TRY(launch_unpack_states(ctx, ctx->stage_states.p, first, n));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB2_OK;
+}
+
+int nb2_upload_manifolds(nb2_context* h, const nb2_manifold* manifolds, uint32_t nm, const nb2_contact* contacts,
+                         uint32_t nc) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if ((nm && !manifolds) || (nc && !contacts)) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null manifold/contact array");
+    if (!ctx->n_bodies) return set_error(ctx, NB2_ERR_NOT_READY, "upload bodies first");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((size_t)nm > ctx->manifolds.cap || (size_t)nc > ctx->contacts.cap)
+        NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // about to reallocate
+    NB2_TRY(ctx->manifolds.reserve(ctx, nm));
+    NB2_TRY(ctx->contacts.reserve(ctx, nc));
+    ctx->n_manifolds = nm;
+    ctx->n_contacts = nc;
+    if (nm)
+        NB2_CUDA(ctx, cudaMemcpyAsync(ctx->manifolds.p, manifolds, (size_t)nm * sizeof(nb2_manifold),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    if (nc)
+        NB2_CUDA(ctx, cudaMemcpyAsync(ctx->contacts.p, contacts, (size_t)nc * sizeof(nb2_contact),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    NB2_TRY(launch_validate_inputs(ctx));
+    // asynchronous: the caller's arrays must stay valid until the next nb2_synchronize / download
+    return NB2_OK;
+}
+
+int nb2_upload_joints(nb2_context* h, const nb2_joint* joints, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (n && !joints) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null joints");
+    if (!ctx->n_bodies) return set_error(ctx, NB2_ERR_NOT_READY, "upload bodies first");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NB2_TRY(ctx->joints.reserve(ctx, n));
+    ctx->n_joints = n;
+    if (n) {
+        NB2_CUDA(ctx, cudaMemcpyAsync(ctx->joints.p, joints, (size_t)n * sizeof(nb2_joint), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+        NB2_TRY(launch_validate_joints(ctx));
+        NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return NB2_OK;
+}
+
+int nb2_clear_impulse_cache(nb2_context* h) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    ctx->ht_cap[0] = ctx->ht_cap[1] = 0;
+    ctx->imp_n[0] = ctx->imp_n[1] = 0;
+    return NB2_OK;
+}
+
+int nb2_step(nb2_context* h, int mode) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (mode != NB2_MODE_REFERENCE_ORDER && mode != NB2_MODE_COLOURED)
+        return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "unknown step mode %d", mode);
+    if (!ctx->n_bodies || !ctx->have_params) return set_error(ctx, NB2_ERR_NOT_READY, "upload bodies and params before stepping");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    return do_step(ctx, mode);
+}
+
+int nb2_synchronize(nb2_context* h) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    return check_flags(ctx);
+}
+
+int nb2_download_body_states(nb2_context* h, nb2_body_state* out, uint32_t first, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!out && n) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null output");
+    if ((uint64_t)first + n > ctx->n_bodies) return set_error(ctx, NB2_ERR_BAD_INDEX, "body range out of bounds");
+    if (!n) return NB2_OK;
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((size_t)n > ctx->stage_states.cap) NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NB2_TRY(ctx->stage_states.reserve(ctx, n));
+    NB2_TRY(launch_pack_states(ctx, ctx->stage_states.p, first, n));
+    NB2_CUDA(ctx, cudaMemcpyAsync(out, ctx->stage_states.p, (size_t)n * sizeof(nb2_body_state), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB2_OK;
+}
+
+int nb2_download_contact_impulses(nb2_context* h, float* out3, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!n) return NB2_OK;
+    if (!out3) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null output");
+    if (!ctx->stepped || n > ctx->imp_n[ctx->cur]) return set_error(ctx, NB2_ERR_BAD_INDEX, "more impulses requested than contacts solved");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    // device rows are float4 (n, t1, t2, pad): copy with a 2D pitch conversion
+    NB2_CUDA(ctx, cudaMemcpy2DAsync(out3, 3 * sizeof(float), ctx->imp[ctx->cur].p, sizeof(float4), 3 * sizeof(float), n,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB2_OK;
+}
+
+int nb2_download_joints(nb2_context* h, nb2_joint* out, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!n) return NB2_OK;
+    if (!out) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null output");
+    if (n > ctx->n_joints) return set_error(ctx, NB2_ERR_BAD_INDEX, "more joints requested than uploaded");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_CUDA(ctx, cudaMemcpyAsync(out, ctx->joints.p, (size_t)n * sizeof(nb2_joint), cudaMemcpyDeviceToHost, ctx->stream));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB2_OK;
+}
+
+int nb2_get_stats(nb2_context* h, nb2_stats* out) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!out) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null output");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    nb2_stats& s = ctx->last_stats;
+    memset(&s, 0, sizeof(s));
+    s.n_bodies = ctx->n_bodies;
+    s.n_dynamic_bodies = ctx->n_dynamic;
+    s.n_manifolds = ctx->n_manifolds;
+    s.n_contacts = ctx->n_contacts;
+    s.n_joints = ctx->n_joints;
+    if (ctx->stepped) {
+        NB2_TRY(launch_stats(ctx, ctx->last_mode));
+        float f[16];
+        unsigned int u[16];
+        NB2_CUDA(ctx, cudaMemcpyAsync(f, ctx->stat_f.p, sizeof(f), cudaMemcpyDeviceToHost, ctx->stream));
+        NB2_CUDA(ctx, cudaMemcpyAsync(u, ctx->stat_u.p, sizeof(u), cudaMemcpyDeviceToHost, ctx->stream));
+        NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        double d[2];
+        memcpy(d, f + 4, sizeof(d));
+        s.residual_max = f[0];
+        s.residual_rms = u[0] ? (float)sqrt(d[0] / (double)u[0]) : 0.f;
+        s.max_penetration = f[1] > 0.f ? f[1] - 1000.f : 0.f;
+        s.kinetic_energy = (float)d[1];
+        s.n_rows_two_body = u[1];
+        s.n_rows_ground = u[2];
+        s.non_finite = u[3];
+        if (ctx->n_joints) {
+            // broken joints: count on the host from a download (diagnostic path only)
+            nb2_joint* tmp = (nb2_joint*)malloc((size_t)ctx->n_joints * sizeof(nb2_joint));
+            if (tmp) {
+                if (cudaMemcpy(tmp, ctx->joints.p, (size_t)ctx->n_joints * sizeof(nb2_joint), cudaMemcpyDeviceToHost) ==
+                    cudaSuccess)
+                    for (uint32_t i = 0; i < ctx->n_joints; ++i) s.n_broken_joints += tmp[i].broken ? 1u : 0u;
+                free(tmp);
+            }
+        }
+        if (ctx->ev_valid) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev.e[0], ctx->ev.e[1]);
+            s.t_assembly_ms = ms;
+            cudaEventElapsedTime(&ms, ctx->ev.e[1], ctx->ev.e[2]);
+            s.t_velocity_resolution_ms = ms;
+            cudaEventElapsedTime(&ms, ctx->ev.e[2], ctx->ev.e[3]);
+            s.t_velocity_update_ms = ms;
+            cudaEventElapsedTime(&ms, ctx->ev.e[3], ctx->ev.e[4]);
+            s.t_position_resolution_ms = ms;
+            cudaEventElapsedTime(&ms, ctx->ev.e[0], ctx->ev.e[5]);
+            s.t_step_ms = ms;
+        }
+    }
+    int rc = check_flags(ctx);
+    *out = ctx->last_stats;
+    if (rc != NB2_OK) return rc;
+    if (out->non_finite) return set_error(ctx, NB2_ERR_NON_FINITE, "%u bodies have a non-finite state", out->non_finite);
+    return NB2_OK;
+}
+
+int nb2_launch_count(const nb2_context* h, uint64_t* out) {
+    if (!h || !out) return NB2_ERR_INVALID_ARGUMENT;
+    *out = h->c.launches;
+    return NB2_OK;
+}
+
+}  // extern "C"

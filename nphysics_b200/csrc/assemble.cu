@@ -1,0 +1,628 @@
+// Constraint-row assembly on device and impulse caching.
+//
+// assemble_contact_rows replaces SignoriniCoulombPyramidModel::constraints
+// (src/solver/signorini_coulomb_pyramid_model.rs:56-224) with SignoriniModel::
+// build_velocity_constraint / build_position_constraint (signorini_model.rs:37-197),
+// helper::constraint_pair_geometry (helper.rs:53-135) and RigidBody::
+// fill_constraint_geometry (src/object/rigid_body.rs:672-722) inlined: one thread per
+// contact emits the non-penetration row, the two friction-pyramid rows and the position row
+// straight into the ELL slots chosen by the schedule.
+// assemble_joint_rows replaces each *_constraint.rs::velocity_constraints (one thread per joint).
+// cache_impulses replaces the two cache_impulses passes (signorini_coulomb_pyramid_model.rs:
+// 226-261, ball_constraint.rs:132-144 and friends).
+#include "solver.cuh"
+
+namespace nb2 {
+
+static const int TPB = 128;
+static inline unsigned int nblk(size_t n) { return (unsigned int)((n + TPB - 1) / TPB); }
+
+// Read-only view of a schedule.
+struct SchedView {
+    const int* it_phase;
+    const int* it_slot;
+    const int* it_type;
+    const unsigned int* ph_count;
+    const unsigned int* ph_gbase;
+    const unsigned int* ph_rbase;
+    unsigned int max_phases;
+    __device__ __forceinline__ unsigned int phase_of(size_t item) const {
+        return min((unsigned int)it_phase[item], max_phases - 1);
+    }
+    __device__ __forceinline__ size_t row_slot(size_t item, int r) const {
+        unsigned int p = phase_of(item);
+        return (size_t)ph_rbase[p] + (size_t)r * ph_count[p] + (size_t)it_slot[item];
+    }
+    __device__ __forceinline__ size_t pos_slot(size_t item, int lcc) const {
+        unsigned int p = phase_of(item);
+        return (size_t)NB2_CHUNK * ph_gbase[p] + (size_t)lcc * ph_count[p] + (size_t)it_slot[item];
+    }
+};
+static SchedView view_of(const Sched& s) {
+    SchedView v;
+    v.it_phase = s.it_phase.p;
+    v.it_slot = s.it_slot.p;
+    v.it_type = s.it_type.p;
+    v.ph_count = s.ph_count.p;
+    v.ph_gbase = s.ph_gbase.p;
+    v.ph_rbase = s.ph_rbase.p;
+    v.max_phases = (unsigned int)s.max_phases;
+    return v;
+}
+
+struct BodyArrays {
+    const nb2_body* raw;
+    const float4* pos_t;
+    const float4* pos_q;
+    const float4* vel;
+    const float4* com_im;
+    const float4* inv_i;
+    const float4* ext;
+};
+
+// What one side of a row needs from its body.
+struct BodySide {
+    int status;
+    Vec3 com;
+    float inv_mass;
+    Mat3 inv_i;
+    float v[6];
+    float e[6];
+    float mask[6];
+};
+__device__ __forceinline__ void load_side(const BodyArrays& B, int idx, BodySide* s) {
+    const nb2_body& rb = B.raw[idx];
+    s->status = (int)rb.status;
+    float4 c = B.com_im[idx];
+    s->com = f4_xyz(c);
+    s->inv_mass = c.w;
+    float4 r0 = B.inv_i[3 * idx], r1 = B.inv_i[3 * idx + 1], r2 = B.inv_i[3 * idx + 2];
+    s->inv_i.m[0][0] = r0.x; s->inv_i.m[0][1] = r0.y; s->inv_i.m[0][2] = r0.z;
+    s->inv_i.m[1][0] = r1.x; s->inv_i.m[1][1] = r1.y; s->inv_i.m[1][2] = r1.z;
+    s->inv_i.m[2][0] = r2.x; s->inv_i.m[2][1] = r2.y; s->inv_i.m[2][2] = r2.z;
+    float4 vl = B.vel[2 * idx], va = B.vel[2 * idx + 1];
+    s->v[0] = vl.x; s->v[1] = vl.y; s->v[2] = vl.z; s->v[3] = va.x; s->v[4] = va.y; s->v[5] = va.z;
+    float4 el = B.ext[2 * idx], ea = B.ext[2 * idx + 1];
+    s->e[0] = el.x; s->e[1] = el.y; s->e[2] = el.z; s->e[3] = ea.x; s->e[4] = ea.y; s->e[5] = ea.z;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s->mask[k] = rb.jacobian_mask[k];
+}
+
+__device__ __forceinline__ float dot6_seq(const float* a, const float* b) {
+    float res = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) res += a[k] * b[k];
+    return res;
+}
+
+// RigidBody::fill_constraint_geometry (rigid_body.rs:672-722) for one side.
+// J / WJ are left zero for non-dynamic sides.
+__device__ __forceinline__ void fill_side(const BodySide& s, Vec3 point, bool angular, Vec3 dir, float* J, float* WJ,
+                                          float* inv_r, float* out_vel, bool with_vel) {
+    Vec3 pos = point - s.com;
+    Vec3 fl = angular ? mk3(0.f, 0.f, 0.f) : dir;
+    Vec3 fa = angular ? dir : cross3(pos, dir);
+    float f[6] = {fl.x, fl.y, fl.z, fa.x, fa.y, fa.z};
+    if (s.status == NB2_BODY_KINEMATIC) {
+        if (with_vel) *out_vel += dot6_seq(f, s.v);
+    } else if (s.status == NB2_BODY_DYNAMIC) {
+        float mf[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) mf[k] = f[k] * s.mask[k];
+        Vec3 wl = mk3(mf[0], mf[1], mf[2]) * s.inv_mass;
+        Vec3 wa = mat_vec(s.inv_i, mk3(mf[3], mf[4], mf[5]));
+#pragma unroll
+        for (int k = 0; k < 6; ++k) J[k] = mf[k];
+        WJ[0] = wl.x; WJ[1] = wl.y; WJ[2] = wl.z; WJ[3] = wa.x; WJ[4] = wa.y; WJ[5] = wa.z;
+        *inv_r += s.inv_mass + dot3(mk3(mf[3], mf[4], mf[5]), wa);
+        if (with_vel) {
+            *out_vel += dot6_seq(f, s.v);
+            *out_vel += dot6_seq(mf, s.e);
+        }
+    }
+}
+
+struct RowOut {
+    float4* jac;   // [6][n_slots_max]
+    float4* hdr;
+    int2* meta;
+    float* imp;
+    size_t n_slots_max;
+};
+__device__ __forceinline__ void write_row(const RowOut& o, size_t slot, const float* J1, const float* J2,
+                                          const float* W1, const float* W2, float rhs, float r, float lo, float hi,
+                                          int kind, int dep, float impulse) {
+    const size_t S = o.n_slots_max;
+    o.jac[0 * S + slot] = make_float4(J1[0], J1[1], J1[2], J1[3]);
+    o.jac[1 * S + slot] = make_float4(J1[4], J1[5], J2[0], J2[1]);
+    o.jac[2 * S + slot] = make_float4(J2[2], J2[3], J2[4], J2[5]);
+    o.jac[3 * S + slot] = make_float4(W1[0], W1[1], W1[2], W1[3]);
+    o.jac[4 * S + slot] = make_float4(W1[4], W1[5], W2[0], W2[1]);
+    o.jac[5 * S + slot] = make_float4(W2[2], W2[3], W2[4], W2[5]);
+    o.hdr[slot] = make_float4(rhs, r, lo, hi);
+    o.meta[slot] = make_int2(kind, dep);
+    o.imp[slot] = impulse;
+}
+
+// helper::constraint_pair_geometry (helper.rs:53-135) + row emission.
+__device__ __forceinline__ void emit_pair_row(const RowOut& o, size_t slot, const BodySide& s1, const BodySide& s2,
+                                              Vec3 c1, Vec3 c2, bool angular, Vec3 dir, float rhs0, float* rhs_out,
+                                              float* r_out, float* J1, float* J2, float* W1, float* W2) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) J1[k] = J2[k] = W1[k] = W2[k] = 0.f;
+    float inv_r = 0.f;
+    float rhs = rhs0;
+    fill_side(s1, c1, angular, dir, J1, W1, &inv_r, &rhs, true);
+    fill_side(s2, c2, angular, -dir, J2, W2, &inv_r, &rhs, true);
+    *r_out = inv_r != 0.f ? 1.f / inv_r : 1.f;
+    *rhs_out = rhs;
+    (void)o;
+    (void)slot;
+}
+
+// ---------------------------------------------------------------- impulse cache (hash)
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+__device__ __forceinline__ bool ht_lookup(const unsigned long long* keys, const unsigned int* vals, size_t cap,
+                                          unsigned long long key, unsigned int* out) {
+    if (cap == 0) return false;
+    size_t h = (size_t)mix64(key) & (cap - 1);
+    for (size_t probe = 0; probe < cap; ++probe) {
+        unsigned long long k = keys[h];
+        if (k == key) {
+            *out = vals[h];
+            return true;
+        }
+        if (k == 0ull) return false;
+        h = (h + 1) & (cap - 1);
+    }
+    return false;
+}
+__device__ __forceinline__ void ht_insert(unsigned long long* keys, unsigned int* vals, size_t cap,
+                                          unsigned long long key, unsigned int val) {
+    size_t h = (size_t)mix64(key) & (cap - 1);
+    for (size_t probe = 0; probe < cap; ++probe) {
+        unsigned long long prev = atomicCAS(&keys[h], 0ull, key);
+        if (prev == 0ull || prev == key) {
+            vals[h] = val;
+            return;
+        }
+        h = (h + 1) & (cap - 1);
+    }
+}
+
+// ---------------------------------------------------------------- contacts
+__global__ void __launch_bounds__(TPB) k_assemble_contacts(
+    int mode, unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
+    const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
+    const unsigned int* __restrict__ chunk_base, BodyArrays B, SchedView vs, SchedView ps, RowOut out,
+    float4* p_row, size_t n_pslots_max, const unsigned long long* __restrict__ ht_keys,
+    const unsigned int* __restrict__ ht_vals, size_t ht_cap, const float4* __restrict__ imp_prev,
+    float warmstart_coeff, float restitution_threshold, float inv_dt) {
+    unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nC) return;
+    const unsigned int m = c_manifold[ci];
+    if (m == 0xFFFFFFFFu) return;
+    const nb2_manifold& mf = manifolds[m];
+    const nb2_contact& c = contacts[ci];
+    BodySide s1, s2;
+    load_side(B, mf.body1, &s1);
+    load_side(B, mf.body2, &s2);
+    const bool d1 = s1.status == NB2_BODY_DYNAMIC, d2 = s2.status == NB2_BODY_DYNAMIC;
+    if (!d1 && !d2) return;  // filtered by the caller in the reference (mechanical_world.rs:287-300)
+    const unsigned int lc = ci - mf.first_contact;
+    const unsigned int chunk = chunk_base[m] + lc / NB2_CHUNK;
+    const int lcc = (int)(lc % NB2_CHUNK);
+    const int ncc = min(NB2_CHUNK, (int)mf.num_contacts - NB2_CHUNK * (int)(lc / NB2_CHUNK));
+
+    const Vec3 n = mk3(c.normal[0], c.normal[1], c.normal[2]);
+    const Vec3 world1 = mk3(c.world1[0], c.world1[1], c.world1[2]);
+    const Vec3 world2 = mk3(c.world2[0], c.world2[1], c.world2[2]);
+    const Vec3 surf = mk3(mf.surface_velocity[0], mf.surface_velocity[1], mf.surface_velocity[2]);
+
+    // impulse cache lookup (signorini_coulomb_pyramid_model.rs:104-108)
+    float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c.key != 0ull) {
+        unsigned int prev;
+        if (ht_lookup(ht_keys, ht_vals, ht_cap, c.key, &prev)) cached = imp_prev[prev];
+    }
+
+    size_t slot_n, slot_t1, slot_t2, pslot;
+    if (mode == NB2_MODE_COLOURED) {
+        size_t item = (size_t)nJ + chunk;
+        slot_t1 = vs.row_slot(item, 2 * lcc);
+        slot_t2 = vs.row_slot(item, 2 * lcc + 1);
+        slot_n = vs.row_slot(item, 2 * ncc + lcc);
+        pslot = vs.pos_slot(item, lcc);
+    } else {
+        size_t item_f = (size_t)nJ + chunk, item_n = (size_t)nJ + maxc + chunk;
+        slot_t1 = vs.row_slot(item_f, 2 * lcc);
+        slot_t2 = vs.row_slot(item_f, 2 * lcc + 1);
+        slot_n = vs.row_slot(item_n, lcc);
+        pslot = ps.pos_slot((size_t)nJ + chunk, lcc);
+    }
+
+    // ---- non-penetration row (signorini_model.rs:65-137)
+    const Vec3 center1 = world1 + n * mf.margin1;
+    const Vec3 center2 = world2 - n * mf.margin2;
+    float J1[6], J2[6], W1[6], W2[6], rhs, r;
+    emit_pair_row(out, slot_n, s1, s2, center1, center2, false, -n, dot3(n, surf), &rhs, &r, J1, J2, W1, W2);
+    if (rhs <= -restitution_threshold) rhs += mf.restitution * rhs;
+    float depth = c.depth + mf.margin1 + mf.margin2;
+    if (depth < 0.f) rhs += (-depth) * inv_dt;
+    write_row(out, slot_n, J1, J2, W1, W2, rhs, r, 0.f, NB2_F32_MAX, NB2_ROW_UNILATERAL, 0,
+              cached.x * warmstart_coeff);
+
+    // ---- friction pyramid rows (signorini_coulomb_pyramid_model.rs:131-216)
+    Vec3 t1, t2;
+    tangent_basis(n, &t1, &t2);
+    emit_pair_row(out, slot_t1, s1, s2, center1, center2, false, t1, dot3(t1, surf), &rhs, &r, J1, J2, W1, W2);
+    write_row(out, slot_t1, J1, J2, W1, W2, rhs, r, mf.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
+              cached.y * warmstart_coeff);
+    emit_pair_row(out, slot_t2, s1, s2, center1, center2, false, t2, dot3(t2, surf), &rhs, &r, J1, J2, W1, W2);
+    write_row(out, slot_t2, J1, J2, W1, W2, rhs, r, mf.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
+              cached.z * warmstart_coeff);
+
+    // ---- position row (signorini_model.rs:153-197)
+    const Quat q1 = f4_quat(B.pos_q[mf.body1]);
+    const Vec3 normal1 = quat_inv_rotate(q1, n);
+    const size_t P = n_pslots_max;
+    p_row[0 * P + pslot] = make_float4(c.local1[0], c.local1[1], c.local1[2], c.dilation1 + mf.margin1);
+    p_row[1 * P + pslot] = make_float4(c.local2[0], c.local2[1], c.local2[2], c.dilation2 + mf.margin2);
+    p_row[2 * P + pslot] = make_float4(c.dir1[0], c.dir1[1], c.dir1[2], __int_as_float((int)c.geom1));
+    p_row[3 * P + pslot] = make_float4(c.dir2[0], c.dir2[1], c.dir2[2], __int_as_float((int)c.geom2));
+    p_row[4 * P + pslot] = make_float4(normal1.x, normal1.y, normal1.z, 0.f);
+}
+
+// ---------------------------------------------------------------- joints
+// Warm-start slot of row r inside nb2_joint.impulses (what each velocity_constraints passes as
+// `impulses[i]`), and the slot cache_impulses stores impulse_id == r into (verbatim, including
+// the pin-slot / cylindrical quirk where id 2 lands in lin_impulses[2]).
+__device__ __forceinline__ int joint_warm_slot(unsigned int type, int r) {
+    switch (type) {
+        case NB2_JOINT_BALL: return r;
+        case NB2_JOINT_REVOLUTE:
+        case NB2_JOINT_FIXED: return r;  // lin[r] | ang[r-3] == impulses[r]
+        case NB2_JOINT_PRISMATIC: return r < 2 ? r : (r < 5 ? 3 + (r - 2) : 6);
+        case NB2_JOINT_UNIVERSAL: return r;
+        case NB2_JOINT_PLANAR:
+        case NB2_JOINT_RECTANGULAR: return r == 0 ? 0 : 3 + (r - 1);
+        case NB2_JOINT_PIN_SLOT:
+        case NB2_JOINT_CYLINDRICAL: return r < 2 ? r : 3 + (r - 2);
+        case NB2_JOINT_CARTESIAN: return 3 + r;
+        default: return 0;
+    }
+}
+__device__ __forceinline__ int joint_cache_slot(unsigned int type, int id) {
+    switch (type) {
+        case NB2_JOINT_BALL: return id;
+        case NB2_JOINT_REVOLUTE:
+        case NB2_JOINT_PIN_SLOT:
+        case NB2_JOINT_CYLINDRICAL:
+        case NB2_JOINT_FIXED: return id;  // id<3 -> lin[id]; else ang[id-3]
+        case NB2_JOINT_PRISMATIC: return id < 2 ? id : (id < 5 ? 3 + (id + 1 - 3) : 6);
+        case NB2_JOINT_UNIVERSAL: return id < 3 ? id : 3;
+        case NB2_JOINT_PLANAR:
+        case NB2_JOINT_RECTANGULAR: return id == 0 ? 0 : 3 + (id - 1);
+        case NB2_JOINT_CARTESIAN: return 3 + id;
+        default: return 0;
+    }
+}
+
+struct JointFrame {
+    Pose pos1, pos2;  // position_at_material_point (* ref_frame for fixed/cartesian)
+};
+__device__ __forceinline__ JointFrame joint_frames(const nb2_joint& j, const Pose& p1, const Pose& p2) {
+    JointFrame f;
+    f.pos1.t = p1.t + quat_rotate(p1.r, mk3(j.anchor1[0], j.anchor1[1], j.anchor1[2]));
+    f.pos1.r = p1.r;
+    f.pos2.t = p2.t + quat_rotate(p2.r, mk3(j.anchor2[0], j.anchor2[1], j.anchor2[2]));
+    f.pos2.r = p2.r;
+    if (j.type == NB2_JOINT_FIXED || j.type == NB2_JOINT_CARTESIAN) {
+        f.pos1.r = quat_mul(f.pos1.r, mkq(j.ref_frame1[0], j.ref_frame1[1], j.ref_frame1[2], j.ref_frame1[3]));
+        f.pos2.r = quat_mul(f.pos2.r, mkq(j.ref_frame2[0], j.ref_frame2[1], j.ref_frame2[2], j.ref_frame2[3]));
+    }
+    return f;
+}
+
+__global__ void __launch_bounds__(TPB) k_assemble_joints(unsigned int nJ, const nb2_joint* __restrict__ joints,
+                                                         BodyArrays B, SchedView vs, RowOut out) {
+    unsigned int ji = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ji >= nJ) return;
+    if (vs.it_type[ji] == NB2_ITEM_INVALID) return;
+    const nb2_joint& j = joints[ji];
+    BodySide s1, s2;
+    load_side(B, j.body1, &s1);
+    load_side(B, j.body2, &s2);
+    Pose p1, p2;
+    p1.t = f4_xyz(B.pos_t[j.body1]);
+    p1.r = f4_quat(B.pos_q[j.body1]);
+    p2.t = f4_xyz(B.pos_t[j.body2]);
+    p2.r = f4_quat(B.pos_q[j.body2]);
+    JointFrame fr = joint_frames(j, p1, p2);
+    const Vec3 a1 = fr.pos1.t, a2 = fr.pos2.t;
+    const Vec3 ex = mk3(1.f, 0.f, 0.f), ey = mk3(0.f, 1.f, 0.f), ez = mk3(0.f, 0.f, 1.f);
+
+    int r = 0;
+    float J1[6], J2[6], W1[6], W2[6], rhs, rr;
+    auto row = [&](bool angular, Vec3 dir, float lo) {
+        emit_pair_row(out, 0, s1, s2, a1, a2, angular, dir, 0.f, &rhs, &rr, J1, J2, W1, W2);
+        float warm = j.impulses[joint_warm_slot(j.type, r)];
+        write_row(out, vs.row_slot(ji, r), J1, J2, W1, W2, rhs, rr, lo, NB2_F32_MAX, NB2_ROW_BILATERAL, 0, warm);
+        ++r;
+    };
+    auto skip = [&]() {
+        out.meta[vs.row_slot(ji, r)] = make_int2(NB2_ROW_NONE, 0);
+        out.imp[vs.row_slot(ji, r)] = 0.f;
+        ++r;
+    };
+    auto lin3 = [&]() {  // helper::cancel_relative_linear_velocity (helper.rs:247-293)
+        row(false, ex, -NB2_F32_MAX);
+        row(false, ey, -NB2_F32_MAX);
+        row(false, ez, -NB2_F32_MAX);
+    };
+    auto ang3 = [&]() {  // helper::cancel_relative_angular_velocity (helper.rs:502-548)
+        row(true, ex, -NB2_F32_MAX);
+        row(true, ey, -NB2_F32_MAX);
+        row(true, ez, -NB2_F32_MAX);
+    };
+    auto restrict2 = [&](bool angular, Vec3 axis) {  // helper.rs:614-695 / 771-853
+        Vec3 t1, t2;
+        tangent_basis(axis, &t1, &t2);
+        row(angular, t1, -NB2_F32_MAX);
+        row(angular, t2, -NB2_F32_MAX);
+    };
+    const Vec3 ax1 = mk3(j.axis1[0], j.axis1[1], j.axis1[2]);
+    const Vec3 ax2 = mk3(j.axis2[0], j.axis2[1], j.axis2[2]);
+    const Vec3 ax3 = mk3(j.axis3[0], j.axis3[1], j.axis3[2]);
+    switch (j.type) {
+        case NB2_JOINT_BALL:  // ball_constraint.rs:92-126
+            lin3();
+            break;
+        case NB2_JOINT_REVOLUTE:  // revolute_constraint.rs:194-258
+            lin3();
+            restrict2(true, quat_rotate(fr.pos1.r, ax1));
+            break;
+        case NB2_JOINT_PRISMATIC: {  // prismatic_constraint.rs:149-236 + unit_constraint.rs:10-125
+            Vec3 axis = quat_rotate(fr.pos1.r, ax1);
+            restrict2(false, axis);
+            ang3();
+            const bool has_min = j.flags & NB2_JOINT_FLAG_MIN_OFFSET, has_max = j.flags & NB2_JOINT_FLAG_MAX_OFFSET;
+            float offset = dot3(axis, a2 - a1);
+            int act = 0;  // 0 none, 1 bilateral +axis, 2 unilateral -axis, 3 unilateral +axis
+            if (has_min && has_max) {
+                float diff = fabsf(j.min_offset - j.max_offset);
+                float largest = fmaxf(fabsf(j.min_offset), fabsf(j.max_offset));
+                bool eq = (j.min_offset == j.max_offset) || diff <= NB2_F32_EPS || diff <= largest * NB2_F32_EPS;
+                if (eq) act = 1;
+                else if (offset <= j.min_offset) act = 2;
+                else if (offset >= j.max_offset) act = 3;
+            } else if (has_min) {
+                if (offset <= j.min_offset) act = 2;
+            } else if (has_max) {
+                if (offset >= j.max_offset) act = 3;
+            }
+            if (act == 0) skip();
+            else row(false, act == 2 ? -axis : axis, act == 1 ? -NB2_F32_MAX : 0.f);
+            skip();  // the reference reserves 7 rows (prismatic_constraint.rs:124-126)
+            break;
+        }
+        case NB2_JOINT_UNIVERSAL: {  // universal_constraint.rs:104-165
+            lin3();
+            Vec3 axis1 = quat_rotate(fr.pos1.r, ax1), axis2 = quat_rotate(fr.pos2.r, ax2);
+            Vec3 orth;
+            float len;
+            if (unit_try_new_and_get(cross3(axis1, axis2), NB2_F32_EPS, &orth, &len)) row(true, orth, -NB2_F32_MAX);
+            else skip();
+            break;
+        }
+        case NB2_JOINT_PLANAR: {  // planar_constraint.rs:101-163
+            Vec3 axis1 = quat_rotate(fr.pos1.r, ax1);
+            row(false, axis1, -NB2_F32_MAX);
+            restrict2(true, axis1);
+            break;
+        }
+        case NB2_JOINT_RECTANGULAR: {  // rectangular_constraint.rs:99-160
+            row(false, quat_rotate(fr.pos1.r, ax1), -NB2_F32_MAX);
+            ang3();
+            break;
+        }
+        case NB2_JOINT_PIN_SLOT:  // pin_slot_constraint.rs:149-212
+            restrict2(false, quat_rotate(fr.pos1.r, ax1));
+            restrict2(true, quat_rotate(fr.pos1.r, ax3));
+            break;
+        case NB2_JOINT_CYLINDRICAL: {  // cylindrical_constraint.rs:143-205
+            Vec3 axis1 = quat_rotate(fr.pos1.r, ax1);
+            restrict2(false, axis1);
+            restrict2(true, axis1);
+            break;
+        }
+        case NB2_JOINT_FIXED:  // fixed_constraint.rs:113-171
+            lin3();
+            ang3();
+            break;
+        case NB2_JOINT_CARTESIAN:  // cartesian_constraint.rs:106-144
+            ang3();
+            break;
+        default:
+            break;
+    }
+    (void)ax2;
+}
+
+// ---------------------------------------------------------------- cache impulses
+__global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
+    int mode, unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
+    const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
+    const unsigned int* __restrict__ chunk_base, const int* __restrict__ status, SchedView vs,
+    const float* __restrict__ r_imp, float4* imp_cur, unsigned long long* ht_keys, unsigned int* ht_vals,
+    size_t ht_cap) {
+    unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nC) return;
+    const unsigned int m = c_manifold[ci];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m == 0xFFFFFFFFu) {
+        imp_cur[ci] = v;
+        return;
+    }
+    const nb2_manifold& mf = manifolds[m];
+    if (status[mf.body1] == NB2_BODY_DYNAMIC || status[mf.body2] == NB2_BODY_DYNAMIC) {
+        const unsigned int lc = ci - mf.first_contact;
+        const unsigned int chunk = chunk_base[m] + lc / NB2_CHUNK;
+        const int lcc = (int)(lc % NB2_CHUNK);
+        const int ncc = min(NB2_CHUNK, (int)mf.num_contacts - NB2_CHUNK * (int)(lc / NB2_CHUNK));
+        if (mode == NB2_MODE_COLOURED) {
+            size_t item = (size_t)nJ + chunk;
+            v.x = r_imp[vs.row_slot(item, 2 * ncc + lcc)];
+            v.y = r_imp[vs.row_slot(item, 2 * lcc)];
+            v.z = r_imp[vs.row_slot(item, 2 * lcc + 1)];
+        } else {
+            size_t item_f = (size_t)nJ + chunk, item_n = (size_t)nJ + maxc + chunk;
+            v.x = r_imp[vs.row_slot(item_n, lcc)];
+            v.y = r_imp[vs.row_slot(item_f, 2 * lcc)];
+            v.z = r_imp[vs.row_slot(item_f, 2 * lcc + 1)];
+        }
+    }
+    imp_cur[ci] = v;
+    const unsigned long long key = contacts[ci].key;
+    if (key != 0ull) ht_insert(ht_keys, ht_vals, ht_cap, key, ci);
+}
+
+__global__ void __launch_bounds__(TPB) k_cache_joint_impulses(unsigned int nJ, nb2_joint* joints, SchedView vs,
+                                                              const int* __restrict__ it_nrows,
+                                                              const int2* __restrict__ r_meta,
+                                                              const float* __restrict__ r_imp, float inv_dt) {
+    unsigned int ji = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ji >= nJ) return;
+    if (vs.it_type[ji] == NB2_ITEM_INVALID) return;
+    nb2_joint& j = joints[ji];
+    const int nrows = it_nrows[ji];
+    for (int r = 0; r < nrows; ++r) {
+        size_t slot = vs.row_slot(ji, r);
+        if (r_meta[slot].x == NB2_ROW_NONE) continue;
+        j.impulses[joint_cache_slot(j.type, r)] = r_imp[slot];
+    }
+    const float* lin = &j.impulses[0];
+    const float* ang = &j.impulses[3];
+    const float inv_dt2 = inv_dt * inv_dt;
+    const float lin_sq = norm_sq3(mk3(lin[0], lin[1], lin[2]));
+    const float ang_sq = norm_sq3(mk3(ang[0], ang[1], ang[2]));
+    bool broken;
+    switch (j.type) {
+        case NB2_JOINT_BALL: broken = lin_sq * inv_dt * inv_dt > j.break_force_squared; break;
+        case NB2_JOINT_UNIVERSAL:
+            broken = lin_sq * inv_dt2 > j.break_force_squared || ang[0] * ang[0] * inv_dt2 > j.break_torque_squared;
+            break;
+        case NB2_JOINT_PLANAR:
+            broken = lin[0] * lin[0] * inv_dt2 > j.break_force_squared ||
+                     ang[0] * ang[0] * inv_dt2 + ang[1] * ang[1] * inv_dt2 > j.break_torque_squared;
+            break;
+        case NB2_JOINT_RECTANGULAR:
+            broken = lin[0] * lin[0] * inv_dt2 > j.break_force_squared || ang_sq * inv_dt2 > j.break_torque_squared;
+            break;
+        case NB2_JOINT_CARTESIAN: broken = ang_sq * inv_dt * inv_dt > j.break_torque_squared; break;
+        default:
+            broken = lin_sq * inv_dt2 > j.break_force_squared || ang_sq * inv_dt2 > j.break_torque_squared;
+            break;
+    }
+    if (broken) j.broken = 1u;
+}
+
+static BodyArrays body_arrays(Context* ctx) {
+    BodyArrays B;
+    B.raw = ctx->raw.p;
+    B.pos_t = ctx->pos_t.p;
+    B.pos_q = ctx->pos_q.p;
+    B.vel = ctx->vel.p;
+    B.com_im = ctx->com_im.p;
+    B.inv_i = ctx->inv_i.p;
+    B.ext = ctx->ext.p;
+    return B;
+}
+static RowOut row_out(Context* ctx) {
+    RowOut o;
+    o.jac = ctx->r_jac.p;
+    o.hdr = ctx->r_hdr.p;
+    o.meta = ctx->r_meta.p;
+    o.imp = ctx->r_imp.p;
+    o.n_slots_max = ctx->n_slots_max;
+    return o;
+}
+
+int launch_assemble(Context* ctx, int mode) {
+    const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
+    const size_t maxc = ctx->max_chunks;
+    // row-slot upper bounds (ELL padding included): every item may be padded to the widest group
+    const size_t n_items = ctx->vs.n_items;
+    const size_t slots = n_items * (size_t)(3 * NB2_CHUNK) + 16;
+    const size_t pitems = ref ? ctx->ps.n_items : n_items;
+    const size_t pslots = pitems * (size_t)NB2_CHUNK + 16;
+    ctx->n_slots_max = slots;
+    ctx->n_pslots_max = pslots;
+    NB2_TRY(ctx->r_jac.reserve(ctx, 6 * slots));
+    ctx->n_slots_max = ctx->r_jac.cap / 6;  // keep the plane stride consistent with the allocation
+    NB2_TRY(ctx->r_hdr.reserve(ctx, ctx->n_slots_max));
+    NB2_TRY(ctx->r_meta.reserve(ctx, ctx->n_slots_max));
+    NB2_TRY(ctx->r_imp.reserve(ctx, ctx->n_slots_max));
+    NB2_TRY(ctx->p_row.reserve(ctx, 5 * pslots));
+    ctx->n_pslots_max = ctx->p_row.cap / 5;
+    SchedView vs = view_of(ctx->vs);
+    SchedView ps = ref ? view_of(ctx->ps) : vs;
+    const int prev = 1 - ctx->cur;
+    if (ctx->n_joints) {
+        k_assemble_joints<<<nblk(ctx->n_joints), TPB, 0, ctx->stream>>>(ctx->n_joints, ctx->joints.p,
+                                                                        body_arrays(ctx), vs, row_out(ctx));
+        ctx->launches++;
+    }
+    if (ctx->n_contacts) {
+        k_assemble_contacts<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
+            mode, ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p,
+            ctx->c_manifold.p, ctx->chunk_base.p, body_arrays(ctx), vs, ps, row_out(ctx), ctx->p_row.p,
+            ctx->n_pslots_max, ctx->ht_keys[prev].p, ctx->ht_vals[prev].p, ctx->ht_cap[prev], ctx->imp[prev].p,
+            ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt);
+        ctx->launches++;
+    }
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
+int launch_cache_impulses(Context* ctx, int mode) {
+    const int cur = ctx->cur;
+    // size the table for this step's contacts
+    size_t cap = 0;
+    if (ctx->n_contacts) {
+        cap = 64;
+        while (cap < 2 * (size_t)ctx->n_contacts) cap <<= 1;
+    }
+    NB2_TRY(ctx->imp[cur].reserve(ctx, ctx->n_contacts + 1));
+    if (cap) {
+        NB2_TRY(ctx->ht_keys[cur].reserve(ctx, cap));
+        NB2_TRY(ctx->ht_vals[cur].reserve(ctx, cap));
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->ht_keys[cur].p, 0, cap * sizeof(unsigned long long), ctx->stream));
+    }
+    ctx->ht_cap[cur] = cap;
+    ctx->imp_n[cur] = ctx->n_contacts;
+    SchedView vs = view_of(ctx->vs);
+    if (ctx->n_contacts) {
+        k_cache_contact_impulses<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
+            mode, ctx->n_contacts, ctx->n_joints, (unsigned int)ctx->max_chunks, ctx->manifolds.p, ctx->contacts.p,
+            ctx->c_manifold.p, ctx->chunk_base.p, ctx->b_status.p, vs, ctx->r_imp.p, ctx->imp[cur].p,
+            ctx->ht_keys[cur].p, ctx->ht_vals[cur].p, cap);
+        ctx->launches++;
+    }
+    if (ctx->n_joints) {
+        k_cache_joint_impulses<<<nblk(ctx->n_joints), TPB, 0, ctx->stream>>>(
+            ctx->n_joints, ctx->joints.p, vs, ctx->vs.it_nrows.p, ctx->r_meta.p, ctx->r_imp.p, ctx->inv_dt);
+        ctx->launches++;
+    }
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
+}  // namespace nb2

@@ -1,0 +1,632 @@
+// Device-side scheduling of constraint groups into conflict-free phases.
+//
+// The reference sweeps every row sequentially (src/solver/sor_prox.rs:159-179).  Here rows are
+// grouped (all rows of <= 4 contacts of one manifold / of one joint: they share their body pair,
+// so one thread runs them in order) and groups are assigned to phases such that no two groups of
+// a phase touch the same dynamic body:
+//   * NB2_MODE_REFERENCE_ORDER: phase = level = 1 + max(level of the previous group, in the
+//     reference's sweep order, on either body).  Executing levels in order reproduces the
+//     sequential sweep exactly.
+//   * NB2_MODE_COLOURED: phase = colour from a Jones-Plassmann greedy colouring of the group
+//     conflict graph, computed on device with per-body colour bitmasks.
+// Non-dynamic bodies (ground, kinematic) never create conflicts.
+#include "solver.cuh"
+
+namespace nb2 {
+
+static const int TPB = 256;
+static inline unsigned int nblk(size_t n) { return (unsigned int)((n + TPB - 1) / TPB); }
+
+// ------------------------------------------------------------------ exclusive scan
+#define SCAN_TPB 512
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_TPB * SCAN_ITEMS)
+
+__device__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* total) {
+    __shared__ unsigned int warp_sums[SCAN_TPB / 32];
+    unsigned int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int s = lane < SCAN_TPB / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane < SCAN_TPB / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    unsigned int base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[SCAN_TPB / 32 - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+__global__ void k_scan_tile_sums(const unsigned int* __restrict__ in, size_t n, unsigned int* tile_sums) {
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    unsigned int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) s += in[base + k];
+    unsigned int total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// single block: in-place exclusive scan of the tile sums (any count)
+__global__ void k_scan_sums(unsigned int* tile_sums, unsigned int ntiles) {
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (unsigned int start = 0; start < ntiles; start += SCAN_TPB) {
+        unsigned int i = start + threadIdx.x;
+        unsigned int v = i < ntiles ? tile_sums[i] : 0;
+        unsigned int total;
+        unsigned int ex = block_exclusive_scan(v, &total);
+        unsigned int c = carry;
+        if (i < ntiles) tile_sums[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+}
+// writes out[0..n) = exclusive prefix and out[n] = total
+__global__ void k_scan_apply(const unsigned int* __restrict__ in, size_t n, const unsigned int* __restrict__ tile_sums,
+                             unsigned int* out) {
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    unsigned int v[SCAN_ITEMS];
+    unsigned int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        s += v[k];
+    }
+    unsigned int total;
+    unsigned int ex = block_exclusive_scan(s, &total) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+        if (base + k + 1 == n) out[n] = ex;
+    }
+}
+__global__ void k_zero_one(unsigned int* p) { *p = 0; }
+
+int exclusive_scan_u32(Context* ctx, const unsigned int* in, unsigned int* out, size_t n) {
+    if (n == 0) {
+        k_zero_one<<<1, 1, 0, ctx->stream>>>(out);
+        ctx->launches++;
+        NB2_CUDA(ctx, cudaGetLastError());
+        return NB2_OK;
+    }
+    unsigned int ntiles = (unsigned int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    NB2_TRY(ctx->scan_tmp.reserve(ctx, ntiles + 1));
+    k_scan_tile_sums<<<ntiles, SCAN_TPB, 0, ctx->stream>>>(in, n, ctx->scan_tmp.p);
+    k_scan_sums<<<1, SCAN_TPB, 0, ctx->stream>>>(ctx->scan_tmp.p, ntiles);
+    k_scan_apply<<<ntiles, SCAN_TPB, 0, ctx->stream>>>(in, n, ctx->scan_tmp.p, out);
+    ctx->launches += 3;
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
+// ------------------------------------------------------------------ input validation
+// Bad records are neutralised on device (no host-side scan of the caller's arrays on the step
+// path); the flag is reported by nb2_synchronize / nb2_get_stats / downloads.
+__global__ void k_validate_manifolds(nb2_manifold* m, unsigned int nm, unsigned int nb, unsigned int nc,
+                                     unsigned int* flags) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nm) return;
+    nb2_manifold& mf = m[i];
+    bool bad = mf.body1 < 0 || mf.body2 < 0 || (unsigned int)mf.body1 >= nb || (unsigned int)mf.body2 >= nb ||
+               (unsigned long long)mf.first_contact + mf.num_contacts > nc;
+    bool self = !bad && mf.body1 == mf.body2;
+    if (bad || self) {
+        mf.body1 = 0;
+        mf.body2 = 0;
+        mf.first_contact = 0;
+        mf.num_contacts = 0;
+        atomicOr(flags, bad ? 1u : 2u);
+    }
+}
+__global__ void k_validate_joints(nb2_joint* j, unsigned int nj, unsigned int nb, unsigned int* flags) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nj) return;
+    nb2_joint& jt = j[i];
+    bool bad = jt.body1 < 0 || jt.body2 < 0 || (unsigned int)jt.body1 >= nb || (unsigned int)jt.body2 >= nb ||
+               jt.type >= NB2_JOINT_TYPE_COUNT;
+    bool self = !bad && jt.body1 == jt.body2;
+    if (bad || self) {
+        jt.body1 = 0;
+        jt.body2 = 0;
+        jt.type = NB2_JOINT_BALL;
+        jt.broken = 1;
+        atomicOr(flags, bad ? 1u : 2u);
+    }
+}
+int launch_validate_inputs(Context* ctx) {
+    NB2_TRY(ctx->flags.reserve(ctx, 4));
+    if (ctx->n_manifolds) {
+        k_validate_manifolds<<<nblk(ctx->n_manifolds), TPB, 0, ctx->stream>>>(ctx->manifolds.p, ctx->n_manifolds,
+                                                                              ctx->n_bodies, ctx->n_contacts,
+                                                                              ctx->flags.p);
+        ctx->launches++;
+    }
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+int launch_validate_joints(Context* ctx) {
+    NB2_TRY(ctx->flags.reserve(ctx, 4));
+    if (ctx->n_joints) {
+        k_validate_joints<<<nblk(ctx->n_joints), TPB, 0, ctx->stream>>>(ctx->joints.p, ctx->n_joints, ctx->n_bodies,
+                                                                        ctx->flags.p);
+        ctx->launches++;
+    }
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
+// ------------------------------------------------------------------ items
+__global__ void k_chunk_counts(const nb2_manifold* __restrict__ m, unsigned int nm, unsigned int* counts) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nm) counts[i] = (m[i].num_contacts + NB2_CHUNK - 1) / NB2_CHUNK;
+}
+__global__ void k_fill_chunks(const nb2_manifold* __restrict__ m, unsigned int nm,
+                              const unsigned int* __restrict__ chunk_base, unsigned int* chunk_manifold,
+                              unsigned int* c_manifold) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nm) return;
+    unsigned int cb = chunk_base[i], ce = chunk_base[i + 1];
+    for (unsigned int k = cb; k < ce; ++k) chunk_manifold[k] = i;
+    unsigned int f = m[i].first_contact, nc = m[i].num_contacts;
+    for (unsigned int k = 0; k < nc; ++k) c_manifold[f + k] = i;
+}
+
+__device__ __forceinline__ int dyn_or_neg(const int* status, int b) {
+    return status[b] == NB2_BODY_DYNAMIC ? b : -1;
+}
+__device__ __forceinline__ int joint_max_rows(unsigned int type) {
+    // num_velocity_constraints() of each *_constraint.rs
+    const int rows[NB2_JOINT_TYPE_COUNT] = {3, 5, 7, 4, 3, 4, 4, 4, 6, 3};
+    return rows[type];
+}
+__device__ __forceinline__ int joint_num_position(const nb2_joint& j) {
+    switch (j.type) {
+        case NB2_JOINT_BALL:
+        case NB2_JOINT_CARTESIAN: return 1;
+        case NB2_JOINT_PRISMATIC:
+            return (j.flags & (NB2_JOINT_FLAG_MIN_OFFSET | NB2_JOINT_FLAG_MAX_OFFSET)) ? 3 : 2;
+        default: return 2;
+    }
+}
+
+// One thread per potential item.  Velocity schedule layout:
+//   [0, nJ) joints | [nJ, nJ+maxc) contact chunks (coloured: all rows; reference: friction rows)
+//   | [nJ+maxc, nJ+2maxc) reference order only: normal rows of the chunks
+// Position schedule (reference order only): [0,nJ) joints | [nJ, nJ+maxc) chunks.
+__global__ void k_build_items(int mode, int position, unsigned int nJ, unsigned int maxc,
+                              const nb2_joint* __restrict__ joints, const nb2_manifold* __restrict__ manifolds,
+                              const unsigned int* __restrict__ chunk_base, unsigned int nM,
+                              const unsigned int* __restrict__ chunk_manifold, const int* __restrict__ status,
+                              int* it_a, int* it_b, int* it_nrows, int* it_type, int* it_src,
+                              unsigned long long* it_key, size_t n_items) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    int a = -1, b = -1, nrows = 0, type = NB2_ITEM_INVALID, src = 0;
+    unsigned long long key = 0;
+    if (i < nJ) {
+        const nb2_joint& j = joints[i];
+        a = dyn_or_neg(status, j.body1);
+        b = dyn_or_neg(status, j.body2);
+        // active_joints filter of mechanical_world.rs:274-279 (+ is_active, joint_constraint.rs:219-228)
+        if (!j.broken && (a >= 0 || b >= 0)) {
+            type = NB2_ITEM_JOINT;
+            src = (int)i;
+            nrows = position ? joint_num_position(j) : joint_max_rows(j.type);
+            unsigned long long bucket = position ? 0ull : ((a < 0 || b < 0) ? 1ull : 0ull);
+            key = (bucket << 40) | (unsigned long long)i;
+        }
+    } else {
+        size_t k = i - nJ;
+        int second = 0;
+        if (k >= maxc) {
+            k -= maxc;
+            second = 1;
+        }
+        unsigned int total = chunk_base[nM];
+        if (k < total) {
+            unsigned int m = chunk_manifold[k];
+            const nb2_manifold& mf = manifolds[m];
+            a = dyn_or_neg(status, mf.body1);
+            b = dyn_or_neg(status, mf.body2);
+            if (a >= 0 || b >= 0) {
+                int local = (int)(k - chunk_base[m]);
+                int ncc = min(NB2_CHUNK, (int)mf.num_contacts - NB2_CHUNK * local);
+                src = (int)k;
+                bool ground = (a < 0 || b < 0);
+                if (position) {
+                    type = NB2_ITEM_CONTACTS;
+                    nrows = ncc;
+                    key = (1ull << 40) | k;
+                } else if (mode == NB2_MODE_COLOURED) {
+                    type = NB2_ITEM_CONTACTS;
+                    nrows = 3 * ncc;
+                } else if (!second) {
+                    type = NB2_ITEM_FRICTION;
+                    nrows = 2 * ncc;
+                    key = ((ground ? 3ull : 2ull) << 40) | k;
+                } else {
+                    type = NB2_ITEM_NORMAL;
+                    nrows = ncc;
+                    key = ((ground ? 5ull : 4ull) << 40) | k;
+                }
+            }
+        }
+    }
+    it_a[i] = a;
+    it_b[i] = b;
+    it_nrows[i] = nrows;
+    it_type[i] = type;
+    it_src[i] = src;
+    it_key[i] = key;
+}
+
+static int reserve_sched(Context* ctx, Sched* s, size_t n_items, size_t max_phases) {
+    s->n_items = n_items;
+    s->max_phases = max_phases;
+    NB2_TRY(s->it_a.reserve(ctx, n_items));
+    NB2_TRY(s->it_b.reserve(ctx, n_items));
+    NB2_TRY(s->it_nrows.reserve(ctx, n_items));
+    NB2_TRY(s->it_type.reserve(ctx, n_items));
+    NB2_TRY(s->it_src.reserve(ctx, n_items));
+    NB2_TRY(s->it_key.reserve(ctx, n_items));
+    NB2_TRY(s->it_phase.reserve(ctx, n_items));
+    NB2_TRY(s->it_slot.reserve(ctx, n_items));
+    NB2_TRY(s->ph_count.reserve(ctx, max_phases + 1));
+    NB2_TRY(s->ph_R.reserve(ctx, max_phases + 1));
+    NB2_TRY(s->ph_gbase.reserve(ctx, max_phases + 1));
+    NB2_TRY(s->ph_rbase.reserve(ctx, max_phases + 1));
+    NB2_TRY(s->g_info.reserve(ctx, n_items));
+    NB2_TRY(s->hdr.reserve(ctx, 1));
+    return NB2_OK;
+}
+
+int launch_build_items(Context* ctx, int mode) {
+    const unsigned int nM = ctx->n_manifolds, nJ = ctx->n_joints;
+    const size_t maxc = ctx->max_chunks;
+    // chunk bookkeeping
+    NB2_TRY(ctx->chunk_base.reserve(ctx, nM + 2));
+    NB2_TRY(ctx->chunk_manifold.reserve(ctx, maxc + 1));
+    NB2_TRY(ctx->c_manifold.reserve(ctx, ctx->n_contacts + 1));
+    NB2_TRY(ctx->deg.reserve(ctx, (size_t)nM + 1));  // reused as scan input
+    // contacts not owned by a (valid) manifold stay unmapped and are skipped by assembly
+    NB2_CUDA(ctx, cudaMemsetAsync(ctx->c_manifold.p, 0xFF, ((size_t)ctx->n_contacts + 1) * sizeof(unsigned int),
+                                  ctx->stream));
+    if (nM) {
+        k_chunk_counts<<<nblk(nM), TPB, 0, ctx->stream>>>(ctx->manifolds.p, nM, ctx->deg.p);
+        ctx->launches++;
+    }
+    NB2_TRY(exclusive_scan_u32(ctx, ctx->deg.p, ctx->chunk_base.p, nM));
+    if (nM) {
+        k_fill_chunks<<<nblk(nM), TPB, 0, ctx->stream>>>(ctx->manifolds.p, nM, ctx->chunk_base.p,
+                                                         ctx->chunk_manifold.p, ctx->c_manifold.p);
+        ctx->launches++;
+    }
+    const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
+    size_t n_items = nJ + (ref ? 2 : 1) * maxc;
+    NB2_TRY(reserve_sched(ctx, &ctx->vs, n_items, ref ? n_items : NB2_MAX_COLOURS));
+    if (n_items) {
+        k_build_items<<<nblk(n_items), TPB, 0, ctx->stream>>>(
+            mode, 0, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
+            ctx->chunk_manifold.p, ctx->b_status.p, ctx->vs.it_a.p, ctx->vs.it_b.p, ctx->vs.it_nrows.p,
+            ctx->vs.it_type.p, ctx->vs.it_src.p, ctx->vs.it_key.p, n_items);
+        ctx->launches++;
+    }
+    if (ref) {
+        size_t np = nJ + maxc;
+        NB2_TRY(reserve_sched(ctx, &ctx->ps, np, np));
+        if (np) {
+            k_build_items<<<nblk(np), TPB, 0, ctx->stream>>>(
+                mode, 1, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
+                ctx->chunk_manifold.p, ctx->b_status.p, ctx->ps.it_a.p, ctx->ps.it_b.p, ctx->ps.it_nrows.p,
+                ctx->ps.it_type.p, ctx->ps.it_src.p, ctx->ps.it_key.p, np);
+            ctx->launches++;
+        }
+    }
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
+// ------------------------------------------------------------------ reference order: levels
+__global__ void k_degree(const int* __restrict__ it_a, const int* __restrict__ it_b, const int* __restrict__ it_type,
+                         size_t n, unsigned int* deg) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || it_type[i] == NB2_ITEM_INVALID) return;
+    int a = it_a[i], b = it_b[i];
+    if (a >= 0) atomicAdd(&deg[a], 1u);
+    if (b >= 0 && b != a) atomicAdd(&deg[b], 1u);
+}
+__global__ void k_fill_adj(const int* __restrict__ it_a, const int* __restrict__ it_b, const int* __restrict__ it_type,
+                           size_t n, const unsigned int* __restrict__ adj_off, unsigned int* cursor, int* adj) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || it_type[i] == NB2_ITEM_INVALID) return;
+    int a = it_a[i], b = it_b[i];
+    if (a >= 0) adj[adj_off[a] + atomicAdd(&cursor[a], 1u)] = (int)i;
+    if (b >= 0 && b != a) adj[adj_off[b] + atomicAdd(&cursor[b], 1u)] = (int)i;
+}
+// one thread per body: order its incident groups by sweep key, then link each group to its
+// predecessor on this body
+__global__ void k_sort_adj_link(unsigned int nb, const unsigned int* __restrict__ adj_off, int* adj,
+                                const unsigned long long* __restrict__ key, const int* __restrict__ it_a,
+                                int* pred_a, int* pred_b) {
+    unsigned int body = blockIdx.x * blockDim.x + threadIdx.x;
+    if (body >= nb) return;
+    unsigned int s = adj_off[body], e = adj_off[body + 1];
+    for (unsigned int i = s + 1; i < e; ++i) {  // insertion sort (segments are short)
+        int v = adj[i];
+        unsigned long long kv = key[v];
+        unsigned int j = i;
+        while (j > s && key[adj[j - 1]] > kv) {
+            adj[j] = adj[j - 1];
+            --j;
+        }
+        adj[j] = v;
+    }
+    int prev = -1;
+    for (unsigned int i = s; i < e; ++i) {
+        int v = adj[i];
+        if (it_a[v] == (int)body)
+            pred_a[v] = prev;
+        else
+            pred_b[v] = prev;
+        prev = v;
+    }
+}
+__global__ void k_fill_int(int* p, size_t n, int v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// cooperative: iterate level[i] = 1 + max(level[pred]) to the fixed point
+__global__ void __launch_bounds__(TPB) k_levelise(size_t n, const int* __restrict__ it_type,
+                                                  const int* __restrict__ pred_a, const int* __restrict__ pred_b,
+                                                  int* level, unsigned int* flags /*3*/, unsigned int* barrier) {
+    GridBarrier gb;
+    gb.init(barrier);
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (unsigned int round = 0;; ++round) {
+        unsigned int changed = 0;
+        for (size_t i = tid; i < n; i += stride) {
+            if (it_type[i] == NB2_ITEM_INVALID) continue;
+            int pa = pred_a[i], pb = pred_b[i];
+            int la = pa >= 0 ? __ldcg(&level[pa]) : -1;
+            int lb = pb >= 0 ? __ldcg(&level[pb]) : -1;
+            int nl = max(la, lb) + 1;
+            if (nl > __ldcg(&level[i])) {
+                __stcg(&level[i], nl);
+                changed = 1;
+            }
+        }
+        if (__syncthreads_or(changed) && threadIdx.x == 0) atomicOr(&flags[round % 3], 1u);
+        gb.sync();
+        unsigned int any = *((volatile unsigned int*)&flags[round % 3]);
+        if (tid == 0) flags[(round + 2) % 3] = 0;
+        if (!any) break;
+    }
+}
+
+// ------------------------------------------------------------------ coloured: Jones-Plassmann
+__device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+__global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict__ it_a, const int* __restrict__ it_b,
+                                                const int* __restrict__ it_type, int* phase,
+                                                unsigned long long* cmask, unsigned long long* best,
+                                                unsigned int* flags /*3*/, SchedHeader* hdr, unsigned int* barrier) {
+    GridBarrier gb;
+    gb.init(barrier);
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (unsigned int round = 1;; ++round) {
+        // A: every uncoloured group bids on its bodies
+        unsigned int pending = 0;
+        for (size_t i = tid; i < n; i += stride) {
+            if (it_type[i] == NB2_ITEM_INVALID || phase[i] >= 0) continue;
+            pending = 1;
+            unsigned long long prio = ((unsigned long long)round << 52) |
+                                      ((unsigned long long)(hash_u32((unsigned int)i) & 0xFFFFFu) << 32) |
+                                      (unsigned long long)(unsigned int)i;
+            int a = it_a[i], b = it_b[i];
+            if (a >= 0) atomicMax(&best[a], prio);
+            if (b >= 0) atomicMax(&best[b], prio);
+        }
+        if (__syncthreads_or(pending) && threadIdx.x == 0) atomicOr(&flags[round % 3], 1u);
+        gb.sync();
+        unsigned int any = *((volatile unsigned int*)&flags[round % 3]);
+        if (tid == 0) flags[(round + 2) % 3] = 0;
+        if (!any) break;
+        // B: the winner on both of its bodies takes the lowest free colour
+        for (size_t i = tid; i < n; i += stride) {
+            if (it_type[i] == NB2_ITEM_INVALID || phase[i] >= 0) continue;
+            unsigned long long prio = ((unsigned long long)round << 52) |
+                                      ((unsigned long long)(hash_u32((unsigned int)i) & 0xFFFFFu) << 32) |
+                                      (unsigned long long)(unsigned int)i;
+            int a = it_a[i], b = it_b[i];
+            if (a >= 0 && __ldcg(&best[a]) != prio) continue;
+            if (b >= 0 && __ldcg(&best[b]) != prio) continue;
+            int colour = -1;
+#pragma unroll
+            for (int w = 0; w < NB2_MASK_WORDS; ++w) {
+                unsigned long long used = 0;
+                if (a >= 0) used |= __ldcg(&cmask[(size_t)a * NB2_MASK_WORDS + w]);
+                if (b >= 0) used |= __ldcg(&cmask[(size_t)b * NB2_MASK_WORDS + w]);
+                if (colour < 0 && used != ~0ull) {
+                    int bit = __ffsll((long long)~used) - 1;
+                    colour = w * 64 + bit;
+                    unsigned long long m = 1ull << bit;
+                    if (a >= 0) __stcg(&cmask[(size_t)a * NB2_MASK_WORDS + w], used | m);
+                    if (b >= 0) __stcg(&cmask[(size_t)b * NB2_MASK_WORDS + w], used | m);
+                }
+            }
+            if (colour < 0) {
+                colour = NB2_MAX_COLOURS - 1;
+                atomicOr(&hdr->overflow, 1u);
+            }
+            phase[i] = colour;
+        }
+        gb.sync();
+    }
+}
+
+// ------------------------------------------------------------------ layout
+__global__ void k_phase_hist(size_t n, const int* __restrict__ it_type, const int* __restrict__ it_nrows,
+                             const int* __restrict__ phase, int* slot, unsigned int* ph_count, unsigned int* ph_R,
+                             SchedHeader* hdr, unsigned int max_phases) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || it_type[i] == NB2_ITEM_INVALID) return;
+    unsigned int p = (unsigned int)phase[i];
+    if (p >= max_phases) {
+        p = max_phases - 1;
+        atomicOr(&hdr->overflow, 2u);
+    }
+    slot[i] = (int)atomicAdd(&ph_count[p], 1u);
+    atomicMax(&ph_R[p], (unsigned int)it_nrows[i]);
+    atomicMax(&hdr->n_phases, p + 1);
+}
+__global__ void k_phase_scan(unsigned int* ph_count, unsigned int* ph_R, unsigned int* ph_gbase,
+                             unsigned int* ph_rbase, SchedHeader* hdr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned int g = 0, r = 0;
+    unsigned int np = hdr->n_phases;
+    for (unsigned int p = 0; p < np; ++p) {
+        ph_gbase[p] = g;
+        ph_rbase[p] = r;
+        g += ph_count[p];
+        r += ph_count[p] * ph_R[p];
+    }
+    ph_gbase[np] = g;
+    ph_rbase[np] = r;
+    hdr->n_groups = g;
+    hdr->n_slots = r;
+}
+__global__ void k_fill_ginfo(size_t n, const int* __restrict__ it_type, const int* __restrict__ it_a,
+                             const int* __restrict__ it_b, const int* __restrict__ it_nrows,
+                             const int* __restrict__ phase, const int* __restrict__ slot,
+                             const unsigned int* __restrict__ ph_gbase, int4* g_info, unsigned int max_phases) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || it_type[i] == NB2_ITEM_INVALID) return;
+    unsigned int p = min((unsigned int)phase[i], max_phases - 1);
+    g_info[ph_gbase[p] + slot[i]] = make_int4(it_a[i], it_b[i], it_nrows[i], (int)i);
+}
+__global__ void k_copy_phase(size_t n, const int* __restrict__ level, int* phase) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) phase[i] = level[i];
+}
+
+template <typename K>
+static int coop_blocks(Context* ctx, K kernel, int* cache) {
+    if (*cache > 0) return NB2_OK;
+    int per_sm = 0;
+    NB2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPB, 0));
+    if (per_sm < 1) return set_error(ctx, NB2_ERR_CUDA, "cooperative kernel does not fit on an SM");
+    if (per_sm > 4) per_sm = 4;
+    *cache = per_sm * ctx->sm_count;
+    return NB2_OK;
+}
+
+int launch_schedule(Context* ctx, Sched* s, int mode) {
+    const size_t n = s->n_items;
+    const unsigned int nb = ctx->n_bodies;
+    NB2_CUDA(ctx, cudaMemsetAsync(s->hdr.p, 0, sizeof(SchedHeader), ctx->stream));
+    NB2_CUDA(ctx, cudaMemsetAsync(s->ph_count.p, 0, (s->max_phases + 1) * sizeof(unsigned int), ctx->stream));
+    NB2_CUDA(ctx, cudaMemsetAsync(s->ph_R.p, 0, (s->max_phases + 1) * sizeof(unsigned int), ctx->stream));
+    if (n == 0) {
+        k_phase_scan<<<1, 1, 0, ctx->stream>>>(s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
+        ctx->launches++;
+        NB2_CUDA(ctx, cudaGetLastError());
+        return NB2_OK;
+    }
+    NB2_TRY(ctx->barrier.reserve(ctx, 8));
+    NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
+    unsigned int* flags = ctx->barrier.p + 4;
+    static int blocks_level = 0, blocks_colour = 0;
+    if (mode == NB2_MODE_REFERENCE_ORDER) {
+        NB2_TRY(ctx->deg.reserve(ctx, (size_t)nb + 1));
+        DevBuf<unsigned int>& adj_off = (s == &ctx->ps) ? ctx->adj_off_p : ctx->adj_off;
+        DevBuf<int>& adj = (s == &ctx->ps) ? ctx->adj_p : ctx->adj;
+        NB2_TRY(adj_off.reserve(ctx, (size_t)nb + 2));
+        NB2_TRY(ctx->cursor.reserve(ctx, (size_t)nb + 1));
+        NB2_TRY(adj.reserve(ctx, 2 * n + 1));
+        NB2_TRY(ctx->pred_a.reserve(ctx, n));
+        NB2_TRY(ctx->pred_b.reserve(ctx, n));
+        NB2_TRY(ctx->level.reserve(ctx, n));
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->deg.p, 0, ((size_t)nb + 1) * sizeof(unsigned int), ctx->stream));
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->cursor.p, 0, ((size_t)nb + 1) * sizeof(unsigned int), ctx->stream));
+        k_degree<<<nblk(n), TPB, 0, ctx->stream>>>(s->it_a.p, s->it_b.p, s->it_type.p, n, ctx->deg.p);
+        ctx->launches++;
+        NB2_TRY(exclusive_scan_u32(ctx, ctx->deg.p, adj_off.p, nb));
+        k_fill_adj<<<nblk(n), TPB, 0, ctx->stream>>>(s->it_a.p, s->it_b.p, s->it_type.p, n, adj_off.p,
+                                                     ctx->cursor.p, adj.p);
+        k_fill_int<<<nblk(n), TPB, 0, ctx->stream>>>(ctx->pred_a.p, n, -1);
+        k_fill_int<<<nblk(n), TPB, 0, ctx->stream>>>(ctx->pred_b.p, n, -1);
+        k_fill_int<<<nblk(n), TPB, 0, ctx->stream>>>(ctx->level.p, n, 0);
+        k_sort_adj_link<<<nblk(nb), TPB, 0, ctx->stream>>>(nb, adj_off.p, adj.p, s->it_key.p, s->it_a.p,
+                                                           ctx->pred_a.p, ctx->pred_b.p);
+        ctx->launches += 5;
+        NB2_TRY(coop_blocks(ctx, k_levelise, &blocks_level));
+        int blocks = (int)min((size_t)blocks_level, (n + TPB - 1) / TPB);
+        size_t n_ = n;
+        const int* ty = s->it_type.p;
+        const int* pa = ctx->pred_a.p;
+        const int* pb = ctx->pred_b.p;
+        int* lv = ctx->level.p;
+        unsigned int* bar = ctx->barrier.p;
+        void* args[] = {&n_, &ty, &pa, &pb, &lv, &flags, &bar};
+        NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_levelise, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
+        k_copy_phase<<<nblk(n), TPB, 0, ctx->stream>>>(n, ctx->level.p, s->it_phase.p);
+        ctx->launches += 2;
+    } else {
+        NB2_TRY(ctx->cmask.reserve(ctx, (size_t)nb * NB2_MASK_WORDS + 1));
+        NB2_TRY(ctx->best.reserve(ctx, (size_t)nb + 1));
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->cmask.p, 0, (size_t)nb * NB2_MASK_WORDS * sizeof(unsigned long long),
+                                      ctx->stream));
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->best.p, 0, (size_t)nb * sizeof(unsigned long long), ctx->stream));
+        k_fill_int<<<nblk(n), TPB, 0, ctx->stream>>>(s->it_phase.p, n, -1);
+        ctx->launches++;
+        NB2_TRY(coop_blocks(ctx, k_colour, &blocks_colour));
+        int blocks = (int)min((size_t)blocks_colour, (n + TPB - 1) / TPB);
+        size_t n_ = n;
+        const int* ia = s->it_a.p;
+        const int* ib = s->it_b.p;
+        const int* ty = s->it_type.p;
+        int* ph = s->it_phase.p;
+        unsigned long long* cm = ctx->cmask.p;
+        unsigned long long* be = ctx->best.p;
+        SchedHeader* hd = s->hdr.p;
+        unsigned int* bar = ctx->barrier.p;
+        void* args[] = {&n_, &ia, &ib, &ty, &ph, &cm, &be, &flags, &hd, &bar};
+        NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_colour, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
+        ctx->launches++;
+    }
+    k_phase_hist<<<nblk(n), TPB, 0, ctx->stream>>>(n, s->it_type.p, s->it_nrows.p, s->it_phase.p, s->it_slot.p,
+                                                   s->ph_count.p, s->ph_R.p, s->hdr.p, (unsigned int)s->max_phases);
+    k_phase_scan<<<1, 1, 0, ctx->stream>>>(s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
+    k_fill_ginfo<<<nblk(n), TPB, 0, ctx->stream>>>(n, s->it_type.p, s->it_a.p, s->it_b.p, s->it_nrows.p,
+                                                   s->it_phase.p, s->it_slot.p, s->ph_gbase.p, s->g_info.p,
+                                                   (unsigned int)s->max_phases);
+    ctx->launches += 3;
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
+}  // namespace nb2

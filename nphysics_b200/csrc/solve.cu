@@ -1,0 +1,804 @@
+// The two projected Gauss-Seidel loops as persistent cooperative kernels.
+//
+// k_velocity_solve replaces SORProx::solve (src/solver/sor_prox.rs:48-436): warm start, then
+// max_velocity_iterations sweeps.  Each sweep walks the phases of the schedule in order with a
+// grid barrier between phases; inside a phase one thread owns one group (rows sharing a body
+// pair), keeps the two bodies' mj_lambda in registers and streams its rows from the ELL planes.
+// k_position_solve replaces NonlinearSORProx::solve (src/solver/nonlinear_sor_prox.rs:17-310)
+// with ncollide's ContactKinematic::contact restated for Plane/Point, Point/Plane, Point/Point.
+#include "solver.cuh"
+
+namespace nb2 {
+
+static const int TPB = 128;
+
+struct SchedDev {
+    const unsigned int* ph_count;
+    const unsigned int* ph_gbase;
+    const unsigned int* ph_rbase;
+    const int4* g_info;
+    const SchedHeader* hdr;
+    const int* it_type;
+    const int* it_src;
+    const int* it_a;
+    const unsigned long long* it_key;
+    const int* it_phase;
+    const int* it_slot;
+    unsigned int max_phases;
+};
+static SchedDev sched_dev(const Sched& s) {
+    SchedDev d;
+    d.ph_count = s.ph_count.p;
+    d.ph_gbase = s.ph_gbase.p;
+    d.ph_rbase = s.ph_rbase.p;
+    d.g_info = s.g_info.p;
+    d.hdr = s.hdr.p;
+    d.it_type = s.it_type.p;
+    d.it_src = s.it_src.p;
+    d.it_a = s.it_a.p;
+    d.it_key = s.it_key.p;
+    d.it_phase = s.it_phase.p;
+    d.it_slot = s.it_slot.p;
+    d.max_phases = (unsigned int)s.max_phases;
+    return d;
+}
+
+struct Rows {
+    const float4* jac;
+    const float4* hdr;
+    const int2* meta;
+    float* imp;
+    size_t S;  // plane stride
+};
+
+struct Lam {
+    float v[6];
+};
+__device__ __forceinline__ Lam load_lam(const float4* lam, int b) {
+    Lam l;
+    float4 a = ldcg4(&lam[2 * b]), c = ldcg4(&lam[2 * b + 1]);
+    l.v[0] = a.x; l.v[1] = a.y; l.v[2] = a.z; l.v[3] = c.x; l.v[4] = c.y; l.v[5] = c.z;
+    return l;
+}
+__device__ __forceinline__ void store_lam(float4* lam, int b, const Lam& l) {
+    stcg4(&lam[2 * b], make_float4(l.v[0], l.v[1], l.v[2], 0.f));
+    stcg4(&lam[2 * b + 1], make_float4(l.v[3], l.v[4], l.v[5], 0.f));
+}
+__device__ __forceinline__ float dot6(const float* a, const float* b) {
+    float res = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) res += a[k] * b[k];
+    return res;
+}
+__device__ __forceinline__ void axpy6(float a, const float* x, float* y) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) y[k] = a * x[k] + y[k];
+}
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v > lo ? (v < hi ? v : hi) : lo; }
+
+struct RowJ {
+    float J1[6], J2[6], W1[6], W2[6];
+};
+__device__ __forceinline__ void load_row_j(const Rows& R, size_t slot, bool a, bool b, RowJ* o) {
+    // 24 floats = 6 float4 planes: J1 | J2 | W1 | W2
+    float4 q0, q1, q2, q3, q4, q5;
+    q1 = __ldg(&R.jac[1 * R.S + slot]);
+    q4 = __ldg(&R.jac[4 * R.S + slot]);
+    if (a) {
+        q0 = __ldg(&R.jac[0 * R.S + slot]);
+        q3 = __ldg(&R.jac[3 * R.S + slot]);
+        o->J1[0] = q0.x; o->J1[1] = q0.y; o->J1[2] = q0.z; o->J1[3] = q0.w; o->J1[4] = q1.x; o->J1[5] = q1.y;
+        o->W1[0] = q3.x; o->W1[1] = q3.y; o->W1[2] = q3.z; o->W1[3] = q3.w; o->W1[4] = q4.x; o->W1[5] = q4.y;
+    }
+    if (b) {
+        q2 = __ldg(&R.jac[2 * R.S + slot]);
+        q5 = __ldg(&R.jac[5 * R.S + slot]);
+        o->J2[0] = q1.z; o->J2[1] = q1.w; o->J2[2] = q2.x; o->J2[3] = q2.y; o->J2[4] = q2.z; o->J2[5] = q2.w;
+        o->W2[0] = q4.z; o->W2[1] = q4.w; o->W2[2] = q5.x; o->W2[3] = q5.y; o->W2[4] = q5.z; o->W2[5] = q5.w;
+    }
+}
+
+// One SORProx row update (sor_prox.rs:181-343) on register-resident mj_lambda.
+// Returns the new impulse.
+__device__ __forceinline__ float solve_row(int kind, float4 h, float impulse, float dep_impulse, const RowJ& J,
+                                           bool a, bool b, Lam* la, Lam* lb) {
+    float lo, hi;
+    if (kind == NB2_ROW_UNILATERAL) {
+        lo = 0.f;
+        hi = NB2_F32_MAX;
+    } else if (kind == NB2_ROW_BILATERAL) {
+        lo = h.z;
+        hi = h.w;
+    } else {  // Dependent: sor_prox.rs:251-272
+        if (dep_impulse == 0.f) {
+            if (impulse != 0.f) {
+                if (a) axpy6(-impulse, J.W1, la->v);
+                if (b) axpy6(-impulse, J.W2, lb->v);
+            }
+            return 0.f;
+        }
+        hi = h.z * dep_impulse;
+        lo = -hi;
+    }
+    float d;
+    if (a && b)
+        d = dot6(J.J1, la->v) + dot6(J.J2, lb->v) + h.x;
+    else if (a)
+        d = dot6(J.J1, la->v) + h.x;
+    else
+        d = dot6(J.J2, lb->v) + h.x;
+    float ni;
+    if (kind == NB2_ROW_UNILATERAL)
+        ni = fmaxf(impulse - h.y * d, 0.f);
+    else
+        ni = clampf(impulse - h.y * d, lo, hi);
+    float dl = ni - impulse;
+    if (a) axpy6(dl, J.W1, la->v);
+    if (b) axpy6(dl, J.W2, lb->v);
+    return ni;
+}
+
+// mode_warm: 1 = run a warm-start pass over the phases first (coloured mode)
+__global__ void __launch_bounds__(TPB) k_velocity_solve(SchedDev sd, Rows R, float4* lam, int iters, int mode_warm,
+                                                        unsigned int* barrier) {
+    GridBarrier gb;
+    gb.init(barrier);
+    const unsigned int np = sd.hdr->n_phases;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int it = mode_warm ? -1 : 0; it < iters; ++it) {
+        for (unsigned int p = 0; p < np; ++p) {
+            const unsigned int cnt = sd.ph_count[p];
+            const size_t rbase = sd.ph_rbase[p], gbase = sd.ph_gbase[p];
+            for (size_t g = tid; g < cnt; g += stride) {
+                const int4 info = sd.g_info[gbase + g];
+                const bool a = info.x >= 0, b = info.y >= 0;
+                Lam la, lb;
+                if (a) la = load_lam(lam, info.x);
+                if (b) lb = load_lam(lam, info.y);
+                for (int r = 0; r < info.z; ++r) {
+                    const size_t slot = rbase + (size_t)r * cnt + g;
+                    const int2 meta = __ldg(&R.meta[slot]);
+                    if (meta.x == NB2_ROW_NONE) continue;
+                    float impulse = __ldcg(&R.imp[slot]);
+                    RowJ J;
+                    load_row_j(R, slot, a, b, &J);
+                    if (it < 0) {  // warm start (sor_prox.rs:345-435)
+                        if (impulse != 0.f) {
+                            if (a) axpy6(impulse, J.W1, la.v);
+                            if (b) axpy6(impulse, J.W2, lb.v);
+                        }
+                        continue;
+                    }
+                    const float4 h = __ldg(&R.hdr[slot]);
+                    float dep = 0.f;
+                    if (meta.x == NB2_ROW_DEPENDENT) dep = __ldcg(&R.imp[meta.y]);
+                    float ni = solve_row(meta.x, h, impulse, dep, J, a, b, &la, &lb);
+                    if (ni != impulse) __stcg(&R.imp[slot], ni);
+                }
+                if (a) store_lam(lam, info.x, la);
+                if (b) store_lam(lam, info.y, lb);
+            }
+            gb.sync();
+        }
+    }
+}
+
+// Reference-order warm start: one thread per body accumulates the impulses of its incident rows
+// in the reference's warm-start order (contact unilateral, unilateral_ground, bilateral,
+// bilateral_ground, then the joint buckets; sor_prox.rs:19-45,57-58).
+__global__ void __launch_bounds__(TPB) k_warmstart_ref(unsigned int nb, const unsigned int* __restrict__ adj_off,
+                                                       const int* __restrict__ adj, SchedDev sd, Rows R,
+                                                       const int* __restrict__ it_nrows, float4* lam) {
+    unsigned int body = blockIdx.x * blockDim.x + threadIdx.x;
+    if (body >= nb) return;
+    const unsigned int s = adj_off[body], e = adj_off[body + 1];
+    if (s == e) return;
+    Lam l;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) l.v[k] = 0.f;
+    const int order[6] = {4, 5, 2, 3, 0, 1};
+    for (int ob = 0; ob < 6; ++ob) {
+        const unsigned long long bucket = (unsigned long long)order[ob];
+        for (unsigned int k = s; k < e; ++k) {
+            const int item = adj[k];
+            if ((sd.it_key[item] >> 40) != bucket) continue;
+            const unsigned int p = min((unsigned int)sd.it_phase[item], sd.max_phases - 1);
+            const unsigned int cnt = sd.ph_count[p];
+            const size_t rbase = sd.ph_rbase[p];
+            const bool side_a = sd.it_a[item] == (int)body;
+            const int nrows = it_nrows[item];
+            for (int r = 0; r < nrows; ++r) {
+                const size_t slot = rbase + (size_t)r * cnt + (size_t)sd.it_slot[item];
+                if (R.meta[slot].x == NB2_ROW_NONE) continue;
+                const float impulse = R.imp[slot];
+                if (impulse == 0.f) continue;
+                RowJ J;
+                load_row_j(R, slot, side_a, !side_a, &J);
+                axpy6(impulse, side_a ? J.W1 : J.W2, l.v);
+            }
+        }
+    }
+    store_lam(lam, (int)body, l);
+}
+
+// ------------------------------------------------------------------------------------------
+// position solve
+// ------------------------------------------------------------------------------------------
+struct PosBody {
+    BodyPose bp;
+    float inv_mass;
+    Mat3 inv_i;
+    float mask[6];
+    Vec3 local_com;
+    bool dynamic;
+};
+struct PosArrays {
+    const nb2_body* raw;
+    float4* pos_t;
+    float4* pos_q;
+    float4* com_im;
+    const float4* inv_i;
+};
+__device__ __forceinline__ void load_pos_body(const PosArrays& A, int idx, PosBody* o) {
+    const nb2_body& rb = A.raw[idx];
+    o->dynamic = rb.status == NB2_BODY_DYNAMIC;
+    o->bp.pose.t = f4_xyz(ldcg4(&A.pos_t[idx]));
+    o->bp.pose.r = f4_quat(ldcg4(&A.pos_q[idx]));
+    float4 c = ldcg4(&A.com_im[idx]);
+    o->bp.com = f4_xyz(c);
+    o->inv_mass = c.w;
+    float4 r0 = A.inv_i[3 * idx], r1 = A.inv_i[3 * idx + 1], r2 = A.inv_i[3 * idx + 2];
+    o->inv_i.m[0][0] = r0.x; o->inv_i.m[0][1] = r0.y; o->inv_i.m[0][2] = r0.z;
+    o->inv_i.m[1][0] = r1.x; o->inv_i.m[1][1] = r1.y; o->inv_i.m[1][2] = r1.z;
+    o->inv_i.m[2][0] = r2.x; o->inv_i.m[2][1] = r2.y; o->inv_i.m[2][2] = r2.z;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o->mask[k] = rb.jacobian_mask[k];
+    o->local_com = mk3(rb.local_com[0], rb.local_com[1], rb.local_com[2]);
+}
+__device__ __forceinline__ void store_pos_body(const PosArrays& A, int idx, const PosBody& b) {
+    stcg4(&A.pos_t[idx], xyz_f4(b.bp.pose.t, 0.f));
+    stcg4(&A.pos_q[idx], quat_f4(b.bp.pose.r));
+    stcg4(&A.com_im[idx], xyz_f4(b.bp.com, b.inv_mass));
+}
+// fill_constraint_geometry without velocities: weighted jacobian + inv_r contribution
+__device__ __forceinline__ void pos_fill(const PosBody& b, Vec3 point, bool angular, Vec3 dir, Vec3* wl, Vec3* wa,
+                                         float* inv_r) {
+    if (!b.dynamic) return;
+    Vec3 pos = point - b.bp.com;
+    Vec3 fl = angular ? mk3(0.f, 0.f, 0.f) : dir;
+    Vec3 fa = angular ? dir : cross3(pos, dir);
+    Vec3 ml = mul3(fl, mk3(b.mask[0], b.mask[1], b.mask[2]));
+    Vec3 ma = mul3(fa, mk3(b.mask[3], b.mask[4], b.mask[5]));
+    *wl = ml * b.inv_mass;
+    *wa = mat_vec(b.inv_i, ma);
+    *inv_r += b.inv_mass + dot3(ma, *wa);
+}
+struct PosParams {
+    float erp, allowed_lin, allowed_ang, max_lin, max_ang;
+};
+__device__ __forceinline__ float clamp_rhs(float rhs, bool angular, const PosParams& P) {
+    if (angular) return fmaxf((rhs + P.allowed_ang) * P.erp, -P.max_ang);
+    return fmaxf((rhs + P.allowed_lin) * P.erp, -P.max_lin);
+}
+// GenericNonlinearConstraint resolution (helper position generators + solve_generic,
+// nonlinear_sor_prox.rs:78-119)
+__device__ __forceinline__ void solve_generic(PosBody* b1, PosBody* b2, Vec3 a1, Vec3 a2, bool angular, Vec3 dir,
+                                              float rhs_in, const PosParams& P) {
+    Vec3 w1l = mk3(0.f, 0.f, 0.f), w1a = w1l, w2l = w1l, w2a = w1l;
+    float inv_r = 0.f;
+    pos_fill(*b1, a1, angular, dir, &w1l, &w1a, &inv_r);
+    pos_fill(*b2, a2, angular, -dir, &w2l, &w2a, &inv_r);
+    float r = inv_r != 0.f ? 1.f / inv_r : 1.f;
+    float rhs = clamp_rhs(rhs_in, angular, P);
+    if (rhs < 0.f) {
+        float impulse = -rhs * r;
+        if (b1->dynamic) apply_displacement(&b1->bp, b1->local_com, w1l * impulse, w1a * impulse);
+        if (b2->dynamic) apply_displacement(&b2->bp, b2->local_com, w2l * impulse, w2a * impulse);
+    }
+}
+__device__ __forceinline__ Vec3 pi_fallback_axis(Vec3 axis1) {  // helper.rs:720-724
+    int imin = 0;
+    float best = fabsf(axis1.x);
+    if (fabsf(axis1.y) < best) {
+        best = fabsf(axis1.y);
+        imin = 1;
+    }
+    if (fabsf(axis1.z) < best) imin = 2;
+    Vec3 e = mk3(imin == 0 ? 1.f : 0.f, imin == 1 ? 1.f : 0.f, imin == 2 ? 1.f : 0.f);
+    Vec3 c = cross3(e, axis1);
+    return (c / norm3(c)) * NB2_PI;
+}
+
+// the position constraints of one joint, in the reference's order
+__device__ void joint_position(const nb2_joint& j, PosBody* b1, PosBody* b2, const PosParams& P) {
+    const Vec3 ax1 = mk3(j.axis1[0], j.axis1[1], j.axis1[2]);
+    const Vec3 ax2 = mk3(j.axis2[0], j.axis2[1], j.axis2[2]);
+    const Vec3 ax3 = mk3(j.axis3[0], j.axis3[1], j.axis3[2]);
+    int n;
+    switch (j.type) {
+        case NB2_JOINT_BALL:
+        case NB2_JOINT_CARTESIAN: n = 1; break;
+        case NB2_JOINT_PRISMATIC: n = (j.flags & (NB2_JOINT_FLAG_MIN_OFFSET | NB2_JOINT_FLAG_MAX_OFFSET)) ? 3 : 2; break;
+        default: n = 2; break;
+    }
+    for (int i = 0; i < n; ++i) {
+        Pose pos1, pos2;
+        pos1.t = b1->bp.pose.t + quat_rotate(b1->bp.pose.r, mk3(j.anchor1[0], j.anchor1[1], j.anchor1[2]));
+        pos1.r = b1->bp.pose.r;
+        pos2.t = b2->bp.pose.t + quat_rotate(b2->bp.pose.r, mk3(j.anchor2[0], j.anchor2[1], j.anchor2[2]));
+        pos2.r = b2->bp.pose.r;
+        if (j.type == NB2_JOINT_FIXED || j.type == NB2_JOINT_CARTESIAN) {
+            pos1.r = quat_mul(pos1.r, mkq(j.ref_frame1[0], j.ref_frame1[1], j.ref_frame1[2], j.ref_frame1[3]));
+            pos2.r = quat_mul(pos2.r, mkq(j.ref_frame2[0], j.ref_frame2[1], j.ref_frame2[2], j.ref_frame2[3]));
+        }
+        const Vec3 a1 = pos1.t, a2 = pos2.t;
+        // 0 translation, 1 align_axis, 2 rotation, 3 project, 4 limits, 5 restore angle, 6 translation wrt axis
+        int what = -1;
+        Vec3 u = mk3(0.f, 0.f, 0.f), v = u;
+        switch (j.type) {
+            case NB2_JOINT_BALL: what = 0; break;
+            case NB2_JOINT_REVOLUTE:
+                what = i == 0 ? 0 : 1;
+                u = quat_rotate(pos1.r, ax1);
+                v = quat_rotate(pos2.r, ax2);
+                break;
+            case NB2_JOINT_PRISMATIC:
+                what = i == 0 ? 2 : (i == 1 ? 3 : 4);
+                u = quat_rotate(pos1.r, ax1);
+                break;
+            case NB2_JOINT_UNIVERSAL:
+                what = i == 0 ? 0 : 5;
+                u = quat_rotate(pos1.r, ax1);
+                v = quat_rotate(pos2.r, ax2);
+                break;
+            case NB2_JOINT_PLANAR:
+                what = i == 0 ? 6 : 1;
+                u = quat_rotate(pos1.r, ax1);
+                v = quat_rotate(pos2.r, ax2);
+                break;
+            case NB2_JOINT_RECTANGULAR:
+                what = i == 0 ? 6 : 2;
+                u = quat_rotate(pos1.r, ax1);
+                break;
+            case NB2_JOINT_PIN_SLOT:
+                what = i == 0 ? 1 : 3;
+                if (i == 0) {
+                    u = quat_rotate(pos1.r, ax3);
+                    v = quat_rotate(pos2.r, ax2);
+                } else {
+                    u = quat_rotate(pos1.r, ax1);
+                }
+                break;
+            case NB2_JOINT_CYLINDRICAL:
+                what = i == 0 ? 1 : 3;
+                u = quat_rotate(pos1.r, ax1);
+                v = quat_rotate(pos2.r, ax2);
+                break;
+            case NB2_JOINT_FIXED: what = i == 0 ? 2 : 0; break;
+            case NB2_JOINT_CARTESIAN: what = 2; break;
+            default: break;
+        }
+        Vec3 dir;
+        float depth;
+        switch (what) {
+            case 0:  // cancel_relative_translation (helper.rs:364-417)
+                if (unit_try_new_and_get(a2 - a1, P.allowed_lin, &dir, &depth))
+                    solve_generic(b1, b2, a1, a2, false, dir, -depth, P);
+                break;
+            case 1: {  // align_axis (helper.rs:701-766)
+                Vec3 error;
+                Quat rot;
+                if (quat_rotation_between_axis(u, v, &rot)) error = quat_scaled_axis(rot);
+                else error = pi_fallback_axis(u);
+                if (unit_try_new_and_get(error, P.allowed_ang, &dir, &depth))
+                    solve_generic(b1, b2, a1, a2, true, dir, -depth, P);
+                break;
+            }
+            case 2: {  // cancel_relative_rotation (helper.rs:553-608)
+                Vec3 error = quat_scaled_axis(quat_mul(pos2.r, quat_conj(pos1.r)));
+                if (unit_try_new_and_get(error, P.allowed_ang, &dir, &depth))
+                    solve_generic(b1, b2, a1, a2, true, dir, -depth, P);
+                break;
+            }
+            case 3: {  // project_anchor_to_axis (helper.rs:858-915)
+                Vec3 dpt = a2 - a1;
+                Vec3 proj = a1 + u * dot3(u, dpt);
+                Vec3 error = a2 - proj;
+                if (unit_try_new_and_get(error, P.allowed_lin, &dir, &depth))
+                    solve_generic(b1, b2, a1, a2, false, dir, -depth, P);
+                break;
+            }
+            case 4: {  // build_linear_limits_position_constraint (unit_constraint.rs:127-197)
+                float offset = dot3(u, a2 - a1);
+                float error = 0.f;
+                dir = u;
+                if (j.flags & NB2_JOINT_FLAG_MIN_OFFSET) {
+                    error = j.min_offset - offset;
+                    dir = -u;
+                }
+                if (error < 0.f && (j.flags & NB2_JOINT_FLAG_MAX_OFFSET)) {
+                    error = offset - j.max_offset;
+                    dir = u;
+                }
+                if (error > P.allowed_lin) solve_generic(b1, b2, a1, a2, false, dir, -error, P);
+                break;
+            }
+            case 5: {  // restore_angle_between_axis (helper.rs:921-998)
+                Vec3 sep;
+                Quat rot;
+                if (quat_rotation_between_axis(u, v, &rot)) sep = quat_scaled_axis(rot);
+                else sep = pi_fallback_axis(u);
+                float curr;
+                if (unit_try_new_and_get(sep, NB2_F32_EPS, &dir, &curr)) {
+                    float error = curr - j.angle;
+                    if (error < 0.f) {
+                        error = -error;
+                        dir = -dir;
+                    }
+                    if (!(error < P.allowed_ang)) solve_generic(b1, b2, a1, a2, true, dir, -error, P);
+                }
+                break;
+            }
+            case 6: {  // cancel_relative_translation_wrt_axis (helper.rs:298-359)
+                depth = dot3(u, a2 - a1);
+                dir = u;
+                if (depth < 0.f) {
+                    depth = -depth;
+                    dir = -u;
+                }
+                if (depth > P.allowed_lin) solve_generic(b1, b2, a1, a2, false, dir, -depth, P);
+                break;
+            }
+            default: break;
+        }
+    }
+}
+
+struct ContactEval {
+    Vec3 world1, world2, normal;
+    float depth;
+};
+// ncollide ContactKinematic::contact
+__device__ __forceinline__ bool kinematic_contact(float4 l1, float4 l2, float4 d1, float4 d2, float4 n1,
+                                                  const Pose& m1, const Pose& m2, ContactEval* o) {
+    const int g1 = __float_as_int(d1.w), g2 = __float_as_int(d2.w);
+    Vec3 world1 = pose_point(m1, f4_xyz(l1));
+    Vec3 world2 = pose_point(m2, f4_xyz(l2));
+    Vec3 normal;
+    float depth;
+    if (g1 == NB2_GEOM_PLANE && g2 == NB2_GEOM_POINT) {
+        normal = quat_rotate(m1.r, f4_xyz(d1));
+        depth = -dot3(normal, world2 - world1);
+        world1 = world2 + normal * depth;
+    } else if (g1 == NB2_GEOM_POINT && g2 == NB2_GEOM_PLANE) {
+        Vec3 wn2 = quat_rotate(m2.r, f4_xyz(d2));
+        depth = -dot3(wn2, world1 - world2);
+        world2 = world1 + wn2 * depth;
+        normal = -wn2;
+    } else if (g1 == NB2_GEOM_POINT && g2 == NB2_GEOM_POINT) {
+        Vec3 n;
+        float d;
+        if (unit_try_new_and_get(world2 - world1, NB2_F32_EPS, &n, &d)) {
+            depth = -d;
+            normal = n;
+        } else {
+            depth = 0.f;
+            normal = quat_rotate(m1.r, f4_xyz(n1));
+        }
+    } else {
+        return false;
+    }
+    world1 = world1 + normal * l1.w;
+    world2 = world2 + normal * (-l2.w);
+    depth += l1.w + l2.w;
+    o->world1 = world1;
+    o->world2 = world2;
+    o->normal = normal;
+    o->depth = depth;
+    return true;
+}
+__device__ __forceinline__ Pose load_coll(const float* p) {
+    Pose r;
+    r.t = mk3(p[0], p[1], p[2]);
+    r.r = mkq(p[3], p[4], p[5], p[6]);
+    return r;
+}
+
+__global__ void __launch_bounds__(TPB) k_position_solve(SchedDev sd, PosArrays A, const nb2_joint* __restrict__ joints,
+                                                        const nb2_manifold* __restrict__ manifolds,
+                                                        const unsigned int* __restrict__ chunk_manifold,
+                                                        const float4* __restrict__ p_row, size_t P_stride, PosParams P,
+                                                        int iters, int rows_div, unsigned int* barrier) {
+    GridBarrier gb;
+    gb.init(barrier);
+    const unsigned int np = sd.hdr->n_phases;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; ++it) {
+        for (unsigned int p = 0; p < np; ++p) {
+            const unsigned int cnt = sd.ph_count[p];
+            const size_t gbase = sd.ph_gbase[p];
+            for (size_t g = tid; g < cnt; g += stride) {
+                const int4 info = sd.g_info[gbase + g];
+                const int item = info.w;
+                const int type = sd.it_type[item];
+                const int src = sd.it_src[item];
+                PosBody b1, b2;
+                if (type == NB2_ITEM_JOINT) {
+                    const nb2_joint& j = joints[src];
+                    load_pos_body(A, j.body1, &b1);
+                    load_pos_body(A, j.body2, &b2);
+                    joint_position(j, &b1, &b2, P);
+                    if (b1.dynamic) store_pos_body(A, j.body1, b1);
+                    if (b2.dynamic) store_pos_body(A, j.body2, b2);
+                } else {
+                    const unsigned int m = chunk_manifold[src];
+                    const nb2_manifold& mf = manifolds[m];
+                    load_pos_body(A, mf.body1, &b1);
+                    load_pos_body(A, mf.body2, &b2);
+                    const Pose c1 = load_coll(mf.coll1_wrt_body), c2 = load_coll(mf.coll2_wrt_body);
+                    const int nrows = info.z / rows_div;
+                    bool moved1 = false, moved2 = false;
+                    for (int lcc = 0; lcc < nrows; ++lcc) {
+                        const size_t ps = (size_t)NB2_CHUNK * gbase + (size_t)lcc * cnt + g;
+                        const float4 l1 = __ldg(&p_row[0 * P_stride + ps]);
+                        const float4 l2 = __ldg(&p_row[1 * P_stride + ps]);
+                        const float4 d1 = __ldg(&p_row[2 * P_stride + ps]);
+                        const float4 d2 = __ldg(&p_row[3 * P_stride + ps]);
+                        const float4 n1 = __ldg(&p_row[4 * P_stride + ps]);
+                        // update_contact_constraint (nonlinear_sor_prox.rs:156-294)
+                        const Pose m1 = pose_mul(b1.bp.pose, c1), m2 = pose_mul(b2.bp.pose, c2);
+                        ContactEval ce;
+                        if (!kinematic_contact(l1, l2, d1, d2, n1, m1, m2, &ce)) continue;
+                        const float rhs = clamp_rhs(-ce.depth, false, P);
+                        if (rhs >= 0.f) continue;
+                        Vec3 w1l = mk3(0.f, 0.f, 0.f), w1a = w1l, w2l = w1l, w2a = w1l;
+                        float inv_r = 0.f;
+                        pos_fill(b1, ce.world1, false, -ce.normal, &w1l, &w1a, &inv_r);
+                        pos_fill(b2, ce.world2, false, ce.normal, &w2l, &w2a, &inv_r);
+                        if (inv_r == 0.f) continue;
+                        const float r = 1.f / inv_r;
+                        const float impulse = -rhs * r;  // solve_unilateral, :137-152
+                        if (b1.dynamic) {
+                            apply_displacement(&b1.bp, b1.local_com, w1l * impulse, w1a * impulse);
+                            moved1 = true;
+                        }
+                        if (b2.dynamic) {
+                            apply_displacement(&b2.bp, b2.local_com, w2l * impulse, w2a * impulse);
+                            moved2 = true;
+                        }
+                    }
+                    if (moved1) store_pos_body(A, mf.body1, b1);
+                    if (moved2) store_pos_body(A, mf.body2, b2);
+                }
+            }
+            gb.sync();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// diagnostics: natural-map residual of the velocity rows, max penetration
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+    atomicMax((int*)addr, __float_as_int(v));  // valid for v >= 0
+}
+__global__ void __launch_bounds__(TPB) k_residual(SchedDev sd, Rows R, const float4* __restrict__ lam, float* res_max,
+                                                  double* res_sq, unsigned int* res_n, unsigned int* rows_two,
+                                                  unsigned int* rows_ground) {
+    const unsigned int np = sd.hdr->n_phases;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    float mx = 0.f;
+    double sq = 0.0;
+    unsigned int cntr = 0, two = 0, ground = 0;
+    for (unsigned int p = 0; p < np; ++p) {
+        const unsigned int cnt = sd.ph_count[p];
+        const size_t rbase = sd.ph_rbase[p], gbase = sd.ph_gbase[p];
+        for (size_t g = tid; g < cnt; g += stride) {
+            const int4 info = sd.g_info[gbase + g];
+            const bool a = info.x >= 0, b = info.y >= 0;
+            Lam la, lb;
+            if (a) la = load_lam(lam, info.x);
+            if (b) lb = load_lam(lam, info.y);
+            for (int r = 0; r < info.z; ++r) {
+                const size_t slot = rbase + (size_t)r * cnt + g;
+                const int2 meta = R.meta[slot];
+                if (meta.x == NB2_ROW_NONE) continue;
+                const float impulse = R.imp[slot];
+                RowJ J;
+                load_row_j(R, slot, a, b, &J);
+                const float4 h = R.hdr[slot];
+                float lo = 0.f, hi = NB2_F32_MAX;
+                if (meta.x == NB2_ROW_BILATERAL) {
+                    lo = h.z;
+                    hi = h.w;
+                } else if (meta.x == NB2_ROW_DEPENDENT) {
+                    hi = h.z * R.imp[meta.y];
+                    lo = -hi;
+                }
+                float w = (a ? dot6(J.J1, la.v) : 0.f) + (b ? dot6(J.J2, lb.v) : 0.f) + h.x;
+                float ni = meta.x == NB2_ROW_UNILATERAL ? fmaxf(impulse - h.y * w, 0.f)
+                                                        : clampf(impulse - h.y * w, lo, hi);
+                float d = fabsf(ni - impulse);
+                mx = fmaxf(mx, d);
+                sq += (double)d * d;
+                ++cntr;
+                if (a && b) ++two; else ++ground;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
+        sq += __shfl_down_sync(0xffffffffu, sq, o);
+        cntr += __shfl_down_sync(0xffffffffu, cntr, o);
+        two += __shfl_down_sync(0xffffffffu, two, o);
+        ground += __shfl_down_sync(0xffffffffu, ground, o);
+    }
+    if ((threadIdx.x & 31) == 0 && cntr) {
+        atomic_max_nonneg(res_max, mx);
+        atomicAdd(res_sq, sq);
+        atomicAdd(res_n, cntr);
+        atomicAdd(rows_two, two);
+        atomicAdd(rows_ground, ground);
+    }
+}
+// max penetration at the current poses; stored with a +1000 offset so that the int-ordered
+// atomicMax also works for negative depths
+__global__ void __launch_bounds__(TPB) k_penetration(SchedDev sd, PosArrays A,
+                                                     const nb2_manifold* __restrict__ manifolds,
+                                                     const unsigned int* __restrict__ chunk_manifold,
+                                                     const float4* __restrict__ p_row, size_t P_stride,
+                                                     int rows_div, float* pen_max) {
+    const unsigned int np = sd.hdr->n_phases;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    float mx = 0.f;
+    for (unsigned int p = 0; p < np; ++p) {
+        const unsigned int cnt = sd.ph_count[p];
+        const size_t gbase = sd.ph_gbase[p];
+        for (size_t g = tid; g < cnt; g += stride) {
+            const int4 info = sd.g_info[gbase + g];
+            const int item = info.w;
+            if (sd.it_type[item] == NB2_ITEM_JOINT) continue;
+            const unsigned int m = chunk_manifold[sd.it_src[item]];
+            const nb2_manifold& mf = manifolds[m];
+            PosBody b1, b2;
+            load_pos_body(A, mf.body1, &b1);
+            load_pos_body(A, mf.body2, &b2);
+            const Pose m1 = pose_mul(b1.bp.pose, load_coll(mf.coll1_wrt_body));
+            const Pose m2 = pose_mul(b2.bp.pose, load_coll(mf.coll2_wrt_body));
+            const int nrows = info.z / rows_div;
+            for (int lcc = 0; lcc < nrows; ++lcc) {
+                const size_t ps = (size_t)NB2_CHUNK * gbase + (size_t)lcc * cnt + g;
+                ContactEval ce;
+                if (kinematic_contact(p_row[0 * P_stride + ps], p_row[1 * P_stride + ps], p_row[2 * P_stride + ps],
+                                      p_row[3 * P_stride + ps], p_row[4 * P_stride + ps], m1, m2, &ce))
+                    mx = fmaxf(mx, ce.depth + 1000.f);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomic_max_nonneg(pen_max, mx);
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static Rows rows_of(Context* ctx) {
+    Rows R;
+    R.jac = ctx->r_jac.p;
+    R.hdr = ctx->r_hdr.p;
+    R.meta = ctx->r_meta.p;
+    R.imp = ctx->r_imp.p;
+    R.S = ctx->n_slots_max;
+    return R;
+}
+static PosArrays pos_arrays(Context* ctx) {
+    PosArrays A;
+    A.raw = ctx->raw.p;
+    A.pos_t = ctx->pos_t.p;
+    A.pos_q = ctx->pos_q.p;
+    A.com_im = ctx->com_im.p;
+    A.inv_i = ctx->inv_i.p;
+    return A;
+}
+template <typename K>
+static int coop_limit(Context* ctx, K kernel, int* cache) {
+    if (*cache > 0) return NB2_OK;
+    int per_sm = 0;
+    NB2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TPB, 0));
+    if (per_sm < 1) return set_error(ctx, NB2_ERR_CUDA, "cooperative kernel does not fit on an SM");
+    if (per_sm > 8) per_sm = 8;
+    *cache = per_sm * ctx->sm_count;
+    return NB2_OK;
+}
+
+int launch_velocity_solve(Context* ctx, int mode) {
+    const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
+    if (ctx->vs.n_items == 0) return NB2_OK;
+    SchedDev sd = sched_dev(ctx->vs);
+    Rows R = rows_of(ctx);
+    if (ref) {
+        unsigned int nb = ctx->n_bodies;
+        k_warmstart_ref<<<(nb + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(nb, ctx->adj_off.p, ctx->adj.p, sd, R,
+                                                                       ctx->vs.it_nrows.p, ctx->lam.p);
+        ctx->launches++;
+    }
+    NB2_TRY(coop_limit(ctx, k_velocity_solve, &ctx->coop_blocks_vel));
+    NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
+    float4* lam = ctx->lam.p;
+    int iters = (int)ctx->params.max_velocity_iterations;
+    int warm = ref ? 0 : 1;
+    unsigned int* bar = ctx->barrier.p;
+    size_t want = (ctx->vs.n_items + TPB - 1) / TPB;
+    int blocks = (int)(want < (size_t)ctx->coop_blocks_vel ? want : (size_t)ctx->coop_blocks_vel);
+    if (blocks < 1) blocks = 1;
+    void* args[] = {&sd, &R, &lam, &iters, &warm, &bar};
+    NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_velocity_solve, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
+    ctx->launches++;
+    return NB2_OK;
+}
+
+int launch_position_solve(Context* ctx, int mode) {
+    const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
+    Sched& s = ref ? ctx->ps : ctx->vs;
+    if (s.n_items == 0 || ctx->params.max_position_iterations == 0) return NB2_OK;
+    SchedDev sd = sched_dev(s);
+    PosArrays A = pos_arrays(ctx);
+    PosParams P;
+    P.erp = ctx->params.erp;
+    P.allowed_lin = ctx->params.allowed_linear_error;
+    P.allowed_ang = ctx->params.allowed_angular_error;
+    P.max_lin = ctx->params.max_linear_correction;
+    P.max_ang = ctx->params.max_angular_correction;
+    NB2_TRY(coop_limit(ctx, k_position_solve, &ctx->coop_blocks_pos));
+    NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
+    const nb2_joint* joints = ctx->joints.p;
+    const nb2_manifold* manifolds = ctx->manifolds.p;
+    const unsigned int* cm = ctx->chunk_manifold.p;
+    const float4* prow = ctx->p_row.p;
+    size_t pstride = ctx->n_pslots_max;
+    int iters = (int)ctx->params.max_position_iterations;
+    unsigned int* bar = ctx->barrier.p;
+    size_t want = (s.n_items + TPB - 1) / TPB;
+    int blocks = (int)(want < (size_t)ctx->coop_blocks_pos ? want : (size_t)ctx->coop_blocks_pos);
+    if (blocks < 1) blocks = 1;
+    int rows_div = ref ? 1 : 3;  // coloured groups carry 3 velocity rows per contact
+    void* args[] = {&sd, &A, &joints, &manifolds, &cm, &prow, &pstride, &P, &iters, &rows_div, &bar};
+    NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_position_solve, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
+    ctx->launches++;
+    return NB2_OK;
+}
+
+// stat_f layout: [0] res_max [1] pen_max(+1000) ; stat_d: [0] res_sq [1] energy ; stat_u: [0] res_n [1] rows_two
+// [2] rows_ground [3] non_finite
+int launch_stats(Context* ctx, int mode) {
+    const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
+    NB2_TRY(ctx->stat_f.reserve(ctx, 16));
+    NB2_TRY(ctx->stat_u.reserve(ctx, 16));
+    NB2_CUDA(ctx, cudaMemsetAsync(ctx->stat_f.p, 0, 16 * sizeof(float), ctx->stream));
+    NB2_CUDA(ctx, cudaMemsetAsync(ctx->stat_u.p, 0, 16 * sizeof(unsigned int), ctx->stream));
+    float* f = ctx->stat_f.p;
+    double* d = (double*)(ctx->stat_f.p + 4);  // 8-byte aligned inside the float scratch
+    unsigned int* u = ctx->stat_u.p;
+    const int blocks = ctx->sm_count * 4;
+    if (ctx->vs.n_items) {
+        k_residual<<<blocks, TPB, 0, ctx->stream>>>(sched_dev(ctx->vs), rows_of(ctx), ctx->lam.p, f + 0, d + 0, u + 0,
+                                                    u + 1, u + 2);
+        ctx->launches++;
+        Sched& s = ref ? ctx->ps : ctx->vs;
+        if (ctx->n_contacts) {
+            k_penetration<<<blocks, TPB, 0, ctx->stream>>>(sched_dev(s), pos_arrays(ctx), ctx->manifolds.p,
+                                                           ctx->chunk_manifold.p, ctx->p_row.p, ctx->n_pslots_max,
+                                                           ref ? 1 : 3, f + 1);
+            ctx->launches++;
+        }
+    }
+    NB2_TRY(launch_body_stats(ctx, d + 1, u + 3));
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
+}  // namespace nb2

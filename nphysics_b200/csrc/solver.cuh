@@ -1,0 +1,287 @@
+// Internal definitions shared by the .cu translation units of libnphysics_b200.so.
+//
+// Layout of the step (DESIGN.md has the full picture):
+//   refresh_dynamics -> schedule (levels | colours) -> assemble rows -> PGS velocity
+//   -> cache impulses -> integrate -> PGS position -> kinematic integrate
+//
+// All hot data are SoA float4 streams indexed by "slot".  Rows of one group
+// (the rows of <= 4 contacts of one manifold, or the rows of one joint) are
+// strided by the number of groups in their phase (ELL layout) so that thread g
+// of a phase reads row r of its group at  rbase + r*count + g  -- consecutive
+// threads touch consecutive 16-byte words.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/nphysics_b200.h"
+#include "math.cuh"
+
+namespace nb2 {
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+struct Context;
+int set_error(Context* ctx, int code, const char* fmt, ...);
+
+#define NB2_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return set_error((ctx), e_ == cudaErrorMemoryAllocation ? NB2_ERR_OUT_OF_MEMORY      \
+                                                                    : NB2_ERR_CUDA,              \
+                             "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,   \
+                             __LINE__);                                                          \
+    } while (0)
+
+#define NB2_TRY(expr)             \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_ != NB2_OK) return rc_; \
+    } while (0)
+
+// Growable device buffer (context-owned).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    int reserve(Context* ctx, size_t n) {
+        if (n <= cap) return NB2_OK;
+        size_t ncap = n + n / 4 + 64;
+        T* np_ = nullptr;
+        cudaError_t e = cudaMalloc((void**)&np_, ncap * sizeof(T));
+        if (e != cudaSuccess)
+            return set_error(ctx, NB2_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu bytes) failed: %s", ncap * sizeof(T),
+                             cudaGetErrorString(e));
+        if (p) cudaFree(p);  // contents are never carried over
+        p = np_;
+        cap = ncap;
+        return NB2_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// scheduling
+// ---------------------------------------------------------------------------
+#define NB2_CHUNK 4            // contacts per contact group
+#define NB2_MAX_JOINT_ROWS 7   // prismatic reserves 7 (prismatic_constraint.rs:124-126)
+#define NB2_MASK_WORDS 4       // 4 x 64 colours
+#define NB2_MAX_COLOURS (64 * NB2_MASK_WORDS)
+
+// velocity-row kinds
+#define NB2_ROW_NONE 0
+#define NB2_ROW_UNILATERAL 1
+#define NB2_ROW_BILATERAL 2   // Independent{lo, hi}
+#define NB2_ROW_DEPENDENT 3   // Dependent{dependency, coeff}
+
+// item types
+#define NB2_ITEM_JOINT 0
+#define NB2_ITEM_CONTACTS 1     // coloured: friction + normal rows of one chunk
+#define NB2_ITEM_FRICTION 2     // reference-order: the friction rows of one chunk
+#define NB2_ITEM_NORMAL 3       // reference-order: the normal rows of one chunk
+#define NB2_ITEM_INVALID -1
+
+// Device-resident header of a schedule (read by kernels; never read back by the
+// host on the step path).
+struct SchedHeader {
+    unsigned int n_phases;
+    unsigned int n_groups;   // total scheduled items
+    unsigned int n_slots;    // total row slots
+    unsigned int overflow;   // != 0: colouring ran out of colours / phases
+    unsigned int work;       // scratch: "something changed" flag
+    unsigned int pad[3];
+};
+
+struct Sched {
+    size_t n_items = 0;      // capacity in items for this step
+    size_t max_phases = 0;
+    DevBuf<int> it_a, it_b;          // dynamic body of each side or -1
+    DevBuf<int> it_nrows;            // velocity rows (position schedule: position constraints)
+    DevBuf<int> it_type;             // NB2_ITEM_*
+    DevBuf<int> it_src;              // joint index / chunk index
+    DevBuf<unsigned long long> it_key;  // sequential position (reference order)
+    DevBuf<int> it_phase, it_slot;   // outputs: phase, index inside the phase
+    DevBuf<unsigned int> ph_count, ph_R, ph_gbase, ph_rbase;
+    DevBuf<int4> g_info;             // per group slot: (a, b, nrows, item)
+    DevBuf<SchedHeader> hdr;         // 1 element
+    void release() {
+        it_a.release(); it_b.release(); it_nrows.release(); it_type.release(); it_src.release();
+        it_key.release(); it_phase.release(); it_slot.release(); ph_count.release(); ph_R.release();
+        ph_gbase.release(); ph_rbase.release(); g_info.release(); hdr.release();
+    }
+};
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct StageEvents {
+    cudaEvent_t e[6];  // step start, assembly done, velocity done, update done, position done, end
+    bool created = false;
+};
+
+struct Context {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    char last_error[512];
+    uint64_t launches = 0;
+
+    nb2_params params;
+    float inv_dt = 0.f;
+    bool have_params = false;
+    bool timers = false;
+    StageEvents ev;
+    bool ev_valid = false;
+
+    // ---- bodies
+    uint32_t n_bodies = 0;
+    uint32_t n_dynamic = 0;
+    DevBuf<nb2_body> raw;         // static properties (pose/velocity fields are upload-time values)
+    DevBuf<float4> pos_t, pos_q;  // live pose
+    DevBuf<float4> vel;           // [2n] linear, angular
+    DevBuf<float4> com_im;        // com.xyz, inverse mass
+    DevBuf<float4> inv_i;         // [3n] rows of the inverse augmented angular inertia
+    DevBuf<float4> ext;           // [2n] ext_vels = dt * acceleration
+    DevBuf<float4> lam;           // [2n] mj_lambda_vel
+    DevBuf<int> b_status;
+
+    // ---- joints
+    uint32_t n_joints = 0;
+    DevBuf<nb2_joint> joints;
+
+    // ---- contacts
+    uint32_t n_manifolds = 0, n_contacts = 0;
+    DevBuf<nb2_manifold> manifolds;
+    DevBuf<nb2_contact> contacts;
+    DevBuf<unsigned int> c_manifold;   // contact -> manifold
+    DevBuf<unsigned int> chunk_base;   // [nM+1] exclusive scan of ceil(nc/4)
+    DevBuf<unsigned int> chunk_manifold;  // chunk -> manifold
+    size_t max_chunks = 0;
+
+    // impulse cache: double-buffered (previous step -> this step)
+    DevBuf<float4> imp[2];
+    DevBuf<unsigned long long> ht_keys[2];
+    DevBuf<unsigned int> ht_vals[2];
+    size_t ht_cap[2] = {0, 0};  // power of two (0 = empty cache)
+    uint32_t imp_n[2] = {0, 0};
+    int cur = 0;                // buffer written by the current step
+
+    // ---- schedules
+    Sched vs, ps;          // velocity / position (coloured mode uses vs for both)
+    // reference-order scratch
+    DevBuf<unsigned int> deg, adj_off, cursor;
+    DevBuf<int> adj, pred_a, pred_b, level;
+    DevBuf<unsigned int> adj_off_p;  // adjacency of the position schedule (kept apart: the velocity
+    DevBuf<int> adj_p;               // adjacency is read again by the reference-order warm start)
+    // colouring scratch
+    DevBuf<unsigned long long> cmask, best;
+    // scan scratch
+    DevBuf<unsigned int> scan_tmp;
+    // grid barrier counter
+    DevBuf<unsigned int> barrier;
+
+    // ---- rows
+    size_t n_slots_max = 0, n_pslots_max = 0;
+    DevBuf<float4> r_jac;   // [6][n_slots_max]: J1.lin|J1.ang.x.. packed as 24 floats
+    DevBuf<float4> r_hdr;   // rhs, r, lo|mu, hi
+    DevBuf<int2> r_meta;    // kind, dependency slot
+    DevBuf<float> r_imp;
+    DevBuf<float4> p_row;   // [5][n_pslots_max] position rows
+
+    // ---- stats
+    DevBuf<float> stat_f;           // reductions
+    DevBuf<unsigned int> stat_u;
+    DevBuf<unsigned int> flags;     // [0] input validation bits
+    DevBuf<nb2_body_state> stage_states;
+    nb2_stats last_stats;
+    int last_mode = -1;
+    bool stepped = false;
+
+    int coop_blocks_vel = 0, coop_blocks_pos = 0, coop_blocks_sched = 0;
+};
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+NB2_D float4 ldcg4(const float4* p) { return __ldcg(p); }
+NB2_D void stcg4(float4* p, float4 v) { __stcg(p, v); }
+
+// Software grid barrier for cooperatively launched kernels: a monotonically
+// increasing arrival counter (zeroed before the launch).
+struct GridBarrier {
+    unsigned int* counter;
+    unsigned int target;
+    __device__ void init(unsigned int* c) {
+        counter = c;
+        target = 0;
+    }
+    __device__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            while (*((volatile unsigned int*)counter) < target) {
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+};
+
+// Live body state as the kernels see it.
+struct BodyPose {
+    Pose pose;
+    Vec3 com;
+};
+NB2_D Vec3 f4_xyz(float4 v) { return mk3(v.x, v.y, v.z); }
+NB2_D float4 xyz_f4(Vec3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+NB2_D Quat f4_quat(float4 v) { return mkq(v.x, v.y, v.z, v.w); }
+NB2_D float4 quat_f4(Quat q) { return make_float4(q.i, q.j, q.k, q.w); }
+
+// RigidBody::apply_displacement (src/object/rigid_body.rs:371-381): the
+// displacement (lin, ang) is applied about the centre of mass, then the com is
+// refreshed from the new pose (set_position, :305-315).
+NB2_D void apply_displacement(BodyPose* b, Vec3 local_com, Vec3 lin, Vec3 ang) {
+    Quat dr = quat_from_scaled_axis(ang);
+    Pose wrt_com;
+    wrt_com.t = (b->com + lin) + quat_rotate(dr, -b->com);
+    wrt_com.r = dr;
+    b->pose = pose_mul(wrt_com, b->pose);
+    b->com = pose_point(b->pose, local_com);
+}
+
+// ---------------------------------------------------------------------------
+// launchers (one per .cu file group)
+// ---------------------------------------------------------------------------
+// bodies.cu
+int launch_unpack_bodies(Context* ctx);
+int launch_refresh_dynamics(Context* ctx);
+int launch_integrate(Context* ctx, bool kinematic_only);
+int launch_pack_states(Context* ctx, nb2_body_state* d_out, uint32_t first, uint32_t n);
+int launch_unpack_states(Context* ctx, const nb2_body_state* d_in, uint32_t first, uint32_t n);
+int launch_stats(Context* ctx, int mode);
+int launch_body_stats(Context* ctx, double* d_energy, unsigned int* d_non_finite);
+int launch_validate_inputs(Context* ctx);
+int launch_validate_joints(Context* ctx);
+// schedule.cu
+int exclusive_scan_u32(Context* ctx, const unsigned int* in, unsigned int* out, size_t n);
+int launch_build_items(Context* ctx, int mode);
+int launch_schedule(Context* ctx, Sched* s, int mode);
+int query_coop_limits(Context* ctx);
+// assemble.cu
+int launch_assemble(Context* ctx, int mode);
+int launch_cache_impulses(Context* ctx, int mode);
+// solve.cu
+int launch_velocity_solve(Context* ctx, int mode);
+int launch_position_solve(Context* ctx, int mode);
+
+}  // namespace nb2

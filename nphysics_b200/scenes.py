@@ -1,0 +1,361 @@
+"""Scene builders and the stand-in manifold producer for the BASELINE.json configs.
+
+The reference takes its contact manifolds from ncollide (out of scope, SURVEY.md
+section 2 row 6); here they come from an analytic face-face generator for
+(near) axis-aligned cuboids: every touching face pair yields one manifold with
+the 4 corners of the overlap rectangle as Plane/Point (or Point/Plane) contacts,
+recomputed from the CURRENT poses each step with persistent feature pairs and
+keys -- the same records ncollide's polyhedral clipping produces for these piles
+(SURVEY.md appendix B, C).  Scene constants follow examples3d/{pyramid3,boxes3,
+wall3,constraints3}.rs as cited per function.
+"""
+import numpy as np
+
+from . import abi
+
+DEFAULT_MARGIN = 0.01       # ColliderDesc::default_margin, src/object/collider.rs:457-479
+LINEAR_PREDICTION = 0.001   # collider.rs:457-479
+DEFAULT_FRICTION = 0.5      # BasicMaterial::default, src/material/basic_material.rs:56-60
+DEFAULT_RESTITUTION = 0.0
+
+
+def quat_rotate(q, v):
+    """Rotate vectors v[...,3] by unit quaternions q[...,4] (i,j,k,w)."""
+    qv = q[..., :3]
+    w = q[..., 3:4]
+    t = 2.0 * np.cross(qv, v)
+    return v + w * t + np.cross(qv, t)
+
+
+def cuboid_mass_properties(half_extents, density):
+    """volumetric_cuboid.rs:10-77: m = rho*8*hx*hy*hz, I_x = m*(4hy^2+4hz^2)/12, ..."""
+    hx, hy, hz = [float(x) for x in half_extents]
+    m = density * 8.0 * hx * hy * hz
+    ix = m * (4 * hy * hy + 4 * hz * hz) / 12.0
+    iy = m * (4 * hx * hx + 4 * hz * hz) / 12.0
+    iz = m * (4 * hx * hx + 4 * hy * hy) / 12.0
+    return m, np.diag([ix, iy, iz])
+
+
+class Scene:
+    """bodies + per-body cuboid collider (half extents, collider offset) + joints."""
+
+    def __init__(self, bodies, half_extents, coll_offset, joints=None, params=None, name="scene"):
+        self.bodies = bodies
+        self.half_extents = np.asarray(half_extents, dtype=np.float64)  # (n,3); 0 = no collider
+        self.coll_offset = np.asarray(coll_offset, dtype=np.float64)    # (n,3) collider translation wrt body
+        self.joints = joints if joints is not None else np.zeros(0, dtype=abi.joint_dtype)
+        self.params = params if params is not None else abi.default_params()
+        self.name = name
+        self.margin = DEFAULT_MARGIN
+        self.friction = DEFAULT_FRICTION
+        self.restitution = DEFAULT_RESTITUTION
+
+    @property
+    def n_dynamic(self):
+        return int((self.bodies["status"] == abi.BODY_DYNAMIC).sum())
+
+
+def _make_boxes(centers, rad, density, ground_half, ground_offset=(0.0, -0.2, 0.0)):
+    """Body 0 = Ground (ground.rs) with a cuboid collider; bodies 1.. = dynamic cubes."""
+    centers = np.asarray(centers, dtype=np.float64)
+    n = len(centers) + 1
+    bodies = abi.new_bodies(n)
+    bodies["status"][0] = abi.BODY_STATIC
+    bodies["flags"][0] = 0
+    m, inertia = cuboid_mass_properties((rad, rad, rad), density)
+    bodies["position"][1:, :3] = centers
+    bodies["mass"][1:] = m
+    bodies["local_inertia"][1:] = inertia.reshape(9)
+    he = np.full((n, 3), rad)
+    he[0] = ground_half
+    off = np.zeros((n, 3))
+    off[0] = ground_offset
+    return bodies, he, off
+
+
+def pyramid3(num=30, rad=0.1, density=1.0):
+    """examples3d/pyramid3.rs:21-72: rows of num, num-1, ..., 1 cubes."""
+    shift = (rad + DEFAULT_MARGIN) * 2.0
+    centerx = shift * num / 2.0
+    centery = shift / 2.0
+    cs = []
+    for i in range(num):
+        for j in range(i, num):
+            fi, fj = float(i), float(j - i)
+            cs.append((fi * shift / 2.0 + fj * shift - centerx, fi * shift + centery, 0.0))
+    bodies, he, off = _make_boxes(cs, rad, density, (6.0, 0.2, 6.0))
+    return Scene(bodies, he, off, name="pyramid3")
+
+
+def boxes3(nx=6, ny=6, nz=6, rad=0.1, density=1.0, height=0.0, ground_half=None, jitter=0.0, seed=12345):
+    """examples3d/boxes3.rs:48-60 generalised to an nx*ny*nz grid (BASELINE config 2:
+    50x40x50 settled, height=0)."""
+    shift = (rad + DEFAULT_MARGIN) * 2.0
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    x = i * shift - shift * nx / 2.0
+    y = j * shift + shift / 2.0 + height
+    z = k * shift - shift * nz / 2.0
+    cs = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+    if jitter > 0:
+        rng = np.random.default_rng(seed)
+        cs = cs + rng.uniform(-jitter, jitter, size=cs.shape)
+    if ground_half is None:
+        ground_half = (max(3.0, shift * nx / 2.0 + 2.5), 0.2, max(3.0, shift * nz / 2.0 + 2.5))
+    bodies, he, off = _make_boxes(cs, rad, density, ground_half)
+    return Scene(bodies, he, off, name="boxes3_%dx%dx%d" % (nx, ny, nz))
+
+
+def wall3(width=50, height=10, rad=0.1, density=1.0):
+    """examples3d/wall3.rs:43-69."""
+    shift = (rad + DEFAULT_MARGIN) * 2.0
+    centerx = shift * width / 2.0
+    centery = shift / 2.0
+    cs = [(i * shift - centerx, j * shift + centery, 0.0) for i in range(width) for j in range(height)]
+    bodies, he, off = _make_boxes(cs, rad, density, (max(15.0, centerx + 2.0), 0.2, 3.0))
+    return Scene(bodies, he, off, name="wall3_%dx%d" % (width, height))
+
+
+def tile(scene, copies, pitch=20.0, per_row=64):
+    """BASELINE config 5: `copies` independent translated copies of one scene (each with its own
+    ground body), world w shifted by (w % per_row * pitch, 0, w // per_row * pitch)."""
+    n = len(scene.bodies)
+    bodies = np.tile(scene.bodies, copies)
+    w = np.repeat(np.arange(copies), n)
+    bodies["position"][:, 0] += (w % per_row) * pitch
+    bodies["position"][:, 2] += (w // per_row) * pitch
+    he = np.tile(scene.half_extents, (copies, 1))
+    off = np.tile(scene.coll_offset, (copies, 1))
+    joints = np.tile(scene.joints, copies)
+    if len(joints):
+        jw = np.repeat(np.arange(copies), len(scene.joints))
+        joints["body1"] += (jw * n).astype(np.int32)
+        joints["body2"] += (jw * n).astype(np.int32)
+    s = Scene(bodies, he, off, joints, scene.params.copy(), name="%s_x%d" % (scene.name, copies))
+    s.tile_of = (scene, copies)
+    return s
+
+
+def joint_chains(n_chains=10, links=6, rad=0.2, density=1.0, kind="mixed", ground_y=-5.2, pitch=3.0,
+                 with_ground_collider=True):
+    """BASELINE config 4: chains of `links` cubes hanging from the ground body.  Even chains use
+    RevoluteConstraint links (examples3d/constraints3.rs:61-95: anchor offset (0,0,0.8), axis x),
+    odd chains BallConstraint links (:138-169: offsets (cos a, 0.3, sin a) * 1.0).  Chains sit on a
+    square lattice with `pitch` metres between them; the ground collider lies `ground_y` below."""
+    per_row = int(np.ceil(np.sqrt(n_chains)))
+    n = 1 + n_chains * links
+    bodies = abi.new_bodies(n)
+    bodies["status"][0] = abi.BODY_STATIC
+    bodies["flags"][0] = 0
+    m, inertia = cuboid_mass_properties((rad, rad, rad), density)
+    bodies["mass"][1:] = m
+    bodies["local_inertia"][1:] = inertia.reshape(9)
+    he = np.full((n, 3), rad)
+    span = per_row * pitch / 2.0 + 5.0
+    he[0] = (span, 0.2, span) if with_ground_collider else (0.0, 0.0, 0.0)
+    off = np.zeros((n, 3))
+    off[0] = (0.0, ground_y - 0.2, 0.0)
+    joints = abi.new_joints(n_chains * links)
+    jn = 0
+    for c in range(n_chains):
+        ox = (c % per_row) * pitch - per_row * pitch / 2.0
+        oz = (c // per_row) * pitch - per_row * pitch / 2.0
+        revolute = (kind == "revolute") or (kind == "mixed" and c % 2 == 0)
+        parent = 0
+        parent_pos = np.array([ox, 0.0, oz])
+        for l in range(links):
+            b = 1 + c * links + l
+            a1 = parent_pos if parent == 0 else np.zeros(3)
+            if revolute:
+                # constraints3.rs:66-95: body_anchor = z * (rad*3 + 0.2); pos -= body_anchor
+                a2 = np.array([0.0, 0.0, 1.0]) * (rad * 3.0 + 0.2)
+                joints["type"][jn] = abi.JOINT_REVOLUTE
+                joints["axis1"][jn] = (1.0, 0.0, 0.0)
+                joints["axis2"][jn] = (1.0, 0.0, 0.0)
+            else:
+                # constraints3.rs:138-169: first link sits on the anchor, the others hang off
+                # (cos a, 0.3, sin a) * rad * 5 with a = i * 2 pi / num
+                ang = l * 2.0 * np.pi / links
+                a2 = np.zeros(3) if l == 0 else np.array([np.cos(ang), 0.3, np.sin(ang)]) * (rad * 5.0)
+                joints["type"][jn] = abi.JOINT_BALL
+            pos = parent_pos - a2
+            bodies["position"][b, :3] = pos
+            joints["body1"][jn] = parent
+            joints["body2"][jn] = b
+            joints["anchor1"][jn] = a1
+            joints["anchor2"][jn] = a2
+            jn += 1
+            parent = b
+            parent_pos = pos
+    return Scene(bodies, he, off, joints, name="chains_%dx%d_%s" % (n_chains, links, kind))
+
+
+# ----------------------------------------------------------------------------------------------
+# the manifold producer
+# ----------------------------------------------------------------------------------------------
+class ContactGenerator:
+    """Persistent face-face feature pairs between (near) axis-aligned cuboids.
+
+    Feature pairs are discovered once from the initial poses (touching or within the prediction
+    distance); `generate(positions)` then re-evaluates every contact of every pair at the given
+    poses, drops contacts farther apart than the narrow-phase prediction
+    (margin+linear_prediction on both sides = 0.022, collider.rs:542-549) and emits
+    (nb2_manifold[], nb2_contact[]) with stable keys.
+    """
+
+    def __init__(self, scene, flip_fraction=0.0, search=None):
+        self.scene = scene
+        pos = scene.bodies["position"].astype(np.float64)
+        centers = pos[:, :3] + scene.coll_offset
+        he = scene.half_extents
+        status = scene.bodies["status"]
+        has_coll = he.max(axis=1) > 0
+        margin = scene.margin
+        reach = 2.0 * (margin + LINEAR_PREDICTION)
+        dyn = np.nonzero((status == abi.BODY_DYNAMIC) & has_coll)[0]
+        big = np.nonzero((status != abi.BODY_DYNAMIC) & has_coll)[0]
+        pa, pb = [], []
+        if len(dyn) > 1:
+            from scipy.spatial import cKDTree
+            r_max = float(he[dyn].max())
+            radius = search if search is not None else (2.0 * r_max + reach) * np.sqrt(2.0) * 1.01
+            tree = cKDTree(centers[dyn])
+            pr = tree.query_pairs(radius, output_type="ndarray")
+            pa.append(dyn[pr[:, 0]])
+            pb.append(dyn[pr[:, 1]])
+        for g in big:  # ground-like bodies against every dynamic box
+            pa.append(np.full(len(dyn), g))
+            pb.append(dyn)
+        if pa:
+            a = np.concatenate(pa)
+            b = np.concatenate(pb)
+        else:
+            a = np.zeros(0, dtype=np.int64)
+            b = np.zeros(0, dtype=np.int64)
+        d = centers[b] - centers[a]
+        hsum = he[a] + he[b]
+        gap = np.abs(d) - hsum                      # per axis; > 0 separated
+        overlap = -gap                              # per axis overlap extent
+        eps = 1e-6
+        keep = np.zeros(len(a), dtype=bool)
+        axis = np.zeros(len(a), dtype=np.int64)
+        for ax in range(3):
+            o1, o2 = (ax + 1) % 3, (ax + 2) % 3
+            ok = (gap[:, ax] <= reach + eps) & (gap[:, ax] > -0.5 * np.minimum(he[a, ax], he[b, ax])) & \
+                 (overlap[:, o1] > eps) & (overlap[:, o2] > eps)
+            ok &= ~keep
+            axis[ok] = ax
+            keep |= ok
+        a, b, d, axis = a[keep], b[keep], d[keep], axis[keep]
+        # deterministic order: by (a, b)
+        order = np.lexsort((b, a))
+        a, b, d, axis = a[order], b[order], d[order], axis[order]
+        npairs = len(a)
+        rows = np.arange(npairs)
+        sign = np.where(d[rows, axis] >= 0, 1.0, -1.0)
+        ca, cb = centers[a], centers[b]
+        u = (axis + 1) % 3
+        v = (axis + 2) % 3
+        lo_u = np.maximum(ca[rows, u] - he[a, u], cb[rows, u] - he[b, u])
+        hi_u = np.minimum(ca[rows, u] + he[a, u], cb[rows, u] + he[b, u])
+        lo_v = np.maximum(ca[rows, v] - he[a, v], cb[rows, v] - he[b, v])
+        hi_v = np.minimum(ca[rows, v] + he[a, v], cb[rows, v] + he[b, v])
+        corners_u = np.stack([lo_u, hi_u, hi_u, lo_u], axis=1)   # (npairs,4)
+        corners_v = np.stack([lo_v, lo_v, hi_v, hi_v], axis=1)
+        # local points in the COLLIDER frames of a (on its face) and b (on its face)
+        la = np.zeros((npairs, 4, 3))
+        lb = np.zeros((npairs, 4, 3))
+        for k in range(4):
+            la[rows, k, u] = corners_u[:, k] - ca[rows, u]
+            la[rows, k, v] = corners_v[:, k] - ca[rows, v]
+            la[rows, k, axis] = sign * he[a, axis]
+            lb[rows, k, u] = corners_u[:, k] - cb[rows, u]
+            lb[rows, k, v] = corners_v[:, k] - cb[rows, v]
+            lb[rows, k, axis] = -sign * he[b, axis]
+        na = np.zeros((npairs, 3))
+        na[rows, axis] = sign                       # outward normal of a's face, local to a
+        # flipped pairs: body1 = b carries the Point, body2 = a carries the Plane
+        h = (a * 2654435761 + b * 40503) % 1000
+        self.flip = h < int(flip_fraction * 1000)
+        self.a, self.b = a, b
+        self.la, self.lb, self.na = la, lb, na
+        self.npairs = npairs
+        self.reach = reach
+
+    def generate(self, positions=None):
+        sc = self.scene
+        if positions is None:
+            positions = sc.bodies["position"]
+        positions = np.asarray(positions, dtype=np.float64)
+        a, b = self.a, self.b
+        npairs = self.npairs
+        off = sc.coll_offset
+        qa, qb = positions[a, 3:7], positions[b, 3:7]
+        # collider pose = body pose * translation(offset)
+        ta = positions[a, :3] + quat_rotate(qa, off[a])
+        tb = positions[b, :3] + quat_rotate(qb, off[b])
+        wa = ta[:, None, :] + quat_rotate(qa[:, None, :], self.la)     # points on a's face
+        wb = tb[:, None, :] + quat_rotate(qb[:, None, :], self.lb)     # points on b's face
+        n = quat_rotate(qa, self.na)                                   # world normal a -> b
+        depth = -np.einsum("pj,pkj->pk", n, wb - wa)                   # Plane(a)/Point(b)
+        w1 = wb + n[:, None, :] * depth[:, :, None]                    # projection on a's plane
+        keep = depth > -self.reach
+        nper = keep.sum(axis=1)
+        mkeep = nper > 0
+        flip = self.flip
+        m_idx = np.nonzero(mkeep)[0]
+        nm = len(m_idx)
+        manifolds = np.zeros(nm, dtype=abi.manifold_dtype)
+        body1 = np.where(flip, b, a)
+        body2 = np.where(flip, a, b)
+        manifolds["body1"] = body1[m_idx]
+        manifolds["body2"] = body2[m_idx]
+        manifolds["num_contacts"] = nper[m_idx]
+        first = np.concatenate([[0], np.cumsum(nper[m_idx])[:-1]]) if nm else np.zeros(0)
+        manifolds["first_contact"] = first
+        manifolds["margin1"] = sc.margin
+        manifolds["margin2"] = sc.margin
+        manifolds["friction"] = sc.friction
+        manifolds["restitution"] = sc.restitution
+        manifolds["coll1_wrt_body"][:, 6] = 1.0
+        manifolds["coll2_wrt_body"][:, 6] = 1.0
+        manifolds["coll1_wrt_body"][:, :3] = off[body1[m_idx]]
+        manifolds["coll2_wrt_body"][:, :3] = off[body2[m_idx]]
+        pi, ki = np.nonzero(keep)          # row-major: pair order, corner order
+        nc = len(pi)
+        contacts = np.zeros(nc, dtype=abi.contact_dtype)
+        f = flip[pi]
+        nn = n[pi]
+        contacts["normal"] = np.where(f[:, None], -nn, nn)
+        contacts["depth"] = depth[pi, ki]
+        contacts["world1"] = np.where(f[:, None], wb[pi, ki], w1[pi, ki])
+        contacts["world2"] = np.where(f[:, None], w1[pi, ki], wb[pi, ki])
+        contacts["key"] = (pi.astype(np.uint64) * np.uint64(4) + ki.astype(np.uint64) + np.uint64(1))
+        contacts["local1"] = np.where(f[:, None], self.lb[pi, ki], self.la[pi, ki])
+        contacts["local2"] = np.where(f[:, None], self.la[pi, ki], self.lb[pi, ki])
+        nl = self.na[pi]
+        contacts["dir1"] = np.where(f[:, None], 0.0, nl)
+        contacts["dir2"] = np.where(f[:, None], nl, 0.0)
+        contacts["geom1"] = np.where(f, abi.GEOM_POINT, abi.GEOM_PLANE)
+        contacts["geom2"] = np.where(f, abi.GEOM_PLANE, abi.GEOM_POINT)
+        return manifolds, contacts
+
+
+def row_counts(scene, manifolds):
+    """(N_R2, N_RG): two-dynamic-body / ground velocity rows of the contact set (+ joints, using
+    the rows each joint type emits when no limit is active)."""
+    st = scene.bodies["status"]
+    d1 = st[manifolds["body1"]] == abi.BODY_DYNAMIC
+    d2 = st[manifolds["body2"]] == abi.BODY_DYNAMIC
+    rows = 3 * manifolds["num_contacts"].astype(np.int64)
+    r2 = int(rows[d1 & d2].sum())
+    rg = int(rows[d1 ^ d2].sum())
+    per_type = np.array([3, 5, 5, 4, 3, 4, 4, 4, 6, 3])
+    j = scene.joints
+    if len(j):
+        jd1 = st[j["body1"]] == abi.BODY_DYNAMIC
+        jd2 = st[j["body2"]] == abi.BODY_DYNAMIC
+        jr = per_type[j["type"]]
+        r2 += int(jr[jd1 & jd2].sum())
+        rg += int(jr[jd1 ^ jd2].sum())
+    return r2, rg
