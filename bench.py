@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the MoreauJeanSolver hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+A "step" is one MoreauJeanSolver step (assembly + SOR-prox velocity iterations + integration +
+nonlinear SOR-prox position iterations) of BASELINE.json configs[1]: the boxes3 scene scaled to a
+settled 50x40x50 = 100 000-box pile, 10 velocity + 5 position iterations.  Metric: solver
+body-steps/s = dynamic bodies x steps / time.  With N > 1 every rank steps
+its own independent 100k-box world (weak scaling; islands/worlds never exchange data, so there is
+no data-path collective -- NCCL only gathers the per-rank timings).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from nphysics_b200 import abi, scenes  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", default="50x40x50", help="boxes3 grid nx x ny x nz (default = BASELINE configs[1])")
+    ap.add_argument("--vel-iters", type=int, default=10)
+    ap.add_argument("--pos-iters", type=int, default=5)
+    ap.add_argument("--mode", default="coloured", choices=["coloured", "reference_order"])
+    ap.add_argument("--cpu-sample-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def build_workload(grid, vel_iters, pos_iters):
+    nx, ny, nz = [int(x) for x in grid.lower().split("x")]
+    sc = scenes.boxes3(nx, ny, nz)
+    p = abi.default_params()
+    p["max_velocity_iterations"] = vel_iters
+    p["max_position_iterations"] = pos_iters
+    sc.params = p
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    return sc, m, c
+
+
+def algorithmic_bytes(n_r2, n_rg, n_c, n_b, iv, ip):
+    """SURVEY.md section 8(d) / BASELINE.md section 4."""
+    vel = iv * (132 * n_r2 + 84 * n_rg)
+    pos = ip * (96 * n_c)
+    asm = 128 * n_r2 + 80 * n_rg + 96 * n_c + 64 * n_c
+    return {"velocity_kernel": vel, "position_kernel": pos, "step": vel + pos + 200 * n_b + asm}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_reference_run(sc, m, c, steps, warmup):
+    """Times the CPU oracle (single thread: the reference has no threads)."""
+    from oracle import Oracle
+    o = Oracle()
+    o.set_params(sc.params)
+    o.upload_bodies(sc.bodies)
+    o.upload_manifolds(m, c)
+    for _ in range(warmup):
+        o.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step()
+    dt = time.perf_counter() - t0
+    st = o.get_stats()
+    o.close()
+    return dt, st
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # bounded sample of the same workload: a 20x40x20 sub-pile (same depth, same row mix per body)
+    sample_grid = "20x40x20" if args.grid == "50x40x50" else args.grid
+    sc, m, c = build_workload(sample_grid, args.vel_iters, args.pos_iters)
+    dt, st = cpu_reference_run(sc, m, c, args.steps, args.warmup)
+    nb = sc.n_dynamic
+    value = nb * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "solver body-steps/sec", "value": value, "unit": "body-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "boxes3 scaled to 100k boxes (50x40x50 settled pile), %d velocity + %d position "
+                               "iterations" % (args.vel_iters, args.pos_iters),
+                   "reference_sample": "%s sub-pile (%d boxes, %d contacts) per step" % (sample_grid, nb, len(c))},
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": 1, "kind": "port",
+                         "sample": "%d steps of a %s settled sub-pile (%d boxes) through oracle/liboracle.so, "
+                                   "single thread" % (args.steps, sample_grid, nb)},
+        "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rows_per_step": int(st["n_rows_two_body"]) + int(st["n_rows_ground"]),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    from nphysics_b200.solver import Solver
+    mode = abi.MODE_COLOURED if args.mode == "coloured" else abi.MODE_REFERENCE_ORDER
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    sc, m, c = build_workload(args.grid, args.vel_iters, args.pos_iters)
+    nb = sc.n_dynamic
+    n_r2, n_rg = scenes.row_counts(sc, m)
+    stream = torch.cuda.Stream(device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        solver = Solver(device=local_rank, stream=stream.cuda_stream)
+        solver.set_params(sc.params)
+        solver.upload_bodies(sc.bodies)
+        solver.upload_manifolds(m, c)
+        for _ in range(max(args.warmup, 3)):
+            solver.step(mode)
+        solver.synchronize()
+
+        # ---------------- timed region: inputs resident in HBM, K steps
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = solver.launch_count()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            solver.step(mode)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = solver.launch_count() - l0
+        clocks = sampler.stop()
+        solver.synchronize()
+
+        # ---------------- kernel times of the same step, CUDA events on the launching stream
+        solver.enable_timers(True)
+        acc = {}
+        n_t = min(args.steps, 20)
+        for _ in range(n_t):
+            solver.step(mode)
+            t = solver.get_timers()
+            for k, v in t.items():
+                acc[k] = acc.get(k, 0.0) + v
+        solver.enable_timers(False)
+        timers = {k: v / n_t for k, v in acc.items()}
+        stats = solver.get_stats()
+
+        # ---------------- end to end through the C ABI with host buffers
+        e2e = None
+        if not args.no_e2e:
+            pm = torch.empty(max(m.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            pc = torch.empty(max(c.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            ps = torch.empty(solver.n_bodies * abi.body_state_dtype.itemsize, dtype=torch.uint8, pin_memory=True)
+            pm.numpy()[:m.nbytes] = m.view(np.uint8).reshape(-1)
+            pc.numpy()[:c.nbytes] = c.view(np.uint8).reshape(-1)
+            for _ in range(2):
+                solver.upload_manifolds_raw(pm.data_ptr(), len(m), pc.data_ptr(), len(c))
+                solver.step(mode)
+                solver.download_body_states_raw(ps.data_ptr(), 0, solver.n_bodies)
+            barrier()
+            t0 = time.perf_counter()
+            g0 = torch.cuda.Event(enable_timing=True)
+            g1 = torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(args.steps):
+                solver.upload_manifolds_raw(pm.data_ptr(), len(m), pc.data_ptr(), len(c))
+                solver.step(mode)
+                solver.download_body_states_raw(ps.data_ptr(), 0, solver.n_bodies)
+            g1.record(stream)
+            barrier()
+            e2e_ms = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))
+            e2e = {"ms": e2e_ms, "h2d": int(m.nbytes + c.nbytes), "d2h": int(solver.n_bodies * 52)}
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        if e2e:
+            e2e["ms"] = float(t[1])
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak = 6650.0
+            peak_src = "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+        ab = algorithmic_bytes(n_r2, n_rg, len(c), nb, args.vel_iters, args.pos_iters)
+        vk_ms = timers.get("velocity_kernel", 0.0)
+        achieved = ab["velocity_kernel"] / (vk_ms * 1e-3) / 1e9 if vk_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "velocity_kernel_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        value = world * nb * args.steps / (ms * 1e-3)
+        line = {
+            "metric": "solver body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "boxes3 scaled to 100k boxes (%s settled pile%s), %d velocity + %d position "
+                                   "iterations, mode=%s" % (args.grid, ", one independent world per GPU" if world > 1
+                                                            else "", args.vel_iters, args.pos_iters, args.mode),
+                       "bodies": nb, "manifolds": int(len(m)), "contacts": int(len(c)), "rows_two_body": n_r2,
+                       "rows_ground": n_rg,
+                       "l2": "row stream %.0f MB per sweep > 126 MB L2 (inputs larger than L2, no flush needed)" %
+                             ((132 * n_r2 + 84 * n_rg) / 1e6)},
+            "constraint_rows_per_sec": world * (n_r2 + n_rg) * args.vel_iters /
+                                       (timers.get("velocity_resolution", 0.0) * 1e-3) if timers.get("velocity_resolution") else None,
+            "roofline": {"bound": "hbm", "kernel": "k_velocity_solve", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": ab["velocity_kernel"], "kernel_ms": vk_ms,
+                         "peak_source": peak_src,
+                         "step_algorithmic_bytes": ab["step"],
+                         "step_frac": ab["step"] / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "stage_ms": timers,
+            "phases": {"velocity": int(stats["n_phases_velocity"]), "position": int(stats["n_phases_position"])},
+            "residual_max": float(stats["residual_max"]), "max_penetration": float(stats["max_penetration"]),
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = {"value": world * nb * args.steps / (e2e["ms"] * 1e-3), "unit": "body-steps/s",
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "ms_per_step": e2e["ms"] / args.steps}
+        if world == 1 and not args.no_cpu_baseline:
+            sgrid = "20x40x20" if args.grid == "50x40x50" else args.grid
+            scs, ms_, cs_ = build_workload(sgrid, args.vel_iters, args.pos_iters)
+            dt, _ = cpu_reference_run(scs, ms_, cs_, args.cpu_sample_steps, 1)
+            line["cpu_baseline"] = {"value": scs.n_dynamic * args.cpu_sample_steps / dt, "unit": "body-steps/s",
+                                    "cores": 1, "kind": "port",
+                                    "sample": "%d steps of a %s settled sub-pile (%d boxes) through "
+                                              "oracle/liboracle.so, single thread (the reference is single-threaded)"
+                                              % (args.cpu_sample_steps, sgrid, scs.n_dynamic)}
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -297,6 +297,10 @@ int nb2_download_joints(nb2_context* ctx, nb2_joint* out, uint32_t n_joints);
 /* Runs the residual / penetration / energy reduction for the last step and
  * returns it with the counters and timers. */
 int nb2_get_stats(nb2_context* ctx, nb2_stats* out);
+/* Stage timers of the last step only (needs nb2_enable_timers): waits for the step's last event
+ * and writes {assembly, velocity_resolution, velocity_update, position_resolution, step,
+ * velocity_kernel, position_kernel, schedule} in milliseconds.  No reductions are launched. */
+int nb2_get_timers(nb2_context* ctx, float* out8);
 /* Number of kernels this context launched since creation (bench.py's
  * gpu_launches). */
 int nb2_launch_count(const nb2_context* ctx, uint64_t* out);

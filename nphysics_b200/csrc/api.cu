@@ -75,16 +75,18 @@ static int do_step(Context* ctx, int mode) {
     ctx->cur = 1 - ctx->cur;
     const bool tm = ctx->timers;
     if (tm && !ctx->ev.created) {
-        for (int k = 0; k < 6; ++k) NB2_CUDA(ctx, cudaEventCreate(&ctx->ev.e[k]));
+        for (int k = 0; k < 12; ++k) NB2_CUDA(ctx, cudaEventCreate(&ctx->ev.e[k]));
         ctx->ev.created = true;
     }
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[0], ctx->stream));
     // ---- dynamics refresh + assembly (Counters: "assembly")
     NB2_TRY(launch_refresh_dynamics(ctx));
     ctx->max_chunks = (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[10], ctx->stream));
     NB2_TRY(launch_build_items(ctx, mode));
     NB2_TRY(launch_schedule(ctx, &ctx->vs, mode));
     if (ref) NB2_TRY(launch_schedule(ctx, &ctx->ps, mode));
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[11], ctx->stream));
     NB2_TRY(launch_assemble(ctx, mode));
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[1], ctx->stream));
     // ---- velocity resolution + impulse caching (Counters: "velocity resolution")
@@ -95,7 +97,9 @@ static int do_step(Context* ctx, int mode) {
     NB2_TRY(launch_integrate(ctx, false));
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[3], ctx->stream));
     // ---- position resolution
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[8], ctx->stream));
     NB2_TRY(launch_position_solve(ctx, mode));
+    if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[9], ctx->stream));
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[4], ctx->stream));
     // ---- kinematic bodies (mechanical_world.rs:328-332)
     NB2_TRY(launch_integrate(ctx, true));
@@ -254,7 +258,7 @@ int nb2_destroy(nb2_context* h) {
     cudaStreamSynchronize(ctx->stream);
     release_all(ctx);
     if (ctx->ev.created)
-        for (int k = 0; k < 6; ++k) cudaEventDestroy(ctx->ev.e[k]);
+        for (int k = 0; k < 12; ++k) cudaEventDestroy(ctx->ev.e[k]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete h;
     return NB2_OK;
@@ -460,7 +464,15 @@ int nb2_get_stats(nb2_context* h, nb2_stats* out) {
         memcpy(d, f + 4, sizeof(d));
         s.residual_max = f[0];
         s.residual_rms = u[0] ? (float)sqrt(d[0] / (double)u[0]) : 0.f;
-        s.max_penetration = f[1] > 0.f ? f[1] - 1000.f : 0.f;
+        {
+            int key = (int)u[4];
+            if (key == (int)0x80000000) {
+                s.max_penetration = 0.f;
+            } else {
+                int bits = key >= 0 ? key : (key ^ 0x7FFFFFFF);
+                memcpy(&s.max_penetration, &bits, sizeof(float));
+            }
+        }
         s.kinetic_energy = (float)d[1];
         s.n_rows_two_body = u[1];
         s.n_rows_ground = u[2];
@@ -493,6 +505,18 @@ int nb2_get_stats(nb2_context* h, nb2_stats* out) {
     *out = ctx->last_stats;
     if (rc != NB2_OK) return rc;
     if (out->non_finite) return set_error(ctx, NB2_ERR_NON_FINITE, "%u bodies have a non-finite state", out->non_finite);
+    return NB2_OK;
+}
+
+int nb2_get_timers(nb2_context* h, float* out8) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!out8) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null output");
+    if (!ctx->ev_valid) return set_error(ctx, NB2_ERR_NOT_READY, "timers were not enabled for the last step");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_CUDA(ctx, cudaEventSynchronize(ctx->ev.e[5]));
+    const int pairs[8][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {0, 5}, {6, 7}, {8, 9}, {10, 11}};
+    for (int k = 0; k < 8; ++k) NB2_CUDA(ctx, cudaEventElapsedTime(&out8[k], ctx->ev.e[pairs[k][0]], ctx->ev.e[pairs[k][1]]));
     return NB2_OK;
 }
 

