@@ -359,3 +359,70 @@ def row_counts(scene, manifolds):
         r2 += int(jr[jd1 & jd2].sum())
         rg += int(jr[jd1 ^ jd2].sum())
     return r2, rg
+
+
+def joint_zoo(seed=7, rad=0.2, density=1.0, with_limits=True):
+    """One short chain (ground -> b1 -> b2) per constraint-based joint type (the mix of
+    examples3d/constraints3.rs, plus Fixed / Cylindrical / Cartesian for completeness), slightly
+    perturbed so that every velocity row and every position generator has something to correct."""
+    rng = np.random.default_rng(seed)
+    types = list(range(10))
+    n = 1 + 2 * len(types)
+    bodies = abi.new_bodies(n)
+    bodies["status"][0] = abi.BODY_STATIC
+    bodies["flags"][0] = 0
+    m, inertia = cuboid_mass_properties((rad, rad * 0.8, rad * 1.2), density)
+    bodies["mass"][1:] = m
+    bodies["local_inertia"][1:] = inertia.reshape(9)
+    he = np.zeros((n, 3))
+    off = np.zeros((n, 3))
+    joints = abi.new_joints(2 * len(types))
+
+    def unit(v):
+        v = np.asarray(v, dtype=np.float64)
+        return v / np.linalg.norm(v)
+
+    def rand_quat(scale):
+        w = rng.normal(size=3) * scale
+        ang = np.linalg.norm(w)
+        if ang < 1e-12:
+            return np.array([0.0, 0.0, 0.0, 1.0])
+        ax = w / ang
+        return np.concatenate([ax * np.sin(ang / 2), [np.cos(ang / 2)]])
+
+    jn = 0
+    for k, t in enumerate(types):
+        base = np.array([3.0 * k, 5.0, 0.0])
+        parent, parent_pos = 0, base
+        for l in range(2):
+            b = 1 + 2 * k + l
+            a2 = np.array([0.0, 0.0, 1.0]) * (rad * 3.0 + 0.2)
+            pos = parent_pos - a2 + rng.normal(size=3) * 0.01     # small anchor error
+            bodies["position"][b, :3] = pos
+            bodies["position"][b, 3:] = rand_quat(0.05)           # small axis error
+            bodies["velocity"][b] = rng.normal(size=6) * 0.3
+            joints["type"][jn] = t
+            joints["body1"][jn] = parent
+            joints["body2"][jn] = b
+            joints["anchor1"][jn] = parent_pos if parent == 0 else np.zeros(3)
+            joints["anchor2"][jn] = a2
+            ax = unit(rng.normal(size=3))
+            joints["axis1"][jn] = ax
+            joints["axis2"][jn] = ax
+            if t == abi.JOINT_PIN_SLOT:
+                joints["axis3"][jn] = unit(np.cross(ax, rng.normal(size=3)))
+                joints["axis2"][jn] = joints["axis3"][jn]
+            if t == abi.JOINT_UNIVERSAL:
+                ax2 = unit(np.cross(ax, rng.normal(size=3)))
+                joints["axis2"][jn] = ax2
+                joints["angle"][jn] = np.pi / 2.0
+            if t == abi.JOINT_PRISMATIC and with_limits:
+                joints["flags"][jn] = abi.JOINT_FLAG_MIN_OFFSET | (abi.JOINT_FLAG_MAX_OFFSET if l else 0)
+                joints["min_offset"][jn] = 0.05 if l == 0 else -0.4
+                joints["max_offset"][jn] = 0.3
+            if t in (abi.JOINT_FIXED, abi.JOINT_CARTESIAN):
+                joints["ref_frame1"][jn] = rand_quat(0.3)
+                joints["ref_frame2"][jn] = joints["ref_frame1"][jn]
+            jn += 1
+            parent, parent_pos = b, pos
+    return Scene(bodies, he, off, joints, name="joint_zoo")

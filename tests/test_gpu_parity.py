@@ -1,0 +1,381 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Run with -m gpu on a B200.
+
+Tolerance (BASELINE.json north_star): reference-order mode must match the oracle's velocities,
+impulses and positions within 1e-5 relative (f32) after each step; the coloured production mode is
+judged on constraint residual, max penetration and energy against the oracle on the same scene."""
+import numpy as np
+import pytest
+
+from nphysics_b200 import abi, scenes
+from tests.conftest import rel_err
+from tests.golden import make_golden as G
+
+pytestmark = pytest.mark.gpu
+
+REF, COL = abi.MODE_REFERENCE_ORDER, abi.MODE_COLOURED
+TOL = 1e-5  # relative, f32 (north_star)
+
+
+def new_solver():
+    from nphysics_b200.solver import Solver
+    return Solver(0)
+
+
+def new_oracle():
+    from oracle import Oracle
+    return Oracle()
+
+
+def check_step(tag, g, o, tol=TOL):
+    sg, so = g.download_body_states(), o.download_body_states()
+    assert rel_err(sg["position"], so["position"]) <= tol, tag
+    assert rel_err(sg["velocity"], so["velocity"]) <= tol, tag
+    ig, io = g.download_contact_impulses(), o.download_contact_impulses()
+    assert ig.shape == io.shape
+    assert rel_err(ig, io) <= tol, tag
+
+
+def lockstep(sc, gen, params, steps, mode=REF, teacher=True, per_step=None):
+    g, o = new_solver(), new_oracle()
+    for s in (g, o):
+        s.set_params(params)
+        s.upload_bodies(sc.bodies)
+        if len(sc.joints):
+            s.upload_joints(sc.joints)
+    for k in range(steps):
+        st = o.download_body_states()
+        if gen is not None:
+            m, c = gen.generate(st["position"])
+        else:
+            m, c = np.zeros(0, abi.manifold_dtype), np.zeros(0, abi.contact_dtype)
+        if teacher and k > 0:
+            g.upload_body_states(st)
+        g.upload_manifolds(m, c)
+        o.upload_manifolds(m, c)
+        g.step(mode)
+        o.step()
+        g.synchronize()
+        if per_step is not None:
+            per_step(k, g, o)
+    return g, o
+
+
+# ------------------------------------------------------------------ reference-order parity
+def test_pyramid3_reference_order_each_step():
+    """BASELINE config 1: examples3d/pyramid3 as shipped, 8 velocity + 3 position iterations."""
+    sc = scenes.pyramid3(30)
+    gen = scenes.ContactGenerator(sc)
+    g, o = lockstep(sc, gen, sc.params, 8, per_step=lambda k, g, o: check_step("step %d" % k, g, o))
+    sg, so = g.get_stats(), o.get_stats()
+    assert int(sg["n_rows_two_body"]) == int(so["n_rows_two_body"]) == 15660
+    assert int(sg["n_rows_ground"]) == int(so["n_rows_ground"]) == 360
+    assert float(sg["residual_max"]) == pytest.approx(float(so["residual_max"]), rel=1e-4)
+    assert float(sg["max_penetration"]) == pytest.approx(float(so["max_penetration"]), rel=1e-4, abs=1e-7)
+    assert float(sg["kinetic_energy"]) == pytest.approx(float(so["kinetic_energy"]), rel=1e-4)
+
+
+def test_pyramid3_reference_order_free_running_drift():
+    """No teacher forcing: both sides integrate their own state for 40 steps."""
+    sc = scenes.pyramid3(12)
+    gen = scenes.ContactGenerator(sc)
+    g, o = lockstep(sc, gen, sc.params, 40, teacher=False)
+    sg, so = g.download_body_states(), o.download_body_states()
+    assert rel_err(sg["position"], so["position"]) <= 1e-4
+    assert np.abs(sg["velocity"] - so["velocity"]).max() <= 1e-3
+
+
+def test_flipped_manifolds_point_plane_and_iterations_10_5():
+    sc = scenes.boxes3(4, 4, 4)
+    p = abi.default_params()
+    p["max_velocity_iterations"] = 10
+    p["max_position_iterations"] = 5
+    gen = scenes.ContactGenerator(sc, flip_fraction=0.5)
+    lockstep(sc, gen, p, 5, per_step=lambda k, g, o: check_step("step %d" % k, g, o))
+
+
+def test_wall3_reference_order():
+    sc = scenes.wall3(50, 10)
+    gen = scenes.ContactGenerator(sc)
+    lockstep(sc, gen, sc.params, 4, per_step=lambda k, g, o: check_step("step %d" % k, g, o))
+
+
+def test_joint_zoo_reference_order_all_joint_types():
+    sc = scenes.joint_zoo()
+
+    def chk(k, g, o):
+        check_step("step %d" % k, g, o)
+        jg, jo = g.download_joints(), o.download_joints()
+        assert rel_err(jg["impulses"], jo["impulses"]) <= TOL
+        assert np.array_equal(jg["broken"], jo["broken"])
+    lockstep(sc, None, sc.params, 10, per_step=chk)
+
+
+def test_joint_breaking_matches():
+    sc = scenes.joint_zoo()
+    sc.joints["break_force_squared"] = 4.0
+    sc.joints["break_torque_squared"] = 0.05
+
+    def chk(k, g, o):
+        jg, jo = g.download_joints(), o.download_joints()
+        assert np.array_equal(jg["broken"], jo["broken"])
+        check_step("step %d" % k, g, o)
+    g, o = lockstep(sc, None, sc.params, 8, per_step=chk)
+    assert o.download_joints()["broken"].sum() > 0
+    assert int(g.get_stats()["n_broken_joints"]) == int(o.download_joints()["broken"].sum())
+
+
+def test_mixed_joint_and_contact_rows():
+    """BASELINE config 4 in small: revolute chains lying on the ground (joint + contact rows)."""
+    sc = scenes.joint_chains(6, 6, kind="revolute", with_ground_collider=True, ground_y=-0.22)
+    gen = scenes.ContactGenerator(sc)
+    g, o = lockstep(sc, gen, sc.params, 6, per_step=lambda k, g, o: check_step("step %d" % k, g, o))
+    assert int(g.get_stats()["n_contacts"]) > 0
+
+
+def test_kinematic_platform_restitution_masks_damping():
+    sc = scenes.boxes3(2, 3, 2, height=1.0)
+    sc.restitution = 0.4
+    b = sc.bodies
+    b["status"][1] = abi.BODY_KINEMATIC
+    b["velocity"][1, :3] = (0.0, 0.8, 0.0)
+    b["velocity"][2:, 1] = -2.5
+    b["jacobian_mask"][3, 3:] = 0.0           # rotations locked on one body
+    b["jacobian_mask"][4, 0] = 0.0            # x translation locked on another
+    b["linear_damping"][5] = 0.3
+    b["angular_damping"][5] = 0.7
+    b["max_linear_velocity"][6] = 1.0
+    b["external_forces"][7] = (0.01, 0.0, 0.0, 0.0, 0.002, 0.0)
+    b["local_com"][8] = (0.01, -0.02, 0.005)
+    gen = scenes.ContactGenerator(sc)
+    lockstep(sc, gen, sc.params, 6, per_step=lambda k, g, o: check_step("step %d" % k, g, o))
+
+
+def test_warm_start_cache_and_null_keys():
+    sc = scenes.boxes3(3, 3, 3)
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    g, o = new_solver(), new_oracle()
+    for s in (g, o):
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+    for k in range(4):
+        cc = c.copy()
+        if k == 2:
+            cc["key"][::3] = 0                       # some null ids: never cached
+        if k == 3:
+            cc = cc[::-1].copy()                     # same keys, different order
+            mm = m.copy()
+            mm["first_contact"] = len(c) - m["first_contact"] - m["num_contacts"]
+        else:
+            mm = m
+        for s in (g, o):
+            s.upload_manifolds(mm, cc)
+        g.step(REF)
+        o.step()
+        g.synchronize()
+        check_step("step %d" % k, g, o)
+    g.clear_impulse_cache()
+    o.clear_impulse_cache()
+    for s in (g, o):
+        s.upload_manifolds(m, c)
+    g.step(REF)
+    o.step()
+    check_step("after clear", g, o)
+
+
+@pytest.mark.parametrize("name", sorted(G.cases().keys()))
+def test_reference_order_reproduces_committed_golden(name):
+    """Against the fixtures under tests/golden/ (teacher-forced on the golden states)."""
+    sc, gen, params, steps = G.cases()[name]
+    gold = G.load(name)
+    res = G.run_case(new_solver(), REF, sc, gen, params, steps, teacher=gold)
+    for k in range(steps):
+        assert rel_err(res["states"][k]["position"], gold["states"][k]["position"]) <= TOL, (name, k)
+        assert rel_err(res["states"][k]["velocity"], gold["states"][k]["velocity"]) <= TOL, (name, k)
+        assert rel_err(res["impulses"][k], gold["impulses"][k]) <= TOL, (name, k)
+    if len(sc.joints):
+        assert rel_err(res["joints"]["impulses"], gold["joint_impulses"]) <= TOL
+
+
+# ------------------------------------------------------------------ coloured production mode
+def settle(sc, gen, params, steps, mode):
+    """Free-running simulation with its own contact generation; returns stats history."""
+    s = new_solver() if mode is not None else new_oracle()
+    s.set_params(params)
+    s.upload_bodies(sc.bodies)
+    if len(sc.joints):
+        s.upload_joints(sc.joints)
+    hist = []
+    for k in range(steps):
+        st = s.download_body_states()
+        m, c = gen.generate(st["position"]) if gen is not None else (np.zeros(0, abi.manifold_dtype),
+                                                                     np.zeros(0, abi.contact_dtype))
+        s.upload_manifolds(m, c)
+        s.step(mode)
+        hist.append(s.get_stats().copy())
+    return s, hist
+
+
+@pytest.mark.parametrize("scene_name", ["pyramid3", "wall3_tall", "boxes_8x8x8"])
+def test_coloured_mode_quality_matches_oracle(scene_name):
+    """Same scene, 60 free-running steps: final residual, max penetration and kinetic energy of
+    the coloured mode within a stated tolerance of the sequential reference order."""
+    if scene_name == "pyramid3":
+        sc = scenes.pyramid3(30)
+    elif scene_name == "wall3_tall":
+        sc = scenes.wall3(20, 40)
+    else:
+        sc = scenes.boxes3(8, 8, 8)
+    gen = scenes.ContactGenerator(sc)
+    sg, hg = settle(sc, gen, sc.params, 60, COL)
+    so, ho = settle(sc, gen, sc.params, 60, None)
+    tail = slice(40, 60)
+    res_g = np.mean([float(h["residual_max"]) for h in hg[tail]])
+    res_o = np.mean([float(h["residual_max"]) for h in ho[tail]])
+    pen_g = max(float(h["max_penetration"]) for h in hg[tail])
+    pen_o = max(float(h["max_penetration"]) for h in ho[tail])
+    ke_g = np.mean([float(h["kinetic_energy"]) for h in hg[tail]])
+    ke_o = np.mean([float(h["kinetic_energy"]) for h in ho[tail]])
+    assert hg[-1]["non_finite"] == 0
+    # tolerances: residual and energy within 3x of the sequential order (the order changes the
+    # iterate, not the fixed point), penetration within 1.5x + the allowed linear error
+    assert res_g <= 3.0 * res_o + 1e-6, (res_g, res_o)
+    assert pen_g <= 1.5 * pen_o + 0.001, (pen_g, pen_o)
+    assert ke_g <= 3.0 * ke_o + 1e-4, (ke_g, ke_o)
+    # the pile must not have collapsed or exploded: same top height within 1 cm
+    pg, po = sg.download_body_states()["position"], so.download_body_states()["position"]
+    assert abs(float(pg[:, 1].max()) - float(po[:, 1].max())) < 0.01
+    # invariants of the row updates hold in any order
+    imp = sg.download_contact_impulses()
+    assert np.all(imp[:, 0] >= 0.0)
+    assert int(hg[-1]["n_phases_velocity"]) <= 64
+
+
+def test_coloured_joint_chains_quality():
+    sc = scenes.joint_chains(16, 6, with_ground_collider=False)
+    sg, hg = settle(sc, None, sc.params, 60, COL)
+    so, ho = settle(sc, None, sc.params, 60, None)
+    assert hg[-1]["non_finite"] == 0
+    pg, po = sg.download_body_states()["position"], so.download_body_states()["position"]
+    assert np.abs(pg[:, :3] - po[:, :3]).max() < 0.1      # same swing, different sweep order
+    ke_g, ke_o = float(hg[-1]["kinetic_energy"]), float(ho[-1]["kinetic_energy"])
+    assert ke_g == pytest.approx(ke_o, rel=0.05)
+
+
+def test_colouring_is_conflict_free_and_deterministic():
+    """Two runs give identical bits (the colouring has no scheduling-dependent choice) and the
+    stats' row counts equal the analytic ones."""
+    sc = scenes.boxes3(6, 6, 6)
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    outs = []
+    for _ in range(2):
+        s = new_solver()
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+        for _ in range(3):
+            s.upload_manifolds(m, c)
+            s.step(COL)
+        outs.append((s.download_body_states(), s.download_contact_impulses(), s.get_stats()))
+    assert np.array_equal(outs[0][0]["position"], outs[1][0]["position"])
+    assert np.array_equal(outs[0][0]["velocity"], outs[1][0]["velocity"])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    r2, rg = scenes.row_counts(sc, m)
+    assert int(outs[0][2]["n_rows_two_body"]) == r2 and int(outs[0][2]["n_rows_ground"]) == rg
+    assert int(outs[0][2]["n_phases_velocity"]) <= 16
+
+
+# ------------------------------------------------------------------ full size, properties
+def test_full_size_100k_pile_properties():
+    """BASELINE config 2 at full size (50x40x50): size-independent properties of one step."""
+    sc = scenes.boxes3(50, 40, 50)
+    p = abi.default_params()
+    p["max_velocity_iterations"] = 10
+    p["max_position_iterations"] = 5
+    m, c = scenes.ContactGenerator(sc).generate()
+    assert (len(m), len(c)) == (296000, 1184000)
+    s = new_solver()
+    s.set_params(p)
+    s.upload_bodies(sc.bodies)
+    for _ in range(3):
+        s.upload_manifolds(m, c)
+        s.step(COL)
+    st = s.get_stats()
+    assert st["non_finite"] == 0
+    assert (int(st["n_rows_two_body"]), int(st["n_rows_ground"])) == (3522000, 30000)
+    imp = s.download_contact_impulses()
+    assert np.all(imp[:, 0] >= 0.0)                                         # Signorini
+    assert np.all(np.abs(imp[:, 1:]) <= 0.5 * imp[:, 0:1].max() + 1e-6)     # friction bounded
+    # the ground carries the pile: sum of ground normal impulses ~ total weight * dt
+    ground = np.repeat((m["body1"] == 0) | (m["body2"] == 0), m["num_contacts"])
+    weight = float(sc.bodies["mass"][1:].astype(np.float64).sum()) * 9.81 / 60.0
+    assert imp[ground, 0].sum() == pytest.approx(weight, rel=0.35)          # 3 steps of a 40-high pile
+    bodies = s.download_body_states()
+    assert np.abs(bodies["velocity"]).max() < 5.0
+    assert np.array_equal(bodies["position"][0], sc.bodies["position"][0])   # static ground untouched
+
+
+def test_bad_records_are_reported_not_crashing():
+    from nphysics_b200.solver import Nb2Error
+    sc = scenes.boxes3(2, 2, 2)
+    m, c = scenes.ContactGenerator(sc).generate()
+    s = new_solver()
+    s.set_params(sc.params)
+    s.upload_bodies(sc.bodies)
+    bad = m.copy()
+    bad["body2"][0] = 10 ** 6
+    s.upload_manifolds(bad, c)
+    s.step(COL)
+    with pytest.raises(Nb2Error) as ei:
+        s.synchronize()
+    assert ei.value.code == abi.ERR_BAD_INDEX
+    with pytest.raises(Nb2Error):
+        s.step(7)
+
+
+def test_empty_inputs_and_ragged_manifolds():
+    sc = scenes.boxes3(3, 2, 3)
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    # ragged: drop one contact from every third manifold, two from every fifth
+    keep = np.ones(len(c), bool)
+    for i in range(len(m)):
+        f = int(m["first_contact"][i])
+        if i % 3 == 0:
+            keep[f] = False
+        if i % 5 == 0:
+            keep[f + 1] = False
+            keep[f + 2] = False
+    nc = np.array([keep[int(f):int(f) + int(n)].sum() for f, n in zip(m["first_contact"], m["num_contacts"])])
+    m2 = m.copy()
+    m2["num_contacts"] = nc
+    m2["first_contact"] = np.concatenate([[0], np.cumsum(nc)[:-1]])
+    c2 = c[keep].copy()
+    # a manifold with 7 contacts (two chunks) and one with none
+    extra = np.concatenate([c2[:4], c2[:3]]).copy()
+    extra["key"] = np.arange(1, 8, dtype=np.uint64) + np.uint64(10 ** 9)
+    m3 = np.concatenate([m2, m2[:2]])
+    m3["first_contact"][-2] = len(c2)
+    m3["num_contacts"][-2] = 7
+    m3["first_contact"][-1] = 0
+    m3["num_contacts"][-1] = 0
+    c3 = np.concatenate([c2, extra])
+    g, o = new_solver(), new_oracle()
+    for s in (g, o):
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+        s.upload_manifolds(m3, c3)
+    g.step(REF)
+    o.step()
+    g.synchronize()
+    check_step("ragged", g, o)
+    # no contacts at all
+    e_m, e_c = np.zeros(0, abi.manifold_dtype), np.zeros(0, abi.contact_dtype)
+    for s in (g, o):
+        s.upload_manifolds(e_m, e_c)
+    g.step(REF)
+    o.step()
+    g.synchronize()
+    check_step("empty", g, o)
+    g.step(COL)
+    g.synchronize()
