@@ -6,6 +6,8 @@
 // pair), keeps the two bodies' mj_lambda in registers and streams its rows from the ELL planes.
 // k_position_solve replaces NonlinearSORProx::solve (src/solver/nonlinear_sor_prox.rs:17-310)
 // with ncollide's ContactKinematic::contact restated for Plane/Point, Point/Plane, Point/Point.
+#include <stdlib.h>
+
 #include "solver.cuh"
 
 namespace nb2 {
@@ -140,14 +142,15 @@ __device__ __forceinline__ float solve_row(int kind, float4 h, float impulse, fl
 
 // mode_warm: 1 = run a warm-start pass over the phases first (coloured mode)
 __global__ void __launch_bounds__(TPB) k_velocity_solve(SchedDev sd, Rows R, float4* lam, int iters, int mode_warm,
-                                                        unsigned int* barrier) {
+                                                        int symmetric, unsigned int* barrier) {
     GridBarrier gb;
     gb.init(barrier);
     const unsigned int np = sd.hdr->n_phases;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (int it = mode_warm ? -1 : 0; it < iters; ++it) {
-        for (unsigned int p = 0; p < np; ++p) {
+        for (unsigned int pp = 0; pp < np; ++pp) {
+            const unsigned int p = (symmetric && (it & 1)) ? (np - 1 - pp) : pp;
             const unsigned int cnt = sd.ph_count[p];
             const size_t rbase = sd.ph_rbase[p], gbase = sd.ph_gbase[p];
             for (size_t g = tid; g < cnt; g += stride) {
@@ -739,7 +742,10 @@ int launch_velocity_solve(Context* ctx, int mode) {
     size_t want = (ctx->vs.n_items + TPB - 1) / TPB;
     int blocks = (int)(want < (size_t)ctx->coop_blocks_vel ? want : (size_t)ctx->coop_blocks_vel);
     if (blocks < 1) blocks = 1;
-    void* args[] = {&sd, &R, &lam, &iters, &warm, &bar};
+    // alternating the colour order per sweep (symmetric Gauss-Seidel) was measured: it helps flat
+    // piles and hurts tall ones (profiles/r01_notes.md), so the plain order stays the default
+    int symmetric = 0;
+    void* args[] = {&sd, &R, &lam, &iters, &warm, &symmetric, &bar};
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_velocity_solve, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[7], ctx->stream));
