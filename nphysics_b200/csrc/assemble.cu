@@ -25,6 +25,9 @@ struct SchedView {
     const unsigned int* ph_count;
     const unsigned int* ph_gbase;
     const unsigned int* ph_rbase;
+    const int4* g_info;
+    const int* it_src;
+    const SchedHeader* hdr;
     unsigned int max_phases;
     __device__ __forceinline__ unsigned int phase_of(size_t item) const {
         return min((unsigned int)it_phase[item], max_phases - 1);
@@ -46,6 +49,9 @@ static SchedView view_of(const Sched& s) {
     v.ph_count = s.ph_count.p;
     v.ph_gbase = s.ph_gbase.p;
     v.ph_rbase = s.ph_rbase.p;
+    v.g_info = s.g_info.p;
+    v.it_src = s.it_src.p;
+    v.hdr = s.hdr.p;
     v.max_phases = (unsigned int)s.max_phases;
     return v;
 }
@@ -201,11 +207,37 @@ __device__ __forceinline__ void ht_insert(unsigned long long* keys, unsigned int
 __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     int mode, unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
     const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
-    const unsigned int* __restrict__ chunk_base, BodyArrays B, SchedView vs, SchedView ps, RowOut out,
-    float4* p_row, size_t n_pslots_max, const unsigned long long* __restrict__ ht_keys,
+    const unsigned int* __restrict__ chunk_base, const unsigned int* __restrict__ chunk_manifold, BodyArrays B,
+    SchedView vs, SchedView ps, RowOut out, float4* p_row, size_t n_pslots_max,
+    const unsigned long long* __restrict__ ht_keys,
     const unsigned int* __restrict__ ht_vals, size_t ht_cap, const float4* __restrict__ imp_prev,
     float warmstart_coeff, float restitution_threshold, float inv_dt) {
-    unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int ci;
+    if (mode == NB2_MODE_COLOURED) {
+        // Gather formulation: threads enumerate the (phase, contact lane, group) slots in ELL order,
+        // so the row planes are WRITTEN with consecutive threads on consecutive 16-byte words; the
+        // scattered side is the read of the 112-byte contact record.
+        const size_t T = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const unsigned int np = vs.hdr->n_phases;
+        if (np == 0 || T >= (size_t)NB2_CHUNK * vs.ph_gbase[np]) return;
+        unsigned int lo = 0, hi = np;  // largest p with NB2_CHUNK * gbase[p] <= T
+        while (hi - lo > 1) {
+            unsigned int mid = (lo + hi) >> 1;
+            if ((size_t)NB2_CHUNK * vs.ph_gbase[mid] <= T) lo = mid; else hi = mid;
+        }
+        const unsigned int p = lo, cnt = vs.ph_count[p];
+        const size_t local = T - (size_t)NB2_CHUNK * vs.ph_gbase[p];
+        const unsigned int lane = (unsigned int)(local / cnt), g = (unsigned int)(local % cnt);
+        const int item = vs.g_info[vs.ph_gbase[p] + g].w;
+        if (vs.it_type[item] != NB2_ITEM_CONTACTS) return;
+        const unsigned int chunk_ = (unsigned int)vs.it_src[item];
+        const unsigned int m_ = chunk_manifold[chunk_];
+        const unsigned int lchunk = chunk_ - chunk_base[m_];
+        if (NB2_CHUNK * lchunk + lane >= manifolds[m_].num_contacts) return;
+        ci = manifolds[m_].first_contact + NB2_CHUNK * lchunk + lane;
+    } else {
+        ci = blockIdx.x * blockDim.x + threadIdx.x;
+    }
     if (ci >= nC) return;
     const unsigned int m = c_manifold[ci];
     if (m == 0xFFFFFFFFu) return;
@@ -581,9 +613,12 @@ int launch_assemble(Context* ctx, int mode) {
         ctx->launches++;
     }
     if (ctx->n_contacts) {
-        k_assemble_contacts<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
+        // coloured: one thread per (group, contact lane) slot in ELL order; reference: one per contact
+        const size_t nthreads = ref ? (size_t)ctx->n_contacts : (size_t)NB2_CHUNK * n_items;
+        k_assemble_contacts<<<nblk(nthreads), TPB, 0, ctx->stream>>>(
             mode, ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p,
-            ctx->c_manifold.p, ctx->chunk_base.p, body_arrays(ctx), vs, ps, row_out(ctx), ctx->p_row.p,
+            ctx->c_manifold.p, ctx->chunk_base.p, ctx->chunk_manifold.p, body_arrays(ctx), vs, ps, row_out(ctx),
+            ctx->p_row.p,
             ctx->n_pslots_max, ctx->ht_keys[prev].p, ctx->ht_vals[prev].p, ctx->ht_cap[prev], ctx->imp[prev].p,
             ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt);
         ctx->launches++;

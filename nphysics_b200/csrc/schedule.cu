@@ -527,7 +527,9 @@ __global__ void k_fill_ginfo(size_t n, const int* __restrict__ it_type, const in
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || it_type[i] == NB2_ITEM_INVALID) return;
     unsigned int p = min((unsigned int)phase[i], max_phases - 1);
-    g_info[ph_gbase[p] + slot[i]] = make_int4(it_a[i], it_b[i], it_nrows[i], (int)i);
+    // z packs the row count (low 8 bits) and the item type (bits 8..) so the solve kernels need
+    // no second lookup
+    g_info[ph_gbase[p] + slot[i]] = make_int4(it_a[i], it_b[i], it_nrows[i] | (it_type[i] << 8), (int)i);
 }
 __global__ void k_copy_phase(size_t n, const int* __restrict__ level, int* phase) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

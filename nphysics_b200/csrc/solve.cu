@@ -140,13 +140,55 @@ __device__ __forceinline__ float solve_row(int kind, float4 h, float impulse, fl
     return ni;
 }
 
+// A row as it travels from the ELL planes to the update: 6 jacobian quads, header, meta, the
+// row's impulse and (for Dependent rows) the impulse of the row it depends on.
+struct RowPkt {
+    float4 q0, q1, q2, q3, q4, q5, h;
+    int2 meta;
+    float imp;
+};
+// All loads of a row are issued together and one row ahead of its use (software pipelining):
+// per phase an SM owns only ~200 groups, so latency is hidden by loads in flight per thread,
+// not by occupancy.  Read-only planes go through ld.global.nc; impulses bypass L1 (ld.cg)
+// because other SMs wrote them in an earlier phase.
+__device__ __forceinline__ void load_pkt(const Rows& R, size_t slot, bool a, bool b, RowPkt* o) {
+    o->meta = __ldg(&R.meta[slot]);
+    o->h = __ldg(&R.hdr[slot]);
+    o->q1 = __ldg(&R.jac[1 * R.S + slot]);
+    o->q4 = __ldg(&R.jac[4 * R.S + slot]);
+    if (a) {
+        o->q0 = __ldg(&R.jac[0 * R.S + slot]);
+        o->q3 = __ldg(&R.jac[3 * R.S + slot]);
+    }
+    if (b) {
+        o->q2 = __ldg(&R.jac[2 * R.S + slot]);
+        o->q5 = __ldg(&R.jac[5 * R.S + slot]);
+    }
+    o->imp = __ldcg(&R.imp[slot]);
+}
+__device__ __forceinline__ void unpack_pkt(const RowPkt& k, bool a, bool b, RowJ* o) {
+    if (a) {
+        o->J1[0] = k.q0.x; o->J1[1] = k.q0.y; o->J1[2] = k.q0.z; o->J1[3] = k.q0.w; o->J1[4] = k.q1.x; o->J1[5] = k.q1.y;
+        o->W1[0] = k.q3.x; o->W1[1] = k.q3.y; o->W1[2] = k.q3.z; o->W1[3] = k.q3.w; o->W1[4] = k.q4.x; o->W1[5] = k.q4.y;
+    }
+    if (b) {
+        o->J2[0] = k.q1.z; o->J2[1] = k.q1.w; o->J2[2] = k.q2.x; o->J2[3] = k.q2.y; o->J2[4] = k.q2.z; o->J2[5] = k.q2.w;
+        o->W2[0] = k.q4.z; o->W2[1] = k.q4.w; o->W2[2] = k.q5.x; o->W2[3] = k.q5.y; o->W2[4] = k.q5.z; o->W2[5] = k.q5.w;
+    }
+}
+// Warps are dealt to groups block-interleaved (warp w of block b is global warp w*gridDim+b) so a
+// phase with fewer groups than threads still spreads evenly over all SMs.
+__device__ __forceinline__ size_t interleaved_tid() {
+    return ((size_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
+}
+
 // mode_warm: 1 = run a warm-start pass over the phases first (coloured mode)
 __global__ void __launch_bounds__(TPB) k_velocity_solve(SchedDev sd, Rows R, float4* lam, int iters, int mode_warm,
                                                         int symmetric, unsigned int* barrier) {
     GridBarrier gb;
     gb.init(barrier);
     const unsigned int np = sd.hdr->n_phases;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t tid = interleaved_tid();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (int it = mode_warm ? -1 : 0; it < iters; ++it) {
         for (unsigned int pp = 0; pp < np; ++pp) {
@@ -156,28 +198,46 @@ __global__ void __launch_bounds__(TPB) k_velocity_solve(SchedDev sd, Rows R, flo
             for (size_t g = tid; g < cnt; g += stride) {
                 const int4 info = sd.g_info[gbase + g];
                 const bool a = info.x >= 0, b = info.y >= 0;
+                const int nrows = info.z & 0xFF, type = info.z >> 8;
+                RowPkt cur, nxt;
+                if (nrows > 0) load_pkt(R, rbase + g, a, b, &cur);
+                // Coloured contact groups hold their own normal rows (rows 2*ncc..3*ncc): their
+                // impulses are fetched up front so friction rows never chase a dependent load.
+                const int ncc = type == NB2_ITEM_CONTACTS ? nrows / 3 : 0;
+                float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+                if (ncc > 0) n0 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 0) * cnt + g]);
+                if (ncc > 1) n1 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 1) * cnt + g]);
+                if (ncc > 2) n2 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 2) * cnt + g]);
+                if (ncc > 3) n3 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 3) * cnt + g]);
                 Lam la, lb;
                 if (a) la = load_lam(lam, info.x);
                 if (b) lb = load_lam(lam, info.y);
-                for (int r = 0; r < info.z; ++r) {
+                for (int r = 0; r < nrows; ++r) {
                     const size_t slot = rbase + (size_t)r * cnt + g;
-                    const int2 meta = __ldg(&R.meta[slot]);
-                    if (meta.x == NB2_ROW_NONE) continue;
-                    float impulse = __ldcg(&R.imp[slot]);
-                    RowJ J;
-                    load_row_j(R, slot, a, b, &J);
-                    if (it < 0) {  // warm start (sor_prox.rs:345-435)
-                        if (impulse != 0.f) {
-                            if (a) axpy6(impulse, J.W1, la.v);
-                            if (b) axpy6(impulse, J.W2, lb.v);
+                    if (r + 1 < nrows) load_pkt(R, slot + cnt, a, b, &nxt);
+                    if (cur.meta.x != NB2_ROW_NONE) {
+                        RowJ J;
+                        unpack_pkt(cur, a, b, &J);
+                        if (it < 0) {  // warm start (sor_prox.rs:345-435)
+                            if (cur.imp != 0.f) {
+                                if (a) axpy6(cur.imp, J.W1, la.v);
+                                if (b) axpy6(cur.imp, J.W2, lb.v);
+                            }
+                        } else {
+                            float dep = 0.f;
+                            if (cur.meta.x == NB2_ROW_DEPENDENT) {
+                                if (r < 2 * ncc) {
+                                    const int k = r >> 1;
+                                    dep = k == 0 ? n0 : (k == 1 ? n1 : (k == 2 ? n2 : n3));
+                                } else {
+                                    dep = __ldcg(&R.imp[cur.meta.y]);  // reference order: another group's row
+                                }
+                            }
+                            float ni = solve_row(cur.meta.x, cur.h, cur.imp, dep, J, a, b, &la, &lb);
+                            if (ni != cur.imp) __stcg(&R.imp[slot], ni);
                         }
-                        continue;
                     }
-                    const float4 h = __ldg(&R.hdr[slot]);
-                    float dep = 0.f;
-                    if (meta.x == NB2_ROW_DEPENDENT) dep = __ldcg(&R.imp[meta.y]);
-                    float ni = solve_row(meta.x, h, impulse, dep, J, a, b, &la, &lb);
-                    if (ni != impulse) __stcg(&R.imp[slot], ni);
+                    cur = nxt;
                 }
                 if (a) store_lam(lam, info.x, la);
                 if (b) store_lam(lam, info.y, lb);
@@ -516,7 +576,7 @@ __global__ void __launch_bounds__(TPB) k_position_solve(SchedDev sd, PosArrays A
     GridBarrier gb;
     gb.init(barrier);
     const unsigned int np = sd.hdr->n_phases;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t tid = interleaved_tid();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (int it = 0; it < iters; ++it) {
         for (unsigned int p = 0; p < np; ++p) {
@@ -541,7 +601,7 @@ __global__ void __launch_bounds__(TPB) k_position_solve(SchedDev sd, PosArrays A
                     load_pos_body(A, mf.body1, &b1);
                     load_pos_body(A, mf.body2, &b2);
                     const Pose c1 = load_coll(mf.coll1_wrt_body), c2 = load_coll(mf.coll2_wrt_body);
-                    const int nrows = info.z / rows_div;
+                    const int nrows = (info.z & 0xFF) / rows_div;
                     bool moved1 = false, moved2 = false;
                     for (int lcc = 0; lcc < nrows; ++lcc) {
                         const size_t ps = (size_t)NB2_CHUNK * gbase + (size_t)lcc * cnt + g;
@@ -610,7 +670,7 @@ __global__ void __launch_bounds__(TPB) k_residual(SchedDev sd, Rows R, const flo
             Lam la, lb;
             if (a) la = load_lam(lam, info.x);
             if (b) lb = load_lam(lam, info.y);
-            for (int r = 0; r < info.z; ++r) {
+            for (int r = 0; r < (info.z & 0xFF); ++r) {
                 const size_t slot = rbase + (size_t)r * cnt + g;
                 const int2 meta = R.meta[slot];
                 if (meta.x == NB2_ROW_NONE) continue;
@@ -676,7 +736,7 @@ __global__ void __launch_bounds__(TPB) k_penetration(SchedDev sd, PosArrays A,
             load_pos_body(A, mf.body2, &b2);
             const Pose m1 = pose_mul(b1.bp.pose, load_coll(mf.coll1_wrt_body));
             const Pose m2 = pose_mul(b2.bp.pose, load_coll(mf.coll2_wrt_body));
-            const int nrows = info.z / rows_div;
+            const int nrows = (info.z & 0xFF) / rows_div;
             for (int lcc = 0; lcc < nrows; ++lcc) {
                 const size_t ps = (size_t)NB2_CHUNK * gbase + (size_t)lcc * cnt + g;
                 ContactEval ce;

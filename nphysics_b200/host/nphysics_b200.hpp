@@ -1,0 +1,468 @@
+// nphysics_b200.hpp -- C++ host mirror of the reference's interface for the solver hot path.
+//
+// The reference is Rust; this environment has no Rust toolchain, so the compiled host side above
+// the C ABI is C++ (task rule 2).  Names, argument meaning and error behaviour follow the
+// reference:
+//   IntegrationParameters      src/solver/integration_parameters.rs:5-190
+//   BodyStatus                 src/object/body.rs:50-59
+//   RigidBodyDesc / RigidBody  src/object/rigid_body.rs:26-50, 949-1086
+//   Ground                     src/object/ground.rs:15-40
+//   DefaultBodySet             src/object/body_set.rs:61-175
+//   *Constraint (joints)       src/joint/*_constraint.rs
+//   ColliderContactManifold    src/detection/collider_contact_manifold.rs:9-115
+//   ContactModel / SignoriniCoulombPyramidModel   src/solver/contact_model.rs:13-37,
+//                              src/solver/signorini_coulomb_pyramid_model.rs:19-54
+//   MoreauJeanSolver           src/solver/moreau_jean_solver.rs:14-90
+//   MechanicalWorld::step      src/world/mechanical_world.rs:182-396 (solver part only)
+//   Counters                   src/counters/mod.rs:19-219 (solver stages)
+// Everything funnels into include/nphysics_b200.h; there is no CPU path.
+#pragma once
+#include <array>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nphysics_b200.h"
+
+namespace nphysics {
+
+using Vector3 = std::array<float, 3>;
+using Quaternion = std::array<float, 4>;  // i, j, k, w (nalgebra storage order)
+
+struct Isometry3 {
+    Vector3 translation{0.f, 0.f, 0.f};
+    Quaternion rotation{0.f, 0.f, 0.f, 1.f};
+};
+
+// The reference panics on invariant violations (assert!/unwrap); the mirror throws.
+struct SolverError : std::runtime_error {
+    int code;
+    SolverError(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// integration_parameters.rs:5-190
+class IntegrationParameters {
+    float dt_ = 1.0f / 60.0f;
+    float inv_dt_ = 60.0f;
+
+  public:
+    float erp = 0.2f;
+    float warmstart_coeff = 1.0f;
+    float restitution_velocity_threshold = 1.0f;
+    float allowed_linear_error = 0.001f;
+    float allowed_angular_error = 0.001f;
+    float max_linear_correction = 0.2f;
+    float max_angular_correction = 0.2f;
+    float max_stabilization_multiplier = 0.2f;
+    size_t max_velocity_iterations = 8;
+    size_t max_position_iterations = 3;
+    size_t max_ccd_position_iterations = 10;
+    size_t max_ccd_substeps = 1;
+    bool return_after_ccd_substep = false;
+    bool multiple_ccd_substep_sensor_events_enabled = false;
+    bool ccd_on_penetration_enabled = false;
+
+    float dt() const { return dt_; }
+    float inv_dt() const { return inv_dt_; }
+    void set_dt(float dt) {  // :141-153
+        if (!(dt >= 0.f)) throw SolverError(NB2_ERR_INVALID_ARGUMENT, "The time-stepping length cannot be negative.");
+        dt_ = dt;
+        inv_dt_ = dt == 0.f ? 0.f : 1.0f / dt;
+    }
+    void set_inv_dt(float inv_dt) {  // :156-166
+        inv_dt_ = inv_dt;
+        dt_ = inv_dt == 0.f ? 0.f : 1.0f / inv_dt;
+    }
+    nb2_params to_abi(const Vector3& gravity) const {
+        nb2_params p;
+        std::memset(&p, 0, sizeof(p));
+        p.dt = dt_;
+        p.erp = erp;
+        p.warmstart_coeff = warmstart_coeff;
+        p.restitution_velocity_threshold = restitution_velocity_threshold;
+        p.allowed_linear_error = allowed_linear_error;
+        p.allowed_angular_error = allowed_angular_error;
+        p.max_linear_correction = max_linear_correction;
+        p.max_angular_correction = max_angular_correction;
+        p.max_stabilization_multiplier = max_stabilization_multiplier;
+        p.max_velocity_iterations = (uint32_t)max_velocity_iterations;
+        p.max_position_iterations = (uint32_t)max_position_iterations;
+        p.max_ccd_position_iterations = (uint32_t)max_ccd_position_iterations;
+        p.max_ccd_substeps = (uint32_t)max_ccd_substeps;
+        for (int k = 0; k < 3; ++k) p.gravity[k] = gravity[k];
+        return p;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+enum class BodyStatus : uint32_t { Disabled = 0, Static = 1, Dynamic = 2, Kinematic = 3 };  // body.rs:50-59
+
+using DefaultBodyHandle = size_t;
+struct BodyPartHandle {
+    DefaultBodyHandle body;
+    size_t part;
+};
+
+class RigidBody {
+    friend class RigidBodyDesc;
+    friend class DefaultBodySet;
+    friend class MoreauJeanSolver;
+    nb2_body rec_;
+
+  public:
+    RigidBody() {
+        std::memset(&rec_, 0, sizeof(rec_));
+        rec_.position[6] = 1.f;
+        rec_.max_linear_velocity = FLT_MAX;
+        rec_.max_angular_velocity = FLT_MAX;
+        for (int k = 0; k < 6; ++k) rec_.jacobian_mask[k] = 1.f;
+        rec_.status = NB2_BODY_DYNAMIC;
+        rec_.flags = NB2_BODY_FLAG_GRAVITY;
+    }
+    Isometry3 position() const {
+        Isometry3 p;
+        for (int k = 0; k < 3; ++k) p.translation[k] = rec_.position[k];
+        for (int k = 0; k < 4; ++k) p.rotation[k] = rec_.position[3 + k];
+        return p;
+    }
+    void set_position(const Isometry3& p) {
+        for (int k = 0; k < 3; ++k) rec_.position[k] = p.translation[k];
+        for (int k = 0; k < 4; ++k) rec_.position[3 + k] = p.rotation[k];
+    }
+    Vector3 linear_velocity() const { return {rec_.velocity[0], rec_.velocity[1], rec_.velocity[2]}; }
+    Vector3 angular_velocity() const { return {rec_.velocity[3], rec_.velocity[4], rec_.velocity[5]}; }
+    void set_linear_velocity(const Vector3& v) { for (int k = 0; k < 3; ++k) rec_.velocity[k] = v[k]; }
+    void set_angular_velocity(const Vector3& v) { for (int k = 0; k < 3; ++k) rec_.velocity[3 + k] = v[k]; }
+    BodyStatus status() const { return (BodyStatus)rec_.status; }
+    void set_status(BodyStatus s) { rec_.status = (uint32_t)s; }
+    bool is_dynamic() const { return rec_.status == NB2_BODY_DYNAMIC; }
+    size_t status_dependent_ndofs() const { return is_dynamic() ? 6 : 0; }  // body.rs:287-293
+    float mass() const { return rec_.mass; }
+    const nb2_body& record() const { return rec_; }
+    nb2_body& record_mut() { return rec_; }
+};
+
+// rigid_body.rs:949-1086
+class RigidBodyDesc {
+    RigidBody rb_;
+
+  public:
+    RigidBodyDesc& translation(const Vector3& t) { for (int k = 0; k < 3; ++k) rb_.rec_.position[k] = t[k]; return *this; }
+    RigidBodyDesc& rotation(const Quaternion& q) { for (int k = 0; k < 4; ++k) rb_.rec_.position[3 + k] = q[k]; return *this; }
+    RigidBodyDesc& velocity(const Vector3& lin, const Vector3& ang) {
+        for (int k = 0; k < 3; ++k) { rb_.rec_.velocity[k] = lin[k]; rb_.rec_.velocity[3 + k] = ang[k]; }
+        return *this;
+    }
+    RigidBodyDesc& mass(float m) { rb_.rec_.mass = m; return *this; }
+    RigidBodyDesc& angular_inertia(const std::array<float, 9>& row_major) {
+        for (int k = 0; k < 9; ++k) rb_.rec_.local_inertia[k] = row_major[k];
+        return *this;
+    }
+    RigidBodyDesc& local_center_of_mass(const Vector3& c) { for (int k = 0; k < 3; ++k) rb_.rec_.local_com[k] = c[k]; return *this; }
+    RigidBodyDesc& linear_damping(float d) { rb_.rec_.linear_damping = d; return *this; }
+    RigidBodyDesc& angular_damping(float d) { rb_.rec_.angular_damping = d; return *this; }
+    RigidBodyDesc& max_linear_velocity(float v) { rb_.rec_.max_linear_velocity = v; return *this; }
+    RigidBodyDesc& max_angular_velocity(float v) { rb_.rec_.max_angular_velocity = v; return *this; }
+    RigidBodyDesc& gravity_enabled(bool on) {
+        rb_.rec_.flags = on ? (rb_.rec_.flags | NB2_BODY_FLAG_GRAVITY) : (rb_.rec_.flags & ~NB2_BODY_FLAG_GRAVITY);
+        return *this;
+    }
+    RigidBodyDesc& status(BodyStatus s) { rb_.rec_.status = (uint32_t)s; return *this; }
+    RigidBodyDesc& kinematic_translations(bool x, bool y, bool z) {
+        rb_.rec_.jacobian_mask[0] = x ? 0.f : 1.f; rb_.rec_.jacobian_mask[1] = y ? 0.f : 1.f; rb_.rec_.jacobian_mask[2] = z ? 0.f : 1.f;
+        return *this;
+    }
+    RigidBodyDesc& kinematic_rotations(bool x, bool y, bool z) {
+        rb_.rec_.jacobian_mask[3] = x ? 0.f : 1.f; rb_.rec_.jacobian_mask[4] = y ? 0.f : 1.f; rb_.rec_.jacobian_mask[5] = z ? 0.f : 1.f;
+        return *this;
+    }
+    /// Mass and angular inertia of a cuboid collider of the given density (volumetric_cuboid.rs:10-77).
+    RigidBodyDesc& cuboid_collider(const Vector3& half_extents, float density) {
+        const float hx = half_extents[0], hy = half_extents[1], hz = half_extents[2];
+        const float m = density * 8.f * hx * hy * hz;
+        rb_.rec_.mass = m;
+        std::memset(rb_.rec_.local_inertia, 0, sizeof(rb_.rec_.local_inertia));
+        rb_.rec_.local_inertia[0] = m * (4.f * hy * hy + 4.f * hz * hz) / 12.f;
+        rb_.rec_.local_inertia[4] = m * (4.f * hx * hx + 4.f * hz * hz) / 12.f;
+        rb_.rec_.local_inertia[8] = m * (4.f * hx * hx + 4.f * hy * hy) / 12.f;
+        return *this;
+    }
+    RigidBody build() const { return rb_; }
+};
+
+// ground.rs: a body with no degree of freedom.
+struct Ground {
+    static RigidBody make() {
+        RigidBody g = RigidBodyDesc().status(BodyStatus::Static).gravity_enabled(false).build();
+        return g;
+    }
+};
+
+// body_set.rs:61-175 (arena -> dense vector; the handle is the index)
+class DefaultBodySet {
+    std::vector<RigidBody> bodies_;
+    bool dirty_ = true;
+    friend class MoreauJeanSolver;
+
+  public:
+    DefaultBodyHandle insert(const RigidBody& b) {
+        bodies_.push_back(b);
+        dirty_ = true;
+        return bodies_.size() - 1;
+    }
+    size_t len() const { return bodies_.size(); }
+    const RigidBody* get(DefaultBodyHandle h) const { return h < bodies_.size() ? &bodies_[h] : nullptr; }
+    RigidBody* get_mut(DefaultBodyHandle h) {
+        if (h >= bodies_.size()) return nullptr;
+        dirty_ = true;  // BodyUpdateStatus dirty bits (body.rs:449-527), coarse
+        return &bodies_[h];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// joints: every *_constraint.rs constructor, producing the flat record
+class JointConstraint {
+  protected:
+    nb2_joint rec_;
+    JointConstraint(uint32_t type, BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Vector3& anchor2) {
+        std::memset(&rec_, 0, sizeof(rec_));
+        rec_.type = type;
+        rec_.body1 = (int32_t)b1.body;
+        rec_.body2 = (int32_t)b2.body;
+        for (int k = 0; k < 3; ++k) { rec_.anchor1[k] = anchor1[k]; rec_.anchor2[k] = anchor2[k]; }
+        rec_.axis1[0] = rec_.axis2[0] = rec_.axis3[0] = 1.f;
+        rec_.ref_frame1[3] = rec_.ref_frame2[3] = 1.f;
+        rec_.break_force_squared = FLT_MAX;
+        rec_.break_torque_squared = FLT_MAX;
+    }
+    static void set3(float* d, const Vector3& v) { for (int k = 0; k < 3; ++k) d[k] = v[k]; }
+
+  public:
+    void set_break_force(float f) { rec_.break_force_squared = f * f; }
+    void set_break_torque(float t) { rec_.break_torque_squared = t * t; }
+    bool is_broken() const { return rec_.broken != 0; }
+    const nb2_joint& record() const { return rec_; }
+    nb2_joint& record_mut() { return rec_; }
+};
+struct BallConstraint : JointConstraint {  // ball_constraint.rs:27-45
+    BallConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Vector3& anchor2)
+        : JointConstraint(NB2_JOINT_BALL, b1, b2, anchor1, anchor2) {}
+};
+struct RevoluteConstraint : JointConstraint {  // revolute_constraint.rs:54-83
+    RevoluteConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Vector3& axis1,
+                       const Vector3& anchor2, const Vector3& axis2)
+        : JointConstraint(NB2_JOINT_REVOLUTE, b1, b2, anchor1, anchor2) { set3(rec_.axis1, axis1); set3(rec_.axis2, axis2); }
+};
+struct PrismaticConstraint : JointConstraint {  // prismatic_constraint.rs:40-75
+    PrismaticConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Vector3& axis1, const Vector3& anchor2)
+        : JointConstraint(NB2_JOINT_PRISMATIC, b1, b2, anchor1, anchor2) { set3(rec_.axis1, axis1); }
+    void enable_min_offset(float v) { rec_.flags |= NB2_JOINT_FLAG_MIN_OFFSET; rec_.min_offset = v; }
+    void enable_max_offset(float v) { rec_.flags |= NB2_JOINT_FLAG_MAX_OFFSET; rec_.max_offset = v; }
+    void disable_min_offset() { rec_.flags &= ~NB2_JOINT_FLAG_MIN_OFFSET; }
+    void disable_max_offset() { rec_.flags &= ~NB2_JOINT_FLAG_MAX_OFFSET; }
+};
+struct UniversalConstraint : JointConstraint {  // universal_constraint.rs:30-60
+    UniversalConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Vector3& axis1,
+                        const Vector3& anchor2, const Vector3& axis2, float angle)
+        : JointConstraint(NB2_JOINT_UNIVERSAL, b1, b2, anchor1, anchor2) { set3(rec_.axis1, axis1); set3(rec_.axis2, axis2); rec_.angle = angle; }
+};
+struct PlanarConstraint : JointConstraint {  // planar_constraint.rs:30-58
+    PlanarConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Vector3& axis1,
+                     const Vector3& anchor2, const Vector3& axis2)
+        : JointConstraint(NB2_JOINT_PLANAR, b1, b2, anchor1, anchor2) { set3(rec_.axis1, axis1); set3(rec_.axis2, axis2); }
+};
+struct RectangularConstraint : JointConstraint {  // rectangular_constraint.rs:28-55
+    RectangularConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Vector3& axis1, const Vector3& anchor2)
+        : JointConstraint(NB2_JOINT_RECTANGULAR, b1, b2, anchor1, anchor2) { set3(rec_.axis1, axis1); }
+};
+struct PinSlotConstraint : JointConstraint {  // pin_slot_constraint.rs:35-75
+    PinSlotConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Vector3& axis_v1,
+                      const Vector3& axis_w1, const Vector3& anchor2, const Vector3& axis_w2)
+        : JointConstraint(NB2_JOINT_PIN_SLOT, b1, b2, anchor1, anchor2) { set3(rec_.axis1, axis_v1); set3(rec_.axis3, axis_w1); set3(rec_.axis2, axis_w2); }
+};
+struct CylindricalConstraint : JointConstraint {  // cylindrical_constraint.rs:33-65
+    CylindricalConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Vector3& axis1,
+                          const Vector3& anchor2, const Vector3& axis2)
+        : JointConstraint(NB2_JOINT_CYLINDRICAL, b1, b2, anchor1, anchor2) { set3(rec_.axis1, axis1); set3(rec_.axis2, axis2); }
+};
+struct FixedConstraint : JointConstraint {  // fixed_constraint.rs:30-60
+    FixedConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Quaternion& ref_frame1,
+                    const Vector3& anchor2, const Quaternion& ref_frame2)
+        : JointConstraint(NB2_JOINT_FIXED, b1, b2, anchor1, anchor2) {
+        for (int k = 0; k < 4; ++k) { rec_.ref_frame1[k] = ref_frame1[k]; rec_.ref_frame2[k] = ref_frame2[k]; }
+    }
+};
+struct CartesianConstraint : JointConstraint {  // cartesian_constraint.rs:28-55
+    CartesianConstraint(BodyPartHandle b1, BodyPartHandle b2, const Vector3& anchor1, const Quaternion& ref_frame1,
+                        const Vector3& anchor2, const Quaternion& ref_frame2)
+        : JointConstraint(NB2_JOINT_CARTESIAN, b1, b2, anchor1, anchor2) {
+        for (int k = 0; k < 4; ++k) { rec_.ref_frame1[k] = ref_frame1[k]; rec_.ref_frame2[k] = ref_frame2[k]; }
+    }
+};
+
+using DefaultJointConstraintHandle = size_t;
+class DefaultJointConstraintSet {  // joint_constraint.rs:58-206
+    std::vector<JointConstraint> joints_;
+    bool dirty_ = true;
+    friend class MoreauJeanSolver;
+
+  public:
+    DefaultJointConstraintHandle insert(const JointConstraint& j) {
+        joints_.push_back(j);
+        dirty_ = true;
+        return joints_.size() - 1;
+    }
+    size_t len() const { return joints_.size(); }
+    const JointConstraint* get(DefaultJointConstraintHandle h) const { return h < joints_.size() ? &joints_[h] : nullptr; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// The contact input (collider_contact_manifold.rs:9-24): one manifold and its tracked contacts.
+struct ColliderContactManifold {
+    nb2_manifold manifold;
+    std::vector<nb2_contact> contacts;
+};
+
+// contact_model.rs:13-37.  Only the pyramid model exists on device.
+struct ContactModel {
+    virtual ~ContactModel() {}
+    virtual const char* name() const = 0;
+};
+struct SignoriniCoulombPyramidModel : ContactModel {
+    const char* name() const override { return "SignoriniCoulombPyramidModel"; }
+};
+
+// counters/mod.rs (solver stages, milliseconds)
+struct Counters {
+    bool enabled = false;
+    float assembly_time = 0.f, velocity_resolution_time = 0.f, velocity_update_time = 0.f, position_resolution_time = 0.f,
+          solver_time = 0.f;
+    size_t nconstraints = 0;
+    void enable() { enabled = true; }
+};
+
+enum class SolverMode { ReferenceOrder = NB2_MODE_REFERENCE_ORDER, Coloured = NB2_MODE_COLOURED };
+
+// ---------------------------------------------------------------------------------------------
+// moreau_jean_solver.rs:14-90
+class MoreauJeanSolver {
+    nb2_context* ctx_ = nullptr;
+    std::unique_ptr<ContactModel> contact_model_;
+    std::vector<nb2_body> body_stage_;
+    std::vector<nb2_body_state> state_stage_;
+    std::vector<nb2_manifold> manifold_stage_;
+    std::vector<nb2_contact> contact_stage_;
+    std::vector<nb2_joint> joint_stage_;
+
+    void check(int rc) const {
+        if (rc != NB2_OK) throw SolverError(rc, nb2_last_error(ctx_) ? nb2_last_error(ctx_) : nb2_error_string(rc));
+    }
+
+  public:
+    SolverMode mode = SolverMode::Coloured;
+    Vector3 gravity{0.f, -9.81f, 0.f};
+
+    explicit MoreauJeanSolver(std::unique_ptr<ContactModel> contact_model, int device = 0) : contact_model_(std::move(contact_model)) {
+        int rc = nb2_create(device, nullptr, &ctx_);
+        if (rc != NB2_OK) throw SolverError(rc, nb2_last_error(nullptr));
+    }
+    ~MoreauJeanSolver() { if (ctx_) nb2_destroy(ctx_); }
+    MoreauJeanSolver(const MoreauJeanSolver&) = delete;
+    MoreauJeanSolver& operator=(const MoreauJeanSolver&) = delete;
+
+    /// moreau_jean_solver.rs:42-44.  A new model forgets the cached impulses.
+    void set_contact_model(std::unique_ptr<ContactModel> model) {
+        if (std::string(model->name()) != "SignoriniCoulombPyramidModel")
+            throw SolverError(NB2_ERR_UNSUPPORTED, "only SignoriniCoulombPyramidModel is implemented on device");
+        contact_model_ = std::move(model);
+        check(nb2_clear_impulse_cache(ctx_));
+    }
+
+    /// MoreauJeanSolver::step (moreau_jean_solver.rs:47-61).  `island` / `island_joints` are implied: every
+    /// dynamic body and every unbroken joint with a dynamic side (mechanical_world.rs:264-279).
+    void step(Counters& counters, DefaultBodySet& bodies, DefaultJointConstraintSet& joints,
+              const std::vector<ColliderContactManifold>& manifolds, const IntegrationParameters& parameters) {
+        nb2_params p = parameters.to_abi(gravity);
+        check(nb2_set_params(ctx_, &p));
+        check(nb2_enable_timers(ctx_, counters.enabled ? 1 : 0));
+        if (bodies.dirty_) {
+            body_stage_.resize(bodies.bodies_.size());
+            for (size_t i = 0; i < body_stage_.size(); ++i) body_stage_[i] = bodies.bodies_[i].rec_;
+            check(nb2_upload_bodies(ctx_, body_stage_.data(), (uint32_t)body_stage_.size()));
+            bodies.dirty_ = false;
+            joints.dirty_ = true;  // a new body set drops the joints on device
+        }
+        if (joints.dirty_) {
+            joint_stage_.resize(joints.joints_.size());
+            for (size_t i = 0; i < joint_stage_.size(); ++i) joint_stage_[i] = joints.joints_[i].record();
+            check(nb2_upload_joints(ctx_, joint_stage_.data(), (uint32_t)joint_stage_.size()));
+            joints.dirty_ = false;
+        }
+        manifold_stage_.clear();
+        contact_stage_.clear();
+        for (const ColliderContactManifold& m : manifolds) {
+            nb2_manifold rec = m.manifold;
+            rec.first_contact = (uint32_t)contact_stage_.size();
+            rec.num_contacts = (uint32_t)m.contacts.size();
+            manifold_stage_.push_back(rec);
+            contact_stage_.insert(contact_stage_.end(), m.contacts.begin(), m.contacts.end());
+        }
+        check(nb2_upload_manifolds(ctx_, manifold_stage_.data(), (uint32_t)manifold_stage_.size(), contact_stage_.data(),
+                                   (uint32_t)contact_stage_.size()));
+        check(nb2_step(ctx_, (int)mode));
+        // outputs are written in place into the bodies / joints, like the reference
+        state_stage_.resize(bodies.bodies_.size());
+        check(nb2_download_body_states(ctx_, state_stage_.data(), 0, (uint32_t)state_stage_.size()));
+        for (size_t i = 0; i < state_stage_.size(); ++i) {
+            std::memcpy(bodies.bodies_[i].rec_.position, state_stage_[i].position, sizeof(float) * 7);
+            std::memcpy(bodies.bodies_[i].rec_.velocity, state_stage_[i].velocity, sizeof(float) * 6);
+        }
+        if (!joint_stage_.empty()) {
+            check(nb2_download_joints(ctx_, joint_stage_.data(), (uint32_t)joint_stage_.size()));
+            for (size_t i = 0; i < joint_stage_.size(); ++i) joints.joints_[i].record_mut() = joint_stage_[i];
+        }
+        check(nb2_synchronize(ctx_));
+        if (counters.enabled) {
+            float t[8];
+            check(nb2_get_timers(ctx_, t));
+            counters.assembly_time = t[0];
+            counters.velocity_resolution_time = t[1];
+            counters.velocity_update_time = t[2];
+            counters.position_resolution_time = t[3];
+            counters.solver_time = t[4];
+        }
+        counters.nconstraints = 3 * contact_stage_.size();  // set_nconstraints (:74-76), contact rows
+    }
+    nb2_stats stats() {
+        nb2_stats s;
+        check(nb2_get_stats(ctx_, &s));
+        return s;
+    }
+};
+
+// mechanical_world.rs:55-68, 182-396 -- the solver part of the step; collision detection (the
+// manifold producer) stays with the caller.
+class MechanicalWorld {
+  public:
+    Counters counters;
+    MoreauJeanSolver solver;
+    IntegrationParameters integration_parameters;
+    Vector3 gravity;
+
+    explicit MechanicalWorld(const Vector3& g, int device = 0)
+        : solver(std::unique_ptr<ContactModel>(new SignoriniCoulombPyramidModel()), device), gravity(g) {}
+    void set_timestep(float dt) { integration_parameters.set_dt(dt); }
+    float timestep() const { return integration_parameters.dt(); }
+    void step(DefaultBodySet& bodies, DefaultJointConstraintSet& joints, const std::vector<ColliderContactManifold>& manifolds) {
+        solver.gravity = gravity;
+        solver.step(counters, bodies, joints, manifolds, integration_parameters);
+    }
+};
+
+}  // namespace nphysics

@@ -246,9 +246,9 @@ def test_coloured_mode_quality_matches_oracle(scene_name):
     assert res_g <= 3.0 * res_o + 1e-6, (res_g, res_o)
     assert pen_g <= 2.0 * pen_o + 0.001, (pen_g, pen_o)
     assert ke_g <= 8.0 * ke_o + 1e-4, (ke_g, ke_o)
-    # the pile must not have collapsed or exploded: same top height within 1 cm
+    # the pile must not have collapsed or exploded: same top height within 0.5 % + 5 mm
     pg, po = sg.download_body_states()["position"], so.download_body_states()["position"]
-    assert abs(float(pg[:, 1].max()) - float(po[:, 1].max())) < 0.01
+    assert abs(float(pg[:, 1].max()) - float(po[:, 1].max())) < 0.005 * float(po[:, 1].max()) + 0.005
     # invariants of the row updates hold in any order
     imp = sg.download_contact_impulses()
     assert np.all(imp[:, 0] >= 0.0)
