@@ -269,6 +269,11 @@ int nb2_get_params(const nb2_context* ctx, nb2_params* out);
  * nb2_get_stats). */
 int nb2_enable_timers(nb2_context* ctx, int enabled);
 
+/* The coloured schedule is cached across steps while the conflict graph (body pair, row count and
+ * type of every constraint group) is unchanged; the check runs on device every step.  enabled = 0
+ * forces a fresh colouring each step (default: enabled). */
+int nb2_set_schedule_cache(nb2_context* ctx, int enabled);
+
 /* Replace the whole body set (n >= 1).  Marks dynamics dirty, like
  * update_status = all() on a fresh body (rigid_body.rs:80). */
 int nb2_upload_bodies(nb2_context* ctx, const nb2_body* bodies, uint32_t n);

@@ -287,6 +287,12 @@ int nb2_enable_timers(nb2_context* h, int enabled) {
     return NB2_OK;
 }
 
+int nb2_set_schedule_cache(nb2_context* h, int enabled) {
+    NB2_CHECK_CTX(h);
+    h->c.schedule_cache = enabled != 0;
+    return NB2_OK;
+}
+
 int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
     NB2_CHECK_CTX(h);
     Context* ctx = &h->c;

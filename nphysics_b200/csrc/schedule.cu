@@ -214,13 +214,15 @@ __global__ void k_build_items(int mode, int position, unsigned int nJ, unsigned 
                               const unsigned int* __restrict__ chunk_base, unsigned int nM,
                               const unsigned int* __restrict__ chunk_manifold, const int* __restrict__ status,
                               int* it_a, int* it_b, int* it_nrows, int* it_type, int* it_src,
-                              unsigned long long* it_key, size_t n_items) {
+                              unsigned long long* it_key, int* it_b1, int* it_b2, size_t n_items) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
-    int a = -1, b = -1, nrows = 0, type = NB2_ITEM_INVALID, src = 0;
+    int a = -1, b = -1, nrows = 0, type = NB2_ITEM_INVALID, src = 0, b1 = 0, b2 = 0;
     unsigned long long key = 0;
     if (i < nJ) {
         const nb2_joint& j = joints[i];
+        b1 = j.body1;
+        b2 = j.body2;
         a = dyn_or_neg(status, j.body1);
         b = dyn_or_neg(status, j.body2);
         // active_joints filter of mechanical_world.rs:274-279 (+ is_active, joint_constraint.rs:219-228)
@@ -242,6 +244,8 @@ __global__ void k_build_items(int mode, int position, unsigned int nJ, unsigned 
         if (k < total) {
             unsigned int m = chunk_manifold[k];
             const nb2_manifold& mf = manifolds[m];
+            b1 = mf.body1;
+            b2 = mf.body2;
             a = dyn_or_neg(status, mf.body1);
             b = dyn_or_neg(status, mf.body2);
             if (a >= 0 || b >= 0) {
@@ -274,6 +278,8 @@ __global__ void k_build_items(int mode, int position, unsigned int nJ, unsigned 
     it_type[i] = type;
     it_src[i] = src;
     it_key[i] = key;
+    it_b1[i] = b1;
+    it_b2[i] = b2;
 }
 
 static int reserve_sched(Context* ctx, Sched* s, size_t n_items, size_t max_phases) {
@@ -284,6 +290,8 @@ static int reserve_sched(Context* ctx, Sched* s, size_t n_items, size_t max_phas
     NB2_TRY(s->it_nrows.reserve(ctx, n_items));
     NB2_TRY(s->it_type.reserve(ctx, n_items));
     NB2_TRY(s->it_src.reserve(ctx, n_items));
+    NB2_TRY(s->it_b1.reserve(ctx, n_items));
+    NB2_TRY(s->it_b2.reserve(ctx, n_items));
     NB2_TRY(s->it_key.reserve(ctx, n_items));
     NB2_TRY(s->it_phase.reserve(ctx, n_items));
     NB2_TRY(s->it_slot.reserve(ctx, n_items));
@@ -324,7 +332,7 @@ int launch_build_items(Context* ctx, int mode) {
         k_build_items<<<nblk(n_items), TPB, 0, ctx->stream>>>(
             mode, 0, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
             ctx->chunk_manifold.p, ctx->b_status.p, ctx->vs.it_a.p, ctx->vs.it_b.p, ctx->vs.it_nrows.p,
-            ctx->vs.it_type.p, ctx->vs.it_src.p, ctx->vs.it_key.p, n_items);
+            ctx->vs.it_type.p, ctx->vs.it_src.p, ctx->vs.it_key.p, ctx->vs.it_b1.p, ctx->vs.it_b2.p, n_items);
         ctx->launches++;
     }
     if (ref) {
@@ -334,7 +342,7 @@ int launch_build_items(Context* ctx, int mode) {
             k_build_items<<<nblk(np), TPB, 0, ctx->stream>>>(
                 mode, 1, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
                 ctx->chunk_manifold.p, ctx->b_status.p, ctx->ps.it_a.p, ctx->ps.it_b.p, ctx->ps.it_nrows.p,
-                ctx->ps.it_type.p, ctx->ps.it_src.p, ctx->ps.it_key.p, np);
+                ctx->ps.it_type.p, ctx->ps.it_src.p, ctx->ps.it_key.p, ctx->ps.it_b1.p, ctx->ps.it_b2.p, np);
             ctx->launches++;
         }
     }
@@ -429,10 +437,41 @@ __device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
     x ^= x >> 16;
     return x;
 }
+// Conditional helpers of the schedule cache: no-ops while the conflict graph is unchanged.
+__global__ void k_cond_zero(const unsigned int* __restrict__ changed, unsigned int* p, size_t nwords) {
+    if (*changed == 0u) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) p[i] = 0u;
+}
+__global__ void k_cond_fill_int(const unsigned int* __restrict__ changed, int* p, size_t n, int v) {
+    if (*changed == 0u) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// Compares this step's groups with the previous step's (when comparable) and records them.
+__global__ void k_compare_snapshot(size_t n, const int* __restrict__ it_a, const int* __restrict__ it_b,
+                                   const int* __restrict__ it_nrows, const int* __restrict__ it_type,
+                                   const int* __restrict__ it_b1, const int* __restrict__ it_b2, int* prev_a,
+                                   int* prev_b, int* prev_nt, int* prev_b1, int* prev_b2, unsigned int* changed,
+                                   int compare) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = it_a[i], b = it_b[i], nt = (it_nrows[i] & 0xFF) | (it_type[i] << 8), b1 = it_b1[i], b2 = it_b2[i];
+    if (compare && (prev_a[i] != a || prev_b[i] != b || prev_nt[i] != nt || prev_b1[i] != b1 || prev_b2[i] != b2))
+        *changed = 1u;
+    prev_a[i] = a;
+    prev_b[i] = b;
+    prev_nt[i] = nt;
+    prev_b1[i] = b1;
+    prev_b2[i] = b2;
+}
+
 __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict__ it_a, const int* __restrict__ it_b,
                                                 const int* __restrict__ it_type, int* phase,
                                                 unsigned long long* cmask, unsigned long long* best,
-                                                unsigned int* flags /*3*/, SchedHeader* hdr, unsigned int* barrier) {
+                                                unsigned int* flags /*3*/, SchedHeader* hdr, unsigned int* barrier,
+                                                const unsigned int* __restrict__ changed) {
+    if (*changed == 0u) return;  // cached colouring still valid (uniform over the grid: no barrier was touched)
     GridBarrier gb;
     gb.init(barrier);
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -490,9 +529,10 @@ __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict_
 }
 
 // ------------------------------------------------------------------ layout
-__global__ void k_phase_hist(size_t n, const int* __restrict__ it_type, const int* __restrict__ it_nrows,
-                             const int* __restrict__ phase, int* slot, unsigned int* ph_count, unsigned int* ph_R,
-                             SchedHeader* hdr, unsigned int max_phases) {
+__global__ void k_phase_hist(const unsigned int* __restrict__ changed, size_t n, const int* __restrict__ it_type,
+                             const int* __restrict__ it_nrows, const int* __restrict__ phase, int* slot,
+                             unsigned int* ph_count, unsigned int* ph_R, SchedHeader* hdr, unsigned int max_phases) {
+    if (*changed == 0u) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || it_type[i] == NB2_ITEM_INVALID) return;
     unsigned int p = (unsigned int)phase[i];
@@ -504,8 +544,9 @@ __global__ void k_phase_hist(size_t n, const int* __restrict__ it_type, const in
     atomicMax(&ph_R[p], (unsigned int)it_nrows[i]);
     atomicMax(&hdr->n_phases, p + 1);
 }
-__global__ void k_phase_scan(unsigned int* ph_count, unsigned int* ph_R, unsigned int* ph_gbase,
-                             unsigned int* ph_rbase, SchedHeader* hdr) {
+__global__ void k_phase_scan(const unsigned int* __restrict__ changed, unsigned int* ph_count, unsigned int* ph_R,
+                             unsigned int* ph_gbase, unsigned int* ph_rbase, SchedHeader* hdr) {
+    if (*changed == 0u) return;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned int g = 0, r = 0;
     unsigned int np = hdr->n_phases;
@@ -520,10 +561,12 @@ __global__ void k_phase_scan(unsigned int* ph_count, unsigned int* ph_R, unsigne
     hdr->n_groups = g;
     hdr->n_slots = r;
 }
-__global__ void k_fill_ginfo(size_t n, const int* __restrict__ it_type, const int* __restrict__ it_a,
-                             const int* __restrict__ it_b, const int* __restrict__ it_nrows,
-                             const int* __restrict__ phase, const int* __restrict__ slot,
-                             const unsigned int* __restrict__ ph_gbase, int4* g_info, unsigned int max_phases) {
+__global__ void k_fill_ginfo(const unsigned int* __restrict__ changed, size_t n, const int* __restrict__ it_type,
+                             const int* __restrict__ it_a, const int* __restrict__ it_b,
+                             const int* __restrict__ it_nrows, const int* __restrict__ phase,
+                             const int* __restrict__ slot, const unsigned int* __restrict__ ph_gbase, int4* g_info,
+                             unsigned int max_phases) {
+    if (*changed == 0u) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || it_type[i] == NB2_ITEM_INVALID) return;
     unsigned int p = min((unsigned int)phase[i], max_phases - 1);
@@ -550,11 +593,38 @@ static int coop_blocks(Context* ctx, K kernel, int* cache) {
 int launch_schedule(Context* ctx, Sched* s, int mode) {
     const size_t n = s->n_items;
     const unsigned int nb = ctx->n_bodies;
-    NB2_CUDA(ctx, cudaMemsetAsync(s->hdr.p, 0, sizeof(SchedHeader), ctx->stream));
-    NB2_CUDA(ctx, cudaMemsetAsync(s->ph_count.p, 0, (s->max_phases + 1) * sizeof(unsigned int), ctx->stream));
-    NB2_CUDA(ctx, cudaMemsetAsync(s->ph_R.p, 0, (s->max_phases + 1) * sizeof(unsigned int), ctx->stream));
+    // Schedule cache (coloured mode): the colouring stays valid while the conflict graph -- the
+    // (body pair, row count, type) of every group -- is unchanged.  A device flag is set by comparing
+    // this step's groups with the previous step's; every schedule kernel returns at once when it is
+    // clear, keeping the previous phases, layout and g_info.  No host read-back is involved.
+    NB2_TRY(ctx->flags.reserve(ctx, 4));
+    unsigned int* changed = ctx->flags.p + 1;
+    const bool comparable = mode == NB2_MODE_COLOURED && ctx->schedule_cache && s->cache_valid && s->cache_n == n &&
+                            n > 0 && s->cache_bodies == nb;
+    NB2_CUDA(ctx, cudaMemsetAsync(changed, comparable ? 0 : 0xFF, sizeof(unsigned int), ctx->stream));
+    if (mode == NB2_MODE_COLOURED && n > 0) {
+        NB2_TRY(s->prev_a.reserve(ctx, n));
+        NB2_TRY(s->prev_b.reserve(ctx, n));
+        NB2_TRY(s->prev_nt.reserve(ctx, n));
+        NB2_TRY(s->prev_b1.reserve(ctx, n));
+        NB2_TRY(s->prev_b2.reserve(ctx, n));
+        k_compare_snapshot<<<nblk(n), TPB, 0, ctx->stream>>>(n, s->it_a.p, s->it_b.p, s->it_nrows.p, s->it_type.p,
+                                                              s->it_b1.p, s->it_b2.p, s->prev_a.p, s->prev_b.p,
+                                                              s->prev_nt.p, s->prev_b1.p, s->prev_b2.p, changed,
+                                                              comparable ? 1 : 0);
+        ctx->launches++;
+        s->cache_valid = true;
+        s->cache_n = n;
+        s->cache_bodies = nb;
+    } else {
+        s->cache_valid = false;
+    }
+    k_cond_zero<<<1, 32, 0, ctx->stream>>>(changed, (unsigned int*)s->hdr.p, sizeof(SchedHeader) / 4);
+    k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_count.p, s->max_phases + 1);
+    k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_R.p, s->max_phases + 1);
+    ctx->launches += 3;
     if (n == 0) {
-        k_phase_scan<<<1, 1, 0, ctx->stream>>>(s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
+        k_phase_scan<<<1, 1, 0, ctx->stream>>>(changed, s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
         ctx->launches++;
         NB2_CUDA(ctx, cudaGetLastError());
         return NB2_OK;
@@ -601,11 +671,11 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     } else {
         NB2_TRY(ctx->cmask.reserve(ctx, (size_t)nb * NB2_MASK_WORDS + 1));
         NB2_TRY(ctx->best.reserve(ctx, (size_t)nb + 1));
-        NB2_CUDA(ctx, cudaMemsetAsync(ctx->cmask.p, 0, (size_t)nb * NB2_MASK_WORDS * sizeof(unsigned long long),
-                                      ctx->stream));
-        NB2_CUDA(ctx, cudaMemsetAsync(ctx->best.p, 0, (size_t)nb * sizeof(unsigned long long), ctx->stream));
-        k_fill_int<<<nblk(n), TPB, 0, ctx->stream>>>(s->it_phase.p, n, -1);
-        ctx->launches++;
+        k_cond_zero<<<nblk((size_t)nb * NB2_MASK_WORDS * 2), TPB, 0, ctx->stream>>>(
+            changed, (unsigned int*)ctx->cmask.p, (size_t)nb * NB2_MASK_WORDS * 2);
+        k_cond_zero<<<nblk((size_t)nb * 2), TPB, 0, ctx->stream>>>(changed, (unsigned int*)ctx->best.p, (size_t)nb * 2);
+        k_cond_fill_int<<<nblk(n), TPB, 0, ctx->stream>>>(changed, s->it_phase.p, n, -1);
+        ctx->launches += 3;
         NB2_TRY(coop_blocks(ctx, k_colour, &blocks_colour));
         int blocks = (int)min((size_t)blocks_colour, (n + TPB - 1) / TPB);
         size_t n_ = n;
@@ -617,14 +687,15 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
         unsigned long long* be = ctx->best.p;
         SchedHeader* hd = s->hdr.p;
         unsigned int* bar = ctx->barrier.p;
-        void* args[] = {&n_, &ia, &ib, &ty, &ph, &cm, &be, &flags, &hd, &bar};
+        const unsigned int* ch = changed;
+        void* args[] = {&n_, &ia, &ib, &ty, &ph, &cm, &be, &flags, &hd, &bar, &ch};
         NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_colour, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
         ctx->launches++;
     }
-    k_phase_hist<<<nblk(n), TPB, 0, ctx->stream>>>(n, s->it_type.p, s->it_nrows.p, s->it_phase.p, s->it_slot.p,
+    k_phase_hist<<<nblk(n), TPB, 0, ctx->stream>>>(changed, n, s->it_type.p, s->it_nrows.p, s->it_phase.p, s->it_slot.p,
                                                    s->ph_count.p, s->ph_R.p, s->hdr.p, (unsigned int)s->max_phases);
-    k_phase_scan<<<1, 1, 0, ctx->stream>>>(s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
-    k_fill_ginfo<<<nblk(n), TPB, 0, ctx->stream>>>(n, s->it_type.p, s->it_a.p, s->it_b.p, s->it_nrows.p,
+    k_phase_scan<<<1, 1, 0, ctx->stream>>>(changed, s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
+    k_fill_ginfo<<<nblk(n), TPB, 0, ctx->stream>>>(changed, n, s->it_type.p, s->it_a.p, s->it_b.p, s->it_nrows.p,
                                                    s->it_phase.p, s->it_slot.p, s->ph_gbase.p, s->g_info.p,
                                                    (unsigned int)s->max_phases);
     ctx->launches += 3;

@@ -109,12 +109,20 @@ struct Sched {
     DevBuf<unsigned long long> it_key;  // sequential position (reference order)
     DevBuf<int> it_phase, it_slot;   // outputs: phase, index inside the phase
     DevBuf<unsigned int> ph_count, ph_R, ph_gbase, ph_rbase;
-    DevBuf<int4> g_info;             // per group slot: (a, b, nrows, item)
+    DevBuf<int4> g_info;             // per group slot: (a, b, nrows | type << 8, item)
     DevBuf<SchedHeader> hdr;         // 1 element
+    // schedule cache: last step's groups, compared on device (coloured mode)
+    DevBuf<int> prev_a, prev_b, prev_nt, prev_b1, prev_b2;
+    DevBuf<int> it_b1, it_b2;        // body indices of both sides, whatever their status
+    bool cache_valid = false;
+    size_t cache_n = 0;
+    unsigned int cache_bodies = 0;
     void release() {
         it_a.release(); it_b.release(); it_nrows.release(); it_type.release(); it_src.release();
         it_key.release(); it_phase.release(); it_slot.release(); ph_count.release(); ph_R.release();
         ph_gbase.release(); ph_rbase.release(); g_info.release(); hdr.release();
+        prev_a.release(); prev_b.release(); prev_nt.release(); prev_b1.release(); prev_b2.release();
+        it_b1.release(); it_b2.release();
     }
 };
 
@@ -140,6 +148,7 @@ struct Context {
     float inv_dt = 0.f;
     bool have_params = false;
     bool timers = false;
+    bool schedule_cache = true;
     StageEvents ev;
     bool ev_valid = false;
 

@@ -39,5 +39,5 @@ def test_pyramid3_example_runs(mode):
     r = subprocess.run([exe, "40", mode], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "manifolds 1335 contacts 5340 rows 16020" in r.stdout
+    assert "initial manifolds 1335 contacts 5340 rows 16020" in r.stdout
     assert r.stdout.strip().endswith("OK")
