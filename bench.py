@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--contact-layout", type=int, default=0, help="0 = 132-byte row stream, 1 = compact 80-byte records")
+    ap.add_argument("--no-schedule-cache", action="store_true")
     return ap.parse_args()
 
 
@@ -189,6 +191,8 @@ def run_b200(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         solver = Solver(device=local_rank, stream=stream.cuda_stream)
         solver.set_params(sc.params)
+        solver.set_contact_layout(args.contact_layout)
+        solver.set_schedule_cache(not args.no_schedule_cache)
         solver.upload_bodies(sc.bodies)
         solver.upload_manifolds(m, c)
         for _ in range(max(args.warmup, 3)):
@@ -283,8 +287,9 @@ def run_b200(args, rank, world, local_rank):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "boxes3 scaled to 100k boxes (%s settled pile%s), %d velocity + %d position "
-                                   "iterations, mode=%s" % (args.grid, ", one independent world per GPU" if world > 1
-                                                            else "", args.vel_iters, args.pos_iters, args.mode),
+                                   "iterations, mode=%s, contact_layout=%d, schedule_cache=%s" %
+                                   (args.grid, ", one independent world per GPU" if world > 1 else "", args.vel_iters,
+                                    args.pos_iters, args.mode, args.contact_layout, not args.no_schedule_cache),
                        "bodies": nb, "manifolds": int(len(m)), "contacts": int(len(c)), "rows_two_body": n_r2,
                        "rows_ground": n_rg,
                        "l2": "row stream %.0f MB per sweep > 126 MB L2 (inputs larger than L2, no flush needed)" %

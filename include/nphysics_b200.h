@@ -274,6 +274,11 @@ int nb2_enable_timers(nb2_context* ctx, int enabled);
  * forces a fresh colouring each step (default: enabled). */
 int nb2_set_schedule_cache(nb2_context* ctx, int enabled);
 
+/* Device representation of contact groups in coloured mode: 0 (default) = the reference's 132-byte
+ * rows [J1|J2|M^-1 J1|M^-1 J2] streamed from HBM; 1 = compact 80-byte contact records from which
+ * the same rows are rebuilt in registers (bit-identical rows, a fifth of the bytes, more ALU). */
+int nb2_set_contact_layout(nb2_context* ctx, int layout);
+
 /* Replace the whole body set (n >= 1).  Marks dynamics dirty, like
  * update_status = all() on a fresh body (rigid_body.rs:80). */
 int nb2_upload_bodies(nb2_context* ctx, const nb2_body* bodies, uint32_t n);

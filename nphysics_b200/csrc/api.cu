@@ -44,6 +44,7 @@ static void release_all(Context* c) {
     c->adj_p.release(); c->cmask.release(); c->best.release(); c->scan_tmp.release(); c->barrier.release();
     c->r_jac.release(); c->r_hdr.release(); c->r_meta.release(); c->r_imp.release(); c->p_row.release();
     c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
+    c->c_geo.release();
 }
 
 static int check_flags(Context* ctx) {
@@ -73,6 +74,7 @@ static int check_flags(Context* ctx) {
 static int do_step(Context* ctx, int mode) {
     const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
     ctx->cur = 1 - ctx->cur;
+    ctx->step_layout = (!ref && ctx->contact_layout == 1) ? 1 : 0;
     const bool tm = ctx->timers;
     if (tm && !ctx->ev.created) {
         for (int k = 0; k < 12; ++k) NB2_CUDA(ctx, cudaEventCreate(&ctx->ev.e[k]));
@@ -293,6 +295,13 @@ int nb2_set_schedule_cache(nb2_context* h, int enabled) {
     return NB2_OK;
 }
 
+int nb2_set_contact_layout(nb2_context* h, int layout) {
+    NB2_CHECK_CTX(h);
+    if (layout != 0 && layout != 1) return set_error(&h->c, NB2_ERR_INVALID_ARGUMENT, "unknown contact layout %d", layout);
+    h->c.contact_layout = layout;
+    return NB2_OK;
+}
+
 int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
     NB2_CHECK_CTX(h);
     Context* ctx = &h->c;
@@ -310,8 +319,13 @@ int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
     NB2_TRY(ctx->b_status.reserve(ctx, n));
     ctx->n_bodies = n;
     uint32_t nd = 0;
-    for (uint32_t i = 0; i < n; ++i) nd += bodies[i].status == NB2_BODY_DYNAMIC ? 1u : 0u;
+    bool any_mask = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        nd += bodies[i].status == NB2_BODY_DYNAMIC ? 1u : 0u;
+        for (int k = 0; k < 6; ++k) any_mask |= bodies[i].jacobian_mask[k] != 1.0f;
+    }
     ctx->n_dynamic = nd;
+    ctx->any_mask = any_mask;
     NB2_CUDA(ctx, cudaMemcpyAsync(ctx->raw.p, bodies, (size_t)n * sizeof(nb2_body), cudaMemcpyHostToDevice, ctx->stream));
     NB2_TRY(launch_unpack_bodies(ctx));
     // joints / manifolds referring to the old set are dropped

@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     int mode, unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
     const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
     const unsigned int* __restrict__ chunk_base, const unsigned int* __restrict__ chunk_manifold, BodyArrays B,
-    SchedView vs, SchedView ps, RowOut out, float4* p_row, size_t n_pslots_max,
+    SchedView vs, SchedView ps, RowOut out, float4* p_row, size_t n_pslots_max, float4* c_geo,
     const unsigned long long* __restrict__ ht_keys,
     const unsigned int* __restrict__ ht_vals, size_t ht_cap, const float4* __restrict__ imp_prev,
-    float warmstart_coeff, float restitution_threshold, float inv_dt) {
+    float warmstart_coeff, float restitution_threshold, float inv_dt, int compact_layout) {
     unsigned int ci;
     if (mode == NB2_MODE_COLOURED) {
         // Gather formulation: threads enumerate the (phase, contact lane, group) slots in ELL order,
@@ -233,7 +233,13 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
         const unsigned int chunk_ = (unsigned int)vs.it_src[item];
         const unsigned int m_ = chunk_manifold[chunk_];
         const unsigned int lchunk = chunk_ - chunk_base[m_];
-        if (NB2_CHUNK * lchunk + lane >= manifolds[m_].num_contacts) return;
+        if (NB2_CHUNK * lchunk + lane >= manifolds[m_].num_contacts) {
+            // fewer than 4 contacts in this chunk: flag the lane's compact record invalid
+            if (compact_layout)
+                c_geo[4 * n_pslots_max + (size_t)NB2_CHUNK * vs.ph_gbase[p] + (size_t)lane * cnt + g] =
+                    make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
         ci = manifolds[m_].first_contact + NB2_CHUNK * lchunk + lane;
     } else {
         ci = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,8 +271,11 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
         if (ht_lookup(ht_keys, ht_vals, ht_cap, c.key, &prev)) cached = imp_prev[prev];
     }
 
-    size_t slot_n, slot_t1, slot_t2, pslot;
-    if (mode == NB2_MODE_COLOURED) {
+    const bool compact = compact_layout != 0;
+    size_t slot_n = 0, slot_t1 = 0, slot_t2 = 0, pslot;
+    if (compact) {
+        pslot = vs.pos_slot((size_t)nJ + chunk, lcc);
+    } else if (mode == NB2_MODE_COLOURED) {
         size_t item = (size_t)nJ + chunk;
         slot_t1 = vs.row_slot(item, 2 * lcc);
         slot_t2 = vs.row_slot(item, 2 * lcc + 1);
@@ -288,18 +297,36 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     if (rhs <= -restitution_threshold) rhs += mf.restitution * rhs;
     float depth = c.depth + mf.margin1 + mf.margin2;
     if (depth < 0.f) rhs += (-depth) * inv_dt;
-    write_row(out, slot_n, J1, J2, W1, W2, rhs, r, 0.f, NB2_F32_MAX, NB2_ROW_UNILATERAL, 0,
-              cached.x * warmstart_coeff);
+    const float rhs_n = rhs, r_n = r;
+    if (!compact)
+        write_row(out, slot_n, J1, J2, W1, W2, rhs, r, 0.f, NB2_F32_MAX, NB2_ROW_UNILATERAL, 0,
+                  cached.x * warmstart_coeff);
 
     // ---- friction pyramid rows (signorini_coulomb_pyramid_model.rs:131-216)
     Vec3 t1, t2;
     tangent_basis(n, &t1, &t2);
     emit_pair_row(out, slot_t1, s1, s2, center1, center2, false, t1, dot3(t1, surf), &rhs, &r, J1, J2, W1, W2);
-    write_row(out, slot_t1, J1, J2, W1, W2, rhs, r, mf.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
-              cached.y * warmstart_coeff);
+    const float rhs_t1 = rhs, r_t1 = r;
+    if (!compact)
+        write_row(out, slot_t1, J1, J2, W1, W2, rhs, r, mf.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
+                  cached.y * warmstart_coeff);
     emit_pair_row(out, slot_t2, s1, s2, center1, center2, false, t2, dot3(t2, surf), &rhs, &r, J1, J2, W1, W2);
-    write_row(out, slot_t2, J1, J2, W1, W2, rhs, r, mf.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
-              cached.z * warmstart_coeff);
+    if (!compact)
+        write_row(out, slot_t2, J1, J2, W1, W2, rhs, r, mf.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
+                  cached.z * warmstart_coeff);
+    if (compact) {
+        // Compact record: the solve kernel rebuilds J = mask*(d, p x d) and WJ = M^-1 J with the
+        // very expressions of fill_side, so the rows it iterates are bit-identical to the
+        // 132-byte rows of the reference-order layout at a fifth of the bytes.
+        const Vec3 p1 = center1 - s1.com, p2 = center2 - s2.com;
+        const size_t P_ = n_pslots_max;
+        c_geo[0 * P_ + pslot] = make_float4(p1.x, p1.y, p1.z, rhs_n);
+        c_geo[1 * P_ + pslot] = make_float4(p2.x, p2.y, p2.z, rhs_t1);
+        c_geo[2 * P_ + pslot] = make_float4(n.x, n.y, n.z, rhs);
+        c_geo[3 * P_ + pslot] = make_float4(r_n, r_t1, r, mf.friction);
+        c_geo[4 * P_ + pslot] = make_float4(cached.x * warmstart_coeff, cached.y * warmstart_coeff,
+                                            cached.z * warmstart_coeff, 1.f);
+    }
 
     // ---- position row (signorini_model.rs:153-197)
     const Quat q1 = f4_quat(B.pos_q[mf.body1]);
@@ -493,8 +520,8 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
     int mode, unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
     const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
     const unsigned int* __restrict__ chunk_base, const int* __restrict__ status, SchedView vs,
-    const float* __restrict__ r_imp, float4* imp_cur, unsigned long long* ht_keys, unsigned int* ht_vals,
-    size_t ht_cap) {
+    const float* __restrict__ r_imp, const float4* __restrict__ c_geo, size_t n_pslots_max, float4* imp_cur,
+    unsigned long long* ht_keys, unsigned int* ht_vals, size_t ht_cap, int compact_layout) {
     unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= nC) return;
     const unsigned int m = c_manifold[ci];
@@ -509,7 +536,10 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
         const unsigned int chunk = chunk_base[m] + lc / NB2_CHUNK;
         const int lcc = (int)(lc % NB2_CHUNK);
         const int ncc = min(NB2_CHUNK, (int)mf.num_contacts - NB2_CHUNK * (int)(lc / NB2_CHUNK));
-        if (mode == NB2_MODE_COLOURED) {
+        if (compact_layout) {
+            const float4 q = c_geo[4 * n_pslots_max + vs.pos_slot((size_t)nJ + chunk, lcc)];
+            v = make_float4(q.x, q.y, q.z, 0.f);
+        } else if (mode == NB2_MODE_COLOURED) {
             size_t item = (size_t)nJ + chunk;
             v.x = r_imp[vs.row_slot(item, 2 * ncc + lcc)];
             v.y = r_imp[vs.row_slot(item, 2 * lcc)];
@@ -592,7 +622,9 @@ int launch_assemble(Context* ctx, int mode) {
     const size_t maxc = ctx->max_chunks;
     // row-slot upper bounds (ELL padding included): every item may be padded to the widest group
     const size_t n_items = ctx->vs.n_items;
-    const size_t slots = n_items * (size_t)(3 * NB2_CHUNK) + 16;
+    // (coloured mode: only joints own generic rows, contacts live in the compact c_geo planes)
+    const size_t slots = (ctx->step_layout == 0 ? n_items * (size_t)(3 * NB2_CHUNK)
+                                                : (ctx->n_joints ? n_items * (size_t)NB2_MAX_JOINT_ROWS : 0)) + 16;
     const size_t pitems = ref ? ctx->ps.n_items : n_items;
     const size_t pslots = pitems * (size_t)NB2_CHUNK + 16;
     ctx->n_slots_max = slots;
@@ -604,6 +636,7 @@ int launch_assemble(Context* ctx, int mode) {
     NB2_TRY(ctx->r_imp.reserve(ctx, ctx->n_slots_max));
     NB2_TRY(ctx->p_row.reserve(ctx, 5 * pslots));
     ctx->n_pslots_max = ctx->p_row.cap / 5;
+    NB2_TRY(ctx->c_geo.reserve(ctx, ctx->step_layout == 0 ? 16 : 5 * ctx->n_pslots_max));
     SchedView vs = view_of(ctx->vs);
     SchedView ps = ref ? view_of(ctx->ps) : vs;
     const int prev = 1 - ctx->cur;
@@ -619,8 +652,8 @@ int launch_assemble(Context* ctx, int mode) {
             mode, ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p,
             ctx->c_manifold.p, ctx->chunk_base.p, ctx->chunk_manifold.p, body_arrays(ctx), vs, ps, row_out(ctx),
             ctx->p_row.p,
-            ctx->n_pslots_max, ctx->ht_keys[prev].p, ctx->ht_vals[prev].p, ctx->ht_cap[prev], ctx->imp[prev].p,
-            ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt);
+            ctx->n_pslots_max, ctx->c_geo.p, ctx->ht_keys[prev].p, ctx->ht_vals[prev].p, ctx->ht_cap[prev], ctx->imp[prev].p,
+            ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt, ctx->step_layout);
         ctx->launches++;
     }
     NB2_CUDA(ctx, cudaGetLastError());
@@ -647,8 +680,9 @@ int launch_cache_impulses(Context* ctx, int mode) {
     if (ctx->n_contacts) {
         k_cache_contact_impulses<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
             mode, ctx->n_contacts, ctx->n_joints, (unsigned int)ctx->max_chunks, ctx->manifolds.p, ctx->contacts.p,
-            ctx->c_manifold.p, ctx->chunk_base.p, ctx->b_status.p, vs, ctx->r_imp.p, ctx->imp[cur].p,
-            ctx->ht_keys[cur].p, ctx->ht_vals[cur].p, cap);
+            ctx->c_manifold.p, ctx->chunk_base.p, ctx->b_status.p, vs, ctx->r_imp.p, ctx->c_geo.p, ctx->n_pslots_max,
+            ctx->imp[cur].p,
+            ctx->ht_keys[cur].p, ctx->ht_vals[cur].p, cap, ctx->step_layout);
         ctx->launches++;
     }
     if (ctx->n_joints) {

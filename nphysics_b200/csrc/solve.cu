@@ -8,179 +8,13 @@
 // with ncollide's ContactKinematic::contact restated for Plane/Point, Point/Plane, Point/Point.
 #include <stdlib.h>
 
-#include "solver.cuh"
+#include "solve_compact.cuh"
 
 namespace nb2 {
 
-static const int TPB = 128;
+static const int TPB = SOLVE_TPB;
 
-struct SchedDev {
-    const unsigned int* ph_count;
-    const unsigned int* ph_gbase;
-    const unsigned int* ph_rbase;
-    const int4* g_info;
-    const SchedHeader* hdr;
-    const int* it_type;
-    const int* it_src;
-    const int* it_a;
-    const unsigned long long* it_key;
-    const int* it_phase;
-    const int* it_slot;
-    unsigned int max_phases;
-};
-static SchedDev sched_dev(const Sched& s) {
-    SchedDev d;
-    d.ph_count = s.ph_count.p;
-    d.ph_gbase = s.ph_gbase.p;
-    d.ph_rbase = s.ph_rbase.p;
-    d.g_info = s.g_info.p;
-    d.hdr = s.hdr.p;
-    d.it_type = s.it_type.p;
-    d.it_src = s.it_src.p;
-    d.it_a = s.it_a.p;
-    d.it_key = s.it_key.p;
-    d.it_phase = s.it_phase.p;
-    d.it_slot = s.it_slot.p;
-    d.max_phases = (unsigned int)s.max_phases;
-    return d;
-}
-
-struct Rows {
-    const float4* jac;
-    const float4* hdr;
-    const int2* meta;
-    float* imp;
-    size_t S;  // plane stride
-};
-
-struct Lam {
-    float v[6];
-};
-__device__ __forceinline__ Lam load_lam(const float4* lam, int b) {
-    Lam l;
-    float4 a = ldcg4(&lam[2 * b]), c = ldcg4(&lam[2 * b + 1]);
-    l.v[0] = a.x; l.v[1] = a.y; l.v[2] = a.z; l.v[3] = c.x; l.v[4] = c.y; l.v[5] = c.z;
-    return l;
-}
-__device__ __forceinline__ void store_lam(float4* lam, int b, const Lam& l) {
-    stcg4(&lam[2 * b], make_float4(l.v[0], l.v[1], l.v[2], 0.f));
-    stcg4(&lam[2 * b + 1], make_float4(l.v[3], l.v[4], l.v[5], 0.f));
-}
-__device__ __forceinline__ float dot6(const float* a, const float* b) {
-    float res = 0.f;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) res += a[k] * b[k];
-    return res;
-}
-__device__ __forceinline__ void axpy6(float a, const float* x, float* y) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) y[k] = a * x[k] + y[k];
-}
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v > lo ? (v < hi ? v : hi) : lo; }
-
-struct RowJ {
-    float J1[6], J2[6], W1[6], W2[6];
-};
-__device__ __forceinline__ void load_row_j(const Rows& R, size_t slot, bool a, bool b, RowJ* o) {
-    // 24 floats = 6 float4 planes: J1 | J2 | W1 | W2
-    float4 q0, q1, q2, q3, q4, q5;
-    q1 = __ldg(&R.jac[1 * R.S + slot]);
-    q4 = __ldg(&R.jac[4 * R.S + slot]);
-    if (a) {
-        q0 = __ldg(&R.jac[0 * R.S + slot]);
-        q3 = __ldg(&R.jac[3 * R.S + slot]);
-        o->J1[0] = q0.x; o->J1[1] = q0.y; o->J1[2] = q0.z; o->J1[3] = q0.w; o->J1[4] = q1.x; o->J1[5] = q1.y;
-        o->W1[0] = q3.x; o->W1[1] = q3.y; o->W1[2] = q3.z; o->W1[3] = q3.w; o->W1[4] = q4.x; o->W1[5] = q4.y;
-    }
-    if (b) {
-        q2 = __ldg(&R.jac[2 * R.S + slot]);
-        q5 = __ldg(&R.jac[5 * R.S + slot]);
-        o->J2[0] = q1.z; o->J2[1] = q1.w; o->J2[2] = q2.x; o->J2[3] = q2.y; o->J2[4] = q2.z; o->J2[5] = q2.w;
-        o->W2[0] = q4.z; o->W2[1] = q4.w; o->W2[2] = q5.x; o->W2[3] = q5.y; o->W2[4] = q5.z; o->W2[5] = q5.w;
-    }
-}
-
-// One SORProx row update (sor_prox.rs:181-343) on register-resident mj_lambda.
-// Returns the new impulse.
-__device__ __forceinline__ float solve_row(int kind, float4 h, float impulse, float dep_impulse, const RowJ& J,
-                                           bool a, bool b, Lam* la, Lam* lb) {
-    float lo, hi;
-    if (kind == NB2_ROW_UNILATERAL) {
-        lo = 0.f;
-        hi = NB2_F32_MAX;
-    } else if (kind == NB2_ROW_BILATERAL) {
-        lo = h.z;
-        hi = h.w;
-    } else {  // Dependent: sor_prox.rs:251-272
-        if (dep_impulse == 0.f) {
-            if (impulse != 0.f) {
-                if (a) axpy6(-impulse, J.W1, la->v);
-                if (b) axpy6(-impulse, J.W2, lb->v);
-            }
-            return 0.f;
-        }
-        hi = h.z * dep_impulse;
-        lo = -hi;
-    }
-    float d;
-    if (a && b)
-        d = dot6(J.J1, la->v) + dot6(J.J2, lb->v) + h.x;
-    else if (a)
-        d = dot6(J.J1, la->v) + h.x;
-    else
-        d = dot6(J.J2, lb->v) + h.x;
-    float ni;
-    if (kind == NB2_ROW_UNILATERAL)
-        ni = fmaxf(impulse - h.y * d, 0.f);
-    else
-        ni = clampf(impulse - h.y * d, lo, hi);
-    float dl = ni - impulse;
-    if (a) axpy6(dl, J.W1, la->v);
-    if (b) axpy6(dl, J.W2, lb->v);
-    return ni;
-}
-
-// A row as it travels from the ELL planes to the update: 6 jacobian quads, header, meta, the
-// row's impulse and (for Dependent rows) the impulse of the row it depends on.
-struct RowPkt {
-    float4 q0, q1, q2, q3, q4, q5, h;
-    int2 meta;
-    float imp;
-};
-// All loads of a row are issued together and one row ahead of its use (software pipelining):
-// per phase an SM owns only ~200 groups, so latency is hidden by loads in flight per thread,
-// not by occupancy.  Read-only planes go through ld.global.nc; impulses bypass L1 (ld.cg)
-// because other SMs wrote them in an earlier phase.
-__device__ __forceinline__ void load_pkt(const Rows& R, size_t slot, bool a, bool b, RowPkt* o) {
-    o->meta = __ldg(&R.meta[slot]);
-    o->h = __ldg(&R.hdr[slot]);
-    o->q1 = __ldg(&R.jac[1 * R.S + slot]);
-    o->q4 = __ldg(&R.jac[4 * R.S + slot]);
-    if (a) {
-        o->q0 = __ldg(&R.jac[0 * R.S + slot]);
-        o->q3 = __ldg(&R.jac[3 * R.S + slot]);
-    }
-    if (b) {
-        o->q2 = __ldg(&R.jac[2 * R.S + slot]);
-        o->q5 = __ldg(&R.jac[5 * R.S + slot]);
-    }
-    o->imp = __ldcg(&R.imp[slot]);
-}
-__device__ __forceinline__ void unpack_pkt(const RowPkt& k, bool a, bool b, RowJ* o) {
-    if (a) {
-        o->J1[0] = k.q0.x; o->J1[1] = k.q0.y; o->J1[2] = k.q0.z; o->J1[3] = k.q0.w; o->J1[4] = k.q1.x; o->J1[5] = k.q1.y;
-        o->W1[0] = k.q3.x; o->W1[1] = k.q3.y; o->W1[2] = k.q3.z; o->W1[3] = k.q3.w; o->W1[4] = k.q4.x; o->W1[5] = k.q4.y;
-    }
-    if (b) {
-        o->J2[0] = k.q1.z; o->J2[1] = k.q1.w; o->J2[2] = k.q2.x; o->J2[3] = k.q2.y; o->J2[4] = k.q2.z; o->J2[5] = k.q2.w;
-        o->W2[0] = k.q4.z; o->W2[1] = k.q4.w; o->W2[2] = k.q5.x; o->W2[3] = k.q5.y; o->W2[4] = k.q5.z; o->W2[5] = k.q5.w;
-    }
-}
-// Warps are dealt to groups block-interleaved (warp w of block b is global warp w*gridDim+b) so a
-// phase with fewer groups than threads still spreads evenly over all SMs.
-__device__ __forceinline__ size_t interleaved_tid() {
-    return ((size_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
-}
+int launch_velocity_solve_coloured(Context* ctx, const SchedDev& sd, const Rows& R, const CompactArrays& CA);
 
 // mode_warm: 1 = run a warm-start pass over the phases first (coloured mode)
 __global__ void __launch_bounds__(TPB) k_velocity_solve(SchedDev sd, Rows R, float4* lam, int iters, int mode_warm,
@@ -652,8 +486,9 @@ __device__ __forceinline__ int float_key(float f) {
     int i = __float_as_int(f);
     return i >= 0 ? i : (i ^ 0x7FFFFFFF);
 }
-__global__ void __launch_bounds__(TPB) k_residual(SchedDev sd, Rows R, const float4* __restrict__ lam, float* res_max,
-                                                  double* res_sq, unsigned int* res_n, unsigned int* rows_two,
+__global__ void __launch_bounds__(TPB) k_residual(SchedDev sd, Rows R, CompactArrays CA,
+                                                  const float4* __restrict__ lam, float* res_max, double* res_sq,
+                                                  unsigned int* res_n, unsigned int* rows_two,
                                                   unsigned int* rows_ground) {
     const unsigned int np = sd.hdr->n_phases;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -667,6 +502,13 @@ __global__ void __launch_bounds__(TPB) k_residual(SchedDev sd, Rows R, const flo
         for (size_t g = tid; g < cnt; g += stride) {
             const int4 info = sd.g_info[gbase + g];
             const bool a = info.x >= 0, b = info.y >= 0;
+            if (NB2_Z_IS_COMPACT(info.z) && CA.c_geo != nullptr) {
+                unsigned int nr = 0;
+                compact_group(CA, 2, info.x, info.y, (size_t)NB2_CHUNK * gbase, cnt, g, (info.z & 0xFF) >> 4, &mx, &sq, &nr);
+                cntr += nr;
+                if (a && b) two += nr; else ground += nr;
+                continue;
+            }
             Lam la, lb;
             if (a) la = load_lam(lam, info.x);
             if (b) lb = load_lam(lam, info.y);
@@ -762,6 +604,17 @@ static Rows rows_of(Context* ctx) {
     R.S = ctx->n_slots_max;
     return R;
 }
+static CompactArrays compact_arrays(Context* ctx, bool ref) {
+    CompactArrays A;
+    A.raw = ctx->raw.p;
+    A.com_im = ctx->com_im.p;
+    A.inv_i = ctx->inv_i.p;
+    A.lam = ctx->lam.p;
+    A.c_geo = ctx->step_layout == 1 ? ctx->c_geo.p : nullptr;
+    A.P = ctx->n_pslots_max;
+    A.any_mask = ctx->any_mask ? 1 : 0;
+    return A;
+}
 static PosArrays pos_arrays(Context* ctx) {
     PosArrays A;
     A.raw = ctx->raw.p;
@@ -805,6 +658,7 @@ int launch_velocity_solve(Context* ctx, int mode) {
     // alternating the colour order per sweep (symmetric Gauss-Seidel) was measured: it helps flat
     // piles and hurts tall ones (profiles/r01_notes.md), so the plain order stays the default
     int symmetric = 0;
+    if (ctx->step_layout == 1) return launch_velocity_solve_coloured(ctx, sd, R, compact_arrays(ctx, ref));
     void* args[] = {&sd, &R, &lam, &iters, &warm, &symmetric, &bar};
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_velocity_solve, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
@@ -837,7 +691,9 @@ int launch_position_solve(Context* ctx, int mode) {
     size_t want = (s.n_items + TPB - 1) / TPB;
     int blocks = (int)(want < (size_t)ctx->coop_blocks_pos ? want : (size_t)ctx->coop_blocks_pos);
     if (blocks < 1) blocks = 1;
-    int rows_div = ref ? 1 : 3;  // coloured groups carry 3 velocity rows per contact
+    // contacts per group: reference order -> the row count itself; coloured rows -> 3 rows per contact;
+    // compact -> the count sits in bits 4..7
+    int rows_div = ref ? 1 : (ctx->step_layout == 1 ? 16 : 3);
     void* args[] = {&sd, &A, &joints, &manifolds, &cm, &prow, &pstride, &P, &iters, &rows_div, &bar};
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_position_solve, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
     ctx->launches++;
@@ -861,14 +717,14 @@ int launch_stats(Context* ctx, int mode) {
     unsigned int* u = ctx->stat_u.p;
     const int blocks = ctx->sm_count * 4;
     if (ctx->vs.n_items) {
-        k_residual<<<blocks, TPB, 0, ctx->stream>>>(sched_dev(ctx->vs), rows_of(ctx), ctx->lam.p, f + 0, d + 0, u + 0,
-                                                    u + 1, u + 2);
+        k_residual<<<blocks, TPB, 0, ctx->stream>>>(sched_dev(ctx->vs), rows_of(ctx), compact_arrays(ctx, ref), ctx->lam.p,
+                                                    f + 0, d + 0, u + 0, u + 1, u + 2);
         ctx->launches++;
         Sched& s = ref ? ctx->ps : ctx->vs;
         if (ctx->n_contacts) {
             k_penetration<<<blocks, TPB, 0, ctx->stream>>>(sched_dev(s), pos_arrays(ctx), ctx->manifolds.p,
                                                            ctx->chunk_manifold.p, ctx->p_row.p, ctx->n_pslots_max,
-                                                           ref ? 1 : 3, (int*)(u + 4));
+                                                           ref ? 1 : (ctx->step_layout == 1 ? 16 : 3), (int*)(u + 4));
             ctx->launches++;
         }
     }

@@ -81,6 +81,10 @@ struct DevBuf {
 #define NB2_ROW_BILATERAL 2   // Independent{lo, hi}
 #define NB2_ROW_DEPENDENT 3   // Dependent{dependency, coeff}
 
+// g_info.z low byte: generic row count (row layout, low nibble != 0 for contact groups: 3,6,9,12) or
+// (contacts << 4) for compact contact groups
+#define NB2_Z_IS_COMPACT(z) ((((z) >> 8) == NB2_ITEM_CONTACTS) && (((z) & 0xF) == 0))
+
 // item types
 #define NB2_ITEM_JOINT 0
 #define NB2_ITEM_CONTACTS 1     // coloured: friction + normal rows of one chunk
@@ -149,6 +153,9 @@ struct Context {
     bool have_params = false;
     bool timers = false;
     bool schedule_cache = true;
+    // coloured mode, contact groups: 0 = 132-byte row stream (default), 1 = 80-byte compact records
+    int contact_layout = 0;
+    int step_layout = 0;  // layout the last assembly used
     StageEvents ev;
     bool ev_valid = false;
 
@@ -206,6 +213,10 @@ struct Context {
     DevBuf<int2> r_meta;    // kind, dependency slot
     DevBuf<float> r_imp;
     DevBuf<float4> p_row;   // [5][n_pslots_max] position rows
+    // coloured mode: compact velocity data of a contact, same slot index as p_row:
+    // (p1, rhs_n) (p2, rhs_t1) (n, rhs_t2) (r_n, r_t1, r_t2, mu) (imp_n, imp_t1, imp_t2, valid)
+    DevBuf<float4> c_geo;   // [5][n_pslots_max]
+    bool any_mask = false;  // some body has a jacobian_mask entry != 1
 
     // ---- stats
     DevBuf<float> stat_f;           // reductions
@@ -216,7 +227,7 @@ struct Context {
     int last_mode = -1;
     bool stepped = false;
 
-    int coop_blocks_vel = 0, coop_blocks_pos = 0, coop_blocks_sched = 0;
+    int coop_blocks_vel = 0, coop_blocks_pos = 0, coop_blocks_sched = 0, coop_blocks_col = 0;
 };
 
 // ---------------------------------------------------------------------------
@@ -238,11 +249,14 @@ struct GridBarrier {
         __syncthreads();
         if (threadIdx.x == 0) {
             target += gridDim.x;
-            __threadfence();
-            atomicAdd(counter, 1u);
-            while (*((volatile unsigned int*)counter) < target) {
-            }
-            __threadfence();
+            // arrive with release semantics (orders this block's earlier writes, made visible to
+            // thread 0 by the bar.sync above), then poll with acquire loads: no separate full
+            // fences on either side of the atomic
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+            unsigned int v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            } while (v < target);
         }
         __syncthreads();
     }

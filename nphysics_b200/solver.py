@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libnphysics_b200.so")
 EXPORTS = [
     "nb2_abi_version", "nb2_error_string", "nb2_default_params", "nb2_sizeof", "nb2_combine_materials",
     "nb2_create", "nb2_destroy", "nb2_last_error", "nb2_set_params", "nb2_get_params", "nb2_enable_timers",
-    "nb2_set_schedule_cache",
+    "nb2_set_schedule_cache", "nb2_set_contact_layout",
     "nb2_upload_bodies", "nb2_upload_body_states", "nb2_upload_manifolds", "nb2_upload_joints",
     "nb2_clear_impulse_cache", "nb2_step", "nb2_synchronize", "nb2_download_body_states",
     "nb2_download_contact_impulses", "nb2_download_joints", "nb2_get_stats", "nb2_get_timers",
@@ -123,6 +123,9 @@ class Solver:
 
     def set_schedule_cache(self, on=True):
         self._chk(self.lib.nb2_set_schedule_cache(self.h, 1 if on else 0))
+
+    def set_contact_layout(self, layout):
+        self._chk(self.lib.nb2_set_contact_layout(self.h, int(layout)))
 
     def upload_bodies(self, bodies):
         b = np.ascontiguousarray(bodies, dtype=abi.body_dtype)

@@ -174,6 +174,7 @@ extern "C" {
     pub fn nb2_get_params(ctx: *const nb2_context, out: *mut nb2_params) -> i32;
     pub fn nb2_enable_timers(ctx: *mut nb2_context, enabled: i32) -> i32;
     pub fn nb2_set_schedule_cache(ctx: *mut nb2_context, enabled: i32) -> i32;
+    pub fn nb2_set_contact_layout(ctx: *mut nb2_context, layout: i32) -> i32;
     pub fn nb2_upload_bodies(ctx: *mut nb2_context, bodies: *const nb2_body, n: u32) -> i32;
     pub fn nb2_upload_body_states(ctx: *mut nb2_context, states: *const nb2_body_state, first: u32, n: u32) -> i32;
     pub fn nb2_upload_manifolds(ctx: *mut nb2_context, manifolds: *const nb2_manifold, n_manifolds: u32,

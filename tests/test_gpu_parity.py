@@ -396,3 +396,31 @@ def test_empty_inputs_and_ragged_manifolds():
     check_step("empty", g, o)
     g.step(COL)
     g.synchronize()
+
+
+def test_compact_contact_layout_matches_row_layout():
+    """nb2_set_contact_layout(1): same rows rebuilt in registers from 80-byte records (FMA-contracted
+    arithmetic, so agreement is to rounding, not bitwise)."""
+    sc = scenes.boxes3(6, 6, 6)
+    sc.bodies["jacobian_mask"][5, 3:] = 0.0      # exercise the masked path of the compact kernel
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    outs = []
+    for layout in (0, 1):
+        s = new_solver()
+        s.set_contact_layout(layout)
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+        for _ in range(4):
+            s.upload_manifolds(m, c)
+            s.step(COL)
+        st = s.get_stats()
+        outs.append((s.download_body_states(), s.download_contact_impulses(), st))
+    (b0, i0, s0), (b1, i1, s1) = outs
+    assert int(s0["n_rows_two_body"]) == int(s1["n_rows_two_body"])
+    assert int(s0["n_rows_ground"]) == int(s1["n_rows_ground"])
+    assert rel_err(i1, i0) < 2e-3
+    assert np.abs(b1["velocity"] - b0["velocity"]).max() < 2e-3
+    assert rel_err(b1["position"], b0["position"]) < 1e-5
+    assert float(s1["residual_max"]) == pytest.approx(float(s0["residual_max"]), rel=0.2)
+    assert float(s1["max_penetration"]) == pytest.approx(float(s0["max_penetration"]), rel=0.05, abs=1e-5)
