@@ -44,7 +44,9 @@ static void release_all(Context* c) {
     c->adj_p.release(); c->cmask.release(); c->best.release(); c->scan_tmp.release(); c->barrier.release();
     c->r_jac.release(); c->r_hdr.release(); c->r_meta.release(); c->r_imp.release(); c->p_row.release();
     c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
-    c->c_geo.release();
+    c->c_geo.release(); c->turn.release(); c->turn_p.release(); c->bal.release();
+    if (c->host_hdr) cudaFreeHost(c->host_hdr);
+    c->host_hdr = nullptr;
 }
 
 static int check_flags(Context* ctx) {
@@ -64,6 +66,7 @@ static int check_flags(Context* ctx) {
     ctx->last_stats.n_phases_velocity = hv.n_phases;
     ctx->last_stats.n_phases_position = ctx->last_mode == NB2_MODE_REFERENCE_ORDER ? hp.n_phases : hv.n_phases;
     if (f & 1u) return set_error(ctx, NB2_ERR_BAD_INDEX, "a manifold/joint record referenced a body or contact out of range");
+    if (f & 4u) return set_error(ctx, NB2_ERR_CUDA, "internal: dataflow solve exceeded its spin limit (dependency never satisfied)");
     if (f & 2u) return set_error(ctx, NB2_ERR_UNSUPPORTED, "a manifold/joint connects a body to itself (unsupported)");
     if ((hv.overflow | hp.overflow) & 1u)
         return set_error(ctx, NB2_ERR_TOO_MANY_COLOURS, "colouring needs more than %d colours", NB2_MAX_COLOURS);
@@ -88,6 +91,14 @@ static int do_step(Context* ctx, int mode) {
     NB2_TRY(launch_build_items(ctx, mode));
     NB2_TRY(launch_schedule(ctx, &ctx->vs, mode));
     if (ref) NB2_TRY(launch_schedule(ctx, &ctx->ps, mode));
+    if (!ref) {
+        // colour count of this step for the next step's launch geometry (a hint: never waited for)
+        if (!ctx->host_hdr) {
+            NB2_CUDA(ctx, cudaHostAlloc(&ctx->host_hdr, sizeof(SchedHeader), cudaHostAllocDefault));
+            memset(ctx->host_hdr, 0, sizeof(SchedHeader));
+        }
+        NB2_CUDA(ctx, cudaMemcpyAsync(ctx->host_hdr, ctx->vs.hdr.p, sizeof(SchedHeader), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[11], ctx->stream));
     NB2_TRY(launch_assemble(ctx, mode));
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[1], ctx->stream));
@@ -222,10 +233,13 @@ int nb2_create(int device, void* stream, nb2_context** out) {
     ctx->last_error[0] = 0;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
     memset(&ctx->last_stats, 0, sizeof(ctx->last_stats));
     nb2_default_params(&ctx->params);
     ctx->inv_dt = 1.0f / ctx->params.dt;
     ctx->have_params = true;
+    // developer knob for A/B measurements of the coloured velocity kernel variants (solver.cuh)
+    if (const char* vk = getenv("NB2_VELOCITY_KERNEL")) ctx->velocity_kernel = atoi(vk);
     if (cudaSetDevice(device) != cudaSuccess) {
         delete h;
         return set_error(nullptr, NB2_ERR_CUDA, "cudaSetDevice failed");

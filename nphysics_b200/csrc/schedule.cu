@@ -302,6 +302,7 @@ static int reserve_sched(Context* ctx, Sched* s, size_t n_items, size_t max_phas
     NB2_TRY(s->ph_gbase.reserve(ctx, max_phases + 1));
     NB2_TRY(s->ph_rbase.reserve(ctx, max_phases + 1));
     NB2_TRY(s->g_info.reserve(ctx, n_items));
+    NB2_TRY(s->g_rank.reserve(ctx, n_items));
     NB2_TRY(s->hdr.reserve(ctx, 1));
     return NB2_OK;
 }
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict_
                                                 const int* __restrict__ it_type, int* phase,
                                                 unsigned long long* cmask, unsigned long long* best,
                                                 unsigned int* flags /*3*/, SchedHeader* hdr, unsigned int* barrier,
-                                                const unsigned int* __restrict__ changed) {
+                                                const unsigned int* __restrict__ changed, unsigned int* bal) {
     if (*changed == 0u) return;  // cached colouring still valid (uniform over the grid: no barrier was touched)
     GridBarrier gb;
     gb.init(barrier);
@@ -528,6 +529,91 @@ __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict_
         }
         gb.sync();
     }
+    // ---- balancing.  First-fit colouring fills the low colours to the brim (~N_bodies/2 groups) and
+    // leaves a tail of nearly empty ones, but every colour costs the solve kernels a grid barrier plus
+    // one group's latency chain however few groups it holds, and an over-full colour makes threads run
+    // two groups back to back.  Groups of over-full colours therefore migrate to under-full colours
+    // that are free at both of their bodies: a deterministic pseudo-random subset (the colour's excess)
+    // bids per round, Jones-Plassmann style, so no two movers of a round share a body.
+    __shared__ unsigned int s_cnt[NB2_MAX_COLOURS];
+    __shared__ unsigned int s_C, s_T, s_over;
+    for (size_t i = tid; i < n; i += stride)
+        if (it_type[i] != NB2_ITEM_INVALID) atomicAdd(&bal[min((unsigned int)phase[i], (unsigned int)NB2_MAX_COLOURS - 1u)], 1u);
+    gb.sync();
+    for (unsigned int r = 0; r < NB2_BALANCE_ROUNDS; ++r) {
+        const unsigned int round = 0x800u + r;  // above every colouring round: bids of this stage beat the stale ones
+        for (unsigned int c = threadIdx.x; c < NB2_MAX_COLOURS; c += blockDim.x) s_cnt[c] = __ldcg(&bal[c]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int C = 0, total = 0, mx = 0;
+            for (unsigned int c = 0; c < NB2_MAX_COLOURS; ++c) {
+                if (s_cnt[c]) C = c + 1;
+                total += s_cnt[c];
+                mx = max(mx, s_cnt[c]);
+            }
+            s_C = C;
+            s_T = C ? (total + C - 1) / C : 0;
+            s_over = C > 1 && mx > s_T + s_T / 32 + 8;
+        }
+        __syncthreads();
+        const unsigned int C = s_C, T = s_T;
+        if (!s_over) break;  // uniform over the grid: every block read the same counts
+        for (int pass = 0; pass < 2; ++pass) {
+            for (size_t i = tid; i < n; i += stride) {
+                if (it_type[i] == NB2_ITEM_INVALID) continue;
+                const unsigned int c = (unsigned int)phase[i];
+                if (c >= C || s_cnt[c] <= T) continue;
+                if (hash_u32((unsigned int)i * 0x9E3779B9u + round) % s_cnt[c] >= s_cnt[c] - T) continue;
+                const int a = it_a[i], b = it_b[i];
+                unsigned long long used[NB2_MASK_WORDS];
+#pragma unroll
+                for (int w = 0; w < NB2_MASK_WORDS; ++w) {
+                    used[w] = 0;
+                    if (a >= 0) used[w] |= __ldcg(&cmask[(size_t)a * NB2_MASK_WORDS + w]);
+                    if (b >= 0) used[w] |= __ldcg(&cmask[(size_t)b * NB2_MASK_WORDS + w]);
+                }
+                int target = -1;
+                unsigned long long best_score = 0;
+                for (unsigned int d = 0; d < C; ++d) {
+                    if (s_cnt[d] >= T) continue;
+                    unsigned long long word = used[0];
+#pragma unroll
+                    for (int w = 1; w < NB2_MASK_WORDS; ++w)
+                        if ((d >> 6) == (unsigned int)w) word = used[w];
+                    if ((word >> (d & 63)) & 1ull) continue;
+                    const unsigned long long score =
+                        (unsigned long long)(T - s_cnt[d]) * (1024u + (hash_u32((unsigned int)i ^ (d * 0x85EBCA6Bu) ^ (round << 20)) & 1023u));
+                    if (score > best_score) {
+                        best_score = score;
+                        target = (int)d;
+                    }
+                }
+                if (target < 0) continue;
+                const unsigned long long prio = ((unsigned long long)round << 52) |
+                                                ((unsigned long long)(hash_u32((unsigned int)i + round) & 0xFFFFFu) << 32) |
+                                                (unsigned long long)(unsigned int)i;
+                if (pass == 0) {
+                    if (a >= 0) atomicMax(&best[a], prio);
+                    if (b >= 0) atomicMax(&best[b], prio);
+                } else {
+                    if (a >= 0 && __ldcg(&best[a]) != prio) continue;
+                    if (b >= 0 && __ldcg(&best[b]) != prio) continue;
+                    // sole mover on both bodies this round: their masks are ours to edit
+                    const int sides[2] = {a, b};
+                    for (int k = 0; k < 2; ++k) {
+                        if (sides[k] < 0) continue;
+                        unsigned long long* m = &cmask[(size_t)sides[k] * NB2_MASK_WORDS];
+                        __stcg(&m[c >> 6], __ldcg(&m[c >> 6]) & ~(1ull << (c & 63)));
+                        __stcg(&m[target >> 6], __ldcg(&m[target >> 6]) | (1ull << (target & 63)));
+                    }
+                    phase[i] = target;
+                    atomicAdd(&bal[target], 1u);
+                    atomicSub(&bal[c], 1u);
+                }
+            }
+            gb.sync();
+        }
+    }
 }
 
 // ------------------------------------------------------------------ layout
@@ -568,6 +654,7 @@ __global__ void k_fill_ginfo(const unsigned int* __restrict__ changed, size_t n,
                              const int* __restrict__ it_a, const int* __restrict__ it_b,
                              const int* __restrict__ it_nrows, const int* __restrict__ phase,
                              const int* __restrict__ slot, const unsigned int* __restrict__ ph_gbase, int4* g_info,
+                             const unsigned long long* __restrict__ cmask, unsigned int* g_rank, SchedHeader* hdr,
                              unsigned int max_phases) {
     if (*changed == 0u) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -576,6 +663,31 @@ __global__ void k_fill_ginfo(const unsigned int* __restrict__ changed, size_t n,
     // z packs the row count (low 8 bits) and the item type (bits 8..) so the solve kernels need
     // no second lookup
     g_info[ph_gbase[p] + slot[i]] = make_int4(it_a[i], it_b[i], it_nrows[i] | (it_type[i] << 8), (int)i);
+    if (cmask != nullptr) {
+        // rank of this group among the groups of each of its bodies, in colour order, and the bodies'
+        // degrees -- straight from the per-body colour masks (all colours on a body are distinct)
+        unsigned int rk = 0;
+        const int sides[2] = {it_a[i], it_b[i]};
+#pragma unroll
+        for (int sd_ = 0; sd_ < 2; ++sd_) {
+            unsigned int below = 0, deg = 0;
+            if (sides[sd_] >= 0) {
+                for (int w = 0; w < NB2_MASK_WORDS; ++w) {
+                    const unsigned long long m = cmask[(size_t)sides[sd_] * NB2_MASK_WORDS + w];
+                    deg += (unsigned int)__popcll(m);
+                    if ((unsigned int)w < (p >> 6)) below += (unsigned int)__popcll(m);
+                    else if ((unsigned int)w == (p >> 6)) below += (unsigned int)__popcll(m & ((1ull << (p & 63)) - 1ull));
+                }
+            }
+            if (deg > 255u) {
+                atomicOr(&hdr->overflow, 1u);
+                deg = 255u;
+            }
+            rk |= (below & 0xFFu) << (16 * sd_);
+            rk |= (deg & 0xFFu) << (16 * sd_ + 8);
+        }
+        g_rank[ph_gbase[p] + slot[i]] = rk;
+    }
 }
 __global__ void k_copy_phase(size_t n, const int* __restrict__ level, int* phase) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -678,7 +790,9 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
             changed, (unsigned int*)ctx->cmask.p, (size_t)nb * NB2_MASK_WORDS * 2);
         k_cond_zero<<<nblk((size_t)nb * 2), TPB, 0, ctx->stream>>>(changed, (unsigned int*)ctx->best.p, (size_t)nb * 2);
         k_cond_fill_int<<<nblk(n), TPB, 0, ctx->stream>>>(changed, s->it_phase.p, n, -1);
-        ctx->launches += 3;
+        NB2_TRY(ctx->bal.reserve(ctx, NB2_MAX_COLOURS));
+        k_cond_zero<<<nblk(NB2_MAX_COLOURS), TPB, 0, ctx->stream>>>(changed, ctx->bal.p, NB2_MAX_COLOURS);
+        ctx->launches += 4;
         NB2_TRY(coop_blocks(ctx, k_colour, &blocks_colour));
         int blocks = (int)min((size_t)blocks_colour, (n + TPB - 1) / TPB);
         size_t n_ = n;
@@ -691,7 +805,8 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
         SchedHeader* hd = s->hdr.p;
         unsigned int* bar = ctx->barrier.p;
         const unsigned int* ch = changed;
-        void* args[] = {&n_, &ia, &ib, &ty, &ph, &cm, &be, &flags, &hd, &bar, &ch};
+        unsigned int* bl = ctx->bal.p;
+        void* args[] = {&n_, &ia, &ib, &ty, &ph, &cm, &be, &flags, &hd, &bar, &ch, &bl};
         NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_colour, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
         ctx->launches++;
     }
@@ -700,7 +815,8 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     k_phase_scan<<<1, 1, 0, ctx->stream>>>(changed, s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
     k_fill_ginfo<<<nblk(n), TPB, 0, ctx->stream>>>(changed, n, s->it_type.p, s->it_a.p, s->it_b.p, s->it_nrows.p,
                                                    s->it_phase.p, s->it_slot.p, s->ph_gbase.p, s->g_info.p,
-                                                   (unsigned int)s->max_phases);
+                                                   mode == NB2_MODE_COLOURED ? ctx->cmask.p : nullptr, s->g_rank.p,
+                                                   s->hdr.p, (unsigned int)s->max_phases);
     ctx->launches += 3;
     NB2_CUDA(ctx, cudaGetLastError());
     return NB2_OK;

@@ -15,8 +15,61 @@ namespace nb2 {
 static const int TPB = SOLVE_TPB;
 
 int launch_velocity_solve_coloured(Context* ctx, const SchedDev& sd, const Rows& R, const CompactArrays& CA);
+int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd, const Rows& R, int tpb, int depth, int blocks);
+bool staged_geometry(Context* ctx, int* tpb, int* depth, int* blocks);
 
-// mode_warm: 1 = run a warm-start pass over the phases first (coloured mode)
+// All rows of one group on register-resident mj_lambda (SORProx row updates, sor_prox.rs:181-343;
+// warm start :345-435 when `warm`).  Rows are software-pipelined one ahead.
+__device__ __forceinline__ void velocity_group(const Rows& R, float4* lam, int4 info, size_t rbase, unsigned int cnt,
+                                               size_t g, bool warm) {
+    const bool a = info.x >= 0, b = info.y >= 0;
+    const int nrows = info.z & 0xFF, type = info.z >> 8;
+    RowPkt cur, nxt;
+    if (nrows > 0) load_pkt(R, rbase + g, a, b, &cur);
+    // Coloured contact groups hold their own normal rows (rows 2*ncc..3*ncc): their impulses are
+    // fetched up front so friction rows never chase a dependent load.
+    const int ncc = type == NB2_ITEM_CONTACTS ? nrows / 3 : 0;
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+    if (ncc > 0) n0 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 0) * cnt + g]);
+    if (ncc > 1) n1 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 1) * cnt + g]);
+    if (ncc > 2) n2 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 2) * cnt + g]);
+    if (ncc > 3) n3 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 3) * cnt + g]);
+    Lam la, lb;
+    if (a) la = load_lam(lam, info.x);
+    if (b) lb = load_lam(lam, info.y);
+    for (int r = 0; r < nrows; ++r) {
+        const size_t slot = rbase + (size_t)r * cnt + g;
+        if (r + 1 < nrows) load_pkt(R, slot + cnt, a, b, &nxt);
+        if (cur.meta.x != NB2_ROW_NONE) {
+            RowJ J;
+            unpack_pkt(cur, a, b, &J);
+            if (warm) {
+                if (cur.imp != 0.f) {
+                    if (a) axpy6(cur.imp, J.W1, la.v);
+                    if (b) axpy6(cur.imp, J.W2, lb.v);
+                }
+            } else {
+                float dep = 0.f;
+                if (cur.meta.x == NB2_ROW_DEPENDENT) {
+                    if (r < 2 * ncc) {
+                        const int k = r >> 1;
+                        dep = k == 0 ? n0 : (k == 1 ? n1 : (k == 2 ? n2 : n3));
+                    } else {
+                        dep = __ldcg(&R.imp[cur.meta.y]);  // reference order: another group's row
+                    }
+                }
+                float ni = solve_row(cur.meta.x, cur.h, cur.imp, dep, J, a, b, &la, &lb);
+                if (ni != cur.imp) __stcg(&R.imp[slot], ni);
+            }
+        }
+        cur = nxt;
+    }
+    if (a) store_lam(lam, info.x, la);
+    if (b) store_lam(lam, info.y, lb);
+}
+
+// Phase-by-phase execution with a grid barrier between phases (reference-order levels; also the
+// fallback of the coloured mode).  mode_warm: 1 = warm-start pass over the phases first.
 __global__ void __launch_bounds__(TPB) k_velocity_solve(SchedDev sd, Rows R, float4* lam, int iters, int mode_warm,
                                                         int symmetric, unsigned int* barrier) {
     GridBarrier gb;
@@ -29,54 +82,75 @@ __global__ void __launch_bounds__(TPB) k_velocity_solve(SchedDev sd, Rows R, flo
             const unsigned int p = (symmetric && (it & 1)) ? (np - 1 - pp) : pp;
             const unsigned int cnt = sd.ph_count[p];
             const size_t rbase = sd.ph_rbase[p], gbase = sd.ph_gbase[p];
-            for (size_t g = tid; g < cnt; g += stride) {
-                const int4 info = sd.g_info[gbase + g];
-                const bool a = info.x >= 0, b = info.y >= 0;
-                const int nrows = info.z & 0xFF, type = info.z >> 8;
-                RowPkt cur, nxt;
-                if (nrows > 0) load_pkt(R, rbase + g, a, b, &cur);
-                // Coloured contact groups hold their own normal rows (rows 2*ncc..3*ncc): their
-                // impulses are fetched up front so friction rows never chase a dependent load.
-                const int ncc = type == NB2_ITEM_CONTACTS ? nrows / 3 : 0;
-                float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-                if (ncc > 0) n0 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 0) * cnt + g]);
-                if (ncc > 1) n1 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 1) * cnt + g]);
-                if (ncc > 2) n2 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 2) * cnt + g]);
-                if (ncc > 3) n3 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 3) * cnt + g]);
-                Lam la, lb;
-                if (a) la = load_lam(lam, info.x);
-                if (b) lb = load_lam(lam, info.y);
-                for (int r = 0; r < nrows; ++r) {
-                    const size_t slot = rbase + (size_t)r * cnt + g;
-                    if (r + 1 < nrows) load_pkt(R, slot + cnt, a, b, &nxt);
-                    if (cur.meta.x != NB2_ROW_NONE) {
-                        RowJ J;
-                        unpack_pkt(cur, a, b, &J);
-                        if (it < 0) {  // warm start (sor_prox.rs:345-435)
-                            if (cur.imp != 0.f) {
-                                if (a) axpy6(cur.imp, J.W1, la.v);
-                                if (b) axpy6(cur.imp, J.W2, lb.v);
-                            }
-                        } else {
-                            float dep = 0.f;
-                            if (cur.meta.x == NB2_ROW_DEPENDENT) {
-                                if (r < 2 * ncc) {
-                                    const int k = r >> 1;
-                                    dep = k == 0 ? n0 : (k == 1 ? n1 : (k == 2 ? n2 : n3));
-                                } else {
-                                    dep = __ldcg(&R.imp[cur.meta.y]);  // reference order: another group's row
-                                }
-                            }
-                            float ni = solve_row(cur.meta.x, cur.h, cur.imp, dep, J, a, b, &la, &lb);
-                            if (ni != cur.imp) __stcg(&R.imp[slot], ni);
-                        }
-                    }
-                    cur = nxt;
-                }
-                if (a) store_lam(lam, info.x, la);
-                if (b) store_lam(lam, info.y, lb);
-            }
+            for (size_t g = tid; g < cnt; g += stride)
+                velocity_group(R, lam, sd.g_info[gbase + g], rbase, cnt, g, it < 0);
             gb.sync();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Barrier-free (dataflow) execution of the coloured schedule.
+//
+// A grid barrier per colour costs ~8 us of pure latency per phase visit and leaves the machine idle
+// while the slowest block arrives; with ~10 colours x 11 sweeps that is most of the kernel on a
+// 100k-body scene.  But a group only depends on the previous visit of ITS two bodies.  Every body
+// carries a turn counter (completed visits).  Group i is the ra-th of da groups on body a (colour
+// order: ra = number of a's colours below i's), so its visit of sweep s may start exactly when
+// turn[a] == s*da + ra and turn[b] == s*db + rb; it ends with a release-increment of both counters.
+// Warps take 32-group batches of one colour (mutually independent) in increasing (sweep, colour,
+// position) order.  Every dependency of a batch lies in a globally earlier batch and every warp
+// walks its batches in increasing order, so the earliest blocked batch always has its dependencies
+// done or running: no deadlock as long as all warps are co-resident (cooperative launch).  A spin
+// cap turns a would-be hang (a bug) into an error flag.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(TPB) k_velocity_solve_flow(SchedDev sd, const unsigned int* __restrict__ g_rank, Rows R,
+                                                             float4* lam, unsigned int* turn, int iters,
+                                                             unsigned int* err_flags) {
+    const unsigned int np = sd.hdr->n_phases;
+    const unsigned int lane = threadIdx.x & 31;
+    const size_t w = (size_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;  // block-interleaved warp id
+    const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (int s = 0; s <= iters; ++s) {  // s == 0: warm start
+        size_t k = w, pstart = 0;
+        unsigned int p = 0;
+        while (p < np) {
+            const unsigned int cnt = sd.ph_count[p];
+            const size_t nbatch = ((size_t)cnt + 31) >> 5;
+            if (k >= pstart + nbatch) {
+                pstart += nbatch;
+                ++p;
+                continue;
+            }
+            const size_t g = ((k - pstart) << 5) + lane;
+            const bool active = g < cnt;
+            const size_t gbase = sd.ph_gbase[p];
+            int4 info = make_int4(-1, -1, 0, 0);
+            unsigned int rk = 0;
+            if (active) {
+                info = __ldg(&sd.g_info[gbase + g]);
+                rk = __ldg(&g_rank[gbase + g]);
+            }
+            const unsigned int ea = (unsigned int)s * ((rk >> 8) & 0xFFu) + (rk & 0xFFu);
+            const unsigned int eb = (unsigned int)s * (rk >> 24) + ((rk >> 16) & 0xFFu);
+            unsigned int spins = 0;
+            for (;;) {
+                bool ok = true;
+                if (info.x >= 0) ok = ld_acquire_u32(&turn[info.x]) == ea;
+                if (ok && info.y >= 0) ok = ld_acquire_u32(&turn[info.y]) == eb;
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (++spins > NB2_SPIN_LIMIT) {
+                    if (lane == 0) atomicOr(err_flags, 4u);
+                    return;
+                }
+            }
+            if (active) {
+                velocity_group(R, lam, info, sd.ph_rbase[p], cnt, g, s == 0);
+                if (info.x >= 0) red_release_inc(&turn[info.x]);
+                if (info.y >= 0) red_release_inc(&turn[info.y]);
+            }
+            k += n_warps;
         }
     }
 }
@@ -659,6 +733,30 @@ int launch_velocity_solve(Context* ctx, int mode) {
     // piles and hurts tall ones (profiles/r01_notes.md), so the plain order stays the default
     int symmetric = 0;
     if (ctx->step_layout == 1) return launch_velocity_solve_coloured(ctx, sd, R, compact_arrays(ctx, ref));
+    if (!ref && ctx->velocity_kernel >= 2) {
+        int tpb_s, depth_s, blocks_s;
+        if (staged_geometry(ctx, &tpb_s, &depth_s, &blocks_s)) return launch_velocity_solve_staged(ctx, sd, R, tpb_s, depth_s, blocks_s);
+    }
+    if (!ref && ctx->velocity_kernel == 1) {
+        NB2_TRY(coop_limit(ctx, k_velocity_solve_flow, &ctx->coop_blocks_flow));
+        NB2_TRY(ctx->turn.reserve(ctx, (size_t)ctx->n_bodies + 1));
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->turn.p, 0, ((size_t)ctx->n_bodies + 1) * sizeof(unsigned int), ctx->stream));
+        const unsigned int* grank = ctx->vs.g_rank.p;
+        float4* lam_ = ctx->lam.p;
+        unsigned int* turn_ = ctx->turn.p;
+        int iters_ = (int)ctx->params.max_velocity_iterations;
+        unsigned int* err_ = ctx->flags.p;
+        size_t want_ = (ctx->vs.n_items + TPB - 1) / TPB;
+        int blocks_ = (int)(want_ < (size_t)ctx->coop_blocks_flow ? want_ : (size_t)ctx->coop_blocks_flow);
+        if (blocks_ < 1) blocks_ = 1;
+        void* fargs[] = {&sd, &grank, &R, &lam_, &turn_, &iters_, &err_};
+        if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
+        NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_velocity_solve_flow, dim3(blocks_), dim3(TPB), fargs, 0,
+                                                  ctx->stream));
+        if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[7], ctx->stream));
+        ctx->launches++;
+        return NB2_OK;
+    }
     void* args[] = {&sd, &R, &lam, &iters, &warm, &symmetric, &bar};
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_velocity_solve, dim3(blocks), dim3(TPB), args, 0, ctx->stream));

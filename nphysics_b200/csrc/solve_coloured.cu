@@ -4,6 +4,9 @@
 // here -- a phase of the 100k-box pile has only ~6 resident warps per SM, so the kernel is bound by
 // instruction issue latency, not by memory (profiles/r01_notes.md).
 #define NB2_COLOURED_TU 1
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "solve_compact.cuh"
 
 namespace nb2 {
@@ -64,6 +67,366 @@ __global__ void __launch_bounds__(SOLVE_TPB) k_velocity_solve_coloured(SchedDev 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Staged row stream (the default coloured velocity kernel).
+//
+// With a barrier per colour the barrier-to-barrier critical path of the register-pipelined kernel is
+// a chain of dependent DRAM round trips: g_info -> first row -> ... -> twelfth row.  None of those
+// loads depends on what other groups computed: the thread -> group mapping is static, and the row
+// planes (J, M^-1 J, rhs/r/limits, kind) are constant during the solve.  So every thread runs a
+// PRODUCER D entries ahead of its own consumption, across phase and sweep boundaries: it walks the
+// same (sweep, phase, group, row) sequence and copies each row's 7 quads + meta into its private
+// slice of a shared-memory ring with cp.async (16 bytes per lane, coalesced over the group index).
+// While the block waits at a grid barrier the rows of its next groups are already landing.  After
+// the barrier only the mutable data is fetched (the two bodies' mj_lambda and the group's impulses,
+// L2 hits, issued together), then the rows are consumed from shared memory.
+//
+// Ring entry = 8 quads x TPB lanes: planes 0..5 jacobian, 6 header, 7 control.  A group is announced
+// by a header entry (control = its g_info, written with st.shared), followed by its rows (control =
+// the row's meta, copied).  Entries are private to their thread, so cp.async.wait_group is the only
+// synchronisation.  A slot is refilled one consume step after it was read, when the values read
+// from it have already been used.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(unsigned int dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned int dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ unsigned long long g_trace[4096];
+struct StreamPos {
+    int s;           // sweep, 0 = warm start
+    unsigned int p;  // phase
+    unsigned int g;  // group within the phase
+};
+// moves q forward to the first existing group at or after q (thread `tid` owns groups tid, tid+stride, ...)
+__device__ __forceinline__ bool seek_group(StreamPos& q, unsigned int tid, unsigned int np, int iters,
+                                           const unsigned int* s_cnt) {
+    for (;;) {
+        if (q.s > iters) return false;
+        if (q.g < s_cnt[q.p]) return true;
+        q.g = tid;
+        if (++q.p == np) {
+            q.p = 0;
+            ++q.s;
+        }
+    }
+}
+
+// depth (ring entries per thread) and the block size are launch-time values: the launcher sizes the
+// block to the groups an SM owns per phase (one group per thread) and gives the rest of shared
+// memory to the ring.
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {
+    switch (pending) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        case 6: cp_async_wait<6>(); break;
+        case 7: cp_async_wait<7>(); break;
+        case 8: cp_async_wait<8>(); break;
+        case 9: cp_async_wait<9>(); break;
+        case 10: cp_async_wait<10>(); break;
+        default: cp_async_wait<11>(); break;
+    }
+}
+// plane base pointers as kernel parameters (constant bank): one IMAD.WIDE per address
+struct StagedRows {
+    const float4* q[7];  // 6 jacobian planes + header
+    const int2* meta;
+    float* imp;
+};
+#define NB2_STAGED_MAX_DEPTH 13
+#define NB2_STAGED_MIN_DEPTH 3
+#define NB2_STAGED_DEPTH 4
+
+// FLOW: no grid barriers; a group starts when the turn counters of its two bodies say that every
+// earlier visit of those bodies is done (see k_velocity_solve_flow in solve.cu for the argument).
+template <bool FLOW>
+__global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, StagedRows R, float4* lam, int iters, int D,
+                                                                  unsigned int* barrier, int trace,
+                                                                  const unsigned int* __restrict__ g_rank,
+                                                                  unsigned int* turn, unsigned int* err_flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned int TPBK = blockDim.x;
+    float4* ring = reinterpret_cast<float4*>(smem_raw);              // [D][8][TPBK]
+    float* simp = reinterpret_cast<float*>(ring + D * 8 * TPBK);     // [12][TPBK] impulses of the running group
+    unsigned int* s_cnt = reinterpret_cast<unsigned int*>(simp + 12 * TPBK);
+    unsigned int* s_rbase = s_cnt + NB2_MAX_COLOURS;
+    unsigned int* s_gbase = s_rbase + NB2_MAX_COLOURS;
+    const unsigned int np = min(sd.hdr->n_phases, (unsigned int)NB2_MAX_COLOURS);
+    if (np == 0) return;
+    for (unsigned int i = threadIdx.x; i < np; i += TPBK) {
+        s_cnt[i] = sd.ph_count[i];
+        s_rbase[i] = sd.ph_rbase[i];
+        s_gbase[i] = sd.ph_gbase[i];
+    }
+    __syncthreads();
+    GridBarrier gb;
+    gb.init(barrier);
+    const unsigned int t = threadIdx.x, lane = threadIdx.x & 31u;
+    const unsigned int tid = (unsigned int)interleaved_tid();
+    const unsigned int stride = gridDim.x * TPBK;
+    const unsigned int ring_u32 = (unsigned int)__cvta_generic_to_shared(ring) + t * 16u;
+    const unsigned int plane_b = TPBK * 16u, entry_b = 8u * plane_b;
+
+    // ---- producer state: the group being copied, and the one after it (its g_info already in flight)
+    StreamPos pc = {0, 0u, tid}, pn;
+    bool vc = seek_group(pc, tid, np, iters, s_cnt), vn = false;
+    int4 ic = make_int4(-1, -1, 0, 0), in_ = ic;
+    auto fetch_info = [&](const StreamPos& q) -> int4 {
+        int4 v = __ldg(&sd.g_info[s_gbase[q.p] + q.g]);
+        if (FLOW) v.w = (int)__ldg(&g_rank[s_gbase[q.p] + q.g]);
+        return v;
+    };
+    if (vc) {
+        ic = fetch_info(pc);
+        pn = pc;
+        pn.g += stride;
+        vn = seek_group(pn, tid, np, iters, s_cnt);
+        if (vn) in_ = fetch_info(pn);
+    }
+    int pr = -1;  // -1: the header entry of `pc` comes next
+    unsigned int pslot = 0, pcnt = 0;  // row slot being copied and its stride (groups of the phase)
+    auto produce = [&](int e) {
+        if (vc) {
+            const unsigned int dst = ring_u32 + (unsigned int)e * entry_b;
+            if (pr < 0) {
+                reinterpret_cast<int4*>(ring)[(e * 8 + 7) * TPBK + t] = ic;
+                pcnt = s_cnt[pc.p];
+                pslot = s_rbase[pc.p] + pc.g;
+            } else {
+                cp_async16(dst + 1u * plane_b, R.q[1] + pslot);
+                cp_async16(dst + 4u * plane_b, R.q[4] + pslot);
+                if (ic.x >= 0) {
+                    cp_async16(dst, R.q[0] + pslot);
+                    cp_async16(dst + 3u * plane_b, R.q[3] + pslot);
+                }
+                if (ic.y >= 0) {
+                    cp_async16(dst + 2u * plane_b, R.q[2] + pslot);
+                    cp_async16(dst + 5u * plane_b, R.q[5] + pslot);
+                }
+                cp_async16(dst + 6u * plane_b, R.q[6] + pslot);
+                cp_async8(dst + 7u * plane_b, R.meta + pslot);
+                pslot += pcnt;
+            }
+            if (++pr >= (ic.z & 0xFF)) {
+                pc = pn;
+                ic = in_;
+                vc = vn;
+                pr = -1;
+                if (vn) {
+                    pn.g += stride;
+                    vn = seek_group(pn, tid, np, iters, s_cnt);
+                    if (vn) in_ = fetch_info(pn);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (int e = 0; e < D; ++e) produce(e);
+
+    int ce = 0;        // ring entry consumed next
+    bool any = false;  // false until the first entry was consumed (nothing to refill yet)
+    auto take = [&]() -> int {  // makes entry `ce` readable and returns it
+        cp_async_wait_dyn(D - 2);
+        const int e = ce;
+        ce = ce + 1 == D ? 0 : ce + 1;
+        return e;
+    };
+    auto refill_prev = [&](int e) {  // refills the entry consumed one step ago
+        if (any) produce(e == 0 ? D - 1 : e - 1);
+        any = true;
+    };
+
+    for (int s = 0; s <= iters; ++s) {
+        for (unsigned int p = 0; p < np; ++p) {
+            const unsigned int cnt = s_cnt[p];
+            const unsigned int rbase = s_rbase[p];
+            for (unsigned int gw = tid - lane; gw < cnt; gw += stride) {  // warp-uniform trip count
+                const unsigned int g = gw + lane;
+                const bool active = g < cnt;
+                int e = 0;
+                int4 info = make_int4(-1, -1, 0, 0);
+                if (active) {
+                    e = take();
+                    info = reinterpret_cast<const int4*>(ring)[(e * 8 + 7) * TPBK + t];
+                }
+                const bool a = info.x >= 0, b = info.y >= 0;
+                if (FLOW) {
+                    const unsigned int rk = (unsigned int)info.w;
+                    const unsigned int ea = (unsigned int)s * ((rk >> 8) & 0xFFu) + (rk & 0xFFu);
+                    const unsigned int eb = (unsigned int)s * (rk >> 24) + ((rk >> 16) & 0xFFu);
+                    unsigned int spins = 0;
+                    for (;;) {
+                        bool ok = true;
+                        if (a) ok = ld_acquire_u32(&turn[info.x]) == ea;
+                        if (ok && b) ok = ld_acquire_u32(&turn[info.y]) == eb;
+                        if (__all_sync(0xffffffffu, ok)) break;
+                        if (++spins > NB2_SPIN_LIMIT) {
+                            if (lane == 0) atomicOr(err_flags, 4u);
+                            cp_async_wait<0>();
+                            return;
+                        }
+                    }
+                }
+                if (!active) continue;
+                const int nrows = info.z & 0xFF;
+                const int ncc = (info.z >> 8) == NB2_ITEM_CONTACTS ? nrows / 3 : 0;
+                // the mutable data of the group, all loads in flight together: mj_lambda of both bodies and
+                // the group's impulses (same thread wrote them a sweep ago)
+                Lam la, lb;
+                if (a) la = load_lam(lam, info.x);
+                if (b) lb = load_lam(lam, info.y);
+                {
+                    float v[12];
+#pragma unroll
+                    for (int r = 0; r < 12; ++r)
+                        if (r < nrows) v[r] = __ldcg(&R.imp[rbase + (unsigned int)r * cnt + g]);
+                    refill_prev(e);
+#pragma unroll
+                    for (int r = 0; r < 12; ++r)
+                        if (r < nrows) simp[r * TPBK + t] = v[r];
+                }
+                unsigned int cslot = rbase + g;
+#pragma unroll 1
+                for (int r = 0; r < nrows; ++r, cslot += cnt) {
+                    e = take();
+                    RowPkt k;
+                    const float4* q = ring + (e * 8) * TPBK + t;
+                    k.q0 = q[0 * TPBK];
+                    k.q1 = q[1 * TPBK];
+                    k.q2 = q[2 * TPBK];
+                    k.q3 = q[3 * TPBK];
+                    k.q4 = q[4 * TPBK];
+                    k.q5 = q[5 * TPBK];
+                    k.h = q[6 * TPBK];
+                    k.meta = *reinterpret_cast<const int2*>(q + 7 * TPBK);
+                    k.imp = simp[r * TPBK + t];
+                    refill_prev(e);
+                    if (k.meta.x == NB2_ROW_NONE) continue;
+                    RowJ J;
+                    unpack_pkt(k, true, true, &J);  // unconditional: pure register renaming (absent sides are never used)
+                    if (s == 0) {
+                        if (k.imp != 0.f) {
+                            if (a) axpy6(k.imp, J.W1, la.v);
+                            if (b) axpy6(k.imp, J.W2, lb.v);
+                        }
+                        continue;
+                    }
+                    float dep = 0.f;
+                    if (k.meta.x == NB2_ROW_DEPENDENT) {
+                        // coloured contact groups hold their own normal rows (rows 2*ncc..3*ncc-1), not yet
+                        // updated in this visit: friction rows come first
+                        dep = r < 2 * ncc ? simp[(2 * ncc + (r >> 1)) * TPBK + t] : __ldcg(&R.imp[k.meta.y]);
+                    }
+                    const float ni = solve_row(k.meta.x, k.h, k.imp, dep, J, a, b, &la, &lb);
+                    if (ni != k.imp) __stcg(&R.imp[cslot], ni);
+                }
+                if (a) store_lam(lam, info.x, la);
+                if (b) store_lam(lam, info.y, lb);
+                if (FLOW) {
+                    if (a) red_release_inc(&turn[info.x]);
+                    if (b) red_release_inc(&turn[info.y]);
+                }
+            }
+            if (!FLOW) gb.sync();
+            if (!FLOW && trace && blockIdx.x == 0 && threadIdx.x == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (s * np + p < 4096) g_trace[s * np + p] = now;
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if (!FLOW && trace && blockIdx.x == 0 && threadIdx.x == 0)
+        for (unsigned int i = 1; i < min((iters + 1) * np, 4096u); ++i)
+            if (i / np == (unsigned int)trace)
+                printf("sweep %u phase %u groups %u dt_ns %llu\n", i / np, i % np, s_cnt[i % np], g_trace[i] - g_trace[i - 1]);
+}
+
+static size_t staged_smem(int depth, int tpb) {
+    return (size_t)depth * 8 * tpb * 16 + 12 * (size_t)tpb * 4 + 3 * NB2_MAX_COLOURS * 4;
+}
+
+// Chooses block size and ring depth for the staged kernel; false = the scene is too large for one
+// group per thread and the register-pipelined kernel (many warps per SM) is the better fit.
+bool staged_geometry(Context* ctx, int* tpb_out, int* depth_out, int* blocks_out) {
+    // groups per phase: the balanced colouring evens the colours out; the colour count is last step's
+    // (an asynchronous copy of the schedule header, never waited for), 8 before the first step
+    unsigned int np = ctx->host_hdr ? ((volatile SchedHeader*)ctx->host_hdr)->n_phases : 0;
+    size_t groups = ctx->host_hdr ? ((volatile SchedHeader*)ctx->host_hdr)->n_groups : 0;
+    if (np == 0 || np > NB2_MAX_COLOURS) np = 8;
+    if (groups == 0 || groups > ctx->vs.n_items) groups = ctx->vs.n_items;
+    const size_t per_phase = (groups + np - 1) / np;
+    const size_t padded = per_phase + per_phase / 16 + 32;  // balancing tolerance
+    // one warp of groups per block until every SM has a block, then wider blocks
+    size_t blocks = (padded + 31) / 32;
+    if (blocks > (size_t)ctx->sm_count) blocks = ctx->sm_count;
+    if (blocks < 1) blocks = 1;
+    const size_t per_block = (padded + blocks - 1) / blocks;
+    int tpb = (int)((per_block + 31) / 32) * 32;
+    if (const char* f = getenv("NB2_STAGED_TPB")) tpb = atoi(f);
+    if (tpb > 384) return false;
+    if (tpb < 32) tpb = 32;
+    // measured on the 100k-box pile (224 threads): depth 3 / 4 / 5 / 7 -> 1.19 / 1.17 / 1.20 / 1.34 ms; a deeper
+    // ring fetches the next phase's rows while the current phase still waits for its own
+    int depth = NB2_STAGED_DEPTH;
+    while (depth > NB2_STAGED_MIN_DEPTH && staged_smem(depth, tpb) > ctx->smem_optin) --depth;
+    if (const char* f = getenv("NB2_STAGED_DEPTH")) depth = atoi(f);
+    *blocks_out = (int)blocks;
+    *tpb_out = tpb;
+    *depth_out = depth;
+    return true;
+}
+
+int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd_in, const Rows& R_in, int tpb, int depth, int blocks) {
+    SchedDev sd = sd_in;
+    StagedRows R;
+    for (int k = 0; k < 6; ++k) R.q[k] = R_in.jac + (size_t)k * R_in.S;
+    R.q[6] = R_in.hdr;
+    R.meta = R_in.meta;
+    R.imp = R_in.imp;
+    const size_t smem = staged_smem(depth, tpb);
+    const bool flow = ctx->velocity_kernel == 3;
+    if (!ctx->staged_attr) {
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)ctx->smem_optin));
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)ctx->smem_optin));
+        ctx->staged_attr = true;
+    }
+    float4* lam = ctx->lam.p;
+    int iters = (int)ctx->params.max_velocity_iterations;
+    unsigned int* bar = ctx->barrier.p;
+    static const int trace = getenv("NB2_TRACE_PHASES") ? atoi(getenv("NB2_TRACE_PHASES")) : 0;
+    int tr = trace;
+    const unsigned int* grank = ctx->vs.g_rank.p;
+    unsigned int* turn = nullptr;
+    unsigned int* err = ctx->flags.p;
+    if (flow) {
+        NB2_TRY(ctx->turn.reserve(ctx, (size_t)ctx->n_bodies + 1));
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->turn.p, 0, ((size_t)ctx->n_bodies + 1) * sizeof(unsigned int), ctx->stream));
+        turn = ctx->turn.p;
+    }
+    void* args[] = {&sd, &R, &lam, &iters, &depth, &bar, &tr, &grank, &turn, &err};
+    if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
+    NB2_CUDA(ctx, cudaLaunchCooperativeKernel(flow ? (void*)k_velocity_solve_staged<true> : (void*)k_velocity_solve_staged<false>,
+                                              dim3(blocks), dim3(tpb), args, smem, ctx->stream));
+    if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[7], ctx->stream));
+    ctx->launches++;
+    return NB2_OK;
+}
 
 template <typename K>
 static int coop_limit_c(Context* ctx, K kernel, int* cache) {

@@ -179,6 +179,17 @@ __device__ __forceinline__ void unpack_pkt(const RowPkt& k, bool a, bool b, RowJ
         o->W2[0] = k.q4.z; o->W2[1] = k.q4.w; o->W2[2] = k.q5.x; o->W2[3] = k.q5.y; o->W2[4] = k.q5.z; o->W2[5] = k.q5.w;
     }
 }
+// per-body turn counters of the barrier-free (dataflow) kernels
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_inc(unsigned int* p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+#define NB2_SPIN_LIMIT (1u << 22)
+
 // Warps are dealt to groups block-interleaved (warp w of block b is global warp w*gridDim+b) so a
 // phase with fewer groups than threads still spreads evenly over all SMs.
 __device__ __forceinline__ size_t interleaved_tid() {
