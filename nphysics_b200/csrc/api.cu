@@ -37,14 +37,14 @@ static void release_all(Context* c) {
     for (int k = 0; k < 2; ++k) {
         c->imp[k].release();
         c->ht_keys[k].release();
-        c->ht_vals[k].release();
+        c->ht_imps[k].release();
     }
     c->vs.release(); c->ps.release(); c->deg.release(); c->adj_off.release(); c->cursor.release();
     c->adj.release(); c->pred_a.release(); c->pred_b.release(); c->level.release(); c->adj_off_p.release();
     c->adj_p.release(); c->cmask.release(); c->best.release(); c->scan_tmp.release(); c->barrier.release();
     c->r_jac.release(); c->r_hdr.release(); c->r_meta.release(); c->r_imp.release(); c->p_row.release();
     c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
-    c->c_geo.release(); c->turn.release(); c->turn_p.release(); c->bal.release();
+    c->c_geo.release(); c->turn.release(); c->turn_p.release(); c->bal.release(); c->p_hdr.release(); c->slot_src.release();
     if (c->host_hdr) cudaFreeHost(c->host_hdr);
     c->host_hdr = nullptr;
 }

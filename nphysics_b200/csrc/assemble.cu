@@ -138,15 +138,17 @@ struct RowOut {
 __device__ __forceinline__ void write_row(const RowOut& o, size_t slot, const float* J1, const float* J2,
                                           const float* W1, const float* W2, float rhs, float r, float lo, float hi,
                                           int kind, int dep, float impulse) {
+    // streaming stores: half a gigabyte of rows must not evict the bodies, manifolds and hash table
+    // the other threads of this kernel are still reading through L2
     const size_t S = o.n_slots_max;
-    o.jac[0 * S + slot] = make_float4(J1[0], J1[1], J1[2], J1[3]);
-    o.jac[1 * S + slot] = make_float4(J1[4], J1[5], J2[0], J2[1]);
-    o.jac[2 * S + slot] = make_float4(J2[2], J2[3], J2[4], J2[5]);
-    o.jac[3 * S + slot] = make_float4(W1[0], W1[1], W1[2], W1[3]);
-    o.jac[4 * S + slot] = make_float4(W1[4], W1[5], W2[0], W2[1]);
-    o.jac[5 * S + slot] = make_float4(W2[2], W2[3], W2[4], W2[5]);
-    o.hdr[slot] = make_float4(rhs, r, lo, hi);
-    o.meta[slot] = make_int2(kind, dep);
+    __stcs(&o.jac[0 * S + slot], make_float4(J1[0], J1[1], J1[2], J1[3]));
+    __stcs(&o.jac[1 * S + slot], make_float4(J1[4], J1[5], J2[0], J2[1]));
+    __stcs(&o.jac[2 * S + slot], make_float4(J2[2], J2[3], J2[4], J2[5]));
+    __stcs(&o.jac[3 * S + slot], make_float4(W1[0], W1[1], W1[2], W1[3]));
+    __stcs(&o.jac[4 * S + slot], make_float4(W1[4], W1[5], W2[0], W2[1]));
+    __stcs(&o.jac[5 * S + slot], make_float4(W2[2], W2[3], W2[4], W2[5]));
+    __stcs(&o.hdr[slot], make_float4(rhs, r, lo, hi));
+    __stcs(&o.meta[slot], make_int2(kind, dep));
     o.imp[slot] = impulse;
 }
 
@@ -175,14 +177,17 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33;
     return x;
 }
-__device__ __forceinline__ bool ht_lookup(const unsigned long long* keys, const unsigned int* vals, size_t cap,
-                                          unsigned long long key, unsigned int* out) {
+// Open-addressing table keyed by the 64-bit contact key; the cached impulses sit in a parallel
+// float4 array at the same index, so a lookup issues both loads at once (one round trip per probe).
+__device__ __forceinline__ bool ht_lookup(const unsigned long long* __restrict__ keys, const float4* __restrict__ imps,
+                                          size_t cap, unsigned long long key, float4* out) {
     if (cap == 0) return false;
     size_t h = (size_t)mix64(key) & (cap - 1);
     for (size_t probe = 0; probe < cap; ++probe) {
-        unsigned long long k = keys[h];
+        const unsigned long long k = keys[h];
+        const float4 v = imps[h];
         if (k == key) {
-            *out = vals[h];
+            *out = v;
             return true;
         }
         if (k == 0ull) return false;
@@ -190,17 +195,65 @@ __device__ __forceinline__ bool ht_lookup(const unsigned long long* keys, const 
     }
     return false;
 }
-__device__ __forceinline__ void ht_insert(unsigned long long* keys, unsigned int* vals, size_t cap,
-                                          unsigned long long key, unsigned int val) {
+__device__ __forceinline__ void ht_insert(unsigned long long* keys, float4* imps, size_t cap, unsigned long long key,
+                                          float4 val) {
     size_t h = (size_t)mix64(key) & (cap - 1);
     for (size_t probe = 0; probe < cap; ++probe) {
         unsigned long long prev = atomicCAS(&keys[h], 0ull, key);
         if (prev == 0ull || prev == key) {
-            vals[h] = val;
+            imps[h] = val;
             return;
         }
         h = (h + 1) & (cap - 1);
     }
+}
+
+// ---------------------------------------------------------------- slot resolution (coloured mode)
+// One thread per (phase, contact lane, group) position slot, in ELL order: walks the index chain
+// g_info -> item -> chunk -> manifold -> first contact once, in a kernel light enough to run at full
+// occupancy, and leaves (contact, manifold, phase | lane << 8 | contacts << 12, group) for the
+// assembly and impulse-cache kernels, which then start from one coalesced load.  Lane 0 also writes
+// the group header of the staged position kernel (bodies, collider-to-body poses).
+__global__ void __launch_bounds__(TPB) k_resolve_slots(const nb2_manifold* __restrict__ manifolds,
+                                                       const unsigned int* __restrict__ chunk_base,
+                                                       const unsigned int* __restrict__ chunk_manifold, SchedView vs,
+                                                       int4* slot_src, float4* p_hdr, size_t n_ghdr_max) {
+    const size_t T = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int np = vs.hdr->n_phases;
+    if (np == 0 || T >= (size_t)NB2_CHUNK * vs.ph_gbase[np]) return;
+    unsigned int lo = 0, hi = np;  // largest p with NB2_CHUNK * gbase[p] <= T
+    while (hi - lo > 1) {
+        unsigned int mid = (lo + hi) >> 1;
+        if ((size_t)NB2_CHUNK * vs.ph_gbase[mid] <= T) lo = mid; else hi = mid;
+    }
+    const unsigned int p = lo, cnt = vs.ph_count[p];
+    const size_t local = T - (size_t)NB2_CHUNK * vs.ph_gbase[p];
+    const unsigned int lane = (unsigned int)(local / cnt), g = (unsigned int)(local % cnt);
+    const int4 gi = vs.g_info[vs.ph_gbase[p] + g];
+    int4 res = make_int4(-1, 0, (int)(p | (lane << 8)), (int)g);
+    if ((gi.z >> 8) == NB2_ITEM_CONTACTS) {
+        const unsigned int chunk = (unsigned int)vs.it_src[gi.w];
+        const unsigned int m = chunk_manifold[chunk];
+        const unsigned int lchunk = chunk - chunk_base[m];
+        const nb2_manifold& mh = manifolds[m];
+        const int left = (int)mh.num_contacts - (int)(NB2_CHUNK * lchunk);
+        const int ncc = min(NB2_CHUNK, left);
+        res.y = (int)m;
+        res.z |= ncc << 12;
+        res.x = (int)lane < left ? (int)(mh.first_contact + NB2_CHUNK * lchunk + lane) : -2;  // -2: padding lane
+        if (lane == 0) {
+            const size_t gs = (size_t)vs.ph_gbase[p] + g;
+            const float* k1 = mh.coll1_wrt_body;
+            const float* k2 = mh.coll2_wrt_body;
+            p_hdr[0 * n_ghdr_max + gs] = make_float4(__int_as_float((int)mh.body1), __int_as_float((int)mh.body2),
+                                                     __int_as_float((int)m), 0.f);
+            p_hdr[1 * n_ghdr_max + gs] = make_float4(k1[0], k1[1], k1[2], k1[3]);
+            p_hdr[2 * n_ghdr_max + gs] = make_float4(k1[4], k1[5], k1[6], 0.f);
+            p_hdr[3 * n_ghdr_max + gs] = make_float4(k2[0], k2[1], k2[2], k2[3]);
+            p_hdr[4 * n_ghdr_max + gs] = make_float4(k2[4], k2[5], k2[6], 0.f);
+        }
+    }
+    slot_src[T] = res;
 }
 
 // ---------------------------------------------------------------- contacts
@@ -208,45 +261,36 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     int mode, unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
     const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
     const unsigned int* __restrict__ chunk_base, const unsigned int* __restrict__ chunk_manifold, BodyArrays B,
-    SchedView vs, SchedView ps, RowOut out, float4* p_row, size_t n_pslots_max, float4* c_geo,
-    const unsigned long long* __restrict__ ht_keys,
-    const unsigned int* __restrict__ ht_vals, size_t ht_cap, const float4* __restrict__ imp_prev,
+    SchedView vs, SchedView ps, RowOut out, float4* p_row, size_t n_pslots_max, float4* p_hdr, size_t n_ghdr_max,
+    float4* c_geo,
+    const int4* __restrict__ slot_src, const unsigned long long* __restrict__ ht_keys,
+    const float4* __restrict__ ht_imps, size_t ht_cap,
     float warmstart_coeff, float restitution_threshold, float inv_dt, int compact_layout) {
-    unsigned int ci;
+    unsigned int ci, m;
+    unsigned int sp = 0, sg = 0, scnt = 0;  // coloured: phase, group, groups of the phase
     if (mode == NB2_MODE_COLOURED) {
         // Gather formulation: threads enumerate the (phase, contact lane, group) slots in ELL order,
         // so the row planes are WRITTEN with consecutive threads on consecutive 16-byte words; the
-        // scattered side is the read of the 112-byte contact record.
+        // scattered side is the read of the 112-byte contact record.  k_resolve_slots did the index walk.
         const size_t T = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
         const unsigned int np = vs.hdr->n_phases;
         if (np == 0 || T >= (size_t)NB2_CHUNK * vs.ph_gbase[np]) return;
-        unsigned int lo = 0, hi = np;  // largest p with NB2_CHUNK * gbase[p] <= T
-        while (hi - lo > 1) {
-            unsigned int mid = (lo + hi) >> 1;
-            if ((size_t)NB2_CHUNK * vs.ph_gbase[mid] <= T) lo = mid; else hi = mid;
-        }
-        const unsigned int p = lo, cnt = vs.ph_count[p];
-        const size_t local = T - (size_t)NB2_CHUNK * vs.ph_gbase[p];
-        const unsigned int lane = (unsigned int)(local / cnt), g = (unsigned int)(local % cnt);
-        const int item = vs.g_info[vs.ph_gbase[p] + g].w;
-        if (vs.it_type[item] != NB2_ITEM_CONTACTS) return;
-        const unsigned int chunk_ = (unsigned int)vs.it_src[item];
-        const unsigned int m_ = chunk_manifold[chunk_];
-        const unsigned int lchunk = chunk_ - chunk_base[m_];
-        if (NB2_CHUNK * lchunk + lane >= manifolds[m_].num_contacts) {
-            // fewer than 4 contacts in this chunk: flag the lane's compact record invalid
-            if (compact_layout)
-                c_geo[4 * n_pslots_max + (size_t)NB2_CHUNK * vs.ph_gbase[p] + (size_t)lane * cnt + g] =
-                    make_float4(0.f, 0.f, 0.f, 0.f);
-            return;
-        }
-        ci = manifolds[m_].first_contact + NB2_CHUNK * lchunk + lane;
+        const int4 src = slot_src[T];
+        if (src.x == -2 && compact_layout)  // fewer than 4 contacts in this chunk: flag the lane's compact record invalid
+            c_geo[4 * n_pslots_max + T] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src.x < 0) return;
+        ci = (unsigned int)src.x;
+        m = (unsigned int)src.y;
+        sp = (unsigned int)src.z & 0xFFu;
+        sg = (unsigned int)src.w;
+        scnt = vs.ph_count[sp];
     } else {
         ci = blockIdx.x * blockDim.x + threadIdx.x;
+        if (ci >= nC) return;
+        m = c_manifold[ci];
+        if (m == 0xFFFFFFFFu) return;
     }
     if (ci >= nC) return;
-    const unsigned int m = c_manifold[ci];
-    if (m == 0xFFFFFFFFu) return;
     const nb2_manifold& mf = manifolds[m];
     const nb2_contact& c = contacts[ci];
     BodySide s1, s2;
@@ -267,20 +311,21 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     // impulse cache lookup (signorini_coulomb_pyramid_model.rs:104-108)
     float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c.key != 0ull) {
-        unsigned int prev;
-        if (ht_lookup(ht_keys, ht_vals, ht_cap, c.key, &prev)) cached = imp_prev[prev];
+        float4 prev;
+        if (ht_lookup(ht_keys, ht_imps, ht_cap, c.key, &prev)) cached = prev;
     }
 
     const bool compact = compact_layout != 0;
     size_t slot_n = 0, slot_t1 = 0, slot_t2 = 0, pslot;
-    if (compact) {
-        pslot = vs.pos_slot((size_t)nJ + chunk, lcc);
-    } else if (mode == NB2_MODE_COLOURED) {
-        size_t item = (size_t)nJ + chunk;
-        slot_t1 = vs.row_slot(item, 2 * lcc);
-        slot_t2 = vs.row_slot(item, 2 * lcc + 1);
-        slot_n = vs.row_slot(item, 2 * ncc + lcc);
-        pslot = vs.pos_slot(item, lcc);
+    if (mode == NB2_MODE_COLOURED) {
+        // this thread IS position slot (sp, lcc, sg); the velocity rows of the group follow from it
+        pslot = (size_t)NB2_CHUNK * vs.ph_gbase[sp] + (size_t)lcc * scnt + sg;
+        if (!compact) {
+            const size_t rb = (size_t)vs.ph_rbase[sp] + sg;
+            slot_t1 = rb + (size_t)(2 * lcc) * scnt;
+            slot_t2 = rb + (size_t)(2 * lcc + 1) * scnt;
+            slot_n = rb + (size_t)(2 * ncc + lcc) * scnt;
+        }
     } else {
         size_t item_f = (size_t)nJ + chunk, item_n = (size_t)nJ + maxc + chunk;
         slot_t1 = vs.row_slot(item_f, 2 * lcc);
@@ -332,11 +377,11 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     const Quat q1 = f4_quat(B.pos_q[mf.body1]);
     const Vec3 normal1 = quat_inv_rotate(q1, n);
     const size_t P = n_pslots_max;
-    p_row[0 * P + pslot] = make_float4(c.local1[0], c.local1[1], c.local1[2], c.dilation1 + mf.margin1);
-    p_row[1 * P + pslot] = make_float4(c.local2[0], c.local2[1], c.local2[2], c.dilation2 + mf.margin2);
-    p_row[2 * P + pslot] = make_float4(c.dir1[0], c.dir1[1], c.dir1[2], __int_as_float((int)c.geom1));
-    p_row[3 * P + pslot] = make_float4(c.dir2[0], c.dir2[1], c.dir2[2], __int_as_float((int)c.geom2));
-    p_row[4 * P + pslot] = make_float4(normal1.x, normal1.y, normal1.z, 0.f);
+    __stcs(&p_row[0 * P + pslot], make_float4(c.local1[0], c.local1[1], c.local1[2], c.dilation1 + mf.margin1));
+    __stcs(&p_row[1 * P + pslot], make_float4(c.local2[0], c.local2[1], c.local2[2], c.dilation2 + mf.margin2));
+    __stcs(&p_row[2 * P + pslot], make_float4(c.dir1[0], c.dir1[1], c.dir1[2], __int_as_float((int)c.geom1)));
+    __stcs(&p_row[3 * P + pslot], make_float4(c.dir2[0], c.dir2[1], c.dir2[2], __int_as_float((int)c.geom2)));
+    __stcs(&p_row[4 * P + pslot], make_float4(normal1.x, normal1.y, normal1.z, 0.f));
 }
 
 // ---------------------------------------------------------------- joints
@@ -521,7 +566,7 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
     const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
     const unsigned int* __restrict__ chunk_base, const int* __restrict__ status, SchedView vs,
     const float* __restrict__ r_imp, const float4* __restrict__ c_geo, size_t n_pslots_max, float4* imp_cur,
-    unsigned long long* ht_keys, unsigned int* ht_vals, size_t ht_cap, int compact_layout) {
+    unsigned long long* ht_keys, float4* ht_imps, size_t ht_cap, int compact_layout) {
     unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= nC) return;
     const unsigned int m = c_manifold[ci];
@@ -553,7 +598,7 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
     }
     imp_cur[ci] = v;
     const unsigned long long key = contacts[ci].key;
-    if (key != 0ull) ht_insert(ht_keys, ht_vals, ht_cap, key, ci);
+    if (key != 0ull) ht_insert(ht_keys, ht_imps, ht_cap, key, v);
 }
 
 __global__ void __launch_bounds__(TPB) k_cache_joint_impulses(unsigned int nJ, nb2_joint* joints, SchedView vs,
@@ -637,6 +682,9 @@ int launch_assemble(Context* ctx, int mode) {
     NB2_TRY(ctx->p_row.reserve(ctx, 5 * pslots));
     ctx->n_pslots_max = ctx->p_row.cap / 5;
     NB2_TRY(ctx->c_geo.reserve(ctx, ctx->step_layout == 0 ? 16 : 5 * ctx->n_pslots_max));
+    NB2_TRY(ctx->p_hdr.reserve(ctx, ref ? 16 : 5 * (n_items + 16)));
+    ctx->n_ghdr_max = ctx->p_hdr.cap / 5;
+    NB2_TRY(ctx->slot_src.reserve(ctx, ref ? 16 : (size_t)NB2_CHUNK * n_items + 16));
     SchedView vs = view_of(ctx->vs);
     SchedView ps = ref ? view_of(ctx->ps) : vs;
     const int prev = 1 - ctx->cur;
@@ -648,11 +696,17 @@ int launch_assemble(Context* ctx, int mode) {
     if (ctx->n_contacts) {
         // coloured: one thread per (group, contact lane) slot in ELL order; reference: one per contact
         const size_t nthreads = ref ? (size_t)ctx->n_contacts : (size_t)NB2_CHUNK * n_items;
+        if (!ref) {
+            k_resolve_slots<<<nblk(nthreads), TPB, 0, ctx->stream>>>(ctx->manifolds.p, ctx->chunk_base.p,
+                                                                      ctx->chunk_manifold.p, vs, ctx->slot_src.p,
+                                                                      ctx->p_hdr.p, ctx->n_ghdr_max);
+            ctx->launches++;
+        }
         k_assemble_contacts<<<nblk(nthreads), TPB, 0, ctx->stream>>>(
             mode, ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p,
             ctx->c_manifold.p, ctx->chunk_base.p, ctx->chunk_manifold.p, body_arrays(ctx), vs, ps, row_out(ctx),
             ctx->p_row.p,
-            ctx->n_pslots_max, ctx->c_geo.p, ctx->ht_keys[prev].p, ctx->ht_vals[prev].p, ctx->ht_cap[prev], ctx->imp[prev].p,
+            ctx->n_pslots_max, ctx->p_hdr.p, ctx->n_ghdr_max, ctx->c_geo.p, ctx->slot_src.p, ctx->ht_keys[prev].p, ctx->ht_imps[prev].p, ctx->ht_cap[prev],
             ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt, ctx->step_layout);
         ctx->launches++;
     }
@@ -671,7 +725,7 @@ int launch_cache_impulses(Context* ctx, int mode) {
     NB2_TRY(ctx->imp[cur].reserve(ctx, ctx->n_contacts + 1));
     if (cap) {
         NB2_TRY(ctx->ht_keys[cur].reserve(ctx, cap));
-        NB2_TRY(ctx->ht_vals[cur].reserve(ctx, cap));
+        NB2_TRY(ctx->ht_imps[cur].reserve(ctx, cap));
         NB2_CUDA(ctx, cudaMemsetAsync(ctx->ht_keys[cur].p, 0, cap * sizeof(unsigned long long), ctx->stream));
     }
     ctx->ht_cap[cur] = cap;
@@ -682,7 +736,7 @@ int launch_cache_impulses(Context* ctx, int mode) {
             mode, ctx->n_contacts, ctx->n_joints, (unsigned int)ctx->max_chunks, ctx->manifolds.p, ctx->contacts.p,
             ctx->c_manifold.p, ctx->chunk_base.p, ctx->b_status.p, vs, ctx->r_imp.p, ctx->c_geo.p, ctx->n_pslots_max,
             ctx->imp[cur].p,
-            ctx->ht_keys[cur].p, ctx->ht_vals[cur].p, cap, ctx->step_layout);
+            ctx->ht_keys[cur].p, ctx->ht_imps[cur].p, cap, ctx->step_layout);
         ctx->launches++;
     }
     if (ctx->n_joints) {

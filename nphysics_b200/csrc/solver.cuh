@@ -189,7 +189,8 @@ struct Context {
     // impulse cache: double-buffered (previous step -> this step)
     DevBuf<float4> imp[2];
     DevBuf<unsigned long long> ht_keys[2];
-    DevBuf<unsigned int> ht_vals[2];
+    DevBuf<float4> ht_imps[2];       // cached impulses (normal, tangent 1, tangent 2) at the key's index
+    DevBuf<int4> slot_src;           // coloured: per position slot (contact, manifold, phase | lane << 8 | contacts << 12, group)
     size_t ht_cap[2] = {0, 0};  // power of two (0 = empty cache)
     uint32_t imp_n[2] = {0, 0};
     int cur = 0;                // buffer written by the current step
@@ -236,7 +237,9 @@ struct Context {
     // streamed through a shared-memory ring with cp.async, prefetched across the phase barrier)
     int velocity_kernel = 2;
     size_t smem_optin = 0;         // cudaDevAttrMaxSharedMemoryPerBlockOptin
-    bool staged_attr = false;
+    bool staged_attr = false, staged_pos_attr = false;
+    DevBuf<float4> p_hdr;          // [5][n_ghdr_max] coloured position groups: bodies + collider-to-body poses
+    size_t n_ghdr_max = 0;
     void* host_hdr = nullptr;      // pinned copy of vs.hdr (launch-geometry hint, never waited for)
     DevBuf<unsigned int> turn, turn_p;
     DevBuf<unsigned int> bal;       // groups per colour while balancing
