@@ -42,9 +42,9 @@ static void release_all(Context* c) {
     c->vs.release(); c->ps.release(); c->deg.release(); c->adj_off.release(); c->cursor.release();
     c->adj.release(); c->pred_a.release(); c->pred_b.release(); c->level.release(); c->adj_off_p.release();
     c->adj_p.release(); c->cmask.release(); c->best.release(); c->scan_tmp.release(); c->barrier.release();
-    c->r_jac.release(); c->r_hdr.release(); c->r_meta.release(); c->r_imp.release(); c->p_row.release();
+    c->r_jac.release(); c->r_hdr.release(); c->r_imp.release(); c->p_row.release();
     c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
-    c->c_geo.release(); c->turn.release(); c->turn_p.release(); c->bal.release(); c->p_hdr.release(); c->slot_src.release();
+    c->c_geo.release(); c->bal.release(); c->p_hdr.release(); c->slot_src.release();
     if (c->host_hdr) cudaFreeHost(c->host_hdr);
     c->host_hdr = nullptr;
 }
@@ -66,7 +66,6 @@ static int check_flags(Context* ctx) {
     ctx->last_stats.n_phases_velocity = hv.n_phases;
     ctx->last_stats.n_phases_position = ctx->last_mode == NB2_MODE_REFERENCE_ORDER ? hp.n_phases : hv.n_phases;
     if (f & 1u) return set_error(ctx, NB2_ERR_BAD_INDEX, "a manifold/joint record referenced a body or contact out of range");
-    if (f & 4u) return set_error(ctx, NB2_ERR_CUDA, "internal: dataflow solve exceeded its spin limit (dependency never satisfied)");
     if (f & 2u) return set_error(ctx, NB2_ERR_UNSUPPORTED, "a manifold/joint connects a body to itself (unsupported)");
     if ((hv.overflow | hp.overflow) & 1u)
         return set_error(ctx, NB2_ERR_TOO_MANY_COLOURS, "colouring needs more than %d colours", NB2_MAX_COLOURS);

@@ -129,9 +129,8 @@ __device__ __forceinline__ void fill_side(const BodySide& s, Vec3 point, bool an
 }
 
 struct RowOut {
-    float4* jac;   // [6][n_slots_max]
+    float4* jac;   // [NB2_ROW_PLANES][n_slots_max], layout in solve_common.cuh
     float4* hdr;
-    int2* meta;
     float* imp;
     size_t n_slots_max;
 };
@@ -139,16 +138,15 @@ __device__ __forceinline__ void write_row(const RowOut& o, size_t slot, const fl
                                           const float* W1, const float* W2, float rhs, float r, float lo, float hi,
                                           int kind, int dep, float impulse) {
     // streaming stores: half a gigabyte of rows must not evict the bodies, manifolds and hash table
-    // the other threads of this kernel are still reading through L2
+    // the other threads of this kernel are still reading through L2.  The linear part of WJ is not
+    // stored (the solve kernels rebuild it as J.lin * inv_mass, the product fill_side formed).
     const size_t S = o.n_slots_max;
     __stcs(&o.jac[0 * S + slot], make_float4(J1[0], J1[1], J1[2], J1[3]));
     __stcs(&o.jac[1 * S + slot], make_float4(J1[4], J1[5], J2[0], J2[1]));
     __stcs(&o.jac[2 * S + slot], make_float4(J2[2], J2[3], J2[4], J2[5]));
-    __stcs(&o.jac[3 * S + slot], make_float4(W1[0], W1[1], W1[2], W1[3]));
-    __stcs(&o.jac[4 * S + slot], make_float4(W1[4], W1[5], W2[0], W2[1]));
-    __stcs(&o.jac[5 * S + slot], make_float4(W2[2], W2[3], W2[4], W2[5]));
+    __stcs(&o.jac[3 * S + slot], make_float4(W1[3], W1[4], W1[5], W2[3]));
+    __stcs(&o.jac[4 * S + slot], make_float4(W2[4], W2[5], __int_as_float(kind), __int_as_float(dep)));
     __stcs(&o.hdr[slot], make_float4(rhs, r, lo, hi));
-    __stcs(&o.meta[slot], make_int2(kind, dep));
     o.imp[slot] = impulse;
 }
 
@@ -462,7 +460,7 @@ __global__ void __launch_bounds__(TPB) k_assemble_joints(unsigned int nJ, const 
         ++r;
     };
     auto skip = [&]() {
-        out.meta[vs.row_slot(ji, r)] = make_int2(NB2_ROW_NONE, 0);
+        out.jac[4 * out.n_slots_max + vs.row_slot(ji, r)] = make_float4(0.f, 0.f, __int_as_float(NB2_ROW_NONE), 0.f);
         out.imp[vs.row_slot(ji, r)] = 0.f;
         ++r;
     };
@@ -603,7 +601,7 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
 
 __global__ void __launch_bounds__(TPB) k_cache_joint_impulses(unsigned int nJ, nb2_joint* joints, SchedView vs,
                                                               const int* __restrict__ it_nrows,
-                                                              const int2* __restrict__ r_meta,
+                                                              const float4* __restrict__ r_kind /* jac plane 4 */,
                                                               const float* __restrict__ r_imp, float inv_dt) {
     unsigned int ji = blockIdx.x * blockDim.x + threadIdx.x;
     if (ji >= nJ) return;
@@ -612,7 +610,7 @@ __global__ void __launch_bounds__(TPB) k_cache_joint_impulses(unsigned int nJ, n
     const int nrows = it_nrows[ji];
     for (int r = 0; r < nrows; ++r) {
         size_t slot = vs.row_slot(ji, r);
-        if (r_meta[slot].x == NB2_ROW_NONE) continue;
+        if (__float_as_int(r_kind[slot].z) == NB2_ROW_NONE) continue;
         j.impulses[joint_cache_slot(j.type, r)] = r_imp[slot];
     }
     const float* lin = &j.impulses[0];
@@ -656,7 +654,6 @@ static RowOut row_out(Context* ctx) {
     RowOut o;
     o.jac = ctx->r_jac.p;
     o.hdr = ctx->r_hdr.p;
-    o.meta = ctx->r_meta.p;
     o.imp = ctx->r_imp.p;
     o.n_slots_max = ctx->n_slots_max;
     return o;
@@ -674,10 +671,9 @@ int launch_assemble(Context* ctx, int mode) {
     const size_t pslots = pitems * (size_t)NB2_CHUNK + 16;
     ctx->n_slots_max = slots;
     ctx->n_pslots_max = pslots;
-    NB2_TRY(ctx->r_jac.reserve(ctx, 6 * slots));
-    ctx->n_slots_max = ctx->r_jac.cap / 6;  // keep the plane stride consistent with the allocation
+    NB2_TRY(ctx->r_jac.reserve(ctx, NB2_ROW_PLANES * slots));
+    ctx->n_slots_max = ctx->r_jac.cap / NB2_ROW_PLANES;  // keep the plane stride consistent with the allocation
     NB2_TRY(ctx->r_hdr.reserve(ctx, ctx->n_slots_max));
-    NB2_TRY(ctx->r_meta.reserve(ctx, ctx->n_slots_max));
     NB2_TRY(ctx->r_imp.reserve(ctx, ctx->n_slots_max));
     NB2_TRY(ctx->p_row.reserve(ctx, 5 * pslots));
     ctx->n_pslots_max = ctx->p_row.cap / 5;
@@ -741,7 +737,7 @@ int launch_cache_impulses(Context* ctx, int mode) {
     }
     if (ctx->n_joints) {
         k_cache_joint_impulses<<<nblk(ctx->n_joints), TPB, 0, ctx->stream>>>(
-            ctx->n_joints, ctx->joints.p, vs, ctx->vs.it_nrows.p, ctx->r_meta.p, ctx->r_imp.p, ctx->inv_dt);
+            ctx->n_joints, ctx->joints.p, vs, ctx->vs.it_nrows.p, ctx->r_jac.p + 4 * ctx->n_slots_max, ctx->r_imp.p, ctx->inv_dt);
         ctx->launches++;
     }
     NB2_CUDA(ctx, cudaGetLastError());

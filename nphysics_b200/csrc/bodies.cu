@@ -117,6 +117,7 @@ __global__ void k_refresh_dynamics(const nb2_body* __restrict__ raw, unsigned in
     acc_lin = mul3(acc_lin, mk3(b.jacobian_mask[0], b.jacobian_mask[1], b.jacobian_mask[2]));
     acc_ang = mul3(acc_ang, mk3(b.jacobian_mask[3], b.jacobian_mask[4], b.jacobian_mask[5]));
     com_im[i] = make_float4(c.x, c.y, c.z, inv_mass);
+    lam[2 * i] = make_float4(0.f, 0.f, 0.f, inv_mass);  // spare lane: the solve kernels rebuild WJ.lin = J.lin * inv_mass
     inv_i[3 * i] = make_float4(inv.m[0][0], inv.m[0][1], inv.m[0][2], 0.f);
     inv_i[3 * i + 1] = make_float4(inv.m[1][0], inv.m[1][1], inv.m[1][2], 0.f);
     inv_i[3 * i + 2] = make_float4(inv.m[2][0], inv.m[2][1], inv.m[2][2], 0.f);

@@ -302,7 +302,6 @@ static int reserve_sched(Context* ctx, Sched* s, size_t n_items, size_t max_phas
     NB2_TRY(s->ph_gbase.reserve(ctx, max_phases + 1));
     NB2_TRY(s->ph_rbase.reserve(ctx, max_phases + 1));
     NB2_TRY(s->g_info.reserve(ctx, n_items));
-    NB2_TRY(s->g_rank.reserve(ctx, n_items));
     NB2_TRY(s->hdr.reserve(ctx, 1));
     return NB2_OK;
 }
@@ -654,7 +653,6 @@ __global__ void k_fill_ginfo(const unsigned int* __restrict__ changed, size_t n,
                              const int* __restrict__ it_a, const int* __restrict__ it_b,
                              const int* __restrict__ it_nrows, const int* __restrict__ phase,
                              const int* __restrict__ slot, const unsigned int* __restrict__ ph_gbase, int4* g_info,
-                             const unsigned long long* __restrict__ cmask, unsigned int* g_rank, SchedHeader* hdr,
                              unsigned int max_phases) {
     if (*changed == 0u) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -663,31 +661,6 @@ __global__ void k_fill_ginfo(const unsigned int* __restrict__ changed, size_t n,
     // z packs the row count (low 8 bits) and the item type (bits 8..) so the solve kernels need
     // no second lookup
     g_info[ph_gbase[p] + slot[i]] = make_int4(it_a[i], it_b[i], it_nrows[i] | (it_type[i] << 8), (int)i);
-    if (cmask != nullptr) {
-        // rank of this group among the groups of each of its bodies, in colour order, and the bodies'
-        // degrees -- straight from the per-body colour masks (all colours on a body are distinct)
-        unsigned int rk = 0;
-        const int sides[2] = {it_a[i], it_b[i]};
-#pragma unroll
-        for (int sd_ = 0; sd_ < 2; ++sd_) {
-            unsigned int below = 0, deg = 0;
-            if (sides[sd_] >= 0) {
-                for (int w = 0; w < NB2_MASK_WORDS; ++w) {
-                    const unsigned long long m = cmask[(size_t)sides[sd_] * NB2_MASK_WORDS + w];
-                    deg += (unsigned int)__popcll(m);
-                    if ((unsigned int)w < (p >> 6)) below += (unsigned int)__popcll(m);
-                    else if ((unsigned int)w == (p >> 6)) below += (unsigned int)__popcll(m & ((1ull << (p & 63)) - 1ull));
-                }
-            }
-            if (deg > 255u) {
-                atomicOr(&hdr->overflow, 1u);
-                deg = 255u;
-            }
-            rk |= (below & 0xFFu) << (16 * sd_);
-            rk |= (deg & 0xFFu) << (16 * sd_ + 8);
-        }
-        g_rank[ph_gbase[p] + slot[i]] = rk;
-    }
 }
 __global__ void k_copy_phase(size_t n, const int* __restrict__ level, int* phase) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -815,8 +788,7 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     k_phase_scan<<<1, 1, 0, ctx->stream>>>(changed, s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
     k_fill_ginfo<<<nblk(n), TPB, 0, ctx->stream>>>(changed, n, s->it_type.p, s->it_a.p, s->it_b.p, s->it_nrows.p,
                                                    s->it_phase.p, s->it_slot.p, s->ph_gbase.p, s->g_info.p,
-                                                   mode == NB2_MODE_COLOURED ? ctx->cmask.p : nullptr, s->g_rank.p,
-                                                   s->hdr.p, (unsigned int)s->max_phases);
+                                                   (unsigned int)s->max_phases);
     ctx->launches += 3;
     NB2_CUDA(ctx, cudaGetLastError());
     return NB2_OK;

@@ -38,14 +38,15 @@ __device__ __forceinline__ void velocity_group(const Rows& R, float4* lam, int4 
     if (ncc > 2) n2 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 2) * cnt + g]);
     if (ncc > 3) n3 = __ldcg(&R.imp[rbase + (size_t)(2 * ncc + 3) * cnt + g]);
     Lam la, lb;
+    la.im = lb.im = 0.f;
     if (a) la = load_lam(lam, info.x);
     if (b) lb = load_lam(lam, info.y);
     for (int r = 0; r < nrows; ++r) {
         const size_t slot = rbase + (size_t)r * cnt + g;
         if (r + 1 < nrows) load_pkt(R, slot + cnt, a, b, &nxt);
-        if (cur.meta.x != NB2_ROW_NONE) {
+        if (cur.kind() != NB2_ROW_NONE) {
             RowJ J;
-            unpack_pkt(cur, a, b, &J);
+            unpack_pkt(cur, a, b, la.im, lb.im, &J);
             if (warm) {
                 if (cur.imp != 0.f) {
                     if (a) axpy6(cur.imp, J.W1, la.v);
@@ -53,15 +54,15 @@ __device__ __forceinline__ void velocity_group(const Rows& R, float4* lam, int4 
                 }
             } else {
                 float dep = 0.f;
-                if (cur.meta.x == NB2_ROW_DEPENDENT) {
+                if (cur.kind() == NB2_ROW_DEPENDENT) {
                     if (r < 2 * ncc) {
                         const int k = r >> 1;
                         dep = k == 0 ? n0 : (k == 1 ? n1 : (k == 2 ? n2 : n3));
                     } else {
-                        dep = __ldcg(&R.imp[cur.meta.y]);  // reference order: another group's row
+                        dep = __ldcg(&R.imp[cur.dep()]);  // reference order: another group's row
                     }
                 }
-                float ni = solve_row(cur.meta.x, cur.h, cur.imp, dep, J, a, b, &la, &lb);
+                float ni = solve_row(cur.kind(), cur.h, cur.imp, dep, J, a, b, &la, &lb);
                 if (ni != cur.imp) __stcg(&R.imp[slot], ni);
             }
         }
@@ -92,72 +93,6 @@ __global__ void __launch_bounds__(TPB) k_velocity_solve(SchedDev sd, Rows R, flo
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Barrier-free (dataflow) execution of the coloured schedule.
-//
-// A grid barrier per colour costs ~8 us of pure latency per phase visit and leaves the machine idle
-// while the slowest block arrives; with ~10 colours x 11 sweeps that is most of the kernel on a
-// 100k-body scene.  But a group only depends on the previous visit of ITS two bodies.  Every body
-// carries a turn counter (completed visits).  Group i is the ra-th of da groups on body a (colour
-// order: ra = number of a's colours below i's), so its visit of sweep s may start exactly when
-// turn[a] == s*da + ra and turn[b] == s*db + rb; it ends with a release-increment of both counters.
-// Warps take 32-group batches of one colour (mutually independent) in increasing (sweep, colour,
-// position) order.  Every dependency of a batch lies in a globally earlier batch and every warp
-// walks its batches in increasing order, so the earliest blocked batch always has its dependencies
-// done or running: no deadlock as long as all warps are co-resident (cooperative launch).  A spin
-// cap turns a would-be hang (a bug) into an error flag.
-// ------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(TPB) k_velocity_solve_flow(SchedDev sd, const unsigned int* __restrict__ g_rank, Rows R,
-                                                             float4* lam, unsigned int* turn, int iters,
-                                                             unsigned int* err_flags) {
-    const unsigned int np = sd.hdr->n_phases;
-    const unsigned int lane = threadIdx.x & 31;
-    const size_t w = (size_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;  // block-interleaved warp id
-    const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
-    for (int s = 0; s <= iters; ++s) {  // s == 0: warm start
-        size_t k = w, pstart = 0;
-        unsigned int p = 0;
-        while (p < np) {
-            const unsigned int cnt = sd.ph_count[p];
-            const size_t nbatch = ((size_t)cnt + 31) >> 5;
-            if (k >= pstart + nbatch) {
-                pstart += nbatch;
-                ++p;
-                continue;
-            }
-            const size_t g = ((k - pstart) << 5) + lane;
-            const bool active = g < cnt;
-            const size_t gbase = sd.ph_gbase[p];
-            int4 info = make_int4(-1, -1, 0, 0);
-            unsigned int rk = 0;
-            if (active) {
-                info = __ldg(&sd.g_info[gbase + g]);
-                rk = __ldg(&g_rank[gbase + g]);
-            }
-            const unsigned int ea = (unsigned int)s * ((rk >> 8) & 0xFFu) + (rk & 0xFFu);
-            const unsigned int eb = (unsigned int)s * (rk >> 24) + ((rk >> 16) & 0xFFu);
-            unsigned int spins = 0;
-            for (;;) {
-                bool ok = true;
-                if (info.x >= 0) ok = ld_acquire_u32(&turn[info.x]) == ea;
-                if (ok && info.y >= 0) ok = ld_acquire_u32(&turn[info.y]) == eb;
-                if (__all_sync(0xffffffffu, ok)) break;
-                if (++spins > NB2_SPIN_LIMIT) {
-                    if (lane == 0) atomicOr(err_flags, 4u);
-                    return;
-                }
-            }
-            if (active) {
-                velocity_group(R, lam, info, sd.ph_rbase[p], cnt, g, s == 0);
-                if (info.x >= 0) red_release_inc(&turn[info.x]);
-                if (info.y >= 0) red_release_inc(&turn[info.y]);
-            }
-            k += n_warps;
-        }
-    }
-}
-
 // Reference-order warm start: one thread per body accumulates the impulses of its incident rows
 // in the reference's warm-start order (contact unilateral, unilateral_ground, bilateral,
 // bilateral_ground, then the joint buckets; sor_prox.rs:19-45,57-58).
@@ -171,6 +106,7 @@ __global__ void __launch_bounds__(TPB) k_warmstart_ref(unsigned int nb, const un
     Lam l;
 #pragma unroll
     for (int k = 0; k < 6; ++k) l.v[k] = 0.f;
+    l.im = lam[2 * body].w;
     const int order[6] = {4, 5, 2, 3, 0, 1};
     for (int ob = 0; ob < 6; ++ob) {
         const unsigned long long bucket = (unsigned long long)order[ob];
@@ -184,11 +120,11 @@ __global__ void __launch_bounds__(TPB) k_warmstart_ref(unsigned int nb, const un
             const int nrows = it_nrows[item];
             for (int r = 0; r < nrows; ++r) {
                 const size_t slot = rbase + (size_t)r * cnt + (size_t)sd.it_slot[item];
-                if (R.meta[slot].x == NB2_ROW_NONE) continue;
+                if (row_kind(R, slot) == NB2_ROW_NONE) continue;
                 const float impulse = R.imp[slot];
                 if (impulse == 0.f) continue;
                 RowJ J;
-                load_row_j(R, slot, side_a, !side_a, &J);
+                load_row_j(R, slot, side_a, !side_a, l.im, l.im, &J);
                 axpy6(impulse, side_a ? J.W1 : J.W2, l.v);
             }
         }
@@ -308,15 +244,17 @@ __global__ void __launch_bounds__(TPB) k_residual(SchedDev sd, Rows R, CompactAr
                 continue;
             }
             Lam la, lb;
+            la.im = lb.im = 0.f;
             if (a) la = load_lam(lam, info.x);
             if (b) lb = load_lam(lam, info.y);
             for (int r = 0; r < (info.z & 0xFF); ++r) {
                 const size_t slot = rbase + (size_t)r * cnt + g;
-                const int2 meta = R.meta[slot];
+                const float4 q4 = R.jac[4 * R.S + slot];
+                const int2 meta = make_int2(__float_as_int(q4.z), __float_as_int(q4.w));
                 if (meta.x == NB2_ROW_NONE) continue;
                 const float impulse = R.imp[slot];
                 RowJ J;
-                load_row_j(R, slot, a, b, &J);
+                load_row_j(R, slot, a, b, la.im, lb.im, &J);
                 const float4 h = R.hdr[slot];
                 float lo = 0.f, hi = NB2_F32_MAX;
                 if (meta.x == NB2_ROW_BILATERAL) {
@@ -397,7 +335,6 @@ static Rows rows_of(Context* ctx) {
     Rows R;
     R.jac = ctx->r_jac.p;
     R.hdr = ctx->r_hdr.p;
-    R.meta = ctx->r_meta.p;
     R.imp = ctx->r_imp.p;
     R.S = ctx->n_slots_max;
     return R;
@@ -460,26 +397,6 @@ int launch_velocity_solve(Context* ctx, int mode) {
     if (!ref && ctx->velocity_kernel >= 2) {
         int tpb_s, depth_s, blocks_s;
         if (staged_geometry(ctx, &tpb_s, &depth_s, &blocks_s)) return launch_velocity_solve_staged(ctx, sd, R, tpb_s, depth_s, blocks_s);
-    }
-    if (!ref && ctx->velocity_kernel == 1) {
-        NB2_TRY(coop_limit(ctx, k_velocity_solve_flow, &ctx->coop_blocks_flow));
-        NB2_TRY(ctx->turn.reserve(ctx, (size_t)ctx->n_bodies + 1));
-        NB2_CUDA(ctx, cudaMemsetAsync(ctx->turn.p, 0, ((size_t)ctx->n_bodies + 1) * sizeof(unsigned int), ctx->stream));
-        const unsigned int* grank = ctx->vs.g_rank.p;
-        float4* lam_ = ctx->lam.p;
-        unsigned int* turn_ = ctx->turn.p;
-        int iters_ = (int)ctx->params.max_velocity_iterations;
-        unsigned int* err_ = ctx->flags.p;
-        size_t want_ = (ctx->vs.n_items + TPB - 1) / TPB;
-        int blocks_ = (int)(want_ < (size_t)ctx->coop_blocks_flow ? want_ : (size_t)ctx->coop_blocks_flow);
-        if (blocks_ < 1) blocks_ = 1;
-        void* fargs[] = {&sd, &grank, &R, &lam_, &turn_, &iters_, &err_};
-        if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
-        NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_velocity_solve_flow, dim3(blocks_), dim3(TPB), fargs, 0,
-                                                  ctx->stream));
-        if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[7], ctx->stream));
-        ctx->launches++;
-        return NB2_OK;
     }
     void* args[] = {&sd, &R, &lam, &iters, &warm, &symmetric, &bar};
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));

@@ -18,15 +18,16 @@ __device__ __noinline__ void generic_group(const Rows& R, float4* lam, int4 info
     const bool a = info.x >= 0, b = info.y >= 0;
     const int nrows = info.z & 0xFF;
     Lam la, lb;
+    la.im = lb.im = 0.f;
     if (a) la = load_lam(lam, info.x);
     if (b) lb = load_lam(lam, info.y);
     for (int r = 0; r < nrows; ++r) {
         const size_t slot = rbase + (size_t)r * cnt + g;
         RowPkt k;
         load_pkt(R, slot, a, b, &k);
-        if (k.meta.x == NB2_ROW_NONE) continue;
+        if (k.kind() == NB2_ROW_NONE) continue;
         RowJ J;
-        unpack_pkt(k, a, b, &J);
+        unpack_pkt(k, a, b, la.im, lb.im, &J);
         if (warm) {
             if (k.imp != 0.f) {
                 if (a) axpy6(k.imp, J.W1, la.v);
@@ -34,8 +35,8 @@ __device__ __noinline__ void generic_group(const Rows& R, float4* lam, int4 info
             }
             continue;
         }
-        const float dep = k.meta.x == NB2_ROW_DEPENDENT ? __ldcg(&R.imp[k.meta.y]) : 0.f;
-        const float ni = solve_row(k.meta.x, k.h, k.imp, dep, J, a, b, &la, &lb);
+        const float dep = k.kind() == NB2_ROW_DEPENDENT ? __ldcg(&R.imp[k.dep()]) : 0.f;
+        const float ni = solve_row(k.kind(), k.h, k.imp, dep, J, a, b, &la, &lb);
         if (ni != k.imp) __stcg(&R.imp[slot], ni);
     }
     if (a) store_lam(lam, info.x, la);
@@ -77,15 +78,14 @@ __global__ void __launch_bounds__(SOLVE_TPB) k_velocity_solve_coloured(SchedDev 
 // loads depends on what other groups computed: the thread -> group mapping is static, and the row
 // planes (J, M^-1 J, rhs/r/limits, kind) are constant during the solve.  So every thread runs a
 // PRODUCER D entries ahead of its own consumption, across phase and sweep boundaries: it walks the
-// same (sweep, phase, group, row) sequence and copies each row's 7 quads + meta into its private
+// same (sweep, phase, group, row) sequence and copies each row's 6 quads into its private
 // slice of a shared-memory ring with cp.async (16 bytes per lane, coalesced over the group index).
 // While the block waits at a grid barrier the rows of its next groups are already landing.  After
 // the barrier only the mutable data is fetched (the two bodies' mj_lambda and the group's impulses,
 // L2 hits, issued together), then the rows are consumed from shared memory.
 //
-// Ring entry = 8 quads x TPB lanes: planes 0..5 jacobian, 6 header, 7 control.  A group is announced
-// by a header entry (control = its g_info, written with st.shared), followed by its rows (control =
-// the row's meta, copied).  Entries are private to their thread, so cp.async.wait_group is the only
+// Ring entry = 7 quads x TPB lanes: planes 0..4 jacobian, 5 header, 6 control.  A group is announced
+// by an entry whose control quad holds its g_info (written with st.shared), followed by its rows.  Entries are private to their thread, so cp.async.wait_group is the only
 // synchronisation.  A slot is refilled one consume step after it was read, when the values read
 // from it have already been used.
 // ------------------------------------------------------------------------------------------
@@ -112,6 +112,12 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 __device__ unsigned long long g_trace[4096];
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // pending in 0..2
+    if (pending <= 0) cp_async_wait<0>();
+    else if (pending == 1) cp_async_wait<1>();
+    else cp_async_wait<2>();
+}
+
 struct StreamPos {
     int s;           // sweep, 0 = warm start
     unsigned int p;  // phase
@@ -131,46 +137,25 @@ __device__ __forceinline__ bool seek_group(StreamPos& q, unsigned int tid, unsig
     }
 }
 
-// depth (ring entries per thread) and the block size are launch-time values: the launcher sizes the
-// block to the groups an SM owns per phase (one group per thread) and gives the rest of shared
-// memory to the ring.
-__device__ __forceinline__ void cp_async_wait_dyn(int pending) {
-    switch (pending) {
-        case 0: cp_async_wait<0>(); break;
-        case 1: cp_async_wait<1>(); break;
-        case 2: cp_async_wait<2>(); break;
-        case 3: cp_async_wait<3>(); break;
-        case 4: cp_async_wait<4>(); break;
-        case 5: cp_async_wait<5>(); break;
-        case 6: cp_async_wait<6>(); break;
-        case 7: cp_async_wait<7>(); break;
-        case 8: cp_async_wait<8>(); break;
-        case 9: cp_async_wait<9>(); break;
-        case 10: cp_async_wait<10>(); break;
-        default: cp_async_wait<11>(); break;
-    }
-}
+// The block size is a launch-time value: the launcher sizes the block to the groups an SM owns per
+// phase (one group per thread).  D = ring entries per thread.
 // plane base pointers as kernel parameters (constant bank): one IMAD.WIDE per address
 struct StagedRows {
-    const float4* q[7];  // 6 jacobian planes + header
-    const int2* meta;
+    const float4* q[6];  // 5 jacobian planes + header
     float* imp;
 };
-#define NB2_STAGED_MAX_DEPTH 13
+#define NB2_VENTRY 7
+#define NB2_STAGED_MAX_DEPTH 5
 #define NB2_STAGED_MIN_DEPTH 3
 #define NB2_STAGED_DEPTH 4
 
-// FLOW: no grid barriers; a group starts when the turn counters of its two bodies say that every
-// earlier visit of those bodies is done (see k_velocity_solve_flow in solve.cu for the argument).
-template <bool FLOW>
-__global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, StagedRows R, float4* lam, int iters, int D,
-                                                                  unsigned int* barrier, int trace,
-                                                                  const unsigned int* __restrict__ g_rank,
-                                                                  unsigned int* turn, unsigned int* err_flags) {
+template <int D>
+__global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, StagedRows R, float4* lam, int iters,
+                                                                  unsigned int* barrier, int trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned int TPBK = blockDim.x;
-    float4* ring = reinterpret_cast<float4*>(smem_raw);              // [D][8][TPBK]
-    float* simp = reinterpret_cast<float*>(ring + D * 8 * TPBK);     // [12][TPBK] impulses of the running group
+    float4* ring = reinterpret_cast<float4*>(smem_raw);                    // [D][NB2_VENTRY][TPBK]
+    float* simp = reinterpret_cast<float*>(ring + D * NB2_VENTRY * TPBK);  // [12][TPBK] impulses of the running group
     unsigned int* s_cnt = reinterpret_cast<unsigned int*>(simp + 12 * TPBK);
     unsigned int* s_rbase = s_cnt + NB2_MAX_COLOURS;
     unsigned int* s_gbase = s_rbase + NB2_MAX_COLOURS;
@@ -184,27 +169,22 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
     __syncthreads();
     GridBarrier gb;
     gb.init(barrier);
-    const unsigned int t = threadIdx.x, lane = threadIdx.x & 31u;
+    const unsigned int t = threadIdx.x;
     const unsigned int tid = (unsigned int)interleaved_tid();
     const unsigned int stride = gridDim.x * TPBK;
     const unsigned int ring_u32 = (unsigned int)__cvta_generic_to_shared(ring) + t * 16u;
-    const unsigned int plane_b = TPBK * 16u, entry_b = 8u * plane_b;
+    const unsigned int plane_b = TPBK * 16u, entry_b = NB2_VENTRY * plane_b;
 
     // ---- producer state: the group being copied, and the one after it (its g_info already in flight)
     StreamPos pc = {0, 0u, tid}, pn;
     bool vc = seek_group(pc, tid, np, iters, s_cnt), vn = false;
     int4 ic = make_int4(-1, -1, 0, 0), in_ = ic;
-    auto fetch_info = [&](const StreamPos& q) -> int4 {
-        int4 v = __ldg(&sd.g_info[s_gbase[q.p] + q.g]);
-        if (FLOW) v.w = (int)__ldg(&g_rank[s_gbase[q.p] + q.g]);
-        return v;
-    };
     if (vc) {
-        ic = fetch_info(pc);
+        ic = __ldg(&sd.g_info[s_gbase[pc.p] + pc.g]);
         pn = pc;
         pn.g += stride;
         vn = seek_group(pn, tid, np, iters, s_cnt);
-        if (vn) in_ = fetch_info(pn);
+        if (vn) in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
     }
     int pr = -1;  // -1: the header entry of `pc` comes next
     const unsigned long long pol = l2_evict_first_policy();
@@ -213,22 +193,16 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
         if (vc) {
             const unsigned int dst = ring_u32 + (unsigned int)e * entry_b;
             if (pr < 0) {
-                reinterpret_cast<int4*>(ring)[(e * 8 + 7) * TPBK + t] = ic;
+                reinterpret_cast<int4*>(ring)[(e * NB2_VENTRY + 6) * TPBK + t] = ic;
                 pcnt = s_cnt[pc.p];
                 pslot = s_rbase[pc.p] + pc.g;
             } else {
                 cp_async16_ef(dst + 1u * plane_b, R.q[1] + pslot, pol);
+                cp_async16_ef(dst + 3u * plane_b, R.q[3] + pslot, pol);
                 cp_async16_ef(dst + 4u * plane_b, R.q[4] + pslot, pol);
-                if (ic.x >= 0) {
-                    cp_async16_ef(dst, R.q[0] + pslot, pol);
-                    cp_async16_ef(dst + 3u * plane_b, R.q[3] + pslot, pol);
-                }
-                if (ic.y >= 0) {
-                    cp_async16_ef(dst + 2u * plane_b, R.q[2] + pslot, pol);
-                    cp_async16_ef(dst + 5u * plane_b, R.q[5] + pslot, pol);
-                }
-                cp_async16_ef(dst + 6u * plane_b, R.q[6] + pslot, pol);
-                cp_async8(dst + 7u * plane_b, R.meta + pslot);
+                cp_async16_ef(dst + 5u * plane_b, R.q[5] + pslot, pol);
+                if (ic.x >= 0) cp_async16_ef(dst, R.q[0] + pslot, pol);
+                if (ic.y >= 0) cp_async16_ef(dst + 2u * plane_b, R.q[2] + pslot, pol);
                 pslot += pcnt;
             }
             if (++pr >= (ic.z & 0xFF)) {
@@ -239,7 +213,7 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
                 if (vn) {
                     pn.g += stride;
                     vn = seek_group(pn, tid, np, iters, s_cnt);
-                    if (vn) in_ = fetch_info(pn);
+                    if (vn) in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
                 }
             }
         }
@@ -251,53 +225,43 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
     int ce = 0;        // ring entry consumed next
     bool any = false;  // false until the first entry was consumed (nothing to refill yet)
     auto take = [&]() -> int {  // makes entry `ce` readable and returns it
-        cp_async_wait_dyn(D - 2);
+        cp_async_wait<D - 2>();
         const int e = ce;
         ce = ce + 1 == D ? 0 : ce + 1;
         return e;
     };
-    auto refill_prev = [&](int e) {  // refills the entry consumed one step ago
+    auto refill_prev = [&](int e) {  // refills the entry consumed one step ago (its values are used up by now)
         if (any) produce(e == 0 ? D - 1 : e - 1);
         any = true;
     };
+    // next row of the running group: ring -> registers, then the refill of the previous entry
+    auto next_row = [&](int r, RowPkt* k) {
+        const int e = take();
+        const float4* q = ring + (e * NB2_VENTRY) * TPBK + t;
+        k->q0 = q[0 * TPBK];
+        k->q1 = q[1 * TPBK];
+        k->q2 = q[2 * TPBK];
+        k->q3 = q[3 * TPBK];
+        k->q4 = q[4 * TPBK];
+        k->h = q[5 * TPBK];
+        k->imp = simp[r * TPBK + t];
+        refill_prev(e);
+    };
 
-    for (int s = 0; s <= iters; ++s) {
+    for (int s = 0; s <= iters; ++s) {  // s == 0: warm start (sor_prox.rs:57-58, 345-435)
         for (unsigned int p = 0; p < np; ++p) {
             const unsigned int cnt = s_cnt[p];
             const unsigned int rbase = s_rbase[p];
-            for (unsigned int gw = tid - lane; gw < cnt; gw += stride) {  // warp-uniform trip count
-                const unsigned int g = gw + lane;
-                const bool active = g < cnt;
-                int e = 0;
-                int4 info = make_int4(-1, -1, 0, 0);
-                if (active) {
-                    e = take();
-                    info = reinterpret_cast<const int4*>(ring)[(e * 8 + 7) * TPBK + t];
-                }
+            for (unsigned int g = tid; g < cnt; g += stride) {
+                const int e0 = take();
+                const int4 info = reinterpret_cast<const int4*>(ring)[(e0 * NB2_VENTRY + 6) * TPBK + t];
                 const bool a = info.x >= 0, b = info.y >= 0;
-                if (FLOW) {
-                    const unsigned int rk = (unsigned int)info.w;
-                    const unsigned int ea = (unsigned int)s * ((rk >> 8) & 0xFFu) + (rk & 0xFFu);
-                    const unsigned int eb = (unsigned int)s * (rk >> 24) + ((rk >> 16) & 0xFFu);
-                    unsigned int spins = 0;
-                    for (;;) {
-                        bool ok = true;
-                        if (a) ok = ld_acquire_u32(&turn[info.x]) == ea;
-                        if (ok && b) ok = ld_acquire_u32(&turn[info.y]) == eb;
-                        if (__all_sync(0xffffffffu, ok)) break;
-                        if (++spins > NB2_SPIN_LIMIT) {
-                            if (lane == 0) atomicOr(err_flags, 4u);
-                            cp_async_wait<0>();
-                            return;
-                        }
-                    }
-                }
-                if (!active) continue;
                 const int nrows = info.z & 0xFF;
                 const int ncc = (info.z >> 8) == NB2_ITEM_CONTACTS ? nrows / 3 : 0;
                 // the mutable data of the group, all loads in flight together: mj_lambda of both bodies and
                 // the group's impulses (same thread wrote them a sweep ago)
                 Lam la, lb;
+                la.im = lb.im = 0.f;
                 if (a) la = load_lam(lam, info.x);
                 if (b) lb = load_lam(lam, info.y);
                 {
@@ -305,30 +269,22 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
 #pragma unroll
                     for (int r = 0; r < 12; ++r)
                         if (r < nrows) v[r] = __ldcg(&R.imp[rbase + (unsigned int)r * cnt + g]);
-                    refill_prev(e);
+                    refill_prev(e0);
 #pragma unroll
                     for (int r = 0; r < 12; ++r)
                         if (r < nrows) simp[r * TPBK + t] = v[r];
                 }
                 unsigned int cslot = rbase + g;
+                // one loop for every group type and both passes: a specialised path per type measured slower
+                // (warps mix ground and two-body groups, so the paths serialise)
 #pragma unroll 1
                 for (int r = 0; r < nrows; ++r, cslot += cnt) {
-                    e = take();
                     RowPkt k;
-                    const float4* q = ring + (e * 8) * TPBK + t;
-                    k.q0 = q[0 * TPBK];
-                    k.q1 = q[1 * TPBK];
-                    k.q2 = q[2 * TPBK];
-                    k.q3 = q[3 * TPBK];
-                    k.q4 = q[4 * TPBK];
-                    k.q5 = q[5 * TPBK];
-                    k.h = q[6 * TPBK];
-                    k.meta = *reinterpret_cast<const int2*>(q + 7 * TPBK);
-                    k.imp = simp[r * TPBK + t];
-                    refill_prev(e);
-                    if (k.meta.x == NB2_ROW_NONE) continue;
+                    next_row(r, &k);
+                    const int kind = k.kind();
+                    if (kind == NB2_ROW_NONE) continue;
                     RowJ J;
-                    unpack_pkt(k, true, true, &J);  // unconditional: pure register renaming (absent sides are never used)
+                    unpack_pkt(k, true, true, la.im, lb.im, &J);  // unconditional: absent sides are never used
                     if (s == 0) {
                         if (k.imp != 0.f) {
                             if (a) axpy6(k.imp, J.W1, la.v);
@@ -337,23 +293,19 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
                         continue;
                     }
                     float dep = 0.f;
-                    if (k.meta.x == NB2_ROW_DEPENDENT) {
+                    if (kind == NB2_ROW_DEPENDENT) {
                         // coloured contact groups hold their own normal rows (rows 2*ncc..3*ncc-1), not yet
                         // updated in this visit: friction rows come first
-                        dep = r < 2 * ncc ? simp[(2 * ncc + (r >> 1)) * TPBK + t] : __ldcg(&R.imp[k.meta.y]);
+                        dep = r < 2 * ncc ? simp[(2 * ncc + (r >> 1)) * TPBK + t] : __ldcg(&R.imp[k.dep()]);
                     }
-                    const float ni = solve_row(k.meta.x, k.h, k.imp, dep, J, a, b, &la, &lb);
+                    const float ni = solve_row(kind, k.h, k.imp, dep, J, a, b, &la, &lb);
                     if (ni != k.imp) __stcg(&R.imp[cslot], ni);
                 }
                 if (a) store_lam(lam, info.x, la);
                 if (b) store_lam(lam, info.y, lb);
-                if (FLOW) {
-                    if (a) red_release_inc(&turn[info.x]);
-                    if (b) red_release_inc(&turn[info.y]);
-                }
             }
-            if (!FLOW) gb.sync();
-            if (!FLOW && trace && blockIdx.x == 0 && threadIdx.x == 0) {
+            gb.sync();
+            if (trace && blockIdx.x == 0 && threadIdx.x == 0) {
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (s * np + p < 4096) g_trace[s * np + p] = now;
@@ -361,14 +313,14 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
         }
     }
     cp_async_wait<0>();
-    if (!FLOW && trace && blockIdx.x == 0 && threadIdx.x == 0)
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0)
         for (unsigned int i = 1; i < min((iters + 1) * np, 4096u); ++i)
             if (i / np == (unsigned int)trace)
                 printf("sweep %u phase %u groups %u dt_ns %llu\n", i / np, i % np, s_cnt[i % np], g_trace[i] - g_trace[i - 1]);
 }
 
 static size_t staged_smem(int depth, int tpb) {
-    return (size_t)depth * 8 * tpb * 16 + 12 * (size_t)tpb * 4 + 3 * NB2_MAX_COLOURS * 4;
+    return (size_t)depth * NB2_VENTRY * tpb * 16 + 12 * (size_t)tpb * 4 + 3 * NB2_MAX_COLOURS * 4;
 }
 
 // Chooses block size and ring depth for the staged kernel; false = the scene is too large for one
@@ -396,6 +348,8 @@ bool staged_geometry(Context* ctx, int* tpb_out, int* depth_out, int* blocks_out
     int depth = NB2_STAGED_DEPTH;
     while (depth > NB2_STAGED_MIN_DEPTH && staged_smem(depth, tpb) > ctx->smem_optin) --depth;
     if (const char* f = getenv("NB2_STAGED_DEPTH")) depth = atoi(f);
+    if (depth < NB2_STAGED_MIN_DEPTH) depth = NB2_STAGED_MIN_DEPTH;
+    if (depth > NB2_STAGED_MAX_DEPTH) depth = NB2_STAGED_MAX_DEPTH;
     *blocks_out = (int)blocks;
     *tpb_out = tpb;
     *depth_out = depth;
@@ -405,17 +359,16 @@ bool staged_geometry(Context* ctx, int* tpb_out, int* depth_out, int* blocks_out
 int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd_in, const Rows& R_in, int tpb, int depth, int blocks) {
     SchedDev sd = sd_in;
     StagedRows R;
-    for (int k = 0; k < 6; ++k) R.q[k] = R_in.jac + (size_t)k * R_in.S;
-    R.q[6] = R_in.hdr;
-    R.meta = R_in.meta;
+    for (int k = 0; k < NB2_ROW_PLANES; ++k) R.q[k] = R_in.jac + (size_t)k * R_in.S;
+    R.q[5] = R_in.hdr;
     R.imp = R_in.imp;
     const size_t smem = staged_smem(depth, tpb);
-    const bool flow = ctx->velocity_kernel == 3;
+    void* kernel = depth == 3 ? (void*)k_velocity_solve_staged<3>
+                              : (depth == 5 ? (void*)k_velocity_solve_staged<5> : (void*)k_velocity_solve_staged<4>);
     if (!ctx->staged_attr) {
-        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)ctx->smem_optin));
-        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)ctx->smem_optin));
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_staged<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_staged<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_staged<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
         ctx->staged_attr = true;
     }
     float4* lam = ctx->lam.p;
@@ -423,18 +376,9 @@ int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd_in, const Rows
     unsigned int* bar = ctx->barrier.p;
     static const int trace = getenv("NB2_TRACE_PHASES") ? atoi(getenv("NB2_TRACE_PHASES")) : 0;
     int tr = trace;
-    const unsigned int* grank = ctx->vs.g_rank.p;
-    unsigned int* turn = nullptr;
-    unsigned int* err = ctx->flags.p;
-    if (flow) {
-        NB2_TRY(ctx->turn.reserve(ctx, (size_t)ctx->n_bodies + 1));
-        NB2_CUDA(ctx, cudaMemsetAsync(ctx->turn.p, 0, ((size_t)ctx->n_bodies + 1) * sizeof(unsigned int), ctx->stream));
-        turn = ctx->turn.p;
-    }
-    void* args[] = {&sd, &R, &lam, &iters, &depth, &bar, &tr, &grank, &turn, &err};
+    void* args[] = {&sd, &R, &lam, &iters, &bar, &tr};
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
-    NB2_CUDA(ctx, cudaLaunchCooperativeKernel(flow ? (void*)k_velocity_solve_staged<true> : (void*)k_velocity_solve_staged<false>,
-                                              dim3(blocks), dim3(tpb), args, smem, ctx->stream));
+    NB2_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(tpb), args, smem, ctx->stream));
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[7], ctx->stream));
     ctx->launches++;
     return NB2_OK;

@@ -37,25 +37,33 @@ static inline SchedDev sched_dev(const Sched& s) {
     return d;
 }
 
+// Velocity rows, 100 bytes each: five jacobian quads, a header quad, the impulse.
+//   jac[0] = J1[0..3]   jac[1] = J1[4..5] J2[0..1]   jac[2] = J2[2..5]
+//   jac[3] = WJ1.ang.xyz, WJ2.ang.x    jac[4] = WJ2.ang.yz, kind (int bits), dependency slot (int bits)
+//   hdr    = rhs, r, lo | mu, hi
+// The linear half of WJ = M^-1 J is not stored: for a rigid body it is J.lin * inv_mass (exactly the
+// product fill_constraint_geometry forms, rigid_body.rs:703-706), and inv_mass rides in the spare
+// lane of the body's mj_lambda quad.
 struct Rows {
     const float4* jac;
     const float4* hdr;
-    const int2* meta;
     float* imp;
     size_t S;  // plane stride
 };
 
 struct Lam {
     float v[6];
+    float im;  // inverse mass of the body (constant; carried through load/store)
 };
 __device__ __forceinline__ Lam load_lam(const float4* lam, int b) {
     Lam l;
     float4 a = ldcg4(&lam[2 * b]), c = ldcg4(&lam[2 * b + 1]);
     l.v[0] = a.x; l.v[1] = a.y; l.v[2] = a.z; l.v[3] = c.x; l.v[4] = c.y; l.v[5] = c.z;
+    l.im = a.w;
     return l;
 }
 __device__ __forceinline__ void store_lam(float4* lam, int b, const Lam& l) {
-    stcg4(&lam[2 * b], make_float4(l.v[0], l.v[1], l.v[2], 0.f));
+    stcg4(&lam[2 * b], make_float4(l.v[0], l.v[1], l.v[2], l.im));
     stcg4(&lam[2 * b + 1], make_float4(l.v[3], l.v[4], l.v[5], 0.f));
 }
 __device__ __forceinline__ float dot6(const float* a, const float* b) {
@@ -84,22 +92,25 @@ __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v 
 struct RowJ {
     float J1[6], J2[6], W1[6], W2[6];
 };
-__device__ __forceinline__ void load_row_j(const Rows& R, size_t slot, bool a, bool b, RowJ* o) {
-    // 24 floats = 6 float4 planes: J1 | J2 | W1 | W2
-    float4 q0, q1, q2, q3, q4, q5;
-    q1 = __ldg(&R.jac[1 * R.S + slot]);
-    q4 = __ldg(&R.jac[4 * R.S + slot]);
+__device__ __forceinline__ int row_kind(const Rows& R, size_t slot) {
+    return __float_as_int(__ldg(&R.jac[4 * R.S + slot]).z);
+}
+// ima / imb: inverse masses of the two bodies (only the present sides are filled)
+__device__ __forceinline__ void load_row_j(const Rows& R, size_t slot, bool a, bool b, float ima, float imb, RowJ* o) {
+    const float4 q1 = __ldg(&R.jac[1 * R.S + slot]);
+    const float4 q3 = __ldg(&R.jac[3 * R.S + slot]);
     if (a) {
-        q0 = __ldg(&R.jac[0 * R.S + slot]);
-        q3 = __ldg(&R.jac[3 * R.S + slot]);
+        const float4 q0 = __ldg(&R.jac[0 * R.S + slot]);
         o->J1[0] = q0.x; o->J1[1] = q0.y; o->J1[2] = q0.z; o->J1[3] = q0.w; o->J1[4] = q1.x; o->J1[5] = q1.y;
-        o->W1[0] = q3.x; o->W1[1] = q3.y; o->W1[2] = q3.z; o->W1[3] = q3.w; o->W1[4] = q4.x; o->W1[5] = q4.y;
+        o->W1[0] = q0.x * ima; o->W1[1] = q0.y * ima; o->W1[2] = q0.z * ima;
+        o->W1[3] = q3.x; o->W1[4] = q3.y; o->W1[5] = q3.z;
     }
     if (b) {
-        q2 = __ldg(&R.jac[2 * R.S + slot]);
-        q5 = __ldg(&R.jac[5 * R.S + slot]);
+        const float4 q2 = __ldg(&R.jac[2 * R.S + slot]);
+        const float4 q4 = __ldg(&R.jac[4 * R.S + slot]);
         o->J2[0] = q1.z; o->J2[1] = q1.w; o->J2[2] = q2.x; o->J2[3] = q2.y; o->J2[4] = q2.z; o->J2[5] = q2.w;
-        o->W2[0] = q4.z; o->W2[1] = q4.w; o->W2[2] = q5.x; o->W2[3] = q5.y; o->W2[4] = q5.z; o->W2[5] = q5.w;
+        o->W2[0] = q1.z * imb; o->W2[1] = q1.w * imb; o->W2[2] = q2.x * imb;
+        o->W2[3] = q3.w; o->W2[4] = q4.x; o->W2[5] = q4.y;
     }
 }
 
@@ -143,53 +154,39 @@ __device__ __forceinline__ float solve_row(int kind, float4 h, float impulse, fl
     return ni;
 }
 
-// A row as it travels from the ELL planes to the update: 6 jacobian quads, header, meta, the
-// row's impulse and (for Dependent rows) the impulse of the row it depends on.
+// A row as it travels from the ELL planes to the update: 5 jacobian quads (kind and dependency slot
+// in the last one), header, the row's impulse.
 struct RowPkt {
-    float4 q0, q1, q2, q3, q4, q5, h;
-    int2 meta;
+    float4 q0, q1, q2, q3, q4, h;
     float imp;
+    __device__ __forceinline__ int kind() const { return __float_as_int(q4.z); }
+    __device__ __forceinline__ int dep() const { return __float_as_int(q4.w); }
 };
 // All loads of a row are issued together and one row ahead of its use (software pipelining):
 // per phase an SM owns only ~200 groups, so latency is hidden by loads in flight per thread,
 // not by occupancy.  Read-only planes go through ld.global.nc; impulses bypass L1 (ld.cg)
 // because other SMs wrote them in an earlier phase.
 __device__ __forceinline__ void load_pkt(const Rows& R, size_t slot, bool a, bool b, RowPkt* o) {
-    o->meta = __ldg(&R.meta[slot]);
     o->h = __ldg(&R.hdr[slot]);
     o->q1 = __ldg(&R.jac[1 * R.S + slot]);
+    o->q3 = __ldg(&R.jac[3 * R.S + slot]);
     o->q4 = __ldg(&R.jac[4 * R.S + slot]);
-    if (a) {
-        o->q0 = __ldg(&R.jac[0 * R.S + slot]);
-        o->q3 = __ldg(&R.jac[3 * R.S + slot]);
-    }
-    if (b) {
-        o->q2 = __ldg(&R.jac[2 * R.S + slot]);
-        o->q5 = __ldg(&R.jac[5 * R.S + slot]);
-    }
+    if (a) o->q0 = __ldg(&R.jac[0 * R.S + slot]);
+    if (b) o->q2 = __ldg(&R.jac[2 * R.S + slot]);
     o->imp = __ldcg(&R.imp[slot]);
 }
-__device__ __forceinline__ void unpack_pkt(const RowPkt& k, bool a, bool b, RowJ* o) {
+__device__ __forceinline__ void unpack_pkt(const RowPkt& k, bool a, bool b, float ima, float imb, RowJ* o) {
     if (a) {
         o->J1[0] = k.q0.x; o->J1[1] = k.q0.y; o->J1[2] = k.q0.z; o->J1[3] = k.q0.w; o->J1[4] = k.q1.x; o->J1[5] = k.q1.y;
-        o->W1[0] = k.q3.x; o->W1[1] = k.q3.y; o->W1[2] = k.q3.z; o->W1[3] = k.q3.w; o->W1[4] = k.q4.x; o->W1[5] = k.q4.y;
+        o->W1[0] = k.q0.x * ima; o->W1[1] = k.q0.y * ima; o->W1[2] = k.q0.z * ima;
+        o->W1[3] = k.q3.x; o->W1[4] = k.q3.y; o->W1[5] = k.q3.z;
     }
     if (b) {
         o->J2[0] = k.q1.z; o->J2[1] = k.q1.w; o->J2[2] = k.q2.x; o->J2[3] = k.q2.y; o->J2[4] = k.q2.z; o->J2[5] = k.q2.w;
-        o->W2[0] = k.q4.z; o->W2[1] = k.q4.w; o->W2[2] = k.q5.x; o->W2[3] = k.q5.y; o->W2[4] = k.q5.z; o->W2[5] = k.q5.w;
+        o->W2[0] = k.q1.z * imb; o->W2[1] = k.q1.w * imb; o->W2[2] = k.q2.x * imb;
+        o->W2[3] = k.q3.w; o->W2[4] = k.q4.x; o->W2[5] = k.q4.y;
     }
 }
-// per-body turn counters of the barrier-free (dataflow) kernels
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_inc(unsigned int* p) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
-#define NB2_SPIN_LIMIT (1u << 22)
-
 // Warps are dealt to groups block-interleaved (warp w of block b is global warp w*gridDim+b) so a
 // phase with fewer groups than threads still spreads evenly over all SMs.
 __device__ __forceinline__ size_t interleaved_tid() {

@@ -74,6 +74,7 @@ struct DevBuf {
 #define NB2_MAX_JOINT_ROWS 7   // prismatic reserves 7 (prismatic_constraint.rs:124-126)
 #define NB2_MASK_WORDS 4       // 4 x 64 colours
 #define NB2_MAX_COLOURS (64 * NB2_MASK_WORDS)
+#define NB2_ROW_PLANES 5       // jacobian quads per velocity row (solve_common.cuh)
 #define NB2_BALANCE_ROUNDS 12
 
 // velocity-row kinds
@@ -115,7 +116,6 @@ struct Sched {
     DevBuf<int> it_phase, it_slot;   // outputs: phase, index inside the phase
     DevBuf<unsigned int> ph_count, ph_R, ph_gbase, ph_rbase;
     DevBuf<int4> g_info;             // per group slot: (a, b, nrows | type << 8, item)
-    DevBuf<unsigned int> g_rank;     // per group slot: rank/degree of the group on its bodies (ra | da<<8 | rb<<16 | db<<24)
     DevBuf<SchedHeader> hdr;         // 1 element
     // schedule cache: last step's groups, compared on device (coloured mode)
     DevBuf<int> prev_a, prev_b, prev_nt, prev_b1, prev_b2;
@@ -128,7 +128,7 @@ struct Sched {
         it_key.release(); it_phase.release(); it_slot.release(); ph_count.release(); ph_R.release();
         ph_gbase.release(); ph_rbase.release(); g_info.release(); hdr.release();
         prev_a.release(); prev_b.release(); prev_nt.release(); prev_b1.release(); prev_b2.release();
-        it_b1.release(); it_b2.release(); g_rank.release();
+        it_b1.release(); it_b2.release();
     }
 };
 
@@ -211,9 +211,8 @@ struct Context {
 
     // ---- rows
     size_t n_slots_max = 0, n_pslots_max = 0;
-    DevBuf<float4> r_jac;   // [6][n_slots_max]: J1.lin|J1.ang.x.. packed as 24 floats
+    DevBuf<float4> r_jac;   // [NB2_ROW_PLANES][n_slots_max] (layout: solve_common.cuh)
     DevBuf<float4> r_hdr;   // rhs, r, lo|mu, hi
-    DevBuf<int2> r_meta;    // kind, dependency slot
     DevBuf<float> r_imp;
     DevBuf<float4> p_row;   // [5][n_pslots_max] position rows
     // coloured mode: compact velocity data of a contact, same slot index as p_row:
@@ -230,18 +229,16 @@ struct Context {
     int last_mode = -1;
     bool stepped = false;
 
-    int coop_blocks_vel = 0, coop_blocks_pos = 0, coop_blocks_sched = 0, coop_blocks_col = 0, coop_blocks_flow = 0,
-        coop_blocks_pflow = 0, coop_blocks_staged = 0;
-    // coloured velocity kernel: 0 = phase barrier + register pipelining, 1 = barrier-free dataflow
-    // (per-body turn counters; measured slower, kept for the record), 2.. = staged variants (rows
-    // streamed through a shared-memory ring with cp.async, prefetched across the phase barrier)
+    int coop_blocks_vel = 0, coop_blocks_pos = 0, coop_blocks_sched = 0, coop_blocks_col = 0;
+    // coloured solve kernels: 0 = phase barrier + register pipelining (also the fallback for scenes with
+    // more than 384 groups per SM and phase), 2 = staged (rows streamed through a shared-memory ring
+    // with cp.async, prefetched across the phase barrier).  NB2_VELOCITY_KERNEL overrides (A/B runs).
     int velocity_kernel = 2;
     size_t smem_optin = 0;         // cudaDevAttrMaxSharedMemoryPerBlockOptin
     bool staged_attr = false, staged_pos_attr = false;
     DevBuf<float4> p_hdr;          // [5][n_ghdr_max] coloured position groups: bodies + collider-to-body poses
     size_t n_ghdr_max = 0;
     void* host_hdr = nullptr;      // pinned copy of vs.hdr (launch-geometry hint, never waited for)
-    DevBuf<unsigned int> turn, turn_p;
     DevBuf<unsigned int> bal;       // groups per colour while balancing
 };
 

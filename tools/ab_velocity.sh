@@ -7,6 +7,12 @@ print(d['value'], d['ms_per_step'], d['stage_ms']['velocity_kernel'], d['stage_m
 }
 timeout 300 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -2
 run A=1
-run NB2_STAGED_PENTRIES=1
-run NB2_STAGED_PENTRIES=3
-timeout 100 python tools/run_configs.py pyramid3 chains10k | cut -c1-600
+run NB2_STAGED_DEPTH=5
+run NB2_STAGED_DEPTH=3
+run NB2_VELOCITY_KERNEL=0
+timeout 300 python tools/run_configs.py | grep -v "^#" | python -c "
+import json,sys
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l[:200]); continue
+    print(d['config'], d['phases'], round(d['ms_per_step'],3), '%.3g'%d['body_steps_per_s'], d['stage_ms'], '%.3g'%d['residual_max'], d['non_finite'])"
