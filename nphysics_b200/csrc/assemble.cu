@@ -77,8 +77,10 @@ struct BodySide {
     float mask[6];
 };
 __device__ __forceinline__ void load_side(const BodyArrays& B, int idx, BodySide* s) {
-    const nb2_body& rb = B.raw[idx];
-    s->status = (int)rb.status;
+    // jacobian_mask[6], status, flags are the last two quads of the 176-byte record
+    const float4* rq = reinterpret_cast<const float4*>(&B.raw[idx]);
+    const float4 m0 = __ldg(rq + 9), m1 = __ldg(rq + 10);
+    s->status = __float_as_int(m1.z);
     float4 c = B.com_im[idx];
     s->com = f4_xyz(c);
     s->inv_mass = c.w;
@@ -90,8 +92,7 @@ __device__ __forceinline__ void load_side(const BodyArrays& B, int idx, BodySide
     s->v[0] = vl.x; s->v[1] = vl.y; s->v[2] = vl.z; s->v[3] = va.x; s->v[4] = va.y; s->v[5] = va.z;
     float4 el = B.ext[2 * idx], ea = B.ext[2 * idx + 1];
     s->e[0] = el.x; s->e[1] = el.y; s->e[2] = el.z; s->e[3] = ea.x; s->e[4] = ea.y; s->e[5] = ea.z;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) s->mask[k] = rb.jacobian_mask[k];
+    s->mask[0] = m0.x; s->mask[1] = m0.y; s->mask[2] = m0.z; s->mask[3] = m0.w; s->mask[4] = m1.x; s->mask[5] = m1.y;
 }
 
 __device__ __forceinline__ float dot6_seq(const float* a, const float* b) {
@@ -290,7 +291,14 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     }
     if (ci >= nC) return;
     const nb2_manifold& mf = manifolds[m];
-    const nb2_contact& c = contacts[ci];
+    // the 112-byte contact record as seven quads in one go (consecutive threads hold unrelated records)
+    struct alignas(16) ContactQuads { float4 q[7]; } cq;
+    {
+        const float4* cp = reinterpret_cast<const float4*>(&contacts[ci]);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) cq.q[k] = __ldg(cp + k);
+    }
+    const nb2_contact& c = *reinterpret_cast<const nb2_contact*>(&cq);
     BodySide s1, s2;
     load_side(B, mf.body1, &s1);
     load_side(B, mf.body2, &s2);

@@ -23,8 +23,11 @@ struct PosArrays {
     const float4* inv_i;
 };
 __device__ __forceinline__ void load_pos_body(const PosArrays& A, int idx, PosBody* o) {
-    const nb2_body& rb = A.raw[idx];
-    o->dynamic = rb.status == NB2_BODY_DYNAMIC;
+    // three quads of the 176-byte record instead of ten scalar loads: local_com (bytes 52..63),
+    // jacobian_mask[6] + status (bytes 144..171)
+    const float4* rq = reinterpret_cast<const float4*>(&A.raw[idx]);
+    const float4 q3 = __ldg(rq + 3), m0 = __ldg(rq + 9), m1 = __ldg(rq + 10);
+    o->dynamic = __float_as_int(m1.z) == NB2_BODY_DYNAMIC;
     o->bp.pose.t = f4_xyz(ldcg4(&A.pos_t[idx]));
     o->bp.pose.r = f4_quat(ldcg4(&A.pos_q[idx]));
     float4 c = ldcg4(&A.com_im[idx]);
@@ -34,9 +37,8 @@ __device__ __forceinline__ void load_pos_body(const PosArrays& A, int idx, PosBo
     o->inv_i.m[0][0] = r0.x; o->inv_i.m[0][1] = r0.y; o->inv_i.m[0][2] = r0.z;
     o->inv_i.m[1][0] = r1.x; o->inv_i.m[1][1] = r1.y; o->inv_i.m[1][2] = r1.z;
     o->inv_i.m[2][0] = r2.x; o->inv_i.m[2][1] = r2.y; o->inv_i.m[2][2] = r2.z;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) o->mask[k] = rb.jacobian_mask[k];
-    o->local_com = mk3(rb.local_com[0], rb.local_com[1], rb.local_com[2]);
+    o->mask[0] = m0.x; o->mask[1] = m0.y; o->mask[2] = m0.z; o->mask[3] = m0.w; o->mask[4] = m1.x; o->mask[5] = m1.y;
+    o->local_com = mk3(q3.y, q3.z, q3.w);
 }
 __device__ __forceinline__ void store_pos_body(const PosArrays& A, int idx, const PosBody& b) {
     stcg4(&A.pos_t[idx], xyz_f4(b.bp.pose.t, 0.f));

@@ -11,6 +11,7 @@
 // threads touch consecutive 16-byte words.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -19,6 +20,12 @@
 #include "math.cuh"
 
 namespace nb2 {
+
+// the kernels read parts of the body record as whole quads (assemble.cu load_side, solve_position.cuh)
+static_assert(sizeof(nb2_body) == 176 && offsetof(nb2_body, local_com) == 52 && offsetof(nb2_body, jacobian_mask) == 144 &&
+                  offsetof(nb2_body, status) == 168,
+              "nb2_body layout changed: update the quad loads");
+static_assert(sizeof(nb2_contact) == 112, "nb2_contact layout changed: update the quad loads in assemble.cu");
 
 // ---------------------------------------------------------------------------
 // error plumbing
