@@ -110,6 +110,13 @@ typedef struct nb2_body_state {
     float velocity[6];
 } nb2_body_state;
 
+/* ActivationStatus of a body (src/object/body.rs:65-125): the sleeping state that
+ * ActivationManager::update (src/detection/activation_manager.rs:60-201) maintains. */
+typedef struct nb2_activation {
+    float threshold; /* deactivation threshold; < 0 = None: the body never sleeps (default 0.01, body.rs:72-74) */
+    float energy;    /* low-pass filtered squared generalized velocity; 0 = asleep (new_active: 4 * threshold) */
+} nb2_activation;
+
 /* --------------------------------------------------------------- manifolds */
 /* LocalShapeApproximation geometry tags of ncollide's ContactKinematic
  * (SURVEY.md appendix B). */
@@ -274,9 +281,10 @@ int nb2_enable_timers(nb2_context* ctx, int enabled);
  * forces a fresh colouring each step (default: enabled). */
 int nb2_set_schedule_cache(nb2_context* ctx, int enabled);
 
-/* Device representation of contact groups in coloured mode: 0 (default) = the reference's 132-byte
- * rows [J1|J2|M^-1 J1|M^-1 J2] streamed from HBM; 1 = compact 80-byte contact records from which
- * the same rows are rebuilt in registers (bit-identical rows, a fifth of the bytes, more ALU). */
+/* Device representation of contact groups in coloured mode: 0 (default) = 100-byte rows
+ * [J1|J2|M^-1 J1 . ang|M^-1 J2 . ang|header] streamed from HBM (the linear half of M^-1 J is rebuilt
+ * from the inverse mass); 1 = compact 80-byte contact records from which the same rows are rebuilt
+ * in registers (bit-identical rows, a quarter of the bytes, more ALU). */
 int nb2_set_contact_layout(nb2_context* ctx, int layout);
 
 /* Replace the whole body set (n >= 1).  Marks dynamics dirty, like
@@ -292,6 +300,21 @@ int nb2_upload_manifolds(nb2_context* ctx, const nb2_manifold* manifolds, uint32
 int nb2_upload_joints(nb2_context* ctx, const nb2_joint* joints, uint32_t n_joints);
 /* Drop the contact impulse cache (a fresh ContactModel). */
 int nb2_clear_impulse_cache(nb2_context* ctx);
+
+/* Sleeping.  Off until nb2_upload_activation is called: every body is then awake for
+ * good, as with set_deactivation_threshold(None).  n must equal the body count. */
+int nb2_upload_activation(nb2_context* ctx, const nb2_activation* activation, uint32_t n);
+/* ActivationManager::update (activation_manager.rs:60-201; call site mechanical_world.rs:265-272),
+ * to be called between nb2_upload_manifolds / nb2_upload_joints and nb2_step: energy low-pass of the
+ * awake dynamic bodies (mix_factor: 0.01 in the reference, mechanical_world.rs:80), deferred
+ * activations (`to_activate`, body indices, may be NULL), islands = connected components over
+ * dynamic and kinematic bodies joined by the uploaded manifolds that hold at least one contact and by
+ * the unbroken joints, then an island whose bodies are all below their thresholds goes to sleep
+ * (velocities zeroed, rigid_body.rs:396-400) and any other island is woken up.  Sleeping dynamic
+ * bodies are left out of the following steps exactly like the reference leaves them out of
+ * active_bodies and of the manifold list (mechanical_world.rs:287-300).  Asynchronous. */
+int nb2_update_activation(nb2_context* ctx, float mix_factor, const int32_t* to_activate, uint32_t n_to_activate);
+int nb2_download_activation(nb2_context* ctx, nb2_activation* out, uint32_t n);
 
 /* One MoreauJeanSolver::step on the uploaded inputs, followed by the
  * kinematic-body integration and end-of-step dynamics refresh of

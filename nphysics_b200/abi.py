@@ -78,9 +78,22 @@ stats_dtype = np.dtype([
     ("t_step_ms", f4), ("pad2_", f4)], align=True)
 
 # index used by nb2_sizeof(which)
+# nb2_activation: ActivationStatus {threshold (< 0 = None), energy (0 = asleep)} (body.rs:65-125)
+activation_dtype = np.dtype([("threshold", f4), ("energy", f4)], align=True)
+DEFAULT_SLEEP_THRESHOLD = 0.01  # ActivationStatus::default_threshold (body.rs:72-74)
+
+
+def new_activation(n, threshold=DEFAULT_SLEEP_THRESHOLD):
+    """ActivationStatus::new_active for n bodies (threshold=None -> bodies that never sleep)."""
+    a = np.zeros(n, dtype=activation_dtype)
+    a["threshold"] = -1.0 if threshold is None else threshold
+    a["energy"] = 0.04 if threshold is None else 4.0 * threshold
+    return a
+
+
 SIZEOF_ORDER = [params_dtype, body_dtype, body_state_dtype, manifold_dtype, contact_dtype, joint_dtype,
-                stats_dtype]
-EXPECTED_SIZES = [64, 176, 52, 100, 112, 160, 88]
+                stats_dtype, activation_dtype]
+EXPECTED_SIZES = [64, 176, 52, 100, 112, 160, 88, 8]
 
 for _d, _s in zip(SIZEOF_ORDER, EXPECTED_SIZES):
     assert _d.itemsize == _s, (_d, _d.itemsize, _s)

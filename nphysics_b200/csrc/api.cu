@@ -45,6 +45,7 @@ static void release_all(Context* c) {
     c->r_jac.release(); c->r_hdr.release(); c->r_imp.release(); c->p_row.release();
     c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
     c->c_geo.release(); c->bal.release(); c->p_hdr.release(); c->slot_src.release();
+    c->true_status.release(); c->act.release(); c->cc_parent.release(); c->cc_can.release(); c->wake_list.release();
     if (c->host_hdr) cudaFreeHost(c->host_hdr);
     c->host_hdr = nullptr;
 }
@@ -186,6 +187,7 @@ int nb2_sizeof(int which) {
         case 4: return (int)sizeof(nb2_contact);
         case 5: return (int)sizeof(nb2_joint);
         case 6: return (int)sizeof(nb2_stats);
+        case 7: return (int)sizeof(nb2_activation);
         default: return NB2_ERR_INVALID_ARGUMENT;
     }
 }
@@ -330,6 +332,8 @@ int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
     NB2_TRY(ctx->ext.reserve(ctx, 2 * (size_t)n));
     NB2_TRY(ctx->lam.reserve(ctx, 2 * (size_t)n));
     NB2_TRY(ctx->b_status.reserve(ctx, n));
+    NB2_TRY(ctx->true_status.reserve(ctx, n));
+    if (n != ctx->n_bodies) ctx->sleeping = false;  // activation records of another body set
     ctx->n_bodies = n;
     uint32_t nd = 0;
     bool any_mask = false;
@@ -341,6 +345,7 @@ int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
     ctx->any_mask = any_mask;
     NB2_CUDA(ctx, cudaMemcpyAsync(ctx->raw.p, bodies, (size_t)n * sizeof(nb2_body), cudaMemcpyHostToDevice, ctx->stream));
     NB2_TRY(launch_unpack_bodies(ctx));
+    NB2_TRY(launch_apply_effective_status(ctx));  // sleeping bodies stay asleep across a re-upload of the same set
     // joints / manifolds referring to the old set are dropped
     ctx->n_manifolds = ctx->n_contacts = 0;
     ctx->n_joints = 0;
@@ -412,6 +417,45 @@ int nb2_clear_impulse_cache(nb2_context* h) {
     Context* ctx = &h->c;
     ctx->ht_cap[0] = ctx->ht_cap[1] = 0;
     ctx->imp_n[0] = ctx->imp_n[1] = 0;
+    return NB2_OK;
+}
+
+int nb2_upload_activation(nb2_context* h, const nb2_activation* activation, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!ctx->n_bodies) return set_error(ctx, NB2_ERR_NOT_READY, "upload bodies before their activation records");
+    if (!activation || n != ctx->n_bodies)
+        return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "activation records: expected %u, got %u", ctx->n_bodies, n);
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_TRY(ctx->act.reserve(ctx, n));
+    static_assert(sizeof(nb2_activation) == sizeof(float2), "nb2_activation is copied as float2");
+    NB2_CUDA(ctx, cudaMemcpyAsync(ctx->act.p, activation, (size_t)n * sizeof(nb2_activation), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    ctx->sleeping = true;
+    NB2_TRY(launch_apply_effective_status(ctx));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may free `activation` on return
+    return NB2_OK;
+}
+
+int nb2_update_activation(nb2_context* h, float mix_factor, const int32_t* to_activate, uint32_t n_to_activate) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!ctx->sleeping) return set_error(ctx, NB2_ERR_NOT_READY, "sleeping is off: call nb2_upload_activation first");
+    if (!(mix_factor >= 0.f)) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "the energy mixing factor must be >= 0");
+    if (n_to_activate && !to_activate) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null activation list");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_update_activation(ctx, mix_factor, to_activate, n_to_activate);
+}
+
+int nb2_download_activation(nb2_context* h, nb2_activation* out, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!ctx->sleeping) return set_error(ctx, NB2_ERR_NOT_READY, "sleeping is off: call nb2_upload_activation first");
+    if (!out || n > ctx->n_bodies) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "bad activation download range");
+    if (!n) return NB2_OK;
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_CUDA(ctx, cudaMemcpyAsync(out, ctx->act.p, (size_t)n * sizeof(nb2_activation), cudaMemcpyDeviceToHost, ctx->stream));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NB2_OK;
 }
 

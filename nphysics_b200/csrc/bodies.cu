@@ -14,7 +14,7 @@ static inline unsigned int nblk(size_t n) { return (unsigned int)((n + TPB - 1) 
 
 // raw AoS -> live SoA state (after nb2_upload_bodies)
 __global__ void k_unpack_bodies(const nb2_body* __restrict__ raw, unsigned int n, float4* pos_t, float4* pos_q,
-                                float4* vel, float4* com_im, int* status) {
+                                float4* vel, float4* com_im, int* status, int* true_status) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const nb2_body& b = raw[i];
@@ -28,6 +28,7 @@ __global__ void k_unpack_bodies(const nb2_body* __restrict__ raw, unsigned int n
     Vec3 com = pose_point(p, mk3(b.local_com[0], b.local_com[1], b.local_com[2]));
     com_im[i] = xyz_f4(com, 0.f);
     status[i] = (int)b.status;
+    true_status[i] = (int)b.status;
 }
 
 __global__ void k_unpack_states(const nb2_body_state* __restrict__ in, const nb2_body* __restrict__ raw,
@@ -205,7 +206,7 @@ int launch_unpack_bodies(Context* ctx) {
     if (!ctx->n_bodies) return NB2_OK;
     k_unpack_bodies<<<nblk(ctx->n_bodies), TPB, 0, ctx->stream>>>(ctx->raw.p, ctx->n_bodies, ctx->pos_t.p,
                                                                   ctx->pos_q.p, ctx->vel.p, ctx->com_im.p,
-                                                                  ctx->b_status.p);
+                                                                  ctx->b_status.p, ctx->true_status.p);
     ctx->launches++;
     NB2_CUDA(ctx, cudaGetLastError());
     return NB2_OK;

@@ -178,7 +178,13 @@ struct Context {
     DevBuf<float4> inv_i;         // [3n] rows of the inverse augmented angular inertia
     DevBuf<float4> ext;           // [2n] ext_vels = dt * acceleration
     DevBuf<float4> lam;           // [2n] mj_lambda_vel
-    DevBuf<int> b_status;
+    DevBuf<int> b_status;            // EFFECTIVE status (a sleeping dynamic body reads as static)
+    // ---- sleeping (activation.cu); off until nb2_upload_activation
+    bool sleeping = false;
+    DevBuf<int> true_status;         // status as uploaded
+    DevBuf<float2> act;              // threshold (< 0: None), energy (0: asleep)
+    DevBuf<unsigned int> cc_parent, cc_can;
+    DevBuf<int> wake_list;
 
     // ---- joints
     uint32_t n_joints = 0;
@@ -308,6 +314,8 @@ NB2_D void apply_displacement(BodyPose* b, Vec3 local_com, Vec3 lin, Vec3 ang) {
 // ---------------------------------------------------------------------------
 // bodies.cu
 int launch_unpack_bodies(Context* ctx);
+int launch_apply_effective_status(Context* ctx);
+int launch_update_activation(Context* ctx, float mix, const int32_t* to_activate, uint32_t n_list);
 int launch_refresh_dynamics(Context* ctx);
 int launch_integrate(Context* ctx, bool kinematic_only);
 int launch_pack_states(Context* ctx, nb2_body_state* d_out, uint32_t first, uint32_t n);

@@ -114,9 +114,12 @@ class RigidBody {
     friend class DefaultBodySet;
     friend class MoreauJeanSolver;
     nb2_body rec_;
+    nb2_activation act_;  // ActivationStatus (body.rs:65-125)
 
   public:
     RigidBody() {
+        act_.threshold = 0.01f;  // ActivationStatus::new_active (body.rs:77-82)
+        act_.energy = 0.04f;
         std::memset(&rec_, 0, sizeof(rec_));
         rec_.position[6] = 1.f;
         rec_.max_linear_velocity = FLT_MAX;
@@ -144,6 +147,11 @@ class RigidBody {
     bool is_dynamic() const { return rec_.status == NB2_BODY_DYNAMIC; }
     size_t status_dependent_ndofs() const { return is_dynamic() ? 6 : 0; }  // body.rs:287-293
     float mass() const { return rec_.mass; }
+    // ActivationStatus (body.rs:65-125, rigid_body.rs:391-405): a negative threshold stands for None
+    bool is_active() const { return act_.energy != 0.f; }
+    float activation_energy() const { return act_.energy; }
+    void set_deactivation_threshold(float threshold_or_negative_for_none) { act_.threshold = threshold_or_negative_for_none; }
+    float deactivation_threshold() const { return act_.threshold; }
     const nb2_body& record() const { return rec_; }
     nb2_body& record_mut() { return rec_; }
 };
@@ -174,6 +182,11 @@ class RigidBodyDesc {
         return *this;
     }
     RigidBodyDesc& status(BodyStatus s) { rb_.rec_.status = (uint32_t)s; return *this; }
+    /// rigid_body.rs desc `sleep_threshold`: negative = None (the body never sleeps).
+    RigidBodyDesc& sleep_threshold(float threshold_or_negative_for_none) {
+        rb_.act_.threshold = threshold_or_negative_for_none;
+        return *this;
+    }
     RigidBodyDesc& kinematic_translations(bool x, bool y, bool z) {
         rb_.rec_.jacobian_mask[0] = x ? 0.f : 1.f; rb_.rec_.jacobian_mask[1] = y ? 0.f : 1.f; rb_.rec_.jacobian_mask[2] = z ? 0.f : 1.f;
         return *this;
@@ -349,6 +362,15 @@ struct Counters {
 
 enum class SolverMode { ReferenceOrder = NB2_MODE_REFERENCE_ORDER, Coloured = NB2_MODE_COLOURED };
 
+// ActivationManager (src/detection/activation_manager.rs:11-45): the island building and the sleeping
+// rules themselves run on the device (nb2_update_activation); the host side keeps the mixing factor and
+// the deferred activation requests.
+struct ActivationManager {
+    float mix_factor = 0.01f;  // mechanical_world.rs:80
+    std::vector<int32_t> to_activate;
+    void deferred_activate(DefaultBodyHandle h) { to_activate.push_back((int32_t)h); }
+};
+
 // ---------------------------------------------------------------------------------------------
 // moreau_jean_solver.rs:14-90
 class MoreauJeanSolver {
@@ -356,6 +378,7 @@ class MoreauJeanSolver {
     std::unique_ptr<ContactModel> contact_model_;
     std::vector<nb2_body> body_stage_;
     std::vector<nb2_body_state> state_stage_;
+    std::vector<nb2_activation> act_stage_;
     std::vector<nb2_manifold> manifold_stage_;
     std::vector<nb2_contact> contact_stage_;
     std::vector<nb2_joint> joint_stage_;
@@ -386,8 +409,10 @@ class MoreauJeanSolver {
 
     /// MoreauJeanSolver::step (moreau_jean_solver.rs:47-61).  `island` / `island_joints` are implied: every
     /// dynamic body and every unbroken joint with a dynamic side (mechanical_world.rs:264-279).
+    /// `activation`: the world's ActivationManager, or null for a bare solver step (every body awake).
     void step(Counters& counters, DefaultBodySet& bodies, DefaultJointConstraintSet& joints,
-              const std::vector<ColliderContactManifold>& manifolds, const IntegrationParameters& parameters) {
+              const std::vector<ColliderContactManifold>& manifolds, const IntegrationParameters& parameters,
+              ActivationManager* activation = nullptr) {
         nb2_params p = parameters.to_abi(gravity);
         check(nb2_set_params(ctx_, &p));
         check(nb2_enable_timers(ctx_, counters.enabled ? 1 : 0));
@@ -395,6 +420,11 @@ class MoreauJeanSolver {
             body_stage_.resize(bodies.bodies_.size());
             for (size_t i = 0; i < body_stage_.size(); ++i) body_stage_[i] = bodies.bodies_[i].rec_;
             check(nb2_upload_bodies(ctx_, body_stage_.data(), (uint32_t)body_stage_.size()));
+            if (activation) {
+                act_stage_.resize(bodies.bodies_.size());
+                for (size_t i = 0; i < act_stage_.size(); ++i) act_stage_[i] = bodies.bodies_[i].act_;
+                check(nb2_upload_activation(ctx_, act_stage_.data(), (uint32_t)act_stage_.size()));
+            }
             bodies.dirty_ = false;
             joints.dirty_ = true;  // a new body set drops the joints on device
         }
@@ -415,9 +445,18 @@ class MoreauJeanSolver {
         }
         check(nb2_upload_manifolds(ctx_, manifold_stage_.data(), (uint32_t)manifold_stage_.size(), contact_stage_.data(),
                                    (uint32_t)contact_stage_.size()));
+        if (activation) {  // ActivationManager::update sits between the narrow phase and the solver (mechanical_world.rs:265-272)
+            check(nb2_update_activation(ctx_, activation->mix_factor, activation->to_activate.data(),
+                                        (uint32_t)activation->to_activate.size()));
+            activation->to_activate.clear();
+        }
         check(nb2_step(ctx_, (int)mode));
         // outputs are written in place into the bodies / joints, like the reference
         state_stage_.resize(bodies.bodies_.size());
+        if (activation) {
+            check(nb2_download_activation(ctx_, act_stage_.data(), (uint32_t)act_stage_.size()));
+            for (size_t i = 0; i < act_stage_.size(); ++i) bodies.bodies_[i].act_ = act_stage_[i];
+        }
         check(nb2_download_body_states(ctx_, state_stage_.data(), 0, (uint32_t)state_stage_.size()));
         for (size_t i = 0; i < state_stage_.size(); ++i) {
             std::memcpy(bodies.bodies_[i].rec_.position, state_stage_[i].position, sizeof(float) * 7);
@@ -459,9 +498,10 @@ class MechanicalWorld {
         : solver(std::unique_ptr<ContactModel>(new SignoriniCoulombPyramidModel()), device), gravity(g) {}
     void set_timestep(float dt) { integration_parameters.set_dt(dt); }
     float timestep() const { return integration_parameters.dt(); }
+    ActivationManager activation_manager;  // mechanical_world.rs:66,80
     void step(DefaultBodySet& bodies, DefaultJointConstraintSet& joints, const std::vector<ColliderContactManifold>& manifolds) {
         solver.gravity = gravity;
-        solver.step(counters, bodies, joints, manifolds, integration_parameters);
+        solver.step(counters, bodies, joints, manifolds, integration_parameters, &activation_manager);
     }
 };
 

@@ -20,7 +20,8 @@ EXPORTS = [
     "nb2_create", "nb2_destroy", "nb2_last_error", "nb2_set_params", "nb2_get_params", "nb2_enable_timers",
     "nb2_set_schedule_cache", "nb2_set_contact_layout",
     "nb2_upload_bodies", "nb2_upload_body_states", "nb2_upload_manifolds", "nb2_upload_joints",
-    "nb2_clear_impulse_cache", "nb2_step", "nb2_synchronize", "nb2_download_body_states",
+    "nb2_clear_impulse_cache", "nb2_upload_activation", "nb2_update_activation", "nb2_download_activation",
+    "nb2_step", "nb2_synchronize", "nb2_download_body_states",
     "nb2_download_contact_impulses", "nb2_download_joints", "nb2_get_stats", "nb2_get_timers",
     "nb2_launch_count",
 ]
@@ -158,6 +159,21 @@ class Solver:
 
     def clear_impulse_cache(self):
         self._chk(self.lib.nb2_clear_impulse_cache(self.h))
+
+    # ---- sleeping (ActivationManager)
+    def upload_activation(self, activation):
+        a = np.ascontiguousarray(activation, dtype=abi.activation_dtype)
+        self._chk(self.lib.nb2_upload_activation(self.h, abi.ptr(a), ctypes.c_uint32(len(a))))
+
+    def update_activation(self, mix_factor=0.01, to_activate=()):
+        lst = np.ascontiguousarray(to_activate, dtype=np.int32)
+        self._chk(self.lib.nb2_update_activation(self.h, ctypes.c_float(mix_factor),
+                                                 abi.ptr(lst) if len(lst) else None, ctypes.c_uint32(len(lst))))
+
+    def download_activation(self):
+        out = np.zeros(self.n_bodies, dtype=abi.activation_dtype)
+        self._chk(self.lib.nb2_download_activation(self.h, abi.ptr(out), ctypes.c_uint32(len(out))))
+        return out
 
     def step(self, mode=abi.MODE_COLOURED):
         self._chk(self.lib.nb2_step(self.h, int(mode)))

@@ -104,6 +104,21 @@ class Oracle:
     def clear_impulse_cache(self):
         self._chk(self.lib.nbo_clear_impulse_cache(self.h))
 
+    # ---- sleeping (ActivationManager::update restated, activation_manager.rs:60-201)
+    def upload_activation(self, activation):
+        a = np.ascontiguousarray(activation, dtype=abi.activation_dtype)
+        self._chk(self.lib.nbo_upload_activation(self.h, abi.ptr(a), ctypes.c_uint32(len(a))))
+
+    def update_activation(self, mix_factor=0.01, to_activate=()):
+        lst = np.ascontiguousarray(to_activate, dtype=np.int32)
+        self._chk(self.lib.nbo_update_activation(self.h, ctypes.c_float(mix_factor),
+                                                 abi.ptr(lst) if len(lst) else None, ctypes.c_uint32(len(lst))))
+
+    def download_activation(self):
+        out = np.zeros(self.n_bodies, dtype=abi.activation_dtype)
+        self._chk(self.lib.nbo_download_activation(self.h, abi.ptr(out), ctypes.c_uint32(len(out))))
+        return out
+
     def step(self, mode=None):
         self._chk(self.lib.nbo_step(self.h))
 

@@ -301,6 +301,9 @@ struct Body {
     Inertia inertia, augmented_mass, inv_augmented_mass;
     S6 acceleration;
     size_t companion_id;
+    /* ActivationStatus (body.rs:65-125): threshold < 0 stands for None (the body never sleeps) */
+    real act_threshold = -1, act_energy = (real)0.04;
+    bool is_active() const { return act_energy != 0; } /* body.rs:93-96 */
 
     size_t status_dependent_ndofs() const { return status == NB2_BODY_DYNAMIC ? 6 : 0; } /* body.rs:287-293 */
 
@@ -602,8 +605,10 @@ struct World {
     nb2_params params;
     real inv_dt;
     std::vector<Body> bodies;
-    std::vector<nb2_manifold> manifolds;
+    std::vector<nb2_manifold> uploaded_manifolds; /* every contact pair of the narrow phase */
+    std::vector<nb2_manifold> manifolds;          /* the step's list (mechanical_world.rs:287-300) */
     std::vector<nb2_contact> contacts;
+    bool sleeping_enabled = false;
     std::vector<Joint> joints;
 
     /* MoreauJeanSolver state (moreau_jean_solver.rs:14-23) */
@@ -878,9 +883,93 @@ struct World {
         if (broken) r.broken = 1;
     }
 
-    /* JointConstraint::is_active (joint_constraint.rs:219-228); all bodies are awake here. */
+    /* JointConstraint::is_active (joint_constraint.rs:219-228). */
     bool joint_is_active(const Joint& j) const {
-        return bodies[j.rec.body1].status_dependent_ndofs() != 0 || bodies[j.rec.body2].status_dependent_ndofs() != 0;
+        const Body& b1 = bodies[j.rec.body1];
+        const Body& b2 = bodies[j.rec.body2];
+        return (b1.status_dependent_ndofs() != 0 && b1.is_active()) || (b2.status_dependent_ndofs() != 0 && b2.is_active());
+    }
+
+    /* ------------------------------------------------------------ sleeping */
+    /* utils/union_find.rs:30-59 */
+    struct UnionFindSet {
+        size_t parent, rank;
+    };
+    static size_t uf_find(size_t x, std::vector<UnionFindSet>& sets) {
+        if (sets[x].parent != x) sets[x].parent = uf_find(sets[x].parent, sets);
+        return sets[x].parent;
+    }
+    static void uf_union(size_t x, size_t y, std::vector<UnionFindSet>& sets) {
+        size_t xr = uf_find(x, sets), yr = uf_find(y, sets);
+        if (xr == yr) return;
+        size_t rx = sets[xr].rank, ry = sets[yr].rank;
+        if (rx < ry) sets[xr].parent = yr;
+        else if (rx > ry) sets[yr].parent = xr;
+        else {
+            sets[yr].parent = xr;
+            sets[xr].rank = rx + 1;
+        }
+    }
+    /* ActivationManager::update (detection/activation_manager.rs:60-201).  `to_activate` are the
+     * deferred_activate handles.  Contact pairs = every uploaded manifold with at least one contact. */
+    void update_activation(real mix_factor, const int32_t* to_activate, uint32_t n_to_activate) {
+        std::vector<size_t> id_to_body;
+        std::vector<size_t> companion(bodies.size(), (size_t)-1);
+        for (size_t i = 0; i < bodies.size(); ++i) { /* :79-93 */
+            Body& b = bodies[i];
+            if (b.status_dependent_ndofs() != 0) {
+                if (b.is_active() && b.act_threshold >= 0) { /* update_energy :47-58 */
+                    const real v[6] = {b.velocity.lin.x, b.velocity.lin.y, b.velocity.lin.z,
+                                       b.velocity.ang.x, b.velocity.ang.y, b.velocity.ang.z};
+                    real nsq = 0; /* nalgebra norm_squared of a 6-slice: sequential (appendix B) */
+                    for (int k = 0; k < 6; ++k) nsq += v[k] * v[k];
+                    real e = ((real)1 - mix_factor) * b.act_energy + mix_factor * nsq;
+                    b.act_energy = std::min(e, b.act_threshold * (real)4);
+                }
+                companion[i] = id_to_body.size();
+                id_to_body.push_back(i);
+            }
+            if (b.status == NB2_BODY_KINEMATIC) {
+                companion[i] = id_to_body.size();
+                id_to_body.push_back(i);
+            }
+        }
+        for (uint32_t k = 0; k < n_to_activate; ++k) { /* :100-108; Body::activate body.rs:338-342 */
+            if (to_activate[k] < 0 || (size_t)to_activate[k] >= bodies.size()) continue;
+            Body& b = bodies[to_activate[k]];
+            if (b.act_threshold >= 0) b.act_energy = b.act_threshold * (real)2;
+        }
+        std::vector<UnionFindSet> ufind(id_to_body.size());
+        std::vector<char> can_deactivate(id_to_body.size(), 1);
+        for (size_t i = 0; i < ufind.size(); ++i) ufind[i] = UnionFindSet{i, 0};
+        auto make_union = [&](int h1, int h2) { /* :138-152 */
+            const Body& b1 = bodies[h1];
+            const Body& b2 = bodies[h2];
+            if ((b1.status_dependent_ndofs() != 0 || b1.status == NB2_BODY_KINEMATIC) &&
+                (b2.status_dependent_ndofs() != 0 || b2.status == NB2_BODY_KINEMATIC))
+                uf_union(companion[h1], companion[h2], ufind);
+        };
+        for (const nb2_manifold& m : uploaded_manifolds)
+            if (m.num_contacts > 0) make_union(m.body1, m.body2);
+        for (const Joint& j : joints)
+            if (!j.rec.broken) make_union(j.rec.body1, j.rec.body2);
+        for (size_t i = 0; i < ufind.size(); ++i) { /* :170-182 */
+            size_t root = uf_find(i, ufind);
+            const Body& b = bodies[id_to_body[i]];
+            can_deactivate[root] = b.act_threshold >= 0 ? (can_deactivate[root] && b.act_energy < b.act_threshold) : 0;
+        }
+        for (size_t i = 0; i < ufind.size(); ++i) { /* :185-206 */
+            size_t root = uf_find(i, ufind);
+            Body& b = bodies[id_to_body[i]];
+            if (can_deactivate[root]) {
+                if (b.is_active()) { /* RigidBody::deactivate rigid_body.rs:396-400 */
+                    b.act_energy = 0;
+                    b.velocity = S6{v3(0, 0, 0), v3(0, 0, 0)};
+                }
+            } else if (b.status != NB2_BODY_KINEMATIC) {
+                if (!b.is_active() && b.act_threshold >= 0) b.act_energy = b.act_threshold * (real)2;
+            }
+        }
     }
 
     /* ----------------------------------------------- joint position rows */
@@ -1468,10 +1557,20 @@ struct World {
         for (Body& b : bodies) b.update_dynamics(dt);
         V3 g = v3(params.gravity[0], params.gravity[1], params.gravity[2]);
         for (Body& b : bodies) b.update_acceleration(g);
-        /* :264-279: no sleeping here -- every dynamic body is in the island */
+        /* :264-279: active_bodies = the non-kinematic members of the islands that stay awake; the caller
+         * ran update_activation (or sleeping is off and every dynamic body is active) */
         island.clear();
         for (size_t i = 0; i < bodies.size(); ++i)
-            if (bodies[i].status == NB2_BODY_DYNAMIC) island.push_back((int)i);
+            if (bodies[i].status == NB2_BODY_DYNAMIC && bodies[i].is_active()) island.push_back((int)i);
+        /* :287-300 contact manifolds of the step */
+        manifolds.clear();
+        for (const nb2_manifold& m : uploaded_manifolds) {
+            const Body& b1 = bodies[m.body1];
+            const Body& b2 = bodies[m.body2];
+            if (m.num_contacts > 0 && b1.status != NB2_BODY_DISABLED && b2.status != NB2_BODY_DISABLED &&
+                ((b1.status_dependent_ndofs() != 0 && b1.is_active()) || (b2.status_dependent_ndofs() != 0 && b2.is_active())))
+                manifolds.push_back(m);
+        }
         active_joints.clear();
         for (size_t i = 0; i < joints.size(); ++i)
             if (!joints[i].rec.broken && joint_is_active(joints[i])) active_joints.push_back(i);
@@ -1662,8 +1761,36 @@ int nbo_upload_manifolds(void* wp, const nb2_manifold* m, uint32_t nm, const nb2
             (size_t)m[i].body2 >= w->bodies.size() || (uint64_t)m[i].first_contact + m[i].num_contacts > nc)
             return NB2_ERR_BAD_INDEX;
     }
+    w->uploaded_manifolds.assign(m, m + nm);
     w->manifolds.assign(m, m + nm);
     w->contacts.assign(c, c + nc);
+    return NB2_OK;
+}
+
+/* Sleeping: nb2_activation records (threshold < 0 = None, energy 0 = asleep). */
+int nbo_upload_activation(void* wp, const nb2_activation* a, uint32_t n) {
+    World* w = (World*)wp;
+    if (n != w->bodies.size()) return NB2_ERR_INVALID_ARGUMENT;
+    for (uint32_t i = 0; i < n; ++i) {
+        w->bodies[i].act_threshold = a[i].threshold;
+        w->bodies[i].act_energy = a[i].energy;
+    }
+    w->sleeping_enabled = true;
+    return NB2_OK;
+}
+int nbo_update_activation(void* wp, float mix_factor, const int32_t* to_activate, uint32_t n) {
+    World* w = (World*)wp;
+    if (!w->sleeping_enabled) return NB2_ERR_NOT_READY;
+    w->update_activation((real)mix_factor, to_activate, n);
+    return NB2_OK;
+}
+int nbo_download_activation(void* wp, nb2_activation* out, uint32_t n) {
+    World* w = (World*)wp;
+    if (n > w->bodies.size()) return NB2_ERR_BAD_INDEX;
+    for (uint32_t i = 0; i < n; ++i) {
+        out[i].threshold = (float)w->bodies[i].act_threshold;
+        out[i].energy = (float)w->bodies[i].act_energy;
+    }
     return NB2_OK;
 }
 

@@ -70,6 +70,14 @@ pub struct nb2_body_state {
     pub velocity: [f32; 6],
 }
 
+/// ActivationStatus (src/object/body.rs:65-125): `threshold < 0` stands for `None`, `energy == 0` for asleep.
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct nb2_activation {
+    pub threshold: f32,
+    pub energy: f32,
+}
+
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]
 pub struct nb2_manifold {
@@ -181,6 +189,9 @@ extern "C" {
                                 contacts: *const nb2_contact, n_contacts: u32) -> i32;
     pub fn nb2_upload_joints(ctx: *mut nb2_context, joints: *const nb2_joint, n_joints: u32) -> i32;
     pub fn nb2_clear_impulse_cache(ctx: *mut nb2_context) -> i32;
+    pub fn nb2_upload_activation(ctx: *mut nb2_context, activation: *const nb2_activation, n: u32) -> i32;
+    pub fn nb2_update_activation(ctx: *mut nb2_context, mix_factor: f32, to_activate: *const i32, n_to_activate: u32) -> i32;
+    pub fn nb2_download_activation(ctx: *mut nb2_context, out: *mut nb2_activation, n: u32) -> i32;
     pub fn nb2_step(ctx: *mut nb2_context, mode: i32) -> i32;
     pub fn nb2_synchronize(ctx: *mut nb2_context) -> i32;
     pub fn nb2_download_body_states(ctx: *mut nb2_context, out: *mut nb2_body_state, first: u32, n: u32) -> i32;
