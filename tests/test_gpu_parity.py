@@ -424,3 +424,30 @@ def test_compact_contact_layout_matches_row_layout():
     assert rel_err(b1["position"], b0["position"]) < 1e-5
     assert float(s1["residual_max"]) == pytest.approx(float(s0["residual_max"]), rel=0.2)
     assert float(s1["max_penetration"]) == pytest.approx(float(s0["max_penetration"]), rel=0.05, abs=1e-5)
+
+
+def test_staged_and_register_pipelined_kernels_agree(monkeypatch):
+    """Coloured mode has two implementations of each solve loop: the staged kernels (cp.async ring in
+    shared memory, default) and the register-pipelined ones (the fallback for scenes with more than
+    384 groups per SM and phase).  Same schedule, same row order; the staged translation unit may
+    contract to FMA, so agreement is to rounding.  Mixed scene: contacts + joints + a masked body."""
+    sc = scenes.joint_chains(24, 6, kind="mixed", with_ground_collider=True, ground_y=-0.22, pitch=6.0)
+    gen = scenes.ContactGenerator(sc, search=0.0)
+    m, c = gen.generate()
+    outs = []
+    for variant in ("0", "2"):
+        monkeypatch.setenv("NB2_VELOCITY_KERNEL", variant)  # read at nb2_create
+        s = new_solver()
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+        s.upload_joints(sc.joints)
+        for _ in range(5):
+            s.upload_manifolds(m, c)
+            s.step(COL)
+        outs.append((s.download_body_states(), s.download_contact_impulses(), s.get_stats()))
+    (b0, i0, s0), (b1, i1, s1) = outs
+    assert int(s0["n_phases_velocity"]) == int(s1["n_phases_velocity"])
+    assert rel_err(b1["position"], b0["position"]) < 1e-5
+    assert np.abs(b1["velocity"] - b0["velocity"]).max() < 1e-3
+    assert rel_err(i1, i0) < 2e-3
+    assert int(s0["non_finite"]) == 0 and int(s1["non_finite"]) == 0
