@@ -10,6 +10,9 @@
 //   * NB2_MODE_COLOURED: phase = colour from a Jones-Plassmann greedy colouring of the group
 //     conflict graph, computed on device with per-body colour bitmasks.
 // Non-dynamic bodies (ground, kinematic) never create conflicts.
+#include <stddef.h>
+#include <stdlib.h>
+
 #include "solver.cuh"
 
 namespace nb2 {
@@ -446,7 +449,7 @@ __global__ void k_cond_zero(const unsigned int* __restrict__ changed, unsigned i
     if (i < nwords) p[i] = 0u;
 }
 __global__ void k_cond_fill_int(const unsigned int* __restrict__ changed, int* p, size_t n, int v) {
-    if (*changed == 0u) return;
+    if (*changed == 0u || *changed == 2u) return;  // a refinement pass starts from the colours it has
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
@@ -468,11 +471,25 @@ __global__ void k_compare_snapshot(size_t n, const int* __restrict__ it_a, const
     prev_b2[i] = b2;
 }
 
+// Schedule-cache verdict of the step: *changed = 0 keep everything, 1 (or ~0) colour from scratch, 2 = the
+// graph is unchanged but the colouring still has refinement passes to run (one iterated-greedy pass per
+// step, so a scene pays for them only while it stays put).
+#define NB2_SCHED_REFINE 2u
+__global__ void k_refine_decide(unsigned int* changed, SchedHeader* hdr) {
+    if (*changed != 0u) {
+        hdr->refine_left = NB2_IG_REFINE;
+    } else if (hdr->refine_left > 0u) {
+        *changed = NB2_SCHED_REFINE;
+        hdr->refine_left -= 1u;
+    }
+}
+
 __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict__ it_a, const int* __restrict__ it_b,
                                                 const int* __restrict__ it_type, int* phase,
                                                 unsigned long long* cmask, unsigned long long* best,
                                                 unsigned int* flags /*3*/, SchedHeader* hdr, unsigned int* barrier,
-                                                const unsigned int* __restrict__ changed, unsigned int* bal) {
+                                                const unsigned int* __restrict__ changed, unsigned int* bal,
+                                                int* tmp_phase, size_t nb, int ig_passes, int* raw_phase) {
     if (*changed == 0u) return;  // cached colouring still valid (uniform over the grid: no barrier was touched)
     GridBarrier gb;
     gb.init(barrier);
@@ -528,6 +545,92 @@ __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict_
         }
         gb.sync();
     }
+    // ---- iterated greedy (Culberson).  Groups of one colour share no body, so a whole colour class can be
+    // recoloured at once with plain first-fit against the classes already redone; visiting the classes in
+    // any order never needs more colours than before and often fewer.  Orders tried in turn: reverse,
+    // largest class first, reverse.  Colours cost the solve kernels one barrier + one latency chain each.
+    // fresh colouring: NB2_IG_PASSES passes now; refinement step: one pass, its order picked by how many are left
+    const bool refine = *changed == NB2_SCHED_REFINE;
+    const int ig_first = refine ? (int)(NB2_IG_REFINE - hdr->refine_left) : 0;
+    const int ig_last = refine ? ig_first + 1 : ig_passes;
+    // the passes work on the colouring as it was BEFORE balancing (kept in raw_phase): balanced classes are
+    // all equally full and none of them can be absorbed any more
+    if (refine) {
+        for (size_t i = tid; i < n; i += stride)
+            if (it_type[i] != NB2_ITEM_INVALID) phase[i] = raw_phase[i];
+        gb.sync();
+    }
+    for (int pass = ig_first; pass < ig_last; ++pass) {
+        __shared__ unsigned int s_order[NB2_MAX_COLOURS];
+        __shared__ unsigned int s_ig_cnt[NB2_MAX_COLOURS];
+        __shared__ unsigned int s_ig_C;
+        for (size_t i = tid; i < NB2_MAX_COLOURS; i += stride) bal[i] = 0u;
+        for (size_t w = tid; w < nb * (size_t)NB2_MASK_WORDS; w += stride) cmask[w] = 0ull;
+        gb.sync();
+        for (size_t i = tid; i < n; i += stride)
+            if (it_type[i] != NB2_ITEM_INVALID) atomicAdd(&bal[min((unsigned int)phase[i], (unsigned int)NB2_MAX_COLOURS - 1u)], 1u);
+        gb.sync();
+        for (unsigned int c = threadIdx.x; c < NB2_MAX_COLOURS; c += blockDim.x) s_ig_cnt[c] = __ldcg(&bal[c]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int C = 0;
+            for (unsigned int c = 0; c < NB2_MAX_COLOURS; ++c)
+                if (s_ig_cnt[c]) C = c + 1;
+            s_ig_C = C;
+            if (pass % 3 == 1) {  // largest class first (selection sort on the counts; ties by index)
+                for (unsigned int k = 0; k < C; ++k) {
+                    unsigned int best_c = 0, best_n = 0;
+                    bool found = false;
+                    for (unsigned int c = 0; c < C; ++c) {
+                        if (s_ig_cnt[c] == 0xFFFFFFFFu) continue;
+                        if (!found || s_ig_cnt[c] > best_n) {
+                            best_c = c;
+                            best_n = s_ig_cnt[c];
+                            found = true;
+                        }
+                    }
+                    s_order[k] = best_c;
+                    s_ig_cnt[best_c] = 0xFFFFFFFFu;
+                }
+            } else {
+                for (unsigned int k = 0; k < C; ++k) s_order[k] = C - 1 - k;
+            }
+        }
+        __syncthreads();
+        const unsigned int C = s_ig_C;
+        for (unsigned int k = 0; k < C; ++k) {
+            const int c = (int)s_order[k];
+            for (size_t i = tid; i < n; i += stride) {
+                if (it_type[i] == NB2_ITEM_INVALID || phase[i] != c) continue;
+                const int a = it_a[i], b = it_b[i];
+                int colour = -1;
+#pragma unroll
+                for (int w = 0; w < NB2_MASK_WORDS; ++w) {
+                    unsigned long long ua = 0, ub = 0;
+                    if (a >= 0) ua = __ldcg(&cmask[(size_t)a * NB2_MASK_WORDS + w]);
+                    if (b >= 0) ub = __ldcg(&cmask[(size_t)b * NB2_MASK_WORDS + w]);
+                    const unsigned long long used = ua | ub;
+                    if (colour < 0 && used != ~0ull) {
+                        const int bit = __ffsll((long long)~used) - 1;
+                        colour = w * 64 + bit;
+                        const unsigned long long m = 1ull << bit;
+                        if (a >= 0) __stcg(&cmask[(size_t)a * NB2_MASK_WORDS + w], ua | m);
+                        if (b >= 0) __stcg(&cmask[(size_t)b * NB2_MASK_WORDS + w], ub | m);
+                    }
+                }
+                if (colour < 0) colour = c;  // cannot happen: the old colouring is a witness
+                tmp_phase[i] = colour;
+            }
+            gb.sync();
+        }
+        for (size_t i = tid; i < n; i += stride)
+            if (it_type[i] != NB2_ITEM_INVALID) phase[i] = tmp_phase[i];
+        gb.sync();
+    }
+    for (size_t i = tid; i < n; i += stride)
+        if (it_type[i] != NB2_ITEM_INVALID) raw_phase[i] = phase[i];
+    for (size_t i = tid; i < NB2_MAX_COLOURS; i += stride) bal[i] = 0u;
+    gb.sync();
     // ---- balancing.  First-fit colouring fills the low colours to the brim (~N_bodies/2 groups) and
     // leaves a tail of nearly empty ones, but every colour costs the solve kernels a grid barrier plus
     // one group's latency chain however few groups it holds, and an over-full colour makes threads run
@@ -707,7 +810,8 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     } else {
         s->cache_valid = false;
     }
-    k_cond_zero<<<1, 32, 0, ctx->stream>>>(changed, (unsigned int*)s->hdr.p, sizeof(SchedHeader) / 4);
+    if (mode == NB2_MODE_COLOURED) k_refine_decide<<<1, 1, 0, ctx->stream>>>(changed, s->hdr.p);
+    k_cond_zero<<<1, 32, 0, ctx->stream>>>(changed, (unsigned int*)s->hdr.p, offsetof(SchedHeader, refine_left) / 4);
     k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_count.p, s->max_phases + 1);
     k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_R.p, s->max_phases + 1);
     ctx->launches += 3;
@@ -779,7 +883,12 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
         unsigned int* bar = ctx->barrier.p;
         const unsigned int* ch = changed;
         unsigned int* bl = ctx->bal.p;
-        void* args[] = {&n_, &ia, &ib, &ty, &ph, &cm, &be, &flags, &hd, &bar, &ch, &bl};
+        int* tmp = s->it_slot.p;  // free until k_phase_hist fills it
+        size_t nb_ = nb;
+        int igp = NB2_IG_PASSES;
+        NB2_TRY(s->it_phase_raw.reserve(ctx, n));
+        int* raw = s->it_phase_raw.p;
+        void* args[] = {&n_, &ia, &ib, &ty, &ph, &cm, &be, &flags, &hd, &bar, &ch, &bl, &tmp, &nb_, &igp, &raw};
         NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_colour, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
         ctx->launches++;
     }

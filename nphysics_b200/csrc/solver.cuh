@@ -83,6 +83,8 @@ struct DevBuf {
 #define NB2_MAX_COLOURS (64 * NB2_MASK_WORDS)
 #define NB2_ROW_PLANES 5       // jacobian quads per velocity row (solve_common.cuh)
 #define NB2_BALANCE_ROUNDS 12
+#define NB2_IG_PASSES 1        // iterated-greedy passes right after a fresh colouring ...
+#define NB2_IG_REFINE 12       // ... and one more per following step with an unchanged conflict graph, up to this many
 
 // velocity-row kinds
 #define NB2_ROW_NONE 0
@@ -109,7 +111,8 @@ struct SchedHeader {
     unsigned int n_slots;    // total row slots
     unsigned int overflow;   // != 0: colouring ran out of colours / phases
     unsigned int work;       // scratch: "something changed" flag
-    unsigned int pad[3];
+    unsigned int refine_left;  // iterated-greedy passes still to run on steps whose conflict graph is unchanged
+    unsigned int pad[2];
 };
 
 struct Sched {
@@ -121,6 +124,7 @@ struct Sched {
     DevBuf<int> it_src;              // joint index / chunk index
     DevBuf<unsigned long long> it_key;  // sequential position (reference order)
     DevBuf<int> it_phase, it_slot;   // outputs: phase, index inside the phase
+    DevBuf<int> it_phase_raw;        // coloured: the colouring before balancing (what the refinement passes work on)
     DevBuf<unsigned int> ph_count, ph_R, ph_gbase, ph_rbase;
     DevBuf<int4> g_info;             // per group slot: (a, b, nrows | type << 8, item)
     DevBuf<SchedHeader> hdr;         // 1 element
@@ -135,7 +139,7 @@ struct Sched {
         it_key.release(); it_phase.release(); it_slot.release(); ph_count.release(); ph_R.release();
         ph_gbase.release(); ph_rbase.release(); g_info.release(); hdr.release();
         prev_a.release(); prev_b.release(); prev_nt.release(); prev_b1.release(); prev_b2.release();
-        it_b1.release(); it_b2.release();
+        it_b1.release(); it_b2.release(); it_phase_raw.release();
     }
 };
 

@@ -96,5 +96,5 @@ if __name__ == "__main__":
             copies = 4096
             sc = scenes.tile(base, copies)
             m, c = tile_contacts(bm, bc, copies, len(base.bodies))
-            run(name, sc, m, c, 8, 3, steps=10, settle=10)
+            run(name, sc, m, c, 8, 3, steps=10, settle=16)  # 12 refinement steps of the colouring first
         print("# %s took %.1f s wall" % (name, time.time() - t0), flush=True)
