@@ -147,6 +147,16 @@ NB2_D Quat quat_from_scaled_axis(Vec3 axisangle) {
     Vec3 h = axisangle / 2.f;
     float nn = norm_sq3(h);
     if (nn <= NB2_F32_EPS * NB2_F32_EPS) return mkq(0.f, 0.f, 0.f, 1.f);
+#ifdef NB2_COLOURED_TU
+    // coloured-mode kernels (tolerance-judged): sin(n)/n and cos(n) are even functions of n, so for the small
+    // rotations of a position correction (|w| <= max_angular_correction = 0.2, n <= 0.1) their Taylor
+    // polynomials in n^2 are exact to f32 rounding (next terms < 1e-11) and need no sqrt, division or sincos
+    if (nn <= 0.015625f) {
+        const float s_over_n = 1.f + nn * (-1.f / 6.f + nn * (1.f / 120.f + nn * (-1.f / 5040.f)));
+        const float c = 1.f + nn * (-0.5f + nn * (1.f / 24.f + nn * (-1.f / 720.f)));
+        return mkq(h.x * s_over_n, h.y * s_over_n, h.z * s_over_n, c);
+    }
+#endif
     float n = sqrtf(nn);
     float s, c;
     sincosf(n, &s, &c);

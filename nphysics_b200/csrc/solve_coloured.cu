@@ -496,13 +496,17 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                     c2.t = mk3(h3.x, h3.y, h3.z);
                     c2.r = mkq(h3.w, h4.x, h4.y, h4.z);
                     const int ncc = (info.z & 0xFF) / rows_div;
+                    // colliders sitting at their body's origin (the usual case) need no pose product
+                    const bool id1 = h1.x == 0.f && h1.y == 0.f && h1.z == 0.f && h1.w == 0.f && h2.x == 0.f && h2.y == 0.f && h2.z == 1.f;
+                    const bool id2 = h3.x == 0.f && h3.y == 0.f && h3.z == 0.f && h3.w == 0.f && h4.x == 0.f && h4.y == 0.f && h4.z == 1.f;
                     bool moved1 = false, moved2 = false;
 #pragma unroll 1
                     for (int lcc = 0; lcc < ncc; ++lcc) {
                         const float4* rq = q + (size_t)(5 + 5 * lcc) * TPBK;
                         const float4 l1 = rq[0], l2 = rq[1 * TPBK], d1 = rq[2 * TPBK], d2 = rq[3 * TPBK], n1 = rq[4 * TPBK];
                         // update_contact_constraint (nonlinear_sor_prox.rs:156-294)
-                        const Pose m1 = pose_mul(b1.bp.pose, c1), m2 = pose_mul(b2.bp.pose, c2);
+                        const Pose m1 = id1 ? b1.bp.pose : pose_mul(b1.bp.pose, c1);
+                        const Pose m2 = id2 ? b2.bp.pose : pose_mul(b2.bp.pose, c2);
                         ContactEval cev;
                         if (!kinematic_contact(l1, l2, d1, d2, n1, m1, m2, &cev)) continue;
                         const float rhs = clamp_rhs(-cev.depth, false, P);

@@ -7,7 +7,7 @@ print(d['value'], d['ms_per_step'], d['stage_ms'], d['roofline']['frac'], d['pha
 }
 timeout 300 python -m pytest tests/ -x -q -m gpu -s 2>&1 | grep -E "quality|passed|failed|^E " | cut -c1-250
 run A=1
-EXTRA=--no-schedule-cache run A=2
+
 timeout 300 python tools/run_configs.py | grep -v "^#" | python -c "
 import json,sys
 for l in sys.stdin:
