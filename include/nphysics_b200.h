@@ -320,6 +320,12 @@ int nb2_download_activation(nb2_context* ctx, nb2_activation* out, uint32_t n);
  * kinematic-body integration and end-of-step dynamics refresh of
  * mechanical_world.rs:328-346.  Asynchronous on the context's stream. */
 int nb2_step(nb2_context* ctx, int mode);
+/* One MoreauJeanSolver::step_ccd (moreau_jean_solver.rs:94-127): a CCD sub-step on the uploaded inputs --
+ * assemble, position resolution FIRST, then velocity resolution and integration; impulses are not cached
+ * and kinematic bodies are not integrated.  The caller is the CCD driver (solve_ccd,
+ * mechanical_world.rs:561-908: times of impact, frozen bodies, sub-step parameters with
+ * warmstart_coeff = 0), which is not part of this library.  Asynchronous. */
+int nb2_step_ccd(nb2_context* ctx, int mode);
 int nb2_synchronize(nb2_context* ctx);
 
 int nb2_download_body_states(nb2_context* ctx, nb2_body_state* out, uint32_t first, uint32_t n);

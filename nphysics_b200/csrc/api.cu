@@ -74,6 +74,28 @@ static int check_flags(Context* ctx) {
     return NB2_OK;
 }
 
+// MoreauJeanSolver::step_ccd (moreau_jean_solver.rs:94-127): the same stages in the order assemble,
+// position, velocity, integrate; no impulse caching, no kinematic integration (the CCD driver around it,
+// mechanical_world.rs:561-908, owns those).
+static int do_step_ccd(Context* ctx, int mode) {
+    ctx->step_layout = (mode != NB2_MODE_REFERENCE_ORDER && ctx->contact_layout == 1) ? 1 : 0;
+    ctx->cur = 1 - ctx->cur;  // assembly warm-starts from the buffer "before cur": point it at the last one written
+    NB2_TRY(launch_refresh_dynamics(ctx));
+    ctx->max_chunks = (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
+    NB2_TRY(launch_build_items(ctx, mode));
+    NB2_TRY(launch_schedule(ctx, &ctx->vs, mode));
+    if (mode == NB2_MODE_REFERENCE_ORDER) NB2_TRY(launch_schedule(ctx, &ctx->ps, mode));
+    NB2_TRY(launch_assemble(ctx, mode));
+    NB2_TRY(launch_position_solve(ctx, mode));
+    NB2_TRY(launch_velocity_solve(ctx, mode));
+    NB2_TRY(launch_integrate(ctx, false));
+    ctx->cur = 1 - ctx->cur;  // nothing was cached: the next step still reads the same buffer
+    ctx->ev_valid = false;
+    ctx->last_mode = mode;
+    ctx->stepped = true;
+    return NB2_OK;
+}
+
 static int do_step(Context* ctx, int mode) {
     const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
     ctx->cur = 1 - ctx->cur;
@@ -467,6 +489,16 @@ int nb2_step(nb2_context* h, int mode) {
     if (!ctx->n_bodies || !ctx->have_params) return set_error(ctx, NB2_ERR_NOT_READY, "upload bodies and params before stepping");
     NB2_CUDA(ctx, cudaSetDevice(ctx->device));
     return do_step(ctx, mode);
+}
+
+int nb2_step_ccd(nb2_context* h, int mode) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (mode != NB2_MODE_REFERENCE_ORDER && mode != NB2_MODE_COLOURED)
+        return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "unknown step mode %d", mode);
+    if (!ctx->n_bodies || !ctx->have_params) return set_error(ctx, NB2_ERR_NOT_READY, "upload bodies and params before stepping");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    return do_step_ccd(ctx, mode);
 }
 
 int nb2_synchronize(nb2_context* h) {

@@ -21,7 +21,7 @@ EXPORTS = [
     "nb2_set_schedule_cache", "nb2_set_contact_layout",
     "nb2_upload_bodies", "nb2_upload_body_states", "nb2_upload_manifolds", "nb2_upload_joints",
     "nb2_clear_impulse_cache", "nb2_upload_activation", "nb2_update_activation", "nb2_download_activation",
-    "nb2_step", "nb2_synchronize", "nb2_download_body_states",
+    "nb2_step", "nb2_step_ccd", "nb2_synchronize", "nb2_download_body_states",
     "nb2_download_contact_impulses", "nb2_download_joints", "nb2_get_stats", "nb2_get_timers",
     "nb2_launch_count",
 ]
@@ -177,6 +177,9 @@ class Solver:
 
     def step(self, mode=abi.MODE_COLOURED):
         self._chk(self.lib.nb2_step(self.h, int(mode)))
+
+    def step_ccd(self, mode=abi.MODE_COLOURED):
+        self._chk(self.lib.nb2_step_ccd(self.h, int(mode)))
 
     def synchronize(self):
         self._chk(self.lib.nb2_synchronize(self.h))

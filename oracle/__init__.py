@@ -122,6 +122,9 @@ class Oracle:
     def step(self, mode=None):
         self._chk(self.lib.nbo_step(self.h))
 
+    def step_ccd(self, mode=None):
+        self._chk(self.lib.nbo_step_ccd(self.h))
+
     def synchronize(self):
         pass
 

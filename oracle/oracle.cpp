@@ -1601,6 +1601,37 @@ struct World {
         return NB2_OK;
     }
 
+    /* MoreauJeanSolver::step_ccd (moreau_jean_solver.rs:94-127) with the island / manifold / joint
+     * selection of the regular step: assemble, position constraints first, velocity constraints, then
+     * update_velocities_and_integrate.  No cache_impulses, no kinematic integration. */
+    int step_ccd() {
+        const real dt = params.dt;
+        for (Body& b : bodies) b.update_dynamics(dt);
+        V3 g = v3(params.gravity[0], params.gravity[1], params.gravity[2]);
+        for (Body& b : bodies) b.update_acceleration(g);
+        island.clear();
+        for (size_t i = 0; i < bodies.size(); ++i)
+            if (bodies[i].status == NB2_BODY_DYNAMIC && bodies[i].is_active()) island.push_back((int)i);
+        manifolds.clear();
+        for (const nb2_manifold& m : uploaded_manifolds) {
+            const Body& b1 = bodies[m.body1];
+            const Body& b2 = bodies[m.body2];
+            if (m.num_contacts > 0 && b1.status != NB2_BODY_DISABLED && b2.status != NB2_BODY_DISABLED &&
+                ((b1.status_dependent_ndofs() != 0 && b1.is_active()) || (b2.status_dependent_ndofs() != 0 && b2.is_active())))
+                manifolds.push_back(m);
+        }
+        active_joints.clear();
+        for (size_t i = 0; i < joints.size(); ++i)
+            if (!joints[i].rec.broken && joint_is_active(joints[i])) active_joints.push_back(i);
+        for (Body& b : bodies) b.companion_id = 0;
+        assemble_system();
+        nonlinear_sor_prox_solve(params.max_position_iterations); /* :121 solve_position_constraints */
+        sor_prox_solve(params.max_velocity_iterations);           /* :126 solve_velocity_constraints */
+        update_velocities_and_integrate();                         /* :127 */
+        compute_residual();
+        return NB2_OK;
+    }
+
     /* Diagnostics shared with the CUDA path's nb2_get_stats (not part of the
      * reference): natural-map residual of every velocity row at the final
      * iterate, evaluated Jacobi-style. */
@@ -1813,6 +1844,7 @@ int nbo_clear_impulse_cache(void* wp) {
 }
 
 int nbo_step(void* wp) { return ((World*)wp)->step(); }
+int nbo_step_ccd(void* wp) { return ((World*)wp)->step_ccd(); }
 
 int nbo_download_body_states(void* wp, nb2_body_state* out, uint32_t first, uint32_t n) {
     World* w = (World*)wp;

@@ -193,6 +193,7 @@ extern "C" {
     pub fn nb2_update_activation(ctx: *mut nb2_context, mix_factor: f32, to_activate: *const i32, n_to_activate: u32) -> i32;
     pub fn nb2_download_activation(ctx: *mut nb2_context, out: *mut nb2_activation, n: u32) -> i32;
     pub fn nb2_step(ctx: *mut nb2_context, mode: i32) -> i32;
+    pub fn nb2_step_ccd(ctx: *mut nb2_context, mode: i32) -> i32;
     pub fn nb2_synchronize(ctx: *mut nb2_context) -> i32;
     pub fn nb2_download_body_states(ctx: *mut nb2_context, out: *mut nb2_body_state, first: u32, n: u32) -> i32;
     pub fn nb2_download_contact_impulses(ctx: *mut nb2_context, out3: *mut f32, n_contacts: u32) -> i32;

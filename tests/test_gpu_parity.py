@@ -451,3 +451,42 @@ def test_staged_and_register_pipelined_kernels_agree(monkeypatch):
     assert np.abs(b1["velocity"] - b0["velocity"]).max() < 1e-3
     assert rel_err(i1, i0) < 2e-3
     assert int(s0["non_finite"]) == 0 and int(s1["non_finite"]) == 0
+
+
+def test_step_ccd_reference_order_matches_oracle():
+    """nb2_step_ccd = MoreauJeanSolver::step_ccd (moreau_jean_solver.rs:94-127): position resolution before
+    velocity resolution, no impulse caching.  Three regular steps warm the cache, then a CCD sub-step with
+    the driver's parameters (short dt, warmstart_coeff = 0), then a regular step again (the cache the
+    sub-step must not have touched)."""
+    sc = scenes.pyramid3(6)
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    g, o = new_solver(), new_oracle()
+    for s in (g, o):
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+    for k in range(3):
+        for s in (g, o):
+            s.upload_manifolds(m, c)
+            s.step(REF)
+        check_step("warm %d" % k, g, o)
+    sub = sc.params.copy()
+    sub["dt"] = 1.0 / 240.0
+    sub["warmstart_coeff"] = 0.0
+    for s in (g, o):
+        s.set_params(sub)
+        s.upload_manifolds(m, c)
+        s.step_ccd(REF)
+    sg, so = g.download_body_states(), o.download_body_states()
+    assert rel_err(sg["position"], so["position"]) <= TOL
+    assert rel_err(sg["velocity"], so["velocity"]) <= TOL
+    assert not np.array_equal(sg["position"], sc.bodies["position"])
+    for s in (g, o):
+        s.set_params(sc.params)
+        s.upload_manifolds(m, c)
+        s.step(REF)
+    check_step("after ccd", g, o)
+    # coloured mode runs the same entry point
+    g.upload_manifolds(m, c)
+    g.step_ccd(COL)
+    assert int(g.get_stats()["non_finite"]) == 0

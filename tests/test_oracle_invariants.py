@@ -324,3 +324,26 @@ def test_warm_start_cache_follows_contact_keys():
     o.upload_manifolds(m, c3)
     o.step()
     assert o.get_stats()["residual_max"] > 0.0
+
+
+def test_step_ccd_does_not_touch_the_impulse_cache():
+    """step_ccd (moreau_jean_solver.rs:94-127) has no cache_impulses call: the impulses a regular step cached
+    survive a CCD sub-step and warm-start the next regular step exactly as if the sub-step had not solved."""
+    sc = scenes.boxes3(2, 2, 2)
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    o = Oracle()
+    o.set_params(sc.params)
+    o.upload_bodies(sc.bodies)
+    for _ in range(3):
+        o.upload_manifolds(m, c)
+        o.step()
+    cached = o.download_contact_impulses().copy()
+    assert np.abs(cached).max() > 0
+    before = o.download_body_states().copy()
+    o.upload_manifolds(m, c)
+    o.step_ccd()
+    assert np.array_equal(o.download_contact_impulses(), cached)
+    after = o.download_body_states()
+    assert not np.array_equal(after["velocity"], before["velocity"])  # the sub-step did solve and integrate
+    assert np.isfinite(after["position"]).all()
