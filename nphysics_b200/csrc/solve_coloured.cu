@@ -323,8 +323,10 @@ static size_t staged_smem(int depth, int tpb) {
     return (size_t)depth * NB2_VENTRY * tpb * 16 + 12 * (size_t)tpb * 4 + 3 * NB2_MAX_COLOURS * 4;
 }
 
-// Chooses block size and ring depth for the staged kernel; false = the scene is too large for one
-// group per thread and the register-pipelined kernel (many warps per SM) is the better fit.
+// Chooses block size and ring depth for the staged kernels: one group per thread and phase while an SM's
+// share of a phase fits 384 threads; beyond that 256 threads walk several groups each (measured on
+// 4096 x pyramid3, 1.9 M bodies: 128 / 192 / 256 / 320 / 384 threads -> 17.5 / 12.8 / 11.7 / 12.3 / 12.6 ms
+// velocity kernel, against 15.0 ms for the register-pipelined kernel).
 bool staged_geometry(Context* ctx, int* tpb_out, int* depth_out, int* blocks_out) {
     // groups per phase: the balanced colouring evens the colours out; the colour count is last step's
     // (an asynchronous copy of the schedule header, never waited for), 8 before the first step
@@ -340,8 +342,9 @@ bool staged_geometry(Context* ctx, int* tpb_out, int* depth_out, int* blocks_out
     if (blocks < 1) blocks = 1;
     const size_t per_block = (padded + blocks - 1) / blocks;
     int tpb = (int)((per_block + 31) / 32) * 32;
+    if (tpb > 384) tpb = 256;
     if (const char* f = getenv("NB2_STAGED_TPB")) tpb = atoi(f);
-    if (tpb > 384) return false;
+    if (tpb > 384) tpb = 384;
     if (tpb < 32) tpb = 32;
     // measured on the 100k-box pile (224 threads): depth 3 / 4 / 5 / 7 -> 1.19 / 1.17 / 1.20 / 1.34 ms; a deeper
     // ring fetches the next phase's rows while the current phase still waits for its own

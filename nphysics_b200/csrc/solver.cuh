@@ -247,9 +247,9 @@ struct Context {
     bool stepped = false;
 
     int coop_blocks_vel = 0, coop_blocks_pos = 0, coop_blocks_sched = 0, coop_blocks_col = 0;
-    // coloured solve kernels: 0 = phase barrier + register pipelining (also the fallback for scenes with
-    // more than 384 groups per SM and phase), 2 = staged (rows streamed through a shared-memory ring
-    // with cp.async, prefetched across the phase barrier).  NB2_VELOCITY_KERNEL overrides (A/B runs).
+    // coloured solve kernels: 0 = phase barrier + register pipelining (the reference-order kernels), 2 =
+    // staged (rows streamed through a shared-memory ring with cp.async, prefetched across the phase
+    // barrier; the default).  NB2_VELOCITY_KERNEL overrides (A/B runs, tests).
     int velocity_kernel = 2;
     size_t smem_optin = 0;         // cudaDevAttrMaxSharedMemoryPerBlockOptin
     bool staged_attr = false, staged_pos_attr = false;
