@@ -170,7 +170,7 @@ int launch_update_activation(Context* ctx, float mix, const int32_t* to_activate
     if (ctx->n_manifolds + ctx->n_joints) {
         NB2_TRY(ctx->barrier.reserve(ctx, 8));
         NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
-        static int blocks_cc = 0;
+        int& blocks_cc = ctx->coop_blocks_islands;
         if (blocks_cc <= 0) {
             int per_sm = 0;
             NB2_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_act_islands, TPB, 0));

@@ -824,7 +824,6 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     NB2_TRY(ctx->barrier.reserve(ctx, 8));
     NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
     unsigned int* flags = ctx->barrier.p + 4;
-    static int blocks_level = 0, blocks_colour = 0;
     if (mode == NB2_MODE_REFERENCE_ORDER) {
         NB2_TRY(ctx->deg.reserve(ctx, (size_t)nb + 1));
         DevBuf<unsigned int>& adj_off = (s == &ctx->ps) ? ctx->adj_off_p : ctx->adj_off;
@@ -848,8 +847,8 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
         k_sort_adj_link<<<nblk(nb), TPB, 0, ctx->stream>>>(nb, adj_off.p, adj.p, s->it_key.p, s->it_a.p,
                                                            ctx->pred_a.p, ctx->pred_b.p);
         ctx->launches += 5;
-        NB2_TRY(coop_blocks(ctx, k_levelise, &blocks_level));
-        int blocks = (int)min((size_t)blocks_level, (n + TPB - 1) / TPB);
+        NB2_TRY(coop_blocks(ctx, k_levelise, &ctx->coop_blocks_level));
+        int blocks = (int)min((size_t)ctx->coop_blocks_level, (n + TPB - 1) / TPB);
         size_t n_ = n;
         const int* ty = s->it_type.p;
         const int* pa = ctx->pred_a.p;
@@ -870,8 +869,8 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
         NB2_TRY(ctx->bal.reserve(ctx, NB2_MAX_COLOURS));
         k_cond_zero<<<nblk(NB2_MAX_COLOURS), TPB, 0, ctx->stream>>>(changed, ctx->bal.p, NB2_MAX_COLOURS);
         ctx->launches += 4;
-        NB2_TRY(coop_blocks(ctx, k_colour, &blocks_colour));
-        int blocks = (int)min((size_t)blocks_colour, (n + TPB - 1) / TPB);
+        NB2_TRY(coop_blocks(ctx, k_colour, &ctx->coop_blocks_colour));
+        int blocks = (int)min((size_t)ctx->coop_blocks_colour, (n + TPB - 1) / TPB);
         size_t n_ = n;
         const int* ia = s->it_a.p;
         const int* ib = s->it_b.p;

@@ -246,7 +246,9 @@ struct Context {
     int last_mode = -1;
     bool stepped = false;
 
-    int coop_blocks_vel = 0, coop_blocks_pos = 0, coop_blocks_sched = 0, coop_blocks_col = 0;
+    // co-resident block limits of the cooperative kernels on this context's device (queried once)
+    int coop_blocks_vel = 0, coop_blocks_pos = 0, coop_blocks_col = 0, coop_blocks_level = 0, coop_blocks_colour = 0,
+        coop_blocks_islands = 0;
     // coloured solve kernels: 0 = phase barrier + register pipelining (the reference-order kernels), 2 =
     // staged (rows streamed through a shared-memory ring with cp.async, prefetched across the phase
     // barrier; the default).  NB2_VELOCITY_KERNEL overrides (A/B runs, tests).

@@ -428,8 +428,8 @@ def test_compact_contact_layout_matches_row_layout():
 
 def test_staged_and_register_pipelined_kernels_agree(monkeypatch):
     """Coloured mode has two implementations of each solve loop: the staged kernels (cp.async ring in
-    shared memory, default) and the register-pipelined ones (the fallback for scenes with more than
-    384 groups per SM and phase).  Same schedule, same row order; the staged translation unit may
+    shared memory, default) and the register-pipelined ones (the reference-order kernels, selectable for
+    A/B runs).  Same schedule, same row order; the staged translation unit may
     contract to FMA, so agreement is to rounding.  Mixed scene: contacts + joints + a masked body."""
     sc = scenes.joint_chains(24, 6, kind="mixed", with_ground_collider=True, ground_y=-0.22, pitch=6.0)
     gen = scenes.ContactGenerator(sc, search=0.0)
