@@ -36,6 +36,7 @@ static void release_all(Context* c) {
     c->chunk_manifold.release();
     for (int k = 0; k < 2; ++k) {
         c->imp[k].release();
+        c->ckey[k].release();
         c->ht_keys[k].release();
         c->ht_imps[k].release();
     }

@@ -207,6 +207,42 @@ __device__ __forceinline__ void ht_insert(unsigned long long* keys, float4* imps
     }
 }
 
+// The cache of the previous step as assembly sees it.  Contacts that kept their key AND their index (the
+// steady state of a resting scene) are served straight from the per-contact arrays; the hash table over
+// the previous step's keys is only built -- on device, by kernels that return at once otherwise -- on
+// steps where some contact misses that fast path (k_cache_probe sets *need_hash).
+struct ImpulseCacheView {
+    const unsigned long long* ckey_prev;  // key of contact i of the previous step
+    const float4* imp_prev;               // its impulses (normal, tangent 1, tangent 2)
+    unsigned int n_prev;
+    const unsigned long long* ht_keys;
+    const float4* ht_imps;
+    size_t ht_cap;
+    unsigned int* need_hash;
+};
+// fast path: both loads in flight together, one round trip
+__device__ __forceinline__ bool cache_fast_path(const ImpulseCacheView& C, unsigned int ci, unsigned long long key, float4* out) {
+    if (ci >= C.n_prev) return false;
+    const unsigned long long pk = C.ckey_prev[ci];
+    const float4 pv = C.imp_prev[ci];
+    if (pk != key) return false;
+    *out = pv;
+    return true;
+}
+__global__ void k_hash_clear(const unsigned int* __restrict__ need_hash, unsigned long long* keys, size_t cap) {
+    if (*need_hash == 0u) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) keys[i] = 0ull;
+}
+__global__ void k_hash_build(const unsigned int* __restrict__ need_hash, const unsigned long long* __restrict__ ckey_prev,
+                             const float4* __restrict__ imp_prev, unsigned int n_prev, unsigned long long* keys,
+                             float4* imps, size_t cap) {
+    if (*need_hash == 0u) return;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_prev; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = ckey_prev[i];
+        if (key != 0ull) ht_insert(keys, imps, cap, key, imp_prev[i]);
+    }
+}
+
 // ---------------------------------------------------------------- slot resolution (coloured mode)
 // One thread per (phase, contact lane, group) position slot, in ELL order: walks the index chain
 // g_info -> item -> chunk -> manifold -> first contact once, in a kernel light enough to run at full
@@ -265,8 +301,7 @@ __global__ void __launch_bounds__(TPB, NB2_ASM_MINBLOCKS) k_assemble_contacts(
     const unsigned int* __restrict__ chunk_base, const unsigned int* __restrict__ chunk_manifold, BodyArrays B,
     SchedView vs, SchedView ps, RowOut out, float4* p_row, size_t n_pslots_max, float4* p_hdr, size_t n_ghdr_max,
     float4* c_geo,
-    const int4* __restrict__ slot_src, const unsigned long long* __restrict__ ht_keys,
-    const float4* __restrict__ ht_imps, size_t ht_cap,
+    const int4* __restrict__ slot_src, ImpulseCacheView cache,
     float warmstart_coeff, float restitution_threshold, float inv_dt, int compact_layout) {
     unsigned int ci, m;
     unsigned int sp = 0, sg = 0, scnt = 0;  // coloured: phase, group, groups of the phase
@@ -321,7 +356,8 @@ __global__ void __launch_bounds__(TPB, NB2_ASM_MINBLOCKS) k_assemble_contacts(
     float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c.key != 0ull) {
         float4 prev;
-        if (ht_lookup(ht_keys, ht_imps, ht_cap, c.key, &prev)) cached = prev;
+        if (cache_fast_path(cache, ci, c.key, &prev)) cached = prev;
+        else *cache.need_hash = 1u;  // k_warm_fixup patches this contact's warm start once the table exists
     }
 
     const bool compact = compact_layout != 0;
@@ -575,11 +611,12 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
     const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
     const unsigned int* __restrict__ chunk_base, const int* __restrict__ status, SchedView vs,
     const float* __restrict__ r_imp, const float4* __restrict__ c_geo, size_t n_pslots_max, float4* imp_cur,
-    unsigned long long* ht_keys, float4* ht_imps, size_t ht_cap, int compact_layout) {
+    unsigned long long* ckey_cur, int compact_layout) {
     unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= nC) return;
     const unsigned int m = c_manifold[ci];
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    ckey_cur[ci] = contacts[ci].key;
     if (m == 0xFFFFFFFFu) {
         imp_cur[ci] = v;
         return;
@@ -606,8 +643,46 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
         }
     }
     imp_cur[ci] = v;
+}
+
+// Steps on which some contact missed the fast path of the impulse cache: the table over the previous step's
+// keys has been built by now; look the missed contacts up and patch their warm-start impulses in place
+// (assembly wrote zeros for them).  Same slot arithmetic as k_cache_contact_impulses.
+__global__ void __launch_bounds__(TPB) k_warm_fixup(
+    int mode, unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
+    const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
+    const unsigned int* __restrict__ chunk_base, const int* __restrict__ status, SchedView vs, float* r_imp,
+    float4* c_geo, size_t n_pslots_max, ImpulseCacheView cache, float warmstart_coeff, int compact_layout) {
+    if (*cache.need_hash == 0u) return;
+    unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nC) return;
+    const unsigned int m = c_manifold[ci];
+    if (m == 0xFFFFFFFFu) return;
     const unsigned long long key = contacts[ci].key;
-    if (key != 0ull) ht_insert(ht_keys, ht_imps, ht_cap, key, v);
+    if (key == 0ull) return;
+    float4 v;
+    if (cache_fast_path(cache, ci, key, &v)) return;  // already warm-started by the assembly
+    if (!ht_lookup(cache.ht_keys, cache.ht_imps, cache.ht_cap, key, &v)) return;
+    const nb2_manifold& mf = manifolds[m];
+    if (status[mf.body1] != NB2_BODY_DYNAMIC && status[mf.body2] != NB2_BODY_DYNAMIC) return;
+    const unsigned int lc = ci - mf.first_contact;
+    const unsigned int chunk = chunk_base[m] + lc / NB2_CHUNK;
+    const int lcc = (int)(lc % NB2_CHUNK);
+    const int ncc = min(NB2_CHUNK, (int)mf.num_contacts - NB2_CHUNK * (int)(lc / NB2_CHUNK));
+    const float wn = v.x * warmstart_coeff, wt1 = v.y * warmstart_coeff, wt2 = v.z * warmstart_coeff;
+    if (compact_layout) {
+        c_geo[4 * n_pslots_max + vs.pos_slot((size_t)nJ + chunk, lcc)] = make_float4(wn, wt1, wt2, 1.f);
+    } else if (mode == NB2_MODE_COLOURED) {
+        size_t item = (size_t)nJ + chunk;
+        r_imp[vs.row_slot(item, 2 * ncc + lcc)] = wn;
+        r_imp[vs.row_slot(item, 2 * lcc)] = wt1;
+        r_imp[vs.row_slot(item, 2 * lcc + 1)] = wt2;
+    } else {
+        size_t item_f = (size_t)nJ + chunk, item_n = (size_t)nJ + maxc + chunk;
+        r_imp[vs.row_slot(item_n, lcc)] = wn;
+        r_imp[vs.row_slot(item_f, 2 * lcc)] = wt1;
+        r_imp[vs.row_slot(item_f, 2 * lcc + 1)] = wt2;
+    }
 }
 
 __global__ void __launch_bounds__(TPB) k_cache_joint_impulses(unsigned int nJ, nb2_joint* joints, SchedView vs,
@@ -701,6 +776,18 @@ int launch_assemble(Context* ctx, int mode) {
         ctx->launches++;
     }
     if (ctx->n_contacts) {
+        // impulse cache of the previous step: per-contact arrays first, hash table only if some contact misses
+        NB2_TRY(ctx->flags.reserve(ctx, 4));
+        unsigned int* need_hash = ctx->flags.p + 2;
+        ImpulseCacheView cache;
+        cache.ckey_prev = ctx->ckey[prev].p;
+        cache.imp_prev = ctx->imp[prev].p;
+        cache.n_prev = ctx->imp_n[prev];
+        cache.ht_keys = ctx->ht_keys[prev].p;
+        cache.ht_imps = ctx->ht_imps[prev].p;
+        cache.ht_cap = ctx->ht_cap[prev];
+        cache.need_hash = need_hash;
+        NB2_CUDA(ctx, cudaMemsetAsync(need_hash, 0, sizeof(unsigned int), ctx->stream));
         // coloured: one thread per (group, contact lane) slot in ELL order; reference: one per contact
         const size_t nthreads = ref ? (size_t)ctx->n_contacts : (size_t)NB2_CHUNK * n_items;
         if (!ref) {
@@ -713,9 +800,20 @@ int launch_assemble(Context* ctx, int mode) {
             mode, ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p,
             ctx->c_manifold.p, ctx->chunk_base.p, ctx->chunk_manifold.p, body_arrays(ctx), vs, ps, row_out(ctx),
             ctx->p_row.p,
-            ctx->n_pslots_max, ctx->p_hdr.p, ctx->n_ghdr_max, ctx->c_geo.p, ctx->slot_src.p, ctx->ht_keys[prev].p, ctx->ht_imps[prev].p, ctx->ht_cap[prev],
+            ctx->n_pslots_max, ctx->p_hdr.p, ctx->n_ghdr_max, ctx->c_geo.p, ctx->slot_src.p, cache,
             ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt, ctx->step_layout);
         ctx->launches++;
+        if (cache.ht_cap) {  // all three return at once unless a contact missed the fast path
+            const unsigned int few = (unsigned int)ctx->sm_count * 16;  // grid-stride: the common case is an immediate return
+            k_hash_clear<<<min(nblk(cache.ht_cap), few), TPB, 0, ctx->stream>>>(need_hash, ctx->ht_keys[prev].p, cache.ht_cap);
+            k_hash_build<<<min(nblk(cache.n_prev), few), TPB, 0, ctx->stream>>>(need_hash, cache.ckey_prev, cache.imp_prev, cache.n_prev,
+                                                                      ctx->ht_keys[prev].p, ctx->ht_imps[prev].p, cache.ht_cap);
+            k_warm_fixup<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
+                mode, ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p, ctx->c_manifold.p,
+                ctx->chunk_base.p, ctx->b_status.p, vs, ctx->r_imp.p, ctx->c_geo.p, ctx->n_pslots_max, cache,
+                ctx->params.warmstart_coeff, ctx->step_layout);
+            ctx->launches += 3;
+        }
     }
     NB2_CUDA(ctx, cudaGetLastError());
     return NB2_OK;
@@ -730,10 +828,10 @@ int launch_cache_impulses(Context* ctx, int mode) {
         while (cap < 2 * (size_t)ctx->n_contacts) cap <<= 1;
     }
     NB2_TRY(ctx->imp[cur].reserve(ctx, ctx->n_contacts + 1));
-    if (cap) {
+    NB2_TRY(ctx->ckey[cur].reserve(ctx, ctx->n_contacts + 1));
+    if (cap) {  // the table itself is filled lazily by the next step's assembly (k_hash_clear / k_hash_build)
         NB2_TRY(ctx->ht_keys[cur].reserve(ctx, cap));
         NB2_TRY(ctx->ht_imps[cur].reserve(ctx, cap));
-        NB2_CUDA(ctx, cudaMemsetAsync(ctx->ht_keys[cur].p, 0, cap * sizeof(unsigned long long), ctx->stream));
     }
     ctx->ht_cap[cur] = cap;
     ctx->imp_n[cur] = ctx->n_contacts;
@@ -742,8 +840,7 @@ int launch_cache_impulses(Context* ctx, int mode) {
         k_cache_contact_impulses<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
             mode, ctx->n_contacts, ctx->n_joints, (unsigned int)ctx->max_chunks, ctx->manifolds.p, ctx->contacts.p,
             ctx->c_manifold.p, ctx->chunk_base.p, ctx->b_status.p, vs, ctx->r_imp.p, ctx->c_geo.p, ctx->n_pslots_max,
-            ctx->imp[cur].p,
-            ctx->ht_keys[cur].p, ctx->ht_imps[cur].p, cap, ctx->step_layout);
+            ctx->imp[cur].p, ctx->ckey[cur].p, ctx->step_layout);
         ctx->launches++;
     }
     if (ctx->n_joints) {

@@ -490,3 +490,38 @@ def test_step_ccd_reference_order_matches_oracle():
     g.upload_manifolds(m, c)
     g.step_ccd(COL)
     assert int(g.get_stats()["non_finite"]) == 0
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_impulse_cache_survives_a_contact_reindexing_coloured(layout):
+    """The impulse cache serves contacts that kept key and index from per-contact arrays and builds its
+    hash table only when some contact misses that path.  Rotating the contact array (every index changes,
+    keys and row order do not) must therefore change nothing, bit for bit, in coloured mode too."""
+    sc = scenes.boxes3(4, 4, 4)
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    n0 = int(m["num_contacts"][0])
+    c_rot = np.concatenate([c[n0:], c[:n0]])
+    m_rot = m.copy()
+    m_rot["first_contact"] = m["first_contact"] - n0
+    m_rot["first_contact"][0] = len(c) - n0
+    outs = []
+    for rotate_at in (None, 3):
+        s = new_solver()
+        s.set_contact_layout(layout)
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+        for k in range(6):
+            if rotate_at is not None and k >= rotate_at:
+                s.upload_manifolds(m_rot, c_rot)
+            else:
+                s.upload_manifolds(m, c)
+            s.step(COL)
+        imp = s.download_contact_impulses()
+        if rotate_at is not None:
+            imp = np.concatenate([imp[len(c) - n0:], imp[:len(c) - n0]])
+        outs.append((s.download_body_states(), imp))
+    assert np.array_equal(outs[0][0]["position"], outs[1][0]["position"])
+    assert np.array_equal(outs[0][0]["velocity"], outs[1][0]["velocity"])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.abs(outs[0][1]).max() > 0
