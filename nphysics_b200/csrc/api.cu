@@ -45,7 +45,7 @@ static void release_all(Context* c) {
     c->adj_p.release(); c->cmask.release(); c->best.release(); c->scan_tmp.release(); c->barrier.release();
     c->r_jac.release(); c->r_hdr.release(); c->r_imp.release(); c->p_row.release();
     c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
-    c->c_geo.release(); c->bal.release(); c->p_hdr.release(); c->slot_src.release();
+    c->c_geo.release(); c->bal.release(); c->p_hdr.release();
     c->true_status.release(); c->act.release(); c->cc_parent.release(); c->cc_can.release(); c->wake_list.release();
     if (c->host_hdr) cudaFreeHost(c->host_hdr);
     c->host_hdr = nullptr;

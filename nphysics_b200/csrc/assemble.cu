@@ -243,149 +243,54 @@ __global__ void k_hash_build(const unsigned int* __restrict__ need_hash, const u
     }
 }
 
-// ---------------------------------------------------------------- slot resolution (coloured mode)
-// One thread per (phase, contact lane, group) position slot, in ELL order: walks the index chain
-// g_info -> item -> chunk -> manifold -> first contact once, in a kernel light enough to run at full
-// occupancy, and leaves (contact, manifold, phase | lane << 8 | contacts << 12, group) for the
-// assembly and impulse-cache kernels, which then start from one coalesced load.  Lane 0 also writes
-// the group header of the staged position kernel (bodies, collider-to-body poses).
-__global__ void __launch_bounds__(TPB) k_resolve_slots(const nb2_manifold* __restrict__ manifolds,
-                                                       const unsigned int* __restrict__ chunk_base,
-                                                       const unsigned int* __restrict__ chunk_manifold, SchedView vs,
-                                                       int4* slot_src, float4* p_hdr, size_t n_ghdr_max) {
-    const size_t T = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int np = vs.hdr->n_phases;
-    if (np == 0 || T >= (size_t)NB2_CHUNK * vs.ph_gbase[np]) return;
-    unsigned int lo = 0, hi = np;  // largest p with NB2_CHUNK * gbase[p] <= T
-    while (hi - lo > 1) {
-        unsigned int mid = (lo + hi) >> 1;
-        if ((size_t)NB2_CHUNK * vs.ph_gbase[mid] <= T) lo = mid; else hi = mid;
-    }
-    const unsigned int p = lo, cnt = vs.ph_count[p];
-    const size_t local = T - (size_t)NB2_CHUNK * vs.ph_gbase[p];
-    const unsigned int lane = (unsigned int)(local / cnt), g = (unsigned int)(local % cnt);
-    const int4 gi = vs.g_info[vs.ph_gbase[p] + g];
-    int4 res = make_int4(-1, 0, (int)(p | (lane << 8)), (int)g);
-    if ((gi.z >> 8) == NB2_ITEM_CONTACTS) {
-        const unsigned int chunk = (unsigned int)vs.it_src[gi.w];
-        const unsigned int m = chunk_manifold[chunk];
-        const unsigned int lchunk = chunk - chunk_base[m];
-        const nb2_manifold& mh = manifolds[m];
-        const int left = (int)mh.num_contacts - (int)(NB2_CHUNK * lchunk);
-        const int ncc = min(NB2_CHUNK, left);
-        res.y = (int)m;
-        res.z |= ncc << 12;
-        res.x = (int)lane < left ? (int)(mh.first_contact + NB2_CHUNK * lchunk + lane) : -2;  // -2: padding lane
-        if (lane == 0) {
-            const size_t gs = (size_t)vs.ph_gbase[p] + g;
-            const float* k1 = mh.coll1_wrt_body;
-            const float* k2 = mh.coll2_wrt_body;
-            p_hdr[0 * n_ghdr_max + gs] = make_float4(__int_as_float((int)mh.body1), __int_as_float((int)mh.body2),
-                                                     __int_as_float((int)m), 0.f);
-            p_hdr[1 * n_ghdr_max + gs] = make_float4(k1[0], k1[1], k1[2], k1[3]);
-            p_hdr[2 * n_ghdr_max + gs] = make_float4(k1[4], k1[5], k1[6], 0.f);
-            p_hdr[3 * n_ghdr_max + gs] = make_float4(k2[0], k2[1], k2[2], k2[3]);
-            p_hdr[4 * n_ghdr_max + gs] = make_float4(k2[4], k2[5], k2[6], 0.f);
-        }
-    }
-    slot_src[T] = res;
+// ---------------------------------------------------------------- contacts
+// What the three rows of a contact need from its manifold.
+struct ManifoldConsts {
+    float margin1, margin2, friction, restitution;
+    Vec3 surf;
+};
+__device__ __forceinline__ ManifoldConsts manifold_consts(const nb2_manifold& mf) {
+    ManifoldConsts K;
+    K.margin1 = mf.margin1;
+    K.margin2 = mf.margin2;
+    K.friction = mf.friction;
+    K.restitution = mf.restitution;
+    K.surf = mk3(mf.surface_velocity[0], mf.surface_velocity[1], mf.surface_velocity[2]);
+    return K;
+}
+struct ContactSlots {
+    size_t n, t1, t2, p;  // row slots of the normal / tangent rows, position slot
+};
+struct alignas(16) ContactQuads {
+    float4 q[7];
+};
+// the 112-byte contact record as seven quads in one go
+__device__ __forceinline__ void load_contact(const nb2_contact* contacts, unsigned int ci, ContactQuads* cq) {
+    const float4* cp = reinterpret_cast<const float4*>(&contacts[ci]);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) cq->q[k] = __ldg(cp + k);
 }
 
-// ---------------------------------------------------------------- contacts
-// 4 blocks of 128 per SM (127 registers, 52 bytes of spill): measured 0.422 vs 0.434 ms assembly stage on the
-// 100k pile against 3 blocks at 157 registers, no difference at 1.9 M bodies; 5+ blocks spill too much
-#define NB2_ASM_MINBLOCKS 4
-__global__ void __launch_bounds__(TPB, NB2_ASM_MINBLOCKS) k_assemble_contacts(
-    int mode, unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
-    const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
-    const unsigned int* __restrict__ chunk_base, const unsigned int* __restrict__ chunk_manifold, BodyArrays B,
-    SchedView vs, SchedView ps, RowOut out, float4* p_row, size_t n_pslots_max, float4* p_hdr, size_t n_ghdr_max,
-    float4* c_geo,
-    const int4* __restrict__ slot_src, ImpulseCacheView cache,
-    float warmstart_coeff, float restitution_threshold, float inv_dt, int compact_layout) {
-    unsigned int ci, m;
-    unsigned int sp = 0, sg = 0, scnt = 0;  // coloured: phase, group, groups of the phase
-    if (mode == NB2_MODE_COLOURED) {
-        // Gather formulation: threads enumerate the (phase, contact lane, group) slots in ELL order,
-        // so the row planes are WRITTEN with consecutive threads on consecutive 16-byte words; the
-        // scattered side is the read of the 112-byte contact record.  k_resolve_slots did the index walk.
-        const size_t T = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const unsigned int np = vs.hdr->n_phases;
-        if (np == 0 || T >= (size_t)NB2_CHUNK * vs.ph_gbase[np]) return;
-        const int4 src = slot_src[T];
-        if (src.x == -2 && compact_layout)  // fewer than 4 contacts in this chunk: flag the lane's compact record invalid
-            c_geo[4 * n_pslots_max + T] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src.x < 0) return;
-        ci = (unsigned int)src.x;
-        m = (unsigned int)src.y;
-        sp = (unsigned int)src.z & 0xFFu;
-        sg = (unsigned int)src.w;
-        scnt = vs.ph_count[sp];
-    } else {
-        ci = blockIdx.x * blockDim.x + threadIdx.x;
-        if (ci >= nC) return;
-        m = c_manifold[ci];
-        if (m == 0xFFFFFFFFu) return;
-    }
-    if (ci >= nC) return;
-    const nb2_manifold& mf = manifolds[m];
-    // the 112-byte contact record as seven quads in one go (consecutive threads hold unrelated records)
-    struct alignas(16) ContactQuads { float4 q[7]; } cq;
-    {
-        const float4* cp = reinterpret_cast<const float4*>(&contacts[ci]);
-#pragma unroll
-        for (int k = 0; k < 7; ++k) cq.q[k] = __ldg(cp + k);
-    }
-    const nb2_contact& c = *reinterpret_cast<const nb2_contact*>(&cq);
-    BodySide s1, s2;
-    load_side(B, mf.body1, &s1);
-    load_side(B, mf.body2, &s2);
-    const bool d1 = s1.status == NB2_BODY_DYNAMIC, d2 = s2.status == NB2_BODY_DYNAMIC;
-    if (!d1 && !d2) return;  // filtered by the caller in the reference (mechanical_world.rs:287-300)
-    const unsigned int lc = ci - mf.first_contact;
-    const unsigned int chunk = chunk_base[m] + lc / NB2_CHUNK;
-    const int lcc = (int)(lc % NB2_CHUNK);
-    const int ncc = min(NB2_CHUNK, (int)mf.num_contacts - NB2_CHUNK * (int)(lc / NB2_CHUNK));
-
+// The three velocity rows and the position row of one contact (signorini_coulomb_pyramid_model.rs:56-224,
+// signorini_model.rs:37-197), written into the given slots.  q1 = orientation of body 1.
+__device__ __forceinline__ void assemble_contact(const RowOut& out, const BodySide& s1, const BodySide& s2,
+                                                 const ManifoldConsts& K, const nb2_contact& c, Quat q1, float4 cached,
+                                                 const ContactSlots& S, bool compact, float4* c_geo, float4* p_row,
+                                                 size_t n_pslots_max, float warmstart_coeff,
+                                                 float restitution_threshold, float inv_dt) {
+    const size_t slot_n = S.n, slot_t1 = S.t1, slot_t2 = S.t2, pslot = S.p;
     const Vec3 n = mk3(c.normal[0], c.normal[1], c.normal[2]);
     const Vec3 world1 = mk3(c.world1[0], c.world1[1], c.world1[2]);
     const Vec3 world2 = mk3(c.world2[0], c.world2[1], c.world2[2]);
-    const Vec3 surf = mk3(mf.surface_velocity[0], mf.surface_velocity[1], mf.surface_velocity[2]);
-
-    // impulse cache lookup (signorini_coulomb_pyramid_model.rs:104-108)
-    float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c.key != 0ull) {
-        float4 prev;
-        if (cache_fast_path(cache, ci, c.key, &prev)) cached = prev;
-        else *cache.need_hash = 1u;  // k_warm_fixup patches this contact's warm start once the table exists
-    }
-
-    const bool compact = compact_layout != 0;
-    size_t slot_n = 0, slot_t1 = 0, slot_t2 = 0, pslot;
-    if (mode == NB2_MODE_COLOURED) {
-        // this thread IS position slot (sp, lcc, sg); the velocity rows of the group follow from it
-        pslot = (size_t)NB2_CHUNK * vs.ph_gbase[sp] + (size_t)lcc * scnt + sg;
-        if (!compact) {
-            const size_t rb = (size_t)vs.ph_rbase[sp] + sg;
-            slot_t1 = rb + (size_t)(2 * lcc) * scnt;
-            slot_t2 = rb + (size_t)(2 * lcc + 1) * scnt;
-            slot_n = rb + (size_t)(2 * ncc + lcc) * scnt;
-        }
-    } else {
-        size_t item_f = (size_t)nJ + chunk, item_n = (size_t)nJ + maxc + chunk;
-        slot_t1 = vs.row_slot(item_f, 2 * lcc);
-        slot_t2 = vs.row_slot(item_f, 2 * lcc + 1);
-        slot_n = vs.row_slot(item_n, lcc);
-        pslot = ps.pos_slot((size_t)nJ + chunk, lcc);
-    }
+    const Vec3 surf = K.surf;
 
     // ---- non-penetration row (signorini_model.rs:65-137)
-    const Vec3 center1 = world1 + n * mf.margin1;
-    const Vec3 center2 = world2 - n * mf.margin2;
+    const Vec3 center1 = world1 + n * K.margin1;
+    const Vec3 center2 = world2 - n * K.margin2;
     float J1[6], J2[6], W1[6], W2[6], rhs, r;
     emit_pair_row(out, slot_n, s1, s2, center1, center2, false, -n, dot3(n, surf), &rhs, &r, J1, J2, W1, W2);
-    if (rhs <= -restitution_threshold) rhs += mf.restitution * rhs;
-    float depth = c.depth + mf.margin1 + mf.margin2;
+    if (rhs <= -restitution_threshold) rhs += K.restitution * rhs;
+    float depth = c.depth + K.margin1 + K.margin2;
     if (depth < 0.f) rhs += (-depth) * inv_dt;
     const float rhs_n = rhs, r_n = r;
     if (!compact)
@@ -398,11 +303,11 @@ __global__ void __launch_bounds__(TPB, NB2_ASM_MINBLOCKS) k_assemble_contacts(
     emit_pair_row(out, slot_t1, s1, s2, center1, center2, false, t1, dot3(t1, surf), &rhs, &r, J1, J2, W1, W2);
     const float rhs_t1 = rhs, r_t1 = r;
     if (!compact)
-        write_row(out, slot_t1, J1, J2, W1, W2, rhs, r, mf.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
+        write_row(out, slot_t1, J1, J2, W1, W2, rhs, r, K.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
                   cached.y * warmstart_coeff);
     emit_pair_row(out, slot_t2, s1, s2, center1, center2, false, t2, dot3(t2, surf), &rhs, &r, J1, J2, W1, W2);
     if (!compact)
-        write_row(out, slot_t2, J1, J2, W1, W2, rhs, r, mf.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
+        write_row(out, slot_t2, J1, J2, W1, W2, rhs, r, K.friction, 0.f, NB2_ROW_DEPENDENT, (int)slot_n,
                   cached.z * warmstart_coeff);
     if (compact) {
         // Compact record: the solve kernel rebuilds J = mask*(d, p x d) and WJ = M^-1 J with the
@@ -413,20 +318,133 @@ __global__ void __launch_bounds__(TPB, NB2_ASM_MINBLOCKS) k_assemble_contacts(
         c_geo[0 * P_ + pslot] = make_float4(p1.x, p1.y, p1.z, rhs_n);
         c_geo[1 * P_ + pslot] = make_float4(p2.x, p2.y, p2.z, rhs_t1);
         c_geo[2 * P_ + pslot] = make_float4(n.x, n.y, n.z, rhs);
-        c_geo[3 * P_ + pslot] = make_float4(r_n, r_t1, r, mf.friction);
+        c_geo[3 * P_ + pslot] = make_float4(r_n, r_t1, r, K.friction);
         c_geo[4 * P_ + pslot] = make_float4(cached.x * warmstart_coeff, cached.y * warmstart_coeff,
                                             cached.z * warmstart_coeff, 1.f);
     }
 
     // ---- position row (signorini_model.rs:153-197)
-    const Quat q1 = f4_quat(B.pos_q[mf.body1]);
     const Vec3 normal1 = quat_inv_rotate(q1, n);
     const size_t P = n_pslots_max;
-    __stcs(&p_row[0 * P + pslot], make_float4(c.local1[0], c.local1[1], c.local1[2], c.dilation1 + mf.margin1));
-    __stcs(&p_row[1 * P + pslot], make_float4(c.local2[0], c.local2[1], c.local2[2], c.dilation2 + mf.margin2));
+    __stcs(&p_row[0 * P + pslot], make_float4(c.local1[0], c.local1[1], c.local1[2], c.dilation1 + K.margin1));
+    __stcs(&p_row[1 * P + pslot], make_float4(c.local2[0], c.local2[1], c.local2[2], c.dilation2 + K.margin2));
     __stcs(&p_row[2 * P + pslot], make_float4(c.dir1[0], c.dir1[1], c.dir1[2], __int_as_float((int)c.geom1)));
     __stcs(&p_row[3 * P + pslot], make_float4(c.dir2[0], c.dir2[1], c.dir2[2], __int_as_float((int)c.geom2)));
     __stcs(&p_row[4 * P + pslot], make_float4(normal1.x, normal1.y, normal1.z, 0.f));
+}
+
+// Coloured mode: one thread per contact GROUP (the <= 4 contacts of a manifold chunk), enumerated in ELL
+// order.  The thread walks g_info -> chunk -> manifold once, loads the two bodies once for all its
+// contacts (a per-contact thread re-reads them four times; at 1.9 M bodies they no longer sit in L2)
+// and writes rows that are consecutive over the group index: consecutive threads hit consecutive
+// 16-byte words of every plane.  It also writes the group header of the staged position kernel.
+// 2 blocks of 128 per SM (254 registers, no spill) measured best: assembly stage 0.346 ms on the 100k pile and
+// 4.8 ms at 1.9 M bodies, against 0.374 / 5.1 at 3 blocks (168 registers, 212 bytes of spill) and 0.411 / 5.8 at 4
+#define NB2_ASMG_MINBLOCKS 2
+__global__ void __launch_bounds__(TPB, NB2_ASMG_MINBLOCKS) k_assemble_groups(
+    unsigned int nC, const nb2_manifold* __restrict__ manifolds, const nb2_contact* __restrict__ contacts,
+    const unsigned int* __restrict__ chunk_base, const unsigned int* __restrict__ chunk_manifold, BodyArrays B,
+    SchedView vs, RowOut out, float4* p_row, size_t n_pslots_max, float4* p_hdr, size_t n_ghdr_max, float4* c_geo,
+    ImpulseCacheView cache, float warmstart_coeff, float restitution_threshold, float inv_dt, int compact_layout) {
+    const size_t T = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int np = vs.hdr->n_phases;
+    if (np == 0 || T >= (size_t)vs.ph_gbase[np]) return;
+    unsigned int lo = 0, hi = np;  // largest p with gbase[p] <= T
+    while (hi - lo > 1) {
+        unsigned int mid = (lo + hi) >> 1;
+        if ((size_t)vs.ph_gbase[mid] <= T) lo = mid; else hi = mid;
+    }
+    const unsigned int p = lo, cnt = vs.ph_count[p];
+    const unsigned int g = (unsigned int)(T - vs.ph_gbase[p]);
+    const int4 gi = vs.g_info[T];
+    if ((gi.z >> 8) != NB2_ITEM_CONTACTS) return;
+    const unsigned int chunk = (unsigned int)vs.it_src[gi.w];
+    const unsigned int m = chunk_manifold[chunk];
+    const unsigned int lchunk = chunk - chunk_base[m];
+    const nb2_manifold& mf = manifolds[m];
+    const int ncc = min(NB2_CHUNK, (int)mf.num_contacts - (int)(NB2_CHUNK * lchunk));
+    const unsigned int ci0 = mf.first_contact + NB2_CHUNK * lchunk;
+    const int body1 = mf.body1, body2 = mf.body2;
+    {
+        const float* k1 = mf.coll1_wrt_body;
+        const float* k2 = mf.coll2_wrt_body;
+        p_hdr[0 * n_ghdr_max + T] = make_float4(__int_as_float(body1), __int_as_float(body2), __int_as_float((int)m), 0.f);
+        p_hdr[1 * n_ghdr_max + T] = make_float4(k1[0], k1[1], k1[2], k1[3]);
+        p_hdr[2 * n_ghdr_max + T] = make_float4(k1[4], k1[5], k1[6], 0.f);
+        p_hdr[3 * n_ghdr_max + T] = make_float4(k2[0], k2[1], k2[2], k2[3]);
+        p_hdr[4 * n_ghdr_max + T] = make_float4(k2[4], k2[5], k2[6], 0.f);
+    }
+    const ManifoldConsts K = manifold_consts(mf);
+    const bool compact = compact_layout != 0;
+    const size_t pbase = (size_t)NB2_CHUNK * vs.ph_gbase[p] + g, rb = (size_t)vs.ph_rbase[p] + g;
+    if (compact)  // lanes beyond the chunk's contacts: flag their compact records invalid
+        for (int lcc = max(ncc, 0); lcc < NB2_CHUNK; ++lcc)
+            c_geo[4 * n_pslots_max + pbase + (size_t)lcc * cnt] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ncc <= 0 || ci0 + (unsigned int)ncc > nC) return;
+    BodySide s1, s2;
+    load_side(B, body1, &s1);
+    load_side(B, body2, &s2);
+    if (s1.status != NB2_BODY_DYNAMIC && s2.status != NB2_BODY_DYNAMIC) return;
+    const Quat q1 = f4_quat(B.pos_q[body1]);
+    ContactQuads cur, nxt;
+    load_contact(contacts, ci0, &cur);
+#pragma unroll 1
+    for (int lcc = 0; lcc < ncc; ++lcc) {
+        const unsigned int ci = ci0 + (unsigned int)lcc;
+        if (lcc + 1 < ncc) load_contact(contacts, ci + 1, &nxt);  // next record in flight while this one is assembled
+        const nb2_contact& c = *reinterpret_cast<const nb2_contact*>(&cur);
+        float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c.key != 0ull) {  // impulse cache (signorini_coulomb_pyramid_model.rs:104-108)
+            float4 prev;
+            if (cache_fast_path(cache, ci, c.key, &prev)) cached = prev;
+            else *cache.need_hash = 1u;  // k_warm_fixup patches this contact's warm start once the table exists
+        }
+        ContactSlots S;
+        S.p = pbase + (size_t)lcc * cnt;
+        S.t1 = rb + (size_t)(2 * lcc) * cnt;
+        S.t2 = rb + (size_t)(2 * lcc + 1) * cnt;
+        S.n = rb + (size_t)(2 * ncc + lcc) * cnt;
+        assemble_contact(out, s1, s2, K, c, q1, cached, S, compact, c_geo, p_row, n_pslots_max, warmstart_coeff,
+                         restitution_threshold, inv_dt);
+        cur = nxt;
+    }
+}
+
+// Reference order: one thread per contact.
+__global__ void __launch_bounds__(TPB) k_assemble_contacts(
+    unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
+    const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
+    const unsigned int* __restrict__ chunk_base, BodyArrays B, SchedView vs, SchedView ps, RowOut out, float4* p_row,
+    size_t n_pslots_max, ImpulseCacheView cache, float warmstart_coeff, float restitution_threshold, float inv_dt) {
+    const unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= nC) return;
+    const unsigned int m = c_manifold[ci];
+    if (m == 0xFFFFFFFFu) return;
+    const nb2_manifold& mf = manifolds[m];
+    ContactQuads cq;
+    load_contact(contacts, ci, &cq);
+    const nb2_contact& c = *reinterpret_cast<const nb2_contact*>(&cq);
+    BodySide s1, s2;
+    load_side(B, mf.body1, &s1);
+    load_side(B, mf.body2, &s2);
+    if (s1.status != NB2_BODY_DYNAMIC && s2.status != NB2_BODY_DYNAMIC) return;  // filtered by the caller in the reference (mechanical_world.rs:287-300)
+    const unsigned int lc = ci - mf.first_contact;
+    const unsigned int chunk = chunk_base[m] + lc / NB2_CHUNK;
+    const int lcc = (int)(lc % NB2_CHUNK);
+    float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c.key != 0ull) {  // impulse cache (signorini_coulomb_pyramid_model.rs:104-108)
+        float4 prev;
+        if (cache_fast_path(cache, ci, c.key, &prev)) cached = prev;
+        else *cache.need_hash = 1u;
+    }
+    const size_t item_f = (size_t)nJ + chunk, item_n = (size_t)nJ + maxc + chunk;
+    ContactSlots S;
+    S.t1 = vs.row_slot(item_f, 2 * lcc);
+    S.t2 = vs.row_slot(item_f, 2 * lcc + 1);
+    S.n = vs.row_slot(item_n, lcc);
+    S.p = ps.pos_slot((size_t)nJ + chunk, lcc);
+    assemble_contact(out, s1, s2, manifold_consts(mf), c, f4_quat(B.pos_q[mf.body1]), cached, S, false, nullptr, p_row,
+                     n_pslots_max, warmstart_coeff, restitution_threshold, inv_dt);
 }
 
 // ---------------------------------------------------------------- joints
@@ -766,7 +784,6 @@ int launch_assemble(Context* ctx, int mode) {
     NB2_TRY(ctx->c_geo.reserve(ctx, ctx->step_layout == 0 ? 16 : 5 * ctx->n_pslots_max));
     NB2_TRY(ctx->p_hdr.reserve(ctx, ref ? 16 : 5 * (n_items + 16)));
     ctx->n_ghdr_max = ctx->p_hdr.cap / 5;
-    NB2_TRY(ctx->slot_src.reserve(ctx, ref ? 16 : (size_t)NB2_CHUNK * n_items + 16));
     SchedView vs = view_of(ctx->vs);
     SchedView ps = ref ? view_of(ctx->ps) : vs;
     const int prev = 1 - ctx->cur;
@@ -788,20 +805,18 @@ int launch_assemble(Context* ctx, int mode) {
         cache.ht_cap = ctx->ht_cap[prev];
         cache.need_hash = need_hash;
         NB2_CUDA(ctx, cudaMemsetAsync(need_hash, 0, sizeof(unsigned int), ctx->stream));
-        // coloured: one thread per (group, contact lane) slot in ELL order; reference: one per contact
-        const size_t nthreads = ref ? (size_t)ctx->n_contacts : (size_t)NB2_CHUNK * n_items;
-        if (!ref) {
-            k_resolve_slots<<<nblk(nthreads), TPB, 0, ctx->stream>>>(ctx->manifolds.p, ctx->chunk_base.p,
-                                                                      ctx->chunk_manifold.p, vs, ctx->slot_src.p,
-                                                                      ctx->p_hdr.p, ctx->n_ghdr_max);
-            ctx->launches++;
+        if (ref) {
+            k_assemble_contacts<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
+                ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p, ctx->c_manifold.p,
+                ctx->chunk_base.p, body_arrays(ctx), vs, ps, row_out(ctx), ctx->p_row.p, ctx->n_pslots_max, cache,
+                ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt);
+        } else {  // one thread per group slot in ELL order
+            k_assemble_groups<<<nblk(n_items), TPB, 0, ctx->stream>>>(
+                ctx->n_contacts, ctx->manifolds.p, ctx->contacts.p, ctx->chunk_base.p, ctx->chunk_manifold.p,
+                body_arrays(ctx), vs, row_out(ctx), ctx->p_row.p, ctx->n_pslots_max, ctx->p_hdr.p, ctx->n_ghdr_max,
+                ctx->c_geo.p, cache, ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt,
+                ctx->step_layout);
         }
-        k_assemble_contacts<<<nblk(nthreads), TPB, 0, ctx->stream>>>(
-            mode, ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p,
-            ctx->c_manifold.p, ctx->chunk_base.p, ctx->chunk_manifold.p, body_arrays(ctx), vs, ps, row_out(ctx),
-            ctx->p_row.p,
-            ctx->n_pslots_max, ctx->p_hdr.p, ctx->n_ghdr_max, ctx->c_geo.p, ctx->slot_src.p, cache,
-            ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt, ctx->step_layout);
         ctx->launches++;
         if (cache.ht_cap) {  // all three return at once unless a contact missed the fast path
             const unsigned int few = (unsigned int)ctx->sm_count * 16;  // grid-stride: the common case is an immediate return

@@ -208,7 +208,6 @@ struct Context {
     DevBuf<unsigned long long> ckey[2];  // key of every contact of that step (the cache's fast path: same key at the same index)
     DevBuf<unsigned long long> ht_keys[2];
     DevBuf<float4> ht_imps[2];       // cached impulses (normal, tangent 1, tangent 2) at the key's index
-    DevBuf<int4> slot_src;           // coloured: per position slot (contact, manifold, phase | lane << 8 | contacts << 12, group)
     size_t ht_cap[2] = {0, 0};  // power of two (0 = empty cache)
     uint32_t imp_n[2] = {0, 0};
     int cur = 0;                // buffer written by the current step
