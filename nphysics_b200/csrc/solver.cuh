@@ -278,6 +278,7 @@ struct GridBarrier {
     }
     __device__ void sync() {
         __syncthreads();
+        if (gridDim.x == 1) return;  // a single block: bar.sync already orders its threads' global accesses
         if (threadIdx.x == 0) {
             target += gridDim.x;
             // arrive with release semantics (orders this block's earlier writes, made visible to
