@@ -191,3 +191,43 @@ def test_gpu_islands_on_a_large_pile():
         res.append(sim.download_activation())
     assert np.array_equal(res[0]["energy"], res[1]["energy"])
     assert np.all(res[1]["energy"][1:] != 0.0)  # one island, kept awake by a single body
+
+
+@pytest.mark.gpu
+def test_gpu_islands_and_sleep_on_a_20x20x20_pile():
+    """8000 boxes in one island (graph diameter ~60): all below their thresholds -> the whole pile goes to
+    sleep at once and the step that follows assembles no row; a deferred activation of one box wakes all
+    8000.  Energies and states equal the oracle's."""
+    from nphysics_b200.solver import Solver
+    sc = scenes.boxes3(20, 20, 20)
+    n = len(sc.bodies)
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    act = abi.new_activation(n)
+    act["energy"][:] = 0.5 * THR
+    sims = (Solver(0), new_oracle())
+    for sim in sims:
+        sim.set_params(sc.params)
+        sim.upload_bodies(sc.bodies)
+        sim.upload_activation(act)
+        sim.upload_manifolds(m, c)
+        sim.update_activation(MIX)
+        sim.step(abi.MODE_REFERENCE_ORDER)
+    a_g, a_o = sims[0].download_activation(), sims[1].download_activation()
+    assert np.array_equal(a_g["energy"], a_o["energy"])
+    assert np.all(a_g["energy"][1:] == 0.0)
+    st = sims[0].get_stats()
+    assert int(st["n_rows_two_body"]) + int(st["n_rows_ground"]) == 0
+    assert np.array_equal(sims[0].download_body_states()["position"], sims[1].download_body_states()["position"])
+    for sim in sims:
+        sim.upload_manifolds(m, c)
+        sim.update_activation(MIX, [n // 2])
+        sim.step(abi.MODE_REFERENCE_ORDER)
+    a_g, a_o = sims[0].download_activation(), sims[1].download_activation()
+    assert np.array_equal(a_g["energy"], a_o["energy"])
+    assert np.all(a_g["energy"][1:] == np.float32(2 * THR))
+    r2, rg = scenes.row_counts(sc, m)
+    st = sims[0].get_stats()
+    assert int(st["n_rows_two_body"]) == r2 and int(st["n_rows_ground"]) == rg
+    sg, so = sims[0].download_body_states(), sims[1].download_body_states()
+    assert np.array_equal(sg["position"], so["position"]) and np.array_equal(sg["velocity"], so["velocity"])
