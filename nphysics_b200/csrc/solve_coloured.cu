@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
                 cp_async16_ef(dst + 3u * plane_b, R.q[3] + pslot, pol);
                 cp_async16_ef(dst + 4u * plane_b, R.q[4] + pslot, pol);
                 cp_async16_ef(dst + 5u * plane_b, R.q[5] + pslot, pol);
-                if (ic.x >= 0) cp_async16_ef(dst, R.q[0] + pslot, pol);
-                if (ic.y >= 0) cp_async16_ef(dst + 2u * plane_b, R.q[2] + pslot, pol);
+                cp_async16_ef(dst, R.q[0] + pslot, pol);  // both sides unconditionally: one branch less per row, and the
+                cp_async16_ef(dst + 2u * plane_b, R.q[2] + pslot, pol);  // absent side of a ground row is only 32 bytes
                 pslot += pcnt;
             }
             if (++pr >= (ic.z & 0xFF)) {
@@ -277,29 +277,45 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
                 unsigned int cslot = rbase + g;
                 // one loop for every group type and both passes: a specialised path per type measured slower
                 // (warps mix ground and two-body groups, so the paths serialise)
+                if (s == 0) {  // warm start (uniform over the grid): mj_lambda += WJ * cached impulse
 #pragma unroll 1
-                for (int r = 0; r < nrows; ++r, cslot += cnt) {
-                    RowPkt k;
-                    next_row(r, &k);
-                    const int kind = k.kind();
-                    if (kind == NB2_ROW_NONE) continue;
-                    RowJ J;
-                    unpack_pkt(k, true, true, la.im, lb.im, &J);  // unconditional: absent sides are never used
-                    if (s == 0) {
-                        if (k.imp != 0.f) {
-                            if (a) axpy6(k.imp, J.W1, la.v);
-                            if (b) axpy6(k.imp, J.W2, lb.v);
-                        }
-                        continue;
+                    for (int r = 0; r < nrows; ++r) {
+                        RowPkt k;
+                        next_row(r, &k);
+                        const float w = k.kind() == NB2_ROW_NONE ? 0.f : k.imp;
+                        RowJ J;
+                        unpack_pkt(k, true, true, la.im, lb.im, &J);  // unconditional: absent sides are never used
+                        if (a) axpy6(w, J.W1, la.v);
+                        if (b) axpy6(w, J.W2, lb.v);
                     }
-                    float dep = 0.f;
-                    if (kind == NB2_ROW_DEPENDENT) {
-                        // coloured contact groups hold their own normal rows (rows 2*ncc..3*ncc-1), not yet
-                        // updated in this visit: friction rows come first
-                        dep = r < 2 * ncc ? simp[(2 * ncc + (r >> 1)) * TPBK + t] : __ldcg(&R.imp[k.dep()]);
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < nrows; ++r, cslot += cnt) {
+                        RowPkt k;
+                        next_row(r, &k);
+                        const int kind = k.kind();
+                        RowJ J;
+                        unpack_pkt(k, true, true, la.im, lb.im, &J);
+                        // limits without branches.  Dependent: +-mu * the normal impulse of the previous sweep --
+                        // the group's own normal rows (2*ncc..3*ncc-1) come after its friction rows and are not
+                        // updated yet; a zero normal impulse clamps to zero, which is what the reference's
+                        // special case (sor_prox.rs:251-258) amounts to.
+                        float dep = 0.f;
+                        if (kind == NB2_ROW_DEPENDENT)
+                            dep = r < 2 * ncc ? simp[(2 * ncc + (r >> 1)) * TPBK + t] : __ldcg(&R.imp[k.dep()]);
+                        const float lim = k.h.z * dep;
+                        const float lo = kind == NB2_ROW_BILATERAL ? k.h.z : (kind == NB2_ROW_DEPENDENT ? -lim : 0.f);
+                        const float hi = kind == NB2_ROW_BILATERAL ? k.h.w : (kind == NB2_ROW_DEPENDENT ? lim : NB2_F32_MAX);
+                        float d = k.h.x;
+                        if (a) d += dot6(J.J1, la.v);
+                        if (b) d += dot6(J.J2, lb.v);
+                        float ni = fminf(fmaxf(k.imp - k.h.y * d, lo), hi);
+                        if (kind == NB2_ROW_NONE) ni = k.imp;
+                        const float dl = ni - k.imp;
+                        if (a) axpy6(dl, J.W1, la.v);
+                        if (b) axpy6(dl, J.W2, lb.v);
+                        if (ni != k.imp) __stcg(&R.imp[cslot], ni);
                     }
-                    const float ni = solve_row(kind, k.h, k.imp, dep, J, a, b, &la, &lb);
-                    if (ni != k.imp) __stcg(&R.imp[cslot], ni);
                 }
                 if (a) store_lam(lam, info.x, la);
                 if (b) store_lam(lam, info.y, lb);
