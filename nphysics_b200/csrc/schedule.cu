@@ -305,7 +305,11 @@ static int reserve_sched(Context* ctx, Sched* s, size_t n_items, size_t max_phas
     NB2_TRY(s->ph_gbase.reserve(ctx, max_phases + 1));
     NB2_TRY(s->ph_rbase.reserve(ctx, max_phases + 1));
     NB2_TRY(s->g_info.reserve(ctx, n_items));
-    NB2_TRY(s->hdr.reserve(ctx, 1));
+    {
+        const SchedHeader* before = s->hdr.p;
+        NB2_TRY(s->hdr.reserve(ctx, 1));
+        if (s->hdr.p != before) NB2_CUDA(ctx, cudaMemsetAsync(s->hdr.p, 0, s->hdr.cap * sizeof(SchedHeader), ctx->stream));  // padding words too
+    }
     return NB2_OK;
 }
 
