@@ -5,15 +5,20 @@ use std::process::Command;
 fn main() {
     let out = PathBuf::from(std::env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from(std::env::var("CARGO_MANIFEST_DIR").unwrap()).join("../../nphysics_b200/csrc");
-    let srcs = ["api.cu", "bodies.cu", "schedule.cu", "assemble.cu", "solve.cu"];
+    // (source, keep the reference's multiply-add order).  solve_coloured.cu holds the coloured-mode staged
+    // kernels, which may contract to FMA (csrc/Makefile).
+    let srcs = [("api.cu", true), ("bodies.cu", true), ("schedule.cu", true), ("assemble.cu", true), ("solve.cu", true),
+                ("activation.cu", true), ("solve_coloured.cu", false)];
     let mut objs = Vec::new();
-    for s in srcs.iter() {
+    for (s, no_fma) in srcs.iter() {
         let src = csrc.join(s);
         println!("cargo:rerun-if-changed={}", src.display());
         let obj = out.join(s).with_extension("o");
+        let mut args = vec!["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo"];
+        if *no_fma { args.push("-fmad=false"); }
+        args.extend_from_slice(&["-Xcompiler", "-fPIC", "--extended-lambda", "-c", "-o"]);
         let status = Command::new("nvcc")
-            .args(&["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-                    "-fmad=false", "-Xcompiler", "-fPIC", "--extended-lambda", "-c", "-o"])
+            .args(&args)
             .arg(&obj)
             .arg(&src)
             .status()
