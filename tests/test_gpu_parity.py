@@ -525,3 +525,69 @@ def test_impulse_cache_survives_a_contact_reindexing_coloured(layout):
     assert np.array_equal(outs[0][0]["velocity"], outs[1][0]["velocity"])
     assert np.array_equal(outs[0][1], outs[1][1])
     assert np.abs(outs[0][1]).max() > 0
+
+
+def _plate_scene(nx, nz):
+    """A dynamic plate on the ground carrying nx*nz small boxes: one body with nx*nz + 1 contact groups."""
+    rad = 0.1
+    centers = [(0.0, 0.11, 0.0)]
+    for i in range(nx):
+        for k in range(nz):
+            centers.append(((i - (nx - 1) / 2) * 0.25, 0.11 + 0.1 + 0.02 + 0.1, (k - (nz - 1) / 2) * 0.25))
+    bodies, he, off = scenes._make_boxes(centers, rad, 1.0, (8.0, 0.2, 8.0))
+    he[1] = (3.0, 0.1, 3.0)
+    mass, inertia = scenes.cuboid_mass_properties((3.0, 0.1, 3.0), 1.0)
+    bodies["mass"][1] = mass
+    bodies["local_inertia"][1] = inertia.reshape(9)
+    return scenes.Scene(bodies, he, off, name="plate%dx%d" % (nx, nz))
+
+
+def test_high_degree_body_needs_one_colour_per_group():
+    """101 groups share the plate, so the colouring needs >= 101 colours (each almost empty): the staged
+    kernels, the balancing and the refinement must cope with a long, thin schedule."""
+    sc = _plate_scene(10, 10)
+    gen = scenes.ContactGenerator(sc, search=4.0)
+    m, c = gen.generate()
+    assert len(m) == 101
+    outs = []
+    for mode in (REF, COL):
+        s = new_solver()
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+        for _ in range(6):
+            s.upload_manifolds(m, c)
+            s.step(mode)
+        st = s.get_stats()
+        assert int(st["non_finite"]) == 0
+        outs.append((s.download_body_states(), int(st["n_phases_velocity"])))
+    assert outs[1][1] >= 101
+    assert np.abs(outs[1][0]["position"][:, :3] - outs[0][0]["position"][:, :3]).max() < 2e-3
+    assert np.abs(outs[1][0]["velocity"] - outs[0][0]["velocity"]).max() < 0.1
+
+
+def test_more_than_256_groups_on_one_body_is_reported_in_coloured_mode():
+    """290 groups on one body exceed the 256 colours of the schedule: coloured mode reports
+    NB2_ERR_TOO_MANY_COLOURS at the next synchronisation point; the reference order (no colours) still
+    matches the oracle."""
+    from nphysics_b200.solver import Nb2Error
+    sc = _plate_scene(17, 17)
+    gen = scenes.ContactGenerator(sc, search=4.0)
+    m, c = gen.generate()
+    assert len(m) == 290
+    s = new_solver()
+    s.set_params(sc.params)
+    s.upload_bodies(sc.bodies)
+    s.upload_manifolds(m, c)
+    s.step(COL)
+    with pytest.raises(Nb2Error) as ei:
+        s.synchronize()
+    assert ei.value.code == abi.ERR_TOO_MANY_COLOURS
+    g, o = new_solver(), new_oracle()
+    for sim in (g, o):
+        sim.set_params(sc.params)
+        sim.upload_bodies(sc.bodies)
+        sim.upload_manifolds(m, c)
+    g.step(REF)
+    o.step()
+    g.synchronize()
+    check_step("plate ref", g, o)
