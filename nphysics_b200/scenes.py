@@ -190,6 +190,53 @@ def joint_chains(n_chains=10, links=6, rad=0.2, density=1.0, kind="mixed", groun
     return Scene(bodies, he, off, joints, name="chains_%dx%d_%s" % (n_chains, links, kind))
 
 
+def ragdolls(n=10, pitch=3.0, height=5.0, spin=2.0, density=0.3):
+    """BASELINE config 4, second half: the topology of examples3d/ragdoll3.rs:65-135 (torso + head + two
+    arms + two legs joined by five spherical joints) restated with BallConstraints between rigid bodies
+    (the shipped example builds a Multibody, which is out of scope).  Members are cuboids of the
+    members' extents (torso 0.2 x 1.2 x 0.4, head 0.4, arms 0.15 x 1.05, legs 0.15 x 1.55), density 0.3,
+    `space` 0.15 between members.  Ragdolls sit on a square lattice `height` above the origin plane and
+    start with an angular velocity of `spin` rad/s about z on the torso, so that the joints work while
+    the whole figure falls.  No colliders (joint rows only)."""
+    body_rady, body_radz, body_radx = 0.6, 0.2, 0.1
+    head_rad, member_rad, arm_length, leg_length, space = 0.2, 0.075, 0.45, 0.7, 0.15
+    members = [  # half extents, anchor on the torso (parent_shift), anchor on the member (body_shift)
+        ((head_rad, head_rad, head_rad), (0.0, body_rady + head_rad + space, 0.0), (0.0, 0.0, 0.0)),
+        ((member_rad, arm_length + member_rad, member_rad), (0.0, body_rady, body_radx + 2.0 * space), (0.0, arm_length + space, 0.0)),
+        ((member_rad, arm_length + member_rad, member_rad), (0.0, body_rady, -body_radx - 2.0 * space), (0.0, arm_length + space, 0.0)),
+        ((member_rad, leg_length + member_rad, member_rad), (0.0, -body_rady, body_radx), (0.0, leg_length + space, 0.0)),
+        ((member_rad, leg_length + member_rad, member_rad), (0.0, -body_rady, -body_radx), (0.0, leg_length + space, 0.0)),
+    ]
+    per_row = int(np.ceil(np.sqrt(n)))
+    nb = 1 + 6 * n
+    bodies = abi.new_bodies(nb)
+    bodies["status"][0] = abi.BODY_STATIC
+    bodies["flags"][0] = 0
+    he = np.zeros((nb, 3))
+    off = np.zeros((nb, 3))
+    joints = abi.new_joints(5 * n, abi.JOINT_BALL)
+    for r in range(n):
+        origin = np.array([(r % per_row) * pitch, height, (r // per_row) * pitch])
+        torso = 1 + 6 * r
+        m, inertia = cuboid_mass_properties((body_radx, body_rady, body_radz), density)
+        bodies["position"][torso, :3] = origin
+        bodies["mass"][torso] = m
+        bodies["local_inertia"][torso] = inertia.reshape(9)
+        bodies["velocity"][torso, 5] = spin
+        for k, (half, a1, a2) in enumerate(members):
+            b = torso + 1 + k
+            m, inertia = cuboid_mass_properties(half, density)
+            bodies["position"][b, :3] = origin + np.array(a1) - np.array(a2)
+            bodies["mass"][b] = m
+            bodies["local_inertia"][b] = inertia.reshape(9)
+            j = 5 * r + k
+            joints["body1"][j] = torso
+            joints["body2"][j] = b
+            joints["anchor1"][j] = a1
+            joints["anchor2"][j] = a2
+    return Scene(bodies, he, off, joints, name="ragdolls_%d" % n)
+
+
 # ----------------------------------------------------------------------------------------------
 # the manifold producer
 # ----------------------------------------------------------------------------------------------

@@ -591,3 +591,39 @@ def test_more_than_256_groups_on_one_body_is_reported_in_coloured_mode():
     o.step()
     g.synchronize()
     check_step("plate ref", g, o)
+
+
+def test_ragdolls_reference_order_and_coloured():
+    """Config 4's ragdoll topology (torso + head + 4 limbs, five BallConstraints per figure): a tree, not a
+    chain -- the torso carries five joint groups.  Reference order must match the oracle step by step;
+    the coloured mode must keep the anchors together as well as the oracle does."""
+    sc = scenes.ragdolls(6)
+    none_m, none_c = np.zeros(0, abi.manifold_dtype), np.zeros(0, abi.contact_dtype)
+    g, o, col = new_solver(), new_oracle(), new_solver()
+    for s in (g, o, col):
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+        s.upload_joints(sc.joints)
+    for k in range(25):
+        for s in (g, o, col):
+            s.upload_manifolds(none_m, none_c)
+        g.step(REF)
+        o.step()
+        col.step(COL)
+        sg, so = g.download_body_states(), o.download_body_states()
+        assert rel_err(sg["position"], so["position"]) <= TOL, k
+        assert rel_err(sg["velocity"], so["velocity"]) <= TOL, k
+    jg, jo = g.download_joints(), o.download_joints()
+    assert rel_err(jg["impulses"], jo["impulses"]) <= 1e-4
+    J = sc.joints
+
+    def drift(st):
+        p = st["position"].astype(np.float64)
+        w1 = p[J["body1"], :3] + scenes.quat_rotate(p[J["body1"], 3:7], J["anchor1"].astype(np.float64))
+        w2 = p[J["body2"], :3] + scenes.quat_rotate(p[J["body2"], 3:7], J["anchor2"].astype(np.float64))
+        return np.abs(w1 - w2).max()
+
+    d_col, d_o = drift(col.download_body_states()), drift(o.download_body_states())
+    assert d_col < max(2.0 * d_o, 5e-3)
+    st = col.get_stats()
+    assert int(st["non_finite"]) == 0 and int(st["n_phases_velocity"]) >= 5  # five joints share each torso

@@ -347,3 +347,34 @@ def test_step_ccd_does_not_touch_the_impulse_cache():
     after = o.download_body_states()
     assert not np.array_equal(after["velocity"], before["velocity"])  # the sub-step did solve and integrate
     assert np.isfinite(after["position"]).all()
+
+
+def test_ragdolls_centre_of_mass_falls_freely_and_joints_hold():
+    """Config 4's ragdoll topology (ragdoll3.rs:65-135 restated with BallConstraints): joint impulses are
+    internal, so each figure's centre of mass follows the semi-implicit free fall y0 - g dt^2 k(k+1)/2
+    while the five joints keep their anchors together."""
+    sc = scenes.ragdolls(3)
+    o = Oracle()
+    o.set_params(sc.params)
+    o.upload_bodies(sc.bodies)
+    o.upload_joints(sc.joints)
+    none_m, none_c = np.zeros(0, abi.manifold_dtype), np.zeros(0, abi.contact_dtype)
+    steps = 40
+    for _ in range(steps):
+        o.upload_manifolds(none_m, none_c)
+        o.step()
+    st = o.download_body_states()
+    dt, g = float(sc.params["dt"]), 9.81
+    mass = sc.bodies["mass"].astype(np.float64)
+    for r in range(3):
+        idx = np.arange(1 + 6 * r, 7 + 6 * r)
+        com0 = (mass[idx, None] * sc.bodies["position"][idx, :3]).sum(0) / mass[idx].sum()
+        com = (mass[idx, None] * st["position"][idx, :3].astype(np.float64)).sum(0) / mass[idx].sum()
+        assert abs(com[1] - (com0[1] - g * dt * dt * steps * (steps + 1) / 2.0)) < 2e-3
+        assert abs(com[0] - com0[0]) < 2e-3 and abs(com[2] - com0[2]) < 2e-3
+    J = sc.joints
+    p = st["position"].astype(np.float64)
+    w1 = p[J["body1"], :3] + scenes.quat_rotate(p[J["body1"], 3:7], J["anchor1"].astype(np.float64))
+    w2 = p[J["body2"], :3] + scenes.quat_rotate(p[J["body2"], 3:7], J["anchor2"].astype(np.float64))
+    assert np.abs(w1 - w2).max() < 5e-3
+    assert int(o.get_stats()["n_rows_two_body"]) == 3 * 5 * 3

@@ -69,7 +69,7 @@ def run(name, sc, m, c, vel, pos, steps=30, settle=40):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["pyramid3", "wall3", "wall3_tall", "chains10k", "pyramid3x4096"]
+    which = sys.argv[1:] or ["pyramid3", "wall3", "wall3_tall", "chains10k", "ragdolls10k", "pyramid3x4096"]
     for name in which:
         t0 = time.time()
         if name == "pyramid3":
@@ -89,6 +89,12 @@ if __name__ == "__main__":
             # links also make contacts (mixed joint/contact rows)
             sc = scenes.joint_chains(10000, 6, kind="mixed", with_ground_collider=True, ground_y=-0.22, pitch=6.0)
             m, c = scenes.ContactGenerator(sc, search=0.0).generate()
+            run(name, sc, m, c, 8, 3)
+        elif name == "ragdolls10k":
+            # 10 000 ragdolls (torso + head + 4 limbs, five BallConstraints each), joint rows only
+            sc = scenes.ragdolls(10000)
+            m = np.zeros(0, dtype=abi.manifold_dtype)
+            c = np.zeros(0, dtype=abi.contact_dtype)
             run(name, sc, m, c, 8, 3)
         elif name == "pyramid3x4096":
             base = scenes.pyramid3(30)
