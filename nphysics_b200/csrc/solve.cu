@@ -437,7 +437,7 @@ int launch_position_solve(Context* ctx, int mode) {
         int tpb_s, depth_s, blocks_s;
         if (staged_geometry(ctx, &tpb_s, &depth_s, &blocks_s)) {
             int rc = launch_position_solve_staged(ctx, sd, A, P, rows_div, tpb_s, blocks_s);
-            if (rc >= 0) return rc;
+            if (rc != NB2_STAGED_NOT_APPLICABLE) return rc;  // NB2_OK or a real error
         }
     }
     void* args[] = {&sd, &A, &joints, &manifolds, &cm, &prow, &pstride, &P, &iters, &rows_div, &bar};

@@ -568,7 +568,7 @@ int launch_position_solve_staged(Context* ctx, const SchedDev& sd_in, const PosA
     auto smem_of = [&](int e) { return (size_t)e * NB2_PENTRY * tpb * 16 + 2 * NB2_MAX_COLOURS * 4; };
     while (E > 1 && smem_of(E) > ctx->smem_optin) --E;
     if (const char* f = getenv("NB2_STAGED_PENTRIES")) E = atoi(f);
-    if (smem_of(E) > ctx->smem_optin) return -1;  // caller falls back to the plain kernel
+    if (smem_of(E) > ctx->smem_optin) return NB2_STAGED_NOT_APPLICABLE;  // caller falls back to the plain kernel
     if (!ctx->staged_pos_attr) {
         NB2_CUDA(ctx, cudaFuncSetAttribute(k_position_solve_staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)ctx->smem_optin));
