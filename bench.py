@@ -68,17 +68,64 @@ def algorithmic_bytes(n_r2, n_rg, n_c, n_b, iv, ip):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).
+
+    In-process NVML from a thread, every 10 ms: an `nvidia-smi -lms` child process initialises NVML inside
+    the timed region and stalls this process's kernel launches while it does (measured: +9 % on a 20-step
+    run).  Falls back to that child process only when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.index = index
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
+        self.thread = None
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()  # here, well before the timed region
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.handle = None
+
+    def _sample(self):
+        nv = self.nvml
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        except Exception:
+            mask = 0
+        for nm, bit in self.BITS.items():
+            if mask & bit:
+                self.reasons.add(nm)
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self.stop_flag.wait(0.01)
 
     def start(self):
+        if self.handle is not None:
+            import threading
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -89,32 +136,39 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        sm, mx, reasons = self.sm, self.mx, self.reasons
+        if self.thread is not None:
+            try:
+                self._sample()  # at least one sample under load even for a very short region
+            except Exception:
+                pass
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.f.close()
+            try:
+                for line in open(self.path):
+                    parts = [x.strip() for x in line.split(",")]
+                    if len(parts) < 9:
+                        continue
+                    try:
+                        sm.append(float(parts[1]))
+                        mx.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for nm, val in zip(self.NAMES, parts[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
+                os.unlink(self.path)
+            except Exception:
+                pass
+        else:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                parts = [x.strip() for x in line.split(",")]
-                if len(parts) < 9:
-                    continue
-                try:
-                    sm.append(float(parts[1]))
-                    mx.append(float(parts[2]))
-                except ValueError:
-                    continue
-                for nm, val in zip(names, parts[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-            os.unlink(self.path)
-        except Exception:
-            pass
         if sm:
             out["sm_mhz"] = float(np.median(sm))
             out["sm_max_mhz"] = float(max(mx))
