@@ -83,8 +83,12 @@ struct DevBuf {
 #define NB2_MAX_COLOURS (64 * NB2_MASK_WORDS)
 #define NB2_ROW_PLANES 5       // jacobian quads per velocity row (solve_common.cuh)
 #define NB2_STAGED_NOT_APPLICABLE 1  // launch_position_solve_staged: not an error (those are negative), use the plain kernel
+#ifndef NB2_BALANCE_ROUNDS
 #define NB2_BALANCE_ROUNDS 12
+#endif
+#ifndef NB2_IG_PASSES
 #define NB2_IG_PASSES 1        // iterated-greedy passes right after a fresh colouring ...
+#endif
 #define NB2_IG_REFINE 12       // ... and one more per following step with an unchanged conflict graph, up to this many
 
 // velocity-row kinds
