@@ -167,6 +167,36 @@ typedef struct nb2_contact {
     uint8_t pad_[6];
 } nb2_contact;
 
+/* The per-step part of a TrackedContact: what ncollide recomputes for a contact that persists from
+ * one step to the next (the leading 40 bytes of nb2_contact).  Everything else in the record -- id,
+ * ContactKinematic local points / directions / dilations / geometry tags -- stays as uploaded. */
+typedef struct nb2_contact_update {
+    float world1[3];
+    float world2[3];
+    float normal[3];
+    float depth;
+} nb2_contact_update;
+
+/* ----------------------------------------------------------------- colliders */
+/* A cuboid collider for the device manifold producer: ncollide's
+ * Cuboid::half_extents plus the Collider fields the contact path reads -- margin
+ * (src/object/collider.rs:165-167, default 0.01: :457-479), position_wrt_body_part and the BasicMaterial
+ * (src/material/basic_material.rs:14-43) with its combine modes (0 Average, 1 Min, 2 Multiply, 3 Max:
+ * src/material/material.rs:72-86).  Surface velocities are not carried (BasicMaterial's default: none). */
+typedef struct nb2_collider {
+    float half_extents[3];
+    float margin;
+    float translation_wrt_body[3];
+    float friction;
+    float rotation_wrt_body[4]; /* unit quaternion ijkw */
+    float restitution;
+    int32_t body;               /* index of the body the collider is attached to */
+    uint8_t friction_mode;
+    uint8_t restitution_mode;
+    uint8_t pad_[2];
+    uint32_t flags;             /* reserved, 0 */
+} nb2_collider;
+
 /* ------------------------------------------------------------------ joints */
 /* Constraint-based joints (src/joint/ *_constraint.rs). */
 typedef enum nb2_joint_type {
@@ -254,7 +284,8 @@ const char* nb2_error_string(int err);
  * (integration_parameters.rs:169-189, examples3d/pyramid3.rs:21). */
 int nb2_default_params(nb2_params* out);
 /* sizeof() of each ABI struct, for binding self-checks:
- * which: 0 params, 1 body, 2 body_state, 3 manifold, 4 contact, 5 joint, 6 stats */
+ * which: 0 params, 1 body, 2 body_state, 3 manifold, 4 contact, 5 joint, 6 stats, 7 activation,
+ * 8 contact_update, 9 collider */
 int nb2_sizeof(int which);
 /* Material::combine for two BasicMaterials (material.rs:72-86,134-177,
  * basic_material.rs:30-43).  mode: 0 Average, 1 Min, 2 Multiply, 3 Max.
@@ -295,6 +326,38 @@ int nb2_upload_body_states(nb2_context* ctx, const nb2_body_state* states, uint3
 /* The contact set for the next step ("uploaded once per step"). */
 int nb2_upload_manifolds(nb2_context* ctx, const nb2_manifold* manifolds, uint32_t n_manifolds,
                          const nb2_contact* contacts, uint32_t n_contacts);
+/* Contacts that persist from the previous step (same manifold list, same contact order, same ids):
+ * only the 40 bytes per contact that changed are uploaded and scattered into the device records of the
+ * last nb2_upload_manifolds.  n_contacts must equal that upload's count; when a contact appears or
+ * disappears the host uploads the whole set again.  Asynchronous like nb2_upload_manifolds. */
+int nb2_update_contacts(nb2_context* ctx, const nb2_contact_update* updates, uint32_t n_contacts);
+
+/* ---- Device manifold producer (replaces the ncollide side of
+ * src/world/geometrical_world.rs:285-320 for cuboid piles).  With it a step needs no contact upload at
+ * all: bodies, colliders and persistent feature pairs live on the device.
+ *
+ * nb2_upload_colliders: the cuboid colliders (any number per body; bodies must be uploaded first).
+ * nb2_detect_pairs: broad phase + feature discovery at the CURRENT device poses: every (dynamic,
+ *   dynamic) collider pair whose centres are within `search_radius` (< 0: (2 r_max + reach) * sqrt(2) *
+ *   1.01, r_max the largest half extent of a dynamic collider) and every (non-dynamic, dynamic) pair,
+ *   that face each other along one axis within reach = margin1 + margin2 + 2 * linear_prediction
+ *   (collider.rs:542-549) with overlapping projections on the other two.  `flip_permille` of the pairs
+ *   (a hash of the pair) list the Point side first (exercises Point/Plane kinematics).  Pairs are
+ *   persistent until the next call; *out_pairs (may be NULL) receives their number.  Synchronises.
+ * nb2_generate_manifolds: one manifold per pair at the current device poses -- the <= 4 corners of the
+ *   faces' overlap rectangle closer than `reach`, contact i of pair p carrying the id 4 p + i + 1 -- written
+ *   where nb2_upload_manifolds would have put them: manifold p owns the contact slots [4p, 4p + 4).
+ *   Call it before every nb2_step instead of nb2_upload_manifolds.  Asynchronous.
+ * nb2_download_manifolds: the device-side contact set of the next step (from either source), e.g. to
+ *   feed a host-side consumer or the test oracle.  Writes min(capacity, n) records of each kind. */
+int nb2_upload_colliders(nb2_context* ctx, const nb2_collider* colliders, uint32_t n_colliders);
+int nb2_detect_pairs(nb2_context* ctx, float linear_prediction, float search_radius, uint32_t flip_permille,
+                     uint32_t* out_pairs);
+int nb2_generate_manifolds(nb2_context* ctx);
+int nb2_download_manifolds(nb2_context* ctx, nb2_manifold* out_manifolds, uint32_t manifold_capacity,
+                           nb2_contact* out_contacts, uint32_t contact_capacity, uint32_t* out_n_manifolds,
+                           uint32_t* out_n_contacts);
+
 /* The active joint set, in island_joints order.  Cached impulses/broken flags
  * in the records seed the device copy. */
 int nb2_upload_joints(nb2_context* ctx, const nb2_joint* joints, uint32_t n_joints);
@@ -340,6 +403,14 @@ int nb2_get_stats(nb2_context* ctx, nb2_stats* out);
  * and writes {assembly, velocity_resolution, velocity_update, position_resolution, step,
  * velocity_kernel, position_kernel, schedule} in milliseconds.  No reductions are launched. */
 int nb2_get_timers(nb2_context* ctx, float* out8);
+/* The schedule of the last step, one entry per constraint group (the rows of <= 4 contacts of a
+ * manifold, or the rows of one joint): its phase (colour in NB2_MODE_COLOURED, level in
+ * NB2_MODE_REFERENCE_ORDER; -1 = group not scheduled: no dynamic side, broken joint) and the DYNAMIC
+ * body of each side (-1 = static / kinematic / sleeping side: such sides never conflict).  Two groups
+ * of one colour never share a dynamic body; tests assert exactly that.  Writes min(capacity, n) entries
+ * and the group count to *out_n.  Any output array may be NULL. */
+int nb2_download_schedule(nb2_context* ctx, int32_t* out_phase, int32_t* out_body1, int32_t* out_body2,
+                          uint32_t capacity, uint32_t* out_n);
 /* Number of kernels this context launched since creation (bench.py's
  * gpu_launches). */
 int nb2_launch_count(const nb2_context* ctx, uint64_t* out);

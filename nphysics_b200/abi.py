@@ -91,9 +91,18 @@ def new_activation(n, threshold=DEFAULT_SLEEP_THRESHOLD):
     return a
 
 
+# nb2_contact_update: the per-step part of a TrackedContact (the leading 40 bytes of nb2_contact)
+contact_update_dtype = np.dtype([("world1", f4, 3), ("world2", f4, 3), ("normal", f4, 3), ("depth", f4)], align=True)
+
+# nb2_collider: cuboid collider of the device manifold producer
+collider_dtype = np.dtype([
+    ("half_extents", f4, 3), ("margin", f4), ("translation_wrt_body", f4, 3), ("friction", f4),
+    ("rotation_wrt_body", f4, 4), ("restitution", f4), ("body", i4), ("friction_mode", u1),
+    ("restitution_mode", u1), ("pad_", u1, 2), ("flags", u4)], align=True)
+
 SIZEOF_ORDER = [params_dtype, body_dtype, body_state_dtype, manifold_dtype, contact_dtype, joint_dtype,
-                stats_dtype, activation_dtype]
-EXPECTED_SIZES = [64, 176, 52, 100, 112, 160, 88, 8]
+                stats_dtype, activation_dtype, contact_update_dtype, collider_dtype]
+EXPECTED_SIZES = [64, 176, 52, 100, 112, 160, 88, 8, 40, 64]
 
 for _d, _s in zip(SIZEOF_ORDER, EXPECTED_SIZES):
     assert _d.itemsize == _s, (_d, _d.itemsize, _s)
@@ -151,3 +160,19 @@ def new_joints(n, jtype=JOINT_BALL):
     j["break_force_squared"] = FLT_MAX
     j["break_torque_squared"] = FLT_MAX
     return j
+
+
+def new_colliders(n):
+    c = np.zeros(n, dtype=collider_dtype)
+    c["rotation_wrt_body"][:, 3] = 1.0
+    c["margin"] = 0.01       # ColliderDesc::default_margin (collider.rs:457-479)
+    c["friction"] = 0.5      # BasicMaterial::default (basic_material.rs:56-60)
+    return c
+
+
+def contact_updates_of(contacts):
+    """The per-step part (nb2_contact_update) of full contact records."""
+    u = np.zeros(len(contacts), dtype=contact_update_dtype)
+    for f in ("world1", "world2", "normal", "depth"):
+        u[f] = contacts[f]
+    return u

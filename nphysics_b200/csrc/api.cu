@@ -47,6 +47,10 @@ static void release_all(Context* c) {
     c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
     c->c_geo.release(); c->bal.release(); c->p_hdr.release();
     c->true_status.release(); c->act.release(); c->cc_parent.release(); c->cc_can.release(); c->wake_list.release();
+    c->colliders.release(); c->coll_world.release(); c->np_is_big.release(); c->np_big_off.release(); c->np_par.release();
+    c->pair_cnt.release(); c->pair_off.release(); c->grid_count.release(); c->grid_off.release(); c->grid_cursor.release();
+    c->np_big_list.release(); c->grid_entries.release(); c->pair_feat.release(); c->pair_q.release();
+    c->contact_updates.release();
     if (c->host_hdr) cudaFreeHost(c->host_hdr);
     c->host_hdr = nullptr;
 }
@@ -211,6 +215,8 @@ int nb2_sizeof(int which) {
         case 5: return (int)sizeof(nb2_joint);
         case 6: return (int)sizeof(nb2_stats);
         case 7: return (int)sizeof(nb2_activation);
+        case 8: return (int)sizeof(nb2_contact_update);
+        case 9: return (int)sizeof(nb2_collider);
         default: return NB2_ERR_INVALID_ARGUMENT;
     }
 }
@@ -264,6 +270,7 @@ int nb2_create(int device, void* stream, nb2_context** out) {
     ctx->have_params = true;
     // developer knob for A/B measurements of the coloured velocity kernel variants (solver.cuh)
     if (const char* vk = getenv("NB2_VELOCITY_KERNEL")) ctx->velocity_kernel = atoi(vk);
+    if (const char* pr = getenv("NB2_POISON_ROWS")) ctx->poison_rows = atoi(pr) != 0;
     if (cudaSetDevice(device) != cudaSuccess) {
         delete h;
         return set_error(nullptr, NB2_ERR_CUDA, "cudaSetDevice failed");
@@ -372,6 +379,8 @@ int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
     // joints / manifolds referring to the old set are dropped
     ctx->n_manifolds = ctx->n_contacts = 0;
     ctx->n_joints = 0;
+    ctx->n_colliders = ctx->n_pairs = 0;
+    ctx->pairs_valid = false;
     ctx->stepped = false;
     NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may free `bodies` on return
     return NB2_OK;
@@ -414,6 +423,77 @@ int nb2_upload_manifolds(nb2_context* h, const nb2_manifold* manifolds, uint32_t
                                       cudaMemcpyHostToDevice, ctx->stream));
     NB2_TRY(launch_validate_inputs(ctx));
     // asynchronous: the caller's arrays must stay valid until the next nb2_synchronize / download
+    return NB2_OK;
+}
+
+int nb2_update_contacts(nb2_context* h, const nb2_contact_update* updates, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (n && !updates) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null contact updates");
+    if (n != ctx->n_contacts)
+        return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "contact updates: expected %u (the last uploaded contact set), got %u",
+                         ctx->n_contacts, n);
+    if (!n) return NB2_OK;
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((size_t)n > ctx->contact_updates.cap) NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return launch_update_contacts(ctx, updates, n);
+}
+
+int nb2_upload_colliders(nb2_context* h, const nb2_collider* colliders, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (n && !colliders) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null colliders");
+    if (!ctx->n_bodies) return set_error(ctx, NB2_ERR_NOT_READY, "upload bodies before their colliders");
+    for (uint32_t i = 0; i < n; ++i)
+        if (colliders[i].body < 0 || (uint32_t)colliders[i].body >= ctx->n_bodies)
+            return set_error(ctx, NB2_ERR_BAD_INDEX, "collider %u is attached to body %d (of %u)", i, colliders[i].body, ctx->n_bodies);
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return launch_upload_colliders(ctx, colliders, n);
+}
+
+int nb2_detect_pairs(nb2_context* h, float linear_prediction, float search_radius, uint32_t flip_permille, uint32_t* out_pairs) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (out_pairs) *out_pairs = 0;
+    if (!ctx->n_colliders) return set_error(ctx, NB2_ERR_NOT_READY, "upload colliders first");
+    if (!(linear_prediction >= 0.f)) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "the prediction distance must be >= 0");
+    if (flip_permille > 1000u) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "flip_permille is a fraction of 1000");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_TRY(launch_detect_pairs(ctx, linear_prediction, search_radius, flip_permille, out_pairs));
+    unsigned int f = 0;
+    NB2_CUDA(ctx, cudaMemcpyAsync(&f, ctx->flags.p, sizeof(f), cudaMemcpyDeviceToHost, ctx->stream));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (f & 4u) {
+        unsigned int keep = f & ~4u;
+        NB2_CUDA(ctx, cudaMemcpyAsync(ctx->flags.p, &keep, sizeof(keep), cudaMemcpyHostToDevice, ctx->stream));
+        NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->pairs_valid = false;
+        return set_error(ctx, NB2_ERR_UNSUPPORTED, "a collider has more contact partners than the producer tracks");
+    }
+    return NB2_OK;
+}
+
+int nb2_generate_manifolds(nb2_context* h) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!ctx->pairs_valid) return set_error(ctx, NB2_ERR_NOT_READY, "call nb2_detect_pairs first");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_generate_manifolds(ctx);
+}
+
+int nb2_download_manifolds(nb2_context* h, nb2_manifold* out_m, uint32_t cap_m, nb2_contact* out_c, uint32_t cap_c,
+                           uint32_t* out_nm, uint32_t* out_nc) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (out_nm) *out_nm = ctx->n_manifolds;
+    if (out_nc) *out_nc = ctx->n_contacts;
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t km = out_m ? (ctx->n_manifolds < cap_m ? ctx->n_manifolds : cap_m) : 0;
+    const size_t kc = out_c ? (ctx->n_contacts < cap_c ? ctx->n_contacts : cap_c) : 0;
+    if (km) NB2_CUDA(ctx, cudaMemcpyAsync(out_m, ctx->manifolds.p, km * sizeof(nb2_manifold), cudaMemcpyDeviceToHost, ctx->stream));
+    if (kc) NB2_CUDA(ctx, cudaMemcpyAsync(out_c, ctx->contacts.p, kc * sizeof(nb2_contact), cudaMemcpyDeviceToHost, ctx->stream));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NB2_OK;
 }
 
@@ -587,16 +667,7 @@ int nb2_get_stats(nb2_context* h, nb2_stats* out) {
         s.n_rows_two_body = u[1];
         s.n_rows_ground = u[2];
         s.non_finite = u[3];
-        if (ctx->n_joints) {
-            // broken joints: count on the host from a download (diagnostic path only)
-            nb2_joint* tmp = (nb2_joint*)malloc((size_t)ctx->n_joints * sizeof(nb2_joint));
-            if (tmp) {
-                if (cudaMemcpy(tmp, ctx->joints.p, (size_t)ctx->n_joints * sizeof(nb2_joint), cudaMemcpyDeviceToHost) ==
-                    cudaSuccess)
-                    for (uint32_t i = 0; i < ctx->n_joints; ++i) s.n_broken_joints += tmp[i].broken ? 1u : 0u;
-                free(tmp);
-            }
-        }
+        s.n_broken_joints = u[5];
         if (ctx->ev_valid) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ctx->ev.e[0], ctx->ev.e[1]);
@@ -627,6 +698,36 @@ int nb2_get_timers(nb2_context* h, float* out8) {
     NB2_CUDA(ctx, cudaEventSynchronize(ctx->ev.e[5]));
     const int pairs[8][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {0, 5}, {6, 7}, {8, 9}, {10, 11}};
     for (int k = 0; k < 8; ++k) NB2_CUDA(ctx, cudaEventElapsedTime(&out8[k], ctx->ev.e[pairs[k][0]], ctx->ev.e[pairs[k][1]]));
+    return NB2_OK;
+}
+
+int nb2_download_schedule(nb2_context* h, int32_t* out_phase, int32_t* out_body1, int32_t* out_body2, uint32_t capacity,
+                          uint32_t* out_n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!out_n) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null out_n");
+    if (!ctx->stepped) return set_error(ctx, NB2_ERR_NOT_READY, "no step has been scheduled yet");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const Sched& s = ctx->vs;
+    const size_t n = s.n_items;
+    *out_n = (uint32_t)n;
+    const size_t k = n < capacity ? n : capacity;
+    if (k) {
+        static_assert(sizeof(int) == sizeof(int32_t), "schedule arrays are copied as int32");
+        if (out_phase) NB2_CUDA(ctx, cudaMemcpyAsync(out_phase, s.it_phase.p, k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_body1) NB2_CUDA(ctx, cudaMemcpyAsync(out_body1, s.it_a.p, k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_body2) NB2_CUDA(ctx, cudaMemcpyAsync(out_body2, s.it_b.p, k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        // unscheduled groups keep whatever phase an earlier step left: report them as -1
+        int* ty = (int*)malloc(k * sizeof(int));
+        if (!ty) return set_error(ctx, NB2_ERR_OUT_OF_MEMORY, "host allocation failed");
+        cudaError_t e = cudaMemcpyAsync(ty, s.it_type.p, k * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess && out_phase)
+            for (size_t i = 0; i < k; ++i)
+                if (ty[i] == NB2_ITEM_INVALID) out_phase[i] = -1;
+        free(ty);
+        NB2_CUDA(ctx, e);
+    }
     return NB2_OK;
 }
 

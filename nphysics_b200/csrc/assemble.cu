@@ -525,8 +525,16 @@ __global__ void __launch_bounds__(TPB) k_assemble_joints(unsigned int nJ, const 
         ++r;
     };
     auto skip = [&]() {
-        out.jac[4 * out.n_slots_max + vs.row_slot(ji, r)] = make_float4(0.f, 0.f, __int_as_float(NB2_ROW_NONE), 0.f);
-        out.imp[vs.row_slot(ji, r)] = 0.f;
+        // a reserved but unused row: every plane is written.  The staged kernel streams and multiplies all
+        // of them unconditionally, and 0 * the stale NaN/Inf bits of a recycled allocation would poison
+        // mj_lambda (tests/test_gpu_parity.py::test_unused_joint_rows_ignore_stale_memory)
+        const size_t slot = vs.row_slot(ji, r);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out.jac[(size_t)k * out.n_slots_max + slot] = z;
+        out.jac[4 * out.n_slots_max + slot] = make_float4(0.f, 0.f, __int_as_float(NB2_ROW_NONE), 0.f);
+        out.hdr[slot] = z;
+        out.imp[slot] = 0.f;
         ++r;
     };
     auto lin3 = [&]() {  // helper::cancel_relative_linear_velocity (helper.rs:247-293)
@@ -787,6 +795,11 @@ int launch_assemble(Context* ctx, int mode) {
     SchedView vs = view_of(ctx->vs);
     SchedView ps = ref ? view_of(ctx->ps) : vs;
     const int prev = 1 - ctx->cur;
+    if (ctx->poison_rows) {  // every byte the solve kernels read must have been written by this step's assembly
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->r_jac.p, 0xFF, ctx->r_jac.cap * sizeof(float4), ctx->stream));
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->r_hdr.p, 0xFF, ctx->r_hdr.cap * sizeof(float4), ctx->stream));
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->r_imp.p, 0xFF, ctx->r_imp.cap * sizeof(float), ctx->stream));
+    }
     if (ctx->n_joints) {
         k_assemble_joints<<<nblk(ctx->n_joints), TPB, 0, ctx->stream>>>(ctx->n_joints, ctx->joints.p,
                                                                         body_arrays(ctx), vs, row_out(ctx));

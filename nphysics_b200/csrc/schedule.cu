@@ -181,10 +181,16 @@ __global__ void k_chunk_counts(const nb2_manifold* __restrict__ m, unsigned int 
 }
 __global__ void k_fill_chunks(const nb2_manifold* __restrict__ m, unsigned int nm,
                               const unsigned int* __restrict__ chunk_base, unsigned int* chunk_manifold,
-                              unsigned int* c_manifold) {
+                              unsigned int* c_manifold, unsigned int maxc, unsigned int* flags) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nm) return;
     unsigned int cb = chunk_base[i], ce = chunk_base[i + 1];
+    // manifolds whose contact ranges overlap can claim more chunks than the n_manifolds + n_contacts / 4
+    // the buffers were sized for: the excess is dropped and reported as a bad record
+    if (ce > maxc) {
+        atomicOr(flags, 1u);
+        ce = maxc;
+    }
     for (unsigned int k = cb; k < ce; ++k) chunk_manifold[k] = i;
     unsigned int f = m[i].first_contact, nc = m[i].num_contacts;
     for (unsigned int k = 0; k < nc; ++k) c_manifold[f + k] = i;
@@ -331,7 +337,8 @@ int launch_build_items(Context* ctx, int mode) {
     NB2_TRY(exclusive_scan_u32(ctx, ctx->deg.p, ctx->chunk_base.p, nM));
     if (nM) {
         k_fill_chunks<<<nblk(nM), TPB, 0, ctx->stream>>>(ctx->manifolds.p, nM, ctx->chunk_base.p,
-                                                         ctx->chunk_manifold.p, ctx->c_manifold.p);
+                                                         ctx->chunk_manifold.p, ctx->c_manifold.p,
+                                                         (unsigned int)maxc, ctx->flags.p);
         ctx->launches++;
     }
     const bool ref = mode == NB2_MODE_REFERENCE_ORDER;

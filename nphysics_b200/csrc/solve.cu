@@ -446,8 +446,14 @@ int launch_position_solve(Context* ctx, int mode) {
     return NB2_OK;
 }
 
+__global__ void k_count_broken(const nb2_joint* __restrict__ joints, unsigned int n, unsigned int* out) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int v = __ballot_sync(0xffffffffu, i < n && joints[i].broken != 0u);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, (unsigned int)__popc(v));
+}
+
 // stat_f layout: [0] res_max ; stat_u[4] pen_max key ; stat_d: [0] res_sq [1] energy ; stat_u: [0] res_n [1] rows_two
-// [2] rows_ground [3] non_finite
+// [2] rows_ground [3] non_finite [5] broken joints
 int launch_stats(Context* ctx, int mode) {
     const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
     NB2_TRY(ctx->stat_f.reserve(ctx, 16));
@@ -475,6 +481,10 @@ int launch_stats(Context* ctx, int mode) {
         }
     }
     NB2_TRY(launch_body_stats(ctx, d + 1, u + 3));
+    if (ctx->n_joints) {
+        k_count_broken<<<(ctx->n_joints + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(ctx->joints.p, ctx->n_joints, u + 5);
+        ctx->launches++;
+    }
     NB2_CUDA(ctx, cudaGetLastError());
     return NB2_OK;
 }

@@ -111,7 +111,9 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+#ifdef NB2_TRACE  // developer build (make EXTRA=-DNB2_TRACE): per-phase timestamps, see DESIGN.md "Developer knobs"
 __device__ unsigned long long g_trace[4096];
+#endif
 __device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // pending in 0..2
     if (pending <= 0) cp_async_wait<0>();
     else if (pending == 1) cp_async_wait<1>();
@@ -321,18 +323,24 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
                 if (b) store_lam(lam, info.y, lb);
             }
             gb.sync();
+#ifdef NB2_TRACE
             if (trace && blockIdx.x == 0 && threadIdx.x == 0) {
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (s * np + p < 4096) g_trace[s * np + p] = now;
             }
+#endif
         }
     }
     cp_async_wait<0>();
+#ifdef NB2_TRACE
     if (trace && blockIdx.x == 0 && threadIdx.x == 0)
         for (unsigned int i = 1; i < min((iters + 1) * np, 4096u); ++i)
             if (i / np == (unsigned int)trace)
                 printf("sweep %u phase %u groups %u dt_ns %llu\n", i / np, i % np, s_cnt[i % np], g_trace[i] - g_trace[i - 1]);
+#else
+    (void)trace;
+#endif
 }
 
 static size_t staged_smem(int depth, int tpb) {
@@ -370,6 +378,9 @@ bool staged_geometry(Context* ctx, int* tpb_out, int* depth_out, int* blocks_out
     if (const char* f = getenv("NB2_STAGED_DEPTH")) depth = atoi(f);
     if (depth < NB2_STAGED_MIN_DEPTH) depth = NB2_STAGED_MIN_DEPTH;
     if (depth > NB2_STAGED_MAX_DEPTH) depth = NB2_STAGED_MAX_DEPTH;
+    // whatever the overrides asked for must still fit the opt-in shared memory of the device
+    while (depth > NB2_STAGED_MIN_DEPTH && staged_smem(depth, tpb) > ctx->smem_optin) --depth;
+    while (tpb > 32 && staged_smem(depth, tpb) > ctx->smem_optin) tpb -= 32;
     *blocks_out = (int)blocks;
     *tpb_out = tpb;
     *depth_out = depth;

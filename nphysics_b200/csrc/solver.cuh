@@ -217,6 +217,17 @@ struct Context {
     uint32_t imp_n[2] = {0, 0};
     int cur = 0;                // buffer written by the current step
 
+    // ---- device manifold producer (narrowphase.cu)
+    uint32_t n_colliders = 0, n_pairs = 0;
+    bool pairs_valid = false;
+    float np_prediction = 0.001f;
+    DevBuf<nb2_collider> colliders;
+    DevBuf<float4> coll_world;            // collider centre in world space, w = 1 for a dynamic collider
+    DevBuf<unsigned int> np_is_big, np_big_off, np_par, pair_cnt, pair_off, grid_count, grid_off, grid_cursor;
+    DevBuf<int> np_big_list, grid_entries, pair_feat;
+    DevBuf<float4> pair_q;                // [3][cap] persistent feature pairs
+    DevBuf<nb2_contact_update> contact_updates;
+
     // ---- schedules
     Sched vs, ps;          // velocity / position (coloured mode uses vs for both)
     // reference-order scratch
@@ -258,6 +269,7 @@ struct Context {
     // staged (rows streamed through a shared-memory ring with cp.async, prefetched across the phase
     // barrier; the default).  NB2_VELOCITY_KERNEL overrides (A/B runs, tests).
     int velocity_kernel = 2;
+    bool poison_rows = false;      // NB2_POISON_ROWS: fill the row planes with NaN bits before every assembly (tests)
     size_t smem_optin = 0;         // cudaDevAttrMaxSharedMemoryPerBlockOptin
     bool staged_attr = false, staged_pos_attr = false;
     DevBuf<float4> p_hdr;          // [5][n_ghdr_max] coloured position groups: bodies + collider-to-body poses
@@ -344,6 +356,11 @@ int query_coop_limits(Context* ctx);
 // assemble.cu
 int launch_assemble(Context* ctx, int mode);
 int launch_cache_impulses(Context* ctx, int mode);
+// narrowphase.cu
+int launch_upload_colliders(Context* ctx, const nb2_collider* colliders, uint32_t n);
+int launch_detect_pairs(Context* ctx, float prediction, float search, unsigned int flip_permille, uint32_t* out_pairs);
+int launch_generate_manifolds(Context* ctx);
+int launch_update_contacts(Context* ctx, const nb2_contact_update* updates, uint32_t n);
 // solve.cu
 int launch_velocity_solve(Context* ctx, int mode);
 int launch_position_solve(Context* ctx, int mode);

@@ -116,12 +116,13 @@ def wall3(width=50, height=10, rad=0.1, density=1.0):
     return Scene(bodies, he, off, name="wall3_%dx%d" % (width, height))
 
 
-def tile(scene, copies, pitch=20.0, per_row=64):
+def tile(scene, copies, pitch=20.0, per_row=64, first_world=0):
     """BASELINE config 5: `copies` independent translated copies of one scene (each with its own
-    ground body), world w shifted by (w % per_row * pitch, 0, w // per_row * pitch)."""
+    ground body), world w shifted by (w % per_row * pitch, 0, w // per_row * pitch); `first_world`
+    selects worlds first_world .. first_world + copies - 1 of the lattice (e.g. its far corner)."""
     n = len(scene.bodies)
     bodies = np.tile(scene.bodies, copies)
-    w = np.repeat(np.arange(copies), n)
+    w = np.repeat(np.arange(first_world, first_world + copies), n)
     bodies["position"][:, 0] += (w % per_row) * pitch
     bodies["position"][:, 2] += (w // per_row) * pitch
     he = np.tile(scene.half_extents, (copies, 1))
@@ -250,7 +251,10 @@ class ContactGenerator:
     (nb2_manifold[], nb2_contact[]) with stable keys.
     """
 
-    def __init__(self, scene, flip_fraction=0.0, search=None):
+    def __init__(self, scene, flip_fraction=0.0, search=None, order="pair"):
+        """order="pair": pairs sorted by (a, b).  order="owner": the canonical order of the device producer
+        (csrc/narrowphase.cu) -- every pair is owned by its dynamic collider (the lower index of two dynamic
+        ones) and pairs are listed owner by owner, an owner's non-dynamic partners before its dynamic ones."""
         self.scene = scene
         pos = scene.bodies["position"].astype(np.float64)
         centers = pos[:, :3] + scene.coll_offset
@@ -294,9 +298,15 @@ class ContactGenerator:
             axis[ok] = ax
             keep |= ok
         a, b, d, axis = a[keep], b[keep], d[keep], axis[keep]
-        # deterministic order: by (a, b)
-        order = np.lexsort((b, a))
-        a, b, d, axis = a[order], b[order], d[order], axis[order]
+        # deterministic order: by (a, b), or owner by owner
+        if order == "owner":
+            a_dyn = status[a] == abi.BODY_DYNAMIC
+            owner = np.where(a_dyn, a, b)
+            partner = np.where(a_dyn, b, a)
+            perm = np.lexsort((partner, a_dyn, owner))
+        else:
+            perm = np.lexsort((b, a))
+        a, b, d, axis = a[perm], b[perm], d[perm], axis[perm]
         npairs = len(a)
         rows = np.arange(npairs)
         sign = np.where(d[rows, axis] >= 0, 1.0, -1.0)
@@ -386,6 +396,21 @@ class ContactGenerator:
         contacts["geom1"] = np.where(f, abi.GEOM_POINT, abi.GEOM_PLANE)
         contacts["geom2"] = np.where(f, abi.GEOM_PLANE, abi.GEOM_POINT)
         return manifolds, contacts
+
+
+def scene_colliders(scene):
+    """nb2_collider records of a Scene: one cuboid per body that has one (in body order, so that collider
+    indices order like body indices), translation-only collider offsets, the scene-wide margin and material."""
+    has = scene.half_extents.max(axis=1) > 0
+    idx = np.nonzero(has)[0]
+    c = abi.new_colliders(len(idx))
+    c["half_extents"] = scene.half_extents[idx]
+    c["translation_wrt_body"] = scene.coll_offset[idx]
+    c["margin"] = scene.margin
+    c["friction"] = scene.friction
+    c["restitution"] = scene.restitution
+    c["body"] = idx
+    return c
 
 
 def row_counts(scene, manifolds):

@@ -23,7 +23,9 @@ EXPORTS = [
     "nb2_clear_impulse_cache", "nb2_upload_activation", "nb2_update_activation", "nb2_download_activation",
     "nb2_step", "nb2_step_ccd", "nb2_synchronize", "nb2_download_body_states",
     "nb2_download_contact_impulses", "nb2_download_joints", "nb2_get_stats", "nb2_get_timers",
-    "nb2_launch_count",
+    "nb2_launch_count", "nb2_download_schedule",
+    "nb2_update_contacts", "nb2_upload_colliders", "nb2_detect_pairs", "nb2_generate_manifolds",
+    "nb2_download_manifolds",
 ]
 
 
@@ -152,6 +154,52 @@ class Solver:
         self._chk(self.lib.nb2_upload_manifolds(self.h, ctypes.c_void_p(m_ptr), ctypes.c_uint32(nm),
                                                 ctypes.c_void_p(c_ptr), ctypes.c_uint32(nc)))
 
+    def update_contacts(self, updates):
+        """Per-step refresh (world1, world2, normal, depth) of the contacts of the last upload_manifolds."""
+        u = np.ascontiguousarray(updates, dtype=abi.contact_update_dtype)
+        self._keep_upd = u  # asynchronous
+        self._chk(self.lib.nb2_update_contacts(self.h, abi.ptr(u), ctypes.c_uint32(len(u))))
+
+    def update_contacts_raw(self, ptr, n):
+        self._chk(self.lib.nb2_update_contacts(self.h, ctypes.c_void_p(ptr), ctypes.c_uint32(n)))
+
+    # ---- device manifold producer (SURVEY 8 f2)
+    def upload_colliders(self, colliders):
+        c = np.ascontiguousarray(colliders, dtype=abi.collider_dtype)
+        self._chk(self.lib.nb2_upload_colliders(self.h, abi.ptr(c), ctypes.c_uint32(len(c))))
+
+    def detect_pairs(self, linear_prediction=0.001, search_radius=-1.0, flip_fraction=0.0):
+        n = ctypes.c_uint32()
+        self._chk(self.lib.nb2_detect_pairs(self.h, ctypes.c_float(linear_prediction), ctypes.c_float(search_radius),
+                                            ctypes.c_uint32(int(flip_fraction * 1000)), ctypes.byref(n)))
+        self.n_pairs = int(n.value)
+        return self.n_pairs
+
+    def generate_manifolds(self):
+        self._chk(self.lib.nb2_generate_manifolds(self.h))
+        self.n_contacts = 4 * self.n_pairs
+
+    def download_manifolds(self, compact=False):
+        """The contact set the next step will solve, as it sits on the device.  compact=True drops manifolds
+        without contacts and closes the gaps of the device producer's 4-slots-per-pair layout, i.e. returns
+        the list a host-side producer would have uploaded (plus the slot of every kept contact)."""
+        nm, nc = ctypes.c_uint32(), ctypes.c_uint32()
+        self._chk(self.lib.nb2_download_manifolds(self.h, None, ctypes.c_uint32(0), None, ctypes.c_uint32(0),
+                                                  ctypes.byref(nm), ctypes.byref(nc)))
+        m = np.zeros(nm.value, dtype=abi.manifold_dtype)
+        c = np.zeros(nc.value, dtype=abi.contact_dtype)
+        self._chk(self.lib.nb2_download_manifolds(self.h, abi.ptr(m), nm, abi.ptr(c), nc, ctypes.byref(nm),
+                                                  ctypes.byref(nc)))
+        if not compact:
+            return m, c
+        keep_m = m["num_contacts"] > 0
+        mm = m[keep_m].copy()
+        counts = mm["num_contacts"].astype(np.int64)
+        starts = mm["first_contact"].astype(np.int64)
+        slots = np.repeat(starts, counts) + (np.arange(int(counts.sum())) - np.repeat(np.cumsum(counts) - counts, counts))
+        mm["first_contact"] = np.cumsum(counts) - counts
+        return mm, c[slots].copy(), slots
+
     def upload_joints(self, joints):
         j = np.ascontiguousarray(joints, dtype=abi.joint_dtype)
         self.n_joints = len(j)
@@ -222,6 +270,15 @@ class Solver:
         out = np.zeros(8, dtype=np.float32)
         self._chk(self.lib.nb2_get_timers(self.h, abi.ptr(out)))
         return dict(zip(self.TIMER_NAMES, [float(x) for x in out]))
+
+    def download_schedule(self):
+        """(phase, dynamic body of side 1 or -1, of side 2 or -1) per constraint group of the last step."""
+        n = ctypes.c_uint32()
+        self._chk(self.lib.nb2_download_schedule(self.h, None, None, None, ctypes.c_uint32(0), ctypes.byref(n)))
+        ph, a, b = (np.full(n.value, -1, dtype=np.int32) for _ in range(3))
+        if n.value:
+            self._chk(self.lib.nb2_download_schedule(self.h, abi.ptr(ph), abi.ptr(a), abi.ptr(b), n, ctypes.byref(n)))
+        return ph, a, b
 
     def launch_count(self):
         v = ctypes.c_uint64()

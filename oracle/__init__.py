@@ -15,16 +15,36 @@ from nphysics_b200 import abi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def _host_stamp():
+    """The oracle is compiled with -march=native: a library built on another host (the snapshot that
+    travels to the GPU box carries the .so files) must be rebuilt, or it may hit an illegal instruction."""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        lines = [l for l in txt.splitlines() if l.startswith(("flags", "model name"))][:2]
+        return hashlib.sha1("\n".join(lines).encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force=False):
-    """Compile liboracle.so / liboracle_f64.so with the recipe in oracle/Makefile."""
+    """Compile liboracle.so / liboracle_f64.so with the recipe in oracle/Makefile (-O3 -march=native)."""
     targets = [os.path.join(_HERE, "liboracle.so"), os.path.join(_HERE, "liboracle_f64.so")]
     src = os.path.join(_HERE, "oracle.cpp")
     hdr = os.path.join(_HERE, "..", "include", "nphysics_b200.h")
-    stale = force or any(
-        (not os.path.exists(t)) or os.path.getmtime(t) < max(os.path.getmtime(src), os.path.getmtime(hdr))
-        for t in targets)
+    mk = os.path.join(_HERE, "Makefile")
+    stamp_path = os.path.join(_HERE, "liboracle.host")
+    stamp = _host_stamp()
+    try:
+        same_host = open(stamp_path).read().strip() == stamp
+    except OSError:
+        same_host = False
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(mk))
+    stale = force or not same_host or any((not os.path.exists(t)) or os.path.getmtime(t) < newest for t in targets)
     if stale:
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+        with open(stamp_path, "w") as f:
+            f.write(stamp + "\n")
     return targets
 
 

@@ -47,6 +47,31 @@ pub struct nb2_params {
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]
+pub struct nb2_contact_update {
+    pub world1: [f32; 3],
+    pub world2: [f32; 3],
+    pub normal: [f32; 3],
+    pub depth: f32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct nb2_collider {
+    pub half_extents: [f32; 3],
+    pub margin: f32,
+    pub translation_wrt_body: [f32; 3],
+    pub friction: f32,
+    pub rotation_wrt_body: [f32; 4],
+    pub restitution: f32,
+    pub body: i32,
+    pub friction_mode: u8,
+    pub restitution_mode: u8,
+    pub pad_: [u8; 2],
+    pub flags: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
 pub struct nb2_body {
     pub position: [f32; 7],
     pub velocity: [f32; 6],
@@ -201,6 +226,16 @@ extern "C" {
     pub fn nb2_get_stats(ctx: *mut nb2_context, out: *mut nb2_stats) -> i32;
     pub fn nb2_get_timers(ctx: *mut nb2_context, out8: *mut f32) -> i32;
     pub fn nb2_launch_count(ctx: *const nb2_context, out: *mut u64) -> i32;
+    pub fn nb2_update_contacts(ctx: *mut nb2_context, updates: *const nb2_contact_update, n_contacts: u32) -> i32;
+    pub fn nb2_upload_colliders(ctx: *mut nb2_context, colliders: *const nb2_collider, n_colliders: u32) -> i32;
+    pub fn nb2_detect_pairs(ctx: *mut nb2_context, linear_prediction: f32, search_radius: f32, flip_permille: u32,
+                            out_pairs: *mut u32) -> i32;
+    pub fn nb2_generate_manifolds(ctx: *mut nb2_context) -> i32;
+    pub fn nb2_download_manifolds(ctx: *mut nb2_context, out_manifolds: *mut nb2_manifold, manifold_capacity: u32,
+                                  out_contacts: *mut nb2_contact, contact_capacity: u32, out_n_manifolds: *mut u32,
+                                  out_n_contacts: *mut u32) -> i32;
+    pub fn nb2_download_schedule(ctx: *mut nb2_context, out_phase: *mut i32, out_body1: *mut i32, out_body2: *mut i32,
+                                 capacity: u32, out_n: *mut u32) -> i32;
 }
 
 #[cfg(test)]

@@ -30,6 +30,19 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def rel_err_q(a, b, floor):
+    """Per-quantity relative error (north_star: "within 1e-5 relative (f32)"): every element is compared
+    with its OWN reference value, max_i |a_i - b_i| / max(|b_i|, floor).  `floor` is the magnitude below
+    which a quantity is judged absolutely (f32 cannot hold 1e-5 relative on a value that is a rounding
+    residue of much larger operands): 1e-3 m / rad for poses, 1e-3 m/s for velocities, 1e-6 N s for
+    impulses in the tests below."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor)).max())
+
+
 class Harness:
     """Drives two solver-like objects (CUDA Solver / Oracle) over the same inputs."""
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from nphysics_b200 import abi, scenes
-from tests.conftest import rel_err
+from tests.conftest import rel_err, rel_err_q
 from tests.golden import make_golden as G
 
 pytestmark = pytest.mark.gpu
@@ -27,11 +27,16 @@ def new_oracle():
 
 
 def check_step(tag, g, o, tol=TOL):
+    """Per quantity: every pose component, velocity component and impulse against its own oracle value
+    (floors: 1 mm, 1 mm/s, 1e-6 N s), plus the whole-array norm-wise check."""
     sg, so = g.download_body_states(), o.download_body_states()
+    assert rel_err_q(sg["position"], so["position"], 1e-3) <= tol, tag
+    assert rel_err_q(sg["velocity"], so["velocity"], 1e-3) <= tol, tag
     assert rel_err(sg["position"], so["position"]) <= tol, tag
     assert rel_err(sg["velocity"], so["velocity"]) <= tol, tag
     ig, io = g.download_contact_impulses(), o.download_contact_impulses()
     assert ig.shape == io.shape
+    assert rel_err_q(ig, io, 1e-6) <= tol, tag
     assert rel_err(ig, io) <= tol, tag
 
 
@@ -108,6 +113,31 @@ def test_joint_zoo_reference_order_all_joint_types():
         assert rel_err(jg["impulses"], jo["impulses"]) <= TOL
         assert np.array_equal(jg["broken"], jo["broken"])
     lockstep(sc, None, sc.params, 10, per_step=chk)
+
+
+def test_unused_joint_rows_ignore_stale_memory(monkeypatch):
+    """Rows a joint reserves but does not emit (a prismatic joint without an active limit, its 7th row,
+    a degenerate universal joint) are streamed by the staged coloured kernel like any other row: with
+    the row planes pre-filled with NaN bits (NB2_POISON_ROWS) the step must give the very same bits."""
+    sc = scenes.joint_zoo(with_limits=False)
+    outs = []
+    for poison in ("0", "1"):
+        monkeypatch.setenv("NB2_POISON_ROWS", poison)  # read at nb2_create
+        s = new_solver()
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+        s.upload_joints(sc.joints)
+        none_m, none_c = np.zeros(0, abi.manifold_dtype), np.zeros(0, abi.contact_dtype)
+        for _ in range(5):
+            s.upload_manifolds(none_m, none_c)
+            s.step(COL)
+        st = s.get_stats()
+        assert int(st["non_finite"]) == 0
+        outs.append((s.download_body_states(), s.download_joints()))
+    assert np.array_equal(outs[0][0]["position"], outs[1][0]["position"])
+    assert np.array_equal(outs[0][0]["velocity"], outs[1][0]["velocity"])
+    assert np.array_equal(outs[0][1]["impulses"], outs[1][1]["impulses"])
+    assert np.isfinite(outs[1][0]["velocity"]).all()
 
 
 def test_joint_breaking_matches():
