@@ -6,10 +6,23 @@
 
 A "step" is one MoreauJeanSolver step (assembly + SOR-prox velocity iterations + integration +
 nonlinear SOR-prox position iterations) of BASELINE.json configs[1]: the boxes3 scene scaled to a
-settled 50x40x50 = 100 000-box pile, 10 velocity + 5 position iterations.  Metric: solver
-body-steps/s = dynamic bodies x steps / time.  With N > 1 every rank steps
-its own independent 100k-box world (weak scaling; islands/worlds never exchange data, so there is
-no data-path collective -- NCCL only gathers the per-rank timings).
+50x40x50 = 100 000-box pile, 10 velocity + 5 position iterations, on its analytic rest-pose contact
+set (input (A): 296 000 manifolds, 1 184 000 contacts, 3 552 000 rows -- the
+same work every step, on both arms).  Metric: solver body-steps/s = dynamic bodies x steps / time.
+
+  value   the contact set is resident in HBM (uploaded / produced once); K steps are timed.
+  e2e     the reference-facing call sequence with HOST buffers, every step inside the timed region: the
+          bodies' states go up from pinned host memory (the host owns the BodySet), the manifolds are
+          produced on the device from them (nb2_generate_manifolds), the step runs, the new
+          states come back.  `e2e_variants` times the two host-manifold sequences as well (full 112-byte
+          records per contact, and the 40-byte per-step refresh of nb2_update_contacts).
+  quality_vs_oracle  the timed scene, free-running from rest with a cold cache and fresh manifolds every
+          step, coloured mode against the oracle's sequential order: residual, penetration, energy.
+  sharded BASELINE configs[4]: 4096 pyramid3 worlds split over the N ranks by island
+          (sharding.make_shards on the device's island labels), stats over NCCL -- strong scaling.
+
+With N > 1 `value` is N independent 100k piles, one per GPU (a single pile is ONE island: it does not
+shard; "replicas", weak scaling, no data-path collective).
 """
 import argparse
 import json
@@ -38,25 +51,40 @@ def parse_args():
     ap.add_argument("--vel-iters", type=int, default=10)
     ap.add_argument("--pos-iters", type=int, default=5)
     ap.add_argument("--mode", default="coloured", choices=["coloured", "reference_order"])
-    ap.add_argument("--cpu-sample-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--contact-layout", type=int, default=0, help="0 = 132-byte row stream, 1 = compact 80-byte records")
+    ap.add_argument("--no-quality", action="store_true")
+    ap.add_argument("--quality-steps", type=int, default=10)
+    ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--sharded-worlds", type=int, default=4096)
+    ap.add_argument("--contact-layout", type=int, default=0, help="0 = 100-byte row stream, 1 = compact 80-byte records")
     ap.add_argument("--no-schedule-cache", action="store_true")
     ap.add_argument("--settle", type=int, default=60, help="untimed impulse-cache settling steps at the rest pose")
     return ap.parse_args()
 
 
-def build_workload(grid, vel_iters, pos_iters):
+def build_scene(grid, vel_iters, pos_iters):
     nx, ny, nz = [int(x) for x in grid.lower().split("x")]
     sc = scenes.boxes3(nx, ny, nz)
     p = abi.default_params()
     p["max_velocity_iterations"] = vel_iters
     p["max_position_iterations"] = pos_iters
     sc.params = p
-    gen = scenes.ContactGenerator(sc)
-    m, c = gen.generate()
-    return sc, m, c
+    return sc
+
+
+def workload_config(args, n_bodies, n_manifolds, n_contacts, n_r2, n_rg, world):
+    """The `config` object: identical on both arms (the driver compares them)."""
+    return {
+        "workload": "boxes3 scaled to %d boxes (%s pile at its rest pose, analytic contact set%s), %d velocity + %d "
+                    "position iterations" % (n_bodies, args.grid, ", one independent world per GPU" if world > 1 else "",
+                                              args.vel_iters, args.pos_iters),
+        "bodies": int(n_bodies), "manifolds": int(n_manifolds), "contacts": int(n_contacts),
+        "rows_two_body": int(n_r2), "rows_ground": int(n_rg),
+        "l2": "row stream %.0f MB per sweep > 126 MB L2 (inputs larger than L2, no flush needed)"
+              % ((100 * n_r2 + 84 * n_rg) / 1e6),
+    }
 
 
 def algorithmic_bytes(n_r2, n_rg, n_c, n_b, iv, ip):
@@ -64,7 +92,7 @@ def algorithmic_bytes(n_r2, n_rg, n_c, n_b, iv, ip):
     vel = iv * (132 * n_r2 + 84 * n_rg)
     pos = ip * (96 * n_c)
     asm = 128 * n_r2 + 80 * n_rg + 96 * n_c + 64 * n_c
-    return {"velocity_kernel": vel, "position_kernel": pos, "step": vel + pos + 200 * n_b + asm}
+    return {"velocity_kernel": vel, "position_kernel": pos, "assembly": asm, "step": vel + pos + 200 * n_b + asm}
 
 
 class ClockSampler:
@@ -121,7 +149,6 @@ class ClockSampler:
 
     def start(self):
         if self.handle is not None:
-            import threading
             self.stop_flag = threading.Event()
             self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
@@ -177,8 +204,12 @@ class ClockSampler:
         return out
 
 
+# ----------------------------------------------------------------------------------------------
+# CPU side: the oracle (the one place outside tests/ and smoke() that may execute oracle/)
+# ----------------------------------------------------------------------------------------------
 def cpu_reference_run(sc, m, c, steps, warmup):
-    """Times the CPU oracle (single thread: the reference has no threads)."""
+    """Times the CPU oracle on the same resident contact set (single thread: the reference has no
+    threads).  Returns (seconds for `steps` steps, stats)."""
     from oracle import Oracle
     o = Oracle()
     o.set_params(sc.params)
@@ -196,26 +227,26 @@ def cpu_reference_run(sc, m, c, steps, warmup):
 
 
 def _reference_worker(grid, vel_iters, pos_iters, steps, warmup, q):
-    sc, m, c = build_workload(grid, vel_iters, pos_iters)
+    sc = build_scene(grid, vel_iters, pos_iters)
+    m, c = scenes.ContactGenerator(sc).generate()
     dt, st = cpu_reference_run(sc, m, c, steps, warmup)
-    q.put((dt, sc.n_dynamic, len(c), int(st["n_rows_two_body"]) + int(st["n_rows_ground"])))
+    q.put((dt, sc.n_dynamic, len(m), len(c), int(st["n_rows_two_body"]), int(st["n_rows_ground"])))
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the CPU implementation of the path on the host cores.  The reference is
+    """Reference arm: the CPU implementation of the path on the host cores, on the SAME configuration as
+    the CUDA arm (the full pile, the same contact set, the same iteration counts).  The reference is
     single-threaded by construction (no threads/rayon/SIMD in src/, one global island:
     src/world/mechanical_world.rs:263), so one world = one thread; with --gpus N the arm steps N
     independent worlds on N cores, mirroring the weak-scaling workload of the CUDA arm."""
     if rank != 0:
         return
-    # bounded sample of the same workload: a 20x40x20 sub-pile (same depth, same row mix per body)
-    sample_grid = "20x40x20" if args.grid == "50x40x50" else args.grid
     n_worlds = max(1, args.gpus)
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_reference_worker,
-                         args=(sample_grid, args.vel_iters, args.pos_iters, args.steps, args.warmup, q))
+                         args=(args.grid, args.vel_iters, args.pos_iters, args.steps, args.warmup, q))
              for _ in range(n_worlds)]
     for p in procs:
         p.start()
@@ -223,25 +254,67 @@ def run_reference(args, rank, world):
     for p in procs:
         p.join()
     dt = max(r[0] for r in res)
-    nb, nc, rows = res[0][1], res[0][2], res[0][3]
+    nb, nm, nc, n_r2, n_rg = res[0][1:]
     value = n_worlds * nb * args.steps / dt
     line = {
         "impl": "reference", "metric": "solver body-steps/sec", "value": value, "unit": "body-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "boxes3 scaled to 100k boxes (50x40x50 settled pile%s), %d velocity + %d position "
-                               "iterations" % (", one independent world per GPU" if n_worlds > 1 else "",
-                                               args.vel_iters, args.pos_iters),
-                   "reference_sample": "%s sub-pile (%d boxes, %d contacts) per step and world" % (sample_grid, nb, nc)},
+        "config": workload_config(args, nb, nm, nc, n_r2, n_rg, n_worlds),
         "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": n_worlds, "kind": "port",
-                         "sample": "%d steps of a %s settled sub-pile (%d boxes) through oracle/liboracle.so, "
-                                   "%d independent single-thread world(s)" % (args.steps, sample_grid, nb, n_worlds)},
+                         "sample": "%d timed steps (after %d warm-up steps) of the full %s pile (%d boxes, %d contacts) "
+                                   "through oracle/liboracle.so (-O3 -march=native), %d independent single-thread world(s); "
+                                   "host has %d cores" % (args.steps, args.warmup, args.grid, nb, nc, n_worlds,
+                                                          os.cpu_count() or 0)},
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "rows_per_step": rows,
+        "rows_per_step": n_r2 + n_rg,
     }
     print(json.dumps(line), flush=True)
 
 
+def quality_vs_oracle(args, sc, device):
+    """The timed scene as a free-running simulation: `quality_steps` steps from the rest pose with a cold
+    impulse cache and manifolds regenerated from the current poses every step -- coloured mode on the GPU
+    (device producer) against the oracle's sequential order (host producer, same canonical pair order)."""
+    from nphysics_b200.solver import Solver
+    from oracle import Oracle
+    n = args.quality_steps
+    g = Solver(device)
+    g.set_params(sc.params)
+    g.upload_bodies(sc.bodies)
+    g.upload_colliders(scenes.scene_colliders(sc))
+    g.detect_pairs(scenes.LINEAR_PREDICTION)
+    for _ in range(n):
+        g.generate_manifolds()
+        g.step(abi.MODE_COLOURED)
+    sg = g.get_stats()
+    g.close()
+    gen = scenes.ContactGenerator(sc, order="owner")
+    o = Oracle()
+    o.set_params(sc.params)
+    o.upload_bodies(sc.bodies)
+    for _ in range(n):
+        m, c = gen.generate(o.download_body_states()["position"])
+        o.upload_manifolds(m, c)
+        o.step()
+    so = o.get_stats()
+    o.close()
+
+    def rec(st):
+        return {"residual_max": float(st["residual_max"]), "max_penetration": float(st["max_penetration"]),
+                "kinetic_energy": float(st["kinetic_energy"])}
+
+    a, b = rec(sg), rec(so)
+    return {"protocol": "%d free-running steps from the rest pose, cold impulse cache, manifolds regenerated every step; "
+                        "stats of the last step" % n,
+            "coloured_gpu": a, "oracle_sequential": b,
+            "ratio": {k: (a[k] / b[k] if b[k] else None) for k in a},
+            "stated_tolerance": {"residual_max": 3.0, "max_penetration": "1.5x + 1 mm", "kinetic_energy": 4.0}}
+
+
+# ----------------------------------------------------------------------------------------------
+# CUDA arm
+# ----------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
     import torch
     from nphysics_b200.solver import Solver
@@ -255,9 +328,8 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    sc, m, c = build_workload(args.grid, args.vel_iters, args.pos_iters)
+    sc = build_scene(args.grid, args.vel_iters, args.pos_iters)
     nb = sc.n_dynamic
-    n_r2, n_rg = scenes.row_counts(sc, m)
     stream = torch.cuda.Stream(device=dev)
 
     def barrier():
@@ -271,10 +343,12 @@ def run_b200(args, rank, world, local_rank):
         solver.set_contact_layout(args.contact_layout)
         solver.set_schedule_cache(not args.no_schedule_cache)
         solver.upload_bodies(sc.bodies)
-        solver.upload_manifolds(m, c)
+        # the contact set (SURVEY 8d config 2 input (A)) is produced on the device, once, at the rest pose
+        solver.upload_colliders(scenes.scene_colliders(sc))
+        n_pairs = solver.detect_pairs(scenes.LINEAR_PREDICTION)
+        solver.generate_manifolds()
         # settle the warm-start cache ("settled scene, warm impulse cache"): the pile
-        # is held at its rest pose while the cached impulses converge, so that the timed steps run on a
-        # supported pile instead of a cold one sinking under zero impulses
+        # is held at its rest pose while the cached impulses converge
         rest = np.zeros(len(sc.bodies), dtype=abi.body_state_dtype)
         rest["position"] = sc.bodies["position"]
         rest["velocity"] = sc.bodies["velocity"]
@@ -314,40 +388,113 @@ def run_b200(args, rank, world, local_rank):
         solver.enable_timers(False)
         timers = {k: v / n_t for k, v in acc.items()}
         stats = solver.get_stats()
+        n_r2, n_rg = int(stats["n_rows_two_body"]), int(stats["n_rows_ground"])
+        m_dev, c_dev, _ = solver.download_manifolds(compact=True)
+        n_m, n_c = len(m_dev), len(c_dev)
+
+        # ---------------- the same K steps with a fresh colouring every step (the contact graph of a live
+        # scene changes; the headline runs on an unchanged graph whose schedule is cached)
+        uncached_ms = None
+        if mode == abi.MODE_COLOURED and not args.no_schedule_cache:
+            solver.set_schedule_cache(False)
+            for _ in range(3):
+                solver.step(mode)
+            barrier()
+            u0 = torch.cuda.Event(enable_timing=True)
+            u1 = torch.cuda.Event(enable_timing=True)
+            u0.record(stream)
+            for _ in range(args.steps):
+                solver.step(mode)
+            u1.record(stream)
+            barrier()
+            uncached_ms = u0.elapsed_time(u1) / args.steps
+            solver.set_schedule_cache(True)
+            for _ in range(14):  # back to the refined cached schedule
+                solver.step(mode)
 
         # ---------------- end to end through the C ABI with host buffers
         e2e = None
+        variants = {}
         if not args.no_e2e:
-            pm = torch.empty(max(m.nbytes, 1), dtype=torch.uint8, pin_memory=True)
-            pc = torch.empty(max(c.nbytes, 1), dtype=torch.uint8, pin_memory=True)
-            ps = torch.empty(solver.n_bodies * abi.body_state_dtype.itemsize, dtype=torch.uint8, pin_memory=True)
-            pm.numpy()[:m.nbytes] = m.view(np.uint8).reshape(-1)
-            pc.numpy()[:c.nbytes] = c.view(np.uint8).reshape(-1)
-            for _ in range(2):
-                solver.upload_manifolds_raw(pm.data_ptr(), len(m), pc.data_ptr(), len(c))
-                solver.step(mode)
-                solver.download_body_states_raw(ps.data_ptr(), 0, solver.n_bodies)
-            barrier()
-            t0 = time.perf_counter()
-            g0 = torch.cuda.Event(enable_timing=True)
-            g1 = torch.cuda.Event(enable_timing=True)
-            g0.record(stream)
-            for _ in range(args.steps):
-                solver.upload_manifolds_raw(pm.data_ptr(), len(m), pc.data_ptr(), len(c))
-                solver.step(mode)
-                solver.download_body_states_raw(ps.data_ptr(), 0, solver.n_bodies)
-            g1.record(stream)
-            barrier()
-            e2e_ms = max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0))
-            e2e = {"ms": e2e_ms, "h2d": int(m.nbytes + c.nbytes), "d2h": int(solver.n_bodies * 52)}
+            nbod = solver.n_bodies
+            ssz = abi.body_state_dtype.itemsize
+            ps_up = torch.empty(nbod * ssz, dtype=torch.uint8, pin_memory=True)
+            ps_dn = torch.empty(nbod * ssz, dtype=torch.uint8, pin_memory=True)
+            ps_up.numpy()[:] = rest.view(np.uint8).reshape(-1)
+            lib, h = solver.lib, solver.h
+            import ctypes
+            up_ptr, dn_ptr = ctypes.c_void_p(ps_up.data_ptr()), ctypes.c_void_p(ps_dn.data_ptr())
+            c_nb, c_0 = ctypes.c_uint32(nbod), ctypes.c_uint32(0)
+
+            def timed(fn, reps):
+                for _ in range(2):
+                    fn()
+                barrier()
+                t0 = time.perf_counter()
+                g0 = torch.cuda.Event(enable_timing=True)
+                g1 = torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+                for _ in range(reps):
+                    fn()
+                g1.record(stream)
+                barrier()
+                return max(g0.elapsed_time(g1), 1e3 * (time.perf_counter() - t0)) / reps
+
+            def step_device_producer():
+                # host BodySet -> device, contacts produced on the device, step, BodySet back to the host
+                solver._chk(lib.nb2_upload_body_states(h, up_ptr, c_0, c_nb))
+                solver._chk(lib.nb2_generate_manifolds(h))
+                solver._chk(lib.nb2_step(h, mode))
+                solver._chk(lib.nb2_download_body_states(h, dn_ptr, c_0, c_nb))
+
+            e2e_ms = timed(step_device_producer, args.steps)
+            e2e = {"ms": e2e_ms, "h2d": int(nbod * ssz), "d2h": int(nbod * ssz)}
+
+            # host-side narrow phase instead (ncollide on the CPU): the contact set travels every step
+            pm = torch.empty(max(m_dev.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            pc = torch.empty(max(c_dev.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            upd = abi.contact_updates_of(c_dev)
+            pu = torch.empty(max(upd.nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            pm.numpy()[:m_dev.nbytes] = m_dev.view(np.uint8).reshape(-1)
+            pc.numpy()[:c_dev.nbytes] = c_dev.view(np.uint8).reshape(-1)
+            pu.numpy()[:upd.nbytes] = upd.view(np.uint8).reshape(-1)
+
+            def step_full_upload():
+                solver.upload_manifolds_raw(pm.data_ptr(), n_m, pc.data_ptr(), n_c)
+                solver._chk(lib.nb2_step(h, mode))
+                solver._chk(lib.nb2_download_body_states(h, dn_ptr, c_0, c_nb))
+
+            def step_incremental():
+                solver.update_contacts_raw(pu.data_ptr(), n_c)
+                solver._chk(lib.nb2_step(h, mode))
+                solver._chk(lib.nb2_download_body_states(h, dn_ptr, c_0, c_nb))
+
+            reps = min(args.steps, 20)
+            full_ms = timed(step_full_upload, reps)
+            incr_ms = timed(step_incremental, reps)
+            variants = {
+                "host_manifolds_full_upload": {"ms_per_step": full_ms, "h2d_bytes_per_step": int(m_dev.nbytes + c_dev.nbytes),
+                                               "d2h_bytes_per_step": int(nbod * ssz)},
+                "host_manifolds_per_step_refresh": {"ms_per_step": incr_ms, "h2d_bytes_per_step": int(upd.nbytes),
+                                                    "d2h_bytes_per_step": int(nbod * ssz)},
+            }
 
     # max over ranks
     if dist is not None:
-        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, uncached_ms or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
         if e2e:
             e2e["ms"] = float(t[1])
+        if uncached_ms is not None:
+            uncached_ms = float(t[2])
+
+    sharded = None
+    if not args.no_sharded and args.mode == "coloured":
+        solver.close()
+        solver = None
+        from tools.sharded_worlds import run_sharded_worlds
+        sharded = run_sharded_worlds(args.sharded_worlds, rank, world, local_rank, dist, steps=min(args.steps, 10))
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -357,58 +504,69 @@ def run_b200(args, rank, world, local_rank):
         else:
             peak = 6650.0
             peak_src = "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-        ab = algorithmic_bytes(n_r2, n_rg, len(c), nb, args.vel_iters, args.pos_iters)
+        ab = algorithmic_bytes(n_r2, n_rg, n_c, nb, args.vel_iters, args.pos_iters)
         vk_ms = timers.get("velocity_kernel", 0.0)
         achieved = ab["velocity_kernel"] / (vk_ms * 1e-3) / 1e9 if vk_ms > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "velocity_kernel_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = tj.get("source")
             except Exception:
                 traffic = None
         value = world * nb * args.steps / (ms * 1e-3)
+        pk_ms = timers.get("position_kernel", 0.0)
         line = {
             "metric": "solver body-steps/sec", "value": value, "unit": "body-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "boxes3 scaled to 100k boxes (%s settled pile%s), %d velocity + %d position "
-                                   "iterations, mode=%s, contact_layout=%d, schedule_cache=%s" %
-                                   (args.grid, ", one independent world per GPU" if world > 1 else "", args.vel_iters,
-                                    args.pos_iters, args.mode, args.contact_layout, not args.no_schedule_cache),
-                       "bodies": nb, "manifolds": int(len(m)), "contacts": int(len(c)), "rows_two_body": n_r2,
-                       "rows_ground": n_rg,
-                       "l2": "row stream %.0f MB per sweep > 126 MB L2 (inputs larger than L2, no flush needed)" %
-                             ((100 * n_r2 + 84 * n_rg) / 1e6)},
+            "config": workload_config(args, nb, n_m, n_c, n_r2, n_rg, world),
+            "b200": {"mode": args.mode, "contact_layout": args.contact_layout, "schedule_cache": not args.no_schedule_cache,
+                     "contact_set": "produced on the device (nb2_detect_pairs + nb2_generate_manifolds), %d pairs" % n_pairs},
             "constraint_rows_per_sec": world * (n_r2 + n_rg) * args.vel_iters /
                                        (timers.get("velocity_resolution", 0.0) * 1e-3) if timers.get("velocity_resolution") else None,
-            "roofline": {"bound": "hbm", "kernel": "k_velocity_solve_staged" if args.mode == "coloured" else "k_velocity_solve", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_velocity_solve_staged" if args.mode == "coloured" else "k_velocity_solve",
+                         "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": ab["velocity_kernel"], "kernel_ms": vk_ms,
                          "peak_source": peak_src,
                          "step_algorithmic_bytes": ab["step"],
-                         "step_frac": ab["step"] / (ms / args.steps * 1e-3) / 1e9 / peak},
+                         "step_frac": ab["step"] / (ms / args.steps * 1e-3) / 1e9 / peak,
+                         "position_kernel": {"algorithmic_bytes_per_launch": ab["position_kernel"], "kernel_ms": pk_ms,
+                                             "frac": ab["position_kernel"] / (pk_ms * 1e-3) / 1e9 / peak if pk_ms > 0 else None}},
             "stage_ms": timers,
+            "uncached_ms_per_step": uncached_ms,
             "phases": {"velocity": int(stats["n_phases_velocity"]), "position": int(stats["n_phases_position"])},
             "residual_max": float(stats["residual_max"]), "max_penetration": float(stats["max_penetration"]),
             "kinetic_energy": float(stats["kinetic_energy"]), "settle_steps": args.settle,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if e2e:
-            line["e2e"] = {"value": world * nb * args.steps / (e2e["ms"] * 1e-3), "unit": "body-steps/s",
+            line["e2e"] = {"value": world * nb / (e2e["ms"] * 1e-3), "unit": "body-steps/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "ms_per_step": e2e["ms"] / args.steps}
+                           "ms_per_step": e2e["ms"],
+                           "sequence": "nb2_upload_body_states (pinned host) -> nb2_generate_manifolds -> nb2_step -> "
+                                       "nb2_download_body_states (pinned host)"}
+            line["e2e_variants"] = variants
+        if sharded is not None:
+            line["sharded"] = sharded
+        if world == 1 and not args.no_quality and args.mode == "coloured":
+            line["quality_vs_oracle"] = quality_vs_oracle(args, sc, local_rank)
         if world == 1 and not args.no_cpu_baseline:
-            sgrid = "20x40x20" if args.grid == "50x40x50" else args.grid
-            scs, ms_, cs_ = build_workload(sgrid, args.vel_iters, args.pos_iters)
-            dt, _ = cpu_reference_run(scs, ms_, cs_, args.cpu_sample_steps, 1)
-            line["cpu_baseline"] = {"value": scs.n_dynamic * args.cpu_sample_steps / dt, "unit": "body-steps/s",
+            mh, ch = scenes.ContactGenerator(sc).generate()
+            dt, _ = cpu_reference_run(sc, mh, ch, args.cpu_sample_steps, 1)
+            line["cpu_baseline"] = {"value": sc.n_dynamic * args.cpu_sample_steps / dt, "unit": "body-steps/s",
                                     "cores": 1, "kind": "port",
-                                    "sample": "%d steps of a %s settled sub-pile (%d boxes) through "
-                                              "oracle/liboracle.so, single thread (the reference is single-threaded)"
-                                              % (args.cpu_sample_steps, sgrid, scs.n_dynamic)}
+                                    "sample": "%d steps (after 1 warm-up step) of the full %s pile (%d boxes, %d contacts) "
+                                              "through oracle/liboracle.so (-O3 -march=native), single thread (the reference "
+                                              "is single-threaded); host has %d cores"
+                                              % (args.cpu_sample_steps, args.grid, sc.n_dynamic, len(ch), os.cpu_count() or 0)}
         print(json.dumps(line), flush=True)
-    solver.close()
+    if solver is not None:
+        solver.close()
     if dist is not None:
         dist.destroy_process_group()
 

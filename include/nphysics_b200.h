@@ -260,7 +260,8 @@ typedef struct nb2_stats {
     uint32_t n_phases_position;
     uint32_t n_broken_joints;
     uint32_t non_finite;      /* count of NaN/Inf body states seen */
-    uint32_t pad_;
+    uint32_t schedule_verdict; /* coloured mode, last step: 0 cached schedule reused, 1 coloured from scratch,
+                                * 2 cached + one refinement pass, 3 edited in place (a few groups changed) */
     float residual_max;       /* max |lambda - prox(lambda - r*(J dv + rhs))| over velocity rows */
     float residual_rms;
     float max_penetration;    /* max contact depth (incl. margins) at the final poses */
@@ -321,7 +322,8 @@ int nb2_set_contact_layout(nb2_context* ctx, int layout);
 /* Replace the whole body set (n >= 1).  Marks dynamics dirty, like
  * update_status = all() on a fresh body (rigid_body.rs:80). */
 int nb2_upload_bodies(nb2_context* ctx, const nb2_body* bodies, uint32_t n);
-/* Overwrite pose+velocity of bodies [first, first+n). */
+/* Overwrite pose+velocity of bodies [first, first+n).  Asynchronous on the context's stream, like
+ * nb2_upload_manifolds: a pinned host array must stay valid until the next nb2_synchronize / download. */
 int nb2_upload_body_states(nb2_context* ctx, const nb2_body_state* states, uint32_t first, uint32_t n);
 /* The contact set for the next step ("uploaded once per step"). */
 int nb2_upload_manifolds(nb2_context* ctx, const nb2_manifold* manifolds, uint32_t n_manifolds,
@@ -378,6 +380,15 @@ int nb2_upload_activation(nb2_context* ctx, const nb2_activation* activation, ui
  * active_bodies and of the manifold list (mechanical_world.rs:287-300).  Asynchronous. */
 int nb2_update_activation(nb2_context* ctx, float mix_factor, const int32_t* to_activate, uint32_t n_to_activate);
 int nb2_download_activation(nb2_context* ctx, nb2_activation* out, uint32_t n);
+
+/* Island labelling for sharding (the union-find of
+ * src/detection/activation_manager.rs:122-159 restricted to dynamic bodies, :141-145): out_labels[i] =
+ * the smallest body index of body i's connected component over the current manifolds (with or without
+ * contacts: potential pairs keep their bodies together) and unbroken joints, -1 for a non-dynamic body;
+ * out_rows[i] (may be NULL) = velocity rows of the constraint groups booked on body i (a group is booked
+ * on its first dynamic body), i.e. the weights a host bin-packs islands onto GPUs with.  n must equal
+ * the body count.  Synchronises. */
+int nb2_label_islands(nb2_context* ctx, int32_t* out_labels, uint32_t* out_rows, uint32_t n);
 
 /* One MoreauJeanSolver::step on the uploaded inputs, followed by the
  * kinematic-body integration and end-of-step dynamics refresh of

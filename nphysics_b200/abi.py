@@ -72,7 +72,7 @@ joint_dtype = np.dtype([
 stats_dtype = np.dtype([
     ("n_bodies", u4), ("n_dynamic_bodies", u4), ("n_manifolds", u4), ("n_contacts", u4), ("n_joints", u4),
     ("n_rows_two_body", u4), ("n_rows_ground", u4), ("n_phases_velocity", u4), ("n_phases_position", u4),
-    ("n_broken_joints", u4), ("non_finite", u4), ("pad_", u4), ("residual_max", f4), ("residual_rms", f4),
+    ("n_broken_joints", u4), ("non_finite", u4), ("schedule_verdict", u4), ("residual_max", f4), ("residual_rms", f4),
     ("max_penetration", f4), ("kinetic_energy", f4), ("t_assembly_ms", f4),
     ("t_velocity_resolution_ms", f4), ("t_velocity_update_ms", f4), ("t_position_resolution_ms", f4),
     ("t_step_ms", f4), ("pad2_", f4)], align=True)

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(TPB) k_act_islands(unsigned int nb, unsigned i
                                                      const nb2_manifold* __restrict__ manifolds,
                                                      const nb2_joint* __restrict__ joints,
                                                      const int* __restrict__ true_status, unsigned int* parent,
-                                                     unsigned int* flags /*3*/, unsigned int* barrier) {
+                                                     unsigned int* flags /*3*/, unsigned int* barrier, int dynamic_only) {
     GridBarrier gb;
     gb.init(barrier);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(TPB) k_act_islands(unsigned int nb, unsigned i
             int b1, b2;
             if (e < nm) {
                 const nb2_manifold& m = manifolds[e];
-                if (m.num_contacts == 0) continue;
+                if (m.num_contacts == 0 && !dynamic_only) continue;  // sharding keeps potential pairs together
                 b1 = m.body1;
                 b2 = m.body2;
             } else {
@@ -78,7 +78,9 @@ __global__ void __launch_bounds__(TPB) k_act_islands(unsigned int nb, unsigned i
                 b2 = j.body2;
             }
             if ((unsigned int)b1 >= nb || (unsigned int)b2 >= nb) continue;  // bad records are reported by the step
-            if (!act_eligible(true_status[b1]) || !act_eligible(true_status[b2])) continue;
+            if (dynamic_only ? (true_status[b1] != NB2_BODY_DYNAMIC || true_status[b2] != NB2_BODY_DYNAMIC)
+                             : (!act_eligible(true_status[b1]) || !act_eligible(true_status[b2])))
+                continue;
             // hook the larger root under the smaller
             unsigned int r1 = __ldcg(&parent[b1]), r2 = __ldcg(&parent[b2]);
             while (r1 != r2) {
@@ -152,6 +154,65 @@ int launch_apply_effective_status(Context* ctx) {
     return NB2_OK;
 }
 
+static int launch_islands(Context* ctx, int dynamic_only);
+
+// nb2_label_islands: the sharding view of the same labelling -- connected components over the
+// DYNAMIC bodies only (static and kinematic bodies are replicated into every shard, so they must not glue
+// islands together: activation_manager.rs:141-145), plus the velocity rows each body owns (a group's rows
+// are booked on its first dynamic body), from which the host bin-packs islands onto ranks.
+__global__ void k_island_init(unsigned int n, unsigned int* parent, unsigned int* rows) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    parent[i] = i;
+    rows[i] = 0u;
+}
+__global__ void k_island_rows(unsigned int nb, unsigned int nm, unsigned int nj, const nb2_manifold* __restrict__ manifolds,
+                              const nb2_joint* __restrict__ joints, const int* __restrict__ true_status, unsigned int* rows) {
+    unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nm + nj) return;
+    int b1, b2;
+    unsigned int r;
+    if (e < nm) {
+        b1 = manifolds[e].body1;
+        b2 = manifolds[e].body2;
+        r = 3u * manifolds[e].num_contacts;
+    } else {
+        const nb2_joint& j = joints[e - nm];
+        if (j.broken) return;
+        const unsigned int per_type[NB2_JOINT_TYPE_COUNT] = {3, 5, 5, 4, 3, 4, 4, 4, 6, 3};
+        b1 = j.body1;
+        b2 = j.body2;
+        r = j.type < NB2_JOINT_TYPE_COUNT ? per_type[j.type] : 0u;
+    }
+    if ((unsigned int)b1 >= nb || (unsigned int)b2 >= nb || r == 0u) return;
+    const int owner = true_status[b1] == NB2_BODY_DYNAMIC ? b1 : (true_status[b2] == NB2_BODY_DYNAMIC ? b2 : -1);
+    if (owner >= 0) atomicAdd(&rows[owner], r);
+}
+__global__ void k_island_labels(unsigned int n, const int* __restrict__ true_status, const unsigned int* __restrict__ parent,
+                                int* labels) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    labels[i] = true_status[i] == NB2_BODY_DYNAMIC ? (int)parent[i] : -1;
+}
+
+int launch_label_islands(Context* ctx, int* d_labels, unsigned int* d_rows) {
+    const unsigned int nb = ctx->n_bodies;
+    NB2_TRY(ctx->cc_parent.reserve(ctx, (size_t)nb + 1));
+    k_island_init<<<nblk(nb), TPB, 0, ctx->stream>>>(nb, ctx->cc_parent.p, d_rows);
+    ctx->launches++;
+    const unsigned int ne = ctx->n_manifolds + ctx->n_joints;
+    if (ne) {
+        NB2_TRY(launch_islands(ctx, 1));
+        k_island_rows<<<nblk(ne), TPB, 0, ctx->stream>>>(nb, ctx->n_manifolds, ctx->n_joints, ctx->manifolds.p, ctx->joints.p,
+                                                        ctx->true_status.p, d_rows);
+        ctx->launches++;
+    }
+    k_island_labels<<<nblk(nb), TPB, 0, ctx->stream>>>(nb, ctx->true_status.p, ctx->cc_parent.p, d_labels);
+    ctx->launches++;
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
 int launch_update_activation(Context* ctx, float mix, const int32_t* to_activate, uint32_t n_list) {
     const unsigned int nb = ctx->n_bodies;
     NB2_TRY(ctx->cc_parent.reserve(ctx, (size_t)nb + 1));
@@ -167,7 +228,20 @@ int launch_update_activation(Context* ctx, float mix, const int32_t* to_activate
         k_act_wake<<<nblk(n_list), TPB, 0, ctx->stream>>>(n_list, ctx->wake_list.p, nb, ctx->act.p);
         ctx->launches++;
     }
-    if (ctx->n_manifolds + ctx->n_joints) {
+    if (ctx->n_manifolds + ctx->n_joints) NB2_TRY(launch_islands(ctx, 0));
+    k_act_verdict<<<nblk(nb), TPB, 0, ctx->stream>>>(nb, ctx->true_status.p, ctx->act.p, ctx->cc_parent.p, ctx->cc_can.p);
+    k_act_apply<<<nblk(nb), TPB, 0, ctx->stream>>>(nb, ctx->true_status.p, ctx->act.p, ctx->cc_parent.p, ctx->cc_can.p,
+                                                   ctx->vel.p, ctx->raw.p, ctx->b_status.p, 1);
+    ctx->launches += 2;
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
+
+// the cooperative labelling kernel over the uploaded / produced manifolds and the joints
+static int launch_islands(Context* ctx, int dynamic_only) {
+    const unsigned int nb = ctx->n_bodies;
+    {
         NB2_TRY(ctx->barrier.reserve(ctx, 8));
         NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
         int& blocks_cc = ctx->coop_blocks_islands;
@@ -188,15 +262,10 @@ int launch_update_activation(Context* ctx, float mix, const int32_t* to_activate
         unsigned int* parent = ctx->cc_parent.p;
         unsigned int* flags = ctx->barrier.p + 4;
         unsigned int* bar = ctx->barrier.p;
-        void* args[] = {&nb_, &nm, &nj, &mf, &jt, &ts, &parent, &flags, &bar};
+        void* args[] = {&nb_, &nm, &nj, &mf, &jt, &ts, &parent, &flags, &bar, &dynamic_only};
         NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_act_islands, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
         ctx->launches++;
     }
-    k_act_verdict<<<nblk(nb), TPB, 0, ctx->stream>>>(nb, ctx->true_status.p, ctx->act.p, ctx->cc_parent.p, ctx->cc_can.p);
-    k_act_apply<<<nblk(nb), TPB, 0, ctx->stream>>>(nb, ctx->true_status.p, ctx->act.p, ctx->cc_parent.p, ctx->cc_can.p,
-                                                   ctx->vel.p, ctx->raw.p, ctx->b_status.p, 1);
-    ctx->launches += 2;
-    NB2_CUDA(ctx, cudaGetLastError());
     return NB2_OK;
 }
 

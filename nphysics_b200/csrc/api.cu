@@ -45,8 +45,8 @@ static void release_all(Context* c) {
     c->adj_p.release(); c->cmask.release(); c->best.release(); c->scan_tmp.release(); c->barrier.release();
     c->r_jac.release(); c->r_hdr.release(); c->r_imp.release(); c->p_row.release();
     c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
-    c->c_geo.release(); c->bal.release(); c->p_hdr.release();
-    c->true_status.release(); c->act.release(); c->cc_parent.release(); c->cc_can.release(); c->wake_list.release();
+    c->c_geo.release(); c->bal.release(); c->p_hdr.release(); c->pos_gstamp.release(); c->pos_moved.release();
+    c->true_status.release(); c->isl_labels.release(); c->act.release(); c->cc_parent.release(); c->cc_can.release(); c->wake_list.release();
     c->colliders.release(); c->coll_world.release(); c->np_is_big.release(); c->np_big_off.release(); c->np_par.release();
     c->pair_cnt.release(); c->pair_off.release(); c->grid_count.release(); c->grid_off.release(); c->grid_cursor.release();
     c->np_big_list.release(); c->grid_entries.release(); c->pair_feat.release(); c->pair_q.release();
@@ -57,9 +57,9 @@ static void release_all(Context* c) {
 
 static int check_flags(Context* ctx) {
     // input-validation bits + schedule overflow, read after a synchronisation point
-    unsigned int f = 0;
+    unsigned int f = 0, fl[4] = {0, 0, 0, 0};
     if (ctx->flags.p) {
-        NB2_CUDA(ctx, cudaMemcpyAsync(&f, ctx->flags.p, sizeof(f), cudaMemcpyDeviceToHost, ctx->stream));
+        NB2_CUDA(ctx, cudaMemcpyAsync(fl, ctx->flags.p, sizeof(fl), cudaMemcpyDeviceToHost, ctx->stream));
     }
     SchedHeader hv, hp;
     memset(&hv, 0, sizeof(hv));
@@ -69,6 +69,8 @@ static int check_flags(Context* ctx) {
     if (ctx->stepped && ctx->last_mode == NB2_MODE_REFERENCE_ORDER && ctx->ps.hdr.p)
         NB2_CUDA(ctx, cudaMemcpyAsync(&hp, ctx->ps.hdr.p, sizeof(hp), cudaMemcpyDeviceToHost, ctx->stream));
     NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    f = fl[0];
+    ctx->last_stats.schedule_verdict = ctx->last_mode == NB2_MODE_COLOURED ? (fl[1] > 3u ? 1u : fl[1]) : 0u;
     ctx->last_stats.n_phases_velocity = hv.n_phases;
     ctx->last_stats.n_phases_position = ctx->last_mode == NB2_MODE_REFERENCE_ORDER ? hp.n_phases : hv.n_phases;
     if (f & 1u) return set_error(ctx, NB2_ERR_BAD_INDEX, "a manifold/joint record referenced a body or contact out of range");
@@ -271,6 +273,8 @@ int nb2_create(int device, void* stream, nb2_context** out) {
     // developer knob for A/B measurements of the coloured velocity kernel variants (solver.cuh)
     if (const char* vk = getenv("NB2_VELOCITY_KERNEL")) ctx->velocity_kernel = atoi(vk);
     if (const char* pr = getenv("NB2_POISON_ROWS")) ctx->poison_rows = atoi(pr) != 0;
+    if (const char* ps = getenv("NB2_POS_SKIP")) ctx->pos_skip = atoi(ps) != 0;
+    if (const char* ic = getenv("NB2_INCREMENTAL_COLOURING")) ctx->incremental_colouring = atoi(ic) != 0;
     if (cudaSetDevice(device) != cudaSuccess) {
         delete h;
         return set_error(nullptr, NB2_ERR_CUDA, "cudaSetDevice failed");
@@ -393,12 +397,13 @@ int nb2_upload_body_states(nb2_context* h, const nb2_body_state* states, uint32_
     if ((uint64_t)first + n > ctx->n_bodies) return set_error(ctx, NB2_ERR_BAD_INDEX, "body range out of bounds");
     if (!n) return NB2_OK;
     NB2_CUDA(ctx, cudaSetDevice(ctx->device));
-    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((size_t)n > ctx->stage_states.cap) NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // about to reallocate
     NB2_TRY(ctx->stage_states.reserve(ctx, n));
     NB2_CUDA(ctx, cudaMemcpyAsync(ctx->stage_states.p, states, (size_t)n * sizeof(nb2_body_state),
                                   cudaMemcpyHostToDevice, ctx->stream));
     NB2_TRY(launch_unpack_states(ctx, ctx->stage_states.p, first, n));
-    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // asynchronous on the context's stream (pageable memory is staged by the runtime before the call returns;
+    // a pinned array must stay valid until the next nb2_synchronize / download, like nb2_upload_manifolds')
     return NB2_OK;
 }
 
@@ -415,6 +420,7 @@ int nb2_upload_manifolds(nb2_context* h, const nb2_manifold* manifolds, uint32_t
     NB2_TRY(ctx->contacts.reserve(ctx, nc));
     ctx->n_manifolds = nm;
     ctx->n_contacts = nc;
+    ctx->manifolds_from_producer = false;
     if (nm)
         NB2_CUDA(ctx, cudaMemcpyAsync(ctx->manifolds.p, manifolds, (size_t)nm * sizeof(nb2_manifold),
                                       cudaMemcpyHostToDevice, ctx->stream));
@@ -558,6 +564,23 @@ int nb2_download_activation(nb2_context* h, nb2_activation* out, uint32_t n) {
     if (!n) return NB2_OK;
     NB2_CUDA(ctx, cudaSetDevice(ctx->device));
     NB2_CUDA(ctx, cudaMemcpyAsync(out, ctx->act.p, (size_t)n * sizeof(nb2_activation), cudaMemcpyDeviceToHost, ctx->stream));
+    NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB2_OK;
+}
+
+int nb2_label_islands(nb2_context* h, int32_t* out_labels, uint32_t* out_rows, uint32_t n) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (!ctx->n_bodies) return set_error(ctx, NB2_ERR_NOT_READY, "upload bodies first");
+    if (n != ctx->n_bodies || !out_labels)
+        return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "island labels: expected room for %u bodies, got %u", ctx->n_bodies, n);
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB2_TRY(ctx->isl_labels.reserve(ctx, n));
+    NB2_TRY(ctx->cc_can.reserve(ctx, (size_t)n + 1));
+    NB2_TRY(launch_label_islands(ctx, ctx->isl_labels.p, ctx->cc_can.p));
+    NB2_CUDA(ctx, cudaMemcpyAsync(out_labels, ctx->isl_labels.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_rows)
+        NB2_CUDA(ctx, cudaMemcpyAsync(out_rows, ctx->cc_can.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NB2_OK;
 }

@@ -435,6 +435,7 @@ int launch_generate_manifolds(Context* ctx) {
     NB2_TRY(ctx->contacts.reserve(ctx, (size_t)4 * np));
     ctx->n_manifolds = np;
     ctx->n_contacts = 4 * np;
+    ctx->manifolds_from_producer = true;
     if (np) {
         PairOut pairs;
         pairs.q = ctx->pair_q.p;

@@ -175,9 +175,13 @@ int launch_validate_joints(Context* ctx) {
 }
 
 // ------------------------------------------------------------------ items
-__global__ void k_chunk_counts(const nb2_manifold* __restrict__ m, unsigned int nm, unsigned int* counts) {
+// min_chunks = 1 for the device producer's manifolds (one per persistent pair, <= 4 contacts each): a pair
+// that loses its contacts keeps an (unscheduled) chunk, so the item numbering -- what the schedule cache and
+// the incremental recolouring compare from step to step -- does not shift.
+__global__ void k_chunk_counts(const nb2_manifold* __restrict__ m, unsigned int nm, unsigned int* counts,
+                               unsigned int min_chunks) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nm) counts[i] = (m[i].num_contacts + NB2_CHUNK - 1) / NB2_CHUNK;
+    if (i < nm) counts[i] = max((m[i].num_contacts + NB2_CHUNK - 1) / NB2_CHUNK, min_chunks);
 }
 __global__ void k_fill_chunks(const nb2_manifold* __restrict__ m, unsigned int nm,
                               const unsigned int* __restrict__ chunk_base, unsigned int* chunk_manifold,
@@ -257,9 +261,9 @@ __global__ void k_build_items(int mode, int compact, int position, unsigned int 
             b2 = mf.body2;
             a = dyn_or_neg(status, mf.body1);
             b = dyn_or_neg(status, mf.body2);
-            if (a >= 0 || b >= 0) {
-                int local = (int)(k - chunk_base[m]);
-                int ncc = min(NB2_CHUNK, (int)mf.num_contacts - NB2_CHUNK * local);
+            const int local = (int)(k - chunk_base[m]);
+            const int ncc = min(NB2_CHUNK, (int)mf.num_contacts - NB2_CHUNK * local);
+            if ((a >= 0 || b >= 0) && ncc > 0) {
                 src = (int)k;
                 bool ground = (a < 0 || b < 0);
                 if (position) {
@@ -331,7 +335,7 @@ int launch_build_items(Context* ctx, int mode) {
     NB2_CUDA(ctx, cudaMemsetAsync(ctx->c_manifold.p, 0xFF, ((size_t)ctx->n_contacts + 1) * sizeof(unsigned int),
                                   ctx->stream));
     if (nM) {
-        k_chunk_counts<<<nblk(nM), TPB, 0, ctx->stream>>>(ctx->manifolds.p, nM, ctx->deg.p);
+        k_chunk_counts<<<nblk(nM), TPB, 0, ctx->stream>>>(ctx->manifolds.p, nM, ctx->deg.p, ctx->manifolds_from_producer ? 1u : 0u);
         ctx->launches++;
     }
     NB2_TRY(exclusive_scan_u32(ctx, ctx->deg.p, ctx->chunk_base.p, nM));
@@ -453,6 +457,10 @@ __device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
     x ^= x >> 16;
     return x;
 }
+// Schedule-cache verdicts (the device flag `changed`): 0 keep everything, 1 (or ~0) colour from scratch, 2 the
+// graph is unchanged but a refinement pass is still due, 3 a few groups changed: edit the colouring in place.
+#define NB2_SCHED_REFINE 2u
+#define NB2_SCHED_INCREMENTAL 3u
 // Conditional helpers of the schedule cache: no-ops while the conflict graph is unchanged.
 __global__ void k_cond_zero(const unsigned int* __restrict__ changed, unsigned int* p, size_t nwords) {
     if (*changed == 0u) return;
@@ -460,21 +468,54 @@ __global__ void k_cond_zero(const unsigned int* __restrict__ changed, unsigned i
     if (i < nwords) p[i] = 0u;
 }
 __global__ void k_cond_fill_int(const unsigned int* __restrict__ changed, int* p, size_t n, int v) {
-    if (*changed == 0u || *changed == 2u) return;  // a refinement pass starts from the colours it has
+    if (*changed == 0u || *changed == NB2_SCHED_REFINE || *changed == NB2_SCHED_INCREMENTAL) return;  // those start from the colours they have
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-// Compares this step's groups with the previous step's (when comparable) and records them.
+// Compares this step's groups with the previous step's (when comparable): counts the groups whose conflict
+// signature -- (dynamic body pair, row count, type, body pair) -- differs.
 __global__ void k_compare_snapshot(size_t n, const int* __restrict__ it_a, const int* __restrict__ it_b,
                                    const int* __restrict__ it_nrows, const int* __restrict__ it_type,
-                                   const int* __restrict__ it_b1, const int* __restrict__ it_b2, int* prev_a,
-                                   int* prev_b, int* prev_nt, int* prev_b1, int* prev_b2, unsigned int* changed,
-                                   int compare) {
+                                   const int* __restrict__ it_b1, const int* __restrict__ it_b2,
+                                   const int* __restrict__ prev_a, const int* __restrict__ prev_b,
+                                   const int* __restrict__ prev_nt, const int* __restrict__ prev_b1,
+                                   const int* __restrict__ prev_b2, unsigned int* n_changed) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool diff = false;
+    if (i < n) {
+        const int nt = (it_nrows[i] & 0xFF) | (it_type[i] << 8);
+        diff = prev_a[i] != it_a[i] || prev_b[i] != it_b[i] || prev_nt[i] != nt || prev_b1[i] != it_b1[i] || prev_b2[i] != it_b2[i];
+    }
+    const unsigned int v = __ballot_sync(0xffffffffu, diff);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(n_changed, (unsigned int)__popc(v));
+}
+// Records this step's groups for the next comparison.  On an incremental step (*changed == NB2_SCHED_INCREMENTAL)
+// it first edits the colouring in place: a group that vanished or changed its bodies gives its colour back
+// (its bit is cleared in both bodies' colour masks), a group that appeared or changed its bodies is marked
+// uncoloured for the Jones-Plassmann rounds of k_colour; a group that only changed its row count keeps its
+// colour (conflicts depend on the bodies alone).
+__global__ void k_apply_snapshot(size_t n, const int* __restrict__ it_a, const int* __restrict__ it_b,
+                                 const int* __restrict__ it_nrows, const int* __restrict__ it_type,
+                                 const int* __restrict__ it_b1, const int* __restrict__ it_b2, int* prev_a, int* prev_b,
+                                 int* prev_nt, int* prev_b1, int* prev_b2, const unsigned int* __restrict__ changed,
+                                 int* phase, unsigned long long* cmask) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int a = it_a[i], b = it_b[i], nt = (it_nrows[i] & 0xFF) | (it_type[i] << 8), b1 = it_b1[i], b2 = it_b2[i];
-    if (compare && (prev_a[i] != a || prev_b[i] != b || prev_nt[i] != nt || prev_b1[i] != b1 || prev_b2[i] != b2))
-        *changed = 1u;
+    if (*changed == NB2_SCHED_INCREMENTAL) {
+        const int pa = prev_a[i], pb = prev_b[i];
+        const bool was = (prev_nt[i] >> 8) != NB2_ITEM_INVALID, now = it_type[i] != NB2_ITEM_INVALID;
+        const bool same = pa == a && pb == b;
+        if (was && !(now && same)) {
+            const int c = phase[i];
+            if (c >= 0 && c < NB2_MAX_COLOURS) {
+                const unsigned long long m = ~(1ull << (c & 63));
+                if (pa >= 0) atomicAnd(&cmask[(size_t)pa * NB2_MASK_WORDS + (c >> 6)], m);
+                if (pb >= 0) atomicAnd(&cmask[(size_t)pb * NB2_MASK_WORDS + (c >> 6)], m);
+            }
+        }
+        if (now && !(was && same)) phase[i] = -1;
+    }
     prev_a[i] = a;
     prev_b[i] = b;
     prev_nt[i] = nt;
@@ -485,14 +526,39 @@ __global__ void k_compare_snapshot(size_t n, const int* __restrict__ it_a, const
 // Schedule-cache verdict of the step: *changed = 0 keep everything, 1 (or ~0) colour from scratch, 2 = the
 // graph is unchanged but the colouring still has refinement passes to run (one iterated-greedy pass per
 // step, so a scene pays for them only while it stays put).
-#define NB2_SCHED_REFINE 2u
-__global__ void k_refine_decide(unsigned int* changed, SchedHeader* hdr) {
-    if (*changed != 0u) {
+// ... 3 = a few groups changed: the colouring is edited in place (k_apply_snapshot + the Jones-Plassmann
+// rounds over the uncoloured groups only; no iterated-greedy pass, no balancing).  Every NB2_INC_MAX-th
+// incremental step in a row, and any step that changes more than 1/8 of the groups, colours from scratch.
+#define NB2_INC_MAX 64u
+__global__ void k_refine_decide(unsigned int* changed, SchedHeader* hdr, const unsigned int* __restrict__ n_changed,
+                                unsigned int n_items, int comparable, int incremental) {
+    const unsigned int nc = *n_changed;
+    if (!comparable) {
+        *changed = 1u;
+    } else if (nc == 0u) {
+        *changed = 0u;
+    } else if (incremental && hdr->n_phases > 0u && hdr->overflow == 0u && nc <= max(256u, n_items / 8u) &&
+               hdr->pad[0] < NB2_INC_MAX) {
+        *changed = NB2_SCHED_INCREMENTAL;
+    } else {
+        *changed = 1u;
+    }
+    if (*changed == 1u) {
         hdr->refine_left = NB2_IG_REFINE;
+        hdr->pad[0] = 0u;
+    } else if (*changed == NB2_SCHED_INCREMENTAL) {
+        hdr->refine_left = 0u;  // the pre-balance colouring the refinement passes work on is stale now
+        hdr->pad[0] += 1u;
     } else if (hdr->refine_left > 0u) {
         *changed = NB2_SCHED_REFINE;
         hdr->refine_left -= 1u;
     }
+}
+// the colour masks are kept on an incremental step
+__global__ void k_cond_zero_full(const unsigned int* __restrict__ changed, unsigned int* p, size_t nwords) {
+    if (*changed == 0u || *changed == NB2_SCHED_INCREMENTAL) return;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) p[i] = 0u;
 }
 
 __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict__ it_a, const int* __restrict__ it_b,
@@ -555,6 +621,11 @@ __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict_
             phase[i] = colour;
         }
         gb.sync();
+    }
+    if (*changed == NB2_SCHED_INCREMENTAL) {  // edited in place: the other groups keep their (refined, balanced) colours
+        for (size_t i = tid; i < n; i += stride)
+            if (it_type[i] != NB2_ITEM_INVALID) raw_phase[i] = phase[i];
+        return;
     }
     // ---- iterated greedy (Culberson).  Groups of one colour share no body, so a whole colour class can be
     // recoloured at once with plain first-fit against the classes already redone; visiting the classes in
@@ -801,27 +872,36 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     // clear, keeping the previous phases, layout and g_info.  No host read-back is involved.
     NB2_TRY(ctx->flags.reserve(ctx, 4));
     unsigned int* changed = ctx->flags.p + 1;
+    unsigned int* n_changed = ctx->flags.p + 3;
     const bool comparable = mode == NB2_MODE_COLOURED && ctx->schedule_cache && s->cache_valid && s->cache_n == n &&
                             n > 0 && s->cache_bodies == nb;
     NB2_CUDA(ctx, cudaMemsetAsync(changed, comparable ? 0 : 0xFF, sizeof(unsigned int), ctx->stream));
+    NB2_CUDA(ctx, cudaMemsetAsync(n_changed, 0, sizeof(unsigned int), ctx->stream));
     if (mode == NB2_MODE_COLOURED && n > 0) {
         NB2_TRY(s->prev_a.reserve(ctx, n));
         NB2_TRY(s->prev_b.reserve(ctx, n));
         NB2_TRY(s->prev_nt.reserve(ctx, n));
         NB2_TRY(s->prev_b1.reserve(ctx, n));
         NB2_TRY(s->prev_b2.reserve(ctx, n));
-        k_compare_snapshot<<<nblk(n), TPB, 0, ctx->stream>>>(n, s->it_a.p, s->it_b.p, s->it_nrows.p, s->it_type.p,
-                                                              s->it_b1.p, s->it_b2.p, s->prev_a.p, s->prev_b.p,
-                                                              s->prev_nt.p, s->prev_b1.p, s->prev_b2.p, changed,
-                                                              comparable ? 1 : 0);
-        ctx->launches++;
+        NB2_TRY(ctx->cmask.reserve(ctx, (size_t)nb * NB2_MASK_WORDS + 1));
+        if (comparable) {
+            k_compare_snapshot<<<nblk(n), TPB, 0, ctx->stream>>>(n, s->it_a.p, s->it_b.p, s->it_nrows.p, s->it_type.p,
+                                                                  s->it_b1.p, s->it_b2.p, s->prev_a.p, s->prev_b.p,
+                                                                  s->prev_nt.p, s->prev_b1.p, s->prev_b2.p, n_changed);
+            ctx->launches++;
+        }
+        k_refine_decide<<<1, 1, 0, ctx->stream>>>(changed, s->hdr.p, n_changed, (unsigned int)n, comparable ? 1 : 0,
+                                                  ctx->incremental_colouring ? 1 : 0);
+        k_apply_snapshot<<<nblk(n), TPB, 0, ctx->stream>>>(n, s->it_a.p, s->it_b.p, s->it_nrows.p, s->it_type.p, s->it_b1.p,
+                                                            s->it_b2.p, s->prev_a.p, s->prev_b.p, s->prev_nt.p, s->prev_b1.p,
+                                                            s->prev_b2.p, changed, s->it_phase.p, ctx->cmask.p);
+        ctx->launches += 2;
         s->cache_valid = true;
         s->cache_n = n;
         s->cache_bodies = nb;
     } else {
         s->cache_valid = false;
     }
-    if (mode == NB2_MODE_COLOURED) k_refine_decide<<<1, 1, 0, ctx->stream>>>(changed, s->hdr.p);
     k_cond_zero<<<1, 32, 0, ctx->stream>>>(changed, (unsigned int*)s->hdr.p, offsetof(SchedHeader, refine_left) / 4);
     k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_count.p, s->max_phases + 1);
     k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_R.p, s->max_phases + 1);
@@ -873,7 +953,7 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     } else {
         NB2_TRY(ctx->cmask.reserve(ctx, (size_t)nb * NB2_MASK_WORDS + 1));
         NB2_TRY(ctx->best.reserve(ctx, (size_t)nb + 1));
-        k_cond_zero<<<nblk((size_t)nb * NB2_MASK_WORDS * 2), TPB, 0, ctx->stream>>>(
+        k_cond_zero_full<<<nblk((size_t)nb * NB2_MASK_WORDS * 2), TPB, 0, ctx->stream>>>(
             changed, (unsigned int*)ctx->cmask.p, (size_t)nb * NB2_MASK_WORDS * 2);
         k_cond_zero<<<nblk((size_t)nb * 2), TPB, 0, ctx->stream>>>(changed, (unsigned int*)ctx->best.p, (size_t)nb * 2);
         k_cond_fill_int<<<nblk(n), TPB, 0, ctx->stream>>>(changed, s->it_phase.p, n, -1);

@@ -17,6 +17,7 @@ static const int TPB = SOLVE_TPB;
 
 int launch_velocity_solve_coloured(Context* ctx, const SchedDev& sd, const Rows& R, const CompactArrays& CA);
 int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd, const Rows& R, int tpb, int depth, int blocks);
+int launch_velocity_solve_bulk(Context* ctx, const SchedDev& sd, const Rows& R, int tpb, int depth, int blocks);
 bool staged_geometry(Context* ctx, int* tpb, int* depth, int* blocks);
 int launch_position_solve_staged(Context* ctx, const SchedDev& sd, const PosArrays& A, const PosParams& P, int rows_div,
                                  int tpb, int blocks);
@@ -396,7 +397,10 @@ int launch_velocity_solve(Context* ctx, int mode) {
     if (ctx->step_layout == 1) return launch_velocity_solve_coloured(ctx, sd, R, compact_arrays(ctx, ref));
     if (!ref && ctx->velocity_kernel >= 2) {
         int tpb_s, depth_s, blocks_s;
-        if (staged_geometry(ctx, &tpb_s, &depth_s, &blocks_s)) return launch_velocity_solve_staged(ctx, sd, R, tpb_s, depth_s, blocks_s);
+        if (staged_geometry(ctx, &tpb_s, &depth_s, &blocks_s)) {
+            if (ctx->velocity_kernel == 3) return launch_velocity_solve_bulk(ctx, sd, R, tpb_s, depth_s, blocks_s);
+            return launch_velocity_solve_staged(ctx, sd, R, tpb_s, depth_s, blocks_s);
+        }
     }
     void* args[] = {&sd, &R, &lam, &iters, &warm, &symmetric, &bar};
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));

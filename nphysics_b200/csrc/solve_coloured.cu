@@ -343,6 +343,274 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
 #endif
 }
 
+// ------------------------------------------------------------------------------------------
+// Bulk-copy row stream (NB2_VELOCITY_KERNEL=3): the same schedule, the same arithmetic, the row ring filled
+// by the copy engine instead of by the threads.
+//
+// The 32 lanes of a warp own 32 consecutive groups of a phase, so row r of those groups is one contiguous
+// 512-byte slice in each of the six row planes.  One elected lane arms an mbarrier with the byte count and
+// issues six cp.async.bulk (global -> shared, completing on that mbarrier); the warp then waits on the
+// mbarrier's phase parity.  Against the per-thread cp.async ring this removes 6 LDGSTS + their address
+// arithmetic per thread and row from a kernel that is issue-bound (profiles/r01_notes.md), and the warp
+// walks its groups in lockstep (rows beyond a lane's own count are predicated off: groups of a warp hold
+// 12 rows each in a pile).  A ring entry is refilled as soon as its values sit in registers.
+// g_info travels in registers: the consumer fetches its next group's record before the phase barrier.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned int bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned int bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned int dst, const void* src, unsigned int bytes, unsigned int bar,
+                                         unsigned long long pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
+}
+
+struct WarpPos {
+    int s;            // sweep, 0 = warm start
+    unsigned int p;   // phase
+    unsigned int gw;  // first group of the warp's 32-group block within the phase
+};
+__device__ __forceinline__ bool seek_block(WarpPos& q, unsigned int w0, unsigned int np, int iters, const unsigned int* s_cnt) {
+    for (;;) {
+        if (q.s > iters) return false;
+        if (q.gw < s_cnt[q.p]) return true;
+        q.gw = w0;
+        if (++q.p == np) {
+            q.p = 0;
+            ++q.s;
+        }
+    }
+}
+
+#define NB2_BULK_PLANES 6  // 5 jacobian planes + header
+
+template <int D>
+__global__ void __launch_bounds__(384, 1) k_velocity_solve_bulk(SchedDev sd, StagedRows R, float4* lam, int iters,
+                                                                unsigned int* barrier) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned int TPBK = blockDim.x, NW = TPBK >> 5;
+    const unsigned int t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    // [warp][D][6][32] quads | [warp][12][32] impulses | [warp][D] mbarriers | phase tables
+    float4* ring_all = reinterpret_cast<float4*>(smem_raw);
+    float* simp_all = reinterpret_cast<float*>(ring_all + (size_t)NW * D * NB2_BULK_PLANES * 32);
+    unsigned long long* bars_all = reinterpret_cast<unsigned long long*>(simp_all + (size_t)NW * 12 * 32);
+    unsigned int* s_cnt = reinterpret_cast<unsigned int*>(bars_all + (size_t)NW * D);
+    unsigned int* s_rbase = s_cnt + NB2_MAX_COLOURS;
+    unsigned int* s_gbase = s_rbase + NB2_MAX_COLOURS;
+    const unsigned int np = min(sd.hdr->n_phases, (unsigned int)NB2_MAX_COLOURS);
+    if (np == 0) return;
+    for (unsigned int i = t; i < np; i += TPBK) {
+        s_cnt[i] = sd.ph_count[i];
+        s_rbase[i] = sd.ph_rbase[i];
+        s_gbase[i] = sd.ph_gbase[i];
+    }
+    float4* ring = ring_all + (size_t)warp * D * NB2_BULK_PLANES * 32;
+    float* simp = simp_all + (size_t)warp * 12 * 32;
+    const unsigned int ring_u32 = (unsigned int)__cvta_generic_to_shared(ring);
+    const unsigned int bar_u32 = (unsigned int)__cvta_generic_to_shared(bars_all + (size_t)warp * D);
+    if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < D; ++e) mbar_init(bar_u32 + 8u * e, 1u);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    GridBarrier gb;
+    gb.init(barrier);
+    const unsigned int w0 = (warp * gridDim.x + blockIdx.x) * 32u;  // block-interleaved warps (interleaved_tid)
+    const unsigned int stride = gridDim.x * TPBK;
+    const unsigned long long pol = l2_evict_first_policy();
+    constexpr unsigned int entry_b = NB2_BULK_PLANES * 32u * 16u, plane_b = 32u * 16u;
+
+    // ---- producer: walks the (sweep, phase, block, row) sequence D entries ahead of the consumer
+    WarpPos pc = {0, 0u, w0};
+    bool vc = seek_block(pc, w0, np, iters, s_cnt);
+    int p_rmax = 0, pr = 0;  // rows of the block being produced, next row
+    unsigned int p_slot = 0, p_cnt = 0, p_bytes = 0;
+    auto open_block = [&]() {  // all lanes: row count of the block = max over its lanes' groups
+        p_cnt = s_cnt[pc.p];
+        const unsigned int nvalid = min(32u, p_cnt - pc.gw);
+        int nr = 0;
+        if (lane < nvalid) nr = __ldg(&sd.g_info[s_gbase[pc.p] + pc.gw + lane]).z & 0xFF;
+        p_rmax = __reduce_max_sync(0xffffffffu, nr);
+        p_slot = s_rbase[pc.p] + pc.gw;
+        p_bytes = nvalid * 16u;
+        pr = 0;
+    };
+    if (vc) open_block();
+    int pe = 0;  // ring entry produced next
+    auto produce = [&]() {
+        while (vc && pr >= p_rmax) {  // next block that has rows
+            pc.gw += stride;
+            vc = seek_block(pc, w0, np, iters, s_cnt);
+            if (vc) open_block();
+        }
+        if (vc) {
+            if (lane == 0) {
+                const unsigned int bar = bar_u32 + 8u * (unsigned int)pe;
+                const unsigned int dst = ring_u32 + (unsigned int)pe * entry_b;
+                mbar_expect_tx(bar, NB2_BULK_PLANES * p_bytes);
+#pragma unroll
+                for (int k = 0; k < NB2_BULK_PLANES; ++k) bulk_g2s(dst + (unsigned int)k * plane_b, R.q[k] + p_slot, p_bytes, bar, pol);
+            }
+            p_slot += p_cnt;
+            ++pr;
+            pe = pe + 1 == D ? 0 : pe + 1;
+        }
+    };
+#pragma unroll 1
+    for (int e = 0; e < D; ++e) produce();
+
+    int ce = 0;
+    unsigned int cpar = 0;  // parity of the consumer's current pass over the ring
+    // next group record of this lane, fetched ahead of the phase barrier
+    WarpPos cn = {0, 0u, w0};
+    bool cv = seek_block(cn, w0, np, iters, s_cnt);
+    int4 info_n = make_int4(-1, -1, 0, 0);
+    if (cv && cn.gw + lane < s_cnt[cn.p]) info_n = __ldg(&sd.g_info[s_gbase[cn.p] + cn.gw + lane]);
+
+    for (int s = 0; s <= iters; ++s) {
+        for (unsigned int p = 0; p < np; ++p) {
+            const unsigned int cnt = s_cnt[p];
+            const unsigned int rbase = s_rbase[p];
+            for (unsigned int gw = w0; gw < cnt; gw += stride) {
+                const unsigned int g = gw + lane;
+                const bool active = g < cnt;
+                const int4 info = info_n;
+                {  // fetch the record of the block after this one
+                    cn.gw += stride;
+                    cv = seek_block(cn, w0, np, iters, s_cnt);
+                    info_n = make_int4(-1, -1, 0, 0);
+                    if (cv && cn.gw + lane < s_cnt[cn.p]) info_n = __ldg(&sd.g_info[s_gbase[cn.p] + cn.gw + lane]);
+                }
+                const bool a = active && info.x >= 0, b = active && info.y >= 0;
+                const int nrows = active ? (info.z & 0xFF) : 0;
+                const int rmax = __reduce_max_sync(0xffffffffu, nrows);
+                const int ncc = (info.z >> 8) == NB2_ITEM_CONTACTS ? nrows / 3 : 0;
+                Lam la, lb;
+                la.im = lb.im = 0.f;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) la.v[k] = lb.v[k] = 0.f;
+                if (a) la = load_lam(lam, info.x);
+                if (b) lb = load_lam(lam, info.y);
+                {
+                    float v[12];
+#pragma unroll
+                    for (int r = 0; r < 12; ++r)
+                        if (r < nrows) v[r] = __ldcg(&R.imp[rbase + (unsigned int)r * cnt + g]);
+#pragma unroll
+                    for (int r = 0; r < 12; ++r)
+                        if (r < nrows) simp[r * 32 + lane] = v[r];
+                }
+                unsigned int cslot = rbase + g;
+#pragma unroll 1
+                for (int r = 0; r < rmax; ++r, cslot += cnt) {
+                    mbar_wait(bar_u32 + 8u * (unsigned int)ce, cpar);
+                    RowPkt k;
+                    const float4* q = ring + (size_t)ce * NB2_BULK_PLANES * 32 + lane;
+                    k.q0 = q[0 * 32];
+                    k.q1 = q[1 * 32];
+                    k.q2 = q[2 * 32];
+                    k.q3 = q[3 * 32];
+                    k.q4 = q[4 * 32];
+                    k.h = q[5 * 32];
+                    if (++ce == D) {
+                        ce = 0;
+                        cpar ^= 1u;
+                    }
+                    if (r < nrows) {
+                        k.imp = simp[r * 32 + lane];
+                        const int kind = k.kind();
+                        RowJ J;
+                        unpack_pkt(k, true, true, la.im, lb.im, &J);
+                        if (s == 0) {  // warm start (sor_prox.rs:57-58, 345-435)
+                            const float w = kind == NB2_ROW_NONE ? 0.f : k.imp;
+                            if (a) axpy6(w, J.W1, la.v);
+                            if (b) axpy6(w, J.W2, lb.v);
+                        } else {
+                            // Dependent limits: +-mu * the normal impulse of the previous sweep (the group's own normal
+                            // rows come after its friction rows), exactly as in k_velocity_solve_staged
+                            float dep = 0.f;
+                            if (kind == NB2_ROW_DEPENDENT)
+                                dep = r < 2 * ncc ? simp[(2 * ncc + (r >> 1)) * 32 + lane] : __ldcg(&R.imp[k.dep()]);
+                            const float lim = k.h.z * dep;
+                            const float lo = kind == NB2_ROW_BILATERAL ? k.h.z : (kind == NB2_ROW_DEPENDENT ? -lim : 0.f);
+                            const float hi = kind == NB2_ROW_BILATERAL ? k.h.w : (kind == NB2_ROW_DEPENDENT ? lim : NB2_F32_MAX);
+                            float d = k.h.x;
+                            if (a) d += dot6(J.J1, la.v);
+                            if (b) d += dot6(J.J2, lb.v);
+                            float ni = fminf(fmaxf(k.imp - k.h.y * d, lo), hi);
+                            if (kind == NB2_ROW_NONE) ni = k.imp;
+                            const float dl = ni - k.imp;
+                            if (a) axpy6(dl, J.W1, la.v);
+                            if (b) axpy6(dl, J.W2, lb.v);
+                            if (ni != k.imp) __stcg(&R.imp[cslot], ni);
+                        }
+                    }
+                    // every lane has used its copy of the row: the entry can be refilled by the copy engine
+                    __syncwarp();
+                    produce();
+                }
+                if (a) store_lam(lam, info.x, la);
+                if (b) store_lam(lam, info.y, lb);
+            }
+            gb.sync();
+        }
+    }
+}
+
+static size_t bulk_smem(int depth, int tpb) {
+    const size_t nw = (size_t)tpb / 32;
+    return nw * depth * NB2_BULK_PLANES * 32 * 16 + nw * 12 * 32 * 4 + nw * depth * 8 + 3 * NB2_MAX_COLOURS * 4;
+}
+
+int launch_velocity_solve_bulk(Context* ctx, const SchedDev& sd_in, const Rows& R_in, int tpb, int depth, int blocks) {
+    SchedDev sd = sd_in;
+    StagedRows R;
+    for (int k = 0; k < NB2_ROW_PLANES; ++k) R.q[k] = R_in.jac + (size_t)k * R_in.S;
+    R.q[5] = R_in.hdr;
+    R.imp = R_in.imp;
+    if (const char* f = getenv("NB2_BULK_DEPTH")) depth = atoi(f);
+    if (depth < 3) depth = 3;
+    if (depth > 6) depth = 6;
+    while (depth > 3 && bulk_smem(depth, tpb) > ctx->smem_optin) --depth;
+    const size_t smem = bulk_smem(depth, tpb);
+    void* kernel = depth == 3 ? (void*)k_velocity_solve_bulk<3>
+                 : depth == 4 ? (void*)k_velocity_solve_bulk<4>
+                 : depth == 5 ? (void*)k_velocity_solve_bulk<5> : (void*)k_velocity_solve_bulk<6>;
+    if (!ctx->bulk_attr) {
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_bulk<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_bulk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_bulk<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_bulk<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        ctx->bulk_attr = true;
+    }
+    float4* lam = ctx->lam.p;
+    int iters = (int)ctx->params.max_velocity_iterations;
+    unsigned int* bar = ctx->barrier.p;
+    void* args[] = {&sd, &R, &lam, &iters, &bar};
+    if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
+    NB2_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(tpb), args, smem, ctx->stream));
+    if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[7], ctx->stream));
+    ctx->launches++;
+    return NB2_OK;
+}
+
 static size_t staged_smem(int depth, int tpb) {
     return (size_t)depth * NB2_VENTRY * tpb * 16 + 12 * (size_t)tpb * 4 + 3 * NB2_MAX_COLOURS * 4;
 }
@@ -427,14 +695,26 @@ int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd_in, const Rows
 // fetched after the barrier, in one round trip.
 //
 // Entry = 26 quads x TPB lanes: 0..4 group header (p_hdr planes), 5+5*lcc+k contact lcc plane k, 25 g_info.
+//
+// Settled groups cost (almost) nothing.  A contact group whose contacts all evaluate to "nothing to correct"
+// (clamp_rhs(-depth) >= 0, nonlinear_sor_prox.rs:199-201) will evaluate to exactly the same thing in the next
+// sweep unless one of its two bodies has been displaced in between -- the evaluation is a pure function of the
+// two poses.  Every displacement is therefore stamped on the body (`moved[body]` = the phase visit it
+// happened in) and every clean evaluation on the group (`g_stamp[group]` = the visit it happened in); a group
+// is skipped when its stamp is newer than both bodies' stamps.  Skipped groups read two stamps instead of two
+// bodies, a header and four contact records, and their rows are not even prefetched.  The result is bit for
+// bit the one of sweeping every group (tests/test_gpu_parity.py::test_position_skip_is_exact).  Visit numbers
+// grow monotonically across launches (`visit_base`), so neither array is ever cleared.
 // ------------------------------------------------------------------------------------------
 #define NB2_PENTRY 26
+#define NB2_POS_NOT_LOADED (1 << 30)  // control-quad flag (bit 30 of g_info.z): the producer skipped this group's data
 
 __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, PosArrays A, const nb2_joint* __restrict__ joints,
                                                                   const float4* __restrict__ p_hdr, size_t G_stride,
                                                                   const float4* __restrict__ p_row, size_t P_stride,
                                                                   PosParams P, int iters, int E, int rows_div,
-                                                                  unsigned int* barrier) {
+                                                                  unsigned int* barrier, int* g_stamp, int* moved,
+                                                                  int visit_base, int skip_enabled) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned int TPBK = blockDim.x;
     float4* ring = reinterpret_cast<float4*>(smem_raw);  // [E][NB2_PENTRY][TPBK]
@@ -455,41 +735,64 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
     const unsigned int ring_u32 = (unsigned int)__cvta_generic_to_shared(ring) + t * 16u;
     const unsigned int plane_b = TPBK * 16u, entry_b = NB2_PENTRY * plane_b;
     const int last_it = iters - 1;
+    // The stamps cost a few loads and stores per group visit.  They are kept during the first sweep, which also
+    // counts how many groups evaluated clean; if fewer than a quarter did (a pile that is still compressing: every
+    // contact asks for a correction in every sweep) the remaining sweeps run without them, like NB2_POS_SKIP=0.
+    bool track = skip_enabled != 0;
+    unsigned int n_clean = 0, n_eval = 0;
 
     StreamPos pc = {0, 0u, tid}, pn;
     bool vc = seek_group(pc, tid, np, last_it, s_cnt), vn = false;
     int4 ic = make_int4(-1, -1, 0, 0), in_ = ic;
+    // the clean-evaluation stamp of the group being produced / of the one after it (fetched one group ahead;
+    // a stale value is only ever older, i.e. errs towards evaluating)
+    int tc = 0, tn = 0;
     if (vc) {
         ic = __ldg(&sd.g_info[s_gbase[pc.p] + pc.g]);
         pn = pc;
         pn.g += stride;
         vn = seek_group(pn, tid, np, last_it, s_cnt);
-        if (vn) in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
+        if (vn) {
+            in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
+            if (track && pn.s > 0) tn = __ldcg(&g_stamp[s_gbase[pn.p] + pn.g]);
+        }
     }
+    // copies the constant data of group (p, g) into ring entry e
+    auto fetch_group = [&](int e, int4 info, unsigned int p, unsigned int g) {
+        const unsigned int dst = ring_u32 + (unsigned int)e * entry_b;
+        const unsigned int cnt = s_cnt[p];
+        const float4* hsrc = p_hdr + s_gbase[p] + g;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) cp_async16(dst + (unsigned int)k * plane_b, hsrc + (size_t)k * G_stride);
+        const int ncc = (info.z & 0xFF) / rows_div;
+        const float4* rsrc = p_row + (size_t)NB2_CHUNK * s_gbase[p] + g;
+        for (int lcc = 0; lcc < ncc; ++lcc, rsrc += cnt) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                cp_async16(dst + (unsigned int)(5 + 5 * lcc + k) * plane_b, rsrc + (size_t)k * P_stride);
+        }
+    };
     auto produce = [&](int e) {
         if (vc) {
-            const unsigned int dst = ring_u32 + (unsigned int)e * entry_b;
-            reinterpret_cast<int4*>(ring)[(e * NB2_PENTRY + 25) * TPBK + t] = ic;
+            int4 ctl = ic;
+            ctl.w = tc;  // the item index is not needed by this kernel: the control quad carries the stamp instead
             if ((ic.z >> 8) != NB2_ITEM_JOINT) {
-                const unsigned int cnt = s_cnt[pc.p];
-                const float4* hsrc = p_hdr + s_gbase[pc.p] + pc.g;
-#pragma unroll
-                for (int k = 0; k < 5; ++k) cp_async16(dst + (unsigned int)k * plane_b, hsrc + (size_t)k * G_stride);
-                const int ncc = (ic.z & 0xFF) / rows_div;
-                const float4* rsrc = p_row + (size_t)NB2_CHUNK * s_gbase[pc.p] + pc.g;
-                for (int lcc = 0; lcc < ncc; ++lcc, rsrc += cnt) {
-#pragma unroll
-                    for (int k = 0; k < 5; ++k)
-                        cp_async16(dst + (unsigned int)(5 + 5 * lcc + k) * plane_b, rsrc + (size_t)k * P_stride);
-                }
+                // a group that evaluated clean in this launch will most likely be skipped: do not stream its rows
+                if (track && pc.s > 0 && tc > visit_base) ctl.z |= NB2_POS_NOT_LOADED;
+                else fetch_group(e, ic, pc.p, pc.g);
             }
+            reinterpret_cast<int4*>(ring)[(e * NB2_PENTRY + 25) * TPBK + t] = ctl;
             pc = pn;
             ic = in_;
+            tc = tn;
             vc = vn;
             if (vn) {
                 pn.g += stride;
                 vn = seek_group(pn, tid, np, last_it, s_cnt);
-                if (vn) in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
+                if (vn) {
+                    in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
+                    tn = (track && pn.s > 0) ? __ldcg(&g_stamp[s_gbase[pn.p] + pn.g]) : 0;
+                }
             }
         }
         cp_async_commit();
@@ -501,22 +804,48 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
     for (int it = 0; it < iters; ++it) {
         for (unsigned int p = 0; p < np; ++p) {
             const unsigned int cnt = s_cnt[p];
+            const int visit = visit_base + it * (int)np + (int)p + 1;
             for (unsigned int gw = tid - lane; gw < cnt; gw += stride) {
                 if (gw + lane >= cnt) continue;
-                cp_async_wait_dyn(E - 1);
                 const int e = ce;
                 ce = ce + 1 == E ? 0 : ce + 1;
                 const float4* q = ring + (size_t)(e * NB2_PENTRY) * TPBK + t;
-                const int4 info = *reinterpret_cast<const int4*>(q + 25 * TPBK);
+                int4 info = *reinterpret_cast<const int4*>(q + 25 * TPBK);  // written with st.shared by this thread
+                const unsigned int gslot = s_gbase[p] + gw + lane;
                 PosBody b1, b2;
                 if ((info.z >> 8) == NB2_ITEM_JOINT) {
-                    const nb2_joint& j = joints[info.w];
+                    cp_async_wait_dyn(E - 1);
+                    const nb2_joint& j = joints[__ldg(&sd.g_info[gslot]).w];
                     load_pos_body(A, j.body1, &b1);
                     load_pos_body(A, j.body2, &b2);
                     joint_position(j, &b1, &b2, P);
-                    if (b1.dynamic) store_pos_body(A, j.body1, b1);
-                    if (b2.dynamic) store_pos_body(A, j.body2, b2);
+                    if (b1.dynamic) {
+                        store_pos_body(A, j.body1, b1);
+                        if (track) __stcg(&moved[j.body1], visit);
+                    }
+                    if (b2.dynamic) {
+                        store_pos_body(A, j.body2, b2);
+                        if (track) __stcg(&moved[j.body2], visit);
+                    }
                 } else {
+                    // ---- exact skip: clean at visit info.w of this launch and neither body displaced since
+                    if (track && it > 0 && info.w > visit_base) {
+                        const int ma = info.x >= 0 ? __ldcg(&moved[info.x]) : 0;
+                        const int mb = info.y >= 0 ? __ldcg(&moved[info.y]) : 0;
+                        if (ma < info.w && mb < info.w) {
+                            if (!(info.z & NB2_POS_NOT_LOADED)) cp_async_wait_dyn(E - 1);  // the entry is about to be refilled
+                            produce(e);
+                            continue;
+                        }
+                    }
+                    if (info.z & NB2_POS_NOT_LOADED) {  // displaced after a clean evaluation: fetch the rows after all
+                        info.z &= ~NB2_POS_NOT_LOADED;
+                        fetch_group(e, info, p, gw + lane);
+                        cp_async_commit();
+                        cp_async_wait<0>();
+                    } else {
+                        cp_async_wait_dyn(E - 1);
+                    }
                     const float4 h0 = q[0], h1 = q[1 * TPBK], h2 = q[2 * TPBK], h3 = q[3 * TPBK], h4 = q[4 * TPBK];
                     const int body1 = __float_as_int(h0.x), body2 = __float_as_int(h0.y);
                     load_pos_body(A, body1, &b1);
@@ -530,7 +859,7 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                     // colliders sitting at their body's origin (the usual case) need no pose product
                     const bool id1 = h1.x == 0.f && h1.y == 0.f && h1.z == 0.f && h1.w == 0.f && h2.x == 0.f && h2.y == 0.f && h2.z == 1.f;
                     const bool id2 = h3.x == 0.f && h3.y == 0.f && h3.z == 0.f && h3.w == 0.f && h4.x == 0.f && h4.y == 0.f && h4.z == 1.f;
-                    bool moved1 = false, moved2 = false;
+                    bool moved1 = false, moved2 = false, any_active = false;
 #pragma unroll 1
                     for (int lcc = 0; lcc < ncc; ++lcc) {
                         const float4* rq = q + (size_t)(5 + 5 * lcc) * TPBK;
@@ -542,6 +871,7 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                         if (!kinematic_contact(l1, l2, d1, d2, n1, m1, m2, &cev)) continue;
                         const float rhs = clamp_rhs(-cev.depth, false, P);
                         if (rhs >= 0.f) continue;
+                        any_active = true;
                         Vec3 w1l = mk3(0.f, 0.f, 0.f), w1a = w1l, w2l = w1l, w2a = w1l;
                         float inv_r = 0.f;
                         pos_fill(b1, cev.world1, false, -cev.normal, &w1l, &w1a, &inv_r);
@@ -557,12 +887,33 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                             moved2 = true;
                         }
                     }
-                    if (moved1) store_pos_body(A, body1, b1);
-                    if (moved2) store_pos_body(A, body2, b2);
+                    if (moved1) {
+                        store_pos_body(A, body1, b1);
+                        if (track) __stcg(&moved[body1], visit);
+                    }
+                    if (moved2) {
+                        store_pos_body(A, body2, b2);
+                        if (track) __stcg(&moved[body2], visit);
+                    }
+                    // clean = no contact of the group asked for a correction (whether or not a body could move)
+                    if (track) __stcg(&g_stamp[gslot], any_active ? 0 : visit);
+                    n_eval += 1u;
+                    n_clean += any_active ? 0u : 1u;
                 }
                 produce(e);
             }
+            if (it == 0 && p + 1 == np && track && iters > 1) {  // the first sweep's verdict, summed over the grid
+                const unsigned int ce_ = __reduce_add_sync(0xffffffffu, n_clean), ev_ = __reduce_add_sync(0xffffffffu, n_eval);
+                if (lane == 0 && ev_) {
+                    atomicAdd(barrier + 2, ce_);
+                    atomicAdd(barrier + 3, ev_);
+                }
+            }
             gb.sync();
+            if (it == 0 && p + 1 == np && track && iters > 1) {
+                const unsigned int ce_ = __ldcg(barrier + 2), ev_ = __ldcg(barrier + 3);
+                track = 4u * ce_ >= ev_ && ce_ > 0u;
+            }
         }
     }
     cp_async_wait<0>();
@@ -593,7 +944,26 @@ int launch_position_solve_staged(Context* ctx, const SchedDev& sd_in, const PosA
     int iters = (int)ctx->params.max_position_iterations;
     unsigned int* bar = ctx->barrier.p;
     size_t smem = smem_of(E);
-    void* args[] = {&sd, &A, &joints, &phdr, &gstride, &prow, &pstride, &P, &iters, &E, &rows_div, &bar};
+    // stamps of the exact skip: zeroed when (re)allocated and when the visit counter is about to wrap
+    const size_t span = (size_t)iters * NB2_MAX_COLOURS + 2;
+    const bool wrap = (size_t)ctx->pos_visit_base + span > (size_t)0x3FFFFFFF;
+    {
+        int* before = ctx->pos_gstamp.p;
+        NB2_TRY(ctx->pos_gstamp.reserve(ctx, ctx->vs.n_items + 16));
+        if (ctx->pos_gstamp.p != before || wrap)
+            NB2_CUDA(ctx, cudaMemsetAsync(ctx->pos_gstamp.p, 0, ctx->pos_gstamp.cap * sizeof(int), ctx->stream));
+        before = ctx->pos_moved.p;
+        NB2_TRY(ctx->pos_moved.reserve(ctx, (size_t)ctx->n_bodies + 16));
+        if (ctx->pos_moved.p != before || wrap)
+            NB2_CUDA(ctx, cudaMemsetAsync(ctx->pos_moved.p, 0, ctx->pos_moved.cap * sizeof(int), ctx->stream));
+        if (wrap) ctx->pos_visit_base = 0;
+    }
+    int* gstamp = ctx->pos_gstamp.p;
+    int* movedp = ctx->pos_moved.p;
+    int vbase = ctx->pos_visit_base;
+    ctx->pos_visit_base += (int)span;
+    int skip = ctx->pos_skip ? 1 : 0;
+    void* args[] = {&sd, &A, &joints, &phdr, &gstride, &prow, &pstride, &P, &iters, &E, &rows_div, &bar, &gstamp, &movedp, &vbase, &skip};
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_position_solve_staged, dim3(blocks), dim3(tpb), args, smem, ctx->stream));
     ctx->launches++;
     return NB2_OK;

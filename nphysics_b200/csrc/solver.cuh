@@ -117,7 +117,7 @@ struct SchedHeader {
     unsigned int overflow;   // != 0: colouring ran out of colours / phases
     unsigned int work;       // scratch: "something changed" flag
     unsigned int refine_left;  // iterated-greedy passes still to run on steps whose conflict graph is unchanged
-    unsigned int pad[2];
+    unsigned int pad[2];       // [0] incremental recolourings since the last colouring from scratch
 };
 
 struct Sched {
@@ -171,6 +171,8 @@ struct Context {
     bool have_params = false;
     bool timers = false;
     bool schedule_cache = true;
+    bool incremental_colouring = true;  // NB2_INCREMENTAL_COLOURING=0: any change of the conflict graph colours from scratch
+    bool manifolds_from_producer = false;  // the contact set of the next step was written by nb2_generate_manifolds
     // coloured mode, contact groups: 0 = 132-byte row stream (default), 1 = 80-byte compact records
     int contact_layout = 0;
     int step_layout = 0;  // layout the last assembly used
@@ -194,6 +196,7 @@ struct Context {
     DevBuf<float2> act;              // threshold (< 0: None), energy (0: asleep)
     DevBuf<unsigned int> cc_parent, cc_can;
     DevBuf<int> wake_list;
+    DevBuf<int> isl_labels;          // nb2_label_islands
 
     // ---- joints
     uint32_t n_joints = 0;
@@ -271,11 +274,15 @@ struct Context {
     int velocity_kernel = 2;
     bool poison_rows = false;      // NB2_POISON_ROWS: fill the row planes with NaN bits before every assembly (tests)
     size_t smem_optin = 0;         // cudaDevAttrMaxSharedMemoryPerBlockOptin
-    bool staged_attr = false, staged_pos_attr = false;
+    bool staged_attr = false, staged_pos_attr = false, bulk_attr = false;
     DevBuf<float4> p_hdr;          // [5][n_ghdr_max] coloured position groups: bodies + collider-to-body poses
     size_t n_ghdr_max = 0;
     void* host_hdr = nullptr;      // pinned copy of vs.hdr (launch-geometry hint, never waited for)
     DevBuf<unsigned int> bal;       // groups per colour while balancing
+    // staged position kernel: exact skip of settled groups (solve_coloured.cu)
+    DevBuf<int> pos_gstamp, pos_moved;
+    int pos_visit_base = 0;
+    bool pos_skip = true;           // NB2_POS_SKIP=0 sweeps every group every iteration (A/B runs, the exactness test)
 };
 
 // ---------------------------------------------------------------------------
@@ -340,6 +347,7 @@ NB2_D void apply_displacement(BodyPose* b, Vec3 local_com, Vec3 lin, Vec3 ang) {
 int launch_unpack_bodies(Context* ctx);
 int launch_apply_effective_status(Context* ctx);
 int launch_update_activation(Context* ctx, float mix, const int32_t* to_activate, uint32_t n_list);
+int launch_label_islands(Context* ctx, int* d_labels, unsigned int* d_rows);
 int launch_refresh_dynamics(Context* ctx);
 int launch_integrate(Context* ctx, bool kinematic_only);
 int launch_pack_states(Context* ctx, nb2_body_state* d_out, uint32_t first, uint32_t n);

@@ -62,6 +62,13 @@ class Shard:
         self.joint_ids = joint_ids
         self.global_to_local = global_to_local
 
+    def localize_colliders(self, colliders):
+        """The colliders attached to this shard's bodies, re-indexed (for the device manifold producer)."""
+        lb = self.global_to_local[colliders["body"]]
+        c = colliders[lb >= 0].copy()
+        c["body"] = lb[lb >= 0]
+        return c
+
     def localize_manifolds(self, manifolds, contacts):
         """Keep the manifolds whose dynamic bodies live in this shard; re-index bodies and contacts."""
         g2l = self.global_to_local
@@ -80,20 +87,46 @@ class Shard:
         return m, c, idx
 
 
-def make_shards(bodies, joints, pairs_a, pairs_b, pair_weights, n_ranks):
+def dense_labels(labels):
+    """Representative labels (any non-negative ids, e.g. the device's "smallest body index of the island")
+    renumbered 0, 1, ... in order of first appearance; -1 stays -1."""
+    lab = np.asarray(labels, dtype=np.int64)
+    out = -np.ones(len(lab), dtype=np.int64)
+    ok = lab >= 0
+    if ok.any():
+        uniq, first, inv = np.unique(lab[ok], return_index=True, return_inverse=True)
+        rank = np.empty(len(uniq), dtype=np.int64)
+        rank[np.argsort(first, kind="stable")] = np.arange(len(uniq))
+        out[ok] = rank[inv]
+    return out
+
+
+def make_shards(bodies, joints, pairs_a=None, pairs_b=None, pair_weights=None, n_ranks=1, labels=None, body_rows=None):
     """Partition a world into n_ranks shards of whole islands.
 
-    pairs_*: body pairs of every potential manifold + joint (topology); pair_weights: rows per pair.
+    Two sources for the islands and their weights:
+      * labels / body_rows: the DEVICE labelling (nb2_label_islands: csrc/activation.cu) -- island id per
+        body (-1 for non-dynamic bodies) and the velocity rows booked on every body;
+      * pairs_a / pairs_b / pair_weights: body pairs of every potential manifold + joint with their rows,
+        labelled on the host (island_labels above; used by the CPU tests and as the device's cross-check).
     Non-dynamic bodies (ground, kinematic) are replicated into every shard that references them."""
     status = bodies["status"]
-    lab = island_labels(status, pairs_a, pairs_b)
-    n_islands = int(lab.max()) + 1 if (lab >= 0).any() else 0
-    pa = np.asarray(pairs_a, dtype=np.int64)
-    pb = np.asarray(pairs_b, dtype=np.int64)
-    pl = np.where(lab[pa] >= 0, lab[pa], lab[pb])
-    w = np.zeros(max(n_islands, 1), dtype=np.int64)
-    ok = pl >= 0
-    np.add.at(w, pl[ok], np.asarray(pair_weights, dtype=np.int64)[ok])
+    if labels is not None:
+        lab = dense_labels(labels)
+        n_islands = int(lab.max()) + 1 if (lab >= 0).any() else 0
+        w = np.zeros(max(n_islands, 1), dtype=np.int64)
+        ok = lab >= 0
+        if body_rows is not None:
+            np.add.at(w, lab[ok], np.asarray(body_rows, dtype=np.int64)[ok])
+    else:
+        lab = island_labels(status, pairs_a, pairs_b)
+        n_islands = int(lab.max()) + 1 if (lab >= 0).any() else 0
+        pa = np.asarray(pairs_a, dtype=np.int64)
+        pb = np.asarray(pairs_b, dtype=np.int64)
+        pl = np.where(lab[pa] >= 0, lab[pa], lab[pb])
+        w = np.zeros(max(n_islands, 1), dtype=np.int64)
+        ok = pl >= 0
+        np.add.at(w, pl[ok], np.asarray(pair_weights, dtype=np.int64)[ok])
     # islands without rows still need an owner: weight 1
     w = np.maximum(w, 1)[:max(n_islands, 0)]
     rank_of_island, load = assign_islands(w, n_ranks)

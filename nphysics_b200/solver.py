@@ -25,7 +25,7 @@ EXPORTS = [
     "nb2_download_contact_impulses", "nb2_download_joints", "nb2_get_stats", "nb2_get_timers",
     "nb2_launch_count", "nb2_download_schedule",
     "nb2_update_contacts", "nb2_upload_colliders", "nb2_detect_pairs", "nb2_generate_manifolds",
-    "nb2_download_manifolds",
+    "nb2_download_manifolds", "nb2_label_islands",
 ]
 
 
@@ -222,6 +222,13 @@ class Solver:
         out = np.zeros(self.n_bodies, dtype=abi.activation_dtype)
         self._chk(self.lib.nb2_download_activation(self.h, abi.ptr(out), ctypes.c_uint32(len(out))))
         return out
+
+    def label_islands(self):
+        """(island label per body or -1, velocity rows booked on each body) from the device labelling."""
+        lab = np.zeros(self.n_bodies, dtype=np.int32)
+        rows = np.zeros(self.n_bodies, dtype=np.uint32)
+        self._chk(self.lib.nb2_label_islands(self.h, abi.ptr(lab), abi.ptr(rows), ctypes.c_uint32(self.n_bodies)))
+        return lab, rows
 
     def step(self, mode=abi.MODE_COLOURED):
         self._chk(self.lib.nb2_step(self.h, int(mode)))

@@ -175,7 +175,7 @@ pub struct nb2_stats {
     pub n_phases_position: u32,
     pub n_broken_joints: u32,
     pub non_finite: u32,
-    pub pad_: u32,
+    pub schedule_verdict: u32,
     pub residual_max: f32,
     pub residual_rms: f32,
     pub max_penetration: f32,
@@ -234,6 +234,7 @@ extern "C" {
     pub fn nb2_download_manifolds(ctx: *mut nb2_context, out_manifolds: *mut nb2_manifold, manifold_capacity: u32,
                                   out_contacts: *mut nb2_contact, contact_capacity: u32, out_n_manifolds: *mut u32,
                                   out_n_contacts: *mut u32) -> i32;
+    pub fn nb2_label_islands(ctx: *mut nb2_context, out_labels: *mut i32, out_rows: *mut u32, n: u32) -> i32;
     pub fn nb2_download_schedule(ctx: *mut nb2_context, out_phase: *mut i32, out_body1: *mut i32, out_body2: *mut i32,
                                  capacity: u32, out_n: *mut u32) -> i32;
 }

@@ -164,6 +164,45 @@ def test_device_producer_is_deterministic_and_warm_starts():
     assert np.abs(outs[0][1]).max() > 0
 
 
+def test_incremental_recolouring_keeps_the_schedule_conflict_free(monkeypatch):
+    """A live scene changes its conflict graph a few groups at a time (manifolds lose and regain contacts).  The
+    schedule is then edited in place -- vanished groups give their colour back, new groups are coloured by
+    Jones-Plassmann rounds against the kept colour masks -- instead of being recoloured from scratch
+    (stats.schedule_verdict == 3).  Every such step must still be conflict-free and cover exactly the groups
+    that have rows; the simulation must stay as close to the from-scratch variant as two colourings are."""
+    sc = scenes.boxes3(8, 6, 8, height=0.008, jitter=0.001)
+    top = np.nonzero(sc.bodies["position"][:, 1] > 1.1)[0]
+    sc.bodies["velocity"][top, 1] = 0.5
+    sc.bodies["velocity"][top[::4], 3] = 3.0
+    finals = []
+    for incremental in ("1", "0"):
+        monkeypatch.setenv("NB2_INCREMENTAL_COLOURING", incremental)  # read at nb2_create
+        s = setup_device(sc)
+        verdicts = []
+        for k in range(40):
+            s.generate_manifolds()
+            s.step(COL)
+            st = s.get_stats()
+            verdicts.append(int(st["schedule_verdict"]))
+            assert int(st["non_finite"]) == 0
+            phase, a, b = s.download_schedule()
+            ok = phase >= 0
+            keys = np.concatenate([phase[ok & (a >= 0)].astype(np.int64) * s.n_bodies + a[ok & (a >= 0)],
+                                   phase[ok & (b >= 0)].astype(np.int64) * s.n_bodies + b[ok & (b >= 0)]])
+            assert len(np.unique(keys)) == len(keys), (incremental, k, verdicts[-1])
+            m, _ = s.download_manifolds()
+            dyn = sc.bodies["status"] == abi.BODY_DYNAMIC
+            has_rows = (m["num_contacts"] > 0) & (dyn[m["body1"]] | dyn[m["body2"]])
+            assert int(ok.sum()) == int(has_rows.sum()), (incremental, k)
+        finals.append((s.download_body_states(), verdicts, int(st["n_phases_velocity"])))
+        print("incremental=%s verdicts: %s colours at the end: %d" % (incremental, "".join(str(v) for v in verdicts), finals[-1][2]))
+    assert 3 in finals[0][1] and 3 not in finals[1][1]
+    assert finals[0][1].count(1) < finals[1][1].count(1)
+    assert finals[0][2] <= finals[1][2] + 4        # editing in place may cost a few colours, not many
+    settled = sc.bodies["position"][:, 1] < 1.0     # the layers that stay put
+    assert np.abs(finals[0][0]["position"][settled, :3] - finals[1][0]["position"][settled, :3]).max() < 5e-3
+
+
 def test_config2_full_size_pair_and_contact_counts():
     """BASELINE config 2: 296 000 pairs / manifolds, 1 184 000 contacts, produced on the device."""
     sc = scenes.boxes3(50, 40, 50)

@@ -483,6 +483,93 @@ def test_staged_and_register_pipelined_kernels_agree(monkeypatch):
     assert int(s0["non_finite"]) == 0 and int(s1["non_finite"]) == 0
 
 
+@pytest.mark.parametrize("scene_name", ["pile", "pyramid_flipped", "chains", "falling"])
+def test_position_skip_is_exact(scene_name, monkeypatch):
+    """The staged position kernel skips a contact group that found nothing to correct at its last visit and
+    whose bodies have not been displaced since (the evaluation is a pure function of the two poses).  That
+    must change nothing, bit for bit, against sweeping every group every iteration (NB2_POS_SKIP=0): settling
+    piles (most groups clean), a mixed joint + contact scene, and boxes dropping onto each other."""
+    if scene_name == "pile":
+        sc, gen = scenes.boxes3(8, 10, 8), None
+    elif scene_name == "pyramid_flipped":
+        sc, gen = scenes.pyramid3(16), None
+    elif scene_name == "chains":
+        sc = scenes.joint_chains(24, 6, kind="mixed", with_ground_collider=True, ground_y=-0.22, pitch=6.0)
+        gen = scenes.ContactGenerator(sc, search=0.0)
+    else:
+        sc, gen = scenes.boxes3(6, 5, 6, height=0.008, jitter=0.001), None
+        sc.bodies["velocity"][1:, 1] = -0.8
+    if gen is None:
+        gen = scenes.ContactGenerator(sc, flip_fraction=0.5 if scene_name == "pyramid_flipped" else 0.0)
+    p = abi.default_params()
+    p["max_position_iterations"] = 6
+    outs = []
+    for skip in ("1", "0"):
+        monkeypatch.setenv("NB2_POS_SKIP", skip)  # read at nb2_create
+        s = new_solver()
+        s.set_params(p)
+        s.upload_bodies(sc.bodies)
+        if len(sc.joints):
+            s.upload_joints(sc.joints)
+        for k in range(12):
+            st = s.download_body_states()
+            m, c = gen.generate(st["position"])
+            s.upload_manifolds(m, c)
+            s.step(COL)
+        outs.append(s.download_body_states())
+        assert int(s.get_stats()["non_finite"]) == 0
+    assert np.array_equal(outs[0]["position"], outs[1]["position"])
+    assert np.array_equal(outs[0]["velocity"], outs[1]["velocity"])
+    assert not np.array_equal(outs[0]["position"], sc.bodies["position"])
+
+
+@pytest.mark.parametrize("scene_name", ["pile", "ragged_mixed", "plate"])
+def test_bulk_copy_velocity_kernel_matches_staged_bitwise(scene_name, monkeypatch):
+    """NB2_VELOCITY_KERNEL=3 streams the rows with cp.async.bulk + mbarriers, one elected lane per warp, the warp
+    walking its 32 groups in lockstep; =2 (default) with one cp.async ring per thread.  Same schedule, same
+    arithmetic, same translation unit: identical bits.  Scenes: a pile (12 rows per group), joints + ragged
+    manifolds (3 to 12 rows per group inside one warp, partial warps), a 101-colour schedule (phases of one group)."""
+    if scene_name == "pile":
+        sc = scenes.boxes3(10, 8, 10)
+        gen = scenes.ContactGenerator(sc)
+    elif scene_name == "ragged_mixed":
+        sc = scenes.joint_chains(40, 6, kind="mixed", with_ground_collider=True, ground_y=-0.22, pitch=0.9)
+        gen = scenes.ContactGenerator(sc)
+    else:
+        sc = _plate_scene(10, 10)
+        gen = scenes.ContactGenerator(sc, search=4.0)
+    m, c = gen.generate()
+    if scene_name == "ragged_mixed":  # drop contacts so that groups of one warp have 3, 6, 9 and 12 rows
+        keep = np.ones(len(c), bool)
+        for i in range(len(m)):
+            f = int(m["first_contact"][i])
+            keep[f:f + (i % 4)] = False
+        nc = np.array([keep[int(f):int(f) + int(n)].sum() for f, n in zip(m["first_contact"], m["num_contacts"])])
+        m = m.copy()
+        m["num_contacts"] = nc
+        m["first_contact"] = np.concatenate([[0], np.cumsum(nc)[:-1]])
+        c = c[keep].copy()
+    outs = []
+    for variant in ("2", "3"):
+        monkeypatch.setenv("NB2_VELOCITY_KERNEL", variant)  # read at nb2_create
+        s = new_solver()
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+        if len(sc.joints):
+            s.upload_joints(sc.joints)
+        for _ in range(6):
+            s.upload_manifolds(m, c)
+            s.step(COL)
+        st = s.get_stats()
+        assert int(st["non_finite"]) == 0
+        outs.append((s.download_body_states(), s.download_contact_impulses(), int(st["n_phases_velocity"])))
+    assert outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][0]["position"], outs[1][0]["position"])
+    assert np.array_equal(outs[0][0]["velocity"], outs[1][0]["velocity"])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.abs(outs[0][1]).max() > 0
+
+
 def test_step_ccd_reference_order_matches_oracle():
     """nb2_step_ccd = MoreauJeanSolver::step_ccd (moreau_jean_solver.rs:94-127): position resolution before
     velocity resolution, no impulse caching.  Three regular steps warm the cache, then a CCD sub-step with
