@@ -412,6 +412,45 @@ def run_b200(args, rank, world, local_rank):
             for _ in range(14):  # back to the refined cached schedule
                 solver.step(mode)
 
+        # ---------------- the same pile as a live simulation: contacts re-produced on the device from the current
+        # poses every step, so the conflict graph changes whenever a manifold gains or loses its contacts
+        live = None
+        if mode == abi.MODE_COLOURED:
+            for _ in range(3):
+                solver.generate_manifolds()
+                solver.step(mode)
+            barrier()
+            v0 = torch.cuda.Event(enable_timing=True)
+            v1 = torch.cuda.Event(enable_timing=True)
+            v0.record(stream)
+            for _ in range(args.steps):
+                solver.generate_manifolds()
+                solver.step(mode)
+            v1.record(stream)
+            barrier()
+            live_ms = v0.elapsed_time(v1) / args.steps
+            names = ["cached", "from_scratch", "refined", "edited_in_place"]
+            hist = dict.fromkeys(names, 0)
+            solver.enable_timers(True)
+            lacc = {}
+            n_l = min(args.steps, 20)
+            for _ in range(n_l):
+                solver.generate_manifolds()
+                solver.step(mode)
+                for k, v in solver.get_timers().items():
+                    lacc[k] = lacc.get(k, 0.0) + v / n_l
+                hist[names[int(solver.get_stats()["schedule_verdict"])]] += 1
+            solver.enable_timers(False)
+            live = {"ms_per_step": live_ms, "includes": "nb2_generate_manifolds + nb2_step per step",
+                    "schedule_verdicts_next_steps": hist, "stage_ms_next_steps": lacc,
+                    "contacts_now": int(solver.download_manifolds()[0]["num_contacts"].sum())}
+            # back to the rest pose and the timed contact set for the end-to-end loops
+            solver.upload_body_states(rest)
+            solver.generate_manifolds()
+            for _ in range(5):
+                solver.step(mode)
+                solver.upload_body_states(rest)
+
         # ---------------- end to end through the C ABI with host buffers
         e2e = None
         variants = {}
@@ -539,6 +578,7 @@ def run_b200(args, rank, world, local_rank):
                                              "frac": ab["position_kernel"] / (pk_ms * 1e-3) / 1e9 / peak if pk_ms > 0 else None}},
             "stage_ms": timers,
             "uncached_ms_per_step": uncached_ms,
+            "live_simulation": live,
             "phases": {"velocity": int(stats["n_phases_velocity"]), "position": int(stats["n_phases_position"])},
             "residual_max": float(stats["residual_max"]), "max_penetration": float(stats["max_penetration"]),
             "kinetic_energy": float(stats["kinetic_energy"]), "settle_steps": args.settle,

@@ -966,6 +966,12 @@ int launch_position_solve_staged(Context* ctx, const SchedDev& sd_in, const PosA
     void* args[] = {&sd, &A, &joints, &phdr, &gstride, &prow, &pstride, &P, &iters, &E, &rows_div, &bar, &gstamp, &movedp, &vbase, &skip};
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_position_solve_staged, dim3(blocks), dim3(tpb), args, smem, ctx->stream));
     ctx->launches++;
+    if (getenv("NB2_DEBUG_POS")) {  // developer knob: the first sweep's verdict (clean / evaluated groups)
+        unsigned int v[4] = {0, 0, 0, 0};
+        cudaMemcpyAsync(v, ctx->barrier.p, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "position solve: %u of %u contact groups clean in the first sweep\n", v[2], v[3]);
+    }
     return NB2_OK;
 }
 

@@ -23,6 +23,19 @@ pub const NB2_GEOM_POINT: u8 = 0;
 pub const NB2_GEOM_LINE: u8 = 1;
 pub const NB2_GEOM_PLANE: u8 = 2;
 
+pub const NB2_JOINT_BALL: u32 = 0;
+pub const NB2_JOINT_REVOLUTE: u32 = 1;
+pub const NB2_JOINT_PRISMATIC: u32 = 2;
+pub const NB2_JOINT_UNIVERSAL: u32 = 3;
+pub const NB2_JOINT_PLANAR: u32 = 4;
+pub const NB2_JOINT_RECTANGULAR: u32 = 5;
+pub const NB2_JOINT_PIN_SLOT: u32 = 6;
+pub const NB2_JOINT_CYLINDRICAL: u32 = 7;
+pub const NB2_JOINT_FIXED: u32 = 8;
+pub const NB2_JOINT_CARTESIAN: u32 = 9;
+pub const NB2_JOINT_FLAG_MIN_OFFSET: u32 = 1;
+pub const NB2_JOINT_FLAG_MAX_OFFSET: u32 = 2;
+
 pub const NB2_MODE_REFERENCE_ORDER: i32 = 0;
 pub const NB2_MODE_COLOURED: i32 = 1;
 

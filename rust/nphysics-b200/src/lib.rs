@@ -1,15 +1,27 @@
 //! `B200MoreauJeanSolver`: same `step` signature as `nphysics3d::solver::MoreauJeanSolver`
 //! (src/solver/moreau_jean_solver.rs:47-61); the body marshals the borrowed inputs into the flat
 //! records of `include/nphysics_b200.h` and calls the C ABI.  NOT compiled in the build environment
-//! (no rustc) -- see ../README.md.
+//! (no rustc) -- see ../README.md.  Everything the C ABI needs is marshalled here:
+//!
+//!   bodies     every field of `nb2_body` (mass properties, damping, velocity caps, kinematic dofs,
+//!              external forces, gravity flag); the whole set is re-uploaded only when a body's
+//!              `update_status()` reports more than a pose / velocity change or the set itself changed --
+//!              otherwise only the touched poses and velocities go up (`nb2_upload_body_states`)
+//!   manifolds  `nb2_manifold` + `nb2_contact` from ncollide's manifolds; when the contact set kept its
+//!              shape since the last step only the 40-byte per-step part travels (`nb2_update_contacts`)
+//!   joints     through `joints::B200Joint` (ten constraint types, cached impulses and `broken` both ways)
+//!   results    poses and velocities written back into the bodies, impulses / broken flags into the joints
+pub mod joints;
+
+use joints::B200Joint;
 use nalgebra as na;
 use ncollide3d::query::ContactKinematic;
-use ncollide3d::shape::FeatureId;
 use nphysics3d::counters::Counters;
 use nphysics3d::detection::ColliderContactManifold;
 use nphysics3d::joint::JointConstraintSet;
 use nphysics3d::material::{Material, MaterialContext, MaterialsCoefficientsTable};
-use nphysics3d::object::{Body, BodyHandle, BodySet, BodyStatus, ColliderAnchor, ColliderHandle, ColliderSet};
+use nphysics3d::object::{Body, BodyHandle, BodyPart, BodySet, BodyStatus, BodyUpdateStatus, ColliderAnchor, ColliderHandle,
+                         ColliderSet, RigidBody};
 use nphysics3d::solver::IntegrationParameters;
 use nphysics_b200_sys as sys;
 use std::collections::HashMap;
@@ -23,8 +35,21 @@ pub struct B200MoreauJeanSolver<Handle: BodyHandle, CollHandle: ColliderHandle> 
     states: Vec<sys::nb2_body_state>,
     manifolds: Vec<sys::nb2_manifold>,
     contacts: Vec<sys::nb2_contact>,
+    updates: Vec<sys::nb2_contact_update>,
+    /// (body1, body2, first_contact, num_contacts) + contact ids of the last full upload
+    uploaded_shape: Vec<(i32, i32, u32, u32)>,
+    uploaded_ids: Vec<u64>,
     joints: Vec<sys::nb2_joint>,
+    mode: i32,
     _marker: std::marker::PhantomData<CollHandle>,
+}
+
+fn check(ctx: *mut sys::nb2_context, rc: i32) {
+    // the reference's step has no error channel: invariants panic (moreau_jean_solver.rs:147-150)
+    if rc != sys::NB2_OK {
+        let msg = unsafe { std::ffi::CStr::from_ptr(sys::nb2_last_error(ctx)) };
+        panic!("nphysics-b200: {}", msg.to_string_lossy());
+    }
 }
 
 impl<Handle: BodyHandle, CollHandle: ColliderHandle> B200MoreauJeanSolver<Handle, CollHandle> {
@@ -36,8 +61,57 @@ impl<Handle: BodyHandle, CollHandle: ColliderHandle> B200MoreauJeanSolver<Handle
             return Err(msg.to_string_lossy().into_owned());
         }
         Ok(Self { ctx, gravity: [gravity.x, gravity.y, gravity.z], index_of: HashMap::new(), handles: vec![],
-                  bodies: vec![], states: vec![], manifolds: vec![], contacts: vec![], joints: vec![],
+                  bodies: vec![], states: vec![], manifolds: vec![], contacts: vec![], updates: vec![],
+                  uploaded_shape: vec![], uploaded_ids: vec![], joints: vec![], mode: sys::NB2_MODE_COLOURED,
                   _marker: std::marker::PhantomData })
+    }
+
+    /// `NB2_MODE_REFERENCE_ORDER` replays the reference's sequential sweep (verification);
+    /// `NB2_MODE_COLOURED` (default) is the production mode.
+    pub fn set_mode(&mut self, mode: i32) { self.mode = mode; }
+
+    fn body_record(b: &dyn Body<f32>) -> sys::nb2_body {
+        let mut rec: sys::nb2_body = unsafe { std::mem::zeroed() };
+        rec.position[6] = 1.0;
+        rec.jacobian_mask = [1.0; 6];
+        rec.max_linear_velocity = f32::MAX;
+        rec.max_angular_velocity = f32::MAX;
+        rec.status = match b.status() {
+            BodyStatus::Disabled => sys::NB2_BODY_DISABLED,
+            BodyStatus::Static => sys::NB2_BODY_STATIC,
+            BodyStatus::Dynamic => sys::NB2_BODY_DYNAMIC,
+            BodyStatus::Kinematic => sys::NB2_BODY_KINEMATIC,
+        };
+        if let Some(rb) = b.downcast_ref::<RigidBody<f32>>() {
+            let p = rb.position();
+            rec.position = [p.translation.x, p.translation.y, p.translation.z,
+                            p.rotation.i, p.rotation.j, p.rotation.k, p.rotation.w];
+            let v = rb.velocity();
+            rec.velocity = [v.linear.x, v.linear.y, v.linear.z, v.angular.x, v.angular.y, v.angular.z];
+            let com = rb.local_center_of_mass();           // BodyPart (rigid_body.rs:928)
+            rec.local_com = [com.x, com.y, com.z];
+            let inertia = rb.local_inertia();              // Inertia3 { linear, angular } (rigid_body.rs:913)
+            rec.mass = inertia.linear;
+            for r in 0..3 { for c in 0..3 { rec.local_inertia[3 * r + c] = inertia.angular[(r, c)]; } }
+            rec.linear_damping = rb.linear_damping();
+            rec.angular_damping = rb.angular_damping();
+            rec.max_linear_velocity = rb.max_linear_velocity();
+            rec.max_angular_velocity = rb.max_angular_velocity();
+            // jacobian_mask: 0 on kinematic dofs (rigid_body.rs:105-121)
+            let (kt, kr) = (rb.kinematic_translations(), rb.kinematic_rotations());
+            for k in 0..3 {
+                rec.jacobian_mask[k] = if kt[k] { 0.0 } else { 1.0 };
+                rec.jacobian_mask[3 + k] = if kr[k] { 0.0 } else { 1.0 };
+            }
+            // external forces: `RigidBody::external_forces` is private (rigid_body.rs:36); the accessor added by
+            // the in-crate patch returns the accumulated Force3
+            let f = rb.b200_external_forces();
+            rec.external_forces = [f.linear.x, f.linear.y, f.linear.z, f.angular.x, f.angular.y, f.angular.z];
+            if b.gravity_enabled() { rec.flags |= sys::NB2_BODY_FLAG_GRAVITY; }
+        } else {
+            rec.status = sys::NB2_BODY_STATIC; // Ground (ground.rs) and body kinds outside SURVEY section 8 act as ground
+        }
+        rec
     }
 
     /// Perform one step of the time-stepping scheme (drop-in for MoreauJeanSolver::step).
@@ -45,50 +119,74 @@ impl<Handle: BodyHandle, CollHandle: ColliderHandle> B200MoreauJeanSolver<Handle
         &mut self,
         _counters: &mut Counters,
         bodies: &mut dyn BodySet<f32, Handle = Handle>,
-        colliders: &Colliders,
-        _joints: &mut Constraints,
+        _colliders: &Colliders,
+        joints: &mut Constraints,
         manifolds: &[ColliderContactManifold<f32, Handle, CollHandle>],
-        _island: &[Handle],
-        _island_joints: &[Constraints::Handle],
+        island: &[Handle],
+        island_joints: &[Constraints::Handle],
         parameters: &IntegrationParameters<f32>,
         coefficients: &MaterialsCoefficientsTable<f32>,
     ) where
         Colliders: ColliderSet<f32, Handle, Handle = CollHandle>,
         Constraints: JointConstraintSet<f32, Handle>,
+        Constraints::JointConstraint: B200Joint<Handle>,
     {
-        let _ = colliders;
-        // 1. bodies -> nb2_body records (index = insertion order); re-uploaded when any update flag is set
-        self.handles.clear();
-        self.bodies.clear();
-        self.index_of.clear();
+        let ctx = self.ctx;
+        // ---- 1. bodies.  The uploaded set is every body of the BodySet in iteration order (bodies outside `island`
+        // -- sleeping, static -- must still be addressable by manifolds); a change of the set or of anything but
+        // pose / velocity re-uploads it, otherwise only edited poses / velocities travel.
+        let mut same_set = true;
+        let mut heavy_change = false;
+        let mut k = 0usize;
         bodies.foreach(&mut |h, b: &dyn Body<f32>| {
-            let rb = b.downcast_ref::<nphysics3d::object::RigidBody<f32>>();
-            let mut rec: sys::nb2_body = unsafe { std::mem::zeroed() };
-            rec.position[6] = 1.0;
-            rec.status = match b.status() {
-                BodyStatus::Disabled => sys::NB2_BODY_DISABLED,
-                BodyStatus::Static => sys::NB2_BODY_STATIC,
-                BodyStatus::Dynamic => sys::NB2_BODY_DYNAMIC,
-                BodyStatus::Kinematic => sys::NB2_BODY_KINEMATIC,
-            };
-            if let Some(rb) = rb {
-                let p = rb.position();
-                rec.position = [p.translation.x, p.translation.y, p.translation.z,
-                                p.rotation.i, p.rotation.j, p.rotation.k, p.rotation.w];
-                let v = rb.velocity();
-                rec.velocity = [v.linear.x, v.linear.y, v.linear.z, v.angular.x, v.angular.y, v.angular.z];
-                // local_com, mass, local_inertia (row-major), damping, caps, jacobian mask, gravity flag ...
-                if b.gravity_enabled() { rec.flags |= sys::NB2_BODY_FLAG_GRAVITY; }
-            } else {
-                rec.status = sys::NB2_BODY_STATIC; // Ground and unsupported body kinds act as ground
+            if k >= self.handles.len() || self.handles[k] != h { same_set = false; }
+            let st = b.update_status();
+            if st.inertia_changed() || st.local_inertia_changed() || st.local_com_changed() || st.damping_changed() || st.status_changed() {
+                heavy_change = true;
             }
-            self.index_of.insert(h, self.bodies.len() as i32);
-            self.handles.push(h);
-            self.bodies.push(rec);
+            k += 1;
         });
-        unsafe { sys::nb2_upload_bodies(self.ctx, self.bodies.as_ptr(), self.bodies.len() as u32); }
+        if k != self.handles.len() { same_set = false; }
+        if !same_set || heavy_change {
+            self.handles.clear();
+            self.bodies.clear();
+            self.index_of.clear();
+            bodies.foreach(&mut |h, b: &dyn Body<f32>| {
+                self.index_of.insert(h, self.bodies.len() as i32);
+                self.handles.push(h);
+                self.bodies.push(Self::body_record(b));
+            });
+            check(ctx, unsafe { sys::nb2_upload_bodies(ctx, self.bodies.as_ptr(), self.bodies.len() as u32) });
+            self.uploaded_shape.clear();
+        } else {
+            // dirty ranges: consecutive bodies whose pose or velocity was edited by the user since the last step
+            let mut i = 0usize;
+            let mut run: Option<(usize, Vec<sys::nb2_body_state>)> = None;
+            let mut flush = |run: &mut Option<(usize, Vec<sys::nb2_body_state>)>| {
+                if let Some((first, st)) = run.take() {
+                    check(ctx, unsafe { sys::nb2_upload_body_states(ctx, st.as_ptr(), first as u32, st.len() as u32) });
+                    check(ctx, unsafe { sys::nb2_synchronize(ctx) });  // `st` is dropped on return
+                }
+            };
+            bodies.foreach(&mut |_h, b: &dyn Body<f32>| {
+                let st = b.update_status();
+                if st.position_changed() || st.velocity_changed() {
+                    let rec = Self::body_record(b);
+                    let s = sys::nb2_body_state { position: rec.position, velocity: rec.velocity };
+                    match run.as_mut() {
+                        Some((_, v)) => v.push(s),
+                        None => run = Some((i, vec![s])),
+                    }
+                } else {
+                    flush(&mut run);
+                }
+                i += 1;
+            });
+            flush(&mut run);
+        }
+        let _ = island; // the device filters by effective status exactly as `island` does (mechanical_world.rs:287-313)
 
-        // 2. manifolds -> nb2_manifold / nb2_contact
+        // ---- 2. manifolds -> nb2_manifold / nb2_contact
         self.manifolds.clear();
         self.contacts.clear();
         for m in manifolds {
@@ -108,7 +206,7 @@ impl<Handle: BodyHandle, CollHandle: ColliderHandle> B200MoreauJeanSolver<Handle
             }
             for c in m.contacts() {
                 if rec.num_contacts == 0 {
-                    // Material::combine is evaluated once per manifold for BasicMaterial pairs
+                    // Material::combine is evaluated once per manifold for BasicMaterial pairs (material.rs:134-177)
                     let ctx1 = MaterialContext::new(m.collider1.shape(), m.collider1.position(), c, true);
                     let ctx2 = MaterialContext::new(m.collider2.shape(), m.collider2.position(), c, false);
                     let props = <dyn Material<f32>>::combine(coefficients, m.collider1.material(), ctx1, m.collider2.material(), ctx2);
@@ -128,8 +226,38 @@ impl<Handle: BodyHandle, CollHandle: ColliderHandle> B200MoreauJeanSolver<Handle
             }
             self.manifolds.push(rec);
         }
-        // 3. joints: anchors/axes/cached impulses of each active constraint (per joint type) -> nb2_joint
-        // 4. params + step + 5. write back
+        // the same contacts as last step (ids, order, manifolds): only world1 / world2 / normal / depth go up
+        let same_shape = self.uploaded_shape.len() == self.manifolds.len()
+            && self.uploaded_ids.len() == self.contacts.len()
+            && self.manifolds.iter().zip(self.uploaded_shape.iter())
+                   .all(|(m, s)| (m.body1, m.body2, m.first_contact, m.num_contacts) == *s)
+            && self.contacts.iter().zip(self.uploaded_ids.iter()).all(|(c, id)| c.key == *id);
+        if same_shape {
+            self.updates.clear();
+            self.updates.extend(self.contacts.iter().map(|c| sys::nb2_contact_update {
+                world1: c.world1, world2: c.world2, normal: c.normal, depth: c.depth }));
+            check(ctx, unsafe { sys::nb2_update_contacts(ctx, self.updates.as_ptr(), self.updates.len() as u32) });
+        } else {
+            check(ctx, unsafe { sys::nb2_upload_manifolds(ctx, self.manifolds.as_ptr(), self.manifolds.len() as u32,
+                                                          self.contacts.as_ptr(), self.contacts.len() as u32) });
+            self.uploaded_shape = self.manifolds.iter().map(|m| (m.body1, m.body2, m.first_contact, m.num_contacts)).collect();
+            self.uploaded_ids = self.contacts.iter().map(|c| c.key).collect();
+        }
+
+        // ---- 3. joints: the active constraints in island_joints order (mechanical_world.rs:274-279)
+        self.joints.clear();
+        {
+            let index_of = &self.index_of;
+            let lookup = |h: Handle| -> i32 { index_of[&h] };
+            for jh in island_joints {
+                if let Some(j) = joints.get(*jh) {
+                    self.joints.push(j.to_record(&lookup));
+                }
+            }
+        }
+        check(ctx, unsafe { sys::nb2_upload_joints(ctx, self.joints.as_ptr(), self.joints.len() as u32) });
+
+        // ---- 4. parameters + step
         let mut p: sys::nb2_params = unsafe { std::mem::zeroed() };
         unsafe { sys::nb2_default_params(&mut p); }
         p.dt = parameters.dt();
@@ -143,26 +271,56 @@ impl<Handle: BodyHandle, CollHandle: ColliderHandle> B200MoreauJeanSolver<Handle
         p.max_stabilization_multiplier = parameters.max_stabilization_multiplier;
         p.max_velocity_iterations = parameters.max_velocity_iterations as u32;
         p.max_position_iterations = parameters.max_position_iterations as u32;
+        p.max_ccd_position_iterations = parameters.max_ccd_position_iterations as u32;
+        p.max_ccd_substeps = parameters.max_ccd_substeps as u32;
         p.gravity = self.gravity;
-        unsafe {
-            sys::nb2_set_params(self.ctx, &p);
-            sys::nb2_upload_manifolds(self.ctx, self.manifolds.as_ptr(), self.manifolds.len() as u32,
-                                      self.contacts.as_ptr(), self.contacts.len() as u32);
-            sys::nb2_step(self.ctx, sys::NB2_MODE_COLOURED);
-            self.states.resize(self.bodies.len(), std::mem::zeroed());
-            sys::nb2_download_body_states(self.ctx, self.states.as_mut_ptr(), 0, self.states.len() as u32);
-        }
+        check(ctx, unsafe { sys::nb2_set_params(ctx, &p) });
+        check(ctx, unsafe { sys::nb2_step(ctx, self.mode) });
+
+        // ---- 5. write back: poses and velocities into the bodies, cached impulses and broken flags into the joints
+        self.states.resize(self.bodies.len(), unsafe { std::mem::zeroed() });
+        check(ctx, unsafe { sys::nb2_download_body_states(ctx, self.states.as_mut_ptr(), 0, self.states.len() as u32) });
         for (h, s) in self.handles.iter().zip(self.states.iter()) {
             if let Some(b) = bodies.get_mut(*h) {
-                if let Some(rb) = b.downcast_mut::<nphysics3d::object::RigidBody<f32>>() {
-                    let q = na::UnitQuaternion::new_unchecked(na::Quaternion::new(s.position[6], s.position[3], s.position[4], s.position[5]));
-                    rb.set_position(na::Isometry3::from_parts(na::Translation3::new(s.position[0], s.position[1], s.position[2]), q));
-                    rb.set_velocity(nphysics3d::algebra::Velocity3::new(
-                        na::Vector3::new(s.velocity[0], s.velocity[1], s.velocity[2]),
-                        na::Vector3::new(s.velocity[3], s.velocity[4], s.velocity[5])));
+                if let Some(rb) = b.downcast_mut::<RigidBody<f32>>() {
+                    if rb.status() == BodyStatus::Dynamic || rb.status() == BodyStatus::Kinematic {
+                        let q = na::UnitQuaternion::new_unchecked(na::Quaternion::new(s.position[6], s.position[3], s.position[4], s.position[5]));
+                        rb.set_position(na::Isometry3::from_parts(na::Translation3::new(s.position[0], s.position[1], s.position[2]), q));
+                        rb.set_velocity(nphysics3d::algebra::Velocity3::new(
+                            na::Vector3::new(s.velocity[0], s.velocity[1], s.velocity[2]),
+                            na::Vector3::new(s.velocity[3], s.velocity[4], s.velocity[5])));
+                    }
+                }
+                // what the device now holds is what the host holds: nothing is dirty (MechanicalWorld::step clears the
+                // flags at the same place, mechanical_world.rs:340-346)
+                b.clear_update_flags();
+            }
+        }
+        if !self.joints.is_empty() {
+            check(ctx, unsafe { sys::nb2_download_joints(ctx, self.joints.as_mut_ptr(), self.joints.len() as u32) });
+            let mut k = 0usize;
+            for jh in island_joints {
+                if let Some(j) = joints.get_mut(*jh) {
+                    j.store_solver_outputs(&self.joints[k]);
+                    k += 1;
                 }
             }
         }
+    }
+
+    /// cuboid piles can leave their narrow phase on the device as well.  Call once with the
+    /// colliders (`nb2_collider` records, `body` = index in BodySet iteration order), then `step_with_device_contacts`
+    /// instead of `step`: no contact data crosses PCIe at all.
+    pub fn use_device_contacts(&mut self, colliders: &[sys::nb2_collider], linear_prediction: f32) -> u32 {
+        let mut n_pairs = 0u32;
+        check(self.ctx, unsafe { sys::nb2_upload_colliders(self.ctx, colliders.as_ptr(), colliders.len() as u32) });
+        check(self.ctx, unsafe { sys::nb2_detect_pairs(self.ctx, linear_prediction, -1.0, 0, &mut n_pairs) });
+        n_pairs
+    }
+
+    pub fn step_with_device_contacts(&mut self) {
+        check(self.ctx, unsafe { sys::nb2_generate_manifolds(self.ctx) });
+        check(self.ctx, unsafe { sys::nb2_step(self.ctx, self.mode) });
     }
 }
 
@@ -194,5 +352,4 @@ fn fill_kinematic(cr: &mut sys::nb2_contact, k: &ContactKinematic<f32>) {
     };
     cr.geom1 = tag(&a1.geometry, &mut cr.dir1);
     cr.geom2 = tag(&a2.geometry, &mut cr.dir2);
-    let _ = FeatureId::Unknown;
 }

