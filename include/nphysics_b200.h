@@ -122,7 +122,8 @@ typedef struct nb2_activation {
  * (SURVEY.md appendix B). */
 typedef enum nb2_kinematic_geom {
     NB2_GEOM_POINT = 0,
-    NB2_GEOM_LINE = 1,  /* accepted, but Line/x pairs yield no position correction */
+    NB2_GEOM_LINE = 1,  /* Line/Line, Line/Point, Point/Line are resolved through their closest points
+                         * (separated branch); Line/Plane, Plane/Line yield none */
     NB2_GEOM_PLANE = 2
 } nb2_kinematic_geom;
 
@@ -363,6 +364,20 @@ int nb2_download_manifolds(nb2_context* ctx, nb2_manifold* out_manifolds, uint32
 /* The active joint set, in island_joints order.  Cached impulses/broken flags
  * in the records seed the device copy. */
 int nb2_upload_joints(nb2_context* ctx, const nb2_joint* joints, uint32_t n_joints);
+/* ContactModel selection (src/solver/contact_model.rs:13-37, MoreauJeanSolver::set_contact_model,
+ * moreau_jean_solver.rs:42-44).  The reference ships two models:
+ *   NB2_CONTACT_SIGNORINI_COULOMB_PYRAMID (default, moreau_jean_solver.rs:29-40): one unilateral normal
+ *     row + two friction-pyramid rows per contact, every contact of a manifold makes rows
+ *     (signorini_coulomb_pyramid_model.rs:56-224);
+ *   NB2_CONTACT_SIGNORINI: frictionless -- the normal row and the position row only, and only for contacts
+ *     with depth + margin1 + margin2 >= 0 (signorini_model.rs:141-150, 200-298); a contact that is
+ *     inactive in a step keeps its cached impulse.
+ * Changing the model drops the impulse cache (the cache belongs to the model object). */
+typedef enum nb2_contact_model {
+    NB2_CONTACT_SIGNORINI_COULOMB_PYRAMID = 0,
+    NB2_CONTACT_SIGNORINI = 1
+} nb2_contact_model;
+int nb2_set_contact_model(nb2_context* ctx, int model);
 /* Drop the contact impulse cache (a fresh ContactModel). */
 int nb2_clear_impulse_cache(nb2_context* ctx);
 

@@ -36,6 +36,9 @@ JOINT_FLAG_MIN_OFFSET, JOINT_FLAG_MAX_OFFSET = 1, 2
 # nb2_step_mode
 MODE_REFERENCE_ORDER, MODE_COLOURED = 0, 1
 
+# nb2_contact_model
+CONTACT_SIGNORINI_COULOMB_PYRAMID, CONTACT_SIGNORINI = 0, 1
+
 f4, u4, i4, u8, u1 = np.float32, np.uint32, np.int32, np.uint64, np.uint8
 
 params_dtype = np.dtype([

@@ -45,7 +45,7 @@ static void release_all(Context* c) {
     c->adj_p.release(); c->cmask.release(); c->best.release(); c->scan_tmp.release(); c->barrier.release();
     c->r_jac.release(); c->r_hdr.release(); c->r_imp.release(); c->p_row.release();
     c->stat_f.release(); c->stat_u.release(); c->flags.release(); c->stage_states.release();
-    c->c_geo.release(); c->bal.release(); c->p_hdr.release(); c->pos_gstamp.release(); c->pos_moved.release();
+    c->c_geo.release(); c->bal.release(); c->p_hdr.release();
     c->true_status.release(); c->isl_labels.release(); c->act.release(); c->cc_parent.release(); c->cc_can.release(); c->wake_list.release();
     c->colliders.release(); c->coll_world.release(); c->np_is_big.release(); c->np_big_off.release(); c->np_par.release();
     c->pair_cnt.release(); c->pair_off.release(); c->grid_count.release(); c->grid_off.release(); c->grid_cursor.release();
@@ -85,7 +85,7 @@ static int check_flags(Context* ctx) {
 // position, velocity, integrate; no impulse caching, no kinematic integration (the CCD driver around it,
 // mechanical_world.rs:561-908, owns those).
 static int do_step_ccd(Context* ctx, int mode) {
-    ctx->step_layout = (mode != NB2_MODE_REFERENCE_ORDER && ctx->contact_layout == 1) ? 1 : 0;
+    ctx->step_layout = (mode != NB2_MODE_REFERENCE_ORDER && ctx->contact_layout == 1 && ctx->contact_model == 0) ? 1 : 0;
     ctx->cur = 1 - ctx->cur;  // assembly warm-starts from the buffer "before cur": point it at the last one written
     NB2_TRY(launch_refresh_dynamics(ctx));
     ctx->max_chunks = (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
@@ -106,7 +106,7 @@ static int do_step_ccd(Context* ctx, int mode) {
 static int do_step(Context* ctx, int mode) {
     const bool ref = mode == NB2_MODE_REFERENCE_ORDER;
     ctx->cur = 1 - ctx->cur;
-    ctx->step_layout = (!ref && ctx->contact_layout == 1) ? 1 : 0;
+    ctx->step_layout = (!ref && ctx->contact_layout == 1 && ctx->contact_model == 0) ? 1 : 0;
     const bool tm = ctx->timers;
     if (tm && !ctx->ev.created) {
         for (int k = 0; k < 12; ++k) NB2_CUDA(ctx, cudaEventCreate(&ctx->ev.e[k]));
@@ -273,7 +273,7 @@ int nb2_create(int device, void* stream, nb2_context** out) {
     // developer knob for A/B measurements of the coloured velocity kernel variants (solver.cuh)
     if (const char* vk = getenv("NB2_VELOCITY_KERNEL")) ctx->velocity_kernel = atoi(vk);
     if (const char* pr = getenv("NB2_POISON_ROWS")) ctx->poison_rows = atoi(pr) != 0;
-    if (const char* ps = getenv("NB2_POS_SKIP")) ctx->pos_skip = atoi(ps) != 0;
+    if (const char* ps = getenv("NB2_POS_EARLY_EXIT")) ctx->pos_early_exit = atoi(ps) != 0;
     if (const char* ic = getenv("NB2_INCREMENTAL_COLOURING")) ctx->incremental_colouring = atoi(ic) != 0;
     if (cudaSetDevice(device) != cudaSuccess) {
         delete h;
@@ -518,6 +518,20 @@ int nb2_upload_joints(nb2_context* h, const nb2_joint* joints, uint32_t n) {
         NB2_TRY(launch_validate_joints(ctx));
         NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return NB2_OK;
+}
+
+int nb2_set_contact_model(nb2_context* h, int model) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (model != NB2_CONTACT_SIGNORINI_COULOMB_PYRAMID && model != NB2_CONTACT_SIGNORINI)
+        return set_error(ctx, NB2_ERR_UNSUPPORTED, "unknown contact model %d (the reference ships two: 0 Signorini-Coulomb pyramid, 1 Signorini)", model);
+    if (model != ctx->contact_model) {
+        ctx->ht_cap[0] = ctx->ht_cap[1] = 0;
+        ctx->imp_n[0] = ctx->imp_n[1] = 0;
+        ctx->vs.cache_valid = false;  // the groups' row counts change
+    }
+    ctx->contact_model = model;
     return NB2_OK;
 }
 

@@ -277,8 +277,26 @@ __device__ __forceinline__ void assemble_contact(const RowOut& out, const BodySi
                                                  const ManifoldConsts& K, const nb2_contact& c, Quat q1, float4 cached,
                                                  const ContactSlots& S, bool compact, float4* c_geo, float4* p_row,
                                                  size_t n_pslots_max, float warmstart_coeff,
-                                                 float restitution_threshold, float inv_dt) {
+                                                 float restitution_threshold, float inv_dt, int model) {
     const size_t slot_n = S.n, slot_t1 = S.t1, slot_t2 = S.t2, pslot = S.p;
+    if (model == NB2_CONTACT_SIGNORINI && !(c.depth + K.margin1 + K.margin2 >= 0.f)) {
+        // SignoriniModel::is_constraint_active (signorini_model.rs:141-150, applied at :230-232): an inactive
+        // contact makes no row at all.  Its slot holds a NONE row whose impulse is the cached one, so that the
+        // caching pass carries it to the next step (the model's cache never forgets, :285-297), and a position
+        // row no kinematic matches.
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t S_ = out.n_slots_max, P_ = n_pslots_max;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out.jac[(size_t)k * S_ + slot_n] = z;
+        out.jac[4 * S_ + slot_n] = make_float4(0.f, 0.f, __int_as_float(NB2_ROW_NONE), 0.f);
+        out.hdr[slot_n] = z;
+        out.imp[slot_n] = cached.x;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) p_row[(size_t)k * P_ + pslot] = z;
+        p_row[2 * P_ + pslot] = make_float4(0.f, 0.f, 0.f, __int_as_float(3));  // geometry tags outside {point, line, plane}
+        p_row[3 * P_ + pslot] = make_float4(0.f, 0.f, 0.f, __int_as_float(3));
+        return;
+    }
     const Vec3 n = mk3(c.normal[0], c.normal[1], c.normal[2]);
     const Vec3 world1 = mk3(c.world1[0], c.world1[1], c.world1[2]);
     const Vec3 world2 = mk3(c.world2[0], c.world2[1], c.world2[2]);
@@ -297,6 +315,7 @@ __device__ __forceinline__ void assemble_contact(const RowOut& out, const BodySi
         write_row(out, slot_n, J1, J2, W1, W2, rhs, r, 0.f, NB2_F32_MAX, NB2_ROW_UNILATERAL, 0,
                   cached.x * warmstart_coeff);
 
+    if (model != NB2_CONTACT_SIGNORINI) {
     // ---- friction pyramid rows (signorini_coulomb_pyramid_model.rs:131-216)
     Vec3 t1, t2;
     tangent_basis(n, &t1, &t2);
@@ -322,6 +341,7 @@ __device__ __forceinline__ void assemble_contact(const RowOut& out, const BodySi
         c_geo[4 * P_ + pslot] = make_float4(cached.x * warmstart_coeff, cached.y * warmstart_coeff,
                                             cached.z * warmstart_coeff, 1.f);
     }
+    }
 
     // ---- position row (signorini_model.rs:153-197)
     const Vec3 normal1 = quat_inv_rotate(q1, n);
@@ -345,7 +365,8 @@ __global__ void __launch_bounds__(TPB, NB2_ASMG_MINBLOCKS) k_assemble_groups(
     unsigned int nC, const nb2_manifold* __restrict__ manifolds, const nb2_contact* __restrict__ contacts,
     const unsigned int* __restrict__ chunk_base, const unsigned int* __restrict__ chunk_manifold, BodyArrays B,
     SchedView vs, RowOut out, float4* p_row, size_t n_pslots_max, float4* p_hdr, size_t n_ghdr_max, float4* c_geo,
-    ImpulseCacheView cache, float warmstart_coeff, float restitution_threshold, float inv_dt, int compact_layout) {
+    ImpulseCacheView cache, float warmstart_coeff, float restitution_threshold, float inv_dt, int compact_layout,
+    int model) {
     const size_t T = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int np = vs.hdr->n_phases;
     if (np == 0 || T >= (size_t)vs.ph_gbase[np]) return;
@@ -403,9 +424,9 @@ __global__ void __launch_bounds__(TPB, NB2_ASMG_MINBLOCKS) k_assemble_groups(
         S.p = pbase + (size_t)lcc * cnt;
         S.t1 = rb + (size_t)(2 * lcc) * cnt;
         S.t2 = rb + (size_t)(2 * lcc + 1) * cnt;
-        S.n = rb + (size_t)(2 * ncc + lcc) * cnt;
+        S.n = model == NB2_CONTACT_SIGNORINI ? rb + (size_t)lcc * cnt : rb + (size_t)(2 * ncc + lcc) * cnt;
         assemble_contact(out, s1, s2, K, c, q1, cached, S, compact, c_geo, p_row, n_pslots_max, warmstart_coeff,
-                         restitution_threshold, inv_dt);
+                         restitution_threshold, inv_dt, model);
         cur = nxt;
     }
 }
@@ -415,7 +436,8 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
     const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
     const unsigned int* __restrict__ chunk_base, BodyArrays B, SchedView vs, SchedView ps, RowOut out, float4* p_row,
-    size_t n_pslots_max, ImpulseCacheView cache, float warmstart_coeff, float restitution_threshold, float inv_dt) {
+    size_t n_pslots_max, ImpulseCacheView cache, float warmstart_coeff, float restitution_threshold, float inv_dt,
+    int model) {
     const unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= nC) return;
     const unsigned int m = c_manifold[ci];
@@ -439,12 +461,15 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     }
     const size_t item_f = (size_t)nJ + chunk, item_n = (size_t)nJ + maxc + chunk;
     ContactSlots S;
-    S.t1 = vs.row_slot(item_f, 2 * lcc);
-    S.t2 = vs.row_slot(item_f, 2 * lcc + 1);
+    S.t1 = S.t2 = 0;
+    if (model != NB2_CONTACT_SIGNORINI) {  // the frictionless model schedules no friction group
+        S.t1 = vs.row_slot(item_f, 2 * lcc);
+        S.t2 = vs.row_slot(item_f, 2 * lcc + 1);
+    }
     S.n = vs.row_slot(item_n, lcc);
     S.p = ps.pos_slot((size_t)nJ + chunk, lcc);
     assemble_contact(out, s1, s2, manifold_consts(mf), c, f4_quat(B.pos_q[mf.body1]), cached, S, false, nullptr, p_row,
-                     n_pslots_max, warmstart_coeff, restitution_threshold, inv_dt);
+                     n_pslots_max, warmstart_coeff, restitution_threshold, inv_dt, model);
 }
 
 // ---------------------------------------------------------------- joints
@@ -637,7 +662,7 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
     const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
     const unsigned int* __restrict__ chunk_base, const int* __restrict__ status, SchedView vs,
     const float* __restrict__ r_imp, const float4* __restrict__ c_geo, size_t n_pslots_max, float4* imp_cur,
-    unsigned long long* ckey_cur, int compact_layout) {
+    unsigned long long* ckey_cur, int compact_layout, int model) {
     unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= nC) return;
     const unsigned int m = c_manifold[ci];
@@ -656,6 +681,9 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
         if (compact_layout) {
             const float4 q = c_geo[4 * n_pslots_max + vs.pos_slot((size_t)nJ + chunk, lcc)];
             v = make_float4(q.x, q.y, q.z, 0.f);
+        } else if (model == NB2_CONTACT_SIGNORINI) {  // one row per contact (an inactive contact's slot carries its old impulse)
+            v.x = r_imp[mode == NB2_MODE_COLOURED ? vs.row_slot((size_t)nJ + chunk, lcc)
+                                                  : vs.row_slot((size_t)nJ + maxc + chunk, lcc)];
         } else if (mode == NB2_MODE_COLOURED) {
             size_t item = (size_t)nJ + chunk;
             v.x = r_imp[vs.row_slot(item, 2 * ncc + lcc)];
@@ -678,7 +706,8 @@ __global__ void __launch_bounds__(TPB) k_warm_fixup(
     int mode, unsigned int nC, unsigned int nJ, unsigned int maxc, const nb2_manifold* __restrict__ manifolds,
     const nb2_contact* __restrict__ contacts, const unsigned int* __restrict__ c_manifold,
     const unsigned int* __restrict__ chunk_base, const int* __restrict__ status, SchedView vs, float* r_imp,
-    float4* c_geo, size_t n_pslots_max, ImpulseCacheView cache, float warmstart_coeff, int compact_layout) {
+    float4* c_geo, size_t n_pslots_max, ImpulseCacheView cache, float warmstart_coeff, int compact_layout, int model,
+    const float4* __restrict__ r_kind /* jac plane 4 */) {
     if (*cache.need_hash == 0u) return;
     unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= nC) return;
@@ -698,6 +727,10 @@ __global__ void __launch_bounds__(TPB) k_warm_fixup(
     const float wn = v.x * warmstart_coeff, wt1 = v.y * warmstart_coeff, wt2 = v.z * warmstart_coeff;
     if (compact_layout) {
         c_geo[4 * n_pslots_max + vs.pos_slot((size_t)nJ + chunk, lcc)] = make_float4(wn, wt1, wt2, 1.f);
+    } else if (model == NB2_CONTACT_SIGNORINI) {
+        const size_t slot = mode == NB2_MODE_COLOURED ? vs.row_slot((size_t)nJ + chunk, lcc) : vs.row_slot((size_t)nJ + maxc + chunk, lcc);
+        // an inactive contact (NONE row) carries the raw cached impulse, an active one is warm-started
+        r_imp[slot] = __float_as_int(r_kind[slot].z) == NB2_ROW_NONE ? v.x : wn;
     } else if (mode == NB2_MODE_COLOURED) {
         size_t item = (size_t)nJ + chunk;
         r_imp[vs.row_slot(item, 2 * ncc + lcc)] = wn;
@@ -822,13 +855,13 @@ int launch_assemble(Context* ctx, int mode) {
             k_assemble_contacts<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
                 ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p, ctx->c_manifold.p,
                 ctx->chunk_base.p, body_arrays(ctx), vs, ps, row_out(ctx), ctx->p_row.p, ctx->n_pslots_max, cache,
-                ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt);
+                ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt, ctx->contact_model);
         } else {  // one thread per group slot in ELL order
             k_assemble_groups<<<nblk(n_items), TPB, 0, ctx->stream>>>(
                 ctx->n_contacts, ctx->manifolds.p, ctx->contacts.p, ctx->chunk_base.p, ctx->chunk_manifold.p,
                 body_arrays(ctx), vs, row_out(ctx), ctx->p_row.p, ctx->n_pslots_max, ctx->p_hdr.p, ctx->n_ghdr_max,
                 ctx->c_geo.p, cache, ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt,
-                ctx->step_layout);
+                ctx->step_layout, ctx->contact_model);
         }
         ctx->launches++;
         if (cache.ht_cap) {  // all three return at once unless a contact missed the fast path
@@ -839,7 +872,7 @@ int launch_assemble(Context* ctx, int mode) {
             k_warm_fixup<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
                 mode, ctx->n_contacts, ctx->n_joints, (unsigned int)maxc, ctx->manifolds.p, ctx->contacts.p, ctx->c_manifold.p,
                 ctx->chunk_base.p, ctx->b_status.p, vs, ctx->r_imp.p, ctx->c_geo.p, ctx->n_pslots_max, cache,
-                ctx->params.warmstart_coeff, ctx->step_layout);
+                ctx->params.warmstart_coeff, ctx->step_layout, ctx->contact_model, ctx->r_jac.p + 4 * ctx->n_slots_max);
             ctx->launches += 3;
         }
     }
@@ -868,7 +901,7 @@ int launch_cache_impulses(Context* ctx, int mode) {
         k_cache_contact_impulses<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
             mode, ctx->n_contacts, ctx->n_joints, (unsigned int)ctx->max_chunks, ctx->manifolds.p, ctx->contacts.p,
             ctx->c_manifold.p, ctx->chunk_base.p, ctx->b_status.p, vs, ctx->r_imp.p, ctx->c_geo.p, ctx->n_pslots_max,
-            ctx->imp[cur].p, ctx->ckey[cur].p, ctx->step_layout);
+            ctx->imp[cur].p, ctx->ckey[cur].p, ctx->step_layout, ctx->contact_model);
         ctx->launches++;
     }
     if (ctx->n_joints) {

@@ -222,7 +222,8 @@ __device__ __forceinline__ int joint_num_position(const nb2_joint& j) {
 //   [0, nJ) joints | [nJ, nJ+maxc) contact chunks (coloured: all rows; reference: friction rows)
 //   | [nJ+maxc, nJ+2maxc) reference order only: normal rows of the chunks
 // Position schedule (reference order only): [0,nJ) joints | [nJ, nJ+maxc) chunks.
-__global__ void k_build_items(int mode, int compact, int position, unsigned int nJ, unsigned int maxc,
+// rpc = velocity rows per contact: 3 (normal + two friction rows) or 1 (frictionless SignoriniModel)
+__global__ void k_build_items(int mode, int compact, int rpc, int position, unsigned int nJ, unsigned int maxc,
                               const nb2_joint* __restrict__ joints, const nb2_manifold* __restrict__ manifolds,
                               const unsigned int* __restrict__ chunk_base, unsigned int nM,
                               const unsigned int* __restrict__ chunk_manifold, const int* __restrict__ status,
@@ -274,11 +275,13 @@ __global__ void k_build_items(int mode, int compact, int position, unsigned int 
                     // compact contact groups (c_geo planes) own no generic row slots; their
                     // contact count travels in bits 4..7
                     type = NB2_ITEM_CONTACTS;
-                    nrows = compact ? (ncc << 4) : 3 * ncc;
+                    nrows = compact ? (ncc << 4) : rpc * ncc;
                 } else if (!second) {
-                    type = NB2_ITEM_FRICTION;
-                    nrows = 2 * ncc;
-                    key = ((ground ? 3ull : 2ull) << 40) | k;
+                    if (rpc == 3) {  // the frictionless model has no friction bucket
+                        type = NB2_ITEM_FRICTION;
+                        nrows = 2 * ncc;
+                        key = ((ground ? 3ull : 2ull) << 40) | k;
+                    }
                 } else {
                     type = NB2_ITEM_NORMAL;
                     nrows = ncc;
@@ -350,7 +353,7 @@ int launch_build_items(Context* ctx, int mode) {
     NB2_TRY(reserve_sched(ctx, &ctx->vs, n_items, ref ? n_items : NB2_MAX_COLOURS));
     if (n_items) {
         k_build_items<<<nblk(n_items), TPB, 0, ctx->stream>>>(
-            mode, ctx->step_layout, 0, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
+            mode, ctx->step_layout, ctx->contact_model == 1 ? 1 : 3, 0, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
             ctx->chunk_manifold.p, ctx->b_status.p, ctx->vs.it_a.p, ctx->vs.it_b.p, ctx->vs.it_nrows.p,
             ctx->vs.it_type.p, ctx->vs.it_src.p, ctx->vs.it_key.p, ctx->vs.it_b1.p, ctx->vs.it_b2.p, n_items);
         ctx->launches++;
@@ -360,7 +363,7 @@ int launch_build_items(Context* ctx, int mode) {
         NB2_TRY(reserve_sched(ctx, &ctx->ps, np, np));
         if (np) {
             k_build_items<<<nblk(np), TPB, 0, ctx->stream>>>(
-                mode, ctx->step_layout, 1, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
+                mode, ctx->step_layout, ctx->contact_model == 1 ? 1 : 3, 1, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
                 ctx->chunk_manifold.p, ctx->b_status.p, ctx->ps.it_a.p, ctx->ps.it_b.p, ctx->ps.it_nrows.p,
                 ctx->ps.it_type.p, ctx->ps.it_src.p, ctx->ps.it_key.p, ctx->ps.it_b1.p, ctx->ps.it_b2.p, np);
             ctx->launches++;

@@ -436,7 +436,7 @@ int launch_position_solve(Context* ctx, int mode) {
     if (blocks < 1) blocks = 1;
     // contacts per group: reference order -> the row count itself; coloured rows -> 3 rows per contact;
     // compact -> the count sits in bits 4..7
-    int rows_div = ref ? 1 : (ctx->step_layout == 1 ? 16 : 3);
+    int rows_div = ref ? 1 : (ctx->step_layout == 1 ? 16 : (ctx->contact_model == 1 ? 1 : 3));
     if (!ref && ctx->velocity_kernel >= 2) {
         int tpb_s, depth_s, blocks_s;
         if (staged_geometry(ctx, &tpb_s, &depth_s, &blocks_s)) {
@@ -480,7 +480,8 @@ int launch_stats(Context* ctx, int mode) {
         if (ctx->n_contacts) {
             k_penetration<<<blocks, TPB, 0, ctx->stream>>>(sched_dev(s), pos_arrays(ctx), ctx->manifolds.p,
                                                            ctx->chunk_manifold.p, ctx->p_row.p, ctx->n_pslots_max,
-                                                           ref ? 1 : (ctx->step_layout == 1 ? 16 : 3), (int*)(u + 4));
+                                                           ref ? 1 : (ctx->step_layout == 1 ? 16 : (ctx->contact_model == 1 ? 1 : 3)),
+                                                           (int*)(u + 4));
             ctx->launches++;
         }
     }

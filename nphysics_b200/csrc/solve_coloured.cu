@@ -696,25 +696,22 @@ int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd_in, const Rows
 //
 // Entry = 26 quads x TPB lanes: 0..4 group header (p_hdr planes), 5+5*lcc+k contact lcc plane k, 25 g_info.
 //
-// Settled groups cost (almost) nothing.  A contact group whose contacts all evaluate to "nothing to correct"
-// (clamp_rhs(-depth) >= 0, nonlinear_sor_prox.rs:199-201) will evaluate to exactly the same thing in the next
-// sweep unless one of its two bodies has been displaced in between -- the evaluation is a pure function of the
-// two poses.  Every displacement is therefore stamped on the body (`moved[body]` = the phase visit it
-// happened in) and every clean evaluation on the group (`g_stamp[group]` = the visit it happened in); a group
-// is skipped when its stamp is newer than both bodies' stamps.  Skipped groups read two stamps instead of two
-// bodies, a header and four contact records, and their rows are not even prefetched.  The result is bit for
-// bit the one of sweeping every group (tests/test_gpu_parity.py::test_position_skip_is_exact).  Visit numbers
-// grow monotonically across launches (`visit_base`), so neither array is ever cleared.
+// Early exit: every correction is a pure function of the poses it reads, so a sweep that displaced no body
+// would be repeated identically by every later sweep.  Each sweep counts its displacements over the grid
+// (one atomic per block that had any); a sweep that ends with the count at zero ends the kernel.  Exact:
+// tests/test_gpu_parity.py::test_position_early_exit_is_exact.  (A finer-grained variant -- per-body
+// displacement stamps + per-group "clean" stamps, so that settled groups of a partly active pile are skipped
+// individually -- was measured on the 100k pile, where 98.7 % of the groups are clean in the first sweep:
+// 0.434 ms against 0.397 ms.  The phase time is the latency chain of the few active groups, not the
+// throughput of the clean ones; profiles/r02_notes.md.)
 // ------------------------------------------------------------------------------------------
 #define NB2_PENTRY 26
-#define NB2_POS_NOT_LOADED (1 << 30)  // control-quad flag (bit 30 of g_info.z): the producer skipped this group's data
 
 __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, PosArrays A, const nb2_joint* __restrict__ joints,
                                                                   const float4* __restrict__ p_hdr, size_t G_stride,
                                                                   const float4* __restrict__ p_row, size_t P_stride,
                                                                   PosParams P, int iters, int E, int rows_div,
-                                                                  unsigned int* barrier, int* g_stamp, int* moved,
-                                                                  int visit_base, int skip_enabled) {
+                                                                  unsigned int* barrier, int early_exit) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned int TPBK = blockDim.x;
     float4* ring = reinterpret_cast<float4*>(smem_raw);  // [E][NB2_PENTRY][TPBK]
@@ -735,64 +732,41 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
     const unsigned int ring_u32 = (unsigned int)__cvta_generic_to_shared(ring) + t * 16u;
     const unsigned int plane_b = TPBK * 16u, entry_b = NB2_PENTRY * plane_b;
     const int last_it = iters - 1;
-    // The stamps cost a few loads and stores per group visit.  They are kept during the first sweep, which also
-    // counts how many groups evaluated clean; if fewer than a quarter did (a pile that is still compressing: every
-    // contact asks for a correction in every sweep) the remaining sweeps run without them, like NB2_POS_SKIP=0.
-    bool track = skip_enabled != 0;
-    unsigned int n_clean = 0, n_eval = 0;
 
     StreamPos pc = {0, 0u, tid}, pn;
     bool vc = seek_group(pc, tid, np, last_it, s_cnt), vn = false;
     int4 ic = make_int4(-1, -1, 0, 0), in_ = ic;
-    // the clean-evaluation stamp of the group being produced / of the one after it (fetched one group ahead;
-    // a stale value is only ever older, i.e. errs towards evaluating)
-    int tc = 0, tn = 0;
     if (vc) {
         ic = __ldg(&sd.g_info[s_gbase[pc.p] + pc.g]);
         pn = pc;
         pn.g += stride;
         vn = seek_group(pn, tid, np, last_it, s_cnt);
-        if (vn) {
-            in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
-            if (track && pn.s > 0) tn = __ldcg(&g_stamp[s_gbase[pn.p] + pn.g]);
-        }
+        if (vn) in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
     }
-    // copies the constant data of group (p, g) into ring entry e
-    auto fetch_group = [&](int e, int4 info, unsigned int p, unsigned int g) {
-        const unsigned int dst = ring_u32 + (unsigned int)e * entry_b;
-        const unsigned int cnt = s_cnt[p];
-        const float4* hsrc = p_hdr + s_gbase[p] + g;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) cp_async16(dst + (unsigned int)k * plane_b, hsrc + (size_t)k * G_stride);
-        const int ncc = (info.z & 0xFF) / rows_div;
-        const float4* rsrc = p_row + (size_t)NB2_CHUNK * s_gbase[p] + g;
-        for (int lcc = 0; lcc < ncc; ++lcc, rsrc += cnt) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-                cp_async16(dst + (unsigned int)(5 + 5 * lcc + k) * plane_b, rsrc + (size_t)k * P_stride);
-        }
-    };
     auto produce = [&](int e) {
         if (vc) {
-            int4 ctl = ic;
-            ctl.w = tc;  // the item index is not needed by this kernel: the control quad carries the stamp instead
+            const unsigned int dst = ring_u32 + (unsigned int)e * entry_b;
+            reinterpret_cast<int4*>(ring)[(e * NB2_PENTRY + 25) * TPBK + t] = ic;
             if ((ic.z >> 8) != NB2_ITEM_JOINT) {
-                // a group that evaluated clean in this launch will most likely be skipped: do not stream its rows
-                if (track && pc.s > 0 && tc > visit_base) ctl.z |= NB2_POS_NOT_LOADED;
-                else fetch_group(e, ic, pc.p, pc.g);
+                const unsigned int cnt = s_cnt[pc.p];
+                const float4* hsrc = p_hdr + s_gbase[pc.p] + pc.g;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) cp_async16(dst + (unsigned int)k * plane_b, hsrc + (size_t)k * G_stride);
+                const int ncc = (ic.z & 0xFF) / rows_div;
+                const float4* rsrc = p_row + (size_t)NB2_CHUNK * s_gbase[pc.p] + pc.g;
+                for (int lcc = 0; lcc < ncc; ++lcc, rsrc += cnt) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+                        cp_async16(dst + (unsigned int)(5 + 5 * lcc + k) * plane_b, rsrc + (size_t)k * P_stride);
+                }
             }
-            reinterpret_cast<int4*>(ring)[(e * NB2_PENTRY + 25) * TPBK + t] = ctl;
             pc = pn;
             ic = in_;
-            tc = tn;
             vc = vn;
             if (vn) {
                 pn.g += stride;
                 vn = seek_group(pn, tid, np, last_it, s_cnt);
-                if (vn) {
-                    in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
-                    tn = (track && pn.s > 0) ? __ldcg(&g_stamp[s_gbase[pn.p] + pn.g]) : 0;
-                }
+                if (vn) in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
             }
         }
         cp_async_commit();
@@ -801,51 +775,39 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
     for (int e = 0; e < E; ++e) produce(e);
 
     int ce = 0;
+    __shared__ unsigned int s_displaced;
+    if (threadIdx.x == 0) s_displaced = 0u;
+    __syncthreads();
+    // [it % 3]: blocks that displaced something in sweep `it`.  Three counters in rotation: the one of sweep it + 2 is
+    // cleared after the last barrier of sweep it, a whole sweep (>= 1 barrier) before its first use and after its last
+    unsigned int* const sweep_moves = barrier + 2;
     for (int it = 0; it < iters; ++it) {
+        unsigned int displaced = 0;
         for (unsigned int p = 0; p < np; ++p) {
             const unsigned int cnt = s_cnt[p];
-            const int visit = visit_base + it * (int)np + (int)p + 1;
             for (unsigned int gw = tid - lane; gw < cnt; gw += stride) {
                 if (gw + lane >= cnt) continue;
+                cp_async_wait_dyn(E - 1);
                 const int e = ce;
                 ce = ce + 1 == E ? 0 : ce + 1;
                 const float4* q = ring + (size_t)(e * NB2_PENTRY) * TPBK + t;
-                int4 info = *reinterpret_cast<const int4*>(q + 25 * TPBK);  // written with st.shared by this thread
-                const unsigned int gslot = s_gbase[p] + gw + lane;
+                const int4 info = *reinterpret_cast<const int4*>(q + 25 * TPBK);
                 PosBody b1, b2;
                 if ((info.z >> 8) == NB2_ITEM_JOINT) {
-                    cp_async_wait_dyn(E - 1);
-                    const nb2_joint& j = joints[__ldg(&sd.g_info[gslot]).w];
+                    const nb2_joint& j = joints[info.w];
                     load_pos_body(A, j.body1, &b1);
                     load_pos_body(A, j.body2, &b2);
+                    const Pose o1 = b1.bp.pose, o2 = b2.bp.pose;
                     joint_position(j, &b1, &b2, P);
-                    if (b1.dynamic) {
-                        store_pos_body(A, j.body1, b1);
-                        if (track) __stcg(&moved[j.body1], visit);
-                    }
-                    if (b2.dynamic) {
-                        store_pos_body(A, j.body2, b2);
-                        if (track) __stcg(&moved[j.body2], visit);
-                    }
+                    if (b1.dynamic) store_pos_body(A, j.body1, b1);
+                    if (b2.dynamic) store_pos_body(A, j.body2, b2);
+                    // bitwise comparison: an unchanged pose means no position constraint of the joint fired
+                    displaced |= (unsigned int)(o1.t.x != b1.bp.pose.t.x || o1.t.y != b1.bp.pose.t.y || o1.t.z != b1.bp.pose.t.z ||
+                                                o1.r.i != b1.bp.pose.r.i || o1.r.j != b1.bp.pose.r.j || o1.r.k != b1.bp.pose.r.k ||
+                                                o1.r.w != b1.bp.pose.r.w || o2.t.x != b2.bp.pose.t.x || o2.t.y != b2.bp.pose.t.y ||
+                                                o2.t.z != b2.bp.pose.t.z || o2.r.i != b2.bp.pose.r.i || o2.r.j != b2.bp.pose.r.j ||
+                                                o2.r.k != b2.bp.pose.r.k || o2.r.w != b2.bp.pose.r.w);
                 } else {
-                    // ---- exact skip: clean at visit info.w of this launch and neither body displaced since
-                    if (track && it > 0 && info.w > visit_base) {
-                        const int ma = info.x >= 0 ? __ldcg(&moved[info.x]) : 0;
-                        const int mb = info.y >= 0 ? __ldcg(&moved[info.y]) : 0;
-                        if (ma < info.w && mb < info.w) {
-                            if (!(info.z & NB2_POS_NOT_LOADED)) cp_async_wait_dyn(E - 1);  // the entry is about to be refilled
-                            produce(e);
-                            continue;
-                        }
-                    }
-                    if (info.z & NB2_POS_NOT_LOADED) {  // displaced after a clean evaluation: fetch the rows after all
-                        info.z &= ~NB2_POS_NOT_LOADED;
-                        fetch_group(e, info, p, gw + lane);
-                        cp_async_commit();
-                        cp_async_wait<0>();
-                    } else {
-                        cp_async_wait_dyn(E - 1);
-                    }
                     const float4 h0 = q[0], h1 = q[1 * TPBK], h2 = q[2 * TPBK], h3 = q[3 * TPBK], h4 = q[4 * TPBK];
                     const int body1 = __float_as_int(h0.x), body2 = __float_as_int(h0.y);
                     load_pos_body(A, body1, &b1);
@@ -859,7 +821,7 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                     // colliders sitting at their body's origin (the usual case) need no pose product
                     const bool id1 = h1.x == 0.f && h1.y == 0.f && h1.z == 0.f && h1.w == 0.f && h2.x == 0.f && h2.y == 0.f && h2.z == 1.f;
                     const bool id2 = h3.x == 0.f && h3.y == 0.f && h3.z == 0.f && h3.w == 0.f && h4.x == 0.f && h4.y == 0.f && h4.z == 1.f;
-                    bool moved1 = false, moved2 = false, any_active = false;
+                    bool moved1 = false, moved2 = false;
 #pragma unroll 1
                     for (int lcc = 0; lcc < ncc; ++lcc) {
                         const float4* rq = q + (size_t)(5 + 5 * lcc) * TPBK;
@@ -871,7 +833,6 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                         if (!kinematic_contact(l1, l2, d1, d2, n1, m1, m2, &cev)) continue;
                         const float rhs = clamp_rhs(-cev.depth, false, P);
                         if (rhs >= 0.f) continue;
-                        any_active = true;
                         Vec3 w1l = mk3(0.f, 0.f, 0.f), w1a = w1l, w2l = w1l, w2a = w1l;
                         float inv_r = 0.f;
                         pos_fill(b1, cev.world1, false, -cev.normal, &w1l, &w1a, &inv_r);
@@ -887,33 +848,26 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                             moved2 = true;
                         }
                     }
-                    if (moved1) {
-                        store_pos_body(A, body1, b1);
-                        if (track) __stcg(&moved[body1], visit);
-                    }
-                    if (moved2) {
-                        store_pos_body(A, body2, b2);
-                        if (track) __stcg(&moved[body2], visit);
-                    }
-                    // clean = no contact of the group asked for a correction (whether or not a body could move)
-                    if (track) __stcg(&g_stamp[gslot], any_active ? 0 : visit);
-                    n_eval += 1u;
-                    n_clean += any_active ? 0u : 1u;
+                    if (moved1) store_pos_body(A, body1, b1);
+                    if (moved2) store_pos_body(A, body2, b2);
+                    displaced |= (unsigned int)(moved1 || moved2);
                 }
                 produce(e);
             }
-            if (it == 0 && p + 1 == np && track && iters > 1) {  // the first sweep's verdict, summed over the grid
-                const unsigned int ce_ = __reduce_add_sync(0xffffffffu, n_clean), ev_ = __reduce_add_sync(0xffffffffu, n_eval);
-                if (lane == 0 && ev_) {
-                    atomicAdd(barrier + 2, ce_);
-                    atomicAdd(barrier + 3, ev_);
+            if (early_exit && p + 1 == np) {  // last phase of the sweep: publish before the barrier, read after it
+                if (displaced) s_displaced = 1u;
+                __syncthreads();
+                if (threadIdx.x == 0 && s_displaced) {
+                    atomicAdd(&sweep_moves[it % 3], 1u);
+                    s_displaced = 0u;  // the grid barrier below orders this before the next sweep's writers
                 }
             }
             gb.sync();
-            if (it == 0 && p + 1 == np && track && iters > 1) {
-                const unsigned int ce_ = __ldcg(barrier + 2), ev_ = __ldcg(barrier + 3);
-                track = 4u * ce_ >= ev_ && ce_ > 0u;
-            }
+        }
+        if (early_exit) {
+            const unsigned int moves = __ldcg(&sweep_moves[it % 3]);
+            if (blockIdx.x == 0 && threadIdx.x == 0) __stcg(&sweep_moves[(it + 2) % 3], 0u);
+            if (moves == 0u) break;  // uniform over the grid: nothing moved, nothing will
         }
     }
     cp_async_wait<0>();
@@ -944,34 +898,10 @@ int launch_position_solve_staged(Context* ctx, const SchedDev& sd_in, const PosA
     int iters = (int)ctx->params.max_position_iterations;
     unsigned int* bar = ctx->barrier.p;
     size_t smem = smem_of(E);
-    // stamps of the exact skip: zeroed when (re)allocated and when the visit counter is about to wrap
-    const size_t span = (size_t)iters * NB2_MAX_COLOURS + 2;
-    const bool wrap = (size_t)ctx->pos_visit_base + span > (size_t)0x3FFFFFFF;
-    {
-        int* before = ctx->pos_gstamp.p;
-        NB2_TRY(ctx->pos_gstamp.reserve(ctx, ctx->vs.n_items + 16));
-        if (ctx->pos_gstamp.p != before || wrap)
-            NB2_CUDA(ctx, cudaMemsetAsync(ctx->pos_gstamp.p, 0, ctx->pos_gstamp.cap * sizeof(int), ctx->stream));
-        before = ctx->pos_moved.p;
-        NB2_TRY(ctx->pos_moved.reserve(ctx, (size_t)ctx->n_bodies + 16));
-        if (ctx->pos_moved.p != before || wrap)
-            NB2_CUDA(ctx, cudaMemsetAsync(ctx->pos_moved.p, 0, ctx->pos_moved.cap * sizeof(int), ctx->stream));
-        if (wrap) ctx->pos_visit_base = 0;
-    }
-    int* gstamp = ctx->pos_gstamp.p;
-    int* movedp = ctx->pos_moved.p;
-    int vbase = ctx->pos_visit_base;
-    ctx->pos_visit_base += (int)span;
-    int skip = ctx->pos_skip ? 1 : 0;
-    void* args[] = {&sd, &A, &joints, &phdr, &gstride, &prow, &pstride, &P, &iters, &E, &rows_div, &bar, &gstamp, &movedp, &vbase, &skip};
+    int early = ctx->pos_early_exit ? 1 : 0;
+    void* args[] = {&sd, &A, &joints, &phdr, &gstride, &prow, &pstride, &P, &iters, &E, &rows_div, &bar, &early};
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_position_solve_staged, dim3(blocks), dim3(tpb), args, smem, ctx->stream));
     ctx->launches++;
-    if (getenv("NB2_DEBUG_POS")) {  // developer knob: the first sweep's verdict (clean / evaluated groups)
-        unsigned int v[4] = {0, 0, 0, 0};
-        cudaMemcpyAsync(v, ctx->barrier.p, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-        fprintf(stderr, "position solve: %u of %u contact groups clean in the first sweep\n", v[2], v[3]);
-    }
     return NB2_OK;
 }
 

@@ -260,7 +260,35 @@ __device__ __forceinline__ bool kinematic_contact(float4 l1, float4 l2, float4 d
         depth = -dot3(wn2, world1 - world2);
         world2 = world1 + wn2 * depth;
         normal = -wn2;
-    } else if (g1 == NB2_GEOM_POINT && g2 == NB2_GEOM_POINT) {
+    } else if (g1 != NB2_GEOM_PLANE && g2 != NB2_GEOM_PLANE && (unsigned int)g1 <= NB2_GEOM_PLANE &&
+               (unsigned int)g2 <= NB2_GEOM_PLANE) {
+        // Point/Point, Line/Line, Line/Point, Point/Line: a Line side is reduced to its point closest to the
+        // other side, then the pair is resolved as Point/Point (separated branch: the shapes, which ncollide
+        // asks for the tangent cone of the feature, are not part of the contact record; see oracle.cpp)
+        if (g1 == NB2_GEOM_LINE && g2 == NB2_GEOM_LINE) {
+            const Vec3 e1 = quat_rotate(m1.r, f4_xyz(d1)), e2 = quat_rotate(m2.r, f4_xyz(d2));
+            const Vec3 r = world1 - world2;
+            const float a = dot3(e1, e1), b = dot3(e1, e2), cc = dot3(e2, e2), d = dot3(e1, r), e = dot3(e2, r);
+            const float denom = a * cc - b * b;
+            float s1, s2;
+            if (denom <= NB2_F32_EPS * a * cc) {
+                s1 = 0.f;
+                s2 = cc != 0.f ? e / cc : 0.f;
+            } else {
+                s1 = (b * e - cc * d) / denom;
+                s2 = (a * e - b * d) / denom;
+            }
+            world1 = world1 + e1 * s1;
+            world2 = world2 + e2 * s2;
+        } else if (g1 == NB2_GEOM_LINE) {
+            const Vec3 e1 = quat_rotate(m1.r, f4_xyz(d1));
+            const float a = dot3(e1, e1);
+            if (a != 0.f) world1 = world1 + e1 * (dot3(e1, world2 - world1) / a);
+        } else if (g2 == NB2_GEOM_LINE) {
+            const Vec3 e2 = quat_rotate(m2.r, f4_xyz(d2));
+            const float a = dot3(e2, e2);
+            if (a != 0.f) world2 = world2 + e2 * (dot3(e2, world1 - world2) / a);
+        }
         Vec3 n;
         float d;
         if (unit_try_new_and_get(world2 - world1, NB2_F32_EPS, &n, &d)) {
@@ -271,7 +299,7 @@ __device__ __forceinline__ bool kinematic_contact(float4 l1, float4 l2, float4 d
             normal = quat_rotate(m1.r, f4_xyz(n1));
         }
     } else {
-        return false;
+        return false;  // Plane/Plane, Plane/Line, Line/Plane: ContactKinematic::contact returns None
     }
     world1 = world1 + normal * l1.w;
     world2 = world2 + normal * (-l2.w);

@@ -174,6 +174,7 @@ struct Context {
     bool incremental_colouring = true;  // NB2_INCREMENTAL_COLOURING=0: any change of the conflict graph colours from scratch
     bool manifolds_from_producer = false;  // the contact set of the next step was written by nb2_generate_manifolds
     // coloured mode, contact groups: 0 = 132-byte row stream (default), 1 = 80-byte compact records
+    int contact_model = 0;  // nb2_contact_model
     int contact_layout = 0;
     int step_layout = 0;  // layout the last assembly used
     StageEvents ev;
@@ -279,10 +280,7 @@ struct Context {
     size_t n_ghdr_max = 0;
     void* host_hdr = nullptr;      // pinned copy of vs.hdr (launch-geometry hint, never waited for)
     DevBuf<unsigned int> bal;       // groups per colour while balancing
-    // staged position kernel: exact skip of settled groups (solve_coloured.cu)
-    DevBuf<int> pos_gstamp, pos_moved;
-    int pos_visit_base = 0;
-    bool pos_skip = true;           // NB2_POS_SKIP=0 sweeps every group every iteration (A/B runs, the exactness test)
+    bool pos_early_exit = true;     // NB2_POS_EARLY_EXIT=0: always run every position iteration (the exactness test)
 };
 
 // ---------------------------------------------------------------------------

@@ -346,9 +346,18 @@ struct ColliderContactManifold {
 struct ContactModel {
     virtual ~ContactModel() {}
     virtual const char* name() const = 0;
+    /// the nb2_contact_model this model runs as on the device, or -1 for a model the device does not carry
+    virtual int device_model() const { return -1; }
 };
+/// src/solver/signorini_coulomb_pyramid_model.rs: unilateral normal row + two friction-pyramid rows per contact
 struct SignoriniCoulombPyramidModel : ContactModel {
     const char* name() const override { return "SignoriniCoulombPyramidModel"; }
+    int device_model() const override { return NB2_CONTACT_SIGNORINI_COULOMB_PYRAMID; }
+};
+/// src/solver/signorini_model.rs:200-298: frictionless, active contacts only
+struct SignoriniModel : ContactModel {
+    const char* name() const override { return "SignoriniModel"; }
+    int device_model() const override { return NB2_CONTACT_SIGNORINI; }
 };
 
 // counters/mod.rs (solver stages, milliseconds)
@@ -401,8 +410,10 @@ class MoreauJeanSolver {
 
     /// moreau_jean_solver.rs:42-44.  A new model forgets the cached impulses.
     void set_contact_model(std::unique_ptr<ContactModel> model) {
-        if (std::string(model->name()) != "SignoriniCoulombPyramidModel")
-            throw SolverError(NB2_ERR_UNSUPPORTED, "only SignoriniCoulombPyramidModel is implemented on device");
+        if (model->device_model() < 0)
+            throw SolverError(NB2_ERR_UNSUPPORTED, "a user-defined ContactModel cannot run on the device: the two models "
+                                                   "nphysics ships (SignoriniCoulombPyramidModel, SignoriniModel) can");
+        check(nb2_set_contact_model(ctx_, model->device_model()));
         contact_model_ = std::move(model);
         check(nb2_clear_impulse_cache(ctx_));
     }

@@ -25,7 +25,7 @@ EXPORTS = [
     "nb2_download_contact_impulses", "nb2_download_joints", "nb2_get_stats", "nb2_get_timers",
     "nb2_launch_count", "nb2_download_schedule",
     "nb2_update_contacts", "nb2_upload_colliders", "nb2_detect_pairs", "nb2_generate_manifolds",
-    "nb2_download_manifolds", "nb2_label_islands",
+    "nb2_download_manifolds", "nb2_label_islands", "nb2_set_contact_model",
 ]
 
 
@@ -204,6 +204,10 @@ class Solver:
         j = np.ascontiguousarray(joints, dtype=abi.joint_dtype)
         self.n_joints = len(j)
         self._chk(self.lib.nb2_upload_joints(self.h, abi.ptr(j), ctypes.c_uint32(len(j))))
+
+    def set_contact_model(self, model):
+        """0 = SignoriniCoulombPyramidModel (default), 1 = SignoriniModel (frictionless)."""
+        self._chk(self.lib.nb2_set_contact_model(self.h, ctypes.c_int(int(model))))
 
     def clear_impulse_cache(self):
         self._chk(self.lib.nb2_clear_impulse_cache(self.h))

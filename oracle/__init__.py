@@ -60,7 +60,7 @@ def _load(f64=False):
         lib = ctypes.CDLL(path)
         lib.nbo_create.restype = ctypes.c_void_p
         for name in ["nbo_destroy", "nbo_set_params", "nbo_upload_bodies", "nbo_upload_body_states",
-                     "nbo_upload_manifolds", "nbo_upload_joints", "nbo_clear_impulse_cache", "nbo_step",
+                     "nbo_upload_manifolds", "nbo_upload_joints", "nbo_clear_impulse_cache", "nbo_set_contact_model", "nbo_step",
                      "nbo_download_body_states", "nbo_download_contact_impulses", "nbo_download_joints",
                      "nbo_get_stats", "nbo_debug_body_dynamics", "nbo_debug_row_counts", "nbo_debug_mj_lambda"]:
             getattr(lib, name).restype = ctypes.c_int
@@ -123,6 +123,10 @@ class Oracle:
 
     def clear_impulse_cache(self):
         self._chk(self.lib.nbo_clear_impulse_cache(self.h))
+
+    def set_contact_model(self, model):
+        """0 = SignoriniCoulombPyramidModel, 1 = SignoriniModel (frictionless)."""
+        self._chk(self.lib.nbo_set_contact_model(self.h, ctypes.c_int(int(model))))
 
     # ---- sleeping (ActivationManager::update restated, activation_manager.rs:60-201)
     def upload_activation(self, activation):

@@ -571,7 +571,39 @@ bool kinematic_contact(const NonlinearUnilateral& c, const Iso& m1, const Iso& m
         depth = -dot(world_normal2, world1 - world2);
         world2 = world1 + world_normal2 * depth;
         normal = -world_normal2;
-    } else if (c.geom1 == NB2_GEOM_POINT && c.geom2 == NB2_GEOM_POINT) {
+    } else if (c.geom1 != NB2_GEOM_PLANE && c.geom2 != NB2_GEOM_PLANE && c.geom1 <= NB2_GEOM_PLANE &&
+               c.geom2 <= NB2_GEOM_PLANE) {
+        /* Point/Point, Line/Line, Line/Point, Point/Line: a Line side is first
+         * reduced to its point closest to the other side -- closest points of the two world lines, or the
+         * projection of the other side's point on the line -- then the pair is resolved as Point/Point.
+         * ncollide additionally asks shape 1 whether its tangent cone at the feature contains the
+         * direction (the features interpenetrate: depth = +len, normal = -dir); the shapes are not part
+         * of the contact record, so the separated branch is taken: with ncollide's margins the
+         * un-dilated cores the features belong to do not interpenetrate in a resting contact. */
+        if (c.geom1 == NB2_GEOM_LINE && c.geom2 == NB2_GEOM_LINE) {
+            const V3 d1 = rotate(m1.r, c.dir1), d2 = rotate(m2.r, c.dir2);
+            const V3 r = world1 - world2;
+            const real a = dot(d1, d1), b = dot(d1, d2), cc = dot(d2, d2), d = dot(d1, r), e = dot(d2, r);
+            const real denom = a * cc - b * b;
+            real s1, s2;
+            if (denom <= REAL_EPS * a * cc) { /* parallel lines: keep point 1, project it on line 2 */
+                s1 = 0;
+                s2 = cc != 0 ? e / cc : 0;
+            } else {
+                s1 = (b * e - cc * d) / denom;
+                s2 = (a * e - b * d) / denom;
+            }
+            world1 = world1 + d1 * s1;
+            world2 = world2 + d2 * s2;
+        } else if (c.geom1 == NB2_GEOM_LINE) {
+            const V3 d1 = rotate(m1.r, c.dir1);
+            const real a = dot(d1, d1);
+            if (a != 0) world1 = world1 + d1 * (dot(d1, world2 - world1) / a);
+        } else if (c.geom2 == NB2_GEOM_LINE) {
+            const V3 d2 = rotate(m2.r, c.dir2);
+            const real a = dot(d2, d2);
+            if (a != 0) world2 = world2 + d2 * (dot(d2, world1 - world2) / a);
+        }
         V3 n;
         real d;
         if (try_new_and_get(world2 - world1, REAL_EPS, &n, &d)) {
@@ -582,7 +614,7 @@ bool kinematic_contact(const NonlinearUnilateral& c, const Iso& m1, const Iso& m
             normal = rotate(m1.r, c.normal1);
         }
     } else {
-        return false;
+        return false; /* Plane/Plane, Plane/Line, Line/Plane: ContactKinematic::contact returns None */
     }
     world1 = world1 + normal * c.margin1;
     world2 = world2 + normal * (-c.margin2);
@@ -1174,6 +1206,10 @@ struct World {
     /* SignoriniCoulombPyramidModel::constraints, signorini_coulomb_pyramid_model.rs:56-224
      * (+ SignoriniModel::build_velocity_constraint signorini_model.rs:37-138 and
      * build_position_constraint :153-197). */
+    /* 0 = SignoriniCoulombPyramidModel (default, moreau_jean_solver.rs:29-40), 1 = SignoriniModel as a
+     * frictionless ContactModel (signorini_model.rs:200-298), selected by set_contact_model (:42-44) */
+    int contact_model = 0;
+
     void contact_constraints(size_t* ground_j_id, size_t* j_id) {
         uni_contact.clear();
         unig_contact.clear();
@@ -1184,6 +1220,9 @@ struct World {
             const Body& body2 = bodies[m.body2];
             for (uint32_t ci = m.first_contact; ci < m.first_contact + m.num_contacts; ++ci) {
                 const nb2_contact& c = contacts[ci];
+                /* SignoriniModel::is_constraint_active (signorini_model.rs:141-150, applied at :230-232;
+                 * commented out in the pyramid model, signorini_coulomb_pyramid_model.rs:100-102) */
+                if (contact_model == 1 && !((real)c.depth + (real)m.margin1 + (real)m.margin2 >= (real)0)) continue;
                 V3 normal = ld3(c.normal), world1 = ld3(c.world1), world2 = ld3(c.world2);
                 V3 surface_velocity = ld3(m.surface_velocity);
                 V3 impulse = v3(0, 0, 0);
@@ -1239,6 +1278,7 @@ struct World {
                 p.r = 0;
                 contact_pos.push_back(p);
 
+                if (contact_model == 1) continue; /* frictionless: the normal row and the position row only */
                 /* --- friction rows: signorini_coulomb_pyramid_model.rs:131-216 */
                 size_t dependency =
                     ground_constraint ? contact_vel.unilateral_ground.size() - 1 : contact_vel.unilateral.size() - 1;
@@ -1269,8 +1309,18 @@ struct World {
      * this step's contacts only: a ContactId (slotmap key) that disappears is
      * never issued again, so forgetting absent keys is equivalent. */
     void contact_cache_impulses() {
-        impulses.clear();
         contact_impulses_out.assign(contacts.size(), v3(0, 0, 0));
+        if (contact_model == 1) {
+            /* signorini_model.rs:285-297: the solved contacts are inserted, nothing is ever removed, so a
+             * contact that was inactive this step keeps the impulse of the step it was last solved in;
+             * contact_impulses_out reports the cache entry of every contact */
+            for (size_t ci = 0; ci < contacts.size(); ++ci) {
+                auto it = contacts[ci].key != 0 ? impulses.find(contacts[ci].key) : impulses.end();
+                if (it != impulses.end()) contact_impulses_out[ci].x = it->second.x;
+            }
+        } else {
+            impulses.clear();
+        }
         for (size_t k = 0; k < contact_vel.unilateral_ground.size(); ++k) {
             const UnilateralGround& c = contact_vel.unilateral_ground[k];
             contact_impulses_out[unig_contact[k]].x = c.impulse;
@@ -1838,6 +1888,13 @@ int nbo_upload_joints(void* wp, const nb2_joint* j, uint32_t n) {
     return NB2_OK;
 }
 
+int nbo_set_contact_model(void* wp, int model) {
+    if (!wp || (model != 0 && model != 1)) return -1;
+    World* w = (World*)wp;
+    if (w->contact_model != model) w->impulses.clear(); /* a fresh ContactModel starts with an empty cache */
+    w->contact_model = model;
+    return 0;
+}
 int nbo_clear_impulse_cache(void* wp) {
     ((World*)wp)->impulses.clear();
     return NB2_OK;

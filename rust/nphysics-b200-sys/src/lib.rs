@@ -36,6 +36,8 @@ pub const NB2_JOINT_CARTESIAN: u32 = 9;
 pub const NB2_JOINT_FLAG_MIN_OFFSET: u32 = 1;
 pub const NB2_JOINT_FLAG_MAX_OFFSET: u32 = 2;
 
+pub const NB2_CONTACT_SIGNORINI_COULOMB_PYRAMID: i32 = 0;
+pub const NB2_CONTACT_SIGNORINI: i32 = 1;
 pub const NB2_MODE_REFERENCE_ORDER: i32 = 0;
 pub const NB2_MODE_COLOURED: i32 = 1;
 
@@ -247,6 +249,7 @@ extern "C" {
     pub fn nb2_download_manifolds(ctx: *mut nb2_context, out_manifolds: *mut nb2_manifold, manifold_capacity: u32,
                                   out_contacts: *mut nb2_contact, contact_capacity: u32, out_n_manifolds: *mut u32,
                                   out_n_contacts: *mut u32) -> i32;
+    pub fn nb2_set_contact_model(ctx: *mut nb2_context, model: i32) -> i32;
     pub fn nb2_label_islands(ctx: *mut nb2_context, out_labels: *mut i32, out_rows: *mut u32, n: u32) -> i32;
     pub fn nb2_download_schedule(ctx: *mut nb2_context, out_phase: *mut i32, out_body1: *mut i32, out_body2: *mut i32,
                                  capacity: u32, out_n: *mut u32) -> i32;

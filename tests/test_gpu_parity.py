@@ -483,16 +483,16 @@ def test_staged_and_register_pipelined_kernels_agree(monkeypatch):
     assert int(s0["non_finite"]) == 0 and int(s1["non_finite"]) == 0
 
 
-@pytest.mark.parametrize("scene_name", ["pile", "pyramid_flipped", "chains", "falling"])
-def test_position_skip_is_exact(scene_name, monkeypatch):
-    """The staged position kernel skips a contact group that found nothing to correct at its last visit and
-    whose bodies have not been displaced since (the evaluation is a pure function of the two poses).  That
-    must change nothing, bit for bit, against sweeping every group every iteration (NB2_POS_SKIP=0): settling
-    piles (most groups clean), a mixed joint + contact scene, and boxes dropping onto each other."""
-    if scene_name == "pile":
+@pytest.mark.parametrize("scene_name", ["resting", "pile", "chains", "falling"])
+def test_position_early_exit_is_exact(scene_name, monkeypatch):
+    """The staged position kernel ends as soon as a whole sweep displaced no body: every later sweep would
+    evaluate the same poses to the same "nothing to correct".  Bit for bit the result of running every
+    iteration (NB2_POS_EARLY_EXIT=0), on a scene that is at rest from the start (one layer of boxes within the
+    allowed error: the exit is taken), a settling pile, a joint + contact scene and boxes dropping onto each other."""
+    if scene_name == "resting":
+        sc, gen = scenes.boxes3(6, 1, 6), None
+    elif scene_name == "pile":
         sc, gen = scenes.boxes3(8, 10, 8), None
-    elif scene_name == "pyramid_flipped":
-        sc, gen = scenes.pyramid3(16), None
     elif scene_name == "chains":
         sc = scenes.joint_chains(24, 6, kind="mixed", with_ground_collider=True, ground_y=-0.22, pitch=6.0)
         gen = scenes.ContactGenerator(sc, search=0.0)
@@ -500,12 +500,12 @@ def test_position_skip_is_exact(scene_name, monkeypatch):
         sc, gen = scenes.boxes3(6, 5, 6, height=0.008, jitter=0.001), None
         sc.bodies["velocity"][1:, 1] = -0.8
     if gen is None:
-        gen = scenes.ContactGenerator(sc, flip_fraction=0.5 if scene_name == "pyramid_flipped" else 0.0)
+        gen = scenes.ContactGenerator(sc, flip_fraction=0.5 if scene_name == "pile" else 0.0)
     p = abi.default_params()
     p["max_position_iterations"] = 6
     outs = []
-    for skip in ("1", "0"):
-        monkeypatch.setenv("NB2_POS_SKIP", skip)  # read at nb2_create
+    for early in ("1", "0"):
+        monkeypatch.setenv("NB2_POS_EARLY_EXIT", early)  # read at nb2_create
         s = new_solver()
         s.set_params(p)
         s.upload_bodies(sc.bodies)
@@ -568,6 +568,83 @@ def test_bulk_copy_velocity_kernel_matches_staged_bitwise(scene_name, monkeypatc
     assert np.array_equal(outs[0][0]["velocity"], outs[1][0]["velocity"])
     assert np.array_equal(outs[0][1], outs[1][1])
     assert np.abs(outs[0][1]).max() > 0
+
+
+def test_line_kinematics_reference_order_matches_oracle():
+    """Line/Line and Line/Point contact kinematics (edge contacts of rotated boxes): the position pass of the
+    reference order against the oracle, per quantity at 1e-5, and the coloured staged kernel to rounding."""
+    from tests.test_oracle_invariants import edge_scene
+    sc, m, c = edge_scene()
+    p = abi.default_params()
+    p["max_position_iterations"] = 8
+    g, o, col = new_solver(), new_oracle(), new_solver()
+    for s in (g, o, col):
+        s.set_params(p)
+        s.upload_bodies(sc.bodies)
+    for k in range(4):
+        for s in (g, o, col):
+            s.upload_manifolds(m, c)
+        g.step(REF)
+        o.step()
+        col.step(COL)
+        g.synchronize()
+        check_step("edges %d" % k, g, o)
+    assert float(g.get_stats()["max_penetration"]) == pytest.approx(float(o.get_stats()["max_penetration"]), rel=1e-4, abs=1e-7)
+    sg, sc_ = g.download_body_states(), col.download_body_states()
+    assert np.abs(sg["position"] - sc_["position"]).max() < 1e-4
+    assert np.abs(sg["position"][1:4, :3] - sc.bodies["position"][1:4, :3]).max() > 1e-3
+
+
+def test_signorini_model_frictionless_contact_model():
+    """MoreauJeanSolver::set_contact_model (moreau_jean_solver.rs:42-44) with the reference's second model,
+    SignoriniModel (signorini_model.rs:200-298): one unilateral row per ACTIVE contact (depth + margins >= 0),
+    no friction rows, a cache that keeps the impulse of contacts that are inactive for a while.  Reference order
+    against the oracle at 1e-5 per quantity; boxes pushed sideways must slide freely; some contacts separate
+    and come back (the top layer hops), exercising the carried impulses."""
+    sc = scenes.boxes3(4, 3, 4)
+    sc.bodies["velocity"][1:, 0] = 0.3                      # a lateral push: nothing but friction would stop it
+    top = np.nonzero(sc.bodies["position"][:, 1] > 0.5)[0]
+    sc.bodies["velocity"][top, 1] = 0.25                    # the top layer leaves its contacts for a few steps
+    gen = scenes.ContactGenerator(sc)
+    g, o, col = new_solver(), new_oracle(), new_solver()
+    for s in (g, o, col):
+        s.set_contact_model(abi.CONTACT_SIGNORINI)
+        s.set_params(sc.params)
+        s.upload_bodies(sc.bodies)
+    inactive_seen = False
+    for k in range(10):
+        st = o.download_body_states()
+        m, c = gen.generate(st["position"])
+        inactive_seen |= bool((c["depth"] + 0.02 < 0).any())
+        if k:
+            g.upload_body_states(st)
+        for s in (g, o, col):
+            s.upload_manifolds(m, c)
+        g.step(REF)
+        o.step()
+        col.step(COL)
+        g.synchronize()
+        check_step("signorini %d" % k, g, o)
+        ig = g.download_contact_impulses()
+        assert np.all(ig[:, 1:] == 0.0)                     # no friction impulses exist
+    assert inactive_seen
+    sg, so = g.get_stats(), o.get_stats()
+    assert int(sg["n_rows_two_body"]) == int(so["n_rows_two_body"]) and int(sg["n_rows_ground"]) == int(so["n_rows_ground"])
+    assert int(sg["n_rows_two_body"]) + int(sg["n_rows_ground"]) <= len(c)  # at most one row per contact
+    vx = o.download_body_states()["velocity"][1:, 0]
+    assert np.all(vx > 0.29)                                # frictionless: the push is not slowed down
+    sc_ = col.get_stats()
+    assert int(sc_["non_finite"]) == 0
+    assert np.all(col.download_body_states()["velocity"][1:, 0] > 0.29)
+    # back to the default model: friction rows again
+    g.set_contact_model(abi.CONTACT_SIGNORINI_COULOMB_PYRAMID)
+    g.upload_manifolds(m, c)
+    g.step(REF)
+    assert np.abs(g.download_contact_impulses()[:, 1:]).max() > 0.0
+    from nphysics_b200.solver import Nb2Error
+    with pytest.raises(Nb2Error) as ei:
+        g.set_contact_model(7)
+    assert ei.value.code == abi.ERR_UNSUPPORTED
 
 
 def test_step_ccd_reference_order_matches_oracle():

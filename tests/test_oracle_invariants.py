@@ -378,3 +378,110 @@ def test_ragdolls_centre_of_mass_falls_freely_and_joints_hold():
     w2 = p[J["body2"], :3] + scenes.quat_rotate(p[J["body2"], 3:7], J["anchor2"].astype(np.float64))
     assert np.abs(w1 - w2).max() < 5e-3
     assert int(o.get_stats()["n_rows_two_body"]) == 3 * 5 * 3
+
+
+# ------------------------------------------------------------------ Line kinematics
+def edge_scene():
+    """Two boxes whose edges cross: A's top edge along x, B's bottom edge along z, B resting 15 mm above A
+    (less than the two margins: the position solver must push them apart), plus a box whose vertex faces
+    A's other top edge (Point/Line) -- contacts ncollide reports as Line/Line and Line/Point."""
+    from nphysics_b200 import scenes
+    rad = 0.1
+    centers = [(0.0, 1.0, 0.0), (0.0, 1.0 + 2 * rad + 0.015, 2 * rad), (0.0, 1.0 + 2 * rad + 0.012, -2 * rad - 0.0)]
+    bodies, he, off = scenes._make_boxes(centers, rad, 1.0, (3.0, 0.2, 3.0))
+    bodies["flags"][:] = 0                      # no gravity: only the position correction moves anything
+    m = np.zeros(2, dtype=abi.manifold_dtype)
+    c = np.zeros(2, dtype=abi.contact_dtype)
+    m["margin1"] = m["margin2"] = 0.01
+    m["friction"] = 0.5
+    m["coll1_wrt_body"][:, 6] = m["coll2_wrt_body"][:, 6] = 1.0
+    # manifold 0: A (body 1) edge y=+rad, z=+rad along x  |  B (body 2) edge y=-rad, z=-rad along x rotated to z:
+    # take B's edge x=0.. along z through (0, -rad, -rad)+... : lines cross above A's edge
+    m["body1"][0], m["body2"][0], m["first_contact"][0], m["num_contacts"][0] = 1, 2, 0, 1
+    c["local1"][0] = (0.03, rad, rad)
+    c["dir1"][0] = (1.0, 0.0, 0.0)
+    c["geom1"][0] = abi.GEOM_LINE
+    c["local2"][0] = (0.0, -rad, -rad + 0.02)
+    c["dir2"][0] = (0.0, 0.0, 1.0)
+    c["geom2"][0] = abi.GEOM_LINE
+    # manifold 1: A edge y=+rad, z=-rad along x (Line)  |  vertex of C (body 3) (Point)
+    m["body1"][1], m["body2"][1], m["first_contact"][1], m["num_contacts"][1] = 1, 3, 1, 1
+    c["local1"][1] = (-0.05, rad, -rad)
+    c["dir1"][1] = (1.0, 0.0, 0.0)
+    c["geom1"][1] = abi.GEOM_LINE
+    c["local2"][1] = (rad, -rad, rad)
+    c["geom2"][1] = abi.GEOM_POINT
+    c["key"] = [11, 12]
+    pos = bodies["position"].astype(np.float64)
+    for k in range(2):                          # world points / normal / depth of the velocity rows
+        b1, b2 = int(m["body1"][k]), int(m["body2"][k])
+        w1 = pos[b1, :3] + c["local1"][k]
+        w2 = pos[b2, :3] + c["local2"][k]
+        d1 = c["dir1"][k].astype(np.float64)
+        if c["geom2"][k] == abi.GEOM_LINE:
+            d2 = c["dir2"][k].astype(np.float64)
+            r = w1 - w2
+            a, b, cc, d, e = d1 @ d1, d1 @ d2, d2 @ d2, d1 @ r, d2 @ r
+            den = a * cc - b * b
+            w1 = w1 + d1 * ((b * e - cc * d) / den)
+            w2 = w2 + d2 * ((a * e - b * d) / den)
+        else:
+            w1 = w1 + d1 * (d1 @ (w2 - w1))
+        n = (w2 - w1) / np.linalg.norm(w2 - w1)
+        c["world1"][k], c["world2"][k], c["normal"][k] = w1, w2, n
+        c["depth"][k] = -np.linalg.norm(w2 - w1)
+    sc = scenes.Scene(bodies, he, off, name="edges")
+    return sc, m, c
+
+
+def test_line_line_and_line_point_position_correction():
+    """Edge/edge and edge/vertex contacts are pushed apart until their distance is within the allowed error of
+    the two margins (nonlinear_sor_prox.rs:156-309 with ContactKinematic's Line cases)."""
+    sc, m, c = edge_scene()
+    o = Oracle()
+    p = abi.default_params()
+    p["max_position_iterations"] = 30
+    o.set_params(p)
+    o.upload_bodies(sc.bodies)
+    gap0 = np.linalg.norm(c["world2"].astype(np.float64) - c["world1"], axis=1)
+    assert np.all(gap0 < 0.02 - 0.001)
+    for _ in range(4):
+        o.upload_manifolds(m, c)
+        o.step()
+    st = o.download_body_states()
+    moved = np.abs(st["position"][1:4, :3] - sc.bodies["position"][1:4, :3]).max(axis=1)
+    assert np.all(moved > 1e-4)                 # all three boxes were displaced
+    # distance between the two features at the final poses (boxes do not rotate much: check along y)
+    yA, yB, yC = st["position"][1, 1], st["position"][2, 1], st["position"][3, 1]
+    assert yB - yA - 0.2 > 0.015 and yC - yA - 0.2 > 0.012
+    assert float(o.get_stats()["max_penetration"]) <= 0.0011 + 1e-6
+
+
+def test_signorini_model_is_frictionless_and_filters_inactive_contacts():
+    """SignoriniModel as a ContactModel (signorini_model.rs:200-298): contacts with depth + margins < 0 make no
+    row (is_constraint_active, :141-150), active ones make exactly one unilateral row, and a box sliding on the
+    ground keeps its tangential velocity."""
+    sc = scenes.boxes3(3, 1, 3)
+    sc.bodies["velocity"][1:, 0] = 0.5
+    gen = scenes.ContactGenerator(sc)
+    m, c = gen.generate()
+    c = c.copy()
+    c["depth"][::2] = -0.03                     # every other contact: separated by more than the two margins
+    o = Oracle()
+    o.set_contact_model(1)
+    o.set_params(sc.params)
+    o.upload_bodies(sc.bodies)
+    o.upload_manifolds(m, c)
+    o.step()
+    counts = o.debug_row_counts()               # joint bilateral (+ground), contact bilateral (+ground), unilateral (+ground)
+    active = int((c["depth"] + 0.02 >= 0).sum())
+    assert int(counts[4]) + int(counts[5]) == active and int(counts[2]) + int(counts[3]) == 0
+    st = o.download_body_states()
+    assert np.allclose(st["velocity"][1:, 0], 0.5, atol=1e-6)
+    imp = o.download_contact_impulses()
+    assert np.all(imp[:, 1:] == 0.0) and imp[:, 0].max() > 0.0
+    o.set_contact_model(0)                      # the pyramid model brakes the same boxes
+    o.upload_bodies(sc.bodies)
+    o.upload_manifolds(m, c)
+    o.step()
+    assert np.all(o.download_body_states()["velocity"][1:, 0] < 0.5 - 1e-3)
