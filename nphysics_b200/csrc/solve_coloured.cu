@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
     for (int e = 0; e < E; ++e) produce(e);
 
     int ce = 0;
-    __shared__ unsigned int s_displaced;
+    unsigned int& s_displaced = s_gbase[NB2_MAX_COLOURS];  // one word behind the phase tables (dynamic shared memory)
     if (threadIdx.x == 0) s_displaced = 0u;
     __syncthreads();
     // [it % 3]: blocks that displaced something in sweep `it`.  Three counters in rotation: the one of sweep it + 2 is
@@ -881,7 +881,7 @@ int launch_position_solve_staged(Context* ctx, const SchedDev& sd_in, const PosA
     // entries per thread: 1 (refilled as soon as its group is done, i.e. while the block waits at the barrier)
     // measured best on the 100k-box pile: 0.52 ms vs 0.54 ms with 2
     int E = 1;
-    auto smem_of = [&](int e) { return (size_t)e * NB2_PENTRY * tpb * 16 + 2 * NB2_MAX_COLOURS * 4; };
+    auto smem_of = [&](int e) { return (size_t)e * NB2_PENTRY * tpb * 16 + 2 * NB2_MAX_COLOURS * 4 + 16; };
     while (E > 1 && smem_of(E) > ctx->smem_optin) --E;
     if (const char* f = getenv("NB2_STAGED_PENTRIES")) E = atoi(f);
     if (smem_of(E) > ctx->smem_optin) return NB2_STAGED_NOT_APPLICABLE;  // caller falls back to the plain kernel

@@ -655,6 +655,7 @@ struct World {
     std::vector<V3> contact_impulses_out; /* per contact, upload order */
     /* maps a contact's rows back to the contact index for the download */
     std::vector<size_t> uni_contact, unig_contact, bil_contact, bilg_contact;
+    std::vector<char> solved_scratch;
 
     nb2_stats stats;
     char last_error[256];
@@ -1319,7 +1320,30 @@ struct World {
                 if (it != impulses.end()) contact_impulses_out[ci].x = it->second.x;
             }
         } else {
-            impulses.clear();
+            /* The reference's cache (a SecondaryMap) never forgets.  A ContactId that leaves the narrow
+             * phase is never issued again, so forgetting ABSENT ids is equivalent -- but a contact that is
+             * still reported and merely not solved this step (its pair sleeps: it is filtered out of the
+             * manifold list, mechanical_world.rs:287-300) must keep its entry, or the island would
+             * cold-start when it wakes.  Those entries are carried over. */
+            std::unordered_map<uint64_t, V3> old;
+            old.swap(impulses);
+            for (size_t ci = 0; ci < contacts.size(); ++ci) {
+                const uint64_t key = contacts[ci].key;
+                if (key == 0) continue;
+                auto it = old.find(key);
+                if (it != old.end()) impulses[key] = it->second; /* overwritten below if solved this step */
+            }
+            solved_scratch.assign(contacts.size(), 0);
+            for (size_t ci : unig_contact) solved_scratch[ci] = 1;
+            for (size_t ci : uni_contact) solved_scratch[ci] = 1;
+            for (size_t ci = 0; ci < contacts.size(); ++ci)
+                if (!solved_scratch[ci] && contacts[ci].key != 0) {
+                    auto it = impulses.find(contacts[ci].key);
+                    if (it != impulses.end()) contact_impulses_out[ci] = it->second;
+                }
+            /* entries of solved contacts are rebuilt from scratch below */
+            for (size_t ci = 0; ci < contacts.size(); ++ci)
+                if (solved_scratch[ci] && contacts[ci].key != 0) impulses.erase(contacts[ci].key);
         }
         for (size_t k = 0; k < contact_vel.unilateral_ground.size(); ++k) {
             const UnilateralGround& c = contact_vel.unilateral_ground[k];

@@ -110,6 +110,27 @@ def test_deferred_activation_wakes_the_whole_island():
     assert rec[160][2] - rec[159][2] == 36
 
 
+def test_woken_island_is_warm_started_from_its_pre_sleep_impulses():
+    """The reference's impulse cache never forgets: the pairs of a sleeping island are filtered out of the
+    manifold list (mechanical_world.rs:287-300) but their cached impulses stay, so the island is warm-started
+    when it wakes.  The ground contact of stack B must carry (about) the stack's weight in the very step it
+    wakes -- not ramp up from zero -- and equal what it carried when it fell asleep."""
+    rec = run_scenario(new_oracle(), None, steps=165, wake_at=160)
+    sc = stacks_scene()
+    m, c = scenes.ContactGenerator(sc).generate()
+    ground_b = np.nonzero((m["body1"] == 0) & (m["body2"] == B[0]))[0]
+    assert len(ground_b) == 1
+    f, n = int(m["first_contact"][ground_b[0]]), int(m["num_contacts"][ground_b[0]])
+    weight_dt = 3 * 0.008 * 9.81 / 60.0
+    first_asleep = [k for k, r in enumerate(rec) if asleep(r[0], B)][0]
+    before = rec[first_asleep - 1][3][f:f + n, 0].sum()
+    during = rec[150][3][f:f + n, 0].sum()
+    woken = rec[160][3][f:f + n, 0].sum()
+    assert before == pytest.approx(weight_dt, rel=0.05)
+    assert during == before                  # carried, step after step, while the island sleeps
+    assert woken == pytest.approx(weight_dt, rel=0.05)
+
+
 def test_kinematic_body_keeps_its_island_awake():
     """Kinematic bodies are island members whose energy is never updated (activation_manager.rs:81-92):
     a dynamic box in contact with one cannot sleep, an identical isolated box does."""
