@@ -501,14 +501,23 @@ __global__ void k_apply_snapshot(size_t n, const int* __restrict__ it_a, const i
                                  const int* __restrict__ it_nrows, const int* __restrict__ it_type,
                                  const int* __restrict__ it_b1, const int* __restrict__ it_b2, int* prev_a, int* prev_b,
                                  int* prev_nt, int* prev_b1, int* prev_b2, const unsigned int* __restrict__ changed,
-                                 int* phase, unsigned long long* cmask) {
+                                 int* phase, unsigned long long* cmask, const unsigned int* __restrict__ ph_count_prev,
+                                 const SchedHeader* __restrict__ hdr) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int a = it_a[i], b = it_b[i], nt = (it_nrows[i] & 0xFF) | (it_type[i] << 8), b1 = it_b1[i], b2 = it_b2[i];
     if (*changed == NB2_SCHED_INCREMENTAL) {
         const int pa = prev_a[i], pb = prev_b[i];
         const bool was = (prev_nt[i] >> 8) != NB2_ITEM_INVALID, now = it_type[i] != NB2_ITEM_INVALID;
-        const bool same = pa == a && pb == b;
+        bool same = pa == a && pb == b;
+        // A colour that holds almost nothing (groups that found no room when they appeared) still costs the
+        // solve kernels a barrier and a latency chain per sweep: its groups try again every step -- room opens
+        // up as other groups vanish.  (Read before this step's layout kernels clear the previous counts.)
+        if (was && now && same) {
+            const int c = phase[i];
+            const unsigned int np_prev = hdr->n_phases, ng_prev = hdr->n_groups;
+            if (c >= 0 && (unsigned int)c < np_prev && np_prev > 1u && ph_count_prev[c] * 16u * np_prev < ng_prev) same = false;
+        }
         if (was && !(now && same)) {
             const int c = phase[i];
             if (c >= 0 && c < NB2_MAX_COLOURS) {
@@ -824,14 +833,16 @@ __global__ void k_phase_scan(const unsigned int* __restrict__ changed, unsigned 
                              unsigned int* ph_gbase, unsigned int* ph_rbase, SchedHeader* hdr) {
     if (*changed == 0u) return;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    unsigned int g = 0, r = 0;
+    unsigned int g = 0, r = 0, mx = 0;
     unsigned int np = hdr->n_phases;
     for (unsigned int p = 0; p < np; ++p) {
         ph_gbase[p] = g;
         ph_rbase[p] = r;
         g += ph_count[p];
         r += ph_count[p] * ph_R[p];
+        mx = max(mx, ph_count[p]);
     }
+    hdr->pad[1] = mx;  // the largest phase: the solve kernels size their blocks to it (one group per thread)
     ph_gbase[np] = g;
     ph_rbase[np] = r;
     hdr->n_groups = g;
@@ -897,7 +908,8 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
                                                   ctx->incremental_colouring ? 1 : 0);
         k_apply_snapshot<<<nblk(n), TPB, 0, ctx->stream>>>(n, s->it_a.p, s->it_b.p, s->it_nrows.p, s->it_type.p, s->it_b1.p,
                                                             s->it_b2.p, s->prev_a.p, s->prev_b.p, s->prev_nt.p, s->prev_b1.p,
-                                                            s->prev_b2.p, changed, s->it_phase.p, ctx->cmask.p);
+                                                            s->prev_b2.p, changed, s->it_phase.p, ctx->cmask.p, s->ph_count.p,
+                                                            s->hdr.p);
         ctx->launches += 2;
         s->cache_valid = true;
         s->cache_n = n;

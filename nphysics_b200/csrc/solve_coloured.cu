@@ -624,9 +624,13 @@ bool staged_geometry(Context* ctx, int* tpb_out, int* depth_out, int* blocks_out
     // (an asynchronous copy of the schedule header, never waited for), 8 before the first step
     unsigned int np = ctx->host_hdr ? ((volatile SchedHeader*)ctx->host_hdr)->n_phases : 0;
     size_t groups = ctx->host_hdr ? ((volatile SchedHeader*)ctx->host_hdr)->n_groups : 0;
+    size_t largest = ctx->host_hdr ? ((volatile SchedHeader*)ctx->host_hdr)->pad[1] : 0;
     if (np == 0 || np > NB2_MAX_COLOURS) np = 8;
     if (groups == 0 || groups > ctx->vs.n_items) groups = ctx->vs.n_items;
-    const size_t per_phase = (groups + np - 1) / np;
+    size_t per_phase = (groups + np - 1) / np;
+    // an edited (incremental) colouring is not balanced: size the blocks to the LARGEST phase, or its threads
+    // would run two groups back to back in every sweep
+    if (largest >= per_phase && largest <= groups) per_phase = largest;
     const size_t padded = per_phase + per_phase / 16 + 32;  // balancing tolerance
     // one warp of groups per block until every SM has a block, then wider blocks (a single fat block for
     // small scenes was measured: the grid barrier it saves is worth less than the SMs it gives up)

@@ -117,7 +117,7 @@ struct SchedHeader {
     unsigned int overflow;   // != 0: colouring ran out of colours / phases
     unsigned int work;       // scratch: "something changed" flag
     unsigned int refine_left;  // iterated-greedy passes still to run on steps whose conflict graph is unchanged
-    unsigned int pad[2];       // [0] incremental recolourings since the last colouring from scratch
+    unsigned int pad[2];       // [0] incremental recolourings since the last colouring from scratch, [1] groups of the largest phase
 };
 
 struct Sched {
