@@ -88,7 +88,9 @@ static int do_step_ccd(Context* ctx, int mode) {
     ctx->step_layout = (mode != NB2_MODE_REFERENCE_ORDER && ctx->contact_layout == 1 && ctx->contact_model == 0) ? 1 : 0;
     ctx->cur = 1 - ctx->cur;  // assembly warm-starts from the buffer "before cur": point it at the last one written
     NB2_TRY(launch_refresh_dynamics(ctx));
-    ctx->max_chunks = (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
+    // chunks (groups of <= 4 contacts): at most one per manifold plus one per four contacts; the device producer's
+    // manifolds own exactly one each
+    ctx->max_chunks = ctx->manifolds_from_producer ? (size_t)ctx->n_manifolds : (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
     NB2_TRY(launch_build_items(ctx, mode));
     NB2_TRY(launch_schedule(ctx, &ctx->vs, mode));
     if (mode == NB2_MODE_REFERENCE_ORDER) NB2_TRY(launch_schedule(ctx, &ctx->ps, mode));
@@ -115,7 +117,9 @@ static int do_step(Context* ctx, int mode) {
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[0], ctx->stream));
     // ---- dynamics refresh + assembly (Counters: "assembly")
     NB2_TRY(launch_refresh_dynamics(ctx));
-    ctx->max_chunks = (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
+    // chunks (groups of <= 4 contacts): at most one per manifold plus one per four contacts; the device producer's
+    // manifolds own exactly one each
+    ctx->max_chunks = ctx->manifolds_from_producer ? (size_t)ctx->n_manifolds : (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[10], ctx->stream));
     NB2_TRY(launch_build_items(ctx, mode));
     NB2_TRY(launch_schedule(ctx, &ctx->vs, mode));

@@ -219,6 +219,9 @@ struct ImpulseCacheView {
     const float4* ht_imps;
     size_t ht_cap;
     unsigned int* need_hash;
+    // the device producer's ids (4 p + i + 1) never leave the four slots of their pair: a contact that is in none
+    // of them was not there last step, and the hash table need not be built to find that out
+    int chunk_local_ids;
 };
 // fast path: both loads in flight together, one round trip
 __device__ __forceinline__ bool cache_fast_path(const ImpulseCacheView& C, unsigned int ci, unsigned long long key, float4* out) {
@@ -228,6 +231,23 @@ __device__ __forceinline__ bool cache_fast_path(const ImpulseCacheView& C, unsig
     if (pk != key) return false;
     *out = pv;
     return true;
+}
+// A contact that is not where it was may still sit in one of the four slots of its own chunk: the device
+// producer compacts a pair's kept corners to the front of the pair's slots, so a corner that drops out shifts
+// its siblings by one.  Looking there first keeps such steps off the hash path (which clears and rebuilds a
+// table over all contacts).
+__device__ __forceinline__ bool cache_chunk_path(const ImpulseCacheView& C, unsigned int chunk_first, unsigned int ci,
+                                                 unsigned long long key, float4* out) {
+#pragma unroll
+    for (unsigned int k = 0; k < NB2_CHUNK; ++k) {
+        const unsigned int j = chunk_first + k;
+        if (j == ci || j >= C.n_prev) continue;
+        if (C.ckey_prev[j] == key) {
+            *out = C.imp_prev[j];
+            return true;
+        }
+    }
+    return false;
 }
 __global__ void k_hash_clear(const unsigned int* __restrict__ need_hash, unsigned long long* keys, size_t cap) {
     if (*need_hash == 0u) return;
@@ -417,8 +437,8 @@ __global__ void __launch_bounds__(TPB, NB2_ASMG_MINBLOCKS) k_assemble_groups(
         float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c.key != 0ull) {  // impulse cache (signorini_coulomb_pyramid_model.rs:104-108)
             float4 prev;
-            if (cache_fast_path(cache, ci, c.key, &prev)) cached = prev;
-            else *cache.need_hash = 1u;  // k_warm_fixup patches this contact's warm start once the table exists
+            if (cache_fast_path(cache, ci, c.key, &prev) || cache_chunk_path(cache, ci0, ci, c.key, &prev)) cached = prev;
+            else if (!cache.chunk_local_ids) *cache.need_hash = 1u;  // k_warm_fixup patches this contact's warm start once the table exists
         }
         ContactSlots S;
         S.p = pbase + (size_t)lcc * cnt;
@@ -456,8 +476,9 @@ __global__ void __launch_bounds__(TPB) k_assemble_contacts(
     float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c.key != 0ull) {  // impulse cache (signorini_coulomb_pyramid_model.rs:104-108)
         float4 prev;
-        if (cache_fast_path(cache, ci, c.key, &prev)) cached = prev;
-        else *cache.need_hash = 1u;
+        if (cache_fast_path(cache, ci, c.key, &prev) || cache_chunk_path(cache, mf.first_contact + NB2_CHUNK * (lc / NB2_CHUNK), ci, c.key, &prev))
+            cached = prev;
+        else if (!cache.chunk_local_ids) *cache.need_hash = 1u;
     }
     const size_t item_f = (size_t)nJ + chunk, item_n = (size_t)nJ + maxc + chunk;
     ContactSlots S;
@@ -679,7 +700,8 @@ __global__ void __launch_bounds__(TPB) k_cache_contact_impulses(
         // mechanical_world.rs:287-300).  The reference's cache never forgets, so the entry is carried over and
         // the island is warm-started when it wakes: from the per-contact arrays when the contact kept its
         // index, else from the hash table if this step's assembly happened to build it.
-        if (key != 0ull && !cache_fast_path(prev, ci, key, &v)) {
+        if (key != 0ull && !cache_fast_path(prev, ci, key, &v) &&
+            !cache_chunk_path(prev, mf.first_contact + NB2_CHUNK * ((ci - mf.first_contact) / NB2_CHUNK), ci, key, &v)) {
             if (!(*prev.need_hash != 0u && ht_lookup(prev.ht_keys, prev.ht_imps, prev.ht_cap, key, &v)))
                 v = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -729,9 +751,10 @@ __global__ void __launch_bounds__(TPB) k_warm_fixup(
     const unsigned long long key = contacts[ci].key;
     if (key == 0ull) return;
     float4 v;
-    if (cache_fast_path(cache, ci, key, &v)) return;  // already warm-started by the assembly
-    if (!ht_lookup(cache.ht_keys, cache.ht_imps, cache.ht_cap, key, &v)) return;
     const nb2_manifold& mf = manifolds[m];
+    if (cache_fast_path(cache, ci, key, &v)) return;  // already warm-started by the assembly
+    if (cache_chunk_path(cache, mf.first_contact + NB2_CHUNK * ((ci - mf.first_contact) / NB2_CHUNK), ci, key, &v)) return;
+    if (!ht_lookup(cache.ht_keys, cache.ht_imps, cache.ht_cap, key, &v)) return;
     if (status[mf.body1] != NB2_BODY_DYNAMIC && status[mf.body2] != NB2_BODY_DYNAMIC) return;
     const unsigned int lc = ci - mf.first_contact;
     const unsigned int chunk = chunk_base[m] + lc / NB2_CHUNK;
@@ -863,6 +886,7 @@ int launch_assemble(Context* ctx, int mode) {
         cache.ht_imps = ctx->ht_imps[prev].p;
         cache.ht_cap = ctx->ht_cap[prev];
         cache.need_hash = need_hash;
+        cache.chunk_local_ids = ctx->manifolds_from_producer ? 1 : 0;
         NB2_CUDA(ctx, cudaMemsetAsync(need_hash, 0, sizeof(unsigned int), ctx->stream));
         if (ref) {
             k_assemble_contacts<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
@@ -920,6 +944,7 @@ int launch_cache_impulses(Context* ctx, int mode) {
         pv.ht_imps = ctx->ht_imps[prev].p;
         pv.ht_cap = ctx->ht_cap[prev];
         pv.need_hash = ctx->flags.p + 2;
+        pv.chunk_local_ids = ctx->manifolds_from_producer ? 1 : 0;
         k_cache_contact_impulses<<<nblk(ctx->n_contacts), TPB, 0, ctx->stream>>>(
             mode, ctx->n_contacts, ctx->n_joints, (unsigned int)ctx->max_chunks, ctx->manifolds.p, ctx->contacts.p,
             ctx->c_manifold.p, ctx->chunk_base.p, ctx->b_status.p, vs, ctx->r_imp.p, ctx->c_geo.p, ctx->n_pslots_max,

@@ -818,7 +818,12 @@ __global__ void k_phase_hist(const unsigned int* __restrict__ changed, size_t n,
                              unsigned int* ph_count, unsigned int* ph_R, SchedHeader* hdr, unsigned int max_phases) {
     if (*changed == 0u) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || it_type[i] == NB2_ITEM_INVALID) return;
+    const bool valid = i < n && it_type[i] != NB2_ITEM_INVALID;
+    {  // rows actually scheduled (hdr->work), against the padded slot count: the solve launcher's "ragged" hint
+        const unsigned int rows = __reduce_add_sync(0xffffffffu, valid && !NB2_Z_IS_COMPACT(it_nrows[i] | (it_type[i] << 8)) ? (unsigned int)it_nrows[i] : 0u);
+        if ((threadIdx.x & 31) == 0 && rows) atomicAdd(&hdr->work, rows);
+    }
+    if (!valid) return;
     unsigned int p = (unsigned int)phase[i];
     if (p >= max_phases) {
         p = max_phases - 1;

@@ -18,6 +18,7 @@ static const int TPB = SOLVE_TPB;
 int launch_velocity_solve_coloured(Context* ctx, const SchedDev& sd, const Rows& R, const CompactArrays& CA);
 int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd, const Rows& R, int tpb, int depth, int blocks);
 int launch_velocity_solve_bulk(Context* ctx, const SchedDev& sd, const Rows& R, int tpb, int depth, int blocks);
+int launch_velocity_solve_lockstep(Context* ctx, const SchedDev& sd, const Rows& R, int tpb, int depth, int blocks);
 bool staged_geometry(Context* ctx, int* tpb, int* depth, int* blocks);
 int launch_position_solve_staged(Context* ctx, const SchedDev& sd, const PosArrays& A, const PosParams& P, int rows_div,
                                  int tpb, int blocks);
@@ -399,6 +400,16 @@ int launch_velocity_solve(Context* ctx, int mode) {
         int tpb_s, depth_s, blocks_s;
         if (staged_geometry(ctx, &tpb_s, &depth_s, &blocks_s)) {
             if (ctx->velocity_kernel == 3) return launch_velocity_solve_bulk(ctx, sd, R, tpb_s, depth_s, blocks_s);
+            // 2 = automatic: groups of equal row counts (a settled pile: 12 rows everywhere) run the free-running
+            // per-thread rings, 0.81 ms on the 100k pile against 0.87 ms in lockstep; a ragged schedule (last step's
+            // header: scheduled rows < padded slots) runs in warp lockstep, which keeps the row copies coalesced
+            // (4096 x pyramid3 live: 15.3 ms against 16.6 ms).  4 / 5 force lockstep / free-running.
+            bool lockstep = ctx->velocity_kernel == 4;
+            if (ctx->velocity_kernel == 2 && ctx->host_hdr) {
+                const volatile SchedHeader* hh = (const volatile SchedHeader*)ctx->host_hdr;
+                lockstep = hh->n_slots != 0u && hh->work < hh->n_slots;
+            }
+            if (lockstep) return launch_velocity_solve_lockstep(ctx, sd, R, tpb_s, depth_s, blocks_s);
             return launch_velocity_solve_staged(ctx, sd, R, tpb_s, depth_s, blocks_s);
         }
     }

@@ -574,6 +574,209 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_bulk(SchedDev sd, Sta
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Lockstep row stream (NB2_VELOCITY_KERNEL=4): the per-thread cp.async ring of k_velocity_solve_staged with
+// the warp-uniform walk of k_velocity_solve_bulk.
+//
+// In k_velocity_solve_staged every thread walks its own (group, row) sequence, a ring entry per group header
+// and per row.  That is fine while all groups of a warp hold the same number of rows; once they do not (a live
+// scene: manifolds with 1..4 contacts side by side) a lane with a short group moves on to its next group while
+// its neighbours are still in theirs, and from then on the lanes of a warp copy rows of DIFFERENT row indices
+// at the same instruction: the 16-byte copies of a warp no longer fall into one 512-byte slice per plane.
+// Measured on 4096 x pyramid3 with 3 % of the manifolds ragged: 12.1 -> 16.2 ms.  Here the warp walks in
+// lockstep: every lane goes through max-over-the-warp rows per group (short groups commit empty copy groups
+// and are predicated off), so lane l always copies row r of group g0 + l: coalesced, whatever the row counts.
+// ------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(384, 1) k_velocity_solve_lockstep(SchedDev sd, StagedRows R, float4* lam, int iters,
+                                                                    unsigned int* barrier) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned int TPBK = blockDim.x;
+    float4* ring = reinterpret_cast<float4*>(smem_raw);                          // [D][6][TPBK]
+    float* simp = reinterpret_cast<float*>(ring + D * NB2_BULK_PLANES * TPBK);    // [12][TPBK]
+    unsigned int* s_cnt = reinterpret_cast<unsigned int*>(simp + 12 * TPBK);
+    unsigned int* s_rbase = s_cnt + NB2_MAX_COLOURS;
+    unsigned int* s_gbase = s_rbase + NB2_MAX_COLOURS;
+    const unsigned int np = min(sd.hdr->n_phases, (unsigned int)NB2_MAX_COLOURS);
+    if (np == 0) return;
+    const unsigned int t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    for (unsigned int i = t; i < np; i += TPBK) {
+        s_cnt[i] = sd.ph_count[i];
+        s_rbase[i] = sd.ph_rbase[i];
+        s_gbase[i] = sd.ph_gbase[i];
+    }
+    __syncthreads();
+    GridBarrier gb;
+    gb.init(barrier);
+    const unsigned int w0 = (warp * gridDim.x + blockIdx.x) * 32u;  // block-interleaved warps (interleaved_tid)
+    const unsigned int stride = gridDim.x * TPBK;
+    const unsigned long long pol = l2_evict_first_policy();
+    const unsigned int ring_u32 = (unsigned int)__cvta_generic_to_shared(ring) + t * 16u;
+    const unsigned int plane_b = TPBK * 16u, entry_b = NB2_BULK_PLANES * plane_b;
+
+    // ---- producer: D entries (rows) ahead of the consumer, warp-uniform position
+    WarpPos pc = {0, 0u, w0};
+    bool vc = seek_block(pc, w0, np, iters, s_cnt);
+    int p_rmax = 0, p_nr = 0, pr = 0;  // rows of the block being produced (warp max / this lane's), next row
+    unsigned int p_slot = 0, p_cnt = 0;
+    auto open_block = [&]() {
+        p_cnt = s_cnt[pc.p];
+        p_nr = 0;
+        if (pc.gw + lane < p_cnt) p_nr = __ldg(&sd.g_info[s_gbase[pc.p] + pc.gw + lane]).z & 0xFF;
+        p_rmax = __reduce_max_sync(0xffffffffu, p_nr);
+        p_slot = s_rbase[pc.p] + pc.gw + lane;
+        pr = 0;
+    };
+    if (vc) open_block();
+    int pe = 0;
+    auto produce = [&]() {
+        while (vc && pr >= p_rmax) {
+            pc.gw += stride;
+            vc = seek_block(pc, w0, np, iters, s_cnt);
+            if (vc) open_block();
+        }
+        if (vc) {
+            if (pr < p_nr) {
+                const unsigned int dst = ring_u32 + (unsigned int)pe * entry_b;
+                cp_async16_ef(dst + 1u * plane_b, R.q[1] + p_slot, pol);
+                cp_async16_ef(dst + 3u * plane_b, R.q[3] + p_slot, pol);
+                cp_async16_ef(dst + 4u * plane_b, R.q[4] + p_slot, pol);
+                cp_async16_ef(dst + 5u * plane_b, R.q[5] + p_slot, pol);
+                cp_async16_ef(dst, R.q[0] + p_slot, pol);
+                cp_async16_ef(dst + 2u * plane_b, R.q[2] + p_slot, pol);
+            }
+            p_slot += p_cnt;
+            ++pr;
+            pe = pe + 1 == D ? 0 : pe + 1;
+        }
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (int e = 0; e < D; ++e) produce();
+
+    int ce = 0;
+    WarpPos cn = {0, 0u, w0};
+    bool cv = seek_block(cn, w0, np, iters, s_cnt);
+    int4 info_n = make_int4(-1, -1, 0, 0);
+    if (cv && cn.gw + lane < s_cnt[cn.p]) info_n = __ldg(&sd.g_info[s_gbase[cn.p] + cn.gw + lane]);
+
+    for (int s = 0; s <= iters; ++s) {
+        for (unsigned int p = 0; p < np; ++p) {
+            const unsigned int cnt = s_cnt[p];
+            const unsigned int rbase = s_rbase[p];
+            for (unsigned int gw = w0; gw < cnt; gw += stride) {
+                const unsigned int g = gw + lane;
+                const bool active = g < cnt;
+                const int4 info = info_n;
+                {
+                    cn.gw += stride;
+                    cv = seek_block(cn, w0, np, iters, s_cnt);
+                    info_n = make_int4(-1, -1, 0, 0);
+                    if (cv && cn.gw + lane < s_cnt[cn.p]) info_n = __ldg(&sd.g_info[s_gbase[cn.p] + cn.gw + lane]);
+                }
+                const bool a = active && info.x >= 0, b = active && info.y >= 0;
+                const int nrows = active ? (info.z & 0xFF) : 0;
+                const int rmax = __reduce_max_sync(0xffffffffu, nrows);
+                const int ncc = (info.z >> 8) == NB2_ITEM_CONTACTS ? nrows / 3 : 0;
+                Lam la, lb;
+                la.im = lb.im = 0.f;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) la.v[k] = lb.v[k] = 0.f;
+                if (a) la = load_lam(lam, info.x);
+                if (b) lb = load_lam(lam, info.y);
+                {
+                    float v[12];
+#pragma unroll
+                    for (int r = 0; r < 12; ++r)
+                        if (r < nrows) v[r] = __ldcg(&R.imp[rbase + (unsigned int)r * cnt + g]);
+#pragma unroll
+                    for (int r = 0; r < 12; ++r)
+                        if (r < nrows) simp[r * TPBK + t] = v[r];
+                }
+                unsigned int cslot = rbase + g;
+#pragma unroll 1
+                for (int r = 0; r < rmax; ++r, cslot += cnt) {
+                    cp_async_wait<D - 1>();
+                    const float4* q = ring + (size_t)(ce * NB2_BULK_PLANES) * TPBK + t;
+                    ce = ce + 1 == D ? 0 : ce + 1;
+                    if (r < nrows) {
+                        RowPkt k;
+                        k.q0 = q[0 * TPBK];
+                        k.q1 = q[1 * TPBK];
+                        k.q2 = q[2 * TPBK];
+                        k.q3 = q[3 * TPBK];
+                        k.q4 = q[4 * TPBK];
+                        k.h = q[5 * TPBK];
+                        k.imp = simp[r * TPBK + t];
+                        const int kind = k.kind();
+                        RowJ J;
+                        unpack_pkt(k, true, true, la.im, lb.im, &J);
+                        if (s == 0) {  // warm start (sor_prox.rs:57-58, 345-435)
+                            const float w = kind == NB2_ROW_NONE ? 0.f : k.imp;
+                            if (a) axpy6(w, J.W1, la.v);
+                            if (b) axpy6(w, J.W2, lb.v);
+                        } else {
+                            float dep = 0.f;
+                            if (kind == NB2_ROW_DEPENDENT)
+                                dep = r < 2 * ncc ? simp[(2 * ncc + (r >> 1)) * TPBK + t] : __ldcg(&R.imp[k.dep()]);
+                            const float lim = k.h.z * dep;
+                            const float lo = kind == NB2_ROW_BILATERAL ? k.h.z : (kind == NB2_ROW_DEPENDENT ? -lim : 0.f);
+                            const float hi = kind == NB2_ROW_BILATERAL ? k.h.w : (kind == NB2_ROW_DEPENDENT ? lim : NB2_F32_MAX);
+                            float d = k.h.x;
+                            if (a) d += dot6(J.J1, la.v);
+                            if (b) d += dot6(J.J2, lb.v);
+                            float ni = fminf(fmaxf(k.imp - k.h.y * d, lo), hi);
+                            if (kind == NB2_ROW_NONE) ni = k.imp;
+                            const float dl = ni - k.imp;
+                            if (a) axpy6(dl, J.W1, la.v);
+                            if (b) axpy6(dl, J.W2, lb.v);
+                            if (ni != k.imp) __stcg(&R.imp[cslot], ni);
+                        }
+                    }
+                    produce();  // refills the entry just used (its values were consumed above)
+                }
+                if (a) store_lam(lam, info.x, la);
+                if (b) store_lam(lam, info.y, lb);
+            }
+            gb.sync();
+        }
+    }
+    cp_async_wait<0>();
+}
+
+static size_t lockstep_smem(int depth, int tpb) {
+    return (size_t)depth * NB2_BULK_PLANES * tpb * 16 + 12 * (size_t)tpb * 4 + 3 * NB2_MAX_COLOURS * 4;
+}
+
+int launch_velocity_solve_lockstep(Context* ctx, const SchedDev& sd_in, const Rows& R_in, int tpb, int depth, int blocks) {
+    SchedDev sd = sd_in;
+    StagedRows R;
+    for (int k = 0; k < NB2_ROW_PLANES; ++k) R.q[k] = R_in.jac + (size_t)k * R_in.S;
+    R.q[5] = R_in.hdr;
+    R.imp = R_in.imp;
+    if (depth < 3) depth = 3;
+    if (depth > 5) depth = 5;
+    while (depth > 3 && lockstep_smem(depth, tpb) > ctx->smem_optin) --depth;
+    const size_t smem = lockstep_smem(depth, tpb);
+    void* kernel = depth == 3 ? (void*)k_velocity_solve_lockstep<3>
+                 : depth == 4 ? (void*)k_velocity_solve_lockstep<4> : (void*)k_velocity_solve_lockstep<5>;
+    if (!ctx->lockstep_attr) {
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_lockstep<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_lockstep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        NB2_CUDA(ctx, cudaFuncSetAttribute(k_velocity_solve_lockstep<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+        ctx->lockstep_attr = true;
+    }
+    float4* lam = ctx->lam.p;
+    int iters = (int)ctx->params.max_velocity_iterations;
+    unsigned int* bar = ctx->barrier.p;
+    void* args[] = {&sd, &R, &lam, &iters, &bar};
+    if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
+    NB2_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(tpb), args, smem, ctx->stream));
+    if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[7], ctx->stream));
+    ctx->launches++;
+    return NB2_OK;
+}
+
 static size_t bulk_smem(int depth, int tpb) {
     const size_t nw = (size_t)tpb / 32;
     return nw * depth * NB2_BULK_PLANES * 32 * 16 + nw * 12 * 32 * 4 + nw * depth * 8 + 3 * NB2_MAX_COLOURS * 4;

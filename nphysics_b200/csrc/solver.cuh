@@ -115,7 +115,7 @@ struct SchedHeader {
     unsigned int n_groups;   // total scheduled items
     unsigned int n_slots;    // total row slots
     unsigned int overflow;   // != 0: colouring ran out of colours / phases
-    unsigned int work;       // scratch: "something changed" flag
+    unsigned int work;       // velocity rows actually scheduled (n_slots counts the ELL padding too)
     unsigned int refine_left;  // iterated-greedy passes still to run on steps whose conflict graph is unchanged
     unsigned int pad[2];       // [0] incremental recolourings since the last colouring from scratch, [1] groups of the largest phase
 };
@@ -269,13 +269,14 @@ struct Context {
     // co-resident block limits of the cooperative kernels on this context's device (queried once)
     int coop_blocks_vel = 0, coop_blocks_pos = 0, coop_blocks_col = 0, coop_blocks_level = 0, coop_blocks_colour = 0,
         coop_blocks_islands = 0;
-    // coloured solve kernels: 0 = phase barrier + register pipelining (the reference-order kernels), 2 =
-    // staged (rows streamed through a shared-memory ring with cp.async, prefetched across the phase
-    // barrier; the default).  NB2_VELOCITY_KERNEL overrides (A/B runs, tests).
+    // coloured solve kernels: 0 = phase barrier + register pipelining (the reference-order kernels), 2 = staged
+    // (rows streamed through a shared-memory ring with cp.async, prefetched across the phase barrier; the default:
+    // free-running rings for a uniform schedule, warp lockstep for a ragged one), 3 = ring filled by cp.async.bulk,
+    // 4 / 5 = force lockstep / free-running.  NB2_VELOCITY_KERNEL overrides (A/B runs, tests).
     int velocity_kernel = 2;
     bool poison_rows = false;      // NB2_POISON_ROWS: fill the row planes with NaN bits before every assembly (tests)
     size_t smem_optin = 0;         // cudaDevAttrMaxSharedMemoryPerBlockOptin
-    bool staged_attr = false, staged_pos_attr = false, bulk_attr = false;
+    bool staged_attr = false, staged_pos_attr = false, bulk_attr = false, lockstep_attr = false;
     DevBuf<float4> p_hdr;          // [5][n_ghdr_max] coloured position groups: bodies + collider-to-body poses
     size_t n_ghdr_max = 0;
     void* host_hdr = nullptr;      // pinned copy of vs.hdr (launch-geometry hint, never waited for)

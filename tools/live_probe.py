@@ -12,10 +12,14 @@ from nphysics_b200.solver import Solver  # noqa: E402
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 120
-    sc = scenes.boxes3(50, 40, 50)
-    p = abi.default_params()
-    p["max_velocity_iterations"] = 10
-    p["max_position_iterations"] = 5
+    if len(sys.argv) > 2 and sys.argv[2].startswith("pyramids"):
+        sc = scenes.tile(scenes.pyramid3(30), int(sys.argv[2][8:] or 4096))
+        p = abi.default_params()
+    else:
+        sc = scenes.boxes3(50, 40, 50)
+        p = abi.default_params()
+        p["max_velocity_iterations"] = 10
+        p["max_position_iterations"] = 5
     s = Solver(0)
     s.set_params(p)
     s.upload_bodies(sc.bodies)
