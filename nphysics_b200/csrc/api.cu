@@ -30,7 +30,7 @@ int set_error(Context* ctx, int code, const char* fmt, ...) {
 }
 
 static void release_all(Context* c) {
-    c->raw.release(); c->pos_t.release(); c->pos_q.release(); c->vel.release(); c->com_im.release();
+    c->raw.release(); c->pos.release(); c->pos_t.p.p = c->pos_q.p.p = nullptr; c->vel.release(); c->com_im.release();
     c->inv_i.release(); c->ext.release(); c->lam.release(); c->b_status.release(); c->joints.release();
     c->manifolds.release(); c->contacts.release(); c->c_manifold.release(); c->chunk_base.release();
     c->chunk_manifold.release();
@@ -362,8 +362,9 @@ int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
     NB2_CUDA(ctx, cudaSetDevice(ctx->device));
     NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // buffers may be reallocated
     NB2_TRY(ctx->raw.reserve(ctx, n));
-    NB2_TRY(ctx->pos_t.reserve(ctx, n));
-    NB2_TRY(ctx->pos_q.reserve(ctx, n));
+    NB2_TRY(ctx->pos.reserve(ctx, 2 * (size_t)n));
+    ctx->pos_t.p.p = ctx->pos.p;
+    ctx->pos_q.p.p = ctx->pos.p + 1;
     NB2_TRY(ctx->vel.reserve(ctx, 2 * (size_t)n));
     NB2_TRY(ctx->com_im.reserve(ctx, n));
     NB2_TRY(ctx->inv_i.reserve(ctx, 3 * (size_t)n));

@@ -49,8 +49,8 @@ static inline SchedView view_of(const Sched& s) {
 
 struct BodyArrays {
     const nb2_body* raw;
-    const float4* pos_t;
-    const float4* pos_q;
+    ConstPoseQuads pos_t;
+    ConstPoseQuads pos_q;
     const float4* vel;
     const float4* com_im;
     const float4* inv_i;

@@ -13,7 +13,7 @@ static const int TPB = 256;
 static inline unsigned int nblk(size_t n) { return (unsigned int)((n + TPB - 1) / TPB); }
 
 // raw AoS -> live SoA state (after nb2_upload_bodies)
-__global__ void k_unpack_bodies(const nb2_body* __restrict__ raw, unsigned int n, float4* pos_t, float4* pos_q,
+__global__ void k_unpack_bodies(const nb2_body* __restrict__ raw, unsigned int n, PoseQuads pos_t, PoseQuads pos_q,
                                 float4* vel, float4* com_im, int* status, int* true_status) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -32,7 +32,7 @@ __global__ void k_unpack_bodies(const nb2_body* __restrict__ raw, unsigned int n
 }
 
 __global__ void k_unpack_states(const nb2_body_state* __restrict__ in, const nb2_body* __restrict__ raw,
-                                unsigned int first, unsigned int n, float4* pos_t, float4* pos_q, float4* vel,
+                                unsigned int first, unsigned int n, PoseQuads pos_t, PoseQuads pos_q, float4* vel,
                                 float4* com_im) {
     unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -52,7 +52,7 @@ __global__ void k_unpack_states(const nb2_body_state* __restrict__ in, const nb2
 }
 
 __global__ void k_pack_states(nb2_body_state* out, unsigned int first, unsigned int n,
-                              const float4* __restrict__ pos_t, const float4* __restrict__ pos_q,
+                              ConstPoseQuads pos_t, ConstPoseQuads pos_q,
                               const float4* __restrict__ vel) {
     unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -68,7 +68,7 @@ __global__ void k_pack_states(nb2_body_state* out, unsigned int first, unsigned 
 // One thread per body.  World inertia, gyroscopic augmented mass and its inverse,
 // acceleration, ext_vels = dt * acceleration; clears mj_lambda.
 __global__ void k_refresh_dynamics(const nb2_body* __restrict__ raw, unsigned int n, float dt, Vec3 gravity,
-                                   const float4* __restrict__ pos_q, const float4* __restrict__ vel,
+                                   ConstPoseQuads pos_q, const float4* __restrict__ vel,
                                    float4* com_im, float4* inv_i, float4* ext, float4* lam) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -128,7 +128,7 @@ __global__ void k_refresh_dynamics(const nb2_body* __restrict__ raw, unsigned in
 
 // v += ext_vels + mj_lambda; damping; velocity caps; displacement about the com.
 __global__ void k_integrate(const nb2_body* __restrict__ raw, unsigned int n, float dt, int kinematic_only,
-                            float4* pos_t, float4* pos_q, float4* vel, float4* com_im,
+                            PoseQuads pos_t, PoseQuads pos_q, float4* vel, float4* com_im,
                             const float4* __restrict__ ext, const float4* __restrict__ lam) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -169,8 +169,8 @@ __global__ void k_integrate(const nb2_body* __restrict__ raw, unsigned int n, fl
 }
 
 // kinetic energy + non-finite guard
-__global__ void k_body_stats(const nb2_body* __restrict__ raw, unsigned int n, const float4* __restrict__ pos_t,
-                             const float4* __restrict__ pos_q, const float4* __restrict__ vel, double* energy,
+__global__ void k_body_stats(const nb2_body* __restrict__ raw, unsigned int n, ConstPoseQuads pos_t,
+                             ConstPoseQuads pos_q, const float4* __restrict__ vel, double* energy,
                              unsigned int* non_finite) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     double ke = 0.0;

@@ -67,7 +67,7 @@ __device__ __forceinline__ ColliderRec load_collider(const nb2_collider* __restr
 
 // collider centre in world space + classification
 __global__ void k_collider_world(const nb2_collider* __restrict__ colliders, unsigned int n,
-                                 const float4* __restrict__ pos_t, const float4* __restrict__ pos_q,
+                                 ConstPoseQuads pos_t, ConstPoseQuads pos_q,
                                  const int* __restrict__ status, float4* cw, unsigned int* is_big, unsigned int* np_par) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -261,8 +261,8 @@ __device__ __forceinline__ float combine_coeff_dev(float a, unsigned int ma, flo
 // and num_contacts says how many there are -- possibly none, in which case the manifold emits no rows.
 __global__ void __launch_bounds__(TPB) k_generate_manifolds(unsigned int n_pairs, PairOut pairs,
                                                             const nb2_collider* __restrict__ colliders,
-                                                            const float4* __restrict__ pos_t,
-                                                            const float4* __restrict__ pos_q, float prediction,
+                                                            ConstPoseQuads pos_t,
+                                                            ConstPoseQuads pos_q, float prediction,
                                                             nb2_manifold* manifolds, nb2_contact* contacts) {
     const unsigned int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;

@@ -113,6 +113,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 #ifdef NB2_TRACE  // developer build (make EXTRA=-DNB2_TRACE): per-phase timestamps, see DESIGN.md "Developer knobs"
 __device__ unsigned long long g_trace[4096];
+__device__ unsigned long long g_ptrace[512 * 8];  // position kernel: per phase visit, see the printf at its end
 #endif
 __device__ __forceinline__ void cp_async_wait_dyn(int pending) {  // pending in 0..2
     if (pending <= 0) cp_async_wait<0>();
@@ -992,9 +993,17 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
         unsigned int displaced = 0;
         for (unsigned int p = 0; p < np; ++p) {
             const unsigned int cnt = s_cnt[p];
+#ifdef NB2_TRACE
+            const bool tracer = blockIdx.x == 0 && threadIdx.x == 0 && it * np + p < 512;
+            unsigned long long* tr = g_ptrace + (it * np + p) * 8;
+            if (tracer) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[0]));
+#endif
             for (unsigned int gw = tid - lane; gw < cnt; gw += stride) {
                 if (gw + lane >= cnt) continue;
                 cp_async_wait_dyn(E - 1);
+#ifdef NB2_TRACE
+                if (tracer) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[1]));
+#endif
                 const int e = ce;
                 ce = ce + 1 == E ? 0 : ce + 1;
                 const float4* q = ring + (size_t)(e * NB2_PENTRY) * TPBK + t;
@@ -1017,8 +1026,6 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                 } else {
                     const float4 h0 = q[0], h1 = q[1 * TPBK], h2 = q[2 * TPBK], h3 = q[3 * TPBK], h4 = q[4 * TPBK];
                     const int body1 = __float_as_int(h0.x), body2 = __float_as_int(h0.y);
-                    load_pos_body(A, body1, &b1);
-                    load_pos_body(A, body2, &b2);
                     Pose c1, c2;
                     c1.t = mk3(h1.x, h1.y, h1.z);
                     c1.r = mkq(h1.w, h2.x, h2.y, h2.z);
@@ -1028,6 +1035,11 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                     // colliders sitting at their body's origin (the usual case) need no pose product
                     const bool id1 = h1.x == 0.f && h1.y == 0.f && h1.z == 0.f && h1.w == 0.f && h2.x == 0.f && h2.y == 0.f && h2.z == 1.f;
                     const bool id2 = h3.x == 0.f && h3.y == 0.f && h3.z == 0.f && h3.w == 0.f && h4.x == 0.f && h4.y == 0.f && h4.z == 1.f;
+                    load_pos_body(A, body1, &b1);
+                    load_pos_body(A, body2, &b2);
+#ifdef NB2_TRACE
+                    if (tracer) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[2]) : "f"(b1.bp.pose.t.x), "f"(b2.bp.com.z), "f"(b1.inv_i.m[2][2]), "f"(b2.mask[5]));
+#endif
                     bool moved1 = false, moved2 = false;
 #pragma unroll 1
                     for (int lcc = 0; lcc < ncc; ++lcc) {
@@ -1055,6 +1067,9 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                             moved2 = true;
                         }
                     }
+#ifdef NB2_TRACE
+                    if (tracer) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[3]) : "f"(b1.bp.pose.t.x), "f"(b2.bp.com.z), "r"((int)moved1), "r"((int)moved2));
+#endif
                     if (moved1) store_pos_body(A, body1, b1);
                     if (moved2) store_pos_body(A, body2, b2);
                     displaced |= (unsigned int)(moved1 || moved2);
@@ -1069,7 +1084,11 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
                     s_displaced = 0u;  // the grid barrier below orders this before the next sweep's writers
                 }
             }
+#ifdef NB2_TRACE
+            gb.sync_traced(tracer ? tr + 4 : nullptr);
+#else
             gb.sync();
+#endif
         }
         if (early_exit) {
             const unsigned int moves = __ldcg(&sweep_moves[it % 3]);
@@ -1078,6 +1097,15 @@ __global__ void __launch_bounds__(384, 1) k_position_solve_staged(SchedDev sd, P
         }
     }
     cp_async_wait<0>();
+#ifdef NB2_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (unsigned int i = 0; i < min((unsigned int)iters * np, 512u); ++i) {
+            const unsigned long long* tr = g_ptrace + i * 8;
+            printf("pos sweep %u phase %u groups %u | ring %llu bodies %llu contacts %llu block-arrive %llu fence %llu grid %llu | total %llu ns\n",
+                   i / np, i % np, s_cnt[i % np], tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4],
+                   tr[6] - tr[5], tr[6] - tr[0]);
+        }
+#endif
 }
 
 int launch_position_solve_staged(Context* ctx, const SchedDev& sd_in, const PosArrays& A_in, const PosParams& P_in,

@@ -17,8 +17,8 @@ struct PosBody {
 };
 struct PosArrays {
     const nb2_body* raw;
-    float4* pos_t;
-    float4* pos_q;
+    PoseQuads pos_t;
+    PoseQuads pos_q;
     float4* com_im;
     const float4* inv_i;
 };

@@ -74,6 +74,17 @@ struct DevBuf {
     }
 };
 
+// Strided view of the interleaved pose buffer: element i is quad 2 * i (+ 1 for the rotation).
+struct ConstPoseQuads {
+    const float4* p;
+    __host__ __device__ __forceinline__ const float4& operator[](size_t i) const { return p[2 * i]; }
+};
+struct PoseQuads {
+    float4* p;
+    __host__ __device__ __forceinline__ float4& operator[](size_t i) const { return p[2 * i]; }
+    __host__ __device__ __forceinline__ operator ConstPoseQuads() const { return ConstPoseQuads{p}; }
+};
+
 // ---------------------------------------------------------------------------
 // scheduling
 // ---------------------------------------------------------------------------
@@ -184,7 +195,11 @@ struct Context {
     uint32_t n_bodies = 0;
     uint32_t n_dynamic = 0;
     DevBuf<nb2_body> raw;         // static properties (pose/velocity fields are upload-time values)
-    DevBuf<float4> pos_t, pos_q;  // live pose
+    // live pose: (t.xyz, 0) and the rotation quaternion of a body are neighbours in ONE buffer, so a pose is one
+    // 32-byte sector (the position solve gathers two poses per group visit and is bound by the sectors it pulls
+    // through the SM's L2 port, profiles/r02_notes.md); pos_t.p / pos_q.p are strided views of it
+    DevBuf<float4> pos;
+    struct PoseView { PoseQuads p; } pos_t, pos_q;
     DevBuf<float4> vel;           // [2n] linear, angular
     DevBuf<float4> com_im;        // com.xyz, inverse mass
     DevBuf<float4> inv_i;         // [3n] rows of the inverse augmented angular inertia
@@ -315,6 +330,26 @@ struct GridBarrier {
         }
         __syncthreads();
     }
+#ifdef NB2_TRACE
+    // the same barrier, block 0 / thread 0 leaving timestamps: [0] whole block arrived, [1] arrival published (the
+    // release fence has drained), [2] every block arrived
+    __device__ void sync_traced(unsigned long long* ts) {
+        __syncthreads();
+        if (gridDim.x == 1) return;
+        if (threadIdx.x == 0) {
+            if (ts) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[0]));
+            target += gridDim.x;
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+            if (ts) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[1]));
+            unsigned int v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            } while (v < target);
+            if (ts) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[2]));
+        }
+        __syncthreads();
+    }
+#endif
 };
 
 // Live body state as the kernels see it.
