@@ -79,7 +79,11 @@ typedef enum nb2_body_status {
     NB2_BODY_DISABLED = 0,
     NB2_BODY_STATIC = 1,
     NB2_BODY_DYNAMIC = 2,
-    NB2_BODY_KINEMATIC = 3
+    NB2_BODY_KINEMATIC = 3,
+    /* The record stands for one link of a multibody (nb2_mb_link.body points at it): manifolds and colliders refer
+     * to the link through this body index; its pose, centre of mass and velocity are OUTPUTS, written by the
+     * multibody kinematics (MultibodyLink::position / velocity, src/object/multibody_link.rs). */
+    NB2_BODY_MULTIBODY_LINK = 4
 } nb2_body_status;
 
 #define NB2_BODY_FLAG_GRAVITY 1u /* RigidBody.gravity_enabled (rigid_body.rs:43) */
@@ -240,6 +244,53 @@ typedef struct nb2_joint {
     uint32_t broken; /* set by the solver when a break threshold is exceeded */
 } nb2_joint;
 
+/* -------------------------------------------------------------- multibodies */
+/* Reduced-coordinate articulated bodies (src/object/multibody.rs, multibody_link.rs).
+ * A multibody is a tree of links; link k hangs on its parent through a joint that owns ndofs generalized
+ * coordinates.  Links of one multibody are contiguous and a parent precedes its children
+ * (MultibodyDesc::build order, multibody.rs:1433-1470). */
+typedef enum nb2_mb_joint_type {
+    NB2_MBJ_FREE = 0,      /* free_joint.rs: 6 dofs (only as the root) */
+    NB2_MBJ_BALL = 1,      /* ball_joint.rs: 3 dofs                     */
+    NB2_MBJ_REVOLUTE = 2,  /* revolute_joint.rs: 1 dof, limits + motor  */
+    NB2_MBJ_PRISMATIC = 3, /* prismatic_joint.rs: 1 dof, limits + motor */
+    NB2_MBJ_FIXED = 4,     /* fixed_joint.rs: 0 dofs                    */
+    NB2_MBJ_TYPE_COUNT = 5
+} nb2_mb_joint_type;
+#define NB2_MBJ_FLAG_MIN 1u   /* min_angle / min_offset is Some(..) */
+#define NB2_MBJ_FLAG_MAX 2u   /* max_angle / max_offset is Some(..) */
+#define NB2_MBJ_FLAG_MOTOR 4u /* JointMotor.enabled (joint_motor.rs) */
+#define NB2_MB_MAX_DOFS 64    /* generalized coordinates of one multibody */
+
+typedef struct nb2_mb_link {
+    int32_t multibody;      /* index into the nb2_multibody array */
+    int32_t parent;         /* link index WITHIN the multibody, -1 = root (its parent is the ground) */
+    uint32_t joint_type;    /* nb2_mb_joint_type */
+    uint32_t flags;         /* NB2_MBJ_FLAG_* */
+    int32_t body;           /* the link's NB2_BODY_MULTIBODY_LINK record (mass properties are read from it:
+                               mass, local_inertia, local_com) */
+    float parent_shift[3];  /* MultibodyLink.parent_shift: joint anchor in the parent's frame */
+    float body_shift[3];    /* MultibodyLink.body_shift: joint anchor to the link's origin, in the link's frame */
+    float axis[3];          /* revolute / prismatic: unit axis */
+    /* joint coordinates.  Free: translation xyz + quaternion ijkw; Ball: quaternion ijkw in [0..4);
+     * Revolute: angle in [0]; Prismatic: offset in [0]; Fixed: body_to_parent isometry (t, q). */
+    float coords[7];
+    float velocity[6];      /* generalized velocities of the link's dofs (first ndofs entries) */
+    float damping[6];       /* Multibody.damping of the link's dofs (Joint::default_damping: 0.1 for ball / revolute) */
+    float min_pos, max_pos; /* unit joints: limits */
+    float motor_velocity;   /* JointMotor.desired_velocity */
+    float motor_max_velocity;
+    float motor_max_force;
+    float impulses[3];      /* unit joints: cached impulses of the motor, min and max rows (unit_joint.rs:77,113,153) */
+} nb2_mb_link;
+
+typedef struct nb2_multibody {
+    uint32_t first_link;
+    uint32_t n_links;
+    uint32_t flags;         /* NB2_BODY_FLAG_GRAVITY */
+    uint32_t reserved;
+} nb2_multibody;
+
 /* ------------------------------------------------------------------- step */
 typedef enum nb2_step_mode {
     /* Replays the reference's sequential Gauss-Seidel order exactly (rows are
@@ -287,7 +338,7 @@ const char* nb2_error_string(int err);
 int nb2_default_params(nb2_params* out);
 /* sizeof() of each ABI struct, for binding self-checks:
  * which: 0 params, 1 body, 2 body_state, 3 manifold, 4 contact, 5 joint, 6 stats, 7 activation,
- * 8 contact_update, 9 collider */
+ * 8 contact_update, 9 collider, 10 mb_link, 11 multibody */
 int nb2_sizeof(int which);
 /* Material::combine for two BasicMaterials (material.rs:72-86,134-177,
  * basic_material.rs:30-43).  mode: 0 Average, 1 Min, 2 Multiply, 3 Max.
@@ -364,6 +415,14 @@ int nb2_download_manifolds(nb2_context* ctx, nb2_manifold* out_manifolds, uint32
 /* The active joint set, in island_joints order.  Cached impulses/broken flags
  * in the records seed the device copy. */
 int nb2_upload_joints(nb2_context* ctx, const nb2_joint* joints, uint32_t n_joints);
+/* Multibodies (Multibody / MultibodyDesc::build, src/object/multibody.rs:1311-1470).  Upload after the bodies: every
+ * link names its NB2_BODY_MULTIBODY_LINK record.  Only dynamic multibodies; they never sleep.  The step writes the
+ * links' joint coordinates, generalized velocities and cached impulses back into the device copy
+ * (nb2_download_multibody_links) and the links' world poses / velocities into their body records
+ * (nb2_download_body_states). */
+int nb2_upload_multibodies(nb2_context* ctx, const nb2_multibody* multibodies, uint32_t n_multibodies,
+                           const nb2_mb_link* links, uint32_t n_links);
+int nb2_download_multibody_links(nb2_context* ctx, nb2_mb_link* out, uint32_t n_links);
 /* ContactModel selection (src/solver/contact_model.rs:13-37, MoreauJeanSolver::set_contact_model,
  * moreau_jean_solver.rs:42-44).  The reference ships two models:
  *   NB2_CONTACT_SIGNORINI_COULOMB_PYRAMID (default, moreau_jean_solver.rs:29-40): one unilateral normal

@@ -22,7 +22,7 @@ ERR_NOT_READY = -8
 ERR_NON_FINITE = -9
 
 # nb2_body_status
-BODY_DISABLED, BODY_STATIC, BODY_DYNAMIC, BODY_KINEMATIC = 0, 1, 2, 3
+BODY_DISABLED, BODY_STATIC, BODY_DYNAMIC, BODY_KINEMATIC, BODY_MULTIBODY_LINK = 0, 1, 2, 3, 4
 BODY_FLAG_GRAVITY = 1
 
 # nb2_kinematic_geom
@@ -32,6 +32,12 @@ GEOM_POINT, GEOM_LINE, GEOM_PLANE = 0, 1, 2
 (JOINT_BALL, JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_UNIVERSAL, JOINT_PLANAR, JOINT_RECTANGULAR,
  JOINT_PIN_SLOT, JOINT_CYLINDRICAL, JOINT_FIXED, JOINT_CARTESIAN) = range(10)
 JOINT_FLAG_MIN_OFFSET, JOINT_FLAG_MAX_OFFSET = 1, 2
+
+# nb2_mb_joint_type (reduced-coordinate joints of a multibody link)
+MBJ_FREE, MBJ_BALL, MBJ_REVOLUTE, MBJ_PRISMATIC, MBJ_FIXED = range(5)
+MBJ_FLAG_MIN, MBJ_FLAG_MAX, MBJ_FLAG_MOTOR = 1, 2, 4
+MBJ_NDOFS = {MBJ_FREE: 6, MBJ_BALL: 3, MBJ_REVOLUTE: 1, MBJ_PRISMATIC: 1, MBJ_FIXED: 0}
+MB_MAX_DOFS = 64
 
 # nb2_step_mode
 MODE_REFERENCE_ORDER, MODE_COLOURED = 0, 1
@@ -103,9 +109,17 @@ collider_dtype = np.dtype([
     ("rotation_wrt_body", f4, 4), ("restitution", f4), ("body", i4), ("friction_mode", u1),
     ("restitution_mode", u1), ("pad_", u1, 2), ("flags", u4)], align=True)
 
+# nb2_mb_link / nb2_multibody: reduced-coordinate multibodies
+mb_link_dtype = np.dtype([
+    ("multibody", i4), ("parent", i4), ("joint_type", u4), ("flags", u4), ("body", i4),
+    ("parent_shift", f4, 3), ("body_shift", f4, 3), ("axis", f4, 3), ("coords", f4, 7), ("velocity", f4, 6),
+    ("damping", f4, 6), ("min_pos", f4), ("max_pos", f4), ("motor_velocity", f4), ("motor_max_velocity", f4),
+    ("motor_max_force", f4), ("impulses", f4, 3)], align=True)
+multibody_dtype = np.dtype([("first_link", u4), ("n_links", u4), ("flags", u4), ("reserved", u4)], align=True)
+
 SIZEOF_ORDER = [params_dtype, body_dtype, body_state_dtype, manifold_dtype, contact_dtype, joint_dtype,
-                stats_dtype, activation_dtype, contact_update_dtype, collider_dtype]
-EXPECTED_SIZES = [64, 176, 52, 100, 112, 160, 88, 8, 40, 64]
+                stats_dtype, activation_dtype, contact_update_dtype, collider_dtype, mb_link_dtype, multibody_dtype]
+EXPECTED_SIZES = [64, 176, 52, 100, 112, 160, 88, 8, 40, 64, 164, 16]
 
 for _d, _s in zip(SIZEOF_ORDER, EXPECTED_SIZES):
     assert _d.itemsize == _s, (_d, _d.itemsize, _s)
@@ -179,3 +193,39 @@ def contact_updates_of(contacts):
     for f in ("world1", "world2", "normal", "depth"):
         u[f] = contacts[f]
     return u
+
+
+def new_mb_links(n, joint_type=MBJ_BALL):
+    """n multibody links with the joints' defaults: identity coordinates, Joint::default_damping (0.1 on the dofs
+    of ball and revolute joints: ball_joint.rs:89-91, revolute_joint.rs:214-216), no limits, JointMotor::new()."""
+    l = np.zeros(n, dtype=mb_link_dtype)
+    l["parent"] = -1
+    l["joint_type"] = joint_type
+    l["body"] = -1
+    l["axis"][:, 0] = 1.0
+    l["motor_max_velocity"] = FLT_MAX
+    l["motor_max_force"] = FLT_MAX
+    set_mb_joint(l, slice(None), joint_type)
+    return l
+
+
+def set_mb_joint(links, idx, joint_type):
+    """Sets the joint type of links[idx] together with its identity coordinates and default damping."""
+    links["joint_type"][idx] = joint_type
+    links["coords"][idx] = 0.0
+    links["damping"][idx] = 0.0
+    if joint_type in (MBJ_FREE, MBJ_FIXED):
+        c = links["coords"][idx]
+        c[..., 6] = 1.0
+        links["coords"][idx] = c
+    elif joint_type == MBJ_BALL:
+        c = links["coords"][idx]
+        c[..., 3] = 1.0
+        links["coords"][idx] = c
+        d = links["damping"][idx]
+        d[..., :3] = 0.1
+        links["damping"][idx] = d
+    elif joint_type == MBJ_REVOLUTE:
+        d = links["damping"][idx]
+        d[..., 0] = 0.1
+        links["damping"][idx] = d

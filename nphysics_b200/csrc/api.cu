@@ -30,6 +30,7 @@ int set_error(Context* ctx, int code, const char* fmt, ...) {
 }
 
 static void release_all(Context* c) {
+    mb_release(c);
     c->raw.release(); c->pos.release(); c->pos_t.p.p = c->pos_q.p.p = nullptr; c->vel.release(); c->com_im.release();
     c->inv_i.release(); c->ext.release(); c->lam.release(); c->b_status.release(); c->joints.release();
     c->manifolds.release(); c->contacts.release(); c->c_manifold.release(); c->chunk_base.release();
@@ -88,6 +89,7 @@ static int do_step_ccd(Context* ctx, int mode) {
     ctx->step_layout = (mode != NB2_MODE_REFERENCE_ORDER && ctx->contact_layout == 1 && ctx->contact_model == 0) ? 1 : 0;
     ctx->cur = 1 - ctx->cur;  // assembly warm-starts from the buffer "before cur": point it at the last one written
     NB2_TRY(launch_refresh_dynamics(ctx));
+    NB2_TRY(mb_launch_refresh(ctx));  // multibodies: kinematics, dynamics, accelerations; their links' body records follow
     // chunks (groups of <= 4 contacts): at most one per manifold plus one per four contacts; the device producer's
     // manifolds own exactly one each
     ctx->max_chunks = ctx->manifolds_from_producer ? (size_t)ctx->n_manifolds : (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
@@ -117,6 +119,7 @@ static int do_step(Context* ctx, int mode) {
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[0], ctx->stream));
     // ---- dynamics refresh + assembly (Counters: "assembly")
     NB2_TRY(launch_refresh_dynamics(ctx));
+    NB2_TRY(mb_launch_refresh(ctx));  // multibodies: kinematics, dynamics, accelerations; their links' body records follow
     // chunks (groups of <= 4 contacts): at most one per manifold plus one per four contacts; the device producer's
     // manifolds own exactly one each
     ctx->max_chunks = ctx->manifolds_from_producer ? (size_t)ctx->n_manifolds : (size_t)ctx->n_manifolds + ctx->n_contacts / NB2_CHUNK;
@@ -138,6 +141,7 @@ static int do_step(Context* ctx, int mode) {
     // ---- velocity resolution + impulse caching (Counters: "velocity resolution")
     NB2_TRY(launch_velocity_solve(ctx, mode));
     NB2_TRY(launch_cache_impulses(ctx, mode));
+    NB2_TRY(mb_launch_velocity(ctx));  // multibodies: rows, velocity resolution, impulse caching, integration of the joints
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[2], ctx->stream));
     // ---- velocity update + integration (Counters: "velocity update")
     NB2_TRY(launch_integrate(ctx, false));
@@ -145,6 +149,7 @@ static int do_step(Context* ctx, int mode) {
     // ---- position resolution
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[8], ctx->stream));
     NB2_TRY(launch_position_solve(ctx, mode));
+    NB2_TRY(mb_launch_position(ctx));  // multibodies: position resolution, then the end-of-step kinematics
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[9], ctx->stream));
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[4], ctx->stream));
     // ---- kinematic bodies (mechanical_world.rs:328-332)
@@ -223,6 +228,8 @@ int nb2_sizeof(int which) {
         case 7: return (int)sizeof(nb2_activation);
         case 8: return (int)sizeof(nb2_contact_update);
         case 9: return (int)sizeof(nb2_collider);
+        case 10: return (int)sizeof(nb2_mb_link);
+        case 11: return (int)sizeof(nb2_multibody);
         default: return NB2_ERR_INVALID_ARGUMENT;
     }
 }
@@ -524,6 +531,22 @@ int nb2_upload_joints(nb2_context* h, const nb2_joint* joints, uint32_t n) {
         NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return NB2_OK;
+}
+
+int nb2_upload_multibodies(nb2_context* h, const nb2_multibody* multibodies, uint32_t n_multibodies, const nb2_mb_link* links,
+                           uint32_t n_links) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    return mb_upload(ctx, multibodies, n_multibodies, links, n_links);
+}
+
+int nb2_download_multibody_links(nb2_context* h, nb2_mb_link* out, uint32_t n_links) {
+    NB2_CHECK_CTX(h);
+    Context* ctx = &h->c;
+    if (n_links && !out) return set_error(ctx, NB2_ERR_INVALID_ARGUMENT, "null output");
+    NB2_CUDA(ctx, cudaSetDevice(ctx->device));
+    return mb_download_links(ctx, out, n_links);
 }
 
 int nb2_set_contact_model(nb2_context* h, int model) {

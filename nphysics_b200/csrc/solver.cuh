@@ -297,6 +297,7 @@ struct Context {
     void* host_hdr = nullptr;      // pinned copy of vs.hdr (launch-geometry hint, never waited for)
     DevBuf<unsigned int> bal;       // groups per colour while balancing
     bool pos_early_exit = true;     // NB2_POS_EARLY_EXIT=0: always run every position iteration (the exactness test)
+    void* mb = nullptr;             // MbState (multibody.cu): reduced-coordinate multibodies, SURVEY 8 f3
 };
 
 // ---------------------------------------------------------------------------
@@ -390,6 +391,14 @@ int launch_stats(Context* ctx, int mode);
 int launch_body_stats(Context* ctx, double* d_energy, unsigned int* d_non_finite);
 int launch_validate_inputs(Context* ctx);
 int launch_validate_joints(Context* ctx);
+// multibody.cu
+int mb_upload(Context* ctx, const nb2_multibody* mbs, uint32_t n_mb, const nb2_mb_link* links, uint32_t n_links);
+int mb_download_links(Context* ctx, nb2_mb_link* out, uint32_t n);
+int mb_launch_refresh(Context* ctx);
+int mb_launch_velocity(Context* ctx);
+int mb_launch_position(Context* ctx);
+int mb_count(Context* ctx);
+void mb_release(Context* ctx);
 // schedule.cu
 int exclusive_scan_u32(Context* ctx, const unsigned int* in, unsigned int* out, size_t n);
 int launch_build_items(Context* ctx, int mode);

@@ -498,3 +498,112 @@ def joint_zoo(seed=7, rad=0.2, density=1.0, with_limits=True):
             jn += 1
             parent, parent_pos = b, pos
     return Scene(bodies, he, off, joints, name="joint_zoo")
+
+
+# ----------------------------------------------------------------------------------------------
+# reduced-coordinate multibodies
+# ----------------------------------------------------------------------------------------------
+class MultibodyBuilder:
+    """MultibodyDesc restated for the flat ABI (src/object/multibody.rs:1311-1470): `add` appends a link to the
+    current multibody (its NB2_BODY_MULTIBODY_LINK record is appended to the body set), `finish` closes it."""
+
+    def __init__(self, bodies, half_extents, coll_offset):
+        self.bodies = list(bodies)
+        self.he = [np.asarray(h, dtype=np.float64) for h in half_extents]
+        self.off = [np.asarray(o, dtype=np.float64) for o in coll_offset]
+        self.links = []
+        self.multibodies = []
+        self._first = 0
+
+    def add(self, parent, joint_type, half_extents, density, parent_shift=(0, 0, 0), body_shift=(0, 0, 0), axis=(1, 0, 0),
+            coords=None, velocity=None, collider=True, **kw):
+        b = abi.new_bodies(1)[0].copy()
+        b["status"] = abi.BODY_MULTIBODY_LINK
+        m, inertia = cuboid_mass_properties(half_extents, density)
+        b["mass"] = m
+        b["local_inertia"] = inertia.reshape(9)
+        self.bodies.append(b)
+        self.he.append(np.asarray(half_extents, dtype=np.float64) if collider else np.zeros(3))
+        self.off.append(np.zeros(3))
+        l = abi.new_mb_links(1, joint_type)
+        l["multibody"] = len(self.multibodies)
+        l["parent"] = parent
+        l["body"] = len(self.bodies) - 1
+        l["parent_shift"] = parent_shift
+        l["body_shift"] = body_shift
+        a = np.asarray(axis, dtype=np.float64)
+        l["axis"] = a / np.linalg.norm(a)
+        if coords is not None:
+            l["coords"][0, :len(coords)] = coords
+        if velocity is not None:
+            l["velocity"][0, :len(velocity)] = velocity
+        for k, v in kw.items():
+            l[k] = v
+        self.links.append(l[0].copy())
+        return len(self.links) - 1 - self._first
+
+    def finish(self, gravity=True):
+        mb = np.zeros(1, dtype=abi.multibody_dtype)
+        mb["first_link"] = self._first
+        mb["n_links"] = len(self.links) - self._first
+        mb["flags"] = abi.BODY_FLAG_GRAVITY if gravity else 0
+        self.multibodies.append(mb[0].copy())
+        self._first = len(self.links)
+
+    def scene(self, name, joints=None):
+        sc = Scene(np.array(self.bodies, dtype=abi.body_dtype), np.array(self.he), np.array(self.off), joints, name=name)
+        sc.multibodies = np.array(self.multibodies, dtype=abi.multibody_dtype)
+        sc.mb_links = np.array(self.links, dtype=abi.mb_link_dtype)
+        return sc
+
+
+def _ground_only(ground_half=(20.0, 0.2, 20.0)):
+    bodies = abi.new_bodies(1)
+    bodies["status"][0] = abi.BODY_STATIC
+    bodies["flags"][0] = 0
+    return MultibodyBuilder(bodies, [ground_half], [(0.0, -0.2, 0.0)])
+
+
+def multibody_ragdolls(n=10, pitch=3.0, height=5.0, spin=2.0, density=0.3, colliders=True):
+    """examples3d/ragdoll3.rs:65-160 AS SHIPPED: one Multibody per ragdoll -- a FreeJoint torso and five BallJoint
+    members (head, two arms, two legs) with the example's parent / body shifts: 6 links, 21 dofs.  Members are
+    cuboids of the members' extents (the example's balls and capsules are ncollide shapes).  `spin`: initial angular
+    velocity of the torso about z."""
+    body_rady, body_radz, body_radx = 0.6, 0.2, 0.1
+    head_rad, member_rad, arm_length, leg_length, space = 0.2, 0.075, 0.45, 0.7, 0.15
+    members = [
+        ((head_rad, head_rad, head_rad), (0.0, body_rady + head_rad + space, 0.0), (0.0, 0.0, 0.0)),
+        ((member_rad, arm_length + member_rad, member_rad), (0.0, body_rady, body_radx + 2.0 * space), (0.0, arm_length + space, 0.0)),
+        ((member_rad, arm_length + member_rad, member_rad), (0.0, body_rady, -body_radx - 2.0 * space), (0.0, arm_length + space, 0.0)),
+        ((member_rad, leg_length + member_rad, member_rad), (0.0, -body_rady, body_radx), (0.0, leg_length + space, 0.0)),
+        ((member_rad, leg_length + member_rad, member_rad), (0.0, -body_rady, -body_radx), (0.0, leg_length + space, 0.0)),
+    ]
+    mb = _ground_only()
+    per_row = int(np.ceil(np.sqrt(n)))
+    for r in range(n):
+        origin = [(r % per_row) * pitch, height, (r // per_row) * pitch]
+        root = mb.add(-1, abi.MBJ_FREE, (body_radx, body_rady, body_radz), density, coords=origin + [0, 0, 0, 1],
+                      velocity=[0, 0, 0, 0, 0, spin], collider=colliders)
+        for half, a1, a2 in members:
+            mb.add(root, abi.MBJ_BALL, half, density, parent_shift=a1, body_shift=a2, collider=colliders)
+        mb.finish()
+    return mb.scene("multibody_ragdolls_%d" % n)
+
+
+def multibody_chain(joint_type=None, links=4, rad=0.2, density=1.0, anchor=(0.0, 5.0, 0.0), spacing=0.8, axis=(1, 0, 0),
+                    damping=None, root_fixed=True, **kw):
+    """A chain hanging from the ground in the manner of examples3d/multibody3.rs: link k hangs `spacing` below link
+    k-1 along -z (so that it swings under gravity about x); the root is attached to the world by the same joint."""
+    joint_type = abi.MBJ_REVOLUTE if joint_type is None else joint_type
+    mb = _ground_only()
+    for k in range(links):
+        extra = dict(kw)
+        if damping is not None:
+            extra["damping"] = [damping] * 6
+        if k == 0:
+            mb.add(-1, joint_type, (rad, rad, rad), density, parent_shift=anchor, body_shift=(0, 0, spacing), axis=axis, **extra)
+        else:
+            mb.add(k - 1, joint_type, (rad, rad, rad), density, parent_shift=(0, 0, 0), body_shift=(0, 0, spacing), axis=axis,
+                   **extra)
+    mb.finish()
+    return mb.scene("multibody_chain")

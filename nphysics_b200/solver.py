@@ -26,6 +26,7 @@ EXPORTS = [
     "nb2_launch_count", "nb2_download_schedule",
     "nb2_update_contacts", "nb2_upload_colliders", "nb2_detect_pairs", "nb2_generate_manifolds",
     "nb2_download_manifolds", "nb2_label_islands", "nb2_set_contact_model",
+    "nb2_upload_multibodies", "nb2_download_multibody_links",
 ]
 
 
@@ -204,6 +205,19 @@ class Solver:
         j = np.ascontiguousarray(joints, dtype=abi.joint_dtype)
         self.n_joints = len(j)
         self._chk(self.lib.nb2_upload_joints(self.h, abi.ptr(j), ctypes.c_uint32(len(j))))
+
+    # ---- reduced-coordinate multibodies (Multibody / MultibodyDesc)
+    def upload_multibodies(self, multibodies, links):
+        m = np.ascontiguousarray(multibodies, dtype=abi.multibody_dtype)
+        l = np.ascontiguousarray(links, dtype=abi.mb_link_dtype)
+        self.n_mb_links = len(l)
+        self._chk(self.lib.nb2_upload_multibodies(self.h, abi.ptr(m), ctypes.c_uint32(len(m)), abi.ptr(l),
+                                                  ctypes.c_uint32(len(l))))
+
+    def download_multibody_links(self):
+        out = np.zeros(self.n_mb_links, dtype=abi.mb_link_dtype)
+        self._chk(self.lib.nb2_download_multibody_links(self.h, abi.ptr(out), ctypes.c_uint32(len(out))))
+        return out
 
     def set_contact_model(self, model):
         """0 = SignoriniCoulombPyramidModel (default), 1 = SignoriniModel (frictionless)."""

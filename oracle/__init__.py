@@ -31,6 +31,7 @@ def build(force=False):
     """Compile liboracle.so / liboracle_f64.so with the recipe in oracle/Makefile (-O3 -march=native)."""
     targets = [os.path.join(_HERE, "liboracle.so"), os.path.join(_HERE, "liboracle_f64.so")]
     src = os.path.join(_HERE, "oracle.cpp")
+    inc = os.path.join(_HERE, "multibody.inc")
     hdr = os.path.join(_HERE, "..", "include", "nphysics_b200.h")
     mk = os.path.join(_HERE, "Makefile")
     stamp_path = os.path.join(_HERE, "liboracle.host")
@@ -39,7 +40,7 @@ def build(force=False):
         same_host = open(stamp_path).read().strip() == stamp
     except OSError:
         same_host = False
-    newest = max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(mk))
+    newest = max(os.path.getmtime(src), os.path.getmtime(inc), os.path.getmtime(hdr), os.path.getmtime(mk))
     stale = force or not same_host or any((not os.path.exists(t)) or os.path.getmtime(t) < newest for t in targets)
     if stale:
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
@@ -62,7 +63,8 @@ def _load(f64=False):
         for name in ["nbo_destroy", "nbo_set_params", "nbo_upload_bodies", "nbo_upload_body_states",
                      "nbo_upload_manifolds", "nbo_upload_joints", "nbo_clear_impulse_cache", "nbo_set_contact_model", "nbo_step",
                      "nbo_download_body_states", "nbo_download_contact_impulses", "nbo_download_joints",
-                     "nbo_get_stats", "nbo_debug_body_dynamics", "nbo_debug_row_counts", "nbo_debug_mj_lambda"]:
+                     "nbo_get_stats", "nbo_debug_body_dynamics", "nbo_debug_row_counts", "nbo_debug_mj_lambda",
+                     "nbo_upload_multibodies", "nbo_download_multibody_links"]:
             getattr(lib, name).restype = ctypes.c_int
         _libs[key] = lib
     return _libs[key]
@@ -123,6 +125,19 @@ class Oracle:
 
     def clear_impulse_cache(self):
         self._chk(self.lib.nbo_clear_impulse_cache(self.h))
+
+    # ---- reduced-coordinate multibodies (src/object/multibody.rs restated, oracle/multibody.inc)
+    def upload_multibodies(self, multibodies, links):
+        m = np.ascontiguousarray(multibodies, dtype=abi.multibody_dtype)
+        l = np.ascontiguousarray(links, dtype=abi.mb_link_dtype)
+        self.n_mb_links = len(l)
+        self._chk(self.lib.nbo_upload_multibodies(self.h, abi.ptr(m), ctypes.c_uint32(len(m)), abi.ptr(l),
+                                                  ctypes.c_uint32(len(l))))
+
+    def download_multibody_links(self):
+        out = np.zeros(self.n_mb_links, dtype=abi.mb_link_dtype)
+        self._chk(self.lib.nbo_download_multibody_links(self.h, abi.ptr(out), ctypes.c_uint32(len(out))))
+        return out
 
     def set_contact_model(self, model):
         """0 = SignoriniCoulombPyramidModel, 1 = SignoriniModel (frictionless)."""

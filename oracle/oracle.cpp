@@ -271,6 +271,9 @@ inline void axpy6(real a, const real* x, real* y) {
     for (int k = 0; k < 6; ++k) y[k] = a * x[k] + y[k];
 }
 
+inline real dotn(size_t n, const real* a, const real* b);
+inline void axpyn(size_t n, real a, const real* x, real* y);
+
 /* Inertia3 (src/algebra/inertia3.rs:8-13). */
 struct Inertia {
     real linear;
@@ -285,6 +288,7 @@ inline Inertia inertia_inverse(const Inertia& in) {
 }
 
 /* ------------------------------------------------------------------ bodies */
+struct Multibody;
 struct Body {
     /* inputs (rigid_body.rs:26-50) */
     Iso position;
@@ -305,7 +309,12 @@ struct Body {
     real act_threshold = -1, act_energy = (real)0.04;
     bool is_active() const { return act_energy != 0; } /* body.rs:93-96 */
 
-    size_t status_dependent_ndofs() const { return status == NB2_BODY_DYNAMIC ? 6 : 0; } /* body.rs:287-293 */
+    /* a NB2_BODY_MULTIBODY_LINK record: the link it stands for (multibody.inc) */
+    Multibody* mb = nullptr;
+    int mb_link = -1;
+    int handle = -1; /* the BodyHandle: the body's own index, or one value per multibody for its links */
+
+    size_t status_dependent_ndofs() const; /* body.rs:287-293 */
 
     /* rigid_body.rs:305-315 (no renormalisation: improved_fixed_point_support off). */
     void set_position(const Iso& pos) {
@@ -387,8 +396,14 @@ inline ForceDirection fd_angular(V3 d) { return ForceDirection{true, d}; }
 inline ForceDirection fd_neg(const ForceDirection& f) { return ForceDirection{f.angular, -f.dir}; }
 
 /* RigidBody::fill_constraint_geometry, rigid_body.rs:672-722. */
+void mb_fill_constraint_geometry(const Body& b, V3 point, const ForceDirection& fdir, size_t j_id, size_t wj_id,
+                                 real* jacobians, real* inv_r, const real* ext_vels, real* out_vel);
 void fill_constraint_geometry(const Body& b, V3 point, const ForceDirection& fdir, size_t j_id, size_t wj_id,
                               real* jacobians, real* inv_r, const real* ext_vels, real* out_vel) {
+    if (b.status == NB2_BODY_MULTIBODY_LINK) { /* Multibody::fill_constraint_geometry, multibody.rs:971-1025 */
+        mb_fill_constraint_geometry(b, point, fdir, j_id, wj_id, jacobians, inv_r, ext_vels, out_vel);
+        return;
+    }
     V3 pos = point - b.com;
     /* ForceDirection::at_point (helper.rs:27-32), force3.rs:63-89 */
     S6 force = fdir.angular ? S6{v3(0, 0, 0), fdir.dir} : S6{fdir.dir, cross(pos, fdir.dir)};
@@ -455,9 +470,9 @@ ConstraintGeometry constraint_pair_geometry(const Body& body1, int h1, const Bod
                              ext_vels2, out_vel);
     if (h1 == h2) { /* helper.rs:118-125: both parts on the same body */
         real c = 0;
-        if (res.ndofs1 == 6 && res.ndofs2 == 6)
-            c = dot6(&jacobians[res.j_id2], &jacobians[res.wj_id1]) +
-                dot6(&jacobians[res.j_id1], &jacobians[res.wj_id2]);
+        if (res.ndofs1 == res.ndofs2 && res.ndofs1 != 0)
+            c = dotn(res.ndofs1, &jacobians[res.j_id2], &jacobians[res.wj_id1]) +
+                dotn(res.ndofs1, &jacobians[res.j_id1], &jacobians[res.wj_id2]);
         inv_r += c;
     }
     res.r = inv_r != (real)0 ? (real)1 / inv_r : (real)1;
@@ -526,6 +541,17 @@ BilateralGround make_bilateral_ground(const ConstraintGeometry& g, size_t a1, si
                                       real impulse, uint64_t id) {
     if (g.ndofs1 == 0) return BilateralGround{impulse, g.r, rhs, lim, id, a2, g.j_id2, g.wj_id2, g.ndofs2};
     return BilateralGround{impulse, g.r, rhs, lim, id, a1, g.j_id1, g.wj_id1, g.ndofs1};
+}
+
+#include "multibody.inc"
+
+size_t Body::status_dependent_ndofs() const {
+    if (status == NB2_BODY_MULTIBODY_LINK) return mb ? mb->ndofs : 0;
+    return status == NB2_BODY_DYNAMIC ? 6 : 0;
+}
+void mb_fill_constraint_geometry(const Body& b, V3 point, const ForceDirection& fdir, size_t j_id, size_t wj_id,
+                                 real* jacobians, real* inv_r, const real* ext_vels, real* out_vel) {
+    b.mb->fill_constraint_geometry(b.mb_link, point, fdir, j_id, wj_id, jacobians, inv_r, ext_vels, out_vel);
 }
 
 /* nonlinear_constraint.rs:60-139: the contact position constraint. */
@@ -642,6 +668,13 @@ struct World {
     std::vector<nb2_contact> contacts;
     bool sleeping_enabled = false;
     std::vector<Joint> joints;
+    std::vector<Multibody> mbs;            /* reduced-coordinate bodies (multibody.inc) */
+    std::vector<nb2_mb_link> mb_link_recs; /* as uploaded, for the download */
+    void apply_body_displacement(int body, const real* d) { /* Body::apply_displacement of the body behind a part */
+        Body& b = bodies[body];
+        if (b.status == NB2_BODY_MULTIBODY_LINK) b.mb->apply_displacement(d, bodies);
+        else b.apply_displacement(d);
+    }
 
     /* MoreauJeanSolver state (moreau_jean_solver.rs:14-23) */
     std::vector<real> jacobians, mj_lambda_vel, ext_vels;
@@ -1240,7 +1273,7 @@ struct World {
                 V3 center2 = world2 - normal * (real)m.margin2;
                 real rhs = dot(normal, surface_velocity);
                 ConstraintGeometry geom =
-                    constraint_pair_geometry(body1, m.body1, body2, m.body2, center1, center2, fd_linear(-normal),
+                    constraint_pair_geometry(body1, body1.handle, body2, body2.handle, center1, center2, fd_linear(-normal),
                                              ground_j_id, j_id, jacobians, ev1, ev2, &rhs);
                 if (rhs <= -params.restitution_velocity_threshold) rhs += (real)m.restitution * rhs;
                 real depth = (real)c.depth + (real)m.margin1 + (real)m.margin2;
@@ -1289,7 +1322,7 @@ struct World {
                 for (int i = 0; i < 2; ++i) {
                     real frhs = dot(t[i], surface_velocity);
                     ConstraintGeometry fgeom =
-                        constraint_pair_geometry(body1, m.body1, body2, m.body2, center1, center2, fd_linear(t[i]),
+                        constraint_pair_geometry(body1, body1.handle, body2, body2.handle, center1, center2, fd_linear(t[i]),
                                                  ground_j_id, j_id, jacobians, ev1, ev2, &frhs);
                     real fwarm = get(impulse, i + 1) * params.warmstart_coeff;
                     if (fgeom.is_ground()) {
@@ -1387,18 +1420,18 @@ struct World {
         const real* jac = jacobians.data();
         for (auto& c : cs.unilateral)
             if (c.impulse != (real)0) {
-                axpy6(c.impulse, jac + c.wj_id1, lam + c.assembly_id1);
-                axpy6(c.impulse, jac + c.wj_id2, lam + c.assembly_id2);
+                axpyn(c.ndofs1, c.impulse, jac + c.wj_id1, lam + c.assembly_id1);
+                axpyn(c.ndofs2, c.impulse, jac + c.wj_id2, lam + c.assembly_id2);
             }
         for (auto& c : cs.unilateral_ground)
-            if (c.impulse != (real)0) axpy6(c.impulse, jac + c.wj_id, lam + c.assembly_id);
+            if (c.impulse != (real)0) axpyn(c.ndofs, c.impulse, jac + c.wj_id, lam + c.assembly_id);
         for (auto& c : cs.bilateral)
             if (c.impulse != (real)0) {
-                axpy6(c.impulse, jac + c.wj_id1, lam + c.assembly_id1);
-                axpy6(c.impulse, jac + c.wj_id2, lam + c.assembly_id2);
+                axpyn(c.ndofs1, c.impulse, jac + c.wj_id1, lam + c.assembly_id1);
+                axpyn(c.ndofs2, c.impulse, jac + c.wj_id2, lam + c.assembly_id2);
             }
         for (auto& c : cs.bilateral_ground)
-            if (c.impulse != (real)0) axpy6(c.impulse, jac + c.wj_id, lam + c.assembly_id);
+            if (c.impulse != (real)0) axpyn(c.ndofs, c.impulse, jac + c.wj_id, lam + c.assembly_id);
     }
     static real clampv(real v, real lo, real hi) { /* na::clamp */
         return v > lo ? (v < hi ? v : hi) : lo;
@@ -1416,8 +1449,8 @@ struct World {
                 real impulse = cs.unilateral[c.limits.dependency].impulse;
                 if (impulse == (real)0) {
                     if (c.impulse != (real)0) {
-                        axpy6(-c.impulse, jac + c.wj_id1, lam + c.assembly_id1);
-                        axpy6(-c.impulse, jac + c.wj_id2, lam + c.assembly_id2);
+                        axpyn(c.ndofs1, -c.impulse, jac + c.wj_id1, lam + c.assembly_id1);
+                        axpyn(c.ndofs2, -c.impulse, jac + c.wj_id2, lam + c.assembly_id2);
                         c.impulse = 0;
                     }
                     continue;
@@ -1425,12 +1458,12 @@ struct World {
                 max_impulse = c.limits.coeff * impulse;
                 min_impulse = -max_impulse;
             }
-            real dimpulse = dot6(jac + c.j_id1, lam + c.assembly_id1) + dot6(jac + c.j_id2, lam + c.assembly_id2) + c.rhs;
+            real dimpulse = dotn(c.ndofs1, jac + c.j_id1, lam + c.assembly_id1) + dotn(c.ndofs2, jac + c.j_id2, lam + c.assembly_id2) + c.rhs;
             real new_impulse = clampv(c.impulse - c.r * dimpulse, min_impulse, max_impulse);
             real dlambda = new_impulse - c.impulse;
             c.impulse = new_impulse;
-            axpy6(dlambda, jac + c.wj_id1, lam + c.assembly_id1);
-            axpy6(dlambda, jac + c.wj_id2, lam + c.assembly_id2);
+            axpyn(c.ndofs1, dlambda, jac + c.wj_id1, lam + c.assembly_id1);
+            axpyn(c.ndofs2, dlambda, jac + c.wj_id2, lam + c.assembly_id2);
         }
         for (auto& c : cs.bilateral_ground) {
             real min_impulse, max_impulse;
@@ -1441,7 +1474,7 @@ struct World {
                 real impulse = cs.unilateral_ground[c.limits.dependency].impulse;
                 if (impulse == (real)0) {
                     if (c.impulse != (real)0) {
-                        axpy6(-c.impulse, jac + c.wj_id, lam + c.assembly_id);
+                        axpyn(c.ndofs, -c.impulse, jac + c.wj_id, lam + c.assembly_id);
                         c.impulse = 0;
                     }
                     continue;
@@ -1449,11 +1482,11 @@ struct World {
                 max_impulse = c.limits.coeff * impulse;
                 min_impulse = -max_impulse;
             }
-            real dimpulse = dot6(jac + c.j_id, lam + c.assembly_id) + c.rhs;
+            real dimpulse = dotn(c.ndofs, jac + c.j_id, lam + c.assembly_id) + c.rhs;
             real new_impulse = clampv(c.impulse - c.r * dimpulse, min_impulse, max_impulse);
             real dlambda = new_impulse - c.impulse;
             c.impulse = new_impulse;
-            axpy6(dlambda, jac + c.wj_id, lam + c.assembly_id);
+            axpyn(c.ndofs, dlambda, jac + c.wj_id, lam + c.assembly_id);
         }
     }
     /* sor_prox.rs:82-110, 181-230. */
@@ -1461,28 +1494,32 @@ struct World {
         real* lam = mj_lambda_vel.data();
         const real* jac = jacobians.data();
         for (auto& c : cs.unilateral) {
-            real dimpulse = dot6(jac + c.j_id1, lam + c.assembly_id1) + dot6(jac + c.j_id2, lam + c.assembly_id2) + c.rhs;
+            real dimpulse = dotn(c.ndofs1, jac + c.j_id1, lam + c.assembly_id1) + dotn(c.ndofs2, jac + c.j_id2, lam + c.assembly_id2) + c.rhs;
             real new_impulse = std::max(c.impulse - c.r * dimpulse, (real)0);
             real dlambda = new_impulse - c.impulse;
             c.impulse = new_impulse;
-            axpy6(dlambda, jac + c.wj_id1, lam + c.assembly_id1);
-            axpy6(dlambda, jac + c.wj_id2, lam + c.assembly_id2);
+            axpyn(c.ndofs1, dlambda, jac + c.wj_id1, lam + c.assembly_id1);
+            axpyn(c.ndofs2, dlambda, jac + c.wj_id2, lam + c.assembly_id2);
         }
         for (auto& c : cs.unilateral_ground) {
-            real dimpulse = dot6(jac + c.j_id, lam + c.assembly_id) + c.rhs;
+            real dimpulse = dotn(c.ndofs, jac + c.j_id, lam + c.assembly_id) + c.rhs;
             real new_impulse = std::max(c.impulse - c.r * dimpulse, (real)0);
             real dlambda = new_impulse - c.impulse;
             c.impulse = new_impulse;
-            axpy6(dlambda, jac + c.wj_id, lam + c.assembly_id);
+            axpyn(c.ndofs, dlambda, jac + c.wj_id, lam + c.assembly_id);
         }
     }
     /* SORProx::solve, sor_prox.rs:48-80 and step :159-179. */
     void sor_prox_solve(size_t max_iter) {
         warmstart_set(contact_vel);
         warmstart_set(joint_vel);
+        for (Multibody& mb : mbs) /* sor_prox.rs:60-65 */
+            if (mb.has_active_internal_constraints()) mb.warmstart_internal_velocity_constraints(&mj_lambda_vel[mb.companion_id]);
         for (size_t it = 0; it < max_iter; ++it) {
             step_bilateral(joint_vel);
             step_bilateral(contact_vel);
+            for (Multibody& mb : mbs) /* sor_prox.rs:170-175 */
+                if (mb.has_active_internal_constraints()) mb.step_solve_internal_velocity_constraints(&mj_lambda_vel[mb.companion_id]);
             step_unilateral(joint_vel);
             step_unilateral(contact_vel);
         }
@@ -1505,8 +1542,8 @@ struct World {
             real impulse = -rhs * c.r;
             for (size_t k = 0; k < c.dim1; ++k) pos_jacobians[c.wj_id1 + k] *= impulse;
             for (size_t k = 0; k < c.dim2; ++k) pos_jacobians[c.wj_id2 + k] *= impulse;
-            if (c.dim1 != 0) bodies[c.body1].apply_displacement(&pos_jacobians[c.wj_id1]);
-            if (c.dim2 != 0) bodies[c.body2].apply_displacement(&pos_jacobians[c.wj_id2]);
+            if (c.dim1 != 0) apply_body_displacement(c.body1, &pos_jacobians[c.wj_id1]);
+            if (c.dim2 != 0) apply_body_displacement(c.body2, &pos_jacobians[c.wj_id2]);
         }
     }
     /* nonlinear_sor_prox.rs:156-294. */
@@ -1522,7 +1559,7 @@ struct World {
         real inv_r = 0;
         size_t j_id1 = c.ndofs1 + c.ndofs2;
         size_t j_id2 = c.ndofs1 * 2 + c.ndofs2;
-        if (pos_jacobians.size() < j_id2 + c.ndofs2 + 6) pos_jacobians.resize(j_id2 + c.ndofs2 + 6, 0);
+        if (pos_jacobians.size() < j_id2 + 2 * c.ndofs2 + 6) pos_jacobians.resize(j_id2 + 2 * c.ndofs2 + 6, 0);
         if (c.ndofs1 != 0)
             fill_constraint_geometry(body1, contact.world1, fd_linear(-contact.normal), j_id1, 0, pos_jacobians.data(),
                                      &inv_r, nullptr, nullptr);
@@ -1539,8 +1576,8 @@ struct World {
             real impulse = -c.rhs * c.r;
             for (size_t k = 0; k < c.ndofs1; ++k) pos_jacobians[k] *= impulse;
             for (size_t k = 0; k < c.ndofs2; ++k) pos_jacobians[c.ndofs1 + k] *= impulse;
-            if (c.ndofs1 != 0) bodies[c.body1].apply_displacement(&pos_jacobians[0]);
-            if (c.ndofs2 != 0) bodies[c.body2].apply_displacement(&pos_jacobians[c.ndofs1]);
+            if (c.ndofs1 != 0) apply_body_displacement(c.body1, &pos_jacobians[0]);
+            if (c.ndofs2 != 0) apply_body_displacement(c.body2, &pos_jacobians[c.ndofs1]);
         }
     }
     /* NonlinearSORProx::solve, nonlinear_sor_prox.rs:17-55. */
@@ -1556,6 +1593,8 @@ struct World {
                     if (joint_position_constraint(j, i, &g)) solve_generic(g);
                 }
             }
+            for (Multibody& mb : mbs) /* nonlinear_sor_prox.rs:40-44 */
+                if (mb.has_active_internal_constraints()) mb.step_solve_internal_position_constraints(params, bodies);
             for (NonlinearUnilateral& c : contact_pos) solve_unilateral_position(c);
         }
     }
@@ -1568,6 +1607,12 @@ struct World {
             Body& b = bodies[h];
             b.companion_id = system_ndofs;
             system_ndofs += 6;
+        }
+        for (Multibody& mb : mbs) { /* a multibody is one body of the island with ndofs dofs; its links share its id */
+            mb.companion_id = system_ndofs;
+            system_ndofs += mb.ndofs;
+            for (const MbLink& l : mb.rbs)
+                if (l.body >= 0) bodies[l.body].companion_id = mb.companion_id;
         }
         mj_lambda_vel.assign(system_ndofs, 0); /* resize_buffers :322-326 */
         ext_vels.assign(system_ndofs, 0);
@@ -1582,6 +1627,8 @@ struct World {
             const real acc[6] = {a.lin.x, a.lin.y, a.lin.z, a.ang.x, a.ang.y, a.ang.z};
             for (int k = 0; k < 6; ++k) e[k] = dt * acc[k];
         }
+        for (const Multibody& mb : mbs)
+            for (size_t k = 0; k < mb.ndofs; ++k) ext_vels[mb.companion_id + k] = dt * mb.accelerations[k];
         /* jacobian sizes :181-216 */
         size_t jacobian_sz = 0, ground_jacobian_sz = 0;
         static const size_t max_rows[NB2_JOINT_TYPE_COUNT] = {3, 5, 7, 4, 3, 4, 4, 4, 6, 3};
@@ -1600,6 +1647,8 @@ struct World {
         size_t j_id = 0, ground_j_id = jacobian_sz;
         for (size_t ji : active_joints) joint_velocity_constraints(joints[ji], &ground_j_id, &j_id);
         contact_constraints(&ground_j_id, &j_id);
+        for (Multibody& mb : mbs) /* :254-259 */
+            if (mb.has_active_internal_constraints()) mb.setup_internal_velocity_constraints(&ext_vels[mb.companion_id], params);
     }
     /* update_velocities_and_integrate, moreau_jean_solver.rs:328-347. */
     void update_velocities_and_integrate() {
@@ -1614,6 +1663,11 @@ struct World {
             b.velocity.lin = v3(v[0], v[1], v[2]);
             b.velocity.ang = v3(v[3], v[4], v[5]);
             b.integrate(params.dt);
+        }
+        for (Multibody& mb : mbs) {
+            for (size_t k = 0; k < mb.ndofs; ++k) mb.velocities[k] += ext_vels[mb.companion_id + k];
+            for (size_t k = 0; k < mb.ndofs; ++k) mb.velocities[k] += mj_lambda_vel[mb.companion_id + k];
+            mb.integrate(params.dt);
         }
     }
 
@@ -1631,6 +1685,11 @@ struct World {
         for (Body& b : bodies) b.update_dynamics(dt);
         V3 g = v3(params.gravity[0], params.gravity[1], params.gravity[2]);
         for (Body& b : bodies) b.update_acceleration(g);
+        for (Multibody& mb : mbs) { /* mechanical_world.rs:230-243 */
+            mb.update_kinematics(bodies);
+            mb.update_dynamics(dt, bodies);
+            mb.update_acceleration(g);
+        }
         /* :264-279: active_bodies = the non-kinematic members of the islands that stay awake; the caller
          * ran update_activation (or sleeping is off and every dynamic body is active) */
         island.clear();
@@ -1663,6 +1722,10 @@ struct World {
         auto T5 = clk::now();
         for (Body& b : bodies) /* :328-332 */
             if (b.status == NB2_BODY_KINEMATIC) b.integrate(dt);
+        for (Multibody& mb : mbs) { /* mechanical_world.rs:343-346: kinematics and dynamics after the resolution */
+            mb.update_kinematics(bodies);
+            mb.update_dynamics(dt, bodies);
+        }
         auto ms = [](clk::time_point a, clk::time_point b) {
             return std::chrono::duration<double, std::milli>(b - a).count();
         };
@@ -1683,6 +1746,11 @@ struct World {
         for (Body& b : bodies) b.update_dynamics(dt);
         V3 g = v3(params.gravity[0], params.gravity[1], params.gravity[2]);
         for (Body& b : bodies) b.update_acceleration(g);
+        for (Multibody& mb : mbs) { /* mechanical_world.rs:230-243 */
+            mb.update_kinematics(bodies);
+            mb.update_dynamics(dt, bodies);
+            mb.update_acceleration(g);
+        }
         island.clear();
         for (size_t i = 0; i < bodies.size(); ++i)
             if (bodies[i].status == NB2_BODY_DYNAMIC && bodies[i].is_active()) island.push_back((int)i);
@@ -1702,6 +1770,10 @@ struct World {
         nonlinear_sor_prox_solve(params.max_position_iterations); /* :121 solve_position_constraints */
         sor_prox_solve(params.max_velocity_iterations);           /* :126 solve_velocity_constraints */
         update_velocities_and_integrate();                         /* :127 */
+        for (Multibody& mb : mbs) {
+            mb.update_kinematics(bodies);
+            mb.update_dynamics(dt, bodies);
+        }
         compute_residual();
         return NB2_OK;
     }
@@ -1726,11 +1798,11 @@ struct World {
         };
         for (LinearConstraints* cs : {&joint_vel, &contact_vel}) {
             for (auto& c : cs->unilateral) {
-                real w = dot6(jac + c.j_id1, lam + c.assembly_id1) + dot6(jac + c.j_id2, lam + c.assembly_id2) + c.rhs;
+                real w = dotn(c.ndofs1, jac + c.j_id1, lam + c.assembly_id1) + dotn(c.ndofs2, jac + c.j_id2, lam + c.assembly_id2) + c.rhs;
                 acc(std::max(c.impulse - c.r * w, (real)0) - c.impulse);
             }
             for (auto& c : cs->unilateral_ground) {
-                real w = dot6(jac + c.j_id, lam + c.assembly_id) + c.rhs;
+                real w = dotn(c.ndofs, jac + c.j_id, lam + c.assembly_id) + c.rhs;
                 acc(std::max(c.impulse - c.r * w, (real)0) - c.impulse);
             }
             for (auto& c : cs->bilateral) {
@@ -1739,7 +1811,7 @@ struct World {
                     hi = c.limits.coeff * cs->unilateral[c.limits.dependency].impulse;
                     lo = -hi;
                 }
-                real w = dot6(jac + c.j_id1, lam + c.assembly_id1) + dot6(jac + c.j_id2, lam + c.assembly_id2) + c.rhs;
+                real w = dotn(c.ndofs1, jac + c.j_id1, lam + c.assembly_id1) + dotn(c.ndofs2, jac + c.j_id2, lam + c.assembly_id2) + c.rhs;
                 acc(clampv(c.impulse - c.r * w, lo, hi) - c.impulse);
             }
             for (auto& c : cs->bilateral_ground) {
@@ -1748,7 +1820,7 @@ struct World {
                     hi = c.limits.coeff * cs->unilateral_ground[c.limits.dependency].impulse;
                     lo = -hi;
                 }
-                real w = dot6(jac + c.j_id, lam + c.assembly_id) + c.rhs;
+                real w = dotn(c.ndofs, jac + c.j_id, lam + c.assembly_id) + c.rhs;
                 acc(clampv(c.impulse - c.r * w, lo, hi) - c.impulse);
             }
         }
@@ -1844,6 +1916,119 @@ int nbo_upload_bodies(void* wp, const nb2_body* in, uint32_t n) {
         b.inv_augmented_mass = b.inertia;
         b.acceleration = S6{v3(0, 0, 0), v3(0, 0, 0)};
         b.companion_id = 0;
+        b.mb = nullptr;
+        b.mb_link = -1;
+        b.handle = (int)i;
+    }
+    w->mbs.clear();
+    w->mb_link_recs.clear();
+    return NB2_OK;
+}
+
+/* MultibodyDesc::build (multibody.rs:1433-1470): links in the uploaded order, add_link :180-254. */
+int nbo_upload_multibodies(void* wp, const nb2_multibody* mb_in, uint32_t n_mb, const nb2_mb_link* links, uint32_t n_links) {
+    World* w = (World*)wp;
+    w->mbs.assign(n_mb, Multibody());
+    w->mb_link_recs.assign(links, links + n_links);
+    for (uint32_t m = 0; m < n_mb; ++m) {
+        Multibody& mb = w->mbs[m];
+        const nb2_multibody& rec = mb_in[m];
+        if ((size_t)rec.first_link + rec.n_links > n_links || rec.n_links == 0) return NB2_ERR_BAD_INDEX;
+        mb.gravity_enabled = (rec.flags & NB2_BODY_FLAG_GRAVITY) != 0;
+        for (uint32_t k = 0; k < rec.n_links; ++k) {
+            const nb2_mb_link& s = links[rec.first_link + k];
+            if (s.joint_type >= NB2_MBJ_TYPE_COUNT || s.parent >= (int)k || (k == 0) != (s.parent < 0)) return NB2_ERR_INVALID_ARGUMENT;
+            if (s.body < 0 || (size_t)s.body >= w->bodies.size() || w->bodies[s.body].status != NB2_BODY_MULTIBODY_LINK)
+                return NB2_ERR_BAD_INDEX;
+            MbLink l;
+            l.parent = s.parent;
+            l.type = s.joint_type;
+            l.flags = s.flags;
+            l.body = s.body;
+            l.parent_shift = ld3(s.parent_shift);
+            l.body_shift = ld3(s.body_shift);
+            l.axis = ld3(s.axis);
+            const Body& pb = w->bodies[s.body];
+            l.local_com = pb.local_com;
+            l.local_inertia = pb.local_inertia;
+            l.min_pos = s.min_pos;
+            l.max_pos = s.max_pos;
+            l.motor_velocity = s.motor_velocity;
+            l.motor_max_velocity = s.motor_max_velocity;
+            l.motor_max_force = s.motor_max_force;
+            l.free_pos = Iso{v3(0, 0, 0), quat_identity()};
+            l.rot = quat_identity();
+            switch (s.joint_type) {
+                case NB2_MBJ_FREE:
+                case NB2_MBJ_FIXED: l.free_pos = Iso{ld3(s.coords), ldq(s.coords + 3)}; break;
+                case NB2_MBJ_BALL: l.rot = ldq(s.coords); break;
+                case NB2_MBJ_REVOLUTE:
+                    l.coord = s.coords[0];
+                    l.rot = from_axis_angle(l.axis, l.coord);
+                    break;
+                default: l.coord = s.coords[0]; break;
+            }
+            l.ndofs = MbLink::ndofs_of(s.joint_type);
+            l.assembly_id = mb.velocities.size();
+            l.impulse_id = mb.impulses.size();
+            for (size_t d = 0; d < l.ndofs; ++d) {
+                mb.velocities.push_back(s.velocity[d]);
+                mb.damping.push_back(s.damping[d]);
+                mb.accelerations.push_back(0);
+                mb.forces.push_back(0);
+            }
+            for (size_t d = 0; d < l.ndofs * 3; ++d) mb.impulses.push_back(l.ndofs == 1 ? s.impulses[d] : 0); /* Joint::nimpulses */
+            mb.ndofs += l.ndofs;
+            mb.rbs.push_back(l);
+        }
+        if (mb.ndofs > NB2_MB_MAX_DOFS) return NB2_ERR_UNSUPPORTED;
+    }
+    for (uint32_t m = 0; m < n_mb; ++m) {
+        Multibody& mb = w->mbs[m];
+        for (size_t k = 0; k < mb.rbs.size(); ++k) {
+            Body& pb = w->bodies[mb.rbs[k].body];
+            pb.mb = &mb;
+            pb.mb_link = (int)k;
+            pb.handle = (int)(w->bodies.size() + m);
+        }
+        mb.update_kinematics(w->bodies);
+        mb.update_dynamics(w->params.dt, w->bodies);
+    }
+    return NB2_OK;
+}
+int nbo_download_multibody_links(void* wp, nb2_mb_link* out, uint32_t n) {
+    World* w = (World*)wp;
+    if (n > w->mb_link_recs.size()) return NB2_ERR_BAD_INDEX;
+    for (uint32_t i = 0; i < n; ++i) {
+        nb2_mb_link r = w->mb_link_recs[i];
+        const Multibody& mb = w->mbs[r.multibody];
+        uint32_t first = 0; /* link index within its multibody */
+        for (uint32_t k = 0; k < i; ++k)
+            if (w->mb_link_recs[k].multibody == r.multibody) ++first;
+        const MbLink& l = mb.rbs[first];
+        switch (l.type) {
+            case NB2_MBJ_FREE:
+            case NB2_MBJ_FIXED:
+                r.coords[0] = l.free_pos.t.x; r.coords[1] = l.free_pos.t.y; r.coords[2] = l.free_pos.t.z;
+                r.coords[3] = l.free_pos.r.i; r.coords[4] = l.free_pos.r.j; r.coords[5] = l.free_pos.r.k; r.coords[6] = l.free_pos.r.w;
+                break;
+            case NB2_MBJ_BALL:
+                r.coords[0] = l.rot.i; r.coords[1] = l.rot.j; r.coords[2] = l.rot.k; r.coords[3] = l.rot.w;
+                break;
+            default: r.coords[0] = l.coord; break;
+        }
+        for (size_t d = 0; d < l.ndofs; ++d) r.velocity[d] = mb.velocities[l.assembly_id + d];
+        if (l.ndofs == 1) {
+            /* the rows' impulses reach Multibody::impulses at the next setup (multibody.rs:1046-1053): report the
+             * latest ones */
+            std::vector<real> imp(mb.impulses.begin() + l.impulse_id, mb.impulses.begin() + l.impulse_id + 3);
+            for (const UnilateralGround& c : mb.internal.unilateral_ground)
+                if (c.impulse_id >= l.impulse_id && c.impulse_id < l.impulse_id + 3) imp[c.impulse_id - l.impulse_id] = c.impulse;
+            for (const BilateralGround& c : mb.internal.bilateral_ground)
+                if (c.impulse_id >= l.impulse_id && c.impulse_id < l.impulse_id + 3) imp[c.impulse_id - l.impulse_id] = c.impulse;
+            for (int d = 0; d < 3; ++d) r.impulses[d] = imp[d];
+        }
+        out[i] = r;
     }
     return NB2_OK;
 }

@@ -8,7 +8,7 @@ fn main() {
     // (source, keep the reference's multiply-add order).  solve_coloured.cu holds the coloured-mode staged
     // kernels, which may contract to FMA (csrc/Makefile).
     let srcs = [("api.cu", true), ("bodies.cu", true), ("schedule.cu", true), ("assemble.cu", true), ("assemble_coloured.cu", true), ("solve.cu", true),
-                ("activation.cu", true), ("narrowphase.cu", true), ("solve_coloured.cu", false)];
+                ("activation.cu", true), ("narrowphase.cu", true), ("multibody.cu", true), ("solve_coloured.cu", false)];
     let mut objs = Vec::new();
     for (s, no_fma) in srcs.iter() {
         let src = csrc.join(s);

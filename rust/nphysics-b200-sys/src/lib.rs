@@ -176,6 +176,38 @@ pub struct nb2_joint {
     pub broken: u32,
 }
 
+/// One link of a reduced-coordinate multibody (`MultibodyLink` + its `Joint`, src/object/multibody_link.rs).
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct nb2_mb_link {
+    pub multibody: i32,
+    pub parent: i32,
+    pub joint_type: u32,
+    pub flags: u32,
+    pub body: i32,
+    pub parent_shift: [f32; 3],
+    pub body_shift: [f32; 3],
+    pub axis: [f32; 3],
+    pub coords: [f32; 7],
+    pub velocity: [f32; 6],
+    pub damping: [f32; 6],
+    pub min_pos: f32,
+    pub max_pos: f32,
+    pub motor_velocity: f32,
+    pub motor_max_velocity: f32,
+    pub motor_max_force: f32,
+    pub impulses: [f32; 3],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct nb2_multibody {
+    pub first_link: u32,
+    pub n_links: u32,
+    pub flags: u32,
+    pub reserved: u32,
+}
+
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
 pub struct nb2_stats {
@@ -228,6 +260,9 @@ extern "C" {
     pub fn nb2_upload_manifolds(ctx: *mut nb2_context, manifolds: *const nb2_manifold, n_manifolds: u32,
                                 contacts: *const nb2_contact, n_contacts: u32) -> i32;
     pub fn nb2_upload_joints(ctx: *mut nb2_context, joints: *const nb2_joint, n_joints: u32) -> i32;
+    pub fn nb2_upload_multibodies(ctx: *mut nb2_context, multibodies: *const nb2_multibody, n_multibodies: u32,
+                                  links: *const nb2_mb_link, n_links: u32) -> i32;
+    pub fn nb2_download_multibody_links(ctx: *mut nb2_context, out: *mut nb2_mb_link, n_links: u32) -> i32;
     pub fn nb2_clear_impulse_cache(ctx: *mut nb2_context) -> i32;
     pub fn nb2_upload_activation(ctx: *mut nb2_context, activation: *const nb2_activation, n: u32) -> i32;
     pub fn nb2_update_activation(ctx: *mut nb2_context, mix_factor: f32, to_activate: *const i32, n_to_activate: u32) -> i32;
