@@ -27,6 +27,7 @@
 namespace nb2 {
 
 static const int MB_TPB = 64;
+#define NB2_MB_CACHE_WINDOW 64  // how far from its previous index a contact's cached impulse is looked for
 #define NB2_MB_MANIFOLD_CAP 32  // manifolds one multibody can be in contact through (more: reported, ignored)
 
 // per multibody (built on the host at upload)
@@ -71,6 +72,7 @@ struct MbView {
     float *jac, *cor;                     // body jacobians, Coriolis matrices
     float* icd;                           // 6 x ndofs scratch per multibody at 6 * dof_off
     float* mass;                          // LU blocks
+    float* accw;                          // workspace.accs: 6 floats per link
     int* piv;                             // [total dofs]
     uint32_t n_mb;
 };
@@ -541,7 +543,7 @@ __device__ void mb_update_acceleration(const MbView& V, const MbMeta& M, Vec3 gr
     float* acc = V.acc + M.dof_off;
     const float* vel = V.vel + M.dof_off;
     const float* damp = V.damp + M.dof_off;
-    float* accs = V.icd + (size_t)6 * M.dof_off;  // workspace.accs: 6 floats per link (n_links <= ndofs + fixed links; see upload)
+    float* accs = V.accw + (size_t)6 * M.first_link;  // workspace.accs
     for (uint32_t c = 0; c < nd; ++c) acc[c] = 0.f;
     for (uint32_t i = 0; i < M.n_links; ++i) {
         const MbLinkDev& rb = L[i];
@@ -731,14 +733,21 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_assemble(MbView V, MbContacts C, 
             const Vec3 normal = ld3(c.normal), world1 = ld3(c.world1), world2 = ld3(c.world2);
             float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c.key != 0ull) {
+                // ImpulseCache lookup by ContactId (signorini_coulomb_pyramid_model.rs:104-108): the per-contact arrays of
+                // the previous step at the same index (a contact that kept its place), else the nearest indices on
+                // both sides -- contacts are dropped and inserted around it, so its old slot is a few entries away.
+                // Beyond NB2_MB_CACHE_WINDOW entries the contact starts cold.
                 bool hit = ci < K.n_prev && K.ckey_prev[ci] == c.key;
                 if (hit) cached = K.imp_prev[ci];
-                else
-                    for (uint32_t j = mf.first_contact; j < mf.first_contact + mf.num_contacts && j < K.n_prev; ++j)
-                        if (K.ckey_prev[j] == c.key) {
-                            cached = K.imp_prev[j];
-                            break;
-                        }
+                for (uint32_t d = 1; !hit && d <= NB2_MB_CACHE_WINDOW; ++d) {
+                    if (ci >= d && ci - d < K.n_prev && K.ckey_prev[ci - d] == c.key) {
+                        cached = K.imp_prev[ci - d];
+                        hit = true;
+                    } else if (ci + d < K.n_prev && K.ckey_prev[ci + d] == c.key) {
+                        cached = K.imp_prev[ci + d];
+                        hit = true;
+                    }
+                }
             }
             const Vec3 center1 = world1 + normal * mf.margin1;
             const Vec3 center2 = world2 - normal * mf.margin2;
@@ -1127,7 +1136,7 @@ struct MbState {
     DevBuf<MbLinkDev> links;
     DevBuf<nb2_mb_link> recs;  // as uploaded (download template)
     DevBuf<int> mb_of_link, link_of_body, piv;
-    DevBuf<float> vel, damp, acc, ext, lam, jac, cor, icd, mass;
+    DevBuf<float> vel, damp, acc, ext, lam, jac, cor, icd, mass, accw;
     DevBuf<uint32_t> mcount, mlist, row_cnt, row_off, seg;
     DevBuf<MbRow> rows;
     DevBuf<float> jw;
@@ -1151,6 +1160,7 @@ static MbView mb_view(MbState* S) {
     V.cor = S->cor.p;
     V.icd = S->icd.p;
     V.mass = S->mass.p;
+    V.accw = S->accw.p;
     V.piv = S->piv.p;
     V.n_mb = S->n_mb;
     return V;
@@ -1170,7 +1180,7 @@ void mb_release(Context* ctx) {
     if (!S) return;
     S->meta.release(); S->links.release(); S->recs.release(); S->mb_of_link.release(); S->link_of_body.release(); S->piv.release();
     S->vel.release(); S->damp.release(); S->acc.release(); S->ext.release(); S->lam.release(); S->jac.release(); S->cor.release();
-    S->icd.release(); S->mass.release(); S->mcount.release(); S->mlist.release(); S->row_cnt.release(); S->row_off.release();
+    S->icd.release(); S->mass.release(); S->accw.release(); S->mcount.release(); S->mlist.release(); S->row_cnt.release(); S->row_off.release();
     S->seg.release(); S->rows.release(); S->jw.release(); S->cpos.release();
     delete S;
     ctx->mb = nullptr;
@@ -1259,7 +1269,6 @@ int mb_upload(Context* ctx, const nb2_multibody* mbs, uint32_t n_mb, const nb2_m
             nd += d.ndofs;
         }
         if (nd == 0 || nd > NB2_MB_MAX_DOFS) return set_error(ctx, NB2_ERR_UNSUPPORTED, "multibody %u: %u dofs (1..%d supported)", m, nd, NB2_MB_MAX_DOFS);
-        if (r.n_links > nd) return set_error(ctx, NB2_ERR_UNSUPPORTED, "multibody %u: more links than dofs", m);
         M.ndofs = nd;
         nd_max = nd > nd_max ? nd : nd_max;
         dof_off += nd;
@@ -1289,6 +1298,7 @@ int mb_upload(Context* ctx, const nb2_multibody* mbs, uint32_t n_mb, const nb2_m
     NB2_TRY(S->cor.reserve(ctx, jac_off));
     NB2_TRY(S->icd.reserve(ctx, (size_t)6 * dof_off));
     NB2_TRY(S->mass.reserve(ctx, mass_off));
+    NB2_TRY(S->accw.reserve(ctx, (size_t)6 * n_links));
     NB2_TRY(S->mcount.reserve(ctx, n_mb));
     NB2_TRY(S->mlist.reserve(ctx, (size_t)n_mb * NB2_MB_MANIFOLD_CAP));
     NB2_TRY(S->row_cnt.reserve(ctx, n_mb + 1));

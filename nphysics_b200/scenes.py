@@ -263,8 +263,9 @@ class ContactGenerator:
         has_coll = he.max(axis=1) > 0
         margin = scene.margin
         reach = 2.0 * (margin + LINEAR_PREDICTION)
-        dyn = np.nonzero((status == abi.BODY_DYNAMIC) & has_coll)[0]
-        big = np.nonzero((status != abi.BODY_DYNAMIC) & has_coll)[0]
+        movable = (status == abi.BODY_DYNAMIC) | (status == abi.BODY_MULTIBODY_LINK)  # a multibody link collides like a body
+        dyn = np.nonzero(movable & has_coll)[0]
+        big = np.nonzero(~movable & has_coll)[0]
         pa, pb = [], []
         if len(dyn) > 1:
             from scipy.spatial import cKDTree
@@ -550,8 +551,47 @@ class MultibodyBuilder:
         self.multibodies.append(mb[0].copy())
         self._first = len(self.links)
 
+    def _forward_kinematics(self, bodies):
+        """Link poses from the joint coordinates (Multibody::update_kinematics, multibody.rs:830-863) so that the link
+        records start where the library will put them (the contact producers look at them before the first step)."""
+        def qmul(a, b):
+            ai, aj, ak, aw = a
+            bi, bj, bk, bw = b
+            return np.array([aw * bi + ai * bw + aj * bk - ak * bj, aw * bj - ai * bk + aj * bw + ak * bi,
+                             aw * bk + ai * bj - aj * bi + ak * bw, aw * bw - ai * bi - aj * bj - ak * bk])
+        world = {}
+        for mb in self.multibodies:
+            for k in range(int(mb["n_links"])):
+                l = self.links[int(mb["first_link"]) + k]
+                ps, bs = l["parent_shift"].astype(np.float64), l["body_shift"].astype(np.float64)
+                c = l["coords"].astype(np.float64)
+                jt = int(l["joint_type"])
+                if jt == abi.MBJ_FREE:
+                    t, q = c[:3], c[3:7]
+                elif jt == abi.MBJ_FIXED:
+                    q = c[3:7]
+                    t = ps + c[:3] + quat_rotate(q, bs)
+                elif jt == abi.MBJ_BALL:
+                    q = c[:4]
+                    t = ps - quat_rotate(q, bs)
+                elif jt == abi.MBJ_REVOLUTE:
+                    ax = l["axis"].astype(np.float64)
+                    q = np.append(ax * np.sin(c[0] / 2), np.cos(c[0] / 2))
+                    t = ps - quat_rotate(q, bs)
+                else:
+                    q = np.array([0.0, 0.0, 0.0, 1.0])
+                    t = ps - bs + l["axis"].astype(np.float64) * c[0]
+                if k > 0:
+                    pt, pq = world[(int(mb["first_link"]), int(l["parent"]))]
+                    t, q = pt + quat_rotate(pq, t), qmul(pq, q)
+                world[(int(mb["first_link"]), k)] = (t, q)
+                bodies["position"][int(l["body"]), :3] = t
+                bodies["position"][int(l["body"]), 3:] = q
+
     def scene(self, name, joints=None):
-        sc = Scene(np.array(self.bodies, dtype=abi.body_dtype), np.array(self.he), np.array(self.off), joints, name=name)
+        bodies = np.array(self.bodies, dtype=abi.body_dtype)
+        self._forward_kinematics(bodies)
+        sc = Scene(bodies, np.array(self.he), np.array(self.off), joints, name=name)
         sc.multibodies = np.array(self.multibodies, dtype=abi.multibody_dtype)
         sc.mb_links = np.array(self.links, dtype=abi.mb_link_dtype)
         return sc
