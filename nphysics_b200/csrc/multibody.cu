@@ -299,8 +299,21 @@ __device__ __forceinline__ float& J_at(float* jac, uint32_t nd, uint32_t link, u
     return jac[(size_t)link * 6 * nd + (size_t)c * 6 + r];
 }
 
+// ---- lane groups.  Every routine below runs either on one thread (G = 1: the position solve, where a multibody's
+// kinematics are redone after every displacement by the thread that owns it) or on a warp (G = 32: one warp per
+// multibody).  The n_links x ndofs matrices are split by COLUMN: lane c % G owns column c of every link's body
+// jacobian and Coriolis matrix and column c of the mass matrix, so the recurrences from parent to child stay inside a
+// lane and only the products that mix columns (J^T M J, the LU) need a warp barrier.  Per-link scalars (poses,
+// velocities, inertias) are computed by all lanes alike.  Each element is produced by the same expression as on one
+// thread, so both shapes give the same bits.
+template <int G>
+__device__ __forceinline__ void mb_sync() {
+    if (G > 1) __syncwarp();
+}
+
 // update_kinematics (:830-863) + update_body_jacobians (:404-439)
-__device__ void mb_update_kinematics(const MbView& V, const MbMeta& M, const Proxies& P) {
+template <int G>
+__device__ void mb_update_kinematics(const MbView& V, const MbMeta& M, const Proxies& P, uint32_t lane) {
     MbLinkDev* L = V.links + M.first_link;
     const uint32_t nd = M.ndofs;
     float* jac = V.jac + M.jac_off;
@@ -325,11 +338,12 @@ __device__ void mb_update_kinematics(const MbView& V, const MbMeta& M, const Pro
         stq(rb.p2w_q, p2w);
         Vec3 com = pose_point(l2w, ld3(rb.local_com));
         st3(rb.com, com);
-        if (rb.body >= 0) {
+        if (rb.body >= 0 && lane == 0) {
             P.pos_t[rb.body] = xyz_f4(l2w.t, 0.f);
             P.pos_q[rb.body] = quat_f4(l2w.r);
             P.com_im[rb.body] = xyz_f4(com, 0.f);
         }
+        mb_sync<G>();
     }
     float jj[36];
     for (uint32_t i = 0; i < M.n_links; ++i) {
@@ -337,7 +351,7 @@ __device__ void mb_update_kinematics(const MbView& V, const MbMeta& M, const Pro
         if (i != 0) {
             const MbLinkDev& pr = L[rb.parent];
             Mat3 shift_tr = cross_matrix_tr(ld3(rb.com) - ld3(pr.com));
-            for (uint32_t c = 0; c < nd; ++c) {
+            for (uint32_t c = lane; c < nd; c += G) {
                 float pj[6];
                 for (int r = 0; r < 6; ++r) pj[r] = J_at(jac, nd, rb.parent, r, c);
                 for (int r = 0; r < 3; ++r) {
@@ -348,17 +362,20 @@ __device__ void mb_update_kinematics(const MbView& V, const MbMeta& M, const Pro
                 for (int r = 3; r < 6; ++r) J_at(jac, nd, i, r, c) = pj[r];
             }
         } else {
-            for (uint32_t c = 0; c < nd; ++c)
+            for (uint32_t c = lane; c < nd; c += G)
                 for (int r = 0; r < 6; ++r) J_at(jac, nd, i, r, c) = 0.f;
         }
         mbj_jacobian(rb, ldq(rb.p2w_q), jj);
         for (uint32_t c = 0; c < rb.ndofs; ++c)
-            for (int r = 0; r < 6; ++r) J_at(jac, nd, i, r, rb.assembly + c) += jj[c * 6 + r];
+            if ((rb.assembly + c) % G == lane)
+                for (int r = 0; r < 6; ++r) J_at(jac, nd, i, r, rb.assembly + c) += jj[c * 6 + r];
     }
+    mb_sync<G>();
 }
 
 // nalgebra LU::new (partial pivoting) on the nd x nd column-major block m; piv[i] = row swapped with row i
-__device__ void mb_lu_factor(float* m, int* piv, int n) {
+template <int G>
+__device__ void mb_lu_factor(float* m, int* piv, int n, uint32_t lane) {
     for (int i = 0; i < n; ++i) {
         int p = i;
         float best = fabsf(m[i * n + i]);
@@ -367,46 +384,65 @@ __device__ void mb_lu_factor(float* m, int* piv, int n) {
                 best = fabsf(m[i * n + r]);
                 p = r;
             }
-        piv[i] = p;
+        if (lane == 0) piv[i] = p;
         const float diag = m[i * n + p];
         if (diag == 0.f) continue;
+        mb_sync<G>();  // everybody has read column i before rows are swapped
         if (p != i)
-            for (int c = 0; c < n; ++c) {
+            for (int c = (int)lane; c < n; c += G) {
                 float t = m[c * n + i];
                 m[c * n + i] = m[c * n + p];
                 m[c * n + p] = t;
             }
+        mb_sync<G>();
         const float inv_diag = 1.f / diag;
-        for (int r = i + 1; r < n; ++r) m[i * n + r] *= inv_diag;
-        for (int c = i + 1; c < n; ++c) {
+        for (int c = i + 1 + (int)((lane + G - (uint32_t)((i + 1) % G)) % G); c < n; c += G) {
             const float pivot_row = m[c * n + i];
-            for (int r = i + 1; r < n; ++r) m[c * n + r] = (-pivot_row) * m[i * n + r] + m[c * n + r];
+            for (int r = i + 1; r < n; ++r) m[c * n + r] = (-pivot_row) * (m[i * n + r] * inv_diag) + m[c * n + r];
         }
+        mb_sync<G>();
+        if ((uint32_t)(i % G) == lane)
+            for (int r = i + 1; r < n; ++r) m[i * n + r] *= inv_diag;
+        mb_sync<G>();
     }
 }
-__device__ bool mb_lu_solve(const float* m, const int* piv, int n, float* b) {
-    for (int i = 0; i < n; ++i)
-        if (piv[i] != i) {
-            float t = b[i];
-            b[i] = b[piv[i]];
-            b[piv[i]] = t;
-        }
+// LU::solve_mut on b (memory every lane of the group sees)
+template <int G>
+__device__ bool mb_lu_solve(const float* m, const int* piv, int n, float* b, uint32_t lane) {
+    if (lane == 0)
+        for (int i = 0; i < n; ++i)
+            if (piv[i] != i) {
+                float t = b[i];
+                b[i] = b[piv[i]];
+                b[piv[i]] = t;
+            }
+    mb_sync<G>();
     for (int i = 0; i + 1 < n; ++i) {
         const float coeff = b[i];
-        for (int r = i + 1; r < n; ++r) b[r] = (-coeff) * m[i * n + r] + b[r];
+        for (int r = i + 1 + (int)lane; r < n; r += G) b[r] = (-coeff) * m[i * n + r] + b[r];
+        mb_sync<G>();
     }
+    bool ok = true;
     for (int i = n - 1; i >= 0; --i) {
         const float diag = m[i * n + i];
-        if (diag == 0.f) return false;
-        b[i] /= diag;
+        if (diag == 0.f) {
+            ok = false;
+            break;
+        }
+        if (lane == 0) b[i] /= diag;
+        mb_sync<G>();
         const float coeff = b[i];
-        for (int r = 0; r < i; ++r) b[r] = (-coeff) * m[i * n + r] + b[r];
+        for (int r = (int)lane; r < i; r += G) b[r] = (-coeff) * m[i * n + r] + b[r];
+        mb_sync<G>();
     }
-    return true;
+    return ok;
 }
+// the same on a vector private to the calling thread
+__device__ __forceinline__ bool mb_lu_solve(const float* m, const int* piv, int n, float* b) { return mb_lu_solve<1>(m, piv, n, b, 0u); }
 
 // update_dynamics (:348-402) + update_inertias (:441-628)
-__device__ void mb_update_dynamics(const MbView& V, const MbMeta& M, const Proxies& P, float dt) {
+template <int G>
+__device__ void mb_update_dynamics(const MbView& V, const MbMeta& M, const Proxies& P, float dt, uint32_t lane) {
     MbLinkDev* L = V.links + M.first_link;
     const uint32_t nd = M.ndofs;
     float* jac = V.jac + M.jac_off;
@@ -442,14 +478,16 @@ __device__ void mb_update_dynamics(const MbView& V, const MbMeta& M, const Proxi
         st3(rb.vwj + 3, wa);
         st3(rb.vel, vl);
         st3(rb.vel + 3, va);
-        if (rb.body >= 0) {
+        if (rb.body >= 0 && lane == 0) {
             P.vel[2 * rb.body] = xyz_f4(vl, 0.f);
             P.vel[2 * rb.body + 1] = xyz_f4(va, 0.f);
         }
         Mat3 rot = quat_to_matrix(ldq(rb.l2w_q));
         stm(rb.inertia, mat_mul(mat_mul(rot, ldm(rb.local_inertia)), mat_transpose(rot)));
+        mb_sync<G>();
     }
-    for (uint32_t k = 0; k < nd * nd; ++k) mass[k] = 0.f;
+    for (uint32_t c = lane; c < nd; c += G)
+        for (uint32_t r = 0; r < nd; ++r) mass[c * nd + r] = 0.f;
     float work[6], t1[36], t2[36];
     for (uint32_t i = 0; i < M.n_links; ++i) {
         const MbLinkDev& rb = L[i];
@@ -461,7 +499,7 @@ __device__ void mb_update_dynamics(const MbView& V, const MbMeta& M, const Proxi
             for (int r = 0; r < 3; ++r)
                 for (int c = 0; c < 3; ++c) aug.m[r][c] = aug.m[r][c] + (a.m[r][c] - b.m[r][c]) * dt;
         }
-        for (uint32_t j = 0; j < nd; ++j) {  // quadform
+        for (uint32_t j = lane; j < nd; j += G) {  // quadform: column j of J^T M J
             float cj[6];
             for (int r = 0; r < 6; ++r) cj[r] = J_at(jac, nd, i, r, j);
             for (int r = 0; r < 3; ++r) work[r] = rb.mass * cj[r];
@@ -479,7 +517,7 @@ __device__ void mb_update_dynamics(const MbView& V, const MbMeta& M, const Proxi
             const Mat3 dvel_tr = cross_matrix_tr(ld3(rb.vel) - ld3(pr.vel));
             const Mat3 vwj_tr = cross_matrix_tr(ld3(rb.vwj));
             const Mat3 vwj_w = cross_matrix(ld3(rb.vwj + 3));
-            for (uint32_t c = 0; c < nd; ++c) {
+            for (uint32_t c = lane; c < nd; c += G) {
                 Vec3 pjv = mk3(J_at(jac, nd, rb.parent, 0, c), J_at(jac, nd, rb.parent, 1, c), J_at(jac, nd, rb.parent, 2, c));
                 Vec3 pjw = mk3(J_at(jac, nd, rb.parent, 3, c), J_at(jac, nd, rb.parent, 4, c), J_at(jac, nd, rb.parent, 5, c));
                 Vec3 rjv = mk3(J_at(jac, nd, i, 0, c), J_at(jac, nd, i, 1, c), J_at(jac, nd, i, 2, c));
@@ -500,9 +538,10 @@ __device__ void mb_update_dynamics(const MbView& V, const MbMeta& M, const Proxi
             }
             mbj_jacobian(rb, ldq(pr.l2w_q), t1);
             for (uint32_t c = 0; c < rb.ndofs; ++c) {
+                const uint32_t cc = rb.assembly + c;
+                if (cc % G != lane) continue;
                 Vec3 a = mat_vec(parent_w, mk3(t1[c * 6], t1[c * 6 + 1], t1[c * 6 + 2]));
                 Vec3 b = mat_vec(parent_w, mk3(t1[c * 6 + 3], t1[c * 6 + 4], t1[c * 6 + 5]));
-                const uint32_t cc = rb.assembly + c;
                 J_at(cor, nd, i, 0, cc) += a.x;
                 J_at(cor, nd, i, 1, cc) += a.y;
                 J_at(cor, nd, i, 2, cc) += a.z;
@@ -511,32 +550,34 @@ __device__ void mb_update_dynamics(const MbView& V, const MbMeta& M, const Proxi
                 J_at(cor, nd, i, 5, cc) += b.z;
             }
         } else {
-            for (uint32_t c = 0; c < nd; ++c)
+            for (uint32_t c = lane; c < nd; c += G)
                 for (int r = 0; r < 6; ++r) J_at(cor, nd, i, r, c) = 0.f;
         }
         mbj_jacobian_dot(rb, ldq(rb.p2w_q), t1);
         mbj_jacobian_dot_veldiff(rb, ldq(rb.p2w_q), vel + rb.assembly, t2);
         for (uint32_t c = 0; c < rb.ndofs; ++c) {
             const uint32_t cc = rb.assembly + c;
+            if (cc % G != lane) continue;
             for (int r = 0; r < 6; ++r) J_at(cor, nd, i, r, cc) += t1[c * 6 + r];
             for (int r = 0; r < 6; ++r) J_at(cor, nd, i, r, cc) += t2[c * 6 + r];
         }
-        for (uint32_t c = 0; c < nd; ++c) {
+        for (uint32_t c = lane; c < nd; c += G) {
             for (int r = 0; r < 3; ++r) icd[c * 6 + r] = J_at(cor, nd, i, r, c) * (rb.mass * dt);
             Vec3 wv = mat_vec(ang_inertia, mk3(J_at(cor, nd, i, 3, c), J_at(cor, nd, i, 4, c), J_at(cor, nd, i, 5, c)));
             icd[c * 6 + 3] = dt * wv.x;
             icd[c * 6 + 4] = dt * wv.y;
             icd[c * 6 + 5] = dt * wv.z;
-        }
-        for (uint32_t c = 0; c < nd; ++c)
             for (uint32_t r = 0; r < nd; ++r) mass[c * nd + r] = dot6v(&J_at(jac, nd, i, 0, r), icd + c * 6) + mass[c * nd + r];
+        }
     }
-    for (uint32_t k = 0; k < nd; ++k) mass[k * nd + k] += damp[k] * dt;
-    mb_lu_factor(mass, V.piv + M.dof_off, (int)nd);
+    for (uint32_t k = lane; k < nd; k += G) mass[k * nd + k] += damp[k] * dt;
+    mb_sync<G>();
+    mb_lu_factor<G>(mass, V.piv + M.dof_off, (int)nd, lane);
 }
 
 // update_acceleration (:271-346); ext = dt * acceleration, mj_lambda = 0
-__device__ void mb_update_acceleration(const MbView& V, const MbMeta& M, Vec3 gravity, float dt) {
+template <int G>
+__device__ void mb_update_acceleration(const MbView& V, const MbMeta& M, Vec3 gravity, float dt, uint32_t lane) {
     MbLinkDev* L = V.links + M.first_link;
     const uint32_t nd = M.ndofs;
     const float* jac = V.jac + M.jac_off;
@@ -544,7 +585,7 @@ __device__ void mb_update_acceleration(const MbView& V, const MbMeta& M, Vec3 gr
     const float* vel = V.vel + M.dof_off;
     const float* damp = V.damp + M.dof_off;
     float* accs = V.accw + (size_t)6 * M.first_link;  // workspace.accs
-    for (uint32_t c = 0; c < nd; ++c) acc[c] = 0.f;
+    for (uint32_t c = lane; c < nd; c += G) acc[c] = 0.f;
     for (uint32_t i = 0; i < M.n_links; ++i) {
         const MbLinkDev& rb = L[i];
         Vec3 al = ld3(rb.vdwj), aa = ld3(rb.vdwj + 3);
@@ -563,6 +604,7 @@ __device__ void mb_update_acceleration(const MbView& V, const MbMeta& M, Vec3 gr
         }
         st3(accs + 6 * i, al);
         st3(accs + 6 * i + 3, aa);
+        mb_sync<G>();
         const Mat3 inertia = ldm(rb.inertia);
         const Vec3 w = ld3(rb.vel + 3);
         Vec3 gf = (M.flags & NB2_BODY_FLAG_GRAVITY) ? gravity * rb.mass : mk3(0.f, 0.f, 0.f);
@@ -570,26 +612,100 @@ __device__ void mb_update_acceleration(const MbView& V, const MbMeta& M, Vec3 gr
         Vec3 fl = gf - al * rb.mass;
         Vec3 fa = (-gyro) - mat_vec(inertia, aa);
         const float f[6] = {fl.x, fl.y, fl.z, fa.x, fa.y, fa.z};
-        for (uint32_t c = 0; c < nd; ++c) acc[c] = dot6v(&jac[(size_t)i * 6 * nd + (size_t)c * 6], f) + acc[c];
+        for (uint32_t c = lane; c < nd; c += G) acc[c] = dot6v(&jac[(size_t)i * 6 * nd + (size_t)c * 6], f) + acc[c];
     }
-    for (uint32_t c = 0; c < nd; ++c) acc[c] = 0.f + acc[c];  // + generalized forces (none through this ABI)
-    for (uint32_t c = 0; c < nd; ++c) acc[c] = -1.f * damp[c] * vel[c] + acc[c];
-    mb_lu_solve(V.mass + M.mass_off, V.piv + M.dof_off, (int)nd, acc);
+    for (uint32_t c = lane; c < nd; c += G) {
+        float a = 0.f + acc[c];  // + generalized forces (none through this ABI)
+        acc[c] = -1.f * damp[c] * vel[c] + a;
+    }
+    mb_sync<G>();
+    mb_lu_solve<G>(V.mass + M.mass_off, V.piv + M.dof_off, (int)nd, acc, lane);
     float* ext = V.ext + M.dof_off;
     float* lam = V.lam + M.dof_off;
-    for (uint32_t c = 0; c < nd; ++c) {
+    for (uint32_t c = lane; c < nd; c += G) {
         ext[c] = dt * acc[c];
         lam[c] = 0.f;
     }
 }
 
-__global__ void __launch_bounds__(MB_TPB) k_mb_refresh(MbView V, Proxies P, float dt, Vec3 gravity, int with_acceleration) {
-    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+// mode 0: kinematics + dynamics (upload); 1: + accelerations (start of a step); 2: kinematics + link velocities only
+// (end of a step: the next step recomputes the mass matrix from the same state, mechanical_world.rs:343-346 / :230-243).
+// One warp per multibody.  `stage_words` != 0: the block's dynamic shared memory holds one scratch region per warp
+// (body jacobians, Coriolis matrices, mass matrix, pivots); the refresh then runs out of shared memory and only the
+// jacobians and the LU go back to global memory, once, coalesced.
+__device__ void mb_link_velocities(const MbView& V, const MbMeta& M, const Proxies& P, uint32_t lane) {
+    MbLinkDev* L = V.links + M.first_link;
+    const float* vel = V.vel + M.dof_off;
+    for (uint32_t i = 0; i < M.n_links; ++i) {
+        MbLinkDev& rb = L[i];
+        Vec3 wl, wa;
+        mbj_jmul(rb, vel + rb.assembly, &wl, &wa);
+        Vec3 vl = wl, va = wa;
+        if (i != 0) {
+            const MbLinkDev& pr = L[rb.parent];
+            Quat pq = ldq(pr.l2w_q);
+            wl = quat_rotate(pq, wl);
+            wa = quat_rotate(pq, wa);
+            vl = ld3(pr.vel) + wl;
+            va = ld3(pr.vel + 3) + wa;
+            vl = vl + cross3(ld3(pr.vel + 3), ld3(rb.com) - ld3(pr.com));
+        }
+        st3(rb.vel, vl);
+        st3(rb.vel + 3, va);
+        if (rb.body >= 0 && lane == 0) {
+            P.vel[2 * rb.body] = xyz_f4(vl, 0.f);
+            P.vel[2 * rb.body + 1] = xyz_f4(va, 0.f);
+        }
+        __syncwarp();
+    }
+}
+#define MB_WPB 4  // warps (multibodies) per block of the warp-per-multibody kernels
+__global__ void __launch_bounds__(32 * MB_WPB) k_mb_refresh(MbView V, Proxies P, float dt, Vec3 gravity, int mode, uint32_t stage_words,
+                                                            uint32_t jac_words) {
+    extern __shared__ float mb_smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= V.n_mb) return;
-    const MbMeta M = V.meta[m];
-    mb_update_kinematics(V, M, P);
-    mb_update_dynamics(V, M, P, dt);
-    if (with_acceleration) mb_update_acceleration(V, M, gravity, dt);
+    MbMeta M = V.meta[m];
+    if (mode == 2) {
+        mb_update_kinematics<32>(V, M, P, lane);
+        mb_link_velocities(V, M, P, lane);
+        return;
+    }
+    if (stage_words == 0) {
+        mb_update_kinematics<32>(V, M, P, lane);
+        mb_update_dynamics<32>(V, M, P, dt, lane);
+        if (mode == 1) mb_update_acceleration<32>(V, M, gravity, dt, lane);
+        return;
+    }
+    // per-warp region: [jac | cor | mass | icd | piv]
+    const uint32_t nd = M.ndofs, jw = M.n_links * 6 * nd;
+    float* reg = mb_smem + (size_t)warp * stage_words;
+    MbView W = V;
+    MbMeta L = M;
+    W.jac = reg;
+    W.cor = reg + jac_words;
+    W.mass = reg + 2 * jac_words;
+    W.icd = W.mass + nd * nd;
+    W.piv = reinterpret_cast<int*>(W.icd + 6 * nd);
+    W.vel = V.vel + M.dof_off;
+    W.damp = V.damp + M.dof_off;
+    W.acc = V.acc + M.dof_off;
+    W.ext = V.ext + M.dof_off;
+    W.lam = V.lam + M.dof_off;
+    L.dof_off = 0;
+    L.jac_off = 0;
+    L.mass_off = 0;
+    mb_update_kinematics<32>(W, L, P, lane);
+    mb_update_dynamics<32>(W, L, P, dt, lane);
+    if (mode == 1) mb_update_acceleration<32>(W, L, gravity, dt, lane);
+    __syncwarp();
+    float* gj = V.jac + M.jac_off;
+    for (uint32_t k = lane; k < jw; k += 32) gj[k] = W.jac[k];
+    float* gm = V.mass + M.mass_off;
+    for (uint32_t k = lane; k < nd * nd; k += 32) gm[k] = W.mass[k];
+    int* gp = V.piv + M.dof_off;
+    for (uint32_t k = lane; k < nd; k += 32) gp[k] = W.piv[k];
 }
 
 // ------------------------------------------------------------------------------------------------ rows
@@ -676,23 +792,52 @@ struct MbCache {
 // One thread per multibody: the rows of its contacts (SignoriniCoulombPyramidModel::constraints,
 // signorini_coulomb_pyramid_model.rs:56-224 with SignoriniModel::build_velocity_constraint, signorini_model.rs:37-138)
 // and of its unit joints' motors and limits (unit_joint.rs:39-196).
-__global__ void __launch_bounds__(MB_TPB) k_mb_assemble(MbView V, MbContacts C, MbRows R, MbCache K, const int* __restrict__ mb_of_link,
-                                                        float warmstart_coeff, float restitution_threshold, float inv_dt) {
-    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= V.n_mb) return;
-    const MbMeta M = V.meta[m];
+__global__ void __launch_bounds__(32 * MB_WPB) k_mb_assemble(MbView Vg, MbContacts C, MbRows R, MbCache K, const int* __restrict__ mb_of_link,
+                                                             float warmstart_coeff, float restitution_threshold, float inv_dt,
+                                                             uint32_t stage_words, uint32_t jac_words) {
+    // One warp per multibody; its lanes take the (contact, row) jobs -- every row is one J = J_link^T f and one
+    // LU solve, independent of the others -- with the body jacobians and the LU of the mass matrix staged in the warp's
+    // slice of shared memory (read by all lanes at the same address: a broadcast).
+    extern __shared__ float mb_smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t m = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (m >= Vg.n_mb) return;
+    MbMeta M = Vg.meta[m];
     const uint32_t nd = M.ndofs;
+    MbView V = Vg;
+    if (stage_words) {
+        float* reg = mb_smem + (size_t)warp * stage_words;
+        const uint32_t jw = M.n_links * 6 * nd;
+        const float* gj = Vg.jac + M.jac_off;
+        for (uint32_t k = lane; k < jw; k += 32) reg[k] = gj[k];
+        float* sm = reg + jac_words;
+        const float* gm = Vg.mass + M.mass_off;
+        for (uint32_t k = lane; k < nd * nd; k += 32) sm[k] = gm[k];
+        int* sp = reinterpret_cast<int*>(sm + nd * nd);
+        const int* gp = Vg.piv + M.dof_off;
+        for (uint32_t k = lane; k < nd; k += 32) sp[k] = gp[k];
+        V.jac = reg;
+        V.mass = sm;
+        V.piv = sp;
+        V.vel = Vg.vel + M.dof_off;
+        V.ext = Vg.ext + M.dof_off;
+        M.jac_off = 0;
+        M.mass_off = 0;
+        M.dof_off = 0;
+    }
     uint32_t* list = C.mlist + (size_t)m * NB2_MB_MANIFOLD_CAP;
     const uint32_t nm = min(C.mcount[m], (uint32_t)NB2_MB_MANIFOLD_CAP);
-    for (uint32_t a = 1; a < nm; ++a) {  // manifold order (the atomics filled the list in any order)
-        const uint32_t v = list[a];
-        uint32_t b = a;
-        while (b > 0 && list[b - 1] > v) {
-            list[b] = list[b - 1];
-            --b;
+    if (lane == 0)
+        for (uint32_t a = 1; a < nm; ++a) {  // manifold order (the atomics filled the list in any order)
+            const uint32_t v = list[a];
+            uint32_t b = a;
+            while (b > 0 && list[b - 1] > v) {
+                list[b] = list[b - 1];
+                --b;
+            }
+            list[b] = v;
         }
-        list[b] = v;
-    }
+    __syncwarp();
     const uint32_t base = R.row_off[m];
     const uint32_t cap = R.row_off[m + 1] - base;
     uint32_t ncon = 0;
@@ -708,27 +853,39 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_assemble(MbView V, MbContacts C, 
         if ((l.flags & NB2_MBJ_FLAG_MAX) && -(l.max_pos - l.coord) >= 0.f) ++n_uni;
     }
     if (2 * ncon + n_uni + n_bil + ncon > cap) {  // cannot happen: the offsets were sized from the same counts
-        atomicOr(&C.flags[0], NB2_FLAG_MB_OVERFLOW);
+        if (lane == 0) atomicOr(&C.flags[0], NB2_FLAG_MB_OVERFLOW);
         ncon = 0;
     }
-    uint32_t* seg = R.seg + 4 * m;
-    seg[0] = 2 * ncon;
-    seg[1] = n_uni;
-    seg[2] = n_bil;
-    seg[3] = ncon;
+    if (lane == 0) {
+        uint32_t* seg = R.seg + 4 * m;
+        seg[0] = 2 * ncon;
+        seg[1] = n_uni;
+        seg[2] = n_bil;
+        seg[3] = ncon;
+    }
     const uint32_t fr0 = base, in0 = base + 2 * ncon, no0 = in0 + n_uni + n_bil;
     const size_t rs = (size_t)2 * R.nd_stride;
     const float* vel = V.vel + M.dof_off;
     const float* ext = V.ext + M.dof_off;
     float tmp[NB2_MB_MAX_DOFS];
-    // ---- contacts
-    uint32_t k = 0;  // contact counter within the multibody
-    for (uint32_t a = 0; a < nm; ++a) {
+    // ---- contacts: job = 3 * k + w, k the contact's rank within the multibody (manifold order), w the row
+    __syncwarp();
+    for (uint32_t job = lane; job < 3 * ncon; job += 32) {
+        const uint32_t k = job / 3;
+        const int w = (int)(job % 3);
+        uint32_t a = 0, before = 0;
+        for (; a < nm; ++a) {
+            const uint32_t n = C.manifolds[list[a]].num_contacts;
+            if (k < before + n) break;
+            before += n;
+        }
         const nb2_manifold& mf = C.manifolds[list[a]];
+        const uint32_t ci = mf.first_contact + (k - before);
+        if (ci >= C.n_contacts) continue;
         const int l1 = C.link_of_body[mf.body1], l2 = C.link_of_body[mf.body2];
         const Vec3 surf = mk3(mf.surface_velocity[0], mf.surface_velocity[1], mf.surface_velocity[2]);
         const Quat q1 = f4_quat(C.pos_q[mf.body1]);
-        for (uint32_t ci = mf.first_contact; ci < mf.first_contact + mf.num_contacts && ci < C.n_contacts; ++ci, ++k) {
+        {
             const nb2_contact& c = C.contacts[ci];
             const Vec3 normal = ld3(c.normal), world1 = ld3(c.world1), world2 = ld3(c.world2);
             float4 cached = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -753,33 +910,33 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_assemble(MbView V, MbContacts C, 
             const Vec3 center2 = world2 - normal * mf.margin2;
             Vec3 t1, t2;
             tangent_basis(normal, &t1, &t2);
-            const Vec3 dirs[3] = {-normal, t1, t2};
-            const float rhs0[3] = {dot3(normal, surf), dot3(t1, surf), dot3(t2, surf)};
-            const uint32_t rows[3] = {no0 + k, fr0 + 2 * k, fr0 + 2 * k + 1};
-            for (int w = 0; w < 3; ++w) {
-                float* J = R.jw + (size_t)rows[w] * rs;
+            const Vec3 dir = w == 0 ? -normal : (w == 1 ? t1 : t2);
+            const float rhs0 = w == 0 ? dot3(normal, surf) : (w == 1 ? dot3(t1, surf) : dot3(t2, surf));
+            const uint32_t rowi = w == 0 ? no0 + k : fr0 + 2 * k + (uint32_t)(w - 1);
+            {
+                float* J = R.jw + (size_t)rowi * rs;
                 float* WJ = J + R.nd_stride;
-                float out_vel = rhs0[w];
+                float out_vel = rhs0;
                 bool first = true;
                 // a kinematic partner contributes its velocity at the contact point (fill_constraint_geometry's
                 // Kinematic branch, rigid_body.rs:693-698); a static one nothing
-                auto kinematic_side = [&](int body, Vec3 center, Vec3 dir) {
+                auto kinematic_side = [&](int body, Vec3 center, Vec3 d) {
                     if (C.status[body] != NB2_BODY_KINEMATIC) return;
                     const Vec3 pos = center - f4_xyz(C.com_im[body]);
-                    const Vec3 fa = cross3(pos, dir);
-                    const float f[6] = {dir.x, dir.y, dir.z, fa.x, fa.y, fa.z};
+                    const Vec3 fa = cross3(pos, d);
+                    const float f[6] = {d.x, d.y, d.z, fa.x, fa.y, fa.z};
                     const float4 vl = C.vel[2 * body], va = C.vel[2 * body + 1];
                     const float v[6] = {vl.x, vl.y, vl.z, va.x, va.y, va.z};
                     out_vel += dot6v(f, v);
                 };
                 if (l1 >= 0) {
-                    mb_fill_geometry(V, M, (uint32_t)l1 - M.first_link, center1, false, dirs[w], tmp, J, WJ, false);
+                    mb_fill_geometry(V, M, (uint32_t)l1 - M.first_link, center1, false, dir, tmp, J, WJ, false);
                     first = false;
                 } else {
-                    kinematic_side(mf.body1, center1, dirs[w]);
+                    kinematic_side(mf.body1, center1, dir);
                 }
-                if (l2 >= 0) mb_fill_geometry(V, M, (uint32_t)l2 - M.first_link, center2, false, -dirs[w], tmp, J, WJ, !first);
-                else kinematic_side(mf.body2, center2, -dirs[w]);
+                if (l2 >= 0) mb_fill_geometry(V, M, (uint32_t)l2 - M.first_link, center2, false, -dir, tmp, J, WJ, !first);
+                else kinematic_side(mf.body2, center2, -dir);
                 float inv_r = mb_dot((int)nd, J, WJ);
                 out_vel += mb_dot((int)nd, J, vel);
                 out_vel += mb_dot((int)nd, J, ext);
@@ -803,10 +960,11 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_assemble(MbView V, MbContacts C, 
                     row.imp = (w == 1 ? cached.y : cached.z) * warmstart_coeff;
                     row.kind = NB2_ROW_DEPENDENT;
                 }
-                R.rows[rows[w]] = row;
+                R.rows[rowi] = row;
             }
         }
     }
+    if (lane != 0) return;  // the few unit-joint rows: one lane
     // ---- internal rows: unilateral (limits) first, then bilateral (motors), each in link order
     uint32_t iu = in0, ib = in0 + n_uni;
     for (uint32_t i = 0; i < M.n_links; ++i) {
@@ -899,9 +1057,13 @@ __global__ void k_mb_row_counts(MbView V, MbContacts C, uint32_t* row_cnt) {
 // SORProx::solve restricted to one multibody (sor_prox.rs:48-80, 159-179), one thread per multibody; then
 // cache_impulses (signorini_coulomb_pyramid_model.rs:226-261; unit_joint rows: multibody.rs:1046-1053), the velocity
 // update and Body::integrate (moreau_jean_solver.rs:328-347, multibody.rs:807-814).
-__global__ void __launch_bounds__(MB_TPB) k_mb_velocity_solve(MbView V, MbRows R, MbCache K, const nb2_contact* __restrict__ contacts,
-                                                              int iters, float dt) {
-    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * MB_WPB) k_mb_velocity_solve(MbView V, MbRows R, MbCache K, const nb2_contact* __restrict__ contacts,
+                                                                   int iters, float dt) {
+    // One warp per multibody: lane c holds mj_lambda[c] and mj_lambda[c + 32] (ndofs <= 64) in registers; a row is
+    // two coalesced loads (J, M^-1 J), a butterfly reduction for J . mj_lambda and an axpy.  The rows stay in the
+    // reference's order; only the summation order inside a dot product differs from the one-thread form.
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (m >= V.n_mb) return;
     const MbMeta M = V.meta[m];
     const int nd = (int)M.ndofs;
@@ -910,22 +1072,25 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_velocity_solve(MbView V, MbRows R
     const uint32_t nf = seg[0], nu = seg[1], nbil = seg[2], nn = seg[3];
     const uint32_t fr0 = base, iu0 = base + nf, ib0 = iu0 + nu, no0 = ib0 + nbil;
     const size_t rs = (size_t)2 * R.nd_stride;
-    float lam[NB2_MB_MAX_DOFS];
-    for (int c = 0; c < nd; ++c) lam[c] = 0.f;
+    const bool h0 = (int)lane < nd, h1 = (int)lane + 32 < nd;
+    float lam0 = 0.f, lam1 = 0.f;
     auto warm = [&](uint32_t r) {
         const float imp = R.rows[r].imp;
         if (imp != 0.f) {
             const float* WJ = R.jw + (size_t)r * rs + R.nd_stride;
-            for (int c = 0; c < nd; ++c) lam[c] = imp * WJ[c] + lam[c];
+            if (h0) lam0 = imp * WJ[lane] + lam0;
+            if (h1) lam1 = imp * WJ[lane + 32] + lam1;
         }
     };
     for (uint32_t r = no0; r < no0 + nn; ++r) warm(r);  // warmstart_set: unilateral, then bilateral rows
     for (uint32_t r = fr0; r < fr0 + nf; ++r) warm(r);
     for (uint32_t r = iu0; r < ib0 + nbil; ++r) warm(r);  // warmstart_internal_velocity_constraints
     auto solve = [&](uint32_t r) {
-        MbRow& row = R.rows[r];
+        const MbRow row = R.rows[r];
         const float* J = R.jw + (size_t)r * rs;
         const float* WJ = J + R.nd_stride;
+        const float j0 = h0 ? J[lane] : 0.f, j1 = h1 ? J[lane + 32] : 0.f;
+        const float w0 = h0 ? WJ[lane] : 0.f, w1 = h1 ? WJ[lane + 32] : 0.f;
         float lo, hi;
         if (row.kind == NB2_ROW_UNILATERAL) {
             lo = 0.f;
@@ -937,15 +1102,19 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_velocity_solve(MbView V, MbRows R
             const float dep = R.rows[base + (uint32_t)row.dep].imp;
             if (dep == 0.f) {
                 if (row.imp != 0.f) {
-                    for (int c = 0; c < nd; ++c) lam[c] = (-row.imp) * WJ[c] + lam[c];
-                    row.imp = 0.f;
+                    lam0 = (-row.imp) * w0 + lam0;
+                    lam1 = (-row.imp) * w1 + lam1;
+                    if (lane == 0) R.rows[r].imp = 0.f;
                 }
                 return;
             }
             hi = row.lim * dep;
             lo = -hi;
         }
-        const float d = mb_dot(nd, J, lam) + row.rhs;
+        float d = j0 * lam0 + j1 * lam1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+        d += row.rhs;
         float ni;
         if (row.kind == NB2_ROW_UNILATERAL) ni = fmaxf(0.f, row.imp - row.r * d);
         else {
@@ -953,37 +1122,49 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_velocity_solve(MbView V, MbRows R
             ni = v > lo ? (v < hi ? v : hi) : lo;
         }
         const float dl = ni - row.imp;
-        row.imp = ni;
-        for (int c = 0; c < nd; ++c) lam[c] = dl * WJ[c] + lam[c];
+        if (lane == 0) R.rows[r].imp = ni;
+        lam0 = dl * w0 + lam0;
+        lam1 = dl * w1 + lam1;
     };
     for (int it = 0; it < iters; ++it) {
         for (uint32_t r = fr0; r < fr0 + nf; ++r) solve(r);        // step_bilateral(contacts)
+        __syncwarp();
         for (uint32_t r = iu0; r < ib0 + nbil; ++r) solve(r);      // internal: unilateral_ground, bilateral_ground
         for (uint32_t r = no0; r < no0 + nn; ++r) solve(r);        // step_unilateral(contacts)
+        __syncwarp();  // the normal impulses written by lane 0 are what the next sweep's friction rows read
     }
     // cache_impulses
-    for (uint32_t k = 0; k < nn; ++k) {
+    for (uint32_t k = lane; k < nn; k += 32) {
         const uint32_t ci = R.rows[no0 + k].contact;
         K.imp_cur[ci] = make_float4(R.rows[no0 + k].imp, R.rows[fr0 + 2 * k].imp, R.rows[fr0 + 2 * k + 1].imp, 0.f);
         K.ckey_cur[ci] = contacts[ci].key;
     }
     MbLinkDev* L = V.links + M.first_link;
-    for (uint32_t r = iu0; r < ib0 + nbil; ++r) {
-        const int s = R.rows[r].slot;
-        L[s / 3].impulses[s % 3] = R.rows[r].imp;
-    }
+    if (lane == 0)
+        for (uint32_t r = iu0; r < ib0 + nbil; ++r) {
+            const int s = R.rows[r].slot;
+            L[s / 3].impulses[s % 3] = R.rows[r].imp;
+        }
     // velocities += ext + mj_lambda; integrate
     float* vel = V.vel + M.dof_off;
     const float* ext = V.ext + M.dof_off;
     float* glam = V.lam + M.dof_off;
-    for (int c = 0; c < nd; ++c) {
-        glam[c] = lam[c];
-        float v = vel[c];
-        v += ext[c];
-        v += lam[c];
-        vel[c] = v;
+    if (h0) {
+        glam[lane] = lam0;
+        float v = vel[lane];
+        v += ext[lane];
+        v += lam0;
+        vel[lane] = v;
     }
-    for (uint32_t i = 0; i < M.n_links; ++i) mbj_integrate(L[i], dt, vel + L[i].assembly);
+    if (h1) {
+        glam[lane + 32] = lam1;
+        float v = vel[lane + 32];
+        v += ext[lane + 32];
+        v += lam1;
+        vel[lane + 32] = v;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < M.n_links; i += 32) mbj_integrate(L[i], dt, vel + L[i].assembly);
 }
 
 // NonlinearSORProx::solve restricted to one multibody (nonlinear_sor_prox.rs:17-55): per iteration its internal
@@ -1002,7 +1183,7 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_position_solve(MbView V, Proxies 
     float J[NB2_MB_MAX_DOFS], WJ[NB2_MB_MAX_DOFS], tmp[NB2_MB_MAX_DOFS];
     auto displace = [&](const float* disp) {
         for (uint32_t i = 0; i < M.n_links; ++i) mbj_apply_displacement(L[i], disp + L[i].assembly);
-        mb_update_kinematics(V, M, P);
+        mb_update_kinematics<1>(V, M, P, 0u);
     };
     for (int it = 0; it < iters; ++it) {
         if (M.has_internal) {
@@ -1039,7 +1220,7 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_position_solve(MbView V, Proxies 
                     displace(WJ);
                 }
             }
-            mb_update_kinematics(V, M, P);
+            mb_update_kinematics<1>(V, M, P, 0u);
         }
         uint32_t k = 0;
         for (uint32_t a = 0; a < nm; ++a) {
@@ -1143,6 +1324,9 @@ struct MbState {
     DevBuf<float4> cpos;
     uint32_t row_cap = 0;
     uint32_t link_bodies = 0;  // n_bodies the link_of_body map was sized for
+    uint32_t jac_words = 0, stage_words = 0;  // largest body-jacobian block; per-thread staging region of k_mb_refresh (0 = none)
+    int refresh_tpb = MB_TPB;
+    bool assemble_attr = false;
 };
 
 static MbState* mb_state(Context* ctx) { return reinterpret_cast<MbState*>(ctx->mb); }
@@ -1188,6 +1372,9 @@ void mb_release(Context* ctx) {
 
 int mb_count(Context* ctx) { return mb_state(ctx) ? (int)mb_state(ctx)->n_mb : 0; }
 
+struct MbState;
+static int mb_refresh(Context* ctx, MbState* S, int mode);
+
 int mb_upload(Context* ctx, const nb2_multibody* mbs, uint32_t n_mb, const nb2_mb_link* links, uint32_t n_links) {
     if (ctx->n_bodies == 0) return set_error(ctx, NB2_ERR_NOT_READY, "upload the bodies before the multibodies");
     if (!mb_state(ctx)) ctx->mb = new MbState();
@@ -1199,7 +1386,7 @@ int mb_upload(Context* ctx, const nb2_multibody* mbs, uint32_t n_mb, const nb2_m
     std::vector<MbLinkDev> dev(n_links);
     std::vector<int> mb_of_link(n_links, -1);
     std::vector<float> vel, damp;
-    uint32_t dof_off = 0, jac_off = 0, mass_off = 0, nd_max = 0;
+    uint32_t dof_off = 0, jac_off = 0, mass_off = 0, nd_max = 0, jac_max = 0;
     for (uint32_t m = 0; m < n_mb; ++m) {
         const nb2_multibody& r = mbs[m];
         if (r.n_links == 0 || (size_t)r.first_link + r.n_links > n_links) return set_error(ctx, NB2_ERR_BAD_INDEX, "multibody %u: link range", m);
@@ -1271,6 +1458,7 @@ int mb_upload(Context* ctx, const nb2_multibody* mbs, uint32_t n_mb, const nb2_m
         if (nd == 0 || nd > NB2_MB_MAX_DOFS) return set_error(ctx, NB2_ERR_UNSUPPORTED, "multibody %u: %u dofs (1..%d supported)", m, nd, NB2_MB_MAX_DOFS);
         M.ndofs = nd;
         nd_max = nd > nd_max ? nd : nd_max;
+        jac_max = r.n_links * 6 * nd > jac_max ? r.n_links * 6 * nd : jac_max;
         dof_off += nd;
         jac_off += r.n_links * 6 * nd;
         mass_off += nd * nd;
@@ -1319,9 +1507,37 @@ int mb_upload(Context* ctx, const nb2_multibody* mbs, uint32_t n_mb, const nb2_m
     k_mb_init_links<<<mb_blocks(n_links), MB_TPB, 0, ctx->stream>>>(S->links.p, n_links, ctx->raw.p, ctx->n_bodies, S->link_of_body.p, ctx->flags.p);
     NB2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
     S->n_mb = n_mb;
+    {  // staging geometry of k_mb_refresh: as many threads per block as regions fit the opt-in shared memory
+        S->jac_words = jac_max;
+        uint32_t words = 2 * jac_max + nd_max * nd_max + 6 * nd_max + nd_max;
+        words |= 1u;
+        size_t optin = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
+        int fit = (int)(optin / ((size_t)words * 4));
+        if (fit >= 1) {
+            S->stage_words = words;
+            S->refresh_tpb = 32 * (fit > MB_WPB ? MB_WPB : fit);
+            NB2_CUDA(ctx, cudaFuncSetAttribute(k_mb_refresh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+        } else {
+            S->stage_words = 0;
+            S->refresh_tpb = 32 * MB_WPB;
+        }
+    }
     // poses and velocities of the links' body records are valid from now on
-    k_mb_refresh<<<mb_blocks(n_mb), MB_TPB, 0, ctx->stream>>>(mb_view(S), mb_proxies(ctx), ctx->params.dt, mk3(0.f, 0.f, 0.f), 0);
-    ctx->launches += 2;
+    NB2_TRY(mb_refresh(ctx, S, 0));
+    ctx->launches += 1;
+    NB2_CUDA(ctx, cudaGetLastError());
+    return NB2_OK;
+}
+
+static int mb_refresh(Context* ctx, MbState* S, int mode) {
+    const Vec3 g = mk3(ctx->params.gravity[0], ctx->params.gravity[1], ctx->params.gravity[2]);
+    const bool stage = S->stage_words != 0 && mode != 2;
+    const int tpb = stage ? S->refresh_tpb : 32 * MB_WPB;  // one warp per multibody
+    const int wpb = tpb / 32;
+    const size_t smem = stage ? (size_t)wpb * S->stage_words * 4 : 0;
+    k_mb_refresh<<<(S->n_mb + wpb - 1) / wpb, tpb, smem, ctx->stream>>>(mb_view(S), mb_proxies(ctx), ctx->params.dt, g, mode,
+                                                                      stage ? S->stage_words : 0u, S->jac_words);
+    ctx->launches++;
     NB2_CUDA(ctx, cudaGetLastError());
     return NB2_OK;
 }
@@ -1341,11 +1557,7 @@ int mb_download_links(Context* ctx, nb2_mb_link* out, uint32_t n) {
 int mb_launch_refresh(Context* ctx) {
     MbState* S = mb_state(ctx);
     if (!S || S->n_mb == 0) return NB2_OK;
-    const Vec3 g = mk3(ctx->params.gravity[0], ctx->params.gravity[1], ctx->params.gravity[2]);
-    k_mb_refresh<<<mb_blocks(S->n_mb), MB_TPB, 0, ctx->stream>>>(mb_view(S), mb_proxies(ctx), ctx->params.dt, g, 1);
-    ctx->launches++;
-    NB2_CUDA(ctx, cudaGetLastError());
-    return NB2_OK;
+    return mb_refresh(ctx, S, 1);
 }
 
 static MbContacts mb_contacts(Context* ctx, MbState* S) {
@@ -1407,10 +1619,22 @@ int mb_launch_velocity(Context* ctx) {
     K.n_prev = ctx->imp_n[prev];
     K.imp_cur = ctx->imp[cur].p;
     K.ckey_cur = ctx->ckey[cur].p;
-    k_mb_assemble<<<mb_blocks(n_mb), MB_TPB, 0, ctx->stream>>>(V, C, R, K, S->mb_of_link.p, ctx->params.warmstart_coeff,
-                                                             ctx->params.restitution_velocity_threshold, ctx->inv_dt);
-    k_mb_velocity_solve<<<mb_blocks(n_mb), MB_TPB, 0, ctx->stream>>>(V, R, K, ctx->contacts.p, (int)ctx->params.max_velocity_iterations,
-                                                                   ctx->params.dt);
+    {
+        const uint32_t words = (S->jac_words + S->nd_max * S->nd_max + S->nd_max) | 1u;
+        const size_t optin = ctx->smem_optin ? ctx->smem_optin : 48 * 1024;
+        int fit = (int)(optin / ((size_t)words * 4));
+        const bool stage = fit >= 1;
+        const int wpb = stage ? (fit > MB_WPB ? MB_WPB : fit) : MB_WPB;
+        if (stage && !S->assemble_attr) {
+            NB2_CUDA(ctx, cudaFuncSetAttribute(k_mb_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+            S->assemble_attr = true;
+        }
+        k_mb_assemble<<<(n_mb + wpb - 1) / wpb, 32 * wpb, stage ? (size_t)wpb * words * 4 : 0, ctx->stream>>>(
+            V, C, R, K, S->mb_of_link.p, ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt,
+            stage ? words : 0u, S->jac_words);
+    }
+    k_mb_velocity_solve<<<(n_mb + MB_WPB - 1) / MB_WPB, 32 * MB_WPB, 0, ctx->stream>>>(V, R, K, ctx->contacts.p,
+                                                                                     (int)ctx->params.max_velocity_iterations, ctx->params.dt);
     ctx->launches += 4;
     NB2_CUDA(ctx, cudaGetLastError());
     return NB2_OK;
@@ -1430,10 +1654,9 @@ int mb_launch_position(Context* ctx) {
     if (ctx->params.max_position_iterations > 0)
         k_mb_position_solve<<<mb_blocks(S->n_mb), MB_TPB, 0, ctx->stream>>>(V, mb_proxies(ctx), mb_contacts(ctx, S), mb_rows(S), P,
                                                                            (int)ctx->params.max_position_iterations);
-    k_mb_refresh<<<mb_blocks(S->n_mb), MB_TPB, 0, ctx->stream>>>(V, mb_proxies(ctx), ctx->params.dt, mk3(0.f, 0.f, 0.f), 0);
-    ctx->launches += 2;
+    ctx->launches += 1;
     NB2_CUDA(ctx, cudaGetLastError());
-    return NB2_OK;
+    return mb_refresh(ctx, S, 2);
 }
 
 }  // namespace nb2

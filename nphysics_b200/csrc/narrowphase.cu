@@ -75,7 +75,7 @@ __global__ void k_collider_world(const nb2_collider* __restrict__ colliders, uns
     const Vec3 centre = f4_xyz(pos_t[c.body]) + quat_rotate(f4_quat(pos_q[c.body]), c.t);
     const bool has = fmaxf(c.he.x, fmaxf(c.he.y, c.he.z)) > 0.f;
     const int st = status[c.body];
-    const bool dyn = has && st == NB2_BODY_DYNAMIC;
+    const bool dyn = has && (st == NB2_BODY_DYNAMIC || st == NB2_BODY_MULTIBODY_LINK);  // a multibody link collides like a body
     const bool big = has && !dyn && st != NB2_BODY_DISABLED;
     cw[i] = xyz_f4(centre, dyn ? 1.f : 0.f);
     is_big[i] = big ? 1u : 0u;

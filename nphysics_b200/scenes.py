@@ -618,8 +618,8 @@ def multibody_ragdolls(n=10, pitch=3.0, height=5.0, spin=2.0, density=0.3, colli
         ((member_rad, leg_length + member_rad, member_rad), (0.0, -body_rady, body_radx), (0.0, leg_length + space, 0.0)),
         ((member_rad, leg_length + member_rad, member_rad), (0.0, -body_rady, -body_radx), (0.0, leg_length + space, 0.0)),
     ]
-    mb = _ground_only()
     per_row = int(np.ceil(np.sqrt(n)))
+    mb = _ground_only((max(20.0, (per_row + 1) * pitch), 0.2, max(20.0, (per_row + 1) * pitch)))
     for r in range(n):
         origin = [(r % per_row) * pitch, height, (r // per_row) * pitch]
         root = mb.add(-1, abi.MBJ_FREE, (body_radx, body_rady, body_radz), density, coords=origin + [0, 0, 0, 1],
