@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--no-quality", action="store_true")
     ap.add_argument("--quality-steps", type=int, default=10)
     ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--no-multibody", action="store_true")
+    ap.add_argument("--multibody-ragdolls", type=int, default=10000,
+                    help="`multibody` record: ragdolls of examples3d/ragdoll3.rs as shipped (reduced coordinates, SURVEY 8 f3)")
     ap.add_argument("--sharded-worlds", type=int, default=4096)
     ap.add_argument("--contact-layout", type=int, default=0, help="0 = 100-byte row stream, 1 = compact 80-byte records")
     ap.add_argument("--no-schedule-cache", action="store_true")
@@ -593,6 +596,11 @@ def run_b200(args, rank, world, local_rank):
             line["e2e_variants"] = variants
         if sharded is not None:
             line["sharded"] = sharded
+        if world == 1 and not args.no_multibody and args.mode == "coloured":
+            # ragdoll3.rs as shipped -- FreeJoint torso + five BallJoint members per Multibody, feet on
+            # the ground (contacts produced on the device every step); one warp per multibody
+            from tools.run_multibody import run as run_multibody
+            line["multibody"] = run_multibody(args.multibody_ragdolls, 20, True, 250)
         if world == 1 and not args.no_quality and args.mode == "coloured":
             line["quality_vs_oracle"] = quality_vs_oracle(args, sc, local_rank)
         if world == 1 and not args.no_cpu_baseline:

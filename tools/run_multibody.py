@@ -13,12 +13,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nphysics_b200 import abi, scenes  # noqa: E402
 
 
-def run(n, steps, contacts, cpu_sample):
+def _run_gpu(sc, n, steps, contacts, stream):
     import torch
     from nphysics_b200.solver import Solver
-    sc = scenes.multibody_ragdolls(n, height=2.245 if contacts else 5.0, spin=0.0 if contacts else 2.0)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)  # the events below are recorded on the stream the library launches on
     s = Solver(0, stream=stream.cuda_stream)
     s.set_params(sc.params)
     s.upload_bodies(sc.bodies)
@@ -51,6 +48,16 @@ def run(n, steps, contacts, cpu_sample):
            "ragdoll_steps_per_s": n / ms * 1e3, "launches_per_step": (s.launch_count() - l0) / steps,
            "non_finite": int(st["non_finite"])}
     s.close()
+    return rec
+
+
+def run(n, steps, contacts, cpu_sample):
+    import torch
+    from nphysics_b200.solver import Solver
+    sc = scenes.multibody_ragdolls(n, height=2.245 if contacts else 5.0, spin=0.0 if contacts else 2.0)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):  # the events below are recorded on the stream the library launches on
+        rec = _run_gpu(sc, n, steps, contacts, stream)
     if cpu_sample:
         from oracle import Oracle
         nc = min(n, cpu_sample)
