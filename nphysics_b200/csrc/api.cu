@@ -78,8 +78,8 @@ static int check_flags(Context* ctx) {
     if (f & 2u) return set_error(ctx, NB2_ERR_UNSUPPORTED, "a manifold/joint connects a body to itself (unsupported)");
     if (f & 0x400u) return set_error(ctx, NB2_ERR_BAD_INDEX, "a multibody link names a body that is not a NB2_BODY_MULTIBODY_LINK record");
     if (f & 0x100u)
-        return set_error(ctx, NB2_ERR_UNSUPPORTED, "a manifold couples a multibody with a dynamic body or with another multibody: such rows are not solved (DESIGN.md section 9)");
-    if (f & 0x200u) return set_error(ctx, NB2_ERR_UNSUPPORTED, "a multibody is in contact through more manifolds than the multibody path holds");
+        return set_error(ctx, NB2_ERR_UNSUPPORTED, "a manifold couples a multibody with a dynamic rigid body: such rows are not solved (DESIGN.md section 8b)");
+    if (f & 0x200u) return set_error(ctx, NB2_ERR_UNSUPPORTED, "a multibody touches more manifolds, or a component of multibodies holds more members / coordinates, than the multibody path holds (DESIGN.md section 8b)");
     if ((hv.overflow | hp.overflow) & 1u)
         return set_error(ctx, NB2_ERR_TOO_MANY_COLOURS, "colouring needs more than %d colours", NB2_MAX_COLOURS);
     if ((hv.overflow | hp.overflow) & 2u) return set_error(ctx, NB2_ERR_CUDA, "internal: phase index overflow");

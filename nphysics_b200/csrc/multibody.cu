@@ -8,15 +8,17 @@
 // src/joint/{free,ball,revolute,prismatic,fixed}_joint.rs.
 //
 // Execution model.  A multibody's rows all act on its own ndofs generalized velocities; rows against static or
-// kinematic bodies (and rows between two links of the same multibody) touch nothing else.  A multibody with only such
-// rows is therefore an island of its own, and ONE thread runs its whole step in the reference's order -- friction
-// rows of its contacts, internal rows, normal rows per sweep (sor_prox.rs:159-179); internal position constraints,
-// then its contacts per position iteration (nonlinear_sor_prox.rs:33-54) -- with mj_lambda in local memory.  The
-// batch dimension is the number of multibodies (10 000 ragdolls = 10 000 threads).  The multibody path runs beside
-// the rigid-body path on the same stream and shares its manifold / contact records, body poses (a link is a
+// kinematic bodies (and rows between two links of the same multibody) touch nothing else, rows between two multibodies
+// touch those two.  The multibodies joined by manifolds form COMPONENTS (labelled on the device every step), and one
+// warp runs a component's whole solve in the reference's order -- friction rows of its contacts (two-link class, then
+// ground class, each in manifold order), the members' unit-joint rows, normal rows per sweep (sor_prox.rs:159-179);
+// internal position constraints, then its contacts per position iteration (nonlinear_sor_prox.rs:33-54).  A multibody
+// that only touches the ground is a component of its own (mj_lambda in registers, lanes over its dofs); the batch
+// dimension is the number of components (10 000 ragdolls = 10 000 warps).  The multibody path runs beside the
+// rigid-body path on the same stream and shares its manifold / contact records, body poses (a link is a
 // NB2_BODY_MULTIBODY_LINK body record whose pose the kinematics write) and the per-contact impulse cache.
-// Rows between a multibody link and a DYNAMIC rigid body, or between two different multibodies, would couple the
-// two paths; they are detected and reported (NB2_ERR_UNSUPPORTED through the validation flags), not solved.
+// Rows between a multibody link and a DYNAMIC rigid body would couple the two paths; they are detected and reported
+// (NB2_ERR_UNSUPPORTED through the validation flags), not solved.
 //
 // Arithmetic follows oracle/multibody.inc expression by expression (-fmad=false): the parity tests compare
 // coordinates, velocities and impulses at 1e-5.
@@ -63,6 +65,8 @@ struct MbRow {
     int dep;                 // Dependent: row index (within the multibody) of the contact's normal row
     uint32_t contact;        // contact index, or 0xFFFFFFFF for an internal row
     int slot;                // contact rows: 0 normal, 1 / 2 tangents; internal rows: link index * 3 + (0 motor, 1 min, 2 max)
+    int other;               // contact rows between two multibodies: the other one (its J / M^-1 J follow this one's in the pool), else -1
+    int two_sided;           // both parts are multibody links (the reference's `unilateral` / `bilateral` classes, solved before the ground classes)
 };
 
 struct MbView {
@@ -714,12 +718,15 @@ struct MbContacts {
     const nb2_contact* contacts;
     uint32_t n_manifolds, n_contacts;
     const int* link_of_body;  // global link index or -1
+    const int* mb_of_link;    // multibody of a (global) link
     const int* status;        // effective body status
     ConstPoseQuads pos_t, pos_q;
     const float4* vel;
     const float4* com_im;
     uint32_t* mcount;         // [n_mb] manifolds of each multibody
     uint32_t* mlist;          // [n_mb][NB2_MB_MANIFOLD_CAP]
+    uint32_t* edges;          // pairs of multibodies joined by a manifold: [2 * edge], capacity n_manifolds
+    uint32_t* n_edges;
     uint32_t* flags;          // validation flags of the context ([0] |= bits)
 };
 #define NB2_FLAG_MB_COUPLED 0x100u   // a manifold couples a multibody with a dynamic body or another multibody
@@ -735,11 +742,13 @@ __global__ void k_mb_collect(MbContacts C, const int* __restrict__ mb_of_link) {
     const int s1 = C.status[mf.body1], s2 = C.status[mf.body2];
     int mb;
     if (l1 >= 0 && l2 >= 0) {
-        if (mb_of_link[l1] != mb_of_link[l2]) {
-            atomicOr(&C.flags[0], NB2_FLAG_MB_COUPLED);
-            return;
+        const int a = mb_of_link[l1], b = mb_of_link[l2];
+        mb = a < b ? a : b;  // a manifold between two multibodies is owned by the lower one and joins their components
+        if (a != b) {
+            const uint32_t e = atomicAdd(C.n_edges, 1u);
+            C.edges[2 * e] = (uint32_t)a;
+            C.edges[2 * e + 1] = (uint32_t)b;
         }
-        mb = mb_of_link[l1];
     } else {
         const int other = l1 >= 0 ? s2 : s1;
         if (other == NB2_BODY_DISABLED) return;  // mechanical_world.rs:287-300
@@ -754,14 +763,61 @@ __global__ void k_mb_collect(MbContacts C, const int* __restrict__ mb_of_link) {
     else atomicOr(&C.flags[0], NB2_FLAG_MB_OVERFLOW);
 }
 
+// Components of the multibodies under "share a manifold": label = smallest member.  One block; labels are relaxed
+// over the edges until nothing changes (the edge list is empty for multibodies that only touch the ground).
+__global__ void k_mb_components(uint32_t n_mb, const uint32_t* __restrict__ edges, const uint32_t* __restrict__ n_edges, uint32_t* comp,
+                                uint32_t* ccount) {
+    __shared__ int changed;
+    for (uint32_t m = threadIdx.x; m < n_mb; m += blockDim.x) {
+        comp[m] = m;
+        ccount[m] = 0u;
+    }
+    if (threadIdx.x == 0) ccount[n_mb] = 0u;
+    const uint32_t ne = *n_edges;
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < ne; e += blockDim.x) {
+            const uint32_t a = comp[edges[2 * e]], b = comp[edges[2 * e + 1]];
+            if (a < b) {
+                atomicMin(&comp[edges[2 * e + 1]], a);
+                changed = 1;
+            } else if (b < a) {
+                atomicMin(&comp[edges[2 * e]], b);
+                changed = 1;
+            }
+        }
+        __syncthreads();
+        if (!changed) break;
+        __syncthreads();
+    }
+    for (uint32_t m = threadIdx.x; m < n_mb; m += blockDim.x) atomicAdd(&ccount[comp[m]], 1u);
+}
+// members of every component, after the scan of ccount into coff (any order: the component's warp sorts its few members)
+__global__ void k_mb_members(uint32_t n_mb, const uint32_t* __restrict__ comp, const uint32_t* __restrict__ coff, uint32_t* ccursor,
+                             uint32_t* cmem) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mb) return;
+    const uint32_t root = comp[m];
+    cmem[coff[root] + atomicAdd(&ccursor[root], 1u)] = m;
+}
+
 struct MbRows {
     MbRow* rows;        // [row_cap]
-    float* jw;          // [row_cap][2 * nd_stride]: J then M^-1 J
+    float* jw;          // [row_cap][4 * nd_stride]: J, M^-1 J over the owner's dofs, then over the other multibody's
     float4* cpos;       // per contact row triple: local normal of body 1 (position solve), [row_cap / 3 + ...] indexed by the normal row
     uint32_t* row_off;  // [n_mb + 1] first row of each multibody (exclusive scan of row_cnt)
     uint32_t* row_cnt;  // [n_mb] rows assembled for each multibody: [0] friction, then internal, then normal
     uint32_t* seg;      // [n_mb][4]: friction rows, internal unilateral rows, internal bilateral rows, normal rows
     uint32_t nd_stride, row_cap;
+    // components (multibodies joined by manifolds): label, member list, scratch for the ordered contact lists
+    const uint32_t *comp, *coff, *cmem_c;
+    uint32_t* cmem;
+    uint32_t* lslot;    // [n_mb] offset of a member's mj_lambda in its component's shared-memory slice
+    uint2* corder;      // ordered contacts of the components: (normal row, first friction row); slices from a bump allocator
+    uint2* morder;      // scratch of the same shape: a component's manifolds while they are sorted
+    uint32_t* cursor;   // the allocator
 };
 
 // Multibody::fill_constraint_geometry (:971-1025): J = body_jacobian^T force, WJ = M^-1 J; accumulates (+=) into J / WJ so
@@ -864,7 +920,7 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_assemble(MbView Vg, MbContac
         seg[3] = ncon;
     }
     const uint32_t fr0 = base, in0 = base + 2 * ncon, no0 = in0 + n_uni + n_bil;
-    const size_t rs = (size_t)2 * R.nd_stride;
+    const size_t rs = (size_t)4 * R.nd_stride;
     const float* vel = V.vel + M.dof_off;
     const float* ext = V.ext + M.dof_off;
     float tmp[NB2_MB_MAX_DOFS];
@@ -929,19 +985,41 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_assemble(MbView Vg, MbContac
                     const float v[6] = {vl.x, vl.y, vl.z, va.x, va.y, va.z};
                     out_vel += dot6v(f, v);
                 };
-                if (l1 >= 0) {
-                    mb_fill_geometry(V, M, (uint32_t)l1 - M.first_link, center1, false, dir, tmp, J, WJ, false);
-                    first = false;
-                } else {
-                    kinematic_side(mf.body1, center1, dir);
-                }
-                if (l2 >= 0) mb_fill_geometry(V, M, (uint32_t)l2 - M.first_link, center2, false, -dir, tmp, J, WJ, !first);
+                // a side on this multibody fills (or adds to) the row's own J / M^-1 J out of the staged jacobians; a
+                // side on ANOTHER multibody fills the second half of the row from that multibody's jacobians and LU
+                const int mbA = l1 >= 0 ? mb_of_link[l1] : -1, mbB = l2 >= 0 ? mb_of_link[l2] : -1;
+                int other = -1;
+                float* J2 = WJ + R.nd_stride;
+                float* WJ2 = J2 + R.nd_stride;
+                auto link_side = [&](int link, int mbx, Vec3 center, Vec3 d) {
+                    if (mbx == (int)m) {
+                        mb_fill_geometry(V, M, (uint32_t)link - M.first_link, center, false, d, tmp, J, WJ, !first);
+                        first = false;
+                    } else {
+                        const MbMeta MX = Vg.meta[mbx];
+                        mb_fill_geometry(Vg, MX, (uint32_t)link - MX.first_link, center, false, d, tmp, J2, WJ2, false);
+                        other = mbx;
+                    }
+                };
+                if (l1 >= 0) link_side(l1, mbA, center1, dir);
+                else kinematic_side(mf.body1, center1, dir);
+                if (l2 >= 0) link_side(l2, mbB, center2, -dir);
                 else kinematic_side(mf.body2, center2, -dir);
+                if (first)  // cannot happen: the owner is one of the two
+                    for (uint32_t cc = 0; cc < nd; ++cc) J[cc] = WJ[cc] = 0.f;
                 float inv_r = mb_dot((int)nd, J, WJ);
                 out_vel += mb_dot((int)nd, J, vel);
                 out_vel += mb_dot((int)nd, J, ext);
+                if (other >= 0) {
+                    const MbMeta MX = Vg.meta[other];
+                    inv_r += mb_dot((int)MX.ndofs, J2, WJ2);
+                    out_vel += mb_dot((int)MX.ndofs, J2, Vg.vel + MX.dof_off);
+                    out_vel += mb_dot((int)MX.ndofs, J2, Vg.ext + MX.dof_off);
+                }
                 MbRow row;
                 row.r = inv_r != 0.f ? 1.f / inv_r : 1.f;
+                row.other = other;
+                row.two_sided = (l1 >= 0 && l2 >= 0) ? 1 : 0;
                 row.contact = ci;
                 row.slot = w;
                 row.lim = mf.friction;
@@ -989,6 +1067,8 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_assemble(MbView Vg, MbContac
             row.lim = l.motor_max_force;
             row.kind = NB2_ROW_BILATERAL;
             row.dep = 0;
+            row.other = -1;
+            row.two_sided = 0;
             row.contact = 0xFFFFFFFFu;
             row.slot = (int)(i * 3 + 0);
             R.rows[ib++] = row;
@@ -1007,6 +1087,8 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_assemble(MbView Vg, MbContac
             row.lim = 0.f;
             row.kind = NB2_ROW_UNILATERAL;
             row.dep = 0;
+            row.other = -1;
+            row.two_sided = 0;
             row.contact = 0xFFFFFFFFu;
             row.slot = (int)(i * 3 + 1);
             min_active = true;
@@ -1032,6 +1114,8 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_assemble(MbView Vg, MbContac
             row.lim = 0.f;
             row.kind = NB2_ROW_UNILATERAL;
             row.dep = 0;
+            row.other = -1;
+            row.two_sided = 0;
             row.contact = 0xFFFFFFFFu;
             row.slot = (int)(i * 3 + 2);
             R.rows[iu++] = row;
@@ -1057,40 +1141,194 @@ __global__ void k_mb_row_counts(MbView V, MbContacts C, uint32_t* row_cnt) {
 // SORProx::solve restricted to one multibody (sor_prox.rs:48-80, 159-179), one thread per multibody; then
 // cache_impulses (signorini_coulomb_pyramid_model.rs:226-261; unit_joint rows: multibody.rs:1046-1053), the velocity
 // update and Body::integrate (moreau_jean_solver.rs:328-347, multibody.rs:807-814).
-__global__ void __launch_bounds__(32 * MB_WPB) k_mb_velocity_solve(MbView V, MbRows R, MbCache K, const nb2_contact* __restrict__ contacts,
-                                                                   int iters, float dt) {
-    // One warp per multibody: lane c holds mj_lambda[c] and mj_lambda[c + 32] (ndofs <= 64) in registers; a row is
-    // two coalesced loads (J, M^-1 J), a butterfly reduction for J . mj_lambda and an axpy.  The rows stay in the
-    // reference's order; only the summation order inside a dot product differs from the one-thread form.
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+#define NB2_MB_COMP_DOFS 1024   // generalized coordinates of one component (multibodies joined by manifolds)
+#define NB2_MB_COMP_MEMBERS 48  // multibodies of one component
+__global__ void __launch_bounds__(32 * MB_WPB) k_mb_velocity_solve(MbView V, MbRows R, MbCache K, MbContacts C,
+                                                                   const nb2_contact* __restrict__ contacts, int iters, float dt) {
+    // One warp per COMPONENT (the warp of its smallest member; a multibody that only touches the ground is its own
+    // component).  mj_lambda of all members lives in the warp's slice of shared memory; a row is two coalesced loads
+    // per side (J, M^-1 J), a butterfly reduction for J . mj_lambda and an axpy.  Sweep order = the reference's:
+    // friction rows of the contacts between two links (manifold order), friction rows against the ground, every
+    // member's unit-joint rows, then the normal rows in the same two classes (sor_prox.rs:159-179).  Only the summation
+    // order inside a dot product differs from the one-thread form.
+    __shared__ float s_lam[MB_WPB][NB2_MB_COMP_DOFS];
+    __shared__ uint32_t s_mem[MB_WPB][NB2_MB_COMP_MEMBERS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t m = blockIdx.x * (blockDim.x >> 5) + warp;
     if (m >= V.n_mb) return;
-    const MbMeta M = V.meta[m];
-    const int nd = (int)M.ndofs;
-    const uint32_t base = R.row_off[m];
-    const uint32_t* seg = R.seg + 4 * m;
-    const uint32_t nf = seg[0], nu = seg[1], nbil = seg[2], nn = seg[3];
-    const uint32_t fr0 = base, iu0 = base + nf, ib0 = iu0 + nu, no0 = ib0 + nbil;
-    const size_t rs = (size_t)2 * R.nd_stride;
-    const bool h0 = (int)lane < nd, h1 = (int)lane + 32 < nd;
-    float lam0 = 0.f, lam1 = 0.f;
-    auto warm = [&](uint32_t r) {
-        const float imp = R.rows[r].imp;
-        if (imp != 0.f) {
-            const float* WJ = R.jw + (size_t)r * rs + R.nd_stride;
-            if (h0) lam0 = imp * WJ[lane] + lam0;
-            if (h1) lam1 = imp * WJ[lane + 32] + lam1;
+    if (R.comp[m] != m) return;  // solved by the warp of the component's smallest member
+    float* lam = s_lam[warp];
+    uint32_t* mem = s_mem[warp];
+    const uint32_t nmem = R.coff[m + 1] - R.coff[m];
+    const size_t rs = (size_t)4 * R.nd_stride;
+    // ---- members in index order, their mj_lambda slots, the ordered contact list
+    uint32_t ndtot = 0, ncont = 0, cstart = 0;
+    if (lane == 0) {
+        bool fits = nmem <= NB2_MB_COMP_MEMBERS;
+        if (fits) {
+            for (uint32_t k = 0; k < nmem; ++k) mem[k] = R.cmem[R.coff[m] + k];
+            for (uint32_t a = 1; a < nmem; ++a) {
+                const uint32_t v = mem[a];
+                uint32_t b = a;
+                while (b > 0 && mem[b - 1] > v) {
+                    mem[b] = mem[b - 1];
+                    --b;
+                }
+                mem[b] = v;
+            }
+            for (uint32_t k = 0; k < nmem; ++k) {
+                R.lslot[mem[k]] = ndtot;
+                ndtot += V.meta[mem[k]].ndofs;
+                ncont += R.seg[4 * mem[k] + 3];
+            }
+            fits = ndtot <= NB2_MB_COMP_DOFS;
         }
+        if (!fits) {
+            atomicOr(&C.flags[0], NB2_FLAG_MB_OVERFLOW);
+            ndtot = 0xFFFFFFFFu;
+        } else {
+            cstart = atomicAdd(R.cursor, ncont);
+            // contacts by class (two links first, then against the ground), each class in manifold order: gather the
+            // members' (sorted) manifold lists, sort by manifold index, expand to (normal row, first friction row)
+            uint2* out = R.corder + cstart;
+            uint2* tm = R.morder + cstart;  // (manifold index, member << 8 | position in the member's list); <= ncont entries
+            uint32_t n = 0;
+            for (int cls = 1; cls >= 0; --cls) {
+                uint32_t nmf = 0;
+                for (uint32_t k = 0; k < nmem; ++k) {
+                    const uint32_t x = mem[k];
+                    if (R.seg[4 * x + 3] == 0) continue;  // no contact rows (or they were dropped)
+                    const uint32_t* list = C.mlist + (size_t)x * NB2_MB_MANIFOLD_CAP;
+                    const uint32_t nm = min(C.mcount[x], (uint32_t)NB2_MB_MANIFOLD_CAP);
+                    for (uint32_t a = 0; a < nm; ++a) {
+                        const nb2_manifold& mf = C.manifolds[list[a]];
+                        const int two = (C.link_of_body[mf.body1] >= 0 && C.link_of_body[mf.body2] >= 0) ? 1 : 0;
+                        if (two != cls) continue;
+                        uint32_t pos = nmf++;
+                        while (pos > 0 && tm[pos - 1].x > list[a]) {
+                            tm[pos] = tm[pos - 1];
+                            --pos;
+                        }
+                        tm[pos] = make_uint2(list[a], (k << 8) | a);
+                    }
+                }
+                for (uint32_t i = 0; i < nmf; ++i) {
+                    const uint32_t x = mem[tm[i].y >> 8], a = tm[i].y & 255u;
+                    const uint32_t* list = C.mlist + (size_t)x * NB2_MB_MANIFOLD_CAP;
+                    const uint32_t* sg = R.seg + 4 * x;
+                    const uint32_t basex = R.row_off[x], no0 = basex + sg[0] + sg[1] + sg[2];
+                    uint32_t kk = 0;
+                    for (uint32_t a2 = 0; a2 < a; ++a2) kk += C.manifolds[list[a2]].num_contacts;
+                    const uint32_t nq = C.manifolds[list[a]].num_contacts;
+                    for (uint32_t q = 0; q < nq && n < ncont; ++q) out[n++] = make_uint2(no0 + kk + q, basex + 2 * (kk + q));
+                }
+            }
+            ncont = n;
+        }
+    }
+    ndtot = __shfl_sync(0xFFFFFFFFu, ndtot, 0);
+    if (ndtot == 0xFFFFFFFFu) return;
+    ncont = __shfl_sync(0xFFFFFFFFu, ncont, 0);
+    cstart = __shfl_sync(0xFFFFFFFFu, cstart, 0);
+    __syncwarp();
+    const uint2* order = R.corder + cstart;
+    if (nmem == 1) {
+        // ---- the common case, a multibody on its own: mj_lambda in registers (lane c holds [c] and [c + 32])
+        const MbMeta M = V.meta[m];
+        const int nd = (int)M.ndofs;
+        const uint32_t* sg = R.seg + 4 * m;
+        const uint32_t iu0 = R.row_off[m] + sg[0], iend = iu0 + sg[1] + sg[2];
+        const bool h0 = (int)lane < nd, h1 = (int)lane + 32 < nd;
+        float lam0 = 0.f, lam1 = 0.f;
+        auto warm1 = [&](uint32_t r) {
+            const float imp = R.rows[r].imp;
+            if (imp != 0.f) {
+                const float* WJ = R.jw + (size_t)r * rs + R.nd_stride;
+                if (h0) lam0 = imp * WJ[lane] + lam0;
+                if (h1) lam1 = imp * WJ[lane + 32] + lam1;
+            }
+        };
+        auto solve1 = [&](uint32_t r) {
+            const MbRow row = R.rows[r];
+            const float* J = R.jw + (size_t)r * rs;
+            const float* WJ = J + R.nd_stride;
+            const float j0 = h0 ? J[lane] : 0.f, j1 = h1 ? J[lane + 32] : 0.f;
+            const float w0 = h0 ? WJ[lane] : 0.f, w1 = h1 ? WJ[lane + 32] : 0.f;
+            float lo, hi;
+            if (row.kind == NB2_ROW_UNILATERAL) {
+                lo = 0.f;
+                hi = NB2_F32_MAX;
+            } else if (row.kind == NB2_ROW_BILATERAL) {
+                lo = -row.lim;
+                hi = row.lim;
+            } else {  // Dependent (sor_prox.rs:251-272)
+                const float dep = R.rows[R.row_off[m] + (uint32_t)row.dep].imp;
+                if (dep == 0.f) {
+                    if (row.imp != 0.f) {
+                        lam0 = (-row.imp) * w0 + lam0;
+                        lam1 = (-row.imp) * w1 + lam1;
+                        if (lane == 0) R.rows[r].imp = 0.f;
+                    }
+                    return;
+                }
+                hi = row.lim * dep;
+                lo = -hi;
+            }
+            float d = j0 * lam0 + j1 * lam1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+            d += row.rhs;
+            float ni;
+            if (row.kind == NB2_ROW_UNILATERAL) ni = fmaxf(0.f, row.imp - row.r * d);
+            else {
+                const float v = row.imp - row.r * d;
+                ni = v > lo ? (v < hi ? v : hi) : lo;
+            }
+            const float dl = ni - row.imp;
+            if (lane == 0) R.rows[r].imp = ni;
+            lam0 = dl * w0 + lam0;
+            lam1 = dl * w1 + lam1;
+        };
+        for (uint32_t q = 0; q < ncont; ++q) warm1(order[q].x);
+        for (uint32_t q = 0; q < ncont; ++q) {
+            warm1(order[q].y);
+            warm1(order[q].y + 1);
+        }
+        for (uint32_t r = iu0; r < iend; ++r) warm1(r);
+        for (int it = 0; it < iters; ++it) {
+            for (uint32_t q = 0; q < ncont; ++q) {
+                solve1(order[q].y);
+                solve1(order[q].y + 1);
+            }
+            __syncwarp();
+            for (uint32_t r = iu0; r < iend; ++r) solve1(r);
+            for (uint32_t q = 0; q < ncont; ++q) solve1(order[q].x);
+            __syncwarp();  // the normal impulses written by lane 0 are what the next sweep's friction rows read
+        }
+        if (h0) lam[lane] = lam0;
+        if (h1) lam[lane + 32] = lam1;
+        __syncwarp();
+    } else {
+    for (uint32_t c = lane; c < ndtot; c += 32) lam[c] = 0.f;
+    __syncwarp();
+    // ---- one row
+    auto sides = [&](uint32_t r, const MbRow& row, uint32_t owner, float dl) {  // mj_lambda += dl * M^-1 J on both sides
+        const uint32_t so = R.lslot[owner], no = V.meta[owner].ndofs;
+        const float* WJ = R.jw + (size_t)r * rs + R.nd_stride;
+        for (uint32_t c = lane; c < no; c += 32) lam[so + c] = dl * WJ[c] + lam[so + c];
+        if (row.other >= 0) {
+            const uint32_t s2 = R.lslot[row.other], n2 = V.meta[row.other].ndofs;
+            const float* WJ2 = WJ + 2 * R.nd_stride;
+            for (uint32_t c = lane; c < n2; c += 32) lam[s2 + c] = dl * WJ2[c] + lam[s2 + c];
+        }
+        __syncwarp();
     };
-    for (uint32_t r = no0; r < no0 + nn; ++r) warm(r);  // warmstart_set: unilateral, then bilateral rows
-    for (uint32_t r = fr0; r < fr0 + nf; ++r) warm(r);
-    for (uint32_t r = iu0; r < ib0 + nbil; ++r) warm(r);  // warmstart_internal_velocity_constraints
-    auto solve = [&](uint32_t r) {
+    auto warm = [&](uint32_t r, uint32_t owner) {
         const MbRow row = R.rows[r];
-        const float* J = R.jw + (size_t)r * rs;
-        const float* WJ = J + R.nd_stride;
-        const float j0 = h0 ? J[lane] : 0.f, j1 = h1 ? J[lane + 32] : 0.f;
-        const float w0 = h0 ? WJ[lane] : 0.f, w1 = h1 ? WJ[lane + 32] : 0.f;
+        if (row.imp != 0.f) sides(r, row, owner, row.imp);
+    };
+    auto solve = [&](uint32_t r, uint32_t owner) {
+        const MbRow row = R.rows[r];
         float lo, hi;
         if (row.kind == NB2_ROW_UNILATERAL) {
             lo = 0.f;
@@ -1099,11 +1337,10 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_velocity_solve(MbView V, MbR
             lo = -row.lim;
             hi = row.lim;
         } else {  // Dependent (sor_prox.rs:251-272)
-            const float dep = R.rows[base + (uint32_t)row.dep].imp;
+            const float dep = R.rows[R.row_off[owner] + (uint32_t)row.dep].imp;
             if (dep == 0.f) {
                 if (row.imp != 0.f) {
-                    lam0 = (-row.imp) * w0 + lam0;
-                    lam1 = (-row.imp) * w1 + lam1;
+                    sides(r, row, owner, -row.imp);
                     if (lane == 0) R.rows[r].imp = 0.f;
                 }
                 return;
@@ -1111,7 +1348,15 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_velocity_solve(MbView V, MbR
             hi = row.lim * dep;
             lo = -hi;
         }
-        float d = j0 * lam0 + j1 * lam1;
+        const uint32_t so = R.lslot[owner], no = V.meta[owner].ndofs;
+        const float* J = R.jw + (size_t)r * rs;
+        float d = 0.f;
+        for (uint32_t c = lane; c < no; c += 32) d += J[c] * lam[so + c];
+        if (row.other >= 0) {
+            const uint32_t s2 = R.lslot[row.other], n2 = V.meta[row.other].ndofs;
+            const float* J2 = J + 2 * R.nd_stride;
+            for (uint32_t c = lane; c < n2; c += 32) d += J2[c] * lam[s2 + c];
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
         d += row.rhs;
@@ -1121,72 +1366,119 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_velocity_solve(MbView V, MbR
             const float v = row.imp - row.r * d;
             ni = v > lo ? (v < hi ? v : hi) : lo;
         }
-        const float dl = ni - row.imp;
         if (lane == 0) R.rows[r].imp = ni;
-        lam0 = dl * w0 + lam0;
-        lam1 = dl * w1 + lam1;
+        sides(r, row, owner, ni - row.imp);
     };
-    for (int it = 0; it < iters; ++it) {
-        for (uint32_t r = fr0; r < fr0 + nf; ++r) solve(r);        // step_bilateral(contacts)
-        __syncwarp();
-        for (uint32_t r = iu0; r < ib0 + nbil; ++r) solve(r);      // internal: unilateral_ground, bilateral_ground
-        for (uint32_t r = no0; r < no0 + nn; ++r) solve(r);        // step_unilateral(contacts)
-        __syncwarp();  // the normal impulses written by lane 0 are what the next sweep's friction rows read
-    }
-    // cache_impulses
-    for (uint32_t k = lane; k < nn; k += 32) {
-        const uint32_t ci = R.rows[no0 + k].contact;
-        K.imp_cur[ci] = make_float4(R.rows[no0 + k].imp, R.rows[fr0 + 2 * k].imp, R.rows[fr0 + 2 * k + 1].imp, 0.f);
-        K.ckey_cur[ci] = contacts[ci].key;
-    }
-    MbLinkDev* L = V.links + M.first_link;
-    if (lane == 0)
-        for (uint32_t r = iu0; r < ib0 + nbil; ++r) {
-            const int s = R.rows[r].slot;
-            L[s / 3].impulses[s % 3] = R.rows[r].imp;
+    auto owner_of = [&](uint32_t r) -> uint32_t {  // the member whose row range holds r
+        uint32_t x = mem[0];
+        for (uint32_t k = 1; k < nmem; ++k)
+            if (R.row_off[mem[k]] <= r) x = mem[k];
+        return x;
+    };
+    auto internal = [&](bool warm_start) {
+        for (uint32_t k = 0; k < nmem; ++k) {
+            const uint32_t x = mem[k];
+            const uint32_t* sg = R.seg + 4 * x;
+            const uint32_t iu0 = R.row_off[x] + sg[0];
+            for (uint32_t r = iu0; r < iu0 + sg[1] + sg[2]; ++r) {
+                if (warm_start) warm(r, x);
+                else solve(r, x);
+            }
         }
-    // velocities += ext + mj_lambda; integrate
-    float* vel = V.vel + M.dof_off;
-    const float* ext = V.ext + M.dof_off;
-    float* glam = V.lam + M.dof_off;
-    if (h0) {
-        glam[lane] = lam0;
-        float v = vel[lane];
-        v += ext[lane];
-        v += lam0;
-        vel[lane] = v;
+    };
+    // warmstart_set: unilateral rows, then bilateral rows, then the internal ones (sor_prox.rs:57-65)
+    for (uint32_t q = 0; q < ncont; ++q) warm(order[q].x, nmem == 1 ? m : owner_of(order[q].x));
+    for (uint32_t q = 0; q < ncont; ++q) {
+        const uint32_t x = nmem == 1 ? m : owner_of(order[q].x);
+        warm(order[q].y, x);
+        warm(order[q].y + 1, x);
     }
-    if (h1) {
-        glam[lane + 32] = lam1;
-        float v = vel[lane + 32];
-        v += ext[lane + 32];
-        v += lam1;
-        vel[lane + 32] = v;
+    internal(true);
+    for (int it = 0; it < iters; ++it) {
+        for (uint32_t q = 0; q < ncont; ++q) {  // step_bilateral(contacts)
+            const uint32_t x = nmem == 1 ? m : owner_of(order[q].x);
+            solve(order[q].y, x);
+            solve(order[q].y + 1, x);
+        }
+        internal(false);                         // unilateral_ground, bilateral_ground of every member
+        for (uint32_t q = 0; q < ncont; ++q) solve(order[q].x, nmem == 1 ? m : owner_of(order[q].x));  // step_unilateral(contacts)
+    }
     }
     __syncwarp();
-    for (uint32_t i = lane; i < M.n_links; i += 32) mbj_integrate(L[i], dt, vel + L[i].assembly);
+    // ---- cache_impulses, velocity update, Body::integrate of every member
+    for (uint32_t q = lane; q < ncont; q += 32) {
+        const uint32_t rn = order[q].x, rf = order[q].y;
+        const uint32_t ci = R.rows[rn].contact;
+        K.imp_cur[ci] = make_float4(R.rows[rn].imp, R.rows[rf].imp, R.rows[rf + 1].imp, 0.f);
+        K.ckey_cur[ci] = contacts[ci].key;
+    }
+    for (uint32_t k = 0; k < nmem; ++k) {
+        const uint32_t x = mem[k];
+        const MbMeta MX = V.meta[x];
+        MbLinkDev* L = V.links + MX.first_link;
+        const uint32_t* sg = R.seg + 4 * x;
+        const uint32_t iu0 = R.row_off[x] + sg[0];
+        if (lane == 0)
+            for (uint32_t r = iu0; r < iu0 + sg[1] + sg[2]; ++r) {
+                const int sl = R.rows[r].slot;
+                L[sl / 3].impulses[sl % 3] = R.rows[r].imp;
+            }
+        float* vel = V.vel + MX.dof_off;
+        const float* ext = V.ext + MX.dof_off;
+        float* glam = V.lam + MX.dof_off;
+        const uint32_t so = R.lslot[x];
+        for (uint32_t c = lane; c < MX.ndofs; c += 32) {
+            const float l = lam[so + c];
+            glam[c] = l;
+            float v = vel[c];
+            v += ext[c];
+            v += l;
+            vel[c] = v;
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < MX.n_links; i += 32) mbj_integrate(L[i], dt, vel + L[i].assembly);
+    }
+}
+
+// Body::apply_displacement (multibody.rs:816-824): the joints take their share, the kinematics are redone.  A real
+// call (not inlined): the caller re-reads the poses it wrote from memory.
+__device__ __noinline__ void mb_displace(const MbView& V, const MbMeta& MX, const Proxies& P, const float* disp) {
+    MbLinkDev* L = V.links + MX.first_link;
+    for (uint32_t i = 0; i < MX.n_links; ++i) mbj_apply_displacement(L[i], disp + L[i].assembly);
+    mb_update_kinematics<1>(V, MX, P, 0u);
 }
 
 // NonlinearSORProx::solve restricted to one multibody (nonlinear_sor_prox.rs:17-55): per iteration its internal
 // position constraints (multibody.rs:1112-1152, unit_joint.rs:198-251), then its contacts in manifold order
 // (update_contact_constraint :156-294, solve_unilateral :121-154); every displacement re-runs update_kinematics.
 __global__ void __launch_bounds__(MB_TPB) k_mb_position_solve(MbView V, Proxies P, MbContacts C, MbRows R, PosParams PP, int iters) {
+    // one thread per component (the thread of its smallest member), see k_mb_velocity_solve
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= V.n_mb) return;
-    const MbMeta M = V.meta[m];
-    const uint32_t nd = M.ndofs;
-    MbLinkDev* L = V.links + M.first_link;
-    const uint32_t* list = C.mlist + (size_t)m * NB2_MB_MANIFOLD_CAP;
-    const uint32_t nm = min(C.mcount[m], (uint32_t)NB2_MB_MANIFOLD_CAP);
-    const uint32_t* seg = R.seg + 4 * m;
-    const uint32_t no0 = R.row_off[m] + seg[0] + seg[1] + seg[2];
+    if (R.comp[m] != m) return;
+    const uint32_t nmem = min(R.coff[m + 1] - R.coff[m], (uint32_t)NB2_MB_COMP_MEMBERS);
+    uint32_t mem[NB2_MB_COMP_MEMBERS];
+    unsigned char ptr[NB2_MB_COMP_MEMBERS];
+    unsigned short kc[NB2_MB_COMP_MEMBERS];
+    for (uint32_t k = 0; k < nmem; ++k) mem[k] = R.cmem[R.coff[m] + k];
+    for (uint32_t a = 1; a < nmem; ++a) {
+        const uint32_t v = mem[a];
+        uint32_t b = a;
+        while (b > 0 && mem[b - 1] > v) {
+            mem[b] = mem[b - 1];
+            --b;
+        }
+        mem[b] = v;
+    }
     float J[NB2_MB_MAX_DOFS], WJ[NB2_MB_MAX_DOFS], tmp[NB2_MB_MAX_DOFS];
-    auto displace = [&](const float* disp) {
-        for (uint32_t i = 0; i < M.n_links; ++i) mbj_apply_displacement(L[i], disp + L[i].assembly);
-        mb_update_kinematics<1>(V, M, P, 0u);
-    };
+    auto displace = [&](const MbMeta& MX, const float* disp) { mb_displace(V, MX, P, disp); };
     for (int it = 0; it < iters; ++it) {
-        if (M.has_internal) {
+        // step_solve_internal_position_constraints of every member with unit-joint constraints (nonlinear_sor_prox.rs:40-44)
+        for (uint32_t k = 0; k < nmem; ++k) {
+            const MbMeta M = V.meta[mem[k]];
+            if (!M.has_internal) continue;
+            const uint32_t nd = M.ndofs;
+            MbLinkDev* L = V.links + M.first_link;
             for (uint32_t i = 0; i < M.n_links; ++i) {
                 const MbLinkDev& l = L[i];
                 if (l.type != NB2_MBJ_REVOLUTE && l.type != NB2_MBJ_PRISMATIC) continue;
@@ -1217,17 +1509,39 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_position_solve(MbView V, Proxies 
                 if (crhs < 0.f) {
                     const float impulse = -crhs * r;
                     for (uint32_t c = 0; c < nd; ++c) WJ[c] *= impulse;
-                    displace(WJ);
+                    displace(M, WJ);
                 }
             }
             mb_update_kinematics<1>(V, M, P, 0u);
         }
-        uint32_t k = 0;
-        for (uint32_t a = 0; a < nm; ++a) {
-            const nb2_manifold& mf = C.manifolds[list[a]];
+        // the component's contacts in manifold order: a merge of the members' (sorted) manifold lists
+        for (uint32_t k = 0; k < nmem; ++k) {
+            ptr[k] = 0;
+            kc[k] = 0;
+        }
+        for (;;) {
+            uint32_t best = 0xFFFFFFFFu, bk = 0;
+            for (uint32_t k = 0; k < nmem; ++k) {
+                const uint32_t x = mem[k];
+                if (R.seg[4 * x + 3] == 0) continue;
+                const uint32_t nm = min(C.mcount[x], (uint32_t)NB2_MB_MANIFOLD_CAP);
+                if (ptr[k] >= nm) continue;
+                const uint32_t mi = C.mlist[(size_t)x * NB2_MB_MANIFOLD_CAP + ptr[k]];
+                if (mi < best) {
+                    best = mi;
+                    bk = k;
+                }
+            }
+            if (best == 0xFFFFFFFFu) break;
+            ++ptr[bk];
+            const uint32_t x = mem[bk];
+            const uint32_t* sg = R.seg + 4 * x;
+            const uint32_t no0 = R.row_off[x] + sg[0] + sg[1] + sg[2];
+            const nb2_manifold& mf = C.manifolds[best];
             const int l1 = C.link_of_body[mf.body1], l2 = C.link_of_body[mf.body2];
             const Pose c1 = load_coll(mf.coll1_wrt_body), c2 = load_coll(mf.coll2_wrt_body);
-            for (uint32_t ci = mf.first_contact; ci < mf.first_contact + mf.num_contacts && ci < C.n_contacts; ++ci, ++k) {
+            for (uint32_t ci = mf.first_contact; ci < mf.first_contact + mf.num_contacts && ci < C.n_contacts; ++ci) {
+                const uint32_t k = kc[bk]++;
                 const nb2_contact& c = C.contacts[ci];
                 Pose b1, b2;
                 b1.t = f4_xyz(P.pos_t[mf.body1]);
@@ -1245,26 +1559,31 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_position_solve(MbView V, Proxies 
                 const float rhs = clamp_rhs(-cev.depth, false, PP);
                 if (rhs >= 0.f) continue;
                 // the reference displaces body 1 and then body 2 with jacobians taken BEFORE either moved
-                // (nonlinear_sor_prox.rs:131-152); both are this multibody when both are links
+                // (nonlinear_sor_prox.rs:131-152); they may be two links of one multibody or of two
                 float inv_r = 0.f;
-                if (l1 >= 0) {
-                    mb_fill_geometry(V, M, (uint32_t)l1 - M.first_link, cev.world1, false, -cev.normal, tmp, J, WJ, false);
-                    inv_r += mb_dot((int)nd, J, WJ);
-                }
                 float J2[NB2_MB_MAX_DOFS], WJ2[NB2_MB_MAX_DOFS];
-                if (l2 >= 0) {
-                    mb_fill_geometry(V, M, (uint32_t)l2 - M.first_link, cev.world2, false, cev.normal, tmp, J2, WJ2, false);
-                    inv_r += mb_dot((int)nd, J2, WJ2);
+                const int xa = l1 >= 0 ? C.mb_of_link[l1] : -1, xb = l2 >= 0 ? C.mb_of_link[l2] : -1;
+                if (xa >= 0) {
+                    const MbMeta M1 = V.meta[xa];
+                    mb_fill_geometry(V, M1, (uint32_t)l1 - M1.first_link, cev.world1, false, -cev.normal, tmp, J, WJ, false);
+                    inv_r += mb_dot((int)M1.ndofs, J, WJ);
+                }
+                if (xb >= 0) {
+                    const MbMeta M2 = V.meta[xb];
+                    mb_fill_geometry(V, M2, (uint32_t)l2 - M2.first_link, cev.world2, false, cev.normal, tmp, J2, WJ2, false);
+                    inv_r += mb_dot((int)M2.ndofs, J2, WJ2);
                 }
                 if (inv_r == 0.f) continue;
                 const float impulse = -rhs * (1.f / inv_r);
-                if (l1 >= 0) {
-                    for (uint32_t cc = 0; cc < nd; ++cc) WJ[cc] *= impulse;
-                    displace(WJ);
+                if (xa >= 0) {
+                    const MbMeta M1 = V.meta[xa];
+                    for (uint32_t cc = 0; cc < M1.ndofs; ++cc) WJ[cc] *= impulse;
+                    displace(M1, WJ);
                 }
-                if (l2 >= 0) {
-                    for (uint32_t cc = 0; cc < nd; ++cc) WJ2[cc] *= impulse;
-                    displace(WJ2);
+                if (xb >= 0) {
+                    const MbMeta M2 = V.meta[xb];
+                    for (uint32_t cc = 0; cc < M2.ndofs; ++cc) WJ2[cc] *= impulse;
+                    displace(M2, WJ2);
                 }
             }
         }
@@ -1319,6 +1638,8 @@ struct MbState {
     DevBuf<int> mb_of_link, link_of_body, piv;
     DevBuf<float> vel, damp, acc, ext, lam, jac, cor, icd, mass, accw;
     DevBuf<uint32_t> mcount, mlist, row_cnt, row_off, seg;
+    DevBuf<uint32_t> edges, ecount, comp, ccount, coff, ccursor, cmem, lslot;  // components; ecount: [0] edges, [1] the corder allocator
+    DevBuf<uint2> corder, morder;
     DevBuf<MbRow> rows;
     DevBuf<float> jw;
     DevBuf<float4> cpos;
@@ -1366,6 +1687,8 @@ void mb_release(Context* ctx) {
     S->vel.release(); S->damp.release(); S->acc.release(); S->ext.release(); S->lam.release(); S->jac.release(); S->cor.release();
     S->icd.release(); S->mass.release(); S->accw.release(); S->mcount.release(); S->mlist.release(); S->row_cnt.release(); S->row_off.release();
     S->seg.release(); S->rows.release(); S->jw.release(); S->cpos.release();
+    S->edges.release(); S->ecount.release(); S->comp.release(); S->ccount.release(); S->coff.release(); S->ccursor.release();
+    S->cmem.release(); S->lslot.release(); S->corder.release(); S->morder.release();
     delete S;
     ctx->mb = nullptr;
 }
@@ -1492,6 +1815,13 @@ int mb_upload(Context* ctx, const nb2_multibody* mbs, uint32_t n_mb, const nb2_m
     NB2_TRY(S->row_cnt.reserve(ctx, n_mb + 1));
     NB2_TRY(S->row_off.reserve(ctx, n_mb + 2));
     NB2_TRY(S->seg.reserve(ctx, (size_t)4 * n_mb));
+    NB2_TRY(S->ecount.reserve(ctx, 4));
+    NB2_TRY(S->comp.reserve(ctx, n_mb));
+    NB2_TRY(S->ccount.reserve(ctx, n_mb + 1));
+    NB2_TRY(S->coff.reserve(ctx, n_mb + 2));
+    NB2_TRY(S->ccursor.reserve(ctx, n_mb));
+    NB2_TRY(S->cmem.reserve(ctx, n_mb));
+    NB2_TRY(S->lslot.reserve(ctx, n_mb));
     S->link_bodies = ctx->n_bodies;
     NB2_CUDA(ctx, cudaMemcpyAsync(S->meta.p, meta.data(), n_mb * sizeof(MbMeta), cudaMemcpyHostToDevice, ctx->stream));
     NB2_CUDA(ctx, cudaMemcpyAsync(S->links.p, dev.data(), n_links * sizeof(MbLinkDev), cudaMemcpyHostToDevice, ctx->stream));
@@ -1567,6 +1897,7 @@ static MbContacts mb_contacts(Context* ctx, MbState* S) {
     C.n_manifolds = ctx->n_manifolds;
     C.n_contacts = ctx->n_contacts;
     C.link_of_body = S->link_of_body.p;
+    C.mb_of_link = S->mb_of_link.p;
     C.status = ctx->b_status.p;
     C.pos_t = ctx->pos_t.p;
     C.pos_q = ctx->pos_q.p;
@@ -1574,6 +1905,8 @@ static MbContacts mb_contacts(Context* ctx, MbState* S) {
     C.com_im = ctx->com_im.p;
     C.mcount = S->mcount.p;
     C.mlist = S->mlist.p;
+    C.edges = S->edges.p;
+    C.n_edges = S->ecount.p;
     C.flags = ctx->flags.p;
     return C;
 }
@@ -1587,6 +1920,14 @@ static MbRows mb_rows(MbState* S) {
     R.seg = S->seg.p;
     R.nd_stride = S->nd_max;
     R.row_cap = S->row_cap;
+    R.comp = S->comp.p;
+    R.coff = S->coff.p;
+    R.cmem_c = S->cmem.p;
+    R.cmem = S->cmem.p;
+    R.lslot = S->lslot.p;
+    R.corder = S->corder.p;
+    R.morder = S->morder.p;
+    R.cursor = S->ecount.p + 1;
     return R;
 }
 
@@ -1601,16 +1942,26 @@ int mb_launch_velocity(Context* ctx) {
     const size_t cap = (size_t)3 * ctx->n_contacts + (size_t)3 * S->n_links + 4;
     if (cap > 0x7FFFFFFFull) return set_error(ctx, NB2_ERR_UNSUPPORTED, "too many multibody rows");
     NB2_TRY(S->rows.reserve(ctx, cap));
-    NB2_TRY(S->jw.reserve(ctx, cap * 2 * S->nd_max));
+    NB2_TRY(S->jw.reserve(ctx, cap * 4 * S->nd_max));
     NB2_TRY(S->cpos.reserve(ctx, cap));
+    NB2_TRY(S->corder.reserve(ctx, cap / 3 + 4));
+    NB2_TRY(S->morder.reserve(ctx, cap / 3 + 4));
+    NB2_TRY(S->edges.reserve(ctx, (size_t)2 * ctx->n_manifolds + 2));
     S->row_cap = (uint32_t)cap;
     MbView V = mb_view(S);
     MbContacts C = mb_contacts(ctx, S);
     NB2_CUDA(ctx, cudaMemsetAsync(S->mcount.p, 0, n_mb * sizeof(uint32_t), ctx->stream));
+    NB2_CUDA(ctx, cudaMemsetAsync(S->ecount.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+    NB2_CUDA(ctx, cudaMemsetAsync(S->ccursor.p, 0, n_mb * sizeof(uint32_t), ctx->stream));
     if (ctx->n_manifolds)
         k_mb_collect<<<(ctx->n_manifolds + 127) / 128, 128, 0, ctx->stream>>>(C, S->mb_of_link.p);
+    // components of the multibodies that share manifolds, their member lists
+    k_mb_components<<<1, 256, 0, ctx->stream>>>(n_mb, S->edges.p, S->ecount.p, S->comp.p, S->ccount.p);
+    NB2_TRY(exclusive_scan_u32(ctx, S->ccount.p, S->coff.p, n_mb + 1));
+    k_mb_members<<<mb_blocks(n_mb), MB_TPB, 0, ctx->stream>>>(n_mb, S->comp.p, S->coff.p, S->ccursor.p, S->cmem.p);
     k_mb_row_counts<<<mb_blocks(n_mb), MB_TPB, 0, ctx->stream>>>(V, C, S->row_cnt.p);
     NB2_TRY(exclusive_scan_u32(ctx, S->row_cnt.p, S->row_off.p, n_mb + 1));
+    ctx->launches += 2;
     MbRows R = mb_rows(S);
     MbCache K;
     const int cur = ctx->cur, prev = 1 - cur;
@@ -1633,7 +1984,7 @@ int mb_launch_velocity(Context* ctx) {
             V, C, R, K, S->mb_of_link.p, ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt,
             stage ? words : 0u, S->jac_words);
     }
-    k_mb_velocity_solve<<<(n_mb + MB_WPB - 1) / MB_WPB, 32 * MB_WPB, 0, ctx->stream>>>(V, R, K, ctx->contacts.p,
+    k_mb_velocity_solve<<<(n_mb + MB_WPB - 1) / MB_WPB, 32 * MB_WPB, 0, ctx->stream>>>(V, R, K, C, ctx->contacts.p,
                                                                                      (int)ctx->params.max_velocity_iterations, ctx->params.dt);
     ctx->launches += 4;
     NB2_CUDA(ctx, cudaGetLastError());

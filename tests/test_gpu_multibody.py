@@ -122,6 +122,81 @@ def test_ragdolls_landing_on_the_ground_match_the_oracle():
     o.close()
 
 
+def _run_with_contacts(sc, steps, tol, min_contacts, mode=abi.MODE_COLOURED, tangential=True):
+    s, o = _pair(sc)
+    gen = scenes.ContactGenerator(sc)
+    seen = 0
+    for k in range(steps):
+        m, c = gen.generate(o.download_body_states()["position"])
+        seen = max(seen, len(c))
+        for x in (s, o):
+            x.upload_manifolds(m, c)
+        s.step(mode)
+        o.step()
+        _compare(s, o, "step %d (%d contacts)" % (k, len(c)), tol=tol)
+        if len(c):
+            gi, oi = s.download_contact_impulses(), o.download_contact_impulses()
+            assert _rel(gi[:, 0], oi[:, 0]) <= tol
+            if tangential:
+                assert _rel(gi, oi) <= tol
+    s.synchronize()
+    assert seen >= min_contacts, seen
+    s.close()
+    o.close()
+
+
+def test_two_multibodies_stacked_on_the_ground_match_the_oracle():
+    """Rows between two different multibodies (both sides Multibody::fill_constraint_geometry; the reference's two-sided
+    `unilateral` / `bilateral` classes, solved before the ground classes): a FreeJoint box on a FreeJoint box on the
+    ground, plus a third one beside them that only touches the ground.  The two stacked ones are one component."""
+    mb = scenes._ground_only((4.0, 0.2, 4.0))
+    mb.add(-1, abi.MBJ_FREE, (0.2, 0.1, 0.2), 1.0, coords=[0.0, 0.11, 0.0, 0, 0, 0, 1])
+    mb.finish()
+    mb.add(-1, abi.MBJ_FREE, (0.1, 0.1, 0.1), 2.0, coords=[0.05, 0.33, -0.03, 0, 0, 0, 1], velocity=[0.2, 0, 0, 0, 0, 0])
+    mb.finish()
+    mb.add(-1, abi.MBJ_FREE, (0.1, 0.1, 0.1), 1.0, coords=[1.0, 0.11, 0.0, 0, 0, 0, 1])
+    mb.finish()
+    _run_with_contacts(mb.scene("mb_stack"), 40, 2e-5, 12)
+
+
+def test_a_multibody_resting_on_its_own_link_matches_the_oracle():
+    """Rows between two links of ONE multibody (helper.rs:118-125, the cross terms of `inv_r`): a slider on a vertical
+    PrismaticJoint comes down on the FreeJoint box that carries it, which stands on the ground.  The tangential rows
+    of that contact are (nearly) redundant with the joint -- J1 + J2 cancels to rounding, r = 1 / (J M^-1 J) is huge -- so
+    their impulses are whatever rounding makes them, in both arms, with no effect on the motion: coordinates, velocities
+    and normal impulses are compared, the tangential impulses of this scene are not."""
+    mb = scenes._ground_only((4.0, 0.2, 4.0))
+    root = mb.add(-1, abi.MBJ_FREE, (0.3, 0.1, 0.3), 1.0, coords=[0.0, 0.11, 0.0, 0, 0, 0, 1])
+    mb.add(root, abi.MBJ_PRISMATIC, (0.1, 0.1, 0.1), 1.0, parent_shift=(0.0, 0.22, 0.0), axis=(0, 1, 0))
+    mb.finish()
+    _run_with_contacts(mb.scene("mb_self_contact"), 40, 2e-5, 8, tangential=False)
+
+
+def test_a_chain_lying_under_a_free_box_matches_the_oracle():
+    """A two-link multibody (FreeJoint + BallJoint boxes side by side on the ground) with a single-link multibody on
+    top of its second link: contact rows over 9 and 6 generalized coordinates in one component."""
+    mb = scenes._ground_only((4.0, 0.2, 4.0))
+    root = mb.add(-1, abi.MBJ_FREE, (0.2, 0.1, 0.2), 1.0, coords=[0.0, 0.11, 0.0, 0, 0, 0, 1])
+    mb.add(root, abi.MBJ_BALL, (0.2, 0.1, 0.2), 1.0, parent_shift=(0.25, 0.0, 0.0), body_shift=(-0.25, 0.0, 0.0))
+    mb.finish()
+    mb.add(-1, abi.MBJ_FREE, (0.1, 0.1, 0.1), 1.0, coords=[0.5, 0.33, 0.0, 0, 0, 0, 1])
+    mb.finish()
+    _run_with_contacts(mb.scene("mb_chain_under_box"), 40, 2e-5, 12)
+
+
+def test_a_tower_of_multibodies_is_one_component():
+    """Five FreeJoint boxes on top of one another (one component, 30 generalized coordinates, rows between consecutive
+    members) next to a revolute pendulum with stops that shares nothing with them."""
+    mb = scenes._ground_only((4.0, 0.2, 4.0))
+    for k in range(5):
+        mb.add(-1, abi.MBJ_FREE, (0.2 - 0.02 * k, 0.1, 0.2 - 0.02 * k), 1.0, coords=[0.01 * k, 0.11 + 0.22 * k, 0.0, 0, 0, 0, 1])
+        mb.finish()
+    mb.add(-1, abi.MBJ_REVOLUTE, (0.1, 0.1, 0.1), 1.0, parent_shift=(2, 3, 0), body_shift=(0, 0, 0.8), axis=(1, 0, 0),
+           flags=abi.MBJ_FLAG_MIN | abi.MBJ_FLAG_MAX, min_pos=-0.3, max_pos=0.2, collider=False)
+    mb.finish()
+    _run_with_contacts(mb.scene("mb_tower"), 60, 5e-5, 20)
+
+
 def test_a_multibody_touching_a_dynamic_body_is_reported():
     mb = scenes._ground_only()
     mb.add(-1, abi.MBJ_FREE, (0.1, 0.1, 0.1), 1.0, coords=[0.0, 0.11, 0.0, 0, 0, 0, 1])
