@@ -9,6 +9,8 @@
 //   Ground                     src/object/ground.rs:15-40
 //   DefaultBodySet             src/object/body_set.rs:61-175
 //   *Constraint (joints)       src/joint/*_constraint.rs
+//   FreeJoint / BallJoint / RevoluteJoint / PrismaticJoint / FixedJoint, MultibodyDesc, Multibody
+//                              src/joint/*_joint.rs, src/object/multibody.rs:1311-1470
 //   ColliderContactManifold    src/detection/collider_contact_manifold.rs:9-115
 //   ContactModel / SignoriniCoulombPyramidModel   src/solver/contact_model.rs:13-37,
 //                              src/solver/signorini_coulomb_pyramid_model.rs:19-54
@@ -101,7 +103,7 @@ class IntegrationParameters {
 };
 
 // ---------------------------------------------------------------------------------------------
-enum class BodyStatus : uint32_t { Disabled = 0, Static = 1, Dynamic = 2, Kinematic = 3 };  // body.rs:50-59
+enum class BodyStatus : uint32_t { Disabled = 0, Static = 1, Dynamic = 2, Kinematic = 3, MultibodyLink = 4 };  // body.rs:50-59 (+ the link proxy)
 
 using DefaultBodyHandle = size_t;
 struct BodyPartHandle {
@@ -217,13 +219,171 @@ struct Ground {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Reduced-coordinate joints (src/joint/*_joint.rs): what a MultibodyDesc link hangs on.
+struct Joint {
+    nb2_mb_link rec;
+    explicit Joint(uint32_t type) {
+        std::memset(&rec, 0, sizeof(rec));
+        rec.joint_type = type;
+        rec.parent = -1;
+        rec.body = -1;
+        rec.axis[0] = 1.f;
+        rec.motor_max_velocity = FLT_MAX;  // JointMotor::new (joint_motor.rs:17-24)
+        rec.motor_max_force = FLT_MAX;
+    }
+};
+struct FreeJoint : Joint {  // free_joint.rs:16-20
+    explicit FreeJoint(const Isometry3& position) : Joint(NB2_MBJ_FREE) {
+        for (int k = 0; k < 3; ++k) rec.coords[k] = position.translation[k];
+        for (int k = 0; k < 4; ++k) rec.coords[3 + k] = position.rotation[k];
+    }
+};
+struct BallJoint : Joint {  // ball_joint.rs:22-29 (identity rotation; default_damping 0.1, :89-91)
+    BallJoint() : Joint(NB2_MBJ_BALL) {
+        rec.coords[3] = 1.f;
+        for (int k = 0; k < 3; ++k) rec.damping[k] = 0.1f;
+    }
+};
+struct UnitJointBase : Joint {  // unit_joint.rs: limits and motor of a one-dof joint
+    explicit UnitJointBase(uint32_t type) : Joint(type) {}
+    void enable_min(float v) { rec.flags |= NB2_MBJ_FLAG_MIN; rec.min_pos = v; }
+    void enable_max(float v) { rec.flags |= NB2_MBJ_FLAG_MAX; rec.max_pos = v; }
+    void enable_motor() { rec.flags |= NB2_MBJ_FLAG_MOTOR; }
+    void set_desired_motor_velocity(float v) { rec.motor_velocity = v; }
+    void set_max_motor_force(float f) { rec.motor_max_force = f; }
+};
+struct RevoluteJoint : UnitJointBase {  // revolute_joint.rs:47-60 (default_damping 0.1, :214-216)
+    RevoluteJoint(const Vector3& axis, float angle) : UnitJointBase(NB2_MBJ_REVOLUTE) {
+        for (int k = 0; k < 3; ++k) rec.axis[k] = axis[k];
+        rec.coords[0] = angle;
+        rec.damping[0] = 0.1f;
+    }
+    void enable_min_angle(float v) { enable_min(v); }
+    void enable_max_angle(float v) { enable_max(v); }
+    void enable_angular_motor() { enable_motor(); }
+    void set_desired_angular_motor_velocity(float v) { set_desired_motor_velocity(v); }
+    void set_max_angular_motor_torque(float t) { set_max_motor_force(t); }
+};
+struct PrismaticJoint : UnitJointBase {  // prismatic_joint.rs:36-46
+    PrismaticJoint(const Vector3& axis, float offset) : UnitJointBase(NB2_MBJ_PRISMATIC) {
+        for (int k = 0; k < 3; ++k) rec.axis[k] = axis[k];
+        rec.coords[0] = offset;
+    }
+    void enable_min_offset(float v) { enable_min(v); }
+    void enable_max_offset(float v) { enable_max(v); }
+    void enable_linear_motor() { enable_motor(); }
+    void set_desired_linear_motor_velocity(float v) { set_desired_motor_velocity(v); }
+    void set_max_linear_motor_force(float f) { set_max_motor_force(f); }
+};
+struct FixedJoint : Joint {  // fixed_joint.rs:14-19: the argument is the joint's pose in the body's frame; identity here
+    FixedJoint() : Joint(NB2_MBJ_FIXED) { rec.coords[6] = 1.f; }
+};
+
+// MultibodyDesc (multibody.rs:1311-1470): a tree of links, each with its joint, shifts and mass properties.
+class MultibodyDesc {
+    Joint joint_;
+    Vector3 parent_shift_{0.f, 0.f, 0.f}, body_shift_{0.f, 0.f, 0.f}, local_com_{0.f, 0.f, 0.f};
+    float mass_ = 0.f;
+    std::array<float, 9> inertia_{};
+    std::vector<MultibodyDesc> children_;
+    friend class Multibody;
+
+  public:
+    explicit MultibodyDesc(const Joint& joint) : joint_(joint) {}
+    MultibodyDesc& add_child(const Joint& joint) {
+        children_.emplace_back(joint);
+        return children_.back();
+    }
+    MultibodyDesc& set_joint(const Joint& j) { joint_ = j; return *this; }
+    MultibodyDesc& set_parent_shift(const Vector3& v) { parent_shift_ = v; return *this; }
+    MultibodyDesc& set_body_shift(const Vector3& v) { body_shift_ = v; return *this; }
+    /// what the colliders contribute in the reference (Body::add_local_inertia_and_com, multibody.rs:1154-1172)
+    MultibodyDesc& local_mass_properties(float mass, const Vector3& local_com, const std::array<float, 9>& inertia_row_major) {
+        mass_ = mass;
+        local_com_ = local_com;
+        inertia_ = inertia_row_major;
+        return *this;
+    }
+    /// mass properties of a cuboid collider (volumetric_cuboid.rs:47-77)
+    MultibodyDesc& cuboid(const Vector3& half_extents, float density) {
+        const float hx = half_extents[0], hy = half_extents[1], hz = half_extents[2];
+        mass_ = density * 8.f * hx * hy * hz;
+        inertia_ = {};
+        inertia_[0] = mass_ * (4.f * hy * hy + 4.f * hz * hz) / 12.f;
+        inertia_[4] = mass_ * (4.f * hx * hx + 4.f * hz * hz) / 12.f;
+        inertia_[8] = mass_ * (4.f * hx * hx + 4.f * hy * hy) / 12.f;
+        return *this;
+    }
+};
+
+// A built Multibody: its links in MultibodyDesc::build order (a parent before its children).
+class Multibody {
+    std::vector<nb2_mb_link> links_;
+    std::vector<nb2_body> parts_;  // the NB2_BODY_MULTIBODY_LINK record of every link
+    bool gravity_enabled_ = true;
+    friend class DefaultBodySet;
+    friend class MoreauJeanSolver;
+    void add(const MultibodyDesc& d, int parent) {
+        nb2_mb_link l = d.joint_.rec;
+        l.parent = parent;
+        for (int k = 0; k < 3; ++k) { l.parent_shift[k] = d.parent_shift_[k]; l.body_shift[k] = d.body_shift_[k]; }
+        nb2_body b;
+        std::memset(&b, 0, sizeof(b));
+        b.position[6] = 1.f;
+        b.status = NB2_BODY_MULTIBODY_LINK;
+        b.mass = d.mass_;
+        for (int k = 0; k < 3; ++k) b.local_com[k] = d.local_com_[k];
+        for (int k = 0; k < 9; ++k) b.local_inertia[k] = d.inertia_[k];
+        for (int k = 0; k < 6; ++k) b.jacobian_mask[k] = 1.f;
+        b.max_linear_velocity = b.max_angular_velocity = FLT_MAX;
+        const int me = (int)links_.size();
+        links_.push_back(l);
+        parts_.push_back(b);
+        for (const MultibodyDesc& c : d.children_) add(c, me);
+    }
+
+  public:
+    explicit Multibody(const MultibodyDesc& desc) { add(desc, -1); }
+    size_t num_links() const { return links_.size(); }
+    const nb2_mb_link& link(size_t i) const { return links_[i]; }
+    /// the link's pose in the world (MultibodyLink::position), as of the last step
+    Isometry3 link_position(size_t i) const {
+        Isometry3 p;
+        for (int k = 0; k < 3; ++k) p.translation[k] = parts_[i].position[k];
+        for (int k = 0; k < 4; ++k) p.rotation[k] = parts_[i].position[3 + k];
+        return p;
+    }
+    void enable_gravity(bool e) { gravity_enabled_ = e; }
+};
+
 // body_set.rs:61-175 (arena -> dense vector; the handle is the index)
 class DefaultBodySet {
     std::vector<RigidBody> bodies_;
+    std::vector<Multibody> multibodies_;
+    std::vector<size_t> mb_first_body_;  // body index of link 0 of every multibody (BodyPartHandle(handle, i) = that + i)
     bool dirty_ = true;
     friend class MoreauJeanSolver;
 
   public:
+    /// A Multibody takes one body slot per link; the returned handle is that of link 0 and
+    /// BodyPartHandle{handle + i, 0} names link i for colliders and manifolds.
+    DefaultBodyHandle insert_multibody(const Multibody& mb) {
+        const size_t first = bodies_.size();
+        for (size_t i = 0; i < mb.num_links(); ++i) {
+            RigidBody proxy;
+            proxy.rec_ = mb.parts_[i];
+            proxy.act_.threshold = -1.f;  // multibodies never sleep
+            bodies_.push_back(proxy);
+        }
+        multibodies_.push_back(mb);
+        mb_first_body_.push_back(first);
+        dirty_ = true;
+        return first;
+    }
+    size_t num_multibodies() const { return multibodies_.size(); }
+    const Multibody& multibody(size_t i) const { return multibodies_[i]; }
+
     DefaultBodyHandle insert(const RigidBody& b) {
         bodies_.push_back(b);
         dirty_ = true;
@@ -391,6 +551,8 @@ class MoreauJeanSolver {
     std::vector<nb2_manifold> manifold_stage_;
     std::vector<nb2_contact> contact_stage_;
     std::vector<nb2_joint> joint_stage_;
+    std::vector<nb2_multibody> mb_stage_;
+    std::vector<nb2_mb_link> link_stage_;
 
     void check(int rc) const {
         if (rc != NB2_OK) throw SolverError(rc, nb2_last_error(ctx_) ? nb2_last_error(ctx_) : nb2_error_string(rc));
@@ -436,6 +598,24 @@ class MoreauJeanSolver {
                 for (size_t i = 0; i < act_stage_.size(); ++i) act_stage_[i] = bodies.bodies_[i].act_;
                 check(nb2_upload_activation(ctx_, act_stage_.data(), (uint32_t)act_stage_.size()));
             }
+            mb_stage_.clear();
+            link_stage_.clear();
+            for (size_t m = 0; m < bodies.multibodies_.size(); ++m) {
+                const Multibody& mb = bodies.multibodies_[m];
+                nb2_multibody rec;
+                rec.first_link = (uint32_t)link_stage_.size();
+                rec.n_links = (uint32_t)mb.links_.size();
+                rec.flags = mb.gravity_enabled_ ? NB2_BODY_FLAG_GRAVITY : 0u;
+                rec.reserved = 0;
+                mb_stage_.push_back(rec);
+                for (size_t i = 0; i < mb.links_.size(); ++i) {
+                    nb2_mb_link l = mb.links_[i];
+                    l.multibody = (int32_t)m;
+                    l.body = (int32_t)(bodies.mb_first_body_[m] + i);
+                    link_stage_.push_back(l);
+                }
+            }
+            check(nb2_upload_multibodies(ctx_, mb_stage_.data(), (uint32_t)mb_stage_.size(), link_stage_.data(), (uint32_t)link_stage_.size()));
             bodies.dirty_ = false;
             joints.dirty_ = true;  // a new body set drops the joints on device
         }
@@ -472,6 +652,17 @@ class MoreauJeanSolver {
         for (size_t i = 0; i < state_stage_.size(); ++i) {
             std::memcpy(bodies.bodies_[i].rec_.position, state_stage_[i].position, sizeof(float) * 7);
             std::memcpy(bodies.bodies_[i].rec_.velocity, state_stage_[i].velocity, sizeof(float) * 6);
+        }
+        if (!link_stage_.empty()) {  // joint coordinates, generalized velocities, cached impulses; link poses came with the body states
+            check(nb2_download_multibody_links(ctx_, link_stage_.data(), (uint32_t)link_stage_.size()));
+            size_t k = 0;
+            for (size_t m = 0; m < bodies.multibodies_.size(); ++m) {
+                Multibody& mb = bodies.multibodies_[m];
+                for (size_t i = 0; i < mb.links_.size(); ++i, ++k) {
+                    mb.links_[i] = link_stage_[k];
+                    mb.parts_[i] = bodies.bodies_[bodies.mb_first_body_[m] + i].rec_;
+                }
+            }
         }
         if (!joint_stage_.empty()) {
             check(nb2_download_joints(ctx_, joint_stage_.data(), (uint32_t)joint_stage_.size()));

@@ -176,6 +176,16 @@ pub struct nb2_joint {
     pub broken: u32,
 }
 
+pub const NB2_BODY_MULTIBODY_LINK: u32 = 4;
+pub const NB2_MBJ_FREE: u32 = 0;
+pub const NB2_MBJ_BALL: u32 = 1;
+pub const NB2_MBJ_REVOLUTE: u32 = 2;
+pub const NB2_MBJ_PRISMATIC: u32 = 3;
+pub const NB2_MBJ_FIXED: u32 = 4;
+pub const NB2_MBJ_FLAG_MIN: u32 = 1;
+pub const NB2_MBJ_FLAG_MAX: u32 = 2;
+pub const NB2_MBJ_FLAG_MOTOR: u32 = 4;
+
 /// One link of a reduced-coordinate multibody (`MultibodyLink` + its `Joint`, src/object/multibody_link.rs).
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]

@@ -18,10 +18,11 @@ use nalgebra as na;
 use ncollide3d::query::ContactKinematic;
 use nphysics3d::counters::Counters;
 use nphysics3d::detection::ColliderContactManifold;
-use nphysics3d::joint::JointConstraintSet;
+use nphysics3d::joint::{BallJoint, FixedJoint, FreeJoint, Joint, JointConstraintSet, JointMotor, PrismaticJoint, RevoluteJoint};
 use nphysics3d::material::{Material, MaterialContext, MaterialsCoefficientsTable};
 use nphysics3d::object::{Body, BodyHandle, BodyPart, BodySet, BodyStatus, BodyUpdateStatus, ColliderAnchor, ColliderHandle,
                          ColliderSet, RigidBody};
+use nphysics3d::object::Multibody;
 use nphysics3d::solver::IntegrationParameters;
 use nphysics_b200_sys as sys;
 use std::collections::HashMap;
@@ -331,6 +332,126 @@ impl<Handle: BodyHandle, CollHandle: ColliderHandle> Drop for B200MoreauJeanSolv
 }
 
 /// ContactId is a slotmap key: its (index, version) pair is a stable 64-bit id.
+// ---------------------------------------------------------------------------------------------------------------
+// Reduced-coordinate multibodies.  A `Multibody` of the body set becomes one `nb2_multibody` and one
+// `nb2_mb_link` per link; every link also takes a `nb2_body` record of status NB2_BODY_MULTIBODY_LINK (the record a
+// `BodyPartHandle(handle, i)` resolves to for colliders and manifolds).  The reference keeps the joint coordinates
+// private to each `Joint` implementation (free_joint.rs:13, ball_joint.rs:14, revolute_joint.rs:24, ...): the accessors
+// used below -- `FreeJoint::position()`, `BallJoint::rotation()`, `FixedJoint::body_to_parent()` and their setters --
+// are the (one-line) additions the integration needs next to the existing `RevoluteJoint::angle()` /
+// `PrismaticJoint::offset()`; the generalized velocities, damping and mass properties are public already
+// (`Multibody::generalized_velocity`, `damping`, `MultibodyLink` + `BodyPart::local_inertia / local_center_of_mass`).
+pub fn marshal_multibody(mb: &Multibody<f32>, mb_index: i32, first_body: i32,
+                         links: &mut Vec<sys::nb2_mb_link>, parts: &mut Vec<sys::nb2_body>) -> sys::nb2_multibody {
+    let first_link = links.len() as u32;
+    let vels = mb.generalized_velocity();
+    let damping = mb.damping();
+    let mut dof = 0usize;
+    for (i, link) in mb.links().enumerate() {
+        let mut l: sys::nb2_mb_link = unsafe { std::mem::zeroed() };
+        l.multibody = mb_index;
+        l.parent = link.parent_id().map(|p| p as i32).unwrap_or(-1);
+        l.body = first_body + i as i32;
+        l.parent_shift = [link.parent_shift().x, link.parent_shift().y, link.parent_shift().z];
+        l.body_shift = [link.body_shift().x, link.body_shift().y, link.body_shift().z];
+        l.axis = [1.0, 0.0, 0.0];
+        l.motor_max_velocity = f32::MAX;
+        l.motor_max_force = f32::MAX;
+        let joint = link.joint();
+        let ndofs = joint.ndofs();
+        let iso = |p: &na::Isometry3<f32>| [p.translation.x, p.translation.y, p.translation.z,
+                                            p.rotation.i, p.rotation.j, p.rotation.k, p.rotation.w];
+        let unit = |l: &mut sys::nb2_mb_link, min: Option<f32>, max: Option<f32>, motor: &JointMotor<f32, f32>| {
+            if let Some(v) = min { l.flags |= sys::NB2_MBJ_FLAG_MIN; l.min_pos = v; }
+            if let Some(v) = max { l.flags |= sys::NB2_MBJ_FLAG_MAX; l.max_pos = v; }
+            if motor.enabled { l.flags |= sys::NB2_MBJ_FLAG_MOTOR; }
+            l.motor_velocity = motor.desired_velocity;
+            l.motor_max_velocity = motor.max_velocity;
+            l.motor_max_force = motor.max_force;
+        };
+        if let Some(j) = joint.downcast_ref::<FreeJoint<f32>>() {
+            l.joint_type = sys::NB2_MBJ_FREE;
+            l.coords = iso(j.position());
+        } else if let Some(j) = joint.downcast_ref::<BallJoint<f32>>() {
+            l.joint_type = sys::NB2_MBJ_BALL;
+            let r = j.rotation();
+            l.coords[..4].copy_from_slice(&[r.i, r.j, r.k, r.w]);
+        } else if let Some(j) = joint.downcast_ref::<RevoluteJoint<f32>>() {
+            l.joint_type = sys::NB2_MBJ_REVOLUTE;
+            l.axis = [j.axis().x, j.axis().y, j.axis().z];
+            l.coords[0] = j.angle();
+            unit(&mut l, j.min_angle(), j.max_angle(), j.motor());
+        } else if let Some(j) = joint.downcast_ref::<PrismaticJoint<f32>>() {
+            l.joint_type = sys::NB2_MBJ_PRISMATIC;
+            l.axis = [j.axis().x, j.axis().y, j.axis().z];
+            l.coords[0] = j.offset();
+            unit(&mut l, j.min_offset(), j.max_offset(), j.motor());
+        } else if let Some(j) = joint.downcast_ref::<FixedJoint<f32>>() {
+            l.joint_type = sys::NB2_MBJ_FIXED;
+            l.coords = iso(j.body_to_parent());
+        } else {
+            panic!("nphysics-b200: this reduced-coordinate joint has no device form (DESIGN.md section 8b)");
+        }
+        for d in 0..ndofs {
+            l.velocity[d] = vels[dof + d];
+            l.damping[d] = damping[dof + d];
+        }
+        if ndofs == 1 {  // cached impulses of the motor / min / max rows (unit_joint.rs:77, 113, 153)
+            let imp = mb.impulses();
+            l.impulses.copy_from_slice(&imp[3 * dof..3 * dof + 3]);
+        }
+        dof += ndofs;
+        links.push(l);
+        // the link as a body record: mass properties in, pose and velocity out
+        let mut b: sys::nb2_body = unsafe { std::mem::zeroed() };
+        b.status = sys::NB2_BODY_MULTIBODY_LINK;
+        b.position[6] = 1.0;
+        b.mass = link.local_inertia().linear;
+        let li = link.local_inertia().angular;
+        b.local_inertia = [li.m11, li.m12, li.m13, li.m21, li.m22, li.m23, li.m31, li.m32, li.m33];
+        let lc = link.local_center_of_mass();
+        b.local_com = [lc.x, lc.y, lc.z];
+        b.jacobian_mask = [1.0; 6];
+        b.max_linear_velocity = f32::MAX;
+        b.max_angular_velocity = f32::MAX;
+        parts.push(b);
+    }
+    sys::nb2_multibody {
+        first_link,
+        n_links: links.len() as u32 - first_link,
+        flags: if mb.gravity_enabled() { sys::NB2_BODY_FLAG_GRAVITY } else { 0 },
+        reserved: 0,
+    }
+}
+
+/// After the step: joint coordinates, generalized velocities and cached impulses back into the Multibody
+/// (`links` = what nb2_download_multibody_links returned for this multibody).
+pub fn unmarshal_multibody(mb: &mut Multibody<f32>, links: &[sys::nb2_mb_link]) {
+    let mut dof = 0usize;
+    for (i, l) in links.iter().enumerate() {
+        let ndofs = {
+            let joint = mb.link_mut(i).unwrap().joint_mut();
+            let q = |c: &[f32]| na::UnitQuaternion::new_unchecked(na::Quaternion::new(c[3], c[0], c[1], c[2]));
+            if let Some(j) = joint.downcast_mut::<FreeJoint<f32>>() {
+                j.set_position(na::Isometry3::from_parts(na::Translation3::new(l.coords[0], l.coords[1], l.coords[2]), q(&l.coords[3..7])));
+            } else if let Some(j) = joint.downcast_mut::<BallJoint<f32>>() {
+                j.set_rotation(q(&l.coords[0..4]));
+            } else if let Some(j) = joint.downcast_mut::<RevoluteJoint<f32>>() {
+                j.set_angle(l.coords[0]);
+            } else if let Some(j) = joint.downcast_mut::<PrismaticJoint<f32>>() {
+                j.set_offset(l.coords[0]);
+            }
+            joint.ndofs()
+        };
+        {
+            let mut v = mb.generalized_velocity_mut();
+            for d in 0..ndofs { v[dof + d] = l.velocity[d]; }
+        }
+        dof += ndofs;
+    }
+    mb.update_kinematics();  // link poses from the new coordinates, as MechanicalWorld::step does at :343-346
+}
+
 fn contact_key(id: &ncollide3d::query::ContactId) -> u64 {
     use slotmap::Key;
     id.data().as_ffi()

@@ -10,18 +10,19 @@ HOST = os.path.join(ROOT, "nphysics_b200", "host")
 EXE = os.path.join(HOST, "example_pyramid3")
 
 
-def build_example():
-    src = os.path.join(HOST, "example_pyramid3.cpp")
+def build_example(name="example_pyramid3"):
+    exe = os.path.join(HOST, name)
+    src = os.path.join(HOST, name + ".cpp")
     hdr = os.path.join(HOST, "nphysics_b200.hpp")
-    if (not os.path.exists(EXE)) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", src, "-o", EXE, "-L" + os.path.join(ROOT, "nphysics_b200"),
+    if (not os.path.exists(exe)) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", src, "-o", exe, "-L" + os.path.join(ROOT, "nphysics_b200"),
                                "-lnphysics_b200", "-Wl,-rpath,$ORIGIN/.."])
-    return EXE
+    return exe
 
 
 def test_host_mirror_compiles_and_links():
-    exe = build_example()
-    assert os.path.exists(exe)
+    for name in ("example_pyramid3", "example_ragdoll3"):
+        assert os.path.exists(build_example(name))
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="only meaningful on a box without a GPU")
@@ -41,3 +42,14 @@ def test_pyramid3_example_runs(mode):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "initial manifolds 1335 contacts 5340 rows 16020" in r.stdout
     assert r.stdout.strip().endswith("OK")
+
+
+@pytest.mark.gpu
+def test_ragdoll3_example_runs():
+    """examples3d/ragdoll3.rs as shipped (one Multibody per ragdoll) through MultibodyDesc / MechanicalWorld::step of the
+    C++ mirror: the program itself checks that no joint anchor drifts."""
+    exe = build_example("example_ragdoll3")
+    r = subprocess.run([exe, "120"], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "27 multibodies (162 links)" in r.stdout
