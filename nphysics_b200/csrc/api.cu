@@ -289,6 +289,7 @@ int nb2_create(int device, void* stream, nb2_context** out) {
     if (const char* vk = getenv("NB2_VELOCITY_KERNEL")) ctx->velocity_kernel = atoi(vk);
     if (const char* pr = getenv("NB2_POISON_ROWS")) ctx->poison_rows = atoi(pr) != 0;
     if (const char* ps = getenv("NB2_POS_EARLY_EXIT")) ctx->pos_early_exit = atoi(ps) != 0;
+    if (const char* rb = getenv("NB2_REF_BLOCKS")) ctx->ref_blocks = atoi(rb);
     if (const char* ic = getenv("NB2_INCREMENTAL_COLOURING")) ctx->incremental_colouring = atoi(ic) != 0;
     if (cudaSetDevice(device) != cudaSuccess) {
         delete h;
@@ -399,6 +400,7 @@ int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
     // joints / manifolds referring to the old set are dropped
     ctx->n_manifolds = ctx->n_contacts = 0;
     ctx->n_joints = 0;
+    mb_invalidate(ctx);  // multibody links name body records of the previous set
     ctx->n_colliders = ctx->n_pairs = 0;
     ctx->pairs_valid = false;
     ctx->stepped = false;

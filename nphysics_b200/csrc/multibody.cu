@@ -1693,6 +1693,11 @@ void mb_release(Context* ctx) {
     ctx->mb = nullptr;
 }
 
+// a new body set drops the multibodies (their links name body records), like the joints
+void mb_invalidate(Context* ctx) {
+    if (mb_state(ctx)) mb_state(ctx)->n_mb = 0;
+}
+
 int mb_count(Context* ctx) { return mb_state(ctx) ? (int)mb_state(ctx)->n_mb : 0; }
 
 struct MbState;

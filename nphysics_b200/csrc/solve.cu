@@ -392,6 +392,7 @@ int launch_velocity_solve(Context* ctx, int mode) {
     size_t want = (ctx->vs.n_items + TPB - 1) / TPB;
     int blocks = (int)(want < (size_t)ctx->coop_blocks_vel ? want : (size_t)ctx->coop_blocks_vel);
     if (blocks < 1) blocks = 1;
+    if (ref && ctx->ref_blocks > 0 && ctx->ref_blocks < blocks) blocks = ctx->ref_blocks;
     // alternating the colour order per sweep (symmetric Gauss-Seidel) was measured: it helps flat
     // piles and hurts tall ones (profiles/r01_notes.md), so the plain order stays the default
     int symmetric = 0;
@@ -445,6 +446,7 @@ int launch_position_solve(Context* ctx, int mode) {
     size_t want = (s.n_items + TPB - 1) / TPB;
     int blocks = (int)(want < (size_t)ctx->coop_blocks_pos ? want : (size_t)ctx->coop_blocks_pos);
     if (blocks < 1) blocks = 1;
+    if (ref && ctx->ref_blocks > 0 && ctx->ref_blocks < blocks) blocks = ctx->ref_blocks;
     // contacts per group: reference order -> the row count itself; coloured rows -> 3 rows per contact;
     // compact -> the count sits in bits 4..7
     int rows_div = ref ? 1 : (ctx->step_layout == 1 ? 16 : (ctx->contact_model == 1 ? 1 : 3));

@@ -297,6 +297,7 @@ struct Context {
     void* host_hdr = nullptr;      // pinned copy of vs.hdr (launch-geometry hint, never waited for)
     DevBuf<unsigned int> bal;       // groups per colour while balancing
     bool pos_early_exit = true;     // NB2_POS_EARLY_EXIT=0: always run every position iteration (the exactness test)
+    int ref_blocks = 0;             // NB2_REF_BLOCKS: cap on the blocks of the reference-order solve kernels (0 = automatic)
     void* mb = nullptr;             // MbState (multibody.cu): reduced-coordinate multibodies, SURVEY 8 f3
 };
 
@@ -399,6 +400,7 @@ int mb_launch_velocity(Context* ctx);
 int mb_launch_position(Context* ctx);
 int mb_count(Context* ctx);
 void mb_release(Context* ctx);
+void mb_invalidate(Context* ctx);
 // schedule.cu
 int exclusive_scan_u32(Context* ctx, const unsigned int* in, unsigned int* out, size_t n);
 int launch_build_items(Context* ctx, int mode);

@@ -122,6 +122,34 @@ def test_ragdolls_landing_on_the_ground_match_the_oracle():
     o.close()
 
 
+def test_composite_joints_as_unit_joints_through_massless_links_match_the_oracle():
+    """The reference's multi-dof joints are unit joints side by side (cylindrical_joint.rs:33-90: a PrismaticJoint and a
+    RevoluteJoint; universal_joint.rs: two RevoluteJoints; ...).  Through this ABI they are written as what they are: a chain
+    of unit joints whose intermediate links carry no mass.  A universal joint (two perpendicular revolutes), a cylindrical
+    one (slide + turn about one axis, with a stop) and a planar one (two slides + a turn) swinging from the world."""
+    mb = scenes._ground_only()
+    a = mb.add(-1, abi.MBJ_REVOLUTE, (0.05, 0.05, 0.05), 0.0, parent_shift=(0, 5, 0), axis=(1, 0, 0), collider=False)
+    mb.add(a, abi.MBJ_REVOLUTE, (0.1, 0.3, 0.1), 1.0, body_shift=(0, 0.5, 0.0), axis=(0, 0, 1), coords=[0.4], velocity=[1.0], collider=False)
+    mb.finish()
+    a = mb.add(-1, abi.MBJ_PRISMATIC, (0.05, 0.05, 0.05), 0.0, parent_shift=(2, 5, 0), axis=(0, 1, 0), collider=False,
+               flags=abi.MBJ_FLAG_MIN, min_pos=-0.4)
+    mb.add(a, abi.MBJ_REVOLUTE, (0.3, 0.1, 0.1), 1.0, body_shift=(0.2, 0, 0.0), axis=(0, 1, 0), velocity=[2.0], collider=False)
+    mb.finish()
+    a = mb.add(-1, abi.MBJ_PRISMATIC, (0.05, 0.05, 0.05), 0.0, parent_shift=(4, 5, 0), axis=(1, 0, 0), velocity=[0.5], collider=False)
+    b = mb.add(a, abi.MBJ_PRISMATIC, (0.05, 0.05, 0.05), 0.0, axis=(0, 1, 0), collider=False)
+    mb.add(b, abi.MBJ_REVOLUTE, (0.3, 0.1, 0.1), 1.0, body_shift=(0.3, 0, 0.0), axis=(0, 0, 1), collider=False)
+    mb.finish()
+    sc = mb.scene("composite_joints")
+    s, o = _pair(sc)
+    for k in range(90):
+        s.step(abi.MODE_COLOURED)
+        o.step()
+        _compare(s, o, "step %d" % k, tol=5e-5)
+    assert s.get_stats()["non_finite"] == 0
+    s.close()
+    o.close()
+
+
 def _run_with_contacts(sc, steps, tol, min_contacts, mode=abi.MODE_COLOURED, tangential=True):
     s, o = _pair(sc)
     gen = scenes.ContactGenerator(sc)
