@@ -99,6 +99,11 @@ __device__ __forceinline__ unsigned long long l2_evict_first_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ unsigned long long l2_evict_normal_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void cp_async16_ef(unsigned int dst, const void* src, unsigned long long pol) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
 }
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_staged(SchedDev sd, S
         if (vn) in_ = __ldg(&sd.g_info[s_gbase[pn.p] + pn.g]);
     }
     int pr = -1;  // -1: the header entry of `pc` comes next
-    const unsigned long long pol = l2_evict_first_policy();
+    const unsigned long long pol = (trace & 0x40000000) ? l2_evict_normal_policy() : l2_evict_first_policy();  // bit 30: A/B of the hint
     unsigned int pslot = 0, pcnt = 0;  // row slot being copied and its stride (groups of the phase)
     auto produce = [&](int e) {
         if (vc) {
@@ -881,7 +886,8 @@ int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd_in, const Rows
     float4* lam = ctx->lam.p;
     int iters = (int)ctx->params.max_velocity_iterations;
     unsigned int* bar = ctx->barrier.p;
-    static const int trace = getenv("NB2_TRACE_PHASES") ? atoi(getenv("NB2_TRACE_PHASES")) : 0;
+    static const int trace = (getenv("NB2_TRACE_PHASES") ? atoi(getenv("NB2_TRACE_PHASES")) : 0) |
+                             (getenv("NB2_NO_EVICT_FIRST") ? 0x40000000 : 0);
     int tr = trace;
     void* args[] = {&sd, &R, &lam, &iters, &bar, &tr};
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
