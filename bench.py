@@ -538,6 +538,30 @@ def run_b200(args, rank, world, local_rank):
         from tools.sharded_worlds import run_sharded_worlds
         sharded = run_sharded_worlds(args.sharded_worlds, rank, world, local_rank, dist, steps=min(args.steps, 10))
 
+    # ragdoll3.rs as shipped -- FreeJoint torso + five BallJoint members per Multibody, feet on the ground
+    # (contacts produced on the device every step); multibodies share nothing, so rank r takes every world-th ragdoll's
+    # worth (strong scaling, no data-path collective: the step time is the max over ranks)
+    multibody = None
+    if not args.no_multibody and args.mode == "coloured":
+        if solver is not None:
+            solver.close()
+            solver = None
+        from tools.run_multibody import run as run_multibody
+        n_local = (args.multibody_ragdolls + world - 1 - rank) // world
+        multibody = run_multibody(n_local, 20, True, 250 if rank == 0 else 0)
+        if dist is not None:
+            t = torch.tensor([multibody["ms_per_step"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cnt = torch.tensor([float(n_local), float(multibody["contacts"])], device=dev, dtype=torch.float64)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            multibody["ragdolls_this_rank"] = n_local
+            multibody["ragdolls"] = int(cnt[0])
+            multibody["links"], multibody["dofs"], multibody["contacts"] = 6 * int(cnt[0]), 21 * int(cnt[0]), int(cnt[1])
+            multibody["ms_per_step"] = float(t[0])
+            multibody["ragdoll_steps_per_s"] = int(cnt[0]) / float(t[0]) * 1e3
+            multibody["n_gpus"] = world
+            multibody["scaling"] = "strong"
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):

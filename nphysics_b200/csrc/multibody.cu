@@ -850,7 +850,7 @@ struct MbCache {
 // and of its unit joints' motors and limits (unit_joint.rs:39-196).
 __global__ void __launch_bounds__(32 * MB_WPB) k_mb_assemble(MbView Vg, MbContacts C, MbRows R, MbCache K, const int* __restrict__ mb_of_link,
                                                              float warmstart_coeff, float restitution_threshold, float inv_dt,
-                                                             uint32_t stage_words, uint32_t jac_words) {
+                                                             uint32_t stage_words, uint32_t jac_words, int model) {
     // One warp per multibody; its lanes take the (contact, row) jobs -- every row is one J = J_link^T f and one
     // LU solve, independent of the others -- with the body jacobians and the LU of the mass matrix staged in the warp's
     // slice of shared memory (read by all lanes at the same address: a broadcast).
@@ -1032,11 +1032,21 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_assemble(MbView Vg, MbContac
                     row.rhs = rhs;
                     row.imp = cached.x * warmstart_coeff;
                     row.kind = NB2_ROW_UNILATERAL;
+                    // SignoriniModel (signorini_model.rs:200-298): a row per ACTIVE contact only (is_constraint_active,
+                    // :141-150); an inactive one keeps its cache entry as it is
+                    if (model == NB2_CONTACT_SIGNORINI && !(depth >= 0.f)) {
+                        row.kind = NB2_ROW_NONE;
+                        row.imp = cached.x;
+                    }
                     R.cpos[no0 + k] = xyz_f4(quat_inv_rotate(q1, normal), 0.f);
                 } else {
                     row.rhs = out_vel;
                     row.imp = (w == 1 ? cached.y : cached.z) * warmstart_coeff;
                     row.kind = NB2_ROW_DEPENDENT;
+                    if (model == NB2_CONTACT_SIGNORINI) {  // frictionless
+                        row.kind = NB2_ROW_NONE;
+                        row.imp = 0.f;
+                    }
                 }
                 R.rows[rowi] = row;
             }
@@ -1126,6 +1136,7 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_assemble(MbView Vg, MbContac
 // rows a multibody will need: 3 per contact + its motors and limits (upper bound for the limits)
 __global__ void k_mb_row_counts(MbView V, MbContacts C, uint32_t* row_cnt) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m == V.n_mb) row_cnt[m] = 0u;  // the scan runs over n_mb + 1 entries
     if (m >= V.n_mb) return;
     const MbMeta M = V.meta[m];
     const uint32_t nm = min(C.mcount[m], (uint32_t)NB2_MB_MANIFOLD_CAP);
@@ -1241,7 +1252,7 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_velocity_solve(MbView V, MbR
         const bool h0 = (int)lane < nd, h1 = (int)lane + 32 < nd;
         float lam0 = 0.f, lam1 = 0.f;
         auto warm1 = [&](uint32_t r) {
-            const float imp = R.rows[r].imp;
+            const float imp = R.rows[r].kind == NB2_ROW_NONE ? 0.f : R.rows[r].imp;
             if (imp != 0.f) {
                 const float* WJ = R.jw + (size_t)r * rs + R.nd_stride;
                 if (h0) lam0 = imp * WJ[lane] + lam0;
@@ -1250,6 +1261,7 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_velocity_solve(MbView V, MbR
         };
         auto solve1 = [&](uint32_t r) {
             const MbRow row = R.rows[r];
+            if (row.kind == NB2_ROW_NONE) return;
             const float* J = R.jw + (size_t)r * rs;
             const float* WJ = J + R.nd_stride;
             const float j0 = h0 ? J[lane] : 0.f, j1 = h1 ? J[lane + 32] : 0.f;
@@ -1325,10 +1337,11 @@ __global__ void __launch_bounds__(32 * MB_WPB) k_mb_velocity_solve(MbView V, MbR
     };
     auto warm = [&](uint32_t r, uint32_t owner) {
         const MbRow row = R.rows[r];
-        if (row.imp != 0.f) sides(r, row, owner, row.imp);
+        if (row.kind != NB2_ROW_NONE && row.imp != 0.f) sides(r, row, owner, row.imp);
     };
     auto solve = [&](uint32_t r, uint32_t owner) {
         const MbRow row = R.rows[r];
+        if (row.kind == NB2_ROW_NONE) return;
         float lo, hi;
         if (row.kind == NB2_ROW_UNILATERAL) {
             lo = 0.f;
@@ -1542,6 +1555,7 @@ __global__ void __launch_bounds__(MB_TPB) k_mb_position_solve(MbView V, Proxies 
             const Pose c1 = load_coll(mf.coll1_wrt_body), c2 = load_coll(mf.coll2_wrt_body);
             for (uint32_t ci = mf.first_contact; ci < mf.first_contact + mf.num_contacts && ci < C.n_contacts; ++ci) {
                 const uint32_t k = kc[bk]++;
+                if (R.rows[no0 + k].kind == NB2_ROW_NONE) continue;  // SignoriniModel: no position constraint for an inactive contact (signorini_model.rs:230-232)
                 const nb2_contact& c = C.contacts[ci];
                 Pose b1, b2;
                 b1.t = f4_xyz(P.pos_t[mf.body1]);
@@ -1964,7 +1978,7 @@ int mb_launch_velocity(Context* ctx) {
     k_mb_components<<<1, 256, 0, ctx->stream>>>(n_mb, S->edges.p, S->ecount.p, S->comp.p, S->ccount.p);
     NB2_TRY(exclusive_scan_u32(ctx, S->ccount.p, S->coff.p, n_mb + 1));
     k_mb_members<<<mb_blocks(n_mb), MB_TPB, 0, ctx->stream>>>(n_mb, S->comp.p, S->coff.p, S->ccursor.p, S->cmem.p);
-    k_mb_row_counts<<<mb_blocks(n_mb), MB_TPB, 0, ctx->stream>>>(V, C, S->row_cnt.p);
+    k_mb_row_counts<<<mb_blocks(n_mb + 1), MB_TPB, 0, ctx->stream>>>(V, C, S->row_cnt.p);
     NB2_TRY(exclusive_scan_u32(ctx, S->row_cnt.p, S->row_off.p, n_mb + 1));
     ctx->launches += 2;
     MbRows R = mb_rows(S);
@@ -1987,7 +2001,7 @@ int mb_launch_velocity(Context* ctx) {
         }
         k_mb_assemble<<<(n_mb + wpb - 1) / wpb, 32 * wpb, stage ? (size_t)wpb * words * 4 : 0, ctx->stream>>>(
             V, C, R, K, S->mb_of_link.p, ctx->params.warmstart_coeff, ctx->params.restitution_velocity_threshold, ctx->inv_dt,
-            stage ? words : 0u, S->jac_words);
+            stage ? words : 0u, S->jac_words, ctx->contact_model);
     }
     k_mb_velocity_solve<<<(n_mb + MB_WPB - 1) / MB_WPB, 32 * MB_WPB, 0, ctx->stream>>>(V, R, K, C, ctx->contacts.p,
                                                                                      (int)ctx->params.max_velocity_iterations, ctx->params.dt);

@@ -225,6 +225,39 @@ def test_a_tower_of_multibodies_is_one_component():
     _run_with_contacts(mb.scene("mb_tower"), 60, 5e-5, 20)
 
 
+def test_multibody_on_a_kinematic_platform_and_the_frictionless_model_match_the_oracle():
+    """A FreeJoint box riding a KINEMATIC platform that moves sideways and up (the platform's velocity enters the rows'
+    right-hand sides, rigid_body.rs:693-698), under the pyramid model and under SignoriniModel (frictionless, rows for
+    active contacts only)."""
+    for model in (abi.CONTACT_SIGNORINI_COULOMB_PYRAMID, abi.CONTACT_SIGNORINI):
+        mb = scenes._ground_only((4.0, 0.2, 4.0))
+        mb.add(-1, abi.MBJ_FREE, (0.1, 0.1, 0.1), 1.0, coords=[0.0, 0.11, 0.0, 0, 0, 0, 1])
+        mb.finish()
+        sc = mb.scene("mb_platform")
+        sc.bodies["status"][0] = abi.BODY_KINEMATIC
+        sc.bodies["velocity"][0, :3] = [0.3, 0.2, 0.0]
+        s, o = _pair(sc)
+        for x in (s, o):
+            x.set_contact_model(model)
+        gen = scenes.ContactGenerator(sc)
+        for k in range(40):
+            m, c = gen.generate(o.download_body_states()["position"])
+            for x in (s, o):
+                x.upload_manifolds(m, c)
+            s.step(abi.MODE_COLOURED)
+            o.step()
+            _compare(s, o, "model %d step %d" % (model, k), tol=2e-5)
+            assert _rel(s.download_contact_impulses()[:, 0], o.download_contact_impulses()[:, 0]) <= 2e-5
+        states = o.download_body_states()
+        assert states["position"][0, 0] > 0.15 and states["position"][1, 1] > 0.2  # the platform carried the box up
+        if model == abi.CONTACT_SIGNORINI_COULOMB_PYRAMID:
+            assert states["position"][1, 0] > 0.1  # friction drags it along; the frictionless model leaves it behind
+        else:
+            assert abs(states["position"][1, 0]) < 1e-3
+        s.close()
+        o.close()
+
+
 def test_a_multibody_touching_a_dynamic_body_is_reported():
     mb = scenes._ground_only()
     mb.add(-1, abi.MBJ_FREE, (0.1, 0.1, 0.1), 1.0, coords=[0.0, 0.11, 0.0, 0, 0, 0, 1])

@@ -16,7 +16,7 @@ from nphysics_b200 import abi, scenes  # noqa: E402
 def _run_gpu(sc, n, steps, contacts, stream):
     import torch
     from nphysics_b200.solver import Solver
-    s = Solver(0, stream=stream.cuda_stream)
+    s = Solver(torch.cuda.current_device(), stream=stream.cuda_stream)
     s.set_params(sc.params)
     s.upload_bodies(sc.bodies)
     s.upload_multibodies(sc.multibodies, sc.mb_links)
