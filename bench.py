@@ -620,11 +620,8 @@ def run_b200(args, rank, world, local_rank):
             line["e2e_variants"] = variants
         if sharded is not None:
             line["sharded"] = sharded
-        if world == 1 and not args.no_multibody and args.mode == "coloured":
-            # ragdoll3.rs as shipped -- FreeJoint torso + five BallJoint members per Multibody, feet on
-            # the ground (contacts produced on the device every step); one warp per multibody
-            from tools.run_multibody import run as run_multibody
-            line["multibody"] = run_multibody(args.multibody_ragdolls, 20, True, 250)
+        if multibody is not None:
+            line["multibody"] = multibody
         if world == 1 and not args.no_quality and args.mode == "coloured":
             line["quality_vs_oracle"] = quality_vs_oracle(args, sc, local_rank)
         if world == 1 and not args.no_cpu_baseline:
