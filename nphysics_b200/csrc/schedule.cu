@@ -315,6 +315,7 @@ static int reserve_sched(Context* ctx, Sched* s, size_t n_items, size_t max_phas
     NB2_TRY(s->it_slot.reserve(ctx, n_items));
     NB2_TRY(s->ph_count.reserve(ctx, max_phases + 1));
     NB2_TRY(s->ph_R.reserve(ctx, max_phases + 1));
+    NB2_TRY(s->ph_bcnt.reserve(ctx, 4 * (max_phases + 1)));
     NB2_TRY(s->ph_gbase.reserve(ctx, max_phases + 1));
     NB2_TRY(s->ph_rbase.reserve(ctx, max_phases + 1));
     NB2_TRY(s->g_info.reserve(ctx, n_items));
@@ -813,9 +814,15 @@ __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict_
 }
 
 // ------------------------------------------------------------------ layout
+#define NB2_ROW_BUCKETS 4
+#define NB2_SMEM_KEYS 1024
+__device__ __forceinline__ unsigned int row_bucket(int nrows) {  // 12+ rows -> 0, 9..11 -> 1, 6..8 -> 2, fewer -> 3
+    const int b = (12 - min(nrows, 12) + 2) / 3;
+    return (unsigned int)min(b, NB2_ROW_BUCKETS - 1);
+}
 __global__ void k_phase_hist(const unsigned int* __restrict__ changed, size_t n, const int* __restrict__ it_type,
-                             const int* __restrict__ it_nrows, const int* __restrict__ phase, int* slot,
-                             unsigned int* ph_count, unsigned int* ph_R, SchedHeader* hdr, unsigned int max_phases) {
+                             const int* __restrict__ it_nrows, const int* __restrict__ phase,
+                             unsigned int* ph_bcnt, unsigned int* ph_R, SchedHeader* hdr, unsigned int max_phases) {
     if (*changed == 0u) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n && it_type[i] != NB2_ITEM_INVALID;
@@ -823,24 +830,50 @@ __global__ void k_phase_hist(const unsigned int* __restrict__ changed, size_t n,
         const unsigned int rows = __reduce_add_sync(0xffffffffu, valid && !NB2_Z_IS_COMPACT(it_nrows[i] | (it_type[i] << 8)) ? (unsigned int)it_nrows[i] : 0u);
         if ((threadIdx.x & 31) == 0 && rows) atomicAdd(&hdr->work, rows);
     }
-    if (!valid) return;
-    unsigned int p = (unsigned int)phase[i];
-    if (p >= max_phases) {
-        p = max_phases - 1;
-        atomicOr(&hdr->overflow, 2u);
+    // slots of a phase are handed out by row-count bucket (k_fill_ginfo), longest groups first: the 32 groups a
+    // warp of the solve kernels owns then hold the same number of rows (up to one bucket edge per warp).
+    // A few dozen (phase, bucket) counters take every item's increment: counted per block in shared memory,
+    // one global atomic per block and counter (a schedule in levels has thousands of phases and goes direct).
+    __shared__ unsigned int s_cnt[NB2_SMEM_KEYS];
+    const unsigned int nkeys = max_phases * NB2_ROW_BUCKETS;
+    const bool blockwise = nkeys <= NB2_SMEM_KEYS;
+    if (blockwise) {
+        for (unsigned int k = threadIdx.x; k < nkeys; k += blockDim.x) s_cnt[k] = 0u;
+        __syncthreads();
     }
-    slot[i] = (int)atomicAdd(&ph_count[p], 1u);
-    // generic row slots: joints and reference-order groups; compact contact groups reserve none
-    atomicMax(&ph_R[p], NB2_Z_IS_COMPACT(it_nrows[i] | (it_type[i] << 8)) ? 0u : (unsigned int)it_nrows[i]);
-    atomicMax(&hdr->n_phases, p + 1);
+    if (valid) {
+        unsigned int p = (unsigned int)phase[i];
+        if (p >= max_phases) {
+            p = max_phases - 1;
+            atomicOr(&hdr->overflow, 2u);
+        }
+        const unsigned int key = p * NB2_ROW_BUCKETS + row_bucket(it_nrows[i]);
+        if (blockwise) atomicAdd(&s_cnt[key], 1u);
+        else atomicAdd(&ph_bcnt[key], 1u);
+        // generic row slots: joints and reference-order groups; compact contact groups reserve none
+        atomicMax(&ph_R[p], NB2_Z_IS_COMPACT(it_nrows[i] | (it_type[i] << 8)) ? 0u : (unsigned int)it_nrows[i]);
+        atomicMax(&hdr->n_phases, p + 1);
+    }
+    if (blockwise) {
+        __syncthreads();
+        for (unsigned int k = threadIdx.x; k < nkeys; k += blockDim.x)
+            if (s_cnt[k]) atomicAdd(&ph_bcnt[k], s_cnt[k]);
+    }
 }
-__global__ void k_phase_scan(const unsigned int* __restrict__ changed, unsigned int* ph_count, unsigned int* ph_R,
-                             unsigned int* ph_gbase, unsigned int* ph_rbase, SchedHeader* hdr) {
+__global__ void k_phase_scan(const unsigned int* __restrict__ changed, unsigned int* ph_count, unsigned int* ph_bcnt,
+                             unsigned int* ph_R, unsigned int* ph_gbase, unsigned int* ph_rbase, SchedHeader* hdr) {
     if (*changed == 0u) return;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned int g = 0, r = 0, mx = 0;
     unsigned int np = hdr->n_phases;
     for (unsigned int p = 0; p < np; ++p) {
+        unsigned int base = 0;  // bucket counts -> bucket cursors (k_fill_ginfo hands the slots out)
+        for (unsigned int b = 0; b < NB2_ROW_BUCKETS; ++b) {
+            const unsigned int c = ph_bcnt[p * NB2_ROW_BUCKETS + b];
+            ph_bcnt[p * NB2_ROW_BUCKETS + b] = base;
+            base += c;
+        }
+        ph_count[p] = base;
         ph_gbase[p] = g;
         ph_rbase[p] = r;
         g += ph_count[p];
@@ -855,16 +888,37 @@ __global__ void k_phase_scan(const unsigned int* __restrict__ changed, unsigned 
 }
 __global__ void k_fill_ginfo(const unsigned int* __restrict__ changed, size_t n, const int* __restrict__ it_type,
                              const int* __restrict__ it_a, const int* __restrict__ it_b,
-                             const int* __restrict__ it_nrows, const int* __restrict__ phase,
-                             const int* __restrict__ slot, const unsigned int* __restrict__ ph_gbase, int4* g_info,
+                             const int* __restrict__ it_nrows, const int* __restrict__ phase, int* slot,
+                             unsigned int* ph_bcnt, const unsigned int* __restrict__ ph_gbase, int4* g_info,
                              unsigned int max_phases) {
     if (*changed == 0u) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || it_type[i] == NB2_ITEM_INVALID) return;
-    unsigned int p = min((unsigned int)phase[i], max_phases - 1);
+    const bool valid = i < n && it_type[i] != NB2_ITEM_INVALID;
+    __shared__ unsigned int s_cnt[NB2_SMEM_KEYS];
+    const unsigned int nkeys = max_phases * NB2_ROW_BUCKETS;
+    const bool blockwise = nkeys <= NB2_SMEM_KEYS;
+    unsigned int p = 0, key = 0, sl = 0;
+    if (valid) {
+        p = min((unsigned int)phase[i], max_phases - 1);
+        key = p * NB2_ROW_BUCKETS + row_bucket(it_nrows[i]);
+    }
+    if (blockwise) {  // rank inside the block, then one reservation per block and counter
+        for (unsigned int k = threadIdx.x; k < nkeys; k += blockDim.x) s_cnt[k] = 0u;
+        __syncthreads();
+        if (valid) sl = atomicAdd(&s_cnt[key], 1u);
+        __syncthreads();
+        for (unsigned int k = threadIdx.x; k < nkeys; k += blockDim.x)
+            if (s_cnt[k]) s_cnt[k] = atomicAdd(&ph_bcnt[k], s_cnt[k]);
+        __syncthreads();
+        if (valid) sl += s_cnt[key];
+    } else if (valid) {
+        sl = atomicAdd(&ph_bcnt[key], 1u);
+    }
+    if (!valid) return;
+    slot[i] = (int)sl;
     // z packs the row count (low 8 bits) and the item type (bits 8..) so the solve kernels need
     // no second lookup
-    g_info[ph_gbase[p] + slot[i]] = make_int4(it_a[i], it_b[i], it_nrows[i] | (it_type[i] << 8), (int)i);
+    g_info[ph_gbase[p] + sl] = make_int4(it_a[i], it_b[i], it_nrows[i] | (it_type[i] << 8), (int)i);
 }
 __global__ void k_copy_phase(size_t n, const int* __restrict__ level, int* phase) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -925,9 +979,10 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     k_cond_zero<<<1, 32, 0, ctx->stream>>>(changed, (unsigned int*)s->hdr.p, offsetof(SchedHeader, refine_left) / 4);
     k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_count.p, s->max_phases + 1);
     k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_R.p, s->max_phases + 1);
-    ctx->launches += 3;
+    k_cond_zero<<<nblk(4 * (s->max_phases + 1)), TPB, 0, ctx->stream>>>(changed, s->ph_bcnt.p, 4 * (s->max_phases + 1));
+    ctx->launches += 4;
     if (n == 0) {
-        k_phase_scan<<<1, 1, 0, ctx->stream>>>(changed, s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
+        k_phase_scan<<<1, 1, 0, ctx->stream>>>(changed, s->ph_count.p, s->ph_bcnt.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
         ctx->launches++;
         NB2_CUDA(ctx, cudaGetLastError());
         return NB2_OK;
@@ -1002,11 +1057,11 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
         NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_colour, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
         ctx->launches++;
     }
-    k_phase_hist<<<nblk(n), TPB, 0, ctx->stream>>>(changed, n, s->it_type.p, s->it_nrows.p, s->it_phase.p, s->it_slot.p,
-                                                   s->ph_count.p, s->ph_R.p, s->hdr.p, (unsigned int)s->max_phases);
-    k_phase_scan<<<1, 1, 0, ctx->stream>>>(changed, s->ph_count.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
+    k_phase_hist<<<nblk(n), TPB, 0, ctx->stream>>>(changed, n, s->it_type.p, s->it_nrows.p, s->it_phase.p,
+                                                   s->ph_bcnt.p, s->ph_R.p, s->hdr.p, (unsigned int)s->max_phases);
+    k_phase_scan<<<1, 1, 0, ctx->stream>>>(changed, s->ph_count.p, s->ph_bcnt.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
     k_fill_ginfo<<<nblk(n), TPB, 0, ctx->stream>>>(changed, n, s->it_type.p, s->it_a.p, s->it_b.p, s->it_nrows.p,
-                                                   s->it_phase.p, s->it_slot.p, s->ph_gbase.p, s->g_info.p,
+                                                   s->it_phase.p, s->it_slot.p, s->ph_bcnt.p, s->ph_gbase.p, s->g_info.p,
                                                    (unsigned int)s->max_phases);
     ctx->launches += 3;
     NB2_CUDA(ctx, cudaGetLastError());

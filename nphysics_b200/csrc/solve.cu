@@ -401,15 +401,11 @@ int launch_velocity_solve(Context* ctx, int mode) {
         int tpb_s, depth_s, blocks_s;
         if (staged_geometry(ctx, &tpb_s, &depth_s, &blocks_s)) {
             if (ctx->velocity_kernel == 3) return launch_velocity_solve_bulk(ctx, sd, R, tpb_s, depth_s, blocks_s);
-            // 2 = automatic: groups of equal row counts (a settled pile: 12 rows everywhere) run the free-running
-            // per-thread rings, 0.81 ms on the 100k pile against 0.87 ms in lockstep; a ragged schedule (last step's
-            // header: scheduled rows < padded slots) runs in warp lockstep, which keeps the row copies coalesced
-            // (4096 x pyramid3 live: 15.3 ms against 16.6 ms).  4 / 5 force lockstep / free-running.
-            bool lockstep = ctx->velocity_kernel == 4;
-            if (ctx->velocity_kernel == 2 && ctx->host_hdr) {
-                const volatile SchedHeader* hh = (const volatile SchedHeader*)ctx->host_hdr;
-                lockstep = hh->n_slots != 0u && hh->work < hh->n_slots;
-            }
+            // 2 = the free-running per-thread rings.  The layout hands the slots of a phase out by row count
+            // (schedule.cu, k_fill_ginfo), so the 32 groups of a warp hold equal row counts and the warp's copies
+            // stay coalesced without walking in lockstep: live 100k pile 0.79 ms (lockstep 0.89 ms, and 1.01 ms
+            // before the slots were sorted), 4096 x pyramid3 21.4 ms (24.0 / 25.6).  4 forces the lockstep stream.
+            const bool lockstep = ctx->velocity_kernel == 4;
             if (lockstep) return launch_velocity_solve_lockstep(ctx, sd, R, tpb_s, depth_s, blocks_s);
             return launch_velocity_solve_staged(ctx, sd, R, tpb_s, depth_s, blocks_s);
         }

@@ -142,6 +142,7 @@ struct Sched {
     DevBuf<int> it_phase, it_slot;   // outputs: phase, index inside the phase
     DevBuf<int> it_phase_raw;        // coloured: the colouring before balancing (what the refinement passes work on)
     DevBuf<unsigned int> ph_count, ph_R, ph_gbase, ph_rbase;
+    DevBuf<unsigned int> ph_bcnt;    // [phase][row-count bucket]: counts, then slot cursors
     DevBuf<int4> g_info;             // per group slot: (a, b, nrows | type << 8, item)
     DevBuf<SchedHeader> hdr;         // 1 element
     // schedule cache: last step's groups, compared on device (coloured mode)
@@ -155,7 +156,7 @@ struct Sched {
         it_key.release(); it_phase.release(); it_slot.release(); ph_count.release(); ph_R.release();
         ph_gbase.release(); ph_rbase.release(); g_info.release(); hdr.release();
         prev_a.release(); prev_b.release(); prev_nt.release(); prev_b1.release(); prev_b2.release();
-        it_b1.release(); it_b2.release(); it_phase_raw.release();
+        it_b1.release(); it_b2.release(); it_phase_raw.release(); ph_bcnt.release();
     }
 };
 
