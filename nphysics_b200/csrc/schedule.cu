@@ -567,6 +567,45 @@ __global__ void k_refine_decide(unsigned int* changed, SchedHeader* hdr, const u
         hdr->refine_left -= 1u;
     }
 }
+// One launch for all the conditional resets of a scheduling pass (seven launches of 2.5 us each before, on
+// every step, cached or not).  kind 0: zero unless the schedule is kept; 1: also kept on an incremental step
+// (the colour masks); 2: fill with -1 unless the colours are carried over (refinement / incremental).
+struct CondRegions {
+    unsigned int* p[8];
+    unsigned long long end[8];  // running end offsets, in words
+    int kind[8];
+    int n;
+};
+static void cond_add(CondRegions& cr, void* p, size_t nwords, int kind) {
+    cr.p[cr.n] = (unsigned int*)p;
+    cr.end[cr.n] = (cr.n ? cr.end[cr.n - 1] : 0ull) + nwords;
+    cr.kind[cr.n] = kind;
+    ++cr.n;
+}
+__global__ void k_cond_reset(const unsigned int* __restrict__ changed, CondRegions cr) {
+    const unsigned int ch = *changed;
+    if (ch == 0u) return;
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long begin = 0ull;
+    for (int k = 0; k < cr.n; ++k) {
+        if (i < cr.end[k]) {
+            if (cr.kind[k] == 1 && ch == NB2_SCHED_INCREMENTAL) return;
+            if (cr.kind[k] == 2) {
+                if (ch == NB2_SCHED_REFINE || ch == NB2_SCHED_INCREMENTAL) return;
+                cr.p[k][i - begin] = 0xFFFFFFFFu;
+                return;
+            }
+            cr.p[k][i - begin] = 0u;
+            return;
+        }
+        begin = cr.end[k];
+    }
+}
+static void cond_launch(Context* ctx, const unsigned int* changed, const CondRegions& cr) {
+    const size_t total = (size_t)cr.end[cr.n - 1];
+    k_cond_reset<<<(unsigned int)((total + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(changed, cr);
+    ctx->launches++;
+}
 // the colour masks are kept on an incremental step
 __global__ void k_cond_zero_full(const unsigned int* __restrict__ changed, unsigned int* p, size_t nwords) {
     if (*changed == 0u || *changed == NB2_SCHED_INCREMENTAL) return;
@@ -826,20 +865,27 @@ __global__ void k_phase_hist(const unsigned int* __restrict__ changed, size_t n,
     if (*changed == 0u) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n && it_type[i] != NB2_ITEM_INVALID;
-    {  // rows actually scheduled (hdr->work), against the padded slot count: the solve launcher's "ragged" hint
-        const unsigned int rows = __reduce_add_sync(0xffffffffu, valid && !NB2_Z_IS_COMPACT(it_nrows[i] | (it_type[i] << 8)) ? (unsigned int)it_nrows[i] : 0u);
-        if ((threadIdx.x & 31) == 0 && rows) atomicAdd(&hdr->work, rows);
-    }
+    const int z = valid ? (it_nrows[i] | (it_type[i] << 8)) : 0;
+    const unsigned int rows_generic = valid && !NB2_Z_IS_COMPACT(z) ? (unsigned int)it_nrows[i] : 0u;
     // slots of a phase are handed out by row-count bucket (k_fill_ginfo), longest groups first: the 32 groups a
     // warp of the solve kernels owns then hold the same number of rows (up to one bucket edge per warp).
-    // A few dozen (phase, bucket) counters take every item's increment: counted per block in shared memory,
-    // one global atomic per block and counter (a schedule in levels has thousands of phases and goes direct).
+    // A few dozen (phase, bucket) counters, the per-phase row maxima and the header words would take every
+    // item's atomic: they are gathered per block in shared memory first (41 us -> a few us on 296k groups).
+    // A schedule in levels has thousands of phases, little contention per counter, and goes direct.
     __shared__ unsigned int s_cnt[NB2_SMEM_KEYS];
+    __shared__ unsigned int s_R[NB2_SMEM_KEYS / NB2_ROW_BUCKETS];
+    __shared__ unsigned int s_work, s_np;
     const unsigned int nkeys = max_phases * NB2_ROW_BUCKETS;
     const bool blockwise = nkeys <= NB2_SMEM_KEYS;
     if (blockwise) {
         for (unsigned int k = threadIdx.x; k < nkeys; k += blockDim.x) s_cnt[k] = 0u;
+        for (unsigned int k = threadIdx.x; k < max_phases; k += blockDim.x) s_R[k] = 0u;
+        if (threadIdx.x == 0) s_work = s_np = 0u;
         __syncthreads();
+    }
+    {  // rows actually scheduled (hdr->work), against the padded slot count
+        const unsigned int rows = __reduce_add_sync(0xffffffffu, rows_generic);
+        if ((threadIdx.x & 31) == 0 && rows) atomicAdd(blockwise ? &s_work : &hdr->work, rows);
     }
     if (valid) {
         unsigned int p = (unsigned int)phase[i];
@@ -848,16 +894,27 @@ __global__ void k_phase_hist(const unsigned int* __restrict__ changed, size_t n,
             atomicOr(&hdr->overflow, 2u);
         }
         const unsigned int key = p * NB2_ROW_BUCKETS + row_bucket(it_nrows[i]);
-        if (blockwise) atomicAdd(&s_cnt[key], 1u);
-        else atomicAdd(&ph_bcnt[key], 1u);
-        // generic row slots: joints and reference-order groups; compact contact groups reserve none
-        atomicMax(&ph_R[p], NB2_Z_IS_COMPACT(it_nrows[i] | (it_type[i] << 8)) ? 0u : (unsigned int)it_nrows[i]);
-        atomicMax(&hdr->n_phases, p + 1);
+        // generic row slots (ph_R): joints and reference-order groups; compact contact groups reserve none
+        if (blockwise) {
+            atomicAdd(&s_cnt[key], 1u);
+            atomicMax(&s_R[p], rows_generic);
+            atomicMax(&s_np, p + 1);
+        } else {
+            atomicAdd(&ph_bcnt[key], 1u);
+            atomicMax(&ph_R[p], rows_generic);
+            atomicMax(&hdr->n_phases, p + 1);
+        }
     }
     if (blockwise) {
         __syncthreads();
         for (unsigned int k = threadIdx.x; k < nkeys; k += blockDim.x)
             if (s_cnt[k]) atomicAdd(&ph_bcnt[k], s_cnt[k]);
+        for (unsigned int k = threadIdx.x; k < max_phases; k += blockDim.x)
+            if (s_R[k]) atomicMax(&ph_R[k], s_R[k]);
+        if (threadIdx.x == 0) {
+            if (s_work) atomicAdd(&hdr->work, s_work);
+            if (s_np) atomicMax(&hdr->n_phases, s_np);
+        }
     }
 }
 __global__ void k_phase_scan(const unsigned int* __restrict__ changed, unsigned int* ph_count, unsigned int* ph_bcnt,
@@ -976,11 +1033,13 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     } else {
         s->cache_valid = false;
     }
-    k_cond_zero<<<1, 32, 0, ctx->stream>>>(changed, (unsigned int*)s->hdr.p, offsetof(SchedHeader, refine_left) / 4);
-    k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_count.p, s->max_phases + 1);
-    k_cond_zero<<<nblk(s->max_phases + 1), TPB, 0, ctx->stream>>>(changed, s->ph_R.p, s->max_phases + 1);
-    k_cond_zero<<<nblk(4 * (s->max_phases + 1)), TPB, 0, ctx->stream>>>(changed, s->ph_bcnt.p, 4 * (s->max_phases + 1));
-    ctx->launches += 4;
+    CondRegions cr;
+    cr.n = 0;
+    cond_add(cr, s->hdr.p, offsetof(SchedHeader, refine_left) / 4, 0);
+    cond_add(cr, s->ph_count.p, s->max_phases + 1, 0);
+    cond_add(cr, s->ph_R.p, s->max_phases + 1, 0);
+    cond_add(cr, s->ph_bcnt.p, 4 * (s->max_phases + 1), 0);
+    if (n == 0 || mode == NB2_MODE_REFERENCE_ORDER) cond_launch(ctx, changed, cr);
     if (n == 0) {
         k_phase_scan<<<1, 1, 0, ctx->stream>>>(changed, s->ph_count.p, s->ph_bcnt.p, s->ph_R.p, s->ph_gbase.p, s->ph_rbase.p, s->hdr.p);
         ctx->launches++;
@@ -1028,13 +1087,12 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
     } else {
         NB2_TRY(ctx->cmask.reserve(ctx, (size_t)nb * NB2_MASK_WORDS + 1));
         NB2_TRY(ctx->best.reserve(ctx, (size_t)nb + 1));
-        k_cond_zero_full<<<nblk((size_t)nb * NB2_MASK_WORDS * 2), TPB, 0, ctx->stream>>>(
-            changed, (unsigned int*)ctx->cmask.p, (size_t)nb * NB2_MASK_WORDS * 2);
-        k_cond_zero<<<nblk((size_t)nb * 2), TPB, 0, ctx->stream>>>(changed, (unsigned int*)ctx->best.p, (size_t)nb * 2);
-        k_cond_fill_int<<<nblk(n), TPB, 0, ctx->stream>>>(changed, s->it_phase.p, n, -1);
         NB2_TRY(ctx->bal.reserve(ctx, NB2_MAX_COLOURS));
-        k_cond_zero<<<nblk(NB2_MAX_COLOURS), TPB, 0, ctx->stream>>>(changed, ctx->bal.p, NB2_MAX_COLOURS);
-        ctx->launches += 4;
+        cond_add(cr, ctx->cmask.p, (size_t)nb * NB2_MASK_WORDS * 2, 1);
+        cond_add(cr, ctx->best.p, (size_t)nb * 2, 0);
+        cond_add(cr, s->it_phase.p, n, 2);
+        cond_add(cr, ctx->bal.p, NB2_MAX_COLOURS, 0);
+        cond_launch(ctx, changed, cr);
         NB2_TRY(coop_blocks(ctx, k_colour, &ctx->coop_blocks_colour));
         int blocks = (int)min((size_t)ctx->coop_blocks_colour, (n + TPB - 1) / TPB);
         size_t n_ = n;
