@@ -225,8 +225,8 @@ __device__ __forceinline__ int joint_num_position(const nb2_joint& j) {
 // rpc = velocity rows per contact: 3 (normal + two friction rows) or 1 (frictionless SignoriniModel)
 __global__ void k_build_items(int mode, int compact, int rpc, int position, unsigned int nJ, unsigned int maxc,
                               const nb2_joint* __restrict__ joints, const nb2_manifold* __restrict__ manifolds,
-                              const unsigned int* __restrict__ chunk_base, unsigned int nM,
-                              const unsigned int* __restrict__ chunk_manifold, const int* __restrict__ status,
+                              unsigned int* chunk_base, unsigned int nM, unsigned int* chunk_manifold,
+                              unsigned int* c_manifold, int producer, const int* __restrict__ status,
                               int* it_a, int* it_b, int* it_nrows, int* it_type, int* it_src,
                               unsigned long long* it_key, int* it_b1, int* it_b2, size_t n_items) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,15 +254,26 @@ __global__ void k_build_items(int mode, int compact, int rpc, int position, unsi
             k -= maxc;
             second = 1;
         }
-        unsigned int total = chunk_base[nM];
+        // The device producer's manifolds own exactly one chunk and four contact slots each (narrowphase.cu):
+        // chunk k IS manifold k, and the chunk bookkeeping (a memset, k_chunk_counts, three scan kernels and
+        // k_fill_chunks for uploaded manifolds) is written right here.
+        unsigned int total = producer ? nM : chunk_base[nM];
         if (k < total) {
-            unsigned int m = chunk_manifold[k];
+            unsigned int m = producer ? (unsigned int)k : chunk_manifold[k];
             const nb2_manifold& mf = manifolds[m];
+            if (producer && !second && !position) {
+                chunk_base[m] = m;
+                if (m == 0) chunk_base[nM] = nM;
+                chunk_manifold[m] = m;
+                const unsigned int nc = mf.num_contacts;
+                *reinterpret_cast<uint4*>(c_manifold + 4u * m) =
+                    make_uint4(nc > 0 ? m : 0xFFFFFFFFu, nc > 1 ? m : 0xFFFFFFFFu, nc > 2 ? m : 0xFFFFFFFFu, nc > 3 ? m : 0xFFFFFFFFu);
+            }
             b1 = mf.body1;
             b2 = mf.body2;
             a = dyn_or_neg(status, mf.body1);
             b = dyn_or_neg(status, mf.body2);
-            const int local = (int)(k - chunk_base[m]);
+            const int local = producer ? 0 : (int)(k - chunk_base[m]);
             const int ncc = min(NB2_CHUNK, (int)mf.num_contacts - NB2_CHUNK * local);
             if ((a >= 0 || b >= 0) && ncc > 0) {
                 src = (int)k;
@@ -335,15 +346,18 @@ int launch_build_items(Context* ctx, int mode) {
     NB2_TRY(ctx->chunk_manifold.reserve(ctx, maxc + 1));
     NB2_TRY(ctx->c_manifold.reserve(ctx, ctx->n_contacts + 1));
     NB2_TRY(ctx->deg.reserve(ctx, (size_t)nM + 1));  // reused as scan input
+    // the producer's layout (one chunk, four contact slots per manifold) is booked by k_build_items itself
+    const bool producer = ctx->manifolds_from_producer && nM > 0 && ctx->n_contacts == 4u * nM && maxc == (size_t)nM;
     // contacts not owned by a (valid) manifold stay unmapped and are skipped by assembly
-    NB2_CUDA(ctx, cudaMemsetAsync(ctx->c_manifold.p, 0xFF, ((size_t)ctx->n_contacts + 1) * sizeof(unsigned int),
-                                  ctx->stream));
-    if (nM) {
+    if (!producer)
+        NB2_CUDA(ctx, cudaMemsetAsync(ctx->c_manifold.p, 0xFF, ((size_t)ctx->n_contacts + 1) * sizeof(unsigned int),
+                                      ctx->stream));
+    if (nM && !producer) {
         k_chunk_counts<<<nblk(nM), TPB, 0, ctx->stream>>>(ctx->manifolds.p, nM, ctx->deg.p, ctx->manifolds_from_producer ? 1u : 0u);
         ctx->launches++;
     }
-    NB2_TRY(exclusive_scan_u32(ctx, ctx->deg.p, ctx->chunk_base.p, nM));
-    if (nM) {
+    if (!producer) NB2_TRY(exclusive_scan_u32(ctx, ctx->deg.p, ctx->chunk_base.p, nM));
+    if (nM && !producer) {
         k_fill_chunks<<<nblk(nM), TPB, 0, ctx->stream>>>(ctx->manifolds.p, nM, ctx->chunk_base.p,
                                                          ctx->chunk_manifold.p, ctx->c_manifold.p,
                                                          (unsigned int)maxc, ctx->flags.p);
@@ -355,7 +369,7 @@ int launch_build_items(Context* ctx, int mode) {
     if (n_items) {
         k_build_items<<<nblk(n_items), TPB, 0, ctx->stream>>>(
             mode, ctx->step_layout, ctx->contact_model == 1 ? 1 : 3, 0, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
-            ctx->chunk_manifold.p, ctx->b_status.p, ctx->vs.it_a.p, ctx->vs.it_b.p, ctx->vs.it_nrows.p,
+            ctx->chunk_manifold.p, ctx->c_manifold.p, producer ? 1 : 0, ctx->b_status.p, ctx->vs.it_a.p, ctx->vs.it_b.p, ctx->vs.it_nrows.p,
             ctx->vs.it_type.p, ctx->vs.it_src.p, ctx->vs.it_key.p, ctx->vs.it_b1.p, ctx->vs.it_b2.p, n_items);
         ctx->launches++;
     }
@@ -365,7 +379,7 @@ int launch_build_items(Context* ctx, int mode) {
         if (np) {
             k_build_items<<<nblk(np), TPB, 0, ctx->stream>>>(
                 mode, ctx->step_layout, ctx->contact_model == 1 ? 1 : 3, 1, nJ, (unsigned int)maxc, ctx->joints.p, ctx->manifolds.p, ctx->chunk_base.p, nM,
-                ctx->chunk_manifold.p, ctx->b_status.p, ctx->ps.it_a.p, ctx->ps.it_b.p, ctx->ps.it_nrows.p,
+                ctx->chunk_manifold.p, ctx->c_manifold.p, producer ? 1 : 0, ctx->b_status.p, ctx->ps.it_a.p, ctx->ps.it_b.p, ctx->ps.it_nrows.p,
                 ctx->ps.it_type.p, ctx->ps.it_src.p, ctx->ps.it_key.p, ctx->ps.it_b1.p, ctx->ps.it_b2.p, np);
             ctx->launches++;
         }
