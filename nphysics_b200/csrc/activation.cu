@@ -242,7 +242,7 @@ int launch_update_activation(Context* ctx, float mix, const int32_t* to_activate
 static int launch_islands(Context* ctx, int dynamic_only) {
     const unsigned int nb = ctx->n_bodies;
     {
-        NB2_TRY(ctx->barrier.reserve(ctx, 8));
+        NB2_TRY(ctx->barrier.reserve(ctx, NB2_BARRIER_WORDS));
         NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
         int& blocks_cc = ctx->coop_blocks_islands;
         if (blocks_cc <= 0) {

@@ -92,6 +92,7 @@ static int check_flags(Context* ctx) {
 static int do_step_ccd(Context* ctx, int mode) {
     ctx->step_layout = (mode != NB2_MODE_REFERENCE_ORDER && ctx->contact_layout == 1 && ctx->contact_model == 0) ? 1 : 0;
     ctx->cur = 1 - ctx->cur;  // assembly warm-starts from the buffer "before cur": point it at the last one written
+    NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p + NB2_BARRIER_VELOCITY, 0, 16 * sizeof(unsigned int), ctx->stream));
     NB2_TRY(launch_refresh_dynamics(ctx));
     NB2_TRY(mb_launch_refresh(ctx));  // multibodies: kinematics, dynamics, accelerations; their links' body records follow
     // chunks (groups of <= 4 contacts): at most one per manifold plus one per four contacts; the device producer's
@@ -121,6 +122,8 @@ static int do_step(Context* ctx, int mode) {
         ctx->ev.created = true;
     }
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[0], ctx->stream));
+    // the grid-barrier counters of the velocity and the position kernel (their own regions: one memset per step)
+    NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p + NB2_BARRIER_VELOCITY, 0, 16 * sizeof(unsigned int), ctx->stream));
     // ---- dynamics refresh + assembly (Counters: "assembly")
     NB2_TRY(launch_refresh_dynamics(ctx));
     NB2_TRY(mb_launch_refresh(ctx));  // multibodies: kinematics, dynamics, accelerations; their links' body records follow
@@ -157,7 +160,7 @@ static int do_step(Context* ctx, int mode) {
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[9], ctx->stream));
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[4], ctx->stream));
     // ---- kinematic bodies (mechanical_world.rs:328-332)
-    NB2_TRY(launch_integrate(ctx, true));
+    if (ctx->n_kinematic) NB2_TRY(launch_integrate(ctx, true));
     if (tm) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[5], ctx->stream));
     ctx->ev_valid = tm;
     ctx->last_mode = mode;
@@ -306,7 +309,7 @@ int nb2_create(int device, void* stream, nb2_context** out) {
         ctx->own_stream = true;
     }
     int rc = ctx->flags.reserve(ctx, 4);
-    if (rc == NB2_OK) rc = ctx->barrier.reserve(ctx, 8);
+    if (rc == NB2_OK) rc = ctx->barrier.reserve(ctx, NB2_BARRIER_WORDS);
     if (rc == NB2_OK && cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(unsigned int), ctx->stream) != cudaSuccess)
         rc = NB2_ERR_CUDA;
     if (rc != NB2_OK) {
@@ -386,13 +389,15 @@ int nb2_upload_bodies(nb2_context* h, const nb2_body* bodies, uint32_t n) {
     NB2_TRY(ctx->true_status.reserve(ctx, n));
     if (n != ctx->n_bodies) ctx->sleeping = false;  // activation records of another body set
     ctx->n_bodies = n;
-    uint32_t nd = 0;
+    uint32_t nd = 0, nk = 0;
     bool any_mask = false;
     for (uint32_t i = 0; i < n; ++i) {
         nd += bodies[i].status == NB2_BODY_DYNAMIC ? 1u : 0u;
+        nk += bodies[i].status == NB2_BODY_KINEMATIC ? 1u : 0u;
         for (int k = 0; k < 6; ++k) any_mask |= bodies[i].jacobian_mask[k] != 1.0f;
     }
     ctx->n_dynamic = nd;
+    ctx->n_kinematic = nk;
     ctx->any_mask = any_mask;
     NB2_CUDA(ctx, cudaMemcpyAsync(ctx->raw.p, bodies, (size_t)n * sizeof(nb2_body), cudaMemcpyHostToDevice, ctx->stream));
     NB2_TRY(launch_unpack_bodies(ctx));

@@ -482,7 +482,8 @@ int launch_assemble(Context* ctx, int mode) {
             ctx->launches--;  // counted below
         }
         ctx->launches++;
-        if (cache.ht_cap) {  // all three return at once unless a contact missed the fast path
+        // the producer's contacts are looked up inside their own pair (cache_chunk_path) and never ask for the table
+        if (cache.ht_cap && !cache.chunk_local_ids) {  // all three return at once unless a contact missed the fast path
             const unsigned int few = (unsigned int)ctx->sm_count * 16;  // grid-stride: the common case is an immediate return
             k_hash_clear<<<min(nblk(cache.ht_cap), few), TPB, 0, ctx->stream>>>(need_hash, ctx->ht_keys[prev].p, cache.ht_cap);
             k_hash_build<<<min(nblk(cache.n_prev), few), TPB, 0, ctx->stream>>>(need_hash, cache.ckey_prev, cache.imp_prev, cache.n_prev,

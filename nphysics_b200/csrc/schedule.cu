@@ -1060,7 +1060,7 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
         NB2_CUDA(ctx, cudaGetLastError());
         return NB2_OK;
     }
-    NB2_TRY(ctx->barrier.reserve(ctx, 8));
+    NB2_TRY(ctx->barrier.reserve(ctx, NB2_BARRIER_WORDS));
     NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
     unsigned int* flags = ctx->barrier.p + 4;
     if (mode == NB2_MODE_REFERENCE_ORDER) {

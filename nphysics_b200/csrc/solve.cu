@@ -384,11 +384,10 @@ int launch_velocity_solve(Context* ctx, int mode) {
         ctx->launches++;
     }
     NB2_TRY(coop_limit(ctx, k_velocity_solve, &ctx->coop_blocks_vel));
-    NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
     float4* lam = ctx->lam.p;
     int iters = (int)ctx->params.max_velocity_iterations;
     int warm = ref ? 0 : 1;
-    unsigned int* bar = ctx->barrier.p;
+    unsigned int* bar = ctx->barrier.p + NB2_BARRIER_VELOCITY;  // zeroed once per step (api.cu)
     size_t want = (ctx->vs.n_items + TPB - 1) / TPB;
     int blocks = (int)(want < (size_t)ctx->coop_blocks_vel ? want : (size_t)ctx->coop_blocks_vel);
     if (blocks < 1) blocks = 1;
@@ -431,14 +430,13 @@ int launch_position_solve(Context* ctx, int mode) {
     P.max_lin = ctx->params.max_linear_correction;
     P.max_ang = ctx->params.max_angular_correction;
     NB2_TRY(coop_limit(ctx, k_position_solve, &ctx->coop_blocks_pos));
-    NB2_CUDA(ctx, cudaMemsetAsync(ctx->barrier.p, 0, 8 * sizeof(unsigned int), ctx->stream));
     const nb2_joint* joints = ctx->joints.p;
     const nb2_manifold* manifolds = ctx->manifolds.p;
     const unsigned int* cm = ctx->chunk_manifold.p;
     const float4* prow = ctx->p_row.p;
     size_t pstride = ctx->n_pslots_max;
     int iters = (int)ctx->params.max_position_iterations;
-    unsigned int* bar = ctx->barrier.p;
+    unsigned int* bar = ctx->barrier.p + NB2_BARRIER_POSITION;
     size_t want = (s.n_items + TPB - 1) / TPB;
     int blocks = (int)(want < (size_t)ctx->coop_blocks_pos ? want : (size_t)ctx->coop_blocks_pos);
     if (blocks < 1) blocks = 1;

@@ -774,7 +774,7 @@ int launch_velocity_solve_lockstep(Context* ctx, const SchedDev& sd_in, const Ro
     }
     float4* lam = ctx->lam.p;
     int iters = (int)ctx->params.max_velocity_iterations;
-    unsigned int* bar = ctx->barrier.p;
+    unsigned int* bar = ctx->barrier.p + NB2_BARRIER_VELOCITY;
     void* args[] = {&sd, &R, &lam, &iters, &bar};
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(tpb), args, smem, ctx->stream));
@@ -811,7 +811,7 @@ int launch_velocity_solve_bulk(Context* ctx, const SchedDev& sd_in, const Rows& 
     }
     float4* lam = ctx->lam.p;
     int iters = (int)ctx->params.max_velocity_iterations;
-    unsigned int* bar = ctx->barrier.p;
+    unsigned int* bar = ctx->barrier.p + NB2_BARRIER_VELOCITY;
     void* args[] = {&sd, &R, &lam, &iters, &bar};
     if (ctx->timers) NB2_CUDA(ctx, cudaEventRecord(ctx->ev.e[6], ctx->stream));
     NB2_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(tpb), args, smem, ctx->stream));
@@ -885,7 +885,7 @@ int launch_velocity_solve_staged(Context* ctx, const SchedDev& sd_in, const Rows
     }
     float4* lam = ctx->lam.p;
     int iters = (int)ctx->params.max_velocity_iterations;
-    unsigned int* bar = ctx->barrier.p;
+    unsigned int* bar = ctx->barrier.p + NB2_BARRIER_VELOCITY;
     static const int trace = (getenv("NB2_TRACE_PHASES") ? atoi(getenv("NB2_TRACE_PHASES")) : 0) |
                              (getenv("NB2_NO_EVICT_FIRST") ? 0x40000000 : 0);
     int tr = trace;
@@ -1137,7 +1137,7 @@ int launch_position_solve_staged(Context* ctx, const SchedDev& sd_in, const PosA
     const float4* prow = ctx->p_row.p;
     size_t pstride = ctx->n_pslots_max;
     int iters = (int)ctx->params.max_position_iterations;
-    unsigned int* bar = ctx->barrier.p;
+    unsigned int* bar = ctx->barrier.p + NB2_BARRIER_POSITION;
     size_t smem = smem_of(E);
     int early = ctx->pos_early_exit ? 1 : 0;
     void* args[] = {&sd, &A, &joints, &phdr, &gstride, &prow, &pstride, &P, &iters, &E, &rows_div, &bar, &early};
@@ -1163,7 +1163,7 @@ int launch_velocity_solve_coloured(Context* ctx, const SchedDev& sd_in, const Ro
     CompactArrays CA = CA_in;
     NB2_TRY(coop_limit_c(ctx, k_velocity_solve_coloured, &ctx->coop_blocks_col));
     int iters = (int)ctx->params.max_velocity_iterations;
-    unsigned int* bar = ctx->barrier.p;
+    unsigned int* bar = ctx->barrier.p + NB2_BARRIER_VELOCITY;
     size_t want = (ctx->vs.n_items + SOLVE_TPB - 1) / SOLVE_TPB;
     int blocks = (int)(want < (size_t)ctx->coop_blocks_col ? want : (size_t)ctx->coop_blocks_col);
     if (blocks < 1) blocks = 1;

@@ -195,6 +195,7 @@ struct Context {
     // ---- bodies
     uint32_t n_bodies = 0;
     uint32_t n_dynamic = 0;
+    unsigned int n_kinematic = 0;  // KINEMATIC bodies of the uploaded set (none: the end-of-step pass is not launched)
     DevBuf<nb2_body> raw;         // static properties (pose/velocity fields are upload-time values)
     // live pose: (t.xyz, 0) and the rotation quaternion of a body are neighbours in ONE buffer, so a pose is one
     // 32-byte sector (the position solve gathers two poses per group visit and is bound by the sectors it pulls
@@ -310,6 +311,11 @@ NB2_D void stcg4(float4* p, float4 v) { __stcg(p, v); }
 
 // Software grid barrier for cooperatively launched kernels: a monotonically
 // increasing arrival counter (zeroed before the launch).
+// Regions of Context::barrier (words): the scheduling kernels' counter and flags, the velocity kernel's counter, the
+// position kernel's counter and sweep flags.  The step zeroes the last two with one memset (api.cu).
+#define NB2_BARRIER_WORDS 32
+#define NB2_BARRIER_VELOCITY 8
+#define NB2_BARRIER_POSITION 16
 struct GridBarrier {
     unsigned int* counter;
     unsigned int target;
