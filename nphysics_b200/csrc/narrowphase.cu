@@ -256,6 +256,10 @@ __device__ __forceinline__ float combine_coeff_dev(float a, unsigned int ma, flo
     return (a + b) * 0.5f;
 }
 
+// shared-memory stride of a pair's four contact records in quads: 28 used, 29 keeps a warp's 16-byte stores
+// (lanes 29 quads apart) off each other's banks
+#define GM_CQ 29
+static_assert(sizeof(nb2_manifold) % 4 == 0 && sizeof(nb2_contact) == 112, "producer staging copies whole words / 7 quads per contact");
 // One thread per persistent pair: the manifold of the pair at the current poses.  Manifold p owns the
 // contact slots [4 p, 4 p + 4); its kept contacts are compacted to the front of that range (corner order)
 // and num_contacts says how many there are -- possibly none, in which case the manifold emits no rows.
@@ -264,8 +268,14 @@ __global__ void __launch_bounds__(TPB) k_generate_manifolds(unsigned int n_pairs
                                                             ConstPoseQuads pos_t,
                                                             ConstPoseQuads pos_q, float prediction,
                                                             nb2_manifold* manifolds, nb2_contact* contacts) {
-    const unsigned int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
+    // Records are staged in shared memory and leave the block as two contiguous runs (the block's 4 x TPB contact
+    // slots, its TPB manifolds): written straight from the threads, every 16-byte store of a warp went to 32
+    // different sectors and the kernel sat in the store queue (lg_throttle 15 per issue, 107 us for 296k pairs).
+    extern __shared__ __align__(16) unsigned char gm_smem[];
+    float4* s_c = reinterpret_cast<float4*>(gm_smem);                                        // [TPB][GM_CQ]: 28 quads used
+    nb2_manifold* s_m = reinterpret_cast<nb2_manifold*>(gm_smem + (size_t)TPB * GM_CQ * 16);  // [TPB]
+    const unsigned int p0 = blockIdx.x * blockDim.x, p = p0 + threadIdx.x;
+    if (p < n_pairs) {
     const float4 ra = pairs.q[0 * pairs.cap + p], rb = pairs.q[1 * pairs.cap + p], fq = pairs.q[2 * pairs.cap + p];
     const int feat = pairs.feat[p];
     const int ax = feat & 3, u = (ax + 1) % 3, v = (ax + 2) % 3;
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(TPB) k_generate_manifolds(unsigned int n_pairs
     const float cu_a[4] = {ra.x, ra.y, ra.y, ra.x}, cv_a[4] = {ra.z, ra.z, ra.w, ra.w};
     const float cu_b[4] = {rb.x, rb.y, rb.y, rb.x}, cv_b[4] = {rb.z, rb.z, rb.w, rb.w};
     int kept = 0;
-    float4* cq = reinterpret_cast<float4*>(contacts + (size_t)4 * p);
+    float4* cq = s_c + (size_t)threadIdx.x * GM_CQ;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         float la_[3], lb_[3];
@@ -324,7 +334,7 @@ __global__ void __launch_bounds__(TPB) k_generate_manifolds(unsigned int n_pairs
 #pragma unroll
         for (int j = 0; j < 7; ++j) o[j] = z;
     }
-    nb2_manifold& m = manifolds[p];
+    nb2_manifold& m = s_m[threadIdx.x];
     const ColliderRec& c1 = flip ? cb : ca;
     const ColliderRec& c2 = flip ? ca : cb;
     m.body1 = c1.body;
@@ -340,6 +350,15 @@ __global__ void __launch_bounds__(TPB) k_generate_manifolds(unsigned int n_pairs
     m.coll1_wrt_body[3] = c1.r.i; m.coll1_wrt_body[4] = c1.r.j; m.coll1_wrt_body[5] = c1.r.k; m.coll1_wrt_body[6] = c1.r.w;
     m.coll2_wrt_body[0] = c2.t.x; m.coll2_wrt_body[1] = c2.t.y; m.coll2_wrt_body[2] = c2.t.z;
     m.coll2_wrt_body[3] = c2.r.i; m.coll2_wrt_body[4] = c2.r.j; m.coll2_wrt_body[5] = c2.r.k; m.coll2_wrt_body[6] = c2.r.w;
+    }
+    __syncthreads();
+    const unsigned int nv = min((unsigned int)TPB, n_pairs - p0);
+    float4* gc = reinterpret_cast<float4*>(contacts + (size_t)4 * p0);
+    for (unsigned int g = threadIdx.x; g < 28u * nv; g += TPB) gc[g] = s_c[(g / 28u) * GM_CQ + g % 28u];
+    unsigned int* gm = reinterpret_cast<unsigned int*>(manifolds + p0);
+    const unsigned int* sm = reinterpret_cast<const unsigned int*>(s_m);
+    const unsigned int mw = (unsigned int)(sizeof(nb2_manifold) / 4);
+    for (unsigned int g = threadIdx.x; g < mw * nv; g += TPB) gm[g] = sm[g];
 }
 
 // nb2_update_contacts: the ten floats of a TrackedContact that change from step to step
@@ -441,7 +460,12 @@ int launch_generate_manifolds(Context* ctx) {
         pairs.q = ctx->pair_q.p;
         pairs.feat = ctx->pair_feat.p;
         pairs.cap = ctx->pair_q.cap / 3;
-        k_generate_manifolds<<<nblk(np), TPB, 0, ctx->stream>>>(np, pairs, ctx->colliders.p, ctx->pos_t.p, ctx->pos_q.p,
+        const size_t smem = (size_t)TPB * GM_CQ * 16 + (size_t)TPB * sizeof(nb2_manifold);
+        if (!ctx->producer_attr) {
+            NB2_CUDA(ctx, cudaFuncSetAttribute(k_generate_manifolds, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->producer_attr = true;
+        }
+        k_generate_manifolds<<<nblk(np), TPB, smem, ctx->stream>>>(np, pairs, ctx->colliders.p, ctx->pos_t.p, ctx->pos_q.p,
                                                                 ctx->np_prediction, ctx->manifolds.p, ctx->contacts.p);
         ctx->launches++;
     }
