@@ -36,4 +36,20 @@ for layout in (0, 1):
         s.step(abi.MODE_COLOURED)
     print("layout", layout, int(s.get_stats()["n_phases_velocity"]))
     s.close()
+# device producer path: persistent pairs, manifolds re-produced every step (shared-memory staged records,
+# chunk bookkeeping inside k_build_items), both orders, a free-running scene whose contacts change
+sc = scenes.boxes3(5, 4, 5)
+for mode in (abi.MODE_COLOURED, abi.MODE_REFERENCE_ORDER):
+    s = Solver(0)
+    s.set_params(sc.params)
+    s.upload_bodies(sc.bodies)
+    s.upload_colliders(scenes.scene_colliders(sc))
+    print("pairs", s.detect_pairs(scenes.LINEAR_PREDICTION))
+    for k in range(12):
+        s.generate_manifolds()
+        s.step(mode)
+    st = s.get_stats()
+    print("producer", mode, int(st["n_phases_velocity"]), float(st["residual_max"]), int(st["non_finite"]))
+    s.download_manifolds(); s.download_body_states(); s.download_contact_impulses()
+    s.close()
 print("sanitizer script done")
