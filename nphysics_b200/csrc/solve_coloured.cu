@@ -592,6 +592,9 @@ __global__ void __launch_bounds__(384, 1) k_velocity_solve_bulk(SchedDev sd, Sta
 // Measured on 4096 x pyramid3 with 3 % of the manifolds ragged: 12.1 -> 16.2 ms.  Here the warp walks in
 // lockstep: every lane goes through max-over-the-warp rows per group (short groups commit empty copy groups
 // and are predicated off), so lane l always copies row r of group g0 + l: coalesced, whatever the row counts.
+// Since the layout hands the slots of a phase out by row count (schedule.cu, k_fill_ginfo) a warp's groups hold equal
+// row counts anyway and the free-running rings are faster again (live 100k pile 0.79 against 0.89 ms): this kernel is
+// kept as the A/B knob NB2_VELOCITY_KERNEL=4.
 // ------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(384, 1) k_velocity_solve_lockstep(SchedDev sd, StagedRows R, float4* lam, int iters,
