@@ -34,7 +34,7 @@ static void release_all(Context* c) {
     c->raw.release(); c->pos.release(); c->pos_t.p.p = c->pos_q.p.p = nullptr; c->vel.release(); c->com_im.release();
     c->inv_i.release(); c->ext.release(); c->lam.release(); c->b_status.release(); c->joints.release();
     c->manifolds.release(); c->contacts.release(); c->c_manifold.release(); c->chunk_base.release();
-    c->chunk_manifold.release();
+    c->chunk_manifold.release(); c->col_edge.release();
     for (int k = 0; k < 2; ++k) {
         c->imp[k].release();
         c->ckey[k].release();
@@ -294,6 +294,7 @@ int nb2_create(int device, void* stream, nb2_context** out) {
     if (const char* ps = getenv("NB2_POS_EARLY_EXIT")) ctx->pos_early_exit = atoi(ps) != 0;
     if (const char* rb = getenv("NB2_REF_BLOCKS")) ctx->ref_blocks = atoi(rb);
     if (const char* ic = getenv("NB2_INCREMENTAL_COLOURING")) ctx->incremental_colouring = atoi(ic) != 0;
+    if (const char* kc = getenv("NB2_KEMPE")) ctx->kempe = atoi(kc) != 0;
     if (cudaSetDevice(device) != cudaSuccess) {
         delete h;
         return set_error(nullptr, NB2_ERR_CUDA, "cudaSetDevice failed");

@@ -627,12 +627,95 @@ __global__ void k_cond_zero_full(const unsigned int* __restrict__ changed, unsig
     if (i < nwords) p[i] = 0u;
 }
 
+
+// ------------------------------------------------------------------ Kempe chains
+// First-fit + iterated greedy leave the pile with max body degree 6 at 8 colours whose last class holds a few
+// hundred groups (3718 after the fresh colouring, 280 after the refinement passes: tools/colour_classes.py).
+// Every colour costs each sweep of both solve kernels a grid barrier and a latency chain, so that class is
+// emptied by Kempe-chain interchanges (the constructive step of Vizing's / Konig's edge-colouring proofs): for a
+// group e = (u, v) of the last class pick a colour `a` free at u and `b` free at v; the path of groups coloured
+// a, b, a, ... that starts at v ends somewhere else than u (always, in a bipartite contact graph), swapping a and b
+// along it frees `a` at v as well, and e takes it.  Parallel version, Jones-Plassmann style: every candidate bids
+// for the bodies of its path, the winners of a round (disjoint paths) swap, the losers try again.
+#define NB2_KEMPE_K 16          // colours the per-body table holds (the stage is skipped beyond)
+#define NB2_KEMPE_MAX 8192u     // largest class the stage takes on
+#define NB2_KEMPE_ROUNDS 10
+#define NB2_KEMPE_LEN 96        // longest path followed
+struct KempePlan {
+    int kind;  // 0 nothing to do this round, 1 a colour free at both ends, 2 interchange along a path
+    int u, v, a, b, n;
+};
+__device__ __forceinline__ unsigned int kempe_free(const unsigned long long* cmask, int body, unsigned int L) {
+    const unsigned long long used = __ldcg(&cmask[(size_t)body * NB2_MASK_WORDS]);
+    return (unsigned int)(~used) & ((1u << L) - 1u);
+}
+__device__ __forceinline__ int kempe_nth_bit(unsigned int m, unsigned int k) {  // k-th (mod popcount) set bit of m != 0
+    k %= (unsigned int)__popc(m);
+    for (unsigned int j = 0; j < k; ++j) m &= m - 1u;
+    return __ffs((int)m) - 1;
+}
+// The plan of candidate e for round r.  Pure function of the tables as they stand after the last grid barrier, so
+// the bidding pass and the applying pass of a round compute the same plan.  Visits the path's bodies through `visit`.
+template <typename Visit>
+__device__ KempePlan kempe_plan(int e, unsigned int r, unsigned int L, const int* __restrict__ it_a,
+                                const int* __restrict__ it_b, const unsigned long long* cmask, const int* col_edge,
+                                Visit visit) {
+    KempePlan P;
+    P.kind = 0;
+    P.u = it_a[e];
+    P.v = it_b[e];
+    P.a = P.b = -1;
+    P.n = 0;
+    if (P.u < 0 || P.v < 0) {  // one dynamic body: any colour free there will do
+        const int x = P.u < 0 ? P.v : P.u;
+        if (x < 0) return P;
+        const unsigned int f = kempe_free(cmask, x, L);
+        if (!f) return P;
+        P.kind = 1;
+        P.a = __ffs((int)f) - 1;
+        visit(x);
+        return P;
+    }
+    const unsigned int fu = kempe_free(cmask, P.u, L), fv = kempe_free(cmask, P.v, L);
+    if (fu & fv) {
+        P.kind = 1;
+        P.a = __ffs((int)(fu & fv)) - 1;
+        visit(P.u);
+        visit(P.v);
+        return P;
+    }
+    if (!fu || !fv) return P;
+    const unsigned int h = hash_u32((unsigned int)e * 0x9E3779B9u + r);
+    P.a = kempe_nth_bit(fu, h + r);
+    P.b = kempe_nth_bit(fv, (h >> 8) + r / 2u);
+    int x = P.v, want = P.a, n = 0;
+    for (;;) {
+        const int f = __ldcg(&col_edge[(size_t)x * NB2_KEMPE_K + want]);
+        if (f < 0) break;
+        if (n >= NB2_KEMPE_LEN) return P;
+        const int fa = it_a[f], fb = it_b[f];
+        const int y = fa == x ? fb : fa;
+        ++n;
+        if (y < 0) break;          // a static side ends the path: nothing to keep proper there
+        if (y == P.u) return P;    // odd cycle through e: this pair of colours does not work
+        visit(y);
+        x = y;
+        want = want == P.a ? P.b : P.a;
+    }
+    if (n == 0) return P;  // cannot happen with exact tables
+    visit(P.u);
+    visit(P.v);
+    P.kind = 2;
+    P.n = n;
+    return P;
+}
 __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict__ it_a, const int* __restrict__ it_b,
                                                 const int* __restrict__ it_type, int* phase,
                                                 unsigned long long* cmask, unsigned long long* best,
                                                 unsigned int* flags /*3*/, SchedHeader* hdr, unsigned int* barrier,
                                                 const unsigned int* __restrict__ changed, unsigned int* bal,
-                                                int* tmp_phase, size_t nb, int ig_passes, int* raw_phase) {
+                                                int* tmp_phase, size_t nb, int ig_passes, int* raw_phase,
+                                                int* col_edge) {
     if (*changed == 0u) return;  // cached colouring still valid (uniform over the grid: no barrier was touched)
     GridBarrier gb;
     gb.init(barrier);
@@ -774,6 +857,158 @@ __global__ void __launch_bounds__(TPB) k_colour(size_t n, const int* __restrict_
         for (size_t i = tid; i < n; i += stride)
             if (it_type[i] != NB2_ITEM_INVALID) phase[i] = tmp_phase[i];
         gb.sync();
+    }
+    // ---- Kempe chains: empty the last colour class while it is small (see kempe_plan above)
+    // Refinement steps only (an unchanged conflict graph, like the iterated-greedy passes): on the 100k pile a
+    // fresh colouring leaves 3718 groups in the last class and the interchanges cost 0.45 ms, one step later the
+    // class holds a few hundred.
+    for (int sweep = 0; col_edge != nullptr && refine && sweep < 2; ++sweep) {
+        __shared__ unsigned int s_kC, s_kN, s_kD;
+        int* const max_degree = col_edge + nb * (size_t)NB2_KEMPE_K;  // one spare word behind the table
+        for (size_t i = tid; i < NB2_MAX_COLOURS; i += stride) bal[i] = 0u;
+        if (tid == 0) *max_degree = 0;
+        gb.sync();
+        for (size_t i = tid; i < n; i += stride)
+            if (it_type[i] != NB2_ITEM_INVALID) atomicAdd(&bal[min((unsigned int)phase[i], (unsigned int)NB2_MAX_COLOURS - 1u)], 1u);
+        {  // the largest number of groups on one body (= colours in its mask: the colouring is proper)
+            int d = 0;
+            for (size_t x = tid; x < nb; x += stride) {
+                int dx = 0;
+#pragma unroll
+                for (int w = 0; w < NB2_MASK_WORDS; ++w) dx += __popcll(__ldcg(&cmask[x * NB2_MASK_WORDS + w]));
+                d = max(d, dx);
+            }
+            d = __reduce_max_sync(0xffffffffu, d);
+            if ((threadIdx.x & 31) == 0 && d) atomicMax(max_degree, d);
+        }
+        gb.sync();
+        if (threadIdx.x == 0) {
+            unsigned int C = 0;
+            for (unsigned int c = 0; c < NB2_MAX_COLOURS; ++c)
+                if (__ldcg(&bal[c])) C = c + 1;
+            s_kC = C;
+            s_kN = C ? __ldcg(&bal[C - 1]) : 0u;
+            s_kD = (unsigned int)__ldcg(max_degree);
+        }
+        __syncthreads();
+        gb.sync();  // every block has read the counts before anybody moves on and clears them (a block that saw half-cleared counts would decide differently and the grid barrier would never fill)
+        const unsigned int C = s_kC, L = C - 1u;
+        // Down to Vizing's bound (largest body degree + 1) and no further: below it the interchanges have to lay
+        // alternating colours along the very stacks whose support has to travel through them within a sweep (the
+        // 50 x 200 wall went from 5 to 4 colours and its worst penetration at step 120 from 58 to 107 mm).
+        if (C < 3u || C > NB2_KEMPE_K || s_kN > NB2_KEMPE_MAX || C <= s_kD + 1u) break;  // uniform over the grid
+        // per body and colour: the group that holds the colour there; pending colour changes travel in tmp_phase
+        // (a group's colour is only ever read by its home thread)
+        for (size_t w = tid; w < nb * (size_t)NB2_KEMPE_K; w += stride) col_edge[w] = -1;
+        for (size_t i = tid; i < n; i += stride) tmp_phase[i] = -1;
+        gb.sync();
+        for (size_t i = tid; i < n; i += stride) {
+            if (it_type[i] == NB2_ITEM_INVALID) continue;
+            const int c = phase[i], a = it_a[i], b = it_b[i];
+            if (a >= 0) __stcg(&col_edge[(size_t)a * NB2_KEMPE_K + c], (int)i);
+            if (b >= 0) __stcg(&col_edge[(size_t)b * NB2_KEMPE_K + c], (int)i);
+        }
+        gb.sync();
+        bool emptied = false;
+        for (unsigned int r = 0; r < NB2_KEMPE_ROUNDS; ++r) {
+            const unsigned int round = 0x400u + (unsigned int)sweep * NB2_KEMPE_ROUNDS + r;  // above the colouring rounds, below the balancing ones
+            // bids
+            for (size_t i = tid; i < n; i += stride) {
+                if (it_type[i] == NB2_ITEM_INVALID || phase[i] != (int)L) continue;
+                const unsigned long long prio = ((unsigned long long)round << 52) |
+                                                ((unsigned long long)(hash_u32((unsigned int)i + round) & 0xFFFFFu) << 32) |
+                                                (unsigned long long)(unsigned int)i;
+                kempe_plan((int)i, r, L, it_a, it_b, cmask, col_edge, [&](int x) { atomicMax(&best[x], prio); });
+            }
+            gb.sync();
+            // winners: every body of the plan still carries the bid
+            for (size_t i = tid; i < n; i += stride) {
+                if (it_type[i] == NB2_ITEM_INVALID || phase[i] != (int)L) continue;
+                const unsigned long long prio = ((unsigned long long)round << 52) |
+                                                ((unsigned long long)(hash_u32((unsigned int)i + round) & 0xFFFFFu) << 32) |
+                                                (unsigned long long)(unsigned int)i;
+                bool mine = true;
+                const KempePlan P = kempe_plan((int)i, r, L, it_a, it_b, cmask, col_edge,
+                                               [&](int x) { mine = mine && __ldcg(&best[x]) == prio; });
+                if (P.kind == 0 || !mine) continue;
+                const unsigned long long bitL = 1ull << L, bitA = 1ull << P.a;
+                if (P.kind == 2) {
+                    const unsigned long long bitB = 1ull << P.b;
+                    // Along the path every body swaps its a-group and its b-group (the start has only an a-group,
+                    // the far end only one of the two, the bodies in between both): swap the two table entries and
+                    // the two mask bits of each body right after reading the group that leads on.
+                    auto swap_at = [&](int x) {
+                        int* ta = &col_edge[(size_t)x * NB2_KEMPE_K + P.a];
+                        int* tb = &col_edge[(size_t)x * NB2_KEMPE_K + P.b];
+                        const int fa_ = __ldcg(ta), fb_ = __ldcg(tb);
+                        __stcg(ta, fb_);
+                        __stcg(tb, fa_);
+                        const unsigned long long m = __ldcg(&cmask[(size_t)x * NB2_MASK_WORDS]);
+                        const unsigned long long sw = (m & ~(bitA | bitB)) | ((m & bitA) ? bitB : 0ull) | ((m & bitB) ? bitA : 0ull);
+                        __stcg(&cmask[(size_t)x * NB2_MASK_WORDS], sw);
+                    };
+                    int x = P.v, want = P.a;
+                    for (int k = 0; k < P.n; ++k) {
+                        const int f = __ldcg(&col_edge[(size_t)x * NB2_KEMPE_K + want]);
+                        const int fa = it_a[f], fb = it_b[f];
+                        const int y = fa == x ? fb : fa;
+                        __stcg(&tmp_phase[f], want == P.a ? P.b : P.a);  // picked up by the group's home thread
+                        swap_at(x);
+                        x = y;
+                        want = want == P.a ? P.b : P.a;
+                    }
+                    if (x >= 0) swap_at(x);  // the far end (a static side has no table)
+                    const unsigned long long mv = __ldcg(&cmask[(size_t)P.v * NB2_MASK_WORDS]);
+                    __stcg(&cmask[(size_t)P.v * NB2_MASK_WORDS], (mv | bitA) & ~bitL);
+                    const unsigned long long mu = __ldcg(&cmask[(size_t)P.u * NB2_MASK_WORDS]);
+                    __stcg(&cmask[(size_t)P.u * NB2_MASK_WORDS], (mu | bitA) & ~bitL);
+                    __stcg(&col_edge[(size_t)P.u * NB2_KEMPE_K + P.a], (int)i);
+                    __stcg(&col_edge[(size_t)P.v * NB2_KEMPE_K + P.a], (int)i);
+                    __stcg(&col_edge[(size_t)P.u * NB2_KEMPE_K + L], -1);
+                    __stcg(&col_edge[(size_t)P.v * NB2_KEMPE_K + L], -1);
+                } else {
+                    if (P.u >= 0) {
+                        const unsigned long long m = __ldcg(&cmask[(size_t)P.u * NB2_MASK_WORDS]);
+                        __stcg(&cmask[(size_t)P.u * NB2_MASK_WORDS], (m | bitA) & ~bitL);
+                        __stcg(&col_edge[(size_t)P.u * NB2_KEMPE_K + P.a], (int)i);
+                        __stcg(&col_edge[(size_t)P.u * NB2_KEMPE_K + L], -1);
+                    }
+                    if (P.v >= 0) {
+                        const unsigned long long m = __ldcg(&cmask[(size_t)P.v * NB2_MASK_WORDS]);
+                        __stcg(&cmask[(size_t)P.v * NB2_MASK_WORDS], (m | bitA) & ~bitL);
+                        __stcg(&col_edge[(size_t)P.v * NB2_KEMPE_K + P.a], (int)i);
+                        __stcg(&col_edge[(size_t)P.v * NB2_KEMPE_K + L], -1);
+                    }
+                }
+                __stcg(&tmp_phase[i], P.a);
+            }
+            gb.sync();
+            // home threads pick their groups' new colours up; is anything left in the class?
+            unsigned int left = 0;
+            for (size_t i = tid; i < n; i += stride) {
+                if (it_type[i] == NB2_ITEM_INVALID) continue;
+                const int c = __ldcg(&tmp_phase[i]);
+                if (c >= 0) {
+                    phase[i] = c;
+                    tmp_phase[i] = -1;
+                }
+                left |= (unsigned int)(phase[i] == (int)L);
+            }
+            const unsigned int fi = (unsigned int)sweep * NB2_KEMPE_ROUNDS + r;
+            if (__syncthreads_or(left) && threadIdx.x == 0) atomicOr(&flags[fi % 3], 1u);
+            gb.sync();
+            const unsigned int any = *((volatile unsigned int*)&flags[fi % 3]);
+            if (tid == 0) flags[(fi + 2) % 3] = 0;
+            if (!any) {
+                emptied = true;
+                break;
+            }
+        }
+        // leave the flag words clean for whoever uses them next
+        gb.sync();
+        if (tid == 0) flags[0] = flags[1] = flags[2] = 0;
+        gb.sync();
+        if (!emptied) break;  // uniform: every block read the same flag
     }
     for (size_t i = tid; i < n; i += stride)
         if (it_type[i] != NB2_ITEM_INVALID) raw_phase[i] = phase[i];
@@ -1125,7 +1360,12 @@ int launch_schedule(Context* ctx, Sched* s, int mode) {
         int igp = NB2_IG_PASSES;
         NB2_TRY(s->it_phase_raw.reserve(ctx, n));
         int* raw = s->it_phase_raw.p;
-        void* args[] = {&n_, &ia, &ib, &ty, &ph, &cm, &be, &flags, &hd, &bar, &ch, &bl, &tmp, &nb_, &igp, &raw};
+        int* col_edge = nullptr;  // Kempe chains (NB2_KEMPE=0 switches the stage off)
+        if (ctx->kempe) {
+            NB2_TRY(ctx->col_edge.reserve(ctx, (size_t)nb * NB2_KEMPE_K + 1));
+            col_edge = ctx->col_edge.p;
+        }
+        void* args[] = {&n_, &ia, &ib, &ty, &ph, &cm, &be, &flags, &hd, &bar, &ch, &bl, &tmp, &nb_, &igp, &raw, &col_edge};
         NB2_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_colour, dim3(blocks), dim3(TPB), args, 0, ctx->stream));
         ctx->launches++;
     }

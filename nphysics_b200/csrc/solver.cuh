@@ -300,6 +300,8 @@ struct Context {
     DevBuf<unsigned int> bal;       // groups per colour while balancing
     bool pos_early_exit = true;     // NB2_POS_EARLY_EXIT=0: always run every position iteration (the exactness test)
     int ref_blocks = 0;             // NB2_REF_BLOCKS: cap on the blocks of the reference-order solve kernels (0 = automatic)
+    bool kempe = true;              // NB2_KEMPE: Kempe-chain stage of the colouring (schedule.cu)
+    DevBuf<int> col_edge;           // its per-body, per-colour group table
     bool producer_attr = false;     // k_generate_manifolds: dynamic shared memory size set
     void* mb = nullptr;             // MbState (multibody.cu): reduced-coordinate multibodies, SURVEY 8 f3
 };
