@@ -104,6 +104,39 @@ def assert_conflict_free(solver, tag):
     return ncol
 
 
+def test_kempe_interchanges_reach_vizing_bound_and_stay_conflict_free(monkeypatch):
+    """A pile's bodies carry at most 6 groups; first-fit + iterated greedy colour it with 8 colours, the Kempe-chain
+    stage of the refinement steps (schedule.cu) empties the last class: 7 = largest body degree + 1, and the
+    schedule stays proper.  NB2_KEMPE=0 keeps the colouring as it was."""
+    sc = scenes.boxes3(24, 20, 24)
+    rest = np.zeros(len(sc.bodies), dtype=abi.body_state_dtype)
+    rest["position"] = sc.bodies["position"]
+    rest["velocity"] = sc.bodies["velocity"]
+    ncols = {}
+    for kempe in ("0", "1"):
+        monkeypatch.setenv("NB2_KEMPE", kempe)  # read at nb2_create
+        s = new_solver()
+        s.set_params(params_10_5())
+        s.upload_bodies(sc.bodies)
+        s.upload_colliders(scenes.scene_colliders(sc))
+        assert s.detect_pairs(scenes.LINEAR_PREDICTION) > 0
+        s.generate_manifolds()
+        for _ in range(4):  # a fresh colouring, then refinement steps on the unchanged conflict graph
+            s.step(COL)
+            s.upload_body_states(rest)
+        ncols[kempe] = assert_conflict_free(s, "pile 24x20x24, NB2_KEMPE=" + kempe)
+        phase, a, b = s.download_schedule()
+        ok = phase >= 0
+        degree = np.bincount(np.concatenate([a[ok & (a >= 0)], b[ok & (b >= 0)]])).max()
+        st = s.get_stats()
+        assert int(st["non_finite"]) == 0
+        s.close()
+        assert degree == 6
+    print("colours without / with the Kempe stage:", ncols)
+    assert ncols["1"] == 7
+    assert ncols["0"] >= ncols["1"]
+
+
 # ------------------------------------------------------------------ config 2: the 100k-box pile
 def test_config2_full_size_reference_order_lockstep():
     """BASELINE config 2 at full size: two reference-order steps of the 50x40x50 pile, each compared with
