@@ -20,6 +20,11 @@ same work every step, on both arms).  Metric: solver body-steps/s = dynamic bodi
           step, coloured mode against the oracle's sequential order: residual, penetration, energy.
   sharded BASELINE configs[4]: 4096 pyramid3 worlds split over the N ranks by island
           (sharding.make_shards on the device's island labels), stats over NCCL -- strong scaling.
+  uncached_ms_per_step  the timed steps again with a from-scratch colouring every step.
+  live_simulation  the pile free-running with its contacts re-produced on the device every step (the schedule
+          is edited in place), timed after 20 untimed free-running steps.
+  multibody  SURVEY 8 f3: ragdolls of examples3d/ragdoll3.rs in reduced coordinates standing on the ground,
+          split over the N ranks, with the oracle's rate on one host thread beside it.
 
 With N > 1 `value` is N independent 100k piles, one per GPU (a single pile is ONE island: it does not
 shard; "replicas", weak scaling, no data-path collective).
