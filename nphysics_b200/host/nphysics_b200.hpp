@@ -496,6 +496,85 @@ class DefaultJointConstraintSet {  // joint_constraint.rs:58-206
 };
 
 // ---------------------------------------------------------------------------------------------
+// Colliders and the geometrical world (src/object/collider.rs:457-560 ColliderDesc, src/object/collider_set.rs,
+// src/world/geometrical_world.rs).  Collision detection is ncollide's in the reference; what runs here is the
+// device manifold producer of SURVEY 8 f2 -- cuboid colliders, face-face contacts -- so that
+// `mechanical_world.step(&mut geometrical_world, &mut bodies, &mut colliders, &mut joint_constraints, ...)`
+// (mechanical_world.rs:182-188) has a counterpart with the same shape.  Other shapes: produce the manifolds with
+// ncollide and call the overload of MechanicalWorld::step that takes them.
+struct BasicMaterial {  // basic_material.rs:14-43 (defaults :46-50: restitution 0, friction 0.5, Average)
+    float restitution = 0.f, friction = 0.5f;
+    uint8_t restitution_combine_mode = 0, friction_combine_mode = 0;  // 0 Average, 1 Min, 2 Multiply, 3 Max
+};
+class Collider {
+    friend class ColliderDesc;
+    friend class DefaultColliderSet;
+    friend class MoreauJeanSolver;
+    nb2_collider rec_;
+    float linear_prediction_ = 0.001f;  // collider.rs:457-479
+
+  public:
+    Collider() { std::memset(&rec_, 0, sizeof(rec_)); rec_.rotation_wrt_body[3] = 1.f; }
+    DefaultBodyHandle body() const { return (DefaultBodyHandle)rec_.body; }
+    float margin() const { return rec_.margin; }
+    Vector3 half_extents() const { return {rec_.half_extents[0], rec_.half_extents[1], rec_.half_extents[2]}; }
+};
+class ColliderDesc {
+    Collider c_;
+
+  public:
+    /// ColliderDesc::new(ShapeHandle::new(Cuboid::new(half_extents)))
+    explicit ColliderDesc(const Vector3& cuboid_half_extents) {
+        for (int k = 0; k < 3; ++k) c_.rec_.half_extents[k] = cuboid_half_extents[k];
+        c_.rec_.margin = 0.01f;  // collider.rs:457-479
+        const BasicMaterial m;
+        material(m);
+    }
+    ColliderDesc& margin(float m) { c_.rec_.margin = m; return *this; }
+    ColliderDesc& linear_prediction(float p) { c_.linear_prediction_ = p; return *this; }
+    ColliderDesc& translation(const Vector3& t) {  // position of the collider in its body part's frame
+        for (int k = 0; k < 3; ++k) c_.rec_.translation_wrt_body[k] = t[k];
+        return *this;
+    }
+    ColliderDesc& material(const BasicMaterial& m) {
+        c_.rec_.friction = m.friction;
+        c_.rec_.restitution = m.restitution;
+        c_.rec_.friction_mode = m.friction_combine_mode;
+        c_.rec_.restitution_mode = m.restitution_combine_mode;
+        return *this;
+    }
+    /// ColliderDesc::build(BodyPartHandle): link i of a multibody is BodyPartHandle{handle + i, 0}
+    Collider build(const BodyPartHandle& part) const {
+        Collider c = c_;
+        c.rec_.body = (int32_t)(part.body + part.part);
+        return c;
+    }
+};
+using DefaultColliderHandle = size_t;
+class DefaultColliderSet {
+    std::vector<Collider> colliders_;
+    bool dirty_ = true;
+    friend class MoreauJeanSolver;
+
+  public:
+    DefaultColliderHandle insert(const Collider& c) {
+        colliders_.push_back(c);
+        dirty_ = true;
+        return colliders_.size() - 1;
+    }
+    size_t len() const { return colliders_.size(); }
+    const Collider* get(DefaultColliderHandle h) const { return h < colliders_.size() ? &colliders_[h] : nullptr; }
+};
+/// geometrical_world.rs: the broad phase (here: the persistent pairs of nb2_detect_pairs, found again every
+/// `broad_phase_interval` steps from the poses of that moment) and the narrow phase (nb2_generate_manifolds, every step).
+struct GeometricalWorld {
+    uint32_t broad_phase_interval = 1;
+    float search_radius = -1.f;  // < 0: derived from the largest dynamic collider
+    uint32_t n_pairs = 0;        // pairs of the last broad phase
+    uint64_t steps_ = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
 // The contact input (collider_contact_manifold.rs:9-24): one manifold and its tracked contacts.
 struct ColliderContactManifold {
     nb2_manifold manifold;
@@ -586,6 +665,54 @@ class MoreauJeanSolver {
     void step(Counters& counters, DefaultBodySet& bodies, DefaultJointConstraintSet& joints,
               const std::vector<ColliderContactManifold>& manifolds, const IntegrationParameters& parameters,
               ActivationManager* activation = nullptr) {
+        upload_sets(counters, bodies, joints, parameters, activation);
+        manifold_stage_.clear();
+        contact_stage_.clear();
+        for (const ColliderContactManifold& m : manifolds) {
+            nb2_manifold rec = m.manifold;
+            rec.first_contact = (uint32_t)contact_stage_.size();
+            rec.num_contacts = (uint32_t)m.contacts.size();
+            manifold_stage_.push_back(rec);
+            contact_stage_.insert(contact_stage_.end(), m.contacts.begin(), m.contacts.end());
+        }
+        check(nb2_upload_manifolds(ctx_, manifold_stage_.data(), (uint32_t)manifold_stage_.size(), contact_stage_.data(),
+                                   (uint32_t)contact_stage_.size()));
+        run_and_download(counters, bodies, joints, activation);
+        counters.nconstraints = 3 * contact_stage_.size();  // set_nconstraints (:74-76), contact rows
+    }
+    /// The same step with the contacts produced on the device from the collider set (cuboids):
+    /// the collision-detection half of MechanicalWorld::step (mechanical_world.rs:241-262) included.
+    void step(Counters& counters, GeometricalWorld& gworld, DefaultBodySet& bodies, DefaultColliderSet& colliders,
+              DefaultJointConstraintSet& joints, const IntegrationParameters& parameters,
+              ActivationManager* activation = nullptr) {
+        const bool new_bodies = upload_sets(counters, bodies, joints, parameters, activation);
+        bool broad_phase = gworld.broad_phase_interval <= 1 || gworld.steps_ % gworld.broad_phase_interval == 0;
+        if (new_bodies || colliders.dirty_) {  // a new body set drops the colliders on the device
+            collider_stage_.resize(colliders.colliders_.size());
+            prediction_ = 0.f;
+            for (size_t i = 0; i < collider_stage_.size(); ++i) {
+                collider_stage_[i] = colliders.colliders_[i].rec_;
+                prediction_ = std::fmax(prediction_, colliders.colliders_[i].linear_prediction_);
+            }
+            check(nb2_upload_colliders(ctx_, collider_stage_.data(), (uint32_t)collider_stage_.size()));
+            colliders.dirty_ = false;
+            broad_phase = true;
+        }
+        if (broad_phase) check(nb2_detect_pairs(ctx_, prediction_, gworld.search_radius, 0u, &gworld.n_pairs));
+        ++gworld.steps_;
+        check(nb2_generate_manifolds(ctx_));
+        run_and_download(counters, bodies, joints, activation);
+        counters.nconstraints = 12 * (size_t)gworld.n_pairs;  // an upper bound (<= 4 contacts x 3 rows per pair); stats() has the count
+    }
+
+  private:
+    std::vector<nb2_collider> collider_stage_;
+    float prediction_ = 0.001f;
+    /// bodies, multibodies, joints, parameters: whatever changed on the host since the last step.  True when the
+    /// body set went up again (the device then holds no joints, colliders or pairs of the old set).
+    bool upload_sets(Counters& counters, DefaultBodySet& bodies, DefaultJointConstraintSet& joints,
+                     const IntegrationParameters& parameters, ActivationManager* activation) {
+        bool new_bodies = false;
         nb2_params p = parameters.to_abi(gravity);
         check(nb2_set_params(ctx_, &p));
         check(nb2_enable_timers(ctx_, counters.enabled ? 1 : 0));
@@ -618,6 +745,7 @@ class MoreauJeanSolver {
             check(nb2_upload_multibodies(ctx_, mb_stage_.data(), (uint32_t)mb_stage_.size(), link_stage_.data(), (uint32_t)link_stage_.size()));
             bodies.dirty_ = false;
             joints.dirty_ = true;  // a new body set drops the joints on device
+            new_bodies = true;
         }
         if (joints.dirty_) {
             joint_stage_.resize(joints.joints_.size());
@@ -625,17 +753,11 @@ class MoreauJeanSolver {
             check(nb2_upload_joints(ctx_, joint_stage_.data(), (uint32_t)joint_stage_.size()));
             joints.dirty_ = false;
         }
-        manifold_stage_.clear();
-        contact_stage_.clear();
-        for (const ColliderContactManifold& m : manifolds) {
-            nb2_manifold rec = m.manifold;
-            rec.first_contact = (uint32_t)contact_stage_.size();
-            rec.num_contacts = (uint32_t)m.contacts.size();
-            manifold_stage_.push_back(rec);
-            contact_stage_.insert(contact_stage_.end(), m.contacts.begin(), m.contacts.end());
-        }
-        check(nb2_upload_manifolds(ctx_, manifold_stage_.data(), (uint32_t)manifold_stage_.size(), contact_stage_.data(),
-                                   (uint32_t)contact_stage_.size()));
+        return new_bodies;
+    }
+    /// activation update, the step, and the outputs written in place into the bodies / joints, like the reference
+    void run_and_download(Counters& counters, DefaultBodySet& bodies, DefaultJointConstraintSet& joints,
+                          ActivationManager* activation) {
         if (activation) {  // ActivationManager::update sits between the narrow phase and the solver (mechanical_world.rs:265-272)
             check(nb2_update_activation(ctx_, activation->mix_factor, activation->to_activate.data(),
                                         (uint32_t)activation->to_activate.size()));
@@ -678,8 +800,9 @@ class MoreauJeanSolver {
             counters.position_resolution_time = t[3];
             counters.solver_time = t[4];
         }
-        counters.nconstraints = 3 * contact_stage_.size();  // set_nconstraints (:74-76), contact rows
     }
+
+  public:
     nb2_stats stats() {
         nb2_stats s;
         check(nb2_get_stats(ctx_, &s));
@@ -704,6 +827,13 @@ class MechanicalWorld {
     void step(DefaultBodySet& bodies, DefaultJointConstraintSet& joints, const std::vector<ColliderContactManifold>& manifolds) {
         solver.gravity = gravity;
         solver.step(counters, bodies, joints, manifolds, integration_parameters, &activation_manager);
+    }
+    /// mechanical_world.rs:182-188: `step(&mut geometrical_world, &mut bodies, &mut colliders, &mut joint_constraints, ..)`
+    /// with the collision detection on the device (cuboid colliders).
+    void step(GeometricalWorld& geometrical_world, DefaultBodySet& bodies, DefaultColliderSet& colliders,
+              DefaultJointConstraintSet& joints) {
+        solver.gravity = gravity;
+        solver.step(counters, geometrical_world, bodies, colliders, joints, integration_parameters, &activation_manager);
     }
 };
 

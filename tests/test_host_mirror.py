@@ -21,7 +21,7 @@ def build_example(name="example_pyramid3"):
 
 
 def test_host_mirror_compiles_and_links():
-    for name in ("example_pyramid3", "example_ragdoll3"):
+    for name in ("example_pyramid3", "example_ragdoll3", "example_ragdoll3_colliders"):
         assert os.path.exists(build_example(name))
 
 
@@ -53,3 +53,15 @@ def test_ragdoll3_example_runs():
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "27 multibodies (162 links)" in r.stdout
+
+
+@pytest.mark.gpu
+def test_ragdoll3_with_colliders_example_runs():
+    """The reference's main loop shape -- `mechanical_world.step(geometrical_world, bodies, colliders, joints)` -- over
+    the C++ mirror: ground collider + one cuboid collider per link in a DefaultColliderSet, contacts produced on the
+    device every step.  The program checks joint drift, that nothing falls through the ground, finiteness."""
+    exe = build_example("example_ragdoll3_colliders")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "8 multibodies (48 links, 49 colliders" in r.stdout
