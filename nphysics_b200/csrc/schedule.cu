@@ -479,17 +479,6 @@ __device__ __forceinline__ unsigned int hash_u32(unsigned int x) {
 // graph is unchanged but a refinement pass is still due, 3 a few groups changed: edit the colouring in place.
 #define NB2_SCHED_REFINE 2u
 #define NB2_SCHED_INCREMENTAL 3u
-// Conditional helpers of the schedule cache: no-ops while the conflict graph is unchanged.
-__global__ void k_cond_zero(const unsigned int* __restrict__ changed, unsigned int* p, size_t nwords) {
-    if (*changed == 0u) return;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nwords) p[i] = 0u;
-}
-__global__ void k_cond_fill_int(const unsigned int* __restrict__ changed, int* p, size_t n, int v) {
-    if (*changed == 0u || *changed == NB2_SCHED_REFINE || *changed == NB2_SCHED_INCREMENTAL) return;  // those start from the colours they have
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
 // Compares this step's groups with the previous step's (when comparable): counts the groups whose conflict
 // signature -- (dynamic body pair, row count, type, body pair) -- differs.
 __global__ void k_compare_snapshot(size_t n, const int* __restrict__ it_a, const int* __restrict__ it_b,
@@ -619,12 +608,6 @@ static void cond_launch(Context* ctx, const unsigned int* changed, const CondReg
     const size_t total = (size_t)cr.end[cr.n - 1];
     k_cond_reset<<<(unsigned int)((total + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(changed, cr);
     ctx->launches++;
-}
-// the colour masks are kept on an incremental step
-__global__ void k_cond_zero_full(const unsigned int* __restrict__ changed, unsigned int* p, size_t nwords) {
-    if (*changed == 0u || *changed == NB2_SCHED_INCREMENTAL) return;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nwords) p[i] = 0u;
 }
 
 
